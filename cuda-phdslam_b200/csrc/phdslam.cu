@@ -1,0 +1,817 @@
+/*
+ * phdslam.cu -- C-ABI of libphdslam.so (see include/phdslam.h): persistent device state and the
+ * launch sequence of the filter step.  One handle = one GPU = one host thread (one rank).
+ *
+ * Reference call sequence being replaced: run_synth loop body (src/main.cpp:1231-1297) ->
+ * phdPredict (src/phdfilter.cu:1080) -> phdUpdateSynth (:3336) -> recoverSlamState (main.cpp:318)
+ * -> resampleParticles (main.cpp:453).  The reference keeps all state on the host and pays
+ * >= 20 cudaMalloc + >= 12 cudaMemcpy per step; here nothing but the M measurements goes up and
+ * a 100-byte estimate comes down.
+ */
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "phdslam_internal.h"
+
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e__ = (call);                                                                        \
+    if (e__ != cudaSuccess) {                                                                        \
+      phdslam_set_error(std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + \
+                        std::to_string(__LINE__) + ")");                                             \
+      return PHDSLAM_ERR_CUDA;                                                                       \
+    }                                                                                                \
+  } while (0)
+
+#define LAUNCH_CHECK(h)            \
+  do {                             \
+    (h)->launches++;               \
+    CK(cudaGetLastError());        \
+  } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+static float float_floor_d(double d) {
+  float f = (float)d;
+  if ((double)f > d) f = nextafterf(f, -INFINITY);
+  return f;
+}
+static float float_ceil_d(double d) {
+  float f = (float)d;
+  if ((double)f < d) f = nextafterf(f, INFINITY);
+  return f;
+}
+
+/* host evaluation of the canonical log (phd_detmath.h is __host__ __device__) */
+static void derive_devcfg(const phdslam_config_t& c, int Cmax, DevCfg* d) {
+  memset(d, 0, sizeof(*d));
+  d->min_range = c.min_range; d->max_range = c.max_range; d->max_bearing = c.max_bearing;
+  d->lo2 = float_ceil_d(0.8 * (double)c.min_range);
+  d->hi2 = float_floor_d(1.2 * (double)c.max_range);
+  d->hb2 = float_floor_d(1.2 * (double)c.max_bearing);
+  d->var_r = c.std_range * c.std_range;
+  d->var_b = c.std_bearing * c.std_bearing;
+  float sr = c.std_range * c.birth_noise_factor, sb = c.std_bearing * c.birth_noise_factor;
+  d->bvar_r = sr * sr;
+  d->bvar_b = sb * sb;
+  d->pd = c.pd;
+  d->log_pd = phd_safe_log(c.pd);
+  d->clutter_density = c.clutter_density;
+  d->clutter_rate = c.clutter_rate;
+  d->log_clutter_rate = phd_safe_log(c.clutter_rate);
+  d->birth_weight = c.birth_weight;
+  d->log_birth_weight = phd_safe_log(c.birth_weight);
+  d->min_sep = c.min_separation;
+  d->min_w = c.min_feature_weight;
+  d->distance_metric = c.distance_metric;
+  d->particle_weighting = c.particle_weighting;
+  d->labeled = c.labeled_measurements;
+  d->filter_type = c.filter_type;
+  d->motion_type = c.motion_type;
+  d->dt_sub = c.dt / (float)c.subdivide_predict;
+  d->l = c.l; d->h = c.h; d->a = c.a; d->b = c.b;
+  d->std_alpha = c.std_alpha; d->std_enc = c.std_encoder;
+  d->ax3 = 3.0f * c.ax; d->ay3 = 3.0f * c.ay; d->ayaw3 = 3.0f * c.ayaw;
+  d->seed_lo = (uint32_t)c.seed; d->seed_hi = (uint32_t)(c.seed >> 32);
+  d->Cmax = Cmax;
+  d->n_card = (c.filter_type == 1) ? c.max_cardinality + 1 : 0;
+}
+
+static int validate_config(const phdslam_config_t* c) {
+  if (c->n_particles < 1 || c->max_components < 1) {
+    phdslam_set_error("n_particles and max_components must be >= 1");
+    return PHDSLAM_ERR_INVALID;
+  }
+  if (c->feature_model != 0) {
+    phdslam_set_error("feature_model != 0 (dynamic / mixed features) is outside the hot path");
+    return PHDSLAM_ERR_INVALID;
+  }
+  if (c->n_predict_particles != 1) {
+    phdslam_set_error("n_predict_particles != 1 is not built yet");
+    return PHDSLAM_ERR_INVALID;
+  }
+  if (c->filter_type == 1) {
+    phdslam_set_error("filter_type = 1 (CPHD) is not built yet");
+    return PHDSLAM_ERR_INVALID;
+  }
+  if (c->subdivide_predict < 1) return PHDSLAM_ERR_INVALID;
+  return 0;
+}
+
+static void free_state(phdslam* h) {
+  for (int b = 0; b < 2; ++b) {
+    cudaFree(h->pose[b]); cudaFree(h->count[b]); cudaFree(h->map[b]); cudaFree(h->card[b]);
+  }
+  cudaFree(h->logw); cudaFree(h->resample_idx);
+  cudaFree(h->snap_pose); cudaFree(h->snap_count); cudaFree(h->snap_map); cudaFree(h->snap_card); cudaFree(h->snap_logw);
+  cudaFree(h->cls); cudaFree(h->n_in); cudaFree(h->dlogw); cudaFree(h->tpad); cudaFree(h->toff); cudaFree(h->scan_tmp);
+  cudaFree(h->dense); cudaFree(h->z_dev); cudaFree(h->draws_dev); cudaFree(h->q_fx); cudaFree(h->cdf_excl);
+  cudaFree(h->ancestors); cudaFree(h->red);
+  if (h->red_host) cudaFreeHost(h->red_host);
+}
+
+static int alloc_state(phdslam* h) {
+  const size_t n = (size_t)h->n_local;
+  const size_t C = (size_t)h->Cmax;
+  for (int b = 0; b < 2; ++b) {
+    CK(cudaMalloc(&h->pose[b], 6 * n * sizeof(float)));
+    CK(cudaMalloc(&h->count[b], n * sizeof(int)));
+    CK(cudaMalloc(&h->map[b], n * PHD_MAP_PLANES * C * sizeof(float)));
+    if (h->n_card) CK(cudaMalloc(&h->card[b], n * h->n_card * sizeof(float)));
+  }
+  CK(cudaMalloc(&h->logw, n * sizeof(float)));
+  CK(cudaMalloc(&h->resample_idx, n * sizeof(int)));
+  CK(cudaMalloc(&h->cls, n * C));
+  CK(cudaMalloc(&h->n_in, n * sizeof(int)));
+  CK(cudaMalloc(&h->dlogw, n * sizeof(float)));
+  CK(cudaMalloc(&h->tpad, n * sizeof(unsigned long long)));
+  CK(cudaMalloc(&h->toff, (n + 1) * sizeof(unsigned long long)));
+  CK(cudaMalloc(&h->scan_tmp, (size_t)(cdiv(n, SCAN_TILE) + 1) * sizeof(unsigned long long)));
+  CK(cudaMalloc(&h->z_dev, 3 * PHD_MAX_MEAS * sizeof(float)));
+  CK(cudaMalloc(&h->q_fx, n * sizeof(unsigned long long)));
+  CK(cudaMalloc(&h->cdf_excl, (n + 1) * sizeof(unsigned long long)));
+  CK(cudaMalloc(&h->ancestors, n * sizeof(int)));
+  CK(cudaMalloc(&h->red, sizeof(Reductions)));
+  CK(cudaMallocHost(&h->red_host, sizeof(Reductions)));
+  return 0;
+}
+
+static int init_particles(phdslam* h) {
+  /* run_synth initialisation, src/main.cpp:1129-1144 */
+  const int n = h->n_local;
+  const phdslam_config_t& c = h->cfg;
+  const float init[6] = {c.x0, c.y0, c.yaw0, c.vx0, c.vy0, c.vyaw0};
+  for (int k = 0; k < 6; ++k) {
+    fill_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->pose[h->cur] + (size_t)k * n, n, init[k]);
+    LAUNCH_CHECK(h);
+  }
+  fill_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->logw, n, -phd_logf((float)h->n_global));
+  LAUNCH_CHECK(h);
+  CK(cudaMemsetAsync(h->count[0], 0, (size_t)n * sizeof(int), h->stream));
+  CK(cudaMemsetAsync(h->count[1], 0, (size_t)n * sizeof(int), h->stream));
+  iota_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->resample_idx, n, h->offset);
+  LAUNCH_CHECK(h);
+  if (h->n_card) {
+    fill_kernel<<<cdiv((long long)n * h->n_card, 256), 256, 0, h->stream>>>(h->card[h->cur], n * h->n_card,
+                                                                            -phd_logf((float)h->n_card));
+    LAUNCH_CHECK(h);
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int phdslam_create(const phdslam_config_t* cfg, int device, phdslam_t** out) {
+  if (!cfg || !out) return PHDSLAM_ERR_INVALID;
+  int rc = validate_config(cfg);
+  if (rc) return rc;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    phdslam_set_error("no CUDA device: libphdslam has no CPU fallback");
+    return PHDSLAM_ERR_CUDA;
+  }
+  CK(cudaSetDevice(device));
+  phdslam* h = new phdslam();
+  memset(h, 0, sizeof(*h));
+  h->cfg = *cfg;
+  h->device = device;
+  h->rank = 0; h->world = 1;
+  h->n_global = cfg->n_particles; h->n_local = cfg->n_particles; h->offset = 0;
+  h->Cmax = (cfg->max_components + 31) & ~31;
+  h->n_card = (cfg->filter_type == 1) ? cfg->max_cardinality + 1 : 0;
+  int smax = 256;
+  while (smax < 4 * h->Cmax && smax < 4096) smax <<= 1;
+  h->Smax = smax;
+  derive_devcfg(h->cfg, h->Cmax, &h->dc);
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 12; ++i) CK(cudaEventCreate(&h->ev[i]));
+  rc = alloc_state(h);
+  if (rc) { free_state(h); delete h; return rc; }
+  CK(cudaFuncSetAttribute(update_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(h->Cmax)));
+  CK(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem_bytes(h->Smax)));
+  rc = init_particles(h);
+  if (rc) { free_state(h); delete h; return rc; }
+  *out = h;
+  return 0;
+}
+
+extern "C" void phdslam_destroy(phdslam_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  free_state(h);
+  for (int i = 0; i < 12; ++i) cudaEventDestroy(h->ev[i]);
+  cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" int phdslam_set_config(phdslam_t* h, const phdslam_config_t* cfg) {
+  if (cfg->n_particles != h->cfg.n_particles || ((cfg->max_components + 31) & ~31) != h->Cmax ||
+      cfg->filter_type != h->cfg.filter_type) {
+    phdslam_set_error("n_particles / max_components / filter_type are fixed at create time");
+    return PHDSLAM_ERR_INVALID;
+  }
+  int rc = validate_config(cfg);
+  if (rc) return rc;
+  h->cfg = *cfg;
+  derive_devcfg(h->cfg, h->Cmax, &h->dc);
+  return 0;
+}
+extern "C" int phdslam_get_config(const phdslam_t* h, phdslam_config_t* cfg) { *cfg = h->cfg; return 0; }
+extern "C" int phdslam_n_local(const phdslam_t* h) { return h->n_local; }
+extern "C" int phdslam_local_offset(const phdslam_t* h) { return h->offset; }
+extern "C" void* phdslam_stream(phdslam_t* h) { return (void*)h->stream; }
+extern "C" int phdslam_synchronize(phdslam_t* h) { CK(cudaStreamSynchronize(h->stream)); return 0; }
+
+extern "C" int phdslam_dist_unique_id(void* id128) {
+  (void)id128;
+  phdslam_set_error("multi-GPU sharding is not built yet");
+  return PHDSLAM_ERR_NCCL;
+}
+extern "C" int phdslam_dist_init(phdslam_t* h, int rank, int world, const void* id) {
+  (void)id;
+  if (world == 1 && rank == 0) return 0;
+  (void)h;
+  phdslam_set_error("multi-GPU sharding is not built yet");
+  return PHDSLAM_ERR_NCCL;
+}
+
+/* ---- exclusive scan helper ---- */
+static int scan_u64(phdslam* h, const unsigned long long* in, int n, unsigned long long* out /* n+1 */,
+                    unsigned long long* grand_dev) {
+  int tiles = cdiv(n, SCAN_TILE);
+  scan_tile_sums_kernel<<<tiles, SCAN_THREADS, 0, h->stream>>>(in, n, h->scan_tmp);
+  LAUNCH_CHECK(h);
+  scan_tile_offsets_kernel<<<1, SCAN_THREADS, 0, h->stream>>>(h->scan_tmp, tiles, grand_dev);
+  LAUNCH_CHECK(h);
+  scan_apply_kernel<<<tiles, SCAN_THREADS, 0, h->stream>>>(in, n, h->scan_tmp, out);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+static int check_err_flag(phdslam* h) {
+  /* red_host was filled by a preceding async copy + sync */
+  if (h->red_host->err_flag & 1) {
+    phdslam_set_error("merge candidate buffer overflow: raise max_components (candidates after prune exceeded 4*max_components)");
+    return PHDSLAM_ERR_CAPACITY;
+  }
+  if (h->red_host->err_flag & 2) {
+    phdslam_set_error("a particle's map exceeded max_components");
+    return PHDSLAM_ERR_CAPACITY;
+  }
+  return 0;
+}
+
+/* ---- predict ---- */
+extern "C" int phdslam_predict(phdslam_t* h, const float* control, const double* draws) {
+  CK(cudaSetDevice(h->device));
+  const int n = h->n_local;
+  const int per = (h->cfg.motion_type == 1) ? 2 : 3;
+  const double* ddev = nullptr;
+  if (draws) {
+    size_t need = (size_t)n * per;
+    if (h->draws_cap < need) {
+      cudaFree(h->draws_dev);
+      CK(cudaMalloc(&h->draws_dev, need * sizeof(double)));
+      h->draws_cap = need;
+    }
+    CK(cudaMemcpyAsync(h->draws_dev, draws, need * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    ddev = h->draws_dev;
+  }
+  float v_enc = control ? control[0] : 0.0f, alpha = control ? control[1] : 0.0f;
+  CK(cudaEventRecord(h->ev[0], h->stream));
+  predict_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->pose[h->cur], n, h->offset, v_enc, alpha, ddev, h->predict_calls, h->dc);
+  LAUNCH_CHECK(h);
+  CK(cudaEventRecord(h->ev[1], h->stream));
+  h->predict_calls++;
+  if (draws) CK(cudaStreamSynchronize(h->stream)); /* the caller may free `draws` on return */
+  return 0;
+}
+
+/* ---- update ---- */
+static int upload_measurements(phdslam* h, const float* z, int M, int fields) {
+  std::vector<float> zz(3 * PHD_MAX_MEAS, 0.0f);
+  for (int m = 0; m < M; ++m) {
+    zz[m] = z[(size_t)m * fields];
+    zz[PHD_MAX_MEAS + m] = z[(size_t)m * fields + 1];
+    zz[2 * PHD_MAX_MEAS + m] = (fields > 2) ? z[(size_t)m * fields + 2] : 0.0f;
+  }
+  CK(cudaMemcpyAsync(h->z_dev, zz.data(), zz.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream)); /* zz is a stack-lifetime staging buffer (768 floats) */
+  return 0;
+}
+
+/* classification + dense-offset scan; leaves total/max padded term counts in red_host */
+static int classify_and_scan(phdslam* h, int M) {
+  const int n = h->n_local;
+  CK(cudaMemsetAsync(h->red, 0, sizeof(Reductions), h->stream));
+  classify_kernel<<<cdiv(n, 8), 256, 0, h->stream>>>(h->map[h->cur], h->count[h->cur], h->pose[h->cur], n, M, h->cls,
+                                                     h->n_in, h->tpad, h->red, h->dc);
+  LAUNCH_CHECK(h);
+  int rc = scan_u64(h, h->tpad, n, h->toff, &h->red->total_terms);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->red_host, h->red, sizeof(Reductions), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+static int ensure_dense(phdslam* h, size_t floats) {
+  if (h->dense_floats >= floats) return 0;
+  cudaFree(h->dense);
+  h->dense = nullptr;
+  h->dense_floats = 0;
+  CK(cudaMalloc(&h->dense, floats * sizeof(float)));
+  h->dense_floats = floats;
+  return 0;
+}
+
+/* Particles stream through the dense buffer in batches [p0, p1) whose padded term total fits the budget. */
+static int plan_batches(phdslam* h, std::vector<int>& bounds, size_t* max_batch_terms) {
+  const int n = h->n_local;
+  const unsigned long long total = h->red_host->total_terms;
+  const unsigned long long budget_terms = std::max<unsigned long long>(h->cfg.update_buffer_bytes / (PHD_NPLANES * 4), 1);
+  bounds.clear();
+  bounds.push_back(0);
+  if (total <= budget_terms) {
+    bounds.push_back(n);
+    *max_batch_terms = (size_t)total;
+    return 0;
+  }
+  const unsigned long long maxT = std::max(h->red_host->max_terms, 1);
+  if (maxT > budget_terms) {
+    phdslam_set_error("update_buffer_bytes is smaller than one particle's update terms");
+    return PHDSLAM_ERR_INVALID;
+  }
+  int per = (int)std::max<unsigned long long>(budget_terms / maxT, 1);
+  for (int p = per; p < n; p += per) bounds.push_back(p);
+  bounds.push_back(n);
+  *max_batch_terms = (size_t)per * maxT;
+  return 0;
+}
+
+static int launch_update_batch(phdslam* h, int M, int p0, int p1, unsigned long long tbase) {
+  UpdArgs a;
+  a.map = h->map[h->cur]; a.count = h->count[h->cur]; a.cls = h->cls; a.pose = h->pose[h->cur];
+  a.z = h->z_dev; a.M = M; a.n = h->n_local; a.p0 = p0;
+  a.toff = h->toff; a.tbase = tbase; a.dense = h->dense; a.n_in = h->n_in; a.dlogw = h->dlogw; a.c = h->dc;
+  update_dense_kernel<<<p1 - p0, UPD_THREADS, update_smem_bytes(h->Cmax), h->stream>>>(a);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+static int launch_merge_batch(phdslam* h, int M, int p0, int p1, unsigned long long tbase) {
+  MrgArgs a;
+  a.dense = h->dense; a.toff = h->toff; a.tbase = tbase; a.n_in = h->n_in; a.M = M; a.n = h->n_local; a.p0 = p0;
+  a.map_in = h->map[h->cur]; a.count_in = h->count[h->cur]; a.cls = h->cls;
+  a.map_out = h->map[h->cur ^ 1]; a.count_out = h->count[h->cur ^ 1];
+  a.red = h->red; a.Smax = h->Smax; a.c = h->dc;
+  merge_kernel<<<p1 - p0, MRG_THREADS, merge_smem_bytes(h->Smax), h->stream>>>(a);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+/* w += dw; normalise (src/phdfilter.cu:3735-3755) */
+static int update_weights(phdslam* h, bool add) {
+  const int n = h->n_local;
+  CK(cudaMemsetAsync(h->red, 0, sizeof(Reductions), h->stream));
+  weights_add_max_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->logw, add ? h->dlogw : nullptr, n, h->red);
+  LAUNCH_CHECK(h);
+  weights_sum_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->logw, n, h->red);
+  LAUNCH_CHECK(h);
+  weights_normalise_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->logw, n, h->red);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+extern "C" int phdslam_update(phdslam_t* h, const float* z, int M, int fields) {
+  CK(cudaSetDevice(h->device));
+  if (M <= 0) return 0;                 /* main.cpp:1258 */
+  if (fields != 2 && fields != 3) return PHDSLAM_ERR_INVALID;
+  if (M > PHD_MAX_MEAS) M = PHD_MAX_MEAS; /* :3390-3394 */
+  int rc = upload_measurements(h, z, M, fields);
+  if (rc) return rc;
+  CK(cudaEventRecord(h->ev[2], h->stream));
+  rc = classify_and_scan(h, M);
+  if (rc) return rc;
+  std::vector<int> bounds;
+  size_t max_terms = 0;
+  rc = plan_batches(h, bounds, &max_terms);
+  if (rc) return rc;
+  rc = ensure_dense(h, max_terms * PHD_NPLANES);
+  if (rc) return rc;
+  std::vector<unsigned long long> tb(bounds.size(), 0);
+  if (bounds.size() > 2) {
+    for (size_t b = 0; b + 1 < bounds.size(); ++b)
+      CK(cudaMemcpyAsync(&tb[b], h->toff + bounds[b], sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  CK(cudaMemsetAsync(h->red, 0, sizeof(Reductions), h->stream));
+  float upd_ms = 0, mrg_ms = 0;
+  const bool multi = bounds.size() > 2;
+  for (size_t b = 0; b + 1 < bounds.size(); ++b) {
+    CK(cudaEventRecord(h->ev[3], h->stream));
+    rc = launch_update_batch(h, M, bounds[b], bounds[b + 1], tb[b]);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev[4], h->stream));
+    rc = launch_merge_batch(h, M, bounds[b], bounds[b + 1], tb[b]);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev[5], h->stream));
+    if (multi) {
+      CK(cudaEventSynchronize(h->ev[5]));
+      float t1, t2;
+      cudaEventElapsedTime(&t1, h->ev[3], h->ev[4]);
+      cudaEventElapsedTime(&t2, h->ev[4], h->ev[5]);
+      upd_ms += t1; mrg_ms += t2;
+    }
+  }
+  CK(cudaMemcpyAsync(h->red_host, h->red, sizeof(Reductions), cudaMemcpyDeviceToHost, h->stream));
+  rc = update_weights(h, h->cfg.particle_weighting != 2);
+  if (rc) return rc;
+  CK(cudaEventRecord(h->ev[6], h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->cur ^= 1; /* merged maps become the front buffer; poses and weights are single-buffered in place */
+  /* pose planes are not touched by the update: keep the front pose buffer consistent with `cur` */
+  std::swap(h->pose[0], h->pose[1]);
+  std::swap(h->card[0], h->card[1]);
+  if (!multi) {
+    cudaEventElapsedTime(&upd_ms, h->ev[3], h->ev[4]);
+    cudaEventElapsedTime(&mrg_ms, h->ev[4], h->ev[5]);
+  }
+  h->tim.update_ms = upd_ms;
+  h->tim.merge_ms = mrg_ms;
+  cudaEventElapsedTime(&h->tim.weights_ms, h->ev[5], h->ev[6]);
+  rc = check_err_flag(h);
+  if (rc) return rc;
+  return 0;
+}
+
+extern "C" int phdslam_update_terms(phdslam_t* h, const float* z, int M, int fields, phdslam_gaussian2d_t* terms_out,
+                                    size_t cap, int* n_in_range_out, float* dlogw_out) {
+  CK(cudaSetDevice(h->device));
+  if (M <= 0 || (fields != 2 && fields != 3)) return PHDSLAM_ERR_INVALID;
+  if (M > PHD_MAX_MEAS) M = PHD_MAX_MEAS;
+  int rc = upload_measurements(h, z, M, fields);
+  if (rc) return rc;
+  rc = classify_and_scan(h, M);
+  if (rc) return rc;
+  const int n = h->n_local;
+  const size_t total = (size_t)h->red_host->total_terms;
+  if (total * PHD_NPLANES * 4 > h->cfg.update_buffer_bytes) {
+    phdslam_set_error("phdslam_update_terms needs the whole dense result to fit update_buffer_bytes");
+    return PHDSLAM_ERR_INVALID;
+  }
+  rc = ensure_dense(h, total * PHD_NPLANES);
+  if (rc) return rc;
+  CK(cudaEventRecord(h->ev[3], h->stream));
+  rc = launch_update_batch(h, M, 0, n, 0);
+  if (rc) return rc;
+  CK(cudaEventRecord(h->ev[4], h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaEventElapsedTime(&h->tim.update_ms, h->ev[3], h->ev[4]);
+  std::vector<int> nin(n);
+  CK(cudaMemcpy(nin.data(), h->n_in, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+  if (n_in_range_out) memcpy(n_in_range_out, nin.data(), (size_t)n * sizeof(int));
+  if (dlogw_out) CK(cudaMemcpy(dlogw_out, h->dlogw, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+  if (terms_out) {
+    std::vector<unsigned long long> ooff(n + 1, 0);
+    for (int p = 0; p < n; ++p) ooff[p + 1] = ooff[p] + (unsigned long long)nin[p] * (M + 1) + M;
+    if (ooff[n] > cap) {
+      phdslam_set_error("terms_out too small");
+      return PHDSLAM_ERR_INVALID;
+    }
+    unsigned long long* d_off = nullptr;
+    phdslam_gaussian2d_t* d_out = nullptr;
+    CK(cudaMalloc(&d_off, (n + 1) * sizeof(unsigned long long)));
+    CK(cudaMalloc(&d_out, std::max<size_t>(ooff[n], 1) * sizeof(phdslam_gaussian2d_t)));
+    CK(cudaMemcpy(d_off, ooff.data(), (n + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    dense_export_kernel<<<n, 256, 0, h->stream>>>(h->dense, h->toff, 0, h->n_in, M, 0, n, d_off, d_out);
+    LAUNCH_CHECK(h);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(terms_out, d_out, ooff[n] * sizeof(phdslam_gaussian2d_t), cudaMemcpyDeviceToHost));
+    cudaFree(d_off);
+    cudaFree(d_out);
+  }
+  return 0;
+}
+
+/* ---- estimate ---- */
+extern "C" int phdslam_estimate(phdslam_t* h, phdslam_estimate_t* out) {
+  CK(cudaSetDevice(h->device));
+  const int n = h->n_local;
+  CK(cudaEventRecord(h->ev[7], h->stream));
+  CK(cudaMemsetAsync(h->red, 0, sizeof(Reductions), h->stream));
+  estimate_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->logw, h->pose[h->cur], n, h->offset, h->red);
+  LAUNCH_CHECK(h);
+  CK(cudaMemcpyAsync(h->red_host, h->red, sizeof(Reductions), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaEventRecord(h->ev[8], h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaEventElapsedTime(&h->tim.estimate_ms, h->ev[7], h->ev[8]);
+  const Reductions& r = *h->red_host;
+  const double inv = 1.0 / (double)(1ull << PHD_FX_POSE_BITS);
+  float* e = &out->expected_pose.px;
+  for (int k = 0; k < 6; ++k) e[k] = (float)((double)r.pose_fx[k] * inv);
+  if (r.argmax_key) {
+    out->map_particle = (int)(0xffffffffu - (unsigned)(r.argmax_key & 0xffffffffull));
+    out->max_log_weight = ordered_uint_to_float((uint32_t)(r.argmax_key >> 32));
+  } else {
+    out->map_particle = -1;
+    out->max_log_weight = -FLT_MAX;
+  }
+  double s2 = (double)r.neff_fx * (1.0 / (double)(1ull << PHD_FX_NEFF_BITS));
+  out->neff = (float)(1.0 / s2 / (double)h->n_global);
+  if (h->n_global == 1) { /* main.cpp:381-387 */
+    std::vector<float> p(6);
+    for (int k = 0; k < 6; ++k) CK(cudaMemcpy(&p[k], h->pose[h->cur] + k, sizeof(float), cudaMemcpyDeviceToHost));
+    memcpy(&out->expected_pose, p.data(), 6 * sizeof(float));
+    out->map_particle = 0;
+  }
+  return 0;
+}
+
+/* ---- resample ---- */
+extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms, int* ancestors_out) {
+  CK(cudaSetDevice(h->device));
+  const int n = h->n_local;
+  if (n_new < 0) n_new = h->n_global;
+  if (n_new != h->n_global) {
+    phdslam_set_error("resampling to a different particle count is not supported (device state is fixed-size)");
+    return PHDSLAM_ERR_INVALID;
+  }
+  const double* udev = nullptr;
+  if (uniforms) {
+    size_t need = (size_t)n_new + 1;
+    if (h->draws_cap < need) {
+      cudaFree(h->draws_dev);
+      CK(cudaMalloc(&h->draws_dev, need * sizeof(double)));
+      h->draws_cap = need;
+    }
+    CK(cudaMemcpyAsync(h->draws_dev, uniforms, need * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    udev = h->draws_dev;
+  }
+  CK(cudaEventRecord(h->ev[9], h->stream));
+  resample_weights_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->logw, n, h->q_fx);
+  LAUNCH_CHECK(h);
+  CK(cudaMemsetAsync(h->red, 0, sizeof(Reductions), h->stream));
+  int rc = scan_u64(h, h->q_fx, n, h->cdf_excl, &h->red->cdf_total);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->red_host, h->red, sizeof(Reductions), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const unsigned long long total = h->red_host->cdf_total;
+  if (total == 0) {
+    phdslam_set_error("all particle weights are zero or NaN");
+    return PHDSLAM_ERR_NAN;
+  }
+  resample_search_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->cdf_excl, n, 0ull, total, n_new, h->offset, n, h->offset, udev,
+                                                            h->cfg.resample_mode == 1, h->resample_calls, h->dc.seed_lo,
+                                                            h->dc.seed_hi, h->ancestors);
+  LAUNCH_CHECK(h);
+  const int b = h->cur;
+  resample_gather_kernel<<<cdiv(n, 8), 256, 0, h->stream>>>(h->ancestors, n, h->offset, n, n, h->pose[b], h->pose[b ^ 1],
+                                                          h->count[b], h->count[b ^ 1], h->map[b], h->map[b ^ 1],
+                                                          h->card[b], h->card[b ^ 1], h->Cmax, h->n_card);
+  LAUNCH_CHECK(h);
+  fill_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->logw, n, -phd_logf((float)n_new));
+  LAUNCH_CHECK(h);
+  CK(cudaMemcpyAsync(h->resample_idx, h->ancestors, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaEventRecord(h->ev[10], h->stream));
+  if (ancestors_out) CK(cudaMemcpyAsync(ancestors_out, h->ancestors, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaEventElapsedTime(&h->tim.resample_ms, h->ev[9], h->ev[10]);
+  h->cur ^= 1;
+  h->resample_calls++;
+  return 0;
+}
+
+/* ---- one loop iteration of run_synth (src/main.cpp:1231-1297) ---- */
+extern "C" int phdslam_step(phdslam_t* h, int step_index, const float* control, const float* z, int M, int fields,
+                            phdslam_estimate_t* est_out, int* resampled_out) {
+  int rc;
+  if (step_index > 0) {
+    for (int i = 0; i < h->cfg.subdivide_predict; ++i) {
+      rc = phdslam_predict(h, control, nullptr);
+      if (rc) return rc;
+    }
+  }
+  if (M > 0) {
+    rc = phdslam_update(h, z, M, fields);
+    if (rc) return rc;
+  }
+  phdslam_estimate_t e;
+  rc = phdslam_estimate(h, &e);
+  if (rc) return rc;
+  int res = 0;
+  if ((e.neff <= h->cfg.resample_threshold && M > 0) || h->n_global > 5 * h->cfg.n_particles) {
+    rc = phdslam_resample(h, h->cfg.n_particles, nullptr, nullptr);
+    if (rc) return rc;
+    res = 1;
+  } else {
+    iota_kernel<<<cdiv(h->n_local, 256), 256, 0, h->stream>>>(h->resample_idx, h->n_local, h->offset);
+    LAUNCH_CHECK(h);
+  }
+  if (est_out) *est_out = e;
+  if (resampled_out) *resampled_out = res;
+  if (e.neff != e.neff) {
+    phdslam_set_error("nan weights detected");
+    return PHDSLAM_ERR_NAN;
+  }
+  return 0;
+}
+
+/* ---- import / export ---- */
+extern "C" int phdslam_get_poses(phdslam_t* h, phdslam_pose_t* out) {
+  CK(cudaSetDevice(h->device));
+  const int n = h->n_local;
+  std::vector<float> soa((size_t)6 * n);
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(soa.data(), h->pose[h->cur], soa.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; ++i) {
+    float* o = &out[i].px;
+    for (int k = 0; k < 6; ++k) o[k] = soa[(size_t)k * n + i];
+  }
+  return 0;
+}
+extern "C" int phdslam_set_poses(phdslam_t* h, const phdslam_pose_t* in) {
+  CK(cudaSetDevice(h->device));
+  const int n = h->n_local;
+  std::vector<float> soa((size_t)6 * n);
+  for (int i = 0; i < n; ++i) {
+    const float* s = &in[i].px;
+    for (int k = 0; k < 6; ++k) soa[(size_t)k * n + i] = s[k];
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(h->pose[h->cur], soa.data(), soa.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+extern "C" int phdslam_get_log_weights(phdslam_t* h, float* out) {
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(out, h->logw, (size_t)h->n_local * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+extern "C" int phdslam_set_log_weights(phdslam_t* h, const float* in) {
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(h->logw, in, (size_t)h->n_local * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+extern "C" int phdslam_get_map_sizes(phdslam_t* h, int* out) {
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(out, h->count[h->cur], (size_t)h->n_local * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+extern "C" int phdslam_get_maps(phdslam_t* h, phdslam_gaussian2d_t* out, size_t cap) {
+  CK(cudaSetDevice(h->device));
+  const int n = h->n_local;
+  const size_t C = h->Cmax;
+  std::vector<int> cnt(n);
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(cnt.data(), h->count[h->cur], (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+  std::vector<float> blk(PHD_MAP_PLANES * C);
+  /* chunked download keeps host memory bounded for large particle counts */
+  const size_t chunk = std::max<size_t>(1, (64u << 20) / (PHD_MAP_PLANES * C * 4));
+  std::vector<float> buf(chunk * PHD_MAP_PLANES * C);
+  size_t k = 0;
+  for (size_t p0 = 0; p0 < (size_t)n; p0 += chunk) {
+    size_t np = std::min(chunk, (size_t)n - p0);
+    CK(cudaMemcpy(buf.data(), h->map[h->cur] + p0 * PHD_MAP_PLANES * C, np * PHD_MAP_PLANES * C * 4, cudaMemcpyDeviceToHost));
+    for (size_t p = 0; p < np; ++p) {
+      const float* b = buf.data() + p * PHD_MAP_PLANES * C;
+      for (int i = 0; i < cnt[p0 + p]; ++i) {
+        if (k >= cap) { phdslam_set_error("phdslam_get_maps: output too small"); return PHDSLAM_ERR_INVALID; }
+        phdslam_gaussian2d_t g;
+        g.weight = b[0 * C + i]; g.mean[0] = b[1 * C + i]; g.mean[1] = b[2 * C + i];
+        g.cov[0] = b[3 * C + i]; g.cov[1] = b[4 * C + i]; g.cov[2] = b[4 * C + i]; g.cov[3] = b[5 * C + i];
+        out[k++] = g;
+      }
+    }
+  }
+  return 0;
+}
+extern "C" int phdslam_set_maps(phdslam_t* h, const int* sizes, const phdslam_gaussian2d_t* in) {
+  CK(cudaSetDevice(h->device));
+  const int n = h->n_local;
+  const size_t C = h->Cmax;
+  for (int p = 0; p < n; ++p)
+    if (sizes[p] > h->Cmax || sizes[p] < 0) {
+      phdslam_set_error("phdslam_set_maps: a map exceeds max_components");
+      return PHDSLAM_ERR_CAPACITY;
+    }
+  CK(cudaStreamSynchronize(h->stream));
+  const size_t chunk = std::max<size_t>(1, (64u << 20) / (PHD_MAP_PLANES * C * 4));
+  std::vector<float> buf(chunk * PHD_MAP_PLANES * C);
+  size_t k = 0;
+  for (size_t p0 = 0; p0 < (size_t)n; p0 += chunk) {
+    size_t np = std::min(chunk, (size_t)n - p0);
+    std::fill(buf.begin(), buf.end(), 0.0f);
+    for (size_t p = 0; p < np; ++p) {
+      float* b = buf.data() + p * PHD_MAP_PLANES * C;
+      for (int i = 0; i < sizes[p0 + p]; ++i) {
+        const phdslam_gaussian2d_t& g = in[k++];
+        b[0 * C + i] = g.weight; b[1 * C + i] = g.mean[0]; b[2 * C + i] = g.mean[1];
+        b[3 * C + i] = g.cov[0]; b[4 * C + i] = g.cov[1]; b[5 * C + i] = g.cov[3];
+      }
+    }
+    CK(cudaMemcpy(h->map[h->cur] + p0 * PHD_MAP_PLANES * C, buf.data(), np * PHD_MAP_PLANES * C * 4, cudaMemcpyHostToDevice));
+  }
+  CK(cudaMemcpy(h->count[h->cur], sizes, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+  return 0;
+}
+extern "C" int phdslam_get_resample_idx(phdslam_t* h, int* out) {
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(out, h->resample_idx, (size_t)h->n_local * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+extern "C" int phdslam_get_cardinalities(phdslam_t* h, float* out) {
+  if (!h->n_card) return PHDSLAM_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(out, h->card[h->cur], (size_t)h->n_local * h->n_card * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+extern "C" int phdslam_set_cardinalities(phdslam_t* h, const float* in) {
+  if (!h->n_card) return PHDSLAM_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(h->card[h->cur], in, (size_t)h->n_local * h->n_card * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int phdslam_map_estimate(phdslam_t* h, int which, phdslam_gaussian2d_t* out, int cap, int* n_out) {
+  CK(cudaSetDevice(h->device));
+  if (which == 1) {
+    phdslam_estimate_t e;
+    int rc = phdslam_estimate(h, &e);
+    if (rc) return rc;
+    int lp = e.map_particle - h->offset;
+    if (lp < 0 || lp >= h->n_local) { *n_out = 0; return 0; }
+    const size_t C = h->Cmax;
+    int cnt = 0;
+    CK(cudaMemcpy(&cnt, h->count[h->cur] + lp, sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<float> b(PHD_MAP_PLANES * C);
+    CK(cudaMemcpy(b.data(), h->map[h->cur] + (size_t)lp * PHD_MAP_PLANES * C, b.size() * 4, cudaMemcpyDeviceToHost));
+    *n_out = cnt;
+    for (int i = 0; i < cnt && i < cap; ++i) {
+      phdslam_gaussian2d_t g;
+      g.weight = b[0 * C + i]; g.mean[0] = b[1 * C + i]; g.mean[1] = b[2 * C + i];
+      g.cov[0] = b[3 * C + i]; g.cov[1] = b[4 * C + i]; g.cov[2] = b[4 * C + i]; g.cov[3] = b[5 * C + i];
+      out[i] = g;
+    }
+    return 0;
+  }
+  phdslam_set_error("EAP map estimate (map_estimate & 2) is not built yet");
+  return PHDSLAM_ERR_INVALID;
+}
+
+/* ---- timings / snapshot ---- */
+extern "C" int phdslam_get_timings(phdslam_t* h, phdslam_timings_t* out) {
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  if (h->predict_calls && cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->tim.predict_ms = ms;
+  h->tim.launches = h->launches;
+  *out = h->tim;
+  return 0;
+}
+
+extern "C" int phdslam_snapshot(phdslam_t* h) {
+  CK(cudaSetDevice(h->device));
+  const size_t n = h->n_local, C = h->Cmax;
+  CK(cudaStreamSynchronize(h->stream));
+  if (!h->snap_pose) {
+    CK(cudaMalloc(&h->snap_pose, 6 * n * sizeof(float)));
+    CK(cudaMalloc(&h->snap_count, n * sizeof(int)));
+    CK(cudaMalloc(&h->snap_map, n * PHD_MAP_PLANES * C * sizeof(float)));
+    CK(cudaMalloc(&h->snap_logw, n * sizeof(float)));
+    if (h->n_card) CK(cudaMalloc(&h->snap_card, n * h->n_card * sizeof(float)));
+  }
+  CK(cudaMemcpy(h->snap_pose, h->pose[h->cur], 6 * n * sizeof(float), cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpy(h->snap_count, h->count[h->cur], n * sizeof(int), cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpy(h->snap_map, h->map[h->cur], n * PHD_MAP_PLANES * C * sizeof(float), cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpy(h->snap_logw, h->logw, n * sizeof(float), cudaMemcpyDeviceToDevice));
+  if (h->n_card) CK(cudaMemcpy(h->snap_card, h->card[h->cur], n * h->n_card * sizeof(float), cudaMemcpyDeviceToDevice));
+  h->snap_predict_calls = h->predict_calls;
+  h->snap_resample_calls = h->resample_calls;
+  return 0;
+}
+extern "C" int phdslam_restore(phdslam_t* h) {
+  CK(cudaSetDevice(h->device));
+  if (!h->snap_pose) return PHDSLAM_ERR_INVALID;
+  const size_t n = h->n_local, C = h->Cmax;
+  CK(cudaMemcpyAsync(h->pose[h->cur], h->snap_pose, 6 * n * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->count[h->cur], h->snap_count, n * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->map[h->cur], h->snap_map, n * PHD_MAP_PLANES * C * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->logw, h->snap_logw, n * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  if (h->n_card)
+    CK(cudaMemcpyAsync(h->card[h->cur], h->snap_card, n * h->n_card * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  h->predict_calls = h->snap_predict_calls;
+  h->resample_calls = h->snap_resample_calls;
+  return 0;
+}

@@ -1,0 +1,92 @@
+/* phdslam_internal.h -- handle layout and kernel-facing derived configuration (not installed). */
+#ifndef PHDSLAM_INTERNAL_H
+#define PHDSLAM_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/phdslam.h"
+
+void phdslam_set_error(const std::string& s);
+
+#define PHD_MAX_MEAS 256   /* reference: __constant__ RangeBearingMeasurement Z[256] (src/phdfilter.cu:120) */
+#define PHD_NPLANES 7      /* dense update term = {c0,c1,c2,c3,mx,my,w}, the field order of Gaussian2D */
+#define PHD_MAP_PLANES 6   /* persistent map component = {w,mx,my,pxx,pxy,pyy} (covariance stored once) */
+
+/* Constants derived on the host once per set_config and passed BY VALUE to every kernel
+ * (the reference copies its whole 324-byte SlamConfig to __constant__ memory, src/phdfilter.cu:3885). */
+struct DevCfg {
+  float min_range, max_range, max_bearing;
+  float lo2, hi2, hb2;            /* "nearly in range" bounds, exact fp32 images of 0.8*minR, 1.2*maxR, 1.2*maxB */
+  float var_r, var_b;             /* stdRange^2, stdBearing^2 */
+  float bvar_r, bvar_b;           /* (std*birthNoiseFactor)^2 */
+  float pd, log_pd;
+  float clutter_density, clutter_rate, birth_weight, log_birth_weight;
+  float min_sep, min_w;
+  int distance_metric, particle_weighting, labeled, filter_type;
+  int motion_type;
+  float dt_sub, l, h, a, b, std_alpha, std_enc, ax3, ay3, ayaw3;
+  uint32_t seed_lo, seed_hi;
+  int Cmax, n_card;
+  float log_clutter_rate;
+};
+
+struct Reductions {       /* device-resident cross-particle accumulators (all order-independent) */
+  unsigned max_key;       /* ordered-uint image of max log-weight (0 = none) */
+  int nan_count;
+  unsigned long long sum_fx;      /* sum exp(w-max) in Q36 */
+  unsigned long long neff_fx;     /* sum exp(2w) in Q60 */
+  long long pose_fx[6];           /* sum exp(w)*pose in Q40 */
+  unsigned long long argmax_key;  /* (ordered weight << 32) | ~global_index */
+  unsigned long long cdf_total;   /* local sum of Q40 weights */
+  int err_flag;                   /* capacity / overflow flags raised by kernels */
+  int max_terms;                  /* max over particles of padded dense term count */
+  unsigned long long total_terms; /* sum over particles of padded dense term count */
+};
+
+struct phdslam {
+  phdslam_config_t cfg;
+  DevCfg dc;
+  int device;
+  cudaStream_t stream;
+  int rank, world;
+  int n_global, n_local, offset;
+  int Cmax, n_card, Smax;
+  /* persistent state, double buffered (front = cur) */
+  int cur;
+  float* pose[2];        /* [6][n_local] SoA */
+  int* count[2];         /* [n_local] */
+  float* map[2];         /* [n_local][6][Cmax] */
+  float* card[2];        /* [n_local][n_card] (CPHD) */
+  float* logw;           /* [n_local] */
+  int* resample_idx;     /* [n_local] */
+  /* snapshot for bench */
+  float* snap_pose; int* snap_count; float* snap_map; float* snap_card; float* snap_logw;
+  unsigned snap_predict_calls, snap_resample_calls;
+  /* per-step scratch */
+  uint8_t* cls;                      /* [n_local][Cmax] in-range class */
+  int* n_in;                         /* [n_local] */
+  float* dlogw;                      /* [n_local] */
+  unsigned long long* tpad;          /* [n_local] padded term counts */
+  unsigned long long* toff;          /* [n_local+1] exclusive scan */
+  unsigned long long* scan_tmp;      /* block sums */
+  float* dense; size_t dense_floats; /* dense update-term buffer */
+  float* z_dev;                      /* [3][256]: range, bearing, label */
+  double* draws_dev; size_t draws_cap;
+  unsigned long long* q_fx;          /* [n_local] Q40 weights */
+  unsigned long long* cdf_excl;      /* [n_local+1] */
+  int* ancestors;                    /* [n_local] */
+  Reductions* red;                   /* device */
+  Reductions* red_host;              /* pinned */
+  /* counters */
+  unsigned predict_calls, resample_calls;
+  unsigned long long launches;
+  cudaEvent_t ev[12];
+  phdslam_timings_t tim;
+  void* nccl_comm;
+};
+
+#endif

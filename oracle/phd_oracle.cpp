@@ -1,0 +1,816 @@
+/*
+ * phd_oracle.cpp -- CPU ORACLE (test infrastructure, NOT product code).
+ * See phd_oracle.h for the role of this file and how parity is pinned.
+ *
+ * Build: g++ -O2 -std=c++17 -ffp-contract=off -mfma -fopenmp -shared -fPIC (oracle/Makefile).
+ * -ffp-contract=off is REQUIRED: every a*b+c below must round twice exactly as the
+ * kernels (nvcc -fmad=false) do; fused operations are written as explicit fmaf().
+ */
+#include "phd_oracle.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../include/phd_detmath.h"
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef phdslam_gaussian2d_t G2;
+typedef phdslam_pose_t Pose;
+
+struct phd_oracle {
+  phdslam_config_t cfg;
+  std::vector<Pose> states;                 /* ParticleSLAM::states   (src/slamtypes.h:279) */
+  std::vector<float> weights;               /* ParticleSLAM::weights  (log domain) */
+  std::vector<std::vector<G2>> maps;        /* SynthSLAM::maps_static (src/slamtypes.h:290) */
+  std::vector<int> resample_idx;
+  std::vector<std::vector<float>> card;     /* SynthSLAM::cardinalities (log domain) */
+  unsigned predict_calls = 0;               /* Philox counter words */
+  unsigned resample_calls = 0;
+  int threads = 1;
+};
+
+/* ------------------------------------------------------------------------- */
+/* helpers                                                                    */
+/* ------------------------------------------------------------------------- */
+
+/* Largest float <= d and smallest float >= d: lets a reference comparison made in double
+ * (`r <= 1.2*dev_config.maxRange`, src/phdfilter.cu:1340-1342) be done exactly in fp32. */
+static float float_floor(double d) {
+  float f = (float)d;
+  if ((double)f > d) f = nextafterf(f, -INFINITY);
+  return f;
+}
+static float float_ceil(double d) {
+  float f = (float)d;
+  if ((double)f < d) f = nextafterf(f, INFINITY);
+  return f;
+}
+
+/* Canonical reduction shape of the kernels: 32 lane-strided sequential partial sums,
+ * then an xor-butterfly (offsets 16,8,4,2,1).  Stands in for the reference's 256-wide
+ * shared-memory tree (sumByReduction, src/device_math.cuh:452-472). */
+static float warp_sum(const float* v, int n) {
+  float p[32];
+  for (int l = 0; l < 32; ++l) {
+    float acc = 0.0f;
+    for (int i = l; i < n; i += 32) acc = acc + v[i];
+    p[l] = acc;
+  }
+  for (int off = 16; off >= 1; off >>= 1) {
+    float q[32];
+    for (int l = 0; l < 32; ++l) q[l] = p[l] + p[l ^ off];
+    memcpy(p, q, sizeof(p));
+  }
+  return p[0];
+}
+
+extern "C" float oracle_warp_sum(const float* v, int n) { return warp_sum(v, n); }
+
+/* ------------------------------------------------------------------------- */
+/* lifetime / state access                                                    */
+/* ------------------------------------------------------------------------- */
+
+extern "C" phd_oracle_t* oracle_create(const phdslam_config_t* cfg) {
+  phd_oracle* o = new phd_oracle();
+  o->cfg = *cfg;
+  int n = cfg->n_particles;
+  /* run_synth initialisation, src/main.cpp:1129-1144 */
+  Pose p0 = {cfg->x0, cfg->y0, cfg->yaw0, cfg->vx0, cfg->vy0, cfg->vyaw0};
+  o->states.assign(n, p0);
+  o->weights.assign(n, -phd_logf((float)n)); /* -log(float(n_particles)), main.cpp:1144 */
+  o->maps.assign(n, std::vector<G2>());
+  o->resample_idx.resize(n);
+  for (int i = 0; i < n; ++i) o->resample_idx[i] = i;
+  o->card.assign(n, std::vector<float>());
+  if (cfg->filter_type == 1) {
+    int nc = cfg->max_cardinality + 1;
+    for (int i = 0; i < n; ++i) o->card[i].assign(nc, -phd_logf((float)nc)); /* main.cpp:1140-1143 */
+  }
+  return o;
+}
+extern "C" void oracle_destroy(phd_oracle_t* o) { delete o; }
+extern "C" void oracle_set_config(phd_oracle_t* o, const phdslam_config_t* cfg) { o->cfg = *cfg; }
+extern "C" void oracle_set_threads(phd_oracle_t* o, int n) { o->threads = n < 1 ? 1 : n; }
+extern "C" int oracle_n_particles(const phd_oracle_t* o) { return (int)o->states.size(); }
+extern "C" void oracle_get_poses(const phd_oracle_t* o, Pose* out) { memcpy(out, o->states.data(), o->states.size() * sizeof(Pose)); }
+extern "C" void oracle_set_poses(phd_oracle_t* o, const Pose* in) { memcpy(o->states.data(), in, o->states.size() * sizeof(Pose)); }
+extern "C" void oracle_get_log_weights(const phd_oracle_t* o, float* out) { memcpy(out, o->weights.data(), o->weights.size() * 4); }
+extern "C" void oracle_set_log_weights(phd_oracle_t* o, const float* in) { memcpy(o->weights.data(), in, o->weights.size() * 4); }
+extern "C" void oracle_get_map_sizes(const phd_oracle_t* o, int* out) {
+  for (size_t i = 0; i < o->maps.size(); ++i) out[i] = (int)o->maps[i].size();
+}
+extern "C" void oracle_get_maps(const phd_oracle_t* o, G2* out) {
+  size_t k = 0;
+  for (auto& m : o->maps)
+    for (auto& g : m) out[k++] = g;
+}
+extern "C" void oracle_set_maps(phd_oracle_t* o, const int* sizes, const G2* in) {
+  size_t k = 0;
+  for (size_t i = 0; i < o->maps.size(); ++i) {
+    o->maps[i].assign(in + k, in + k + sizes[i]);
+    k += sizes[i];
+  }
+}
+extern "C" void oracle_get_resample_idx(const phd_oracle_t* o, int* out) { memcpy(out, o->resample_idx.data(), o->resample_idx.size() * 4); }
+extern "C" void oracle_get_cardinalities(const phd_oracle_t* o, float* out) {
+  int nc = o->cfg.max_cardinality + 1;
+  for (size_t i = 0; i < o->card.size(); ++i)
+    if ((int)o->card[i].size() == nc) memcpy(out + i * nc, o->card[i].data(), nc * 4);
+}
+extern "C" void oracle_set_cardinalities(phd_oracle_t* o, const float* in) {
+  int nc = o->cfg.max_cardinality + 1;
+  for (size_t i = 0; i < o->card.size(); ++i) o->card[i].assign(in + i * nc, in + (i + 1) * nc);
+}
+
+/* ------------------------------------------------------------------------- */
+/* predict                                                                    */
+/* ------------------------------------------------------------------------- */
+
+/* phdPredict host wrapper (src/phdfilter.cu:1080-1257) + phdPredictKernelAckerman (:785-825)
+ * + phdPredictKernel (:827-859).  One call = one sub-step; dt = config.dt / subdividePredict.
+ * Noise draws: injected (reference call order, :1113-1117 / :1148-1152) or Philox4x32-10. */
+extern "C" void oracle_predict(phd_oracle_t* o, const float* control, const double* draws) {
+  const phdslam_config_t& c = o->cfg;
+  if (c.n_predict_particles != 1) {
+    fprintf(stderr, "oracle: n_predict_particles != 1 is not on the path yet\n");
+    abort();
+  }
+  int n = (int)o->states.size();
+  float dt = c.dt / (float)c.subdivide_predict; /* REAL dt = dev_config.dt/dev_config.subdividePredict */
+  unsigned call = o->predict_calls++;
+  for (int i = 0; i < n; ++i) {
+    Pose s = o->states[i];
+    Pose ns;
+    float sn, cs;
+    phd_sincosf(s.ptheta, &sn, &cs);
+    if (c.motion_type == 1) {
+      double d_alpha, d_enc;
+      if (draws) {
+        d_alpha = draws[2 * i];
+        d_enc = draws[2 * i + 1];
+      } else {
+        phd_philox4_t r = phd_philox4x32_10((uint32_t)i, call, PHD_STREAM_PREDICT, 0u, (uint32_t)c.seed, (uint32_t)(c.seed >> 32));
+        float z0, z1;
+        phd_box_muller(r.v[0], r.v[1], &z0, &z1);
+        d_alpha = (double)z0;
+        d_enc = (double)z1;
+      }
+      /* noiseVector[i].n_alpha = config.stdAlpha * randn() : float*double, stored as float (:1150-1151) */
+      float n_alpha = (float)((double)c.std_alpha * d_alpha);
+      float n_enc = (float)((double)c.std_encoder * d_enc);
+      float v_enc = control ? control[0] : 0.0f, alpha = control ? control[1] : 0.0f;
+      float ve = v_enc + n_enc;                       /* :804 */
+      float al = alpha + n_alpha;                     /* :805 */
+      float ta = phd_tanf(al);
+      float vc = ve / (1.0f - ta * c.h / c.l);        /* :806 */
+      float xc_dot = vc * cs;                         /* :807 */
+      float yc_dot = vc * sn;                         /* :808 */
+      float thc_dot = vc * ta / c.l;                  /* :809 */
+      ns.px = s.px + dt * (xc_dot - thc_dot * (c.a * sn + c.b * cs));   /* :811-814 */
+      ns.py = s.py + dt * (yc_dot + thc_dot * (c.a * cs - c.b * sn));   /* :815-818 */
+      ns.ptheta = phd_wrap_angle(s.ptheta + dt * thc_dot);              /* :819 */
+      ns.vx = 0.0f; ns.vy = 0.0f; ns.vtheta = 0.0f;                     /* :820-822 */
+    } else {
+      double d0, d1, d2;
+      if (draws) {
+        d0 = draws[3 * i]; d1 = draws[3 * i + 1]; d2 = draws[3 * i + 2];
+      } else {
+        phd_philox4_t r = phd_philox4x32_10((uint32_t)i, call, PHD_STREAM_PREDICT, 0u, (uint32_t)c.seed, (uint32_t)(c.seed >> 32));
+        float z0, z1, z2, z3;
+        phd_box_muller(r.v[0], r.v[1], &z0, &z1);
+        phd_box_muller(r.v[2], r.v[3], &z2, &z3);
+        d0 = z0; d1 = z1; d2 = z2;
+      }
+      /* noiseVector[i].ax = 3*config.ax * randn() (:1115-1117; note the factor 3) */
+      float nax = (float)((double)(3.0f * c.ax) * d0);
+      float nay = (float)((double)(3.0f * c.ay) * d1);
+      float nat = (float)((double)(3.0f * c.ayaw) * d2);
+      float hdt2 = dt * dt * 0.5f;
+      ns.px = s.px + dt * (s.vx * cs - s.vy * sn) + hdt2 * (nax * cs - nay * sn);      /* :843-847 */
+      ns.py = s.py + dt * (s.vx * sn + s.vy * cs) + hdt2 * (nax * sn + nay * cs);      /* :848-852 */
+      ns.ptheta = phd_wrap_angle(s.ptheta + dt * s.vtheta + hdt2 * nat);               /* :853-855 */
+      ns.vx = s.vx + dt * nax;                                                         /* :856-858 */
+      ns.vy = s.vy + dt * nay;
+      ns.vtheta = s.vtheta + dt * nat;
+    }
+    o->states[i] = ns;
+  }
+}
+
+/* ------------------------------------------------------------------------- */
+/* GM-PHD update                                                              */
+/* ------------------------------------------------------------------------- */
+
+/* computeInRangeKernel classification (src/phdfilter.cu:1328-1346):
+ * 1 = in the field of view, 2 = "nearly" (bypasses the update, joins the merge), 0 = far. */
+static int classify(const phdslam_config_t& c, const Pose& pose, const G2& f) {
+  float dx = f.mean[0] - pose.px;
+  float dy = f.mean[1] - pose.py;
+  float r2 = dx * dx + dy * dy;
+  float r = sqrtf(r2);
+  float bearing = phd_wrap_angle(phd_atan2f(dy, dx) - pose.ptheta);
+  if (r >= c.min_range && r <= c.max_range && fabsf(bearing) <= c.max_bearing) return 1;
+  /* 0.8*minRange etc. are double products in the reference; exact fp32 equivalents: */
+  float lo2 = float_ceil(0.8 * (double)c.min_range);
+  float hi2 = float_floor(1.2 * (double)c.max_range);
+  float hb2 = float_floor(1.2 * (double)c.max_bearing);
+  if (r >= lo2 && r <= hi2 && fabsf(bearing) <= hb2) return 2;
+  return 0;
+}
+
+/* birth Gaussian from one measurement (host loop, src/phdfilter.cu:3468-3507) */
+static G2 birth_term(const phdslam_config_t& c, const Pose& pose, float zr, float zb, int label) {
+  G2 b;
+  float theta = pose.ptheta + zb;
+  float sn, cs;
+  phd_sincosf(theta, &sn, &cs);
+  float dx = zr * cs;
+  float dy = zr * sn;
+  b.mean[0] = pose.px + dx;
+  b.mean[1] = pose.py + dy;
+  float J0 = dx / zr, J1 = dy / zr, J2 = -dy, J3 = dx;
+  float sr = c.std_range * c.birth_noise_factor;
+  float sb = c.std_bearing * c.birth_noise_factor;
+  float var_range = sr * sr;      /* pow(config.stdRange*config.birthNoiseFactor,2) */
+  float var_bearing = sb * sb;
+  b.cov[0] = J0 * J0 * var_range + J2 * J2 * var_bearing;
+  b.cov[1] = J0 * J1 * var_range + J2 * J3 * var_bearing;
+  b.cov[2] = b.cov[1];
+  b.cov[3] = J1 * J1 * var_range + J3 * J3 * var_bearing;
+  if (label == 0 || !c.labeled_measurements)
+    b.weight = phd_safe_log(c.birth_weight);
+  else
+    b.weight = phd_safe_log(0.0f);
+  return b;
+}
+
+struct UpdateOut {
+  std::vector<G2> terms;  /* [nondetect C | detect m-major M*C | birth M] */
+  int n_in = 0;
+  float dlogw = 0.0f;
+};
+
+/* preUpdateSynthKernel (src/phdfilter.cu:1824-1925) followed by phdUpdateKernel (:2083-2321)
+ * for ONE particle.  `in` are the in-range (class 1) components in map order. */
+static void update_particle(const phdslam_config_t& c, const Pose& pose, const std::vector<G2>& in, const float* z,
+                            int M, int fields, UpdateOut& out) {
+  const int C = (int)in.size();
+  const int T = C * (M + 1) + M;
+  out.n_in = C;
+  out.terms.assign(T, G2());
+  std::vector<float> pdv(C), logdet(C), rj(C), bj(C);
+  std::vector<float> K(4 * C), S(4 * C), covu(4 * C);
+  const float var_r = c.std_range * c.std_range;      /* pow(dev_config.stdRange,2) */
+  const float var_b = c.std_bearing * c.std_bearing;
+  for (int i = 0; i < C; ++i) {
+    const G2& f = in[i];
+    float dx = f.mean[0] - pose.px;
+    float dy = f.mean[1] - pose.py;
+    float r2 = dx * dx + dy * dy;
+    float r = sqrtf(r2);
+    float bearing = phd_wrap_angle(phd_atan2f(dy, dx) - pose.ptheta);
+    float pd = 0.0f;
+    if (r <= c.max_range && fabsf(bearing) <= c.max_bearing) pd = c.pd;   /* :1841-1844 (no minRange test) */
+    float J[4];
+    J[0] = dx / r; J[2] = dy / r; J[1] = -dy / r2; J[3] = dx / r2;          /* :1847-1851 */
+    const float* P = f.cov;
+    float sigma[4];                                                        /* :1857-1861 */
+    sigma[0] = (P[0] * J[0] + J[2] * P[1]) * J[0] + (J[0] * P[2] + P[3] * J[2]) * J[2] + var_r;
+    sigma[1] = (P[0] * J[1] + J[3] * P[1]) * J[0] + (J[1] * P[2] + P[3] * J[3]) * J[2];
+    sigma[2] = (P[0] * J[0] + J[2] * P[1]) * J[1] + (J[0] * P[2] + P[3] * J[2]) * J[3];
+    sigma[3] = (P[0] * J[1] + J[3] * P[1]) * J[1] + (J[1] * P[2] + P[3] * J[3]) * J[3] + var_b;
+    sigma[1] = (sigma[1] + sigma[2]) / 2.0f;                               /* :1864-1865 */
+    sigma[2] = sigma[1];
+    float det = sigma[0] * sigma[3] - sigma[1] * sigma[2];                 /* :1867 */
+    float* Si = &S[4 * i];
+    Si[0] = sigma[3] / det; Si[1] = -sigma[1] / det; Si[2] = -sigma[2] / det; Si[3] = sigma[0] / det;
+    float* Ki = &K[4 * i];                                                 /* :1877-1881 */
+    Ki[0] = Si[0] * (P[0] * J[0] + P[2] * J[2]) + Si[1] * (P[0] * J[1] + P[2] * J[3]);
+    Ki[1] = Si[0] * (P[1] * J[0] + P[3] * J[2]) + Si[1] * (P[1] * J[1] + P[3] * J[3]);
+    Ki[2] = Si[2] * (P[0] * J[0] + P[2] * J[2]) + Si[3] * (P[0] * J[1] + P[2] * J[3]);
+    Ki[3] = Si[2] * (P[1] * J[0] + P[3] * J[2]) + Si[3] * (P[1] * J[1] + P[3] * J[3]);
+    /* Joseph-form covariance, Maple-expanded in the reference (:1883-1887).  a,b,cc,d = I - K*J */
+    float a = 1.0f - Ki[0] * J[0] - Ki[2] * J[1];
+    float b = -Ki[0] * J[2] - Ki[2] * J[3];
+    float cc = -Ki[1] * J[0] - Ki[3] * J[1];
+    float d = 1.0f - Ki[1] * J[2] - Ki[3] * J[3];
+    float* cu = &covu[4 * i];
+    cu[0] = (a * P[0] + b * P[1]) * a + (a * P[2] + b * P[3]) * b + Ki[0] * Ki[0] * var_r + Ki[2] * Ki[2] * var_b;
+    cu[2] = (a * P[0] + b * P[1]) * cc + (a * P[2] + b * P[3]) * d + Ki[0] * var_r * Ki[1] + Ki[2] * var_b * Ki[3];
+    cu[1] = (cc * P[0] + d * P[1]) * a + (cc * P[2] + d * P[3]) * b + Ki[0] * var_r * Ki[1] + Ki[2] * var_b * Ki[3];
+    cu[3] = (cc * P[0] + d * P[1]) * cc + (cc * P[2] + d * P[3]) * d + Ki[1] * Ki[1] * var_r + Ki[3] * Ki[3] * var_b;
+    pdv[i] = pd; logdet[i] = phd_safe_log(det); rj[i] = r; bj[i] = bearing;
+    /* non-detection term (:2137-2141) */
+    G2& nd = out.terms[i];
+    nd = f;
+    nd.weight = f.weight * (1.0f - pd);
+  }
+  /* detection terms, measurement-major (:1898-1923, copied by :2144-2151) */
+  for (int m = 0; m < M; ++m) {
+    float zr = z[m * fields], zb = z[m * fields + 1];
+    int label = fields > 2 ? (int)z[m * fields + 2] : 0;
+    for (int i = 0; i < C; ++i) {
+      const G2& f = in[i];
+      const float* Ki = &K[4 * i];
+      const float* Si = &S[4 * i];
+      float innov0 = zr - rj[i];
+      float innov1 = phd_wrap_angle(zb - bj[i]);
+      G2& t = out.terms[C + m * C + i];
+      t.mean[0] = f.mean[0] + Ki[0] * innov0 + Ki[2] * innov1;
+      t.mean[1] = f.mean[1] + Ki[1] * innov0 + Ki[3] * innov1;
+      for (int n = 0; n < 4; ++n) t.cov[n] = covu[4 * i + n];
+      float dist = innov0 * innov0 * Si[0] + innov0 * innov1 * (Si[1] + Si[2]) + innov1 * innov1 * Si[3];
+      float g = -0.5f * dist - PHD_LOG_2PI_F - 0.5f * logdet[i];           /* :1911 */
+      if (label == 0 || !c.labeled_measurements)
+        t.weight = phd_safe_log(pdv[i]) + phd_safe_log(f.weight) + g;       /* :1916-1917, log domain */
+      else
+        t.weight = phd_safe_log(0.0f);
+    }
+  }
+  /* births (:3468-3507), log(birthWeight) */
+  for (int m = 0; m < M; ++m) {
+    int label = fields > 2 ? (int)z[m * fields + 2] : 0;
+    out.terms[C + M * C + m] = birth_term(c, pose, z[m * fields], z[m * fields + 1], label);
+  }
+  /* predicted cardinality: sum of pd*w over features then birthWeight per measurement (:2133-2186) */
+  std::vector<float> tmp(C + M);
+  for (int i = 0; i < C; ++i) tmp[i] = pdv[i] * in[i].weight;
+  for (int m = 0; m < M; ++m) tmp[C + m] = c.birth_weight;
+  float cardinality_predict = warp_sum(tmp.data(), C + M);
+  /* per-measurement normaliser and final weights (:2190-2252) */
+  float particle_weight = 0.0f;
+  std::vector<float> ev(C), dsum(M);
+  for (int m = 0; m < M; ++m) {
+    G2* det = &out.terms[C + m * C];
+    for (int i = 0; i < C; ++i) ev[i] = phd_expf(det[i].weight);
+    float sum = (C > 0) ? warp_sum(ev.data(), C) : 0.0f;
+    sum = sum + c.clutter_density;
+    sum = sum + c.birth_weight;
+    float log_normalizer = phd_safe_log(sum);
+    for (int i = 0; i < C; ++i) {
+      det[i].weight = phd_expf(det[i].weight - log_normalizer);
+      ev[i] = det[i].weight;
+    }
+    G2& bt = out.terms[C + M * C + m];
+    bt.weight = phd_expf(bt.weight - log_normalizer);
+    dsum[m] = ((C > 0) ? warp_sum(ev.data(), C) : 0.0f) + bt.weight;
+    particle_weight = particle_weight + log_normalizer;                     /* :2250 */
+  }
+  if (c.particle_weighting == 0) {
+    out.dlogw = particle_weight - cardinality_predict;                      /* :2260-2262 */
+  } else if (c.particle_weighting == 1) {
+    /* Vo empty-map weighting (:2264-2279).  The reference sums serially on thread 0; canonical order:
+     * warp_sum per block of terms, blocks accumulated in term order. */
+    std::vector<float> w(std::max(C, 1));
+    for (int i = 0; i < C; ++i) w[i] = in[i].weight;
+    float cn_predict = warp_sum(w.data(), C);
+    for (int i = 0; i < C; ++i) w[i] = out.terms[i].weight;
+    float cn_update = warp_sum(w.data(), C);
+    for (int m = 0; m < M; ++m) cn_update = cn_update + dsum[m];
+    out.dlogw = (float)M * c.clutter_density + cn_update - cn_predict - c.clutter_rate;
+  } else {
+    out.dlogw = 0.0f; /* scheme 2 is unfinished in the reference's device code (:2281-2305) */
+  }
+}
+
+/* computeMahalDist (src/device_math.cuh:309-325) with invert_matrix2 (:61-70) */
+static float mahal(const G2& a, const G2& b) {
+  float sigma[4], inv[4];
+  for (int i = 0; i < 4; ++i) sigma[i] = (a.cov[i] + b.cov[i]) / 2.0f;
+  float det = sigma[0] * sigma[3] - sigma[2] * sigma[1];
+  inv[0] = sigma[3] / det; inv[1] = -sigma[1] / det; inv[2] = -sigma[2] / det; inv[3] = sigma[0] / det;
+  float i0 = a.mean[0] - b.mean[0];
+  float i1 = a.mean[1] - b.mean[1];
+  return i0 * i0 * inv[0] + i0 * i1 * (inv[1] + inv[2]) + i1 * i1 * inv[3];
+}
+
+/* computeHellingerDist (src/device_math.cuh:380-413) */
+static float hellinger(const G2& a, const G2& b) {
+  float innov0 = a.mean[0] - b.mean[0], innov1 = a.mean[1] - b.mean[1];
+  float s[4] = {a.cov[0] + b.cov[0], a.cov[1] + b.cov[1], a.cov[2] + b.cov[2], a.cov[3] + b.cov[3]};
+  float det = s[0] * s[3] - s[2] * s[1];
+  float inv[4] = {1.0f, 0.0f, 0.0f, 1.0f};
+  if (det > FLT_MIN) {
+    inv[0] = s[3] / det; inv[1] = -s[1] / det; inv[2] = -s[2] / det; inv[3] = s[0] / det;
+  }
+  float eps = -0.25f * (innov0 * innov0 * inv[0] + innov0 * innov1 * (inv[1] + inv[2]) + innov1 * innov1 * inv[3]);
+  det = det / 4.0f;
+  float dist = 1.0f / det;
+  float p[4];
+  p[0] = a.cov[0] * b.cov[0] + a.cov[2] * b.cov[1];
+  p[1] = a.cov[1] * b.cov[0] + a.cov[3] * b.cov[1];
+  p[2] = a.cov[0] * b.cov[2] + a.cov[2] * b.cov[3];
+  p[3] = a.cov[1] * b.cov[2] + a.cov[3] * b.cov[3];
+  float detp = p[0] * p[3] - p[2] * p[1];
+  dist = dist * sqrtf(detp);
+  dist = 1.0f - sqrtf(dist) * phd_expf(eps);
+  return dist;
+}
+
+extern "C" float oracle_mahalanobis(const G2* a, const G2* b) { return mahal(*a, *b); }
+extern "C" float oracle_hellinger(const G2* a, const G2* b) { return hellinger(*a, *b); }
+
+/* phdUpdateMergeKernel (src/phdfilter.cu:2707-2898): greedy Gaussian-mixture reduction.
+ * Canonical choices where the reference is order-dependent: arg-max ties -> lowest index;
+ * cluster sums accumulate sequentially in ascending index order. */
+static void merge_mixture(const phdslam_config_t& c, const std::vector<G2>& cand, std::vector<G2>& out) {
+  const int n = (int)cand.size();
+  std::vector<char> merged(n, 0);
+  std::vector<int> members;
+  while (true) {
+    int best = -1;
+    for (int i = 0; i < n; ++i)
+      if (!merged[i] && (best < 0 || cand[best].weight < cand[i].weight)) best = i;   /* :2751-2787 */
+    if (best < 0) break;
+    const G2& mx = cand[best];
+    members.clear();
+    for (int i = 0; i < n; ++i) {
+      if (merged[i]) continue;
+      float dist = (c.distance_metric == 0) ? mahal(mx, cand[i]) : hellinger(mx, cand[i]);  /* :2802-2805 */
+      if (dist < c.min_separation) members.push_back(i);
+    }
+    G2 mg;
+    memset(&mg, 0, sizeof(mg));
+    float wsum = 0.0f, m0 = 0.0f, m1 = 0.0f;
+    for (int i : members) {                                             /* :2808-2811 */
+      wsum = wsum + cand[i].weight;
+      m0 = m0 + cand[i].weight * cand[i].mean[0];
+      m1 = m1 + cand[i].weight * cand[i].mean[1];
+    }
+    if (wsum == 0.0f) break;                                            /* :2821-2822 */
+    mg.weight = wsum;
+    mg.mean[0] = m0 / wsum;                                             /* :2823-2829 */
+    mg.mean[1] = m1 / wsum;
+    float cv[4] = {0, 0, 0, 0};
+    for (int i : members) {                                             /* :2836-2872 */
+      float d[2] = {mg.mean[0] - cand[i].mean[0], mg.mean[1] - cand[i].mean[1]};
+      for (int j = 0; j < 2; ++j)
+        for (int k = 0; k < 2; ++k) cv[j * 2 + k] = cv[j * 2 + k] + cand[i].weight * (cand[i].cov[j * 2 + k] + d[j] * d[k]);
+      merged[i] = 1;
+    }
+    for (int j = 0; j < 4; ++j) mg.cov[j] = cv[j] / wsum;               /* :2874-2881 */
+    mg.cov[1] = (mg.cov[1] + mg.cov[2]) / 2.0f;                         /* force_symmetric_covariance, device_math.cuh:710-725 */
+    mg.cov[2] = mg.cov[1];
+    out.push_back(mg);
+  }
+}
+
+extern "C" int oracle_merge(const phdslam_config_t* cfg, const G2* in, int n, G2* out) {
+  std::vector<G2> cand(in, in + n), res;
+  merge_mixture(*cfg, cand, res);
+  memcpy(out, res.data(), res.size() * sizeof(G2));
+  return (int)res.size();
+}
+
+/* prepareUpdateInputs split (src/phdfilter.cu:3030-3070) */
+static void split_map(const phdslam_config_t& c, const Pose& pose, const std::vector<G2>& map, std::vector<G2>& in,
+                      std::vector<G2>& out2, std::vector<G2>& out1) {
+  for (const G2& f : map) {
+    int cls = classify(c, pose, f);
+    if (cls == 1) in.push_back(f);
+    else if (cls == 2) out2.push_back(f);
+    else out1.push_back(f);
+  }
+}
+
+extern "C" size_t oracle_update_terms(phd_oracle_t* o, const float* z, int M, int fields, G2* terms_out, size_t cap,
+                                      int* n_in_range_out, float* dlogw_out) {
+  if (M > 256) M = 256;
+  size_t k = 0;
+  for (size_t p = 0; p < o->states.size(); ++p) {
+    std::vector<G2> in, out2, out1;
+    split_map(o->cfg, o->states[p], o->maps[p], in, out2, out1);
+    UpdateOut u;
+    update_particle(o->cfg, o->states[p], in, z, M, fields, u);
+    if (n_in_range_out) n_in_range_out[p] = u.n_in;
+    if (dlogw_out) dlogw_out[p] = u.dlogw;
+    if (terms_out && k + u.terms.size() <= cap) memcpy(terms_out + k, u.terms.data(), u.terms.size() * sizeof(G2));
+    k += u.terms.size();
+  }
+  return k;
+}
+
+/* Canonical order-independent log-sum-exp: fixed-point accumulation of exp(w - max).
+ * Stands in for the host logSumExp (src/device_math.cuh:549-558), a sequential fp32 sum. */
+static float log_sum_exp_fx(const std::vector<float>& w) {
+  float mx = -FLT_MAX;
+  for (float v : w) mx = (v > mx) ? v : mx;
+  uint64_t acc = 0;
+  for (float v : w) acc += phd_fx_from_unit(phd_expf(v - mx), PHD_FX_WEIGHT_BITS);
+  float sumf = (float)((double)acc * (1.0 / (double)((uint64_t)1 << PHD_FX_WEIGHT_BITS)));
+  return phd_safe_log(sumf) + mx;
+}
+
+static void cphd_update_particle(phd_oracle_t* o, size_t p, const std::vector<G2>& in, const float* z, int M, int fields,
+                                 UpdateOut& u);
+
+/* phdUpdateSynth (src/phdfilter.cu:3336-3761) */
+extern "C" void oracle_update(phd_oracle_t* o, const float* z, int M, int fields) {
+  const phdslam_config_t& c = o->cfg;
+  if (M <= 0) return;           /* main.cpp:1258 */
+  if (M > 256) M = 256;         /* :3390-3394 */
+  const int n = (int)o->states.size();
+  std::vector<float> dlogw(n, 0.0f);
+#pragma omp parallel for schedule(dynamic, 8) num_threads(o->threads)
+  for (int p = 0; p < n; ++p) {
+    std::vector<G2> in, out2, out1;
+    split_map(c, o->states[p], o->maps[p], in, out2, out1);
+    UpdateOut u;
+    if (c.filter_type == 1)
+      cphd_update_particle(o, p, in, z, M, fields, u);
+    else
+      update_particle(c, o->states[p], in, z, M, fields, u);
+    dlogw[p] = u.dlogw;
+    /* pruneMap (:3120-3174): stable removal of terms with weight < minFeatureWeight (flags :2308-2319) */
+    std::vector<G2> cand;
+    for (const G2& t : u.terms)
+      if (!(t.weight < c.min_feature_weight)) cand.push_back(t);
+    /* recombine with the nearly-in-range features (:3227-3257) and merge (:3276) */
+    cand.insert(cand.end(), out2.begin(), out2.end());
+    std::vector<G2> mergedv;
+    merge_mixture(c, cand, mergedv);
+    /* re-append the far features (:3311-3318) */
+    mergedv.insert(mergedv.end(), out1.begin(), out1.end());
+    o->maps[p].swap(mergedv);
+  }
+  /* particle weights (:3735-3755) */
+  if (c.particle_weighting != 2)
+    for (int p = 0; p < n; ++p) o->weights[p] = o->weights[p] + dlogw[p];
+  float lse = log_sum_exp_fx(o->weights);
+  for (int p = 0; p < n; ++p) o->weights[p] = o->weights[p] - lse;
+}
+
+/* ------------------------------------------------------------------------- */
+/* state extraction                                                           */
+/* ------------------------------------------------------------------------- */
+
+/* recoverSlamState (src/main.cpp:318-388) + nEff (main.cpp:1281-1284).  Sums over particles use the
+ * fixed-point encodings of phd_detmath.h so they do not depend on summation order / GPU count. */
+extern "C" void oracle_estimate(phd_oracle_t* o, phdslam_estimate_t* out) {
+  const int n = (int)o->states.size();
+  int64_t acc[6] = {0, 0, 0, 0, 0, 0};
+  uint64_t e2 = 0;
+  float maxw = -FLT_MAX;
+  int max_idx = -1;
+  for (int i = 0; i < n; ++i) {
+    float w = o->weights[i];
+    float ew = phd_expf(w);                                         /* REAL exp_weight = exp(weights[i]) */
+    const float* s = &o->states[i].px;
+    for (int k = 0; k < 6; ++k) acc[k] += phd_fx_from_prod(ew, s[k], PHD_FX_POSE_BITS);
+    e2 += phd_fx_from_unit(phd_expf(2.0f * w), PHD_FX_NEFF_BITS);   /* nEff += exp(2*weights[i]) */
+    if (w > maxw) { maxw = w; max_idx = i; }                        /* main.cpp:349-356, strict > */
+  }
+  float* e = &out->expected_pose.px;
+  const double inv = 1.0 / (double)((uint64_t)1 << PHD_FX_POSE_BITS);
+  if (n > 1) {
+    for (int k = 0; k < 6; ++k) e[k] = (float)((double)acc[k] * inv);
+  } else {
+    out->expected_pose = o->states[0];                              /* main.cpp:381-387 */
+    max_idx = 0;
+  }
+  out->map_particle = max_idx;
+  out->max_log_weight = maxw;
+  double s2 = (double)e2 * (1.0 / (double)((uint64_t)1 << PHD_FX_NEFF_BITS));
+  out->neff = (float)(1.0 / s2 / (double)n);                        /* nEff = 1.0/nEff/n_particles */
+}
+
+/* 2x2 Cholesky-based Mahalanobis of gm_reduce.cpp:31-38: L L^T = (Pa+Pb)/2, x = L^-1 d, |x|^2 */
+static float mahal_llt(const G2& a, const G2& b) {
+  float s00 = 0.5f * (a.cov[0] + b.cov[0]);
+  float s10 = 0.5f * (a.cov[1] + b.cov[1]);
+  float s11 = 0.5f * (a.cov[3] + b.cov[3]);
+  float d0 = a.mean[0] - b.mean[0], d1 = a.mean[1] - b.mean[1];
+  float l00 = sqrtf(s00);
+  float l10 = s10 / l00;
+  float l11 = sqrtf(s11 - l10 * l10);
+  float x0 = d0 / l00;
+  float x1 = (d1 - l10 * x0) / l11;
+  return x0 * x0 + x1 * x1;
+}
+
+/* reduceGaussianMixture<Gaussian2D> (src/gm_reduce.cpp:57-134).  std::sort is not stable in the
+ * reference; canonical order: weight descending, ties by original index. */
+static void reduce_mixture(const std::vector<G2>& in, float min_distance, std::vector<G2>& out) {
+  const int n = (int)in.size();
+  std::vector<int> order(n);
+  for (int i = 0; i < n; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return in[a].weight > in[b].weight; });
+  std::vector<char> gone(n, 0);
+  std::vector<int> mergel;
+  for (int oi = 0; oi < n; ++oi) {
+    int s = order[oi];
+    if (gone[s]) continue;
+    gone[s] = 1;
+    const G2& mx = in[s];
+    mergel.clear();
+    for (int oj = oi + 1; oj < n; ++oj) {                            /* :86-101 */
+      int t = order[oj];
+      if (gone[t]) continue;
+      if (mahal_llt(mx, in[t]) < min_distance) { mergel.push_back(t); gone[t] = 1; }
+    }
+    G2 mg = mx;                                                      /* :104-110 */
+    float w = mx.weight;
+    float m0 = mx.mean[0] * mx.weight, m1 = mx.mean[1] * mx.weight;
+    for (int t : mergel) {
+      m0 = m0 + in[t].weight * in[t].mean[0];
+      m1 = m1 + in[t].weight * in[t].mean[1];
+      w = w + in[t].weight;
+    }
+    mg.weight = w;
+    mg.mean[0] = m0 / w;
+    mg.mean[1] = m1 / w;
+    float d0 = mg.mean[0] - mx.mean[0], d1 = mg.mean[1] - mx.mean[1];   /* :111-113 */
+    float cv[4];
+    cv[0] = mx.weight * (mx.cov[0] + d0 * d0);
+    cv[1] = mx.weight * (mx.cov[1] + d1 * d0);
+    cv[2] = mx.weight * (mx.cov[2] + d0 * d1);
+    cv[3] = mx.weight * (mx.cov[3] + d1 * d1);
+    for (int t : mergel) {                                            /* :115-119 */
+      d0 = mg.mean[0] - in[t].mean[0];
+      d1 = mg.mean[1] - in[t].mean[1];
+      cv[0] = cv[0] + in[t].weight * (in[t].cov[0] + d0 * d0);
+      cv[1] = cv[1] + in[t].weight * (in[t].cov[1] + d1 * d0);
+      cv[2] = cv[2] + in[t].weight * (in[t].cov[2] + d0 * d1);
+      cv[3] = cv[3] + in[t].weight * (in[t].cov[3] + d1 * d1);
+    }
+    for (int k = 0; k < 4; ++k) mg.cov[k] = cv[k] / w;               /* :120 */
+    out.push_back(mg);
+  }
+}
+
+extern "C" int oracle_reduce_mixture(const G2* in, int n, float min_distance, G2* out) {
+  std::vector<G2> v(in, in + n), r;
+  reduce_mixture(v, min_distance, r);
+  memcpy(out, r.data(), r.size() * sizeof(G2));
+  return (int)r.size();
+}
+
+/* which = 1: MAP map (main.cpp:344-361); which = 2: EAP map, computeExpectedMap (main.cpp:290-316) */
+extern "C" int oracle_map_estimate(phd_oracle_t* o, int which, G2* out, int cap) {
+  std::vector<G2> res;
+  if (which == 1) {
+    phdslam_estimate_t e;
+    oracle_estimate(o, &e);
+    res = o->maps[e.map_particle];
+  } else {
+    std::vector<G2> concat;
+    for (size_t p = 0; p < o->maps.size(); ++p) {
+      float ew = phd_expf(o->weights[p]);
+      for (G2 g : o->maps[p]) {
+        g.weight = g.weight * ew;                                    /* map[i].weight *= exp(weights[n]) */
+        concat.push_back(g);
+      }
+    }
+    if (!concat.empty()) reduce_mixture(concat, o->cfg.min_separation, res);
+  }
+  int n = (int)std::min<size_t>(res.size(), (size_t)cap);
+  memcpy(out, res.data(), n * sizeof(G2));
+  return (int)res.size();
+}
+
+/* ------------------------------------------------------------------------- */
+/* resampling                                                                 */
+/* ------------------------------------------------------------------------- */
+
+/* resampleParticles (src/main.cpp:453-501) + SynthSLAM::copy_particles (src/slamtypes.h:313-333).
+ * HEAD is *stratified*: one uniform is drawn and discarded, then a fresh one per offspring.
+ *   literal   : the reference's sequential double CDF walk, verbatim semantics.
+ *   canonical : integer CDF of Q40 weights; ancestor(j) = min{ i : C_i > floor(r_j * C_total) }.
+ *               Order-independent, hence identical for any GPU count; agrees with `literal`
+ *               except when r_j falls within ~1e-12 of a CDF step (tests/test_oracle_kat.py). */
+extern "C" void oracle_resample(phd_oracle_t* o, int n_new, const double* uniforms, int literal, int* ancestors_out) {
+  const phdslam_config_t& c = o->cfg;
+  const int n = (int)o->states.size();
+  if (n_new < 0) n_new = n;
+  std::vector<int> idx(n_new, 0);
+  const double interval = 1.0 / (double)n_new;
+  unsigned call = o->resample_calls++;
+  auto draw = [&](int j) -> double {
+    if (uniforms) return (c.resample_mode == 1) ? uniforms[0] : uniforms[1 + j];
+    uint32_t ctr = (c.resample_mode == 1) ? 0u : (uint32_t)j;
+    phd_philox4_t r = phd_philox4x32_10(ctr, call, PHD_STREAM_RESAMPLE, 0u, (uint32_t)c.seed, (uint32_t)(c.seed >> 32));
+    return phd_u01d(r.v[0], r.v[1]);
+  };
+  if (literal) {
+    double cdf = (double)expf(o->weights[0]);
+    int i = 0;
+    for (int j = 0; j < n_new; ++j) {
+      double r = j * interval + draw(j) * interval;
+      while (r > cdf) {
+        i++;
+        if (i >= n) {                                                /* :475-494 overflow guard */
+          double mw = -1;
+          int mi = -1;
+          for (int k = 0; k < n; ++k)
+            if ((double)expf(o->weights[k]) > mw) { mw = (double)expf(o->weights[k]); mi = k; }
+          i = mi;
+          cdf = 2;
+          break;
+        }
+        cdf += (double)expf(o->weights[i]);
+      }
+      idx[j] = i;
+    }
+  } else {
+    std::vector<uint64_t> cdf(n);
+    uint64_t run = 0;
+    for (int i = 0; i < n; ++i) {
+      run += phd_fx_from_unit(phd_expf(o->weights[i]), PHD_FX_CDF_BITS);
+      cdf[i] = run;
+    }
+    const uint64_t total = run;
+    for (int j = 0; j < n_new; ++j) {
+      double r = (double)j * interval + draw(j) * interval;
+      double t = floor(r * (double)total);
+      uint64_t R = (t <= 0.0) ? 0 : (uint64_t)t;
+      if (R >= total) R = total - 1;
+      idx[j] = (int)(std::upper_bound(cdf.begin(), cdf.end(), R) - cdf.begin());
+    }
+  }
+  /* copy_particles: deep copy, every weight = -log(N_new), resample_idx = indices */
+  std::vector<Pose> ns(n_new);
+  std::vector<std::vector<G2>> nm(n_new);
+  std::vector<std::vector<float>> nc(n_new);
+  for (int j = 0; j < n_new; ++j) {
+    ns[j] = o->states[idx[j]];
+    nm[j] = o->maps[idx[j]];
+    nc[j] = o->card[idx[j]];
+  }
+  o->states.swap(ns);
+  o->maps.swap(nm);
+  o->card.swap(nc);
+  o->weights.assign(n_new, -phd_logf((float)n_new));
+  o->resample_idx = idx;
+  if (ancestors_out) memcpy(ancestors_out, idx.data(), n_new * sizeof(int));
+}
+
+/* run_synth loop body (src/main.cpp:1231-1297) */
+extern "C" void oracle_step(phd_oracle_t* o, int step_index, const float* control, const float* z, int M, int fields,
+                            phdslam_estimate_t* est_out, int* resampled_out) {
+  const phdslam_config_t& c = o->cfg;
+  if (step_index > 0)
+    for (int i = 0; i < c.subdivide_predict; ++i) oracle_predict(o, control, nullptr);   /* :1244-1255 */
+  if (M > 0) oracle_update(o, z, M, fields);                                             /* :1258-1272 */
+  phdslam_estimate_t e;
+  oracle_estimate(o, &e);                                                                /* :1274, :1281-1284 */
+  int n = (int)o->states.size();
+  int res = 0;
+  if ((e.neff <= c.resample_threshold && M > 0) || n > 5 * c.n_particles) {              /* :1286 */
+    oracle_resample(o, c.n_particles, nullptr, 0, nullptr);
+    res = 1;
+  } else {
+    for (int i = 0; i < n; ++i) o->resample_idx[i] = i;                                  /* :1293-1296 */
+  }
+  if (est_out) *est_out = e;
+  if (resampled_out) *resampled_out = res;
+}
+
+/* ------------------------------------------------------------------------- */
+/* CPHD (spec: commented kernels src/phdfilter.cu:701-748,1430-1822; live older forms in       */
+/* src/phdfilter.cu.bak:369-448,518-545,779-791,1058-1504,2473-2544)                            */
+/* ------------------------------------------------------------------------- */
+
+/* Elementary symmetric functions e_0..e_n of `roots` (Vieta recursion of computeEsfKernel,
+ * src/phdfilter.cu:1553-1576, evaluated in double so it is safe for M up to 256). */
+extern "C" void oracle_esf(const double* roots, int n, double* out) {
+  out[0] = 1.0;
+  for (int i = 1; i <= n; ++i) out[i] = 0.0;
+  for (int m = 0; m < n; ++m)
+    for (int k = m + 1; k >= 1; --k) out[k] = out[k] + roots[m] * out[k - 1];
+}
+
+static void cphd_update_particle(phd_oracle_t* o, size_t p, const std::vector<G2>& in, const float* z, int M, int fields,
+                                 UpdateOut& u) {
+  (void)o; (void)p; (void)in; (void)z; (void)M; (void)fields; (void)u;
+  fprintf(stderr, "oracle: CPHD update not built yet\n");
+  abort();
+}
+
+/* ------------------------------------------------------------------------- */
+/* test hooks for the shared deterministic math                               */
+/* ------------------------------------------------------------------------- */
+extern "C" void oracle_detmath(int fn, const float* x, const float* y, float* out, float* out2, int n) {
+  for (int i = 0; i < n; ++i) {
+    switch (fn) {
+      case 0: out[i] = phd_expf(x[i]); break;
+      case 1: out[i] = phd_logf(x[i]); break;
+      case 2: out[i] = phd_atan2f(y[i], x[i]); break;
+      case 3: phd_sincosf(x[i], &out[i], &out2[i]); break;
+      case 4: out[i] = phd_wrap_angle(x[i]); break;
+      case 5: out[i] = phd_tanf(x[i]); break;
+      case 6: out[i] = phd_safe_log(x[i]); break;
+      default: out[i] = 0.0f;
+    }
+  }
+}
+extern "C" void oracle_philox(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned* out4) {
+  phd_philox4_t r = phd_philox4x32_10(c0, c1, c2, c3, k0, k1);
+  for (int i = 0; i < 4; ++i) out4[i] = r.v[i];
+}

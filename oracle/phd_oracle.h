@@ -1,0 +1,80 @@
+/*
+ * phd_oracle.h -- CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * A scalar C++ restatement of the reference's RB-PHD-SLAM filter step
+ * (cheesinglee/cuda-PHDSLAM), function by function, each citing the reference
+ * file:line it follows.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this library; the product
+ * (libphdslam.so) never does.
+ *
+ * PARITY PIN: the reference ships no tests, golden vectors or fixtures
+ *  and its named CPU path (src/scphd_cpu.cpp) is an empty stub.
+ * The pin is therefore (a) oracle/_ref: the reference's own CUDA kernels
+ * compiled unmodified for the CPU through a SIMT shim (oracle/ref_build.sh,
+ * built only where /root/reference exists) and compared with this oracle in
+ * tests/test_oracle_vs_ref.py, with the outputs committed under tests/golden/;
+ * (b) closed-form known-answer tests (tests/test_oracle_kat.py).
+ *
+ * Arithmetic: fp32 in the reference's operation order, with the transcendental
+ * functions of include/phd_detmath.h so that results are bit-reproducible on the
+ * GPU.  Deviations from the reference's literal arithmetic are listed in
+ * DESIGN.md section "Canonical arithmetic".
+ */
+#ifndef PHD_ORACLE_H
+#define PHD_ORACLE_H
+
+#include "../include/phdslam.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct phd_oracle phd_oracle_t;
+
+phd_oracle_t* oracle_create(const phdslam_config_t* cfg);
+void oracle_destroy(phd_oracle_t* o);
+void oracle_set_config(phd_oracle_t* o, const phdslam_config_t* cfg);
+void oracle_set_threads(phd_oracle_t* o, int n_threads);
+
+int oracle_n_particles(const phd_oracle_t* o);
+void oracle_get_poses(const phd_oracle_t* o, phdslam_pose_t* out);
+void oracle_set_poses(phd_oracle_t* o, const phdslam_pose_t* in);
+void oracle_get_log_weights(const phd_oracle_t* o, float* out);
+void oracle_set_log_weights(phd_oracle_t* o, const float* in);
+void oracle_get_map_sizes(const phd_oracle_t* o, int* out);
+void oracle_get_maps(const phd_oracle_t* o, phdslam_gaussian2d_t* out);
+void oracle_set_maps(phd_oracle_t* o, const int* sizes, const phdslam_gaussian2d_t* in);
+void oracle_get_resample_idx(const phd_oracle_t* o, int* out);
+void oracle_get_cardinalities(const phd_oracle_t* o, float* out);
+void oracle_set_cardinalities(phd_oracle_t* o, const float* in);
+
+/* phdPredict, one sub-step (src/phdfilter.cu:1080-1257) */
+void oracle_predict(phd_oracle_t* o, const float* control, const double* draws);
+/* phdUpdateSynth (src/phdfilter.cu:3336-3761) */
+void oracle_update(phd_oracle_t* o, const float* z, int M, int fields);
+/* dense update terms only (preUpdateSynthKernel + phdUpdateKernel), no state change */
+size_t oracle_update_terms(phd_oracle_t* o, const float* z, int M, int fields, phdslam_gaussian2d_t* terms_out,
+                           size_t cap, int* n_in_range_out, float* dlogw_out);
+/* recoverSlamState + nEff (src/main.cpp:318-388,1281-1284) */
+void oracle_estimate(phd_oracle_t* o, phdslam_estimate_t* out);
+int oracle_map_estimate(phd_oracle_t* o, int which, phdslam_gaussian2d_t* out, int cap);
+/* resampleParticles (src/main.cpp:453-501); mode 0 = canonical integer CDF, 1 = literal double CDF walk */
+void oracle_resample(phd_oracle_t* o, int n_new, const double* uniforms, int literal, int* ancestors_out);
+/* run_synth loop body (src/main.cpp:1231-1297) */
+void oracle_step(phd_oracle_t* o, int step_index, const float* control, const float* z, int M, int fields,
+                 phdslam_estimate_t* est_out, int* resampled_out);
+
+/* pieces exposed for known-answer tests */
+float oracle_mahalanobis(const phdslam_gaussian2d_t* a, const phdslam_gaussian2d_t* b);
+float oracle_hellinger(const phdslam_gaussian2d_t* a, const phdslam_gaussian2d_t* b);
+int oracle_merge(const phdslam_config_t* cfg, const phdslam_gaussian2d_t* in, int n, phdslam_gaussian2d_t* out);
+int oracle_reduce_mixture(const phdslam_gaussian2d_t* in, int n, float min_distance, phdslam_gaussian2d_t* out);
+float oracle_warp_sum(const float* v, int n);
+void oracle_detmath(int fn, const float* x, const float* y, float* out, float* out2, int n);
+void oracle_philox(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned* out4);
+void oracle_esf(const double* roots, int n, double* out /* n+1 */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,262 @@
+"""Parity of the sm_100a path (through the C-ABI of libphdslam.so) against the CPU oracle on identical
+seeded inputs.  Bar (BASELINE.json north_star): component counts and ancestor indices bit-exact;
+poses, map means, covariances and log-weights within 1e-4 relative.  Because both sides implement the
+same canonical fp32 arithmetic (include/phd_detmath.h) the float outputs are in fact expected to be
+bit-identical; tests assert the 1e-4 bar and report bit-exactness separately."""
+import os
+
+import numpy as np
+import pytest
+
+import phdslam_b200 as P
+from phdslam_b200 import scene as S
+from oracle import oracle as O
+from conftest import DATA, GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4   # north_star tolerance for floating-point outputs
+
+
+def close(a, b, what, rtol=RTOL, atol=1e-7):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    err = np.abs(a - b) - (atol + rtol * np.abs(b))
+    assert (err <= 0).all(), "%s: max rel err %.3g" % (what, np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-30)))
+
+
+def assert_gaussians(g, o, what):
+    assert len(g) == len(o), what
+    for f in ("weight", "mean", "cov"):
+        close(g[f], o[f], what + "." + f)
+
+
+def pair(cfg, sc=None):
+    g, o = P.PhdSlam(cfg), O.Oracle(cfg)
+    if sc is not None:
+        S.load_scene(g, sc)
+        S.load_scene(o, sc)
+    return g, o
+
+
+def assert_state_equal(g, o, what=""):
+    gs, gm = g.get_maps()
+    os_, om = o.get_maps()
+    assert (gs == os_).all(), what + " component counts differ"           # bit-exact
+    assert_gaussians(gm, om, what + " maps")
+    close(g.log_weights, o.log_weights, what + " log-weights", atol=1e-6)
+    gp, op = g.poses, o.poses
+    for f in gp.dtype.names:
+        close(gp[f], op[f], what + " pose." + f, atol=1e-6)
+    return (gm.tobytes() == om.tobytes()) and (g.log_weights.tobytes() == o.log_weights.tobytes())
+
+
+@pytest.mark.parametrize("Pn,C,M,near,far", [(8, 1, 1, 0, 0), (32, 48, 24, 7, 9), (16, 100, 37, 3, 0), (4, 0, 5, 0, 4)])
+def test_dense_update_terms(Pn, C, M, near, far):
+    """rows 3-6 of SURVEY 8(a): in-range split, births, EKF pre-update, PHD update, particle log-weight"""
+    cfg = S.scene_config(Pn, C, M, max_components=256)
+    sc = S.make_scene(Pn, C, M, seed=11, n_near=near, n_far=far)
+    g, o = pair(cfg, sc)
+    gt, gn, gd = g.update_terms(sc["Z"])
+    ot, on, od = o.update_terms(sc["Z"])
+    assert (gn == on).all() and (gn == C).all()
+    assert_gaussians(gt, ot, "update terms")
+    close(gd, od, "particle log-weight increment", atol=1e-5)
+    # prune decisions (w < min_feature_weight) must agree exactly
+    assert ((gt["weight"] < cfg.min_feature_weight) == (ot["weight"] < cfg.min_feature_weight)).all()
+    assert gt.tobytes() == ot.tobytes(), "dense terms are expected to be bit-identical"
+    assert gd.tobytes() == od.tobytes()
+
+
+@pytest.mark.parametrize("weighting,metric", [(0, 0), (1, 0), (0, 1)])
+def test_full_update_prune_merge_weights(weighting, metric):
+    """rows 7-9: prune, merge (Mahalanobis / Hellinger), weight update + normalisation"""
+    Pn, C, M = 48, 60, 20
+    cfg = S.scene_config(Pn, C, M, max_components=256, particle_weighting=weighting, distance_metric=metric,
+                         min_separation=10.0 if metric == 0 else 0.6)
+    sc = S.make_scene(Pn, C, M, seed=3, n_near=5, n_far=6)
+    g, o = pair(cfg, sc)
+    g.phdUpdateSynth(sc["Z"])
+    o.phdUpdateSynth(sc["Z"])
+    assert assert_state_equal(g, o, "after update"), "state expected bit-identical"
+    # second update on the merged maps (maps now contain merged + re-appended far components)
+    Z2 = S.make_scene(Pn, C, M, seed=4)["Z"]
+    g.phdUpdateSynth(Z2)
+    o.phdUpdateSynth(Z2)
+    assert assert_state_equal(g, o, "after second update")
+    ge, oe = g.recoverSlamState(), o.recoverSlamState()
+    close(ge.pose, oe.pose, "expected pose", atol=1e-6)
+    close(ge.neff, oe.neff, "nEff")
+    assert ge.map_particle == oe.map_particle
+
+
+def test_batched_update_matches_single_batch():
+    Pn, C, M = 64, 40, 16
+    sc = S.make_scene(Pn, C, M, seed=8, n_near=2, n_far=2)
+    cfg1 = S.scene_config(Pn, C, M, max_components=128)
+    per_particle = (C * (M + 1) + M + 8) * 28
+    cfg2 = S.scene_config(Pn, C, M, max_components=128, update_buffer_bytes=str(per_particle * 10))
+    g1, g2 = P.PhdSlam(cfg1), P.PhdSlam(cfg2)
+    for g in (g1, g2):
+        S.load_scene(g, sc)
+        g.phdUpdateSynth(sc["Z"])
+    s1, m1 = g1.get_maps()
+    s2, m2 = g2.get_maps()
+    assert (s1 == s2).all() and m1.tobytes() == m2.tobytes()
+    assert g1.log_weights.tobytes() == g2.log_weights.tobytes()
+
+
+@pytest.mark.parametrize("motion", [1, 0])
+def test_predict(motion):
+    """rows 1-2: Ackerman / constant-velocity prediction with injected draws and with the Philox RNG"""
+    n = 1000
+    cfg = S.scene_config(n, 1, 1, motion_type=motion, acc_x=0.5, acc_y=0.2, acc_yaw=0.05, initial_vx=2.0,
+                         initial_vyaw=0.2, seed="1234")
+    g, o = pair(cfg)
+    rng = np.random.default_rng(0)
+    poses = np.zeros(n, dtype=P.POSE_DTYPE)
+    for f in poses.dtype.names:
+        poses[f] = rng.normal(0, 2, n)
+    g.poses = poses
+    o.poses = poses
+    u = np.float32([2.2, -0.15])
+    draws = rng.normal(0, 1, n * (2 if motion == 1 else 3))
+    g.phdPredict(u, draws)
+    o.phdPredict(u, draws)
+    for f in poses.dtype.names:
+        close(g.poses[f], o.poses[f], "injected " + f, atol=1e-6)
+    assert g.poses.tobytes() == o.poses.tobytes()
+    for k in range(3):   # counter-based RNG: same stream on both sides
+        g.phdPredict(u)
+        o.phdPredict(u)
+    assert g.poses.tobytes() == o.poses.tobytes()
+    assert np.abs(g.poses["px"] - poses["px"]).max() > 1e-3
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_resample_ancestors_bit_exact(mode):
+    """row 12: ancestor indices are bit-exact; maps, poses and cardinalities follow their ancestors"""
+    Pn, C, M = 512, 12, 6
+    cfg = S.scene_config(Pn, C, M, max_components=64, resample_mode=mode, seed="99")
+    sc = S.make_scene(Pn, C, M, seed=21)
+    g, o = pair(cfg, sc)
+    g.phdUpdateSynth(sc["Z"])
+    o.phdUpdateSynth(sc["Z"])
+    u = np.random.default_rng(5).uniform(0, 1, Pn + 1)
+    ga = g.resampleParticles(u)
+    oa = o.resampleParticles(u)
+    assert (ga == oa).all()
+    assert len(np.unique(ga)) < Pn          # the scene's weights are not uniform
+    assert assert_state_equal(g, o, "after resample")
+    assert (g.resample_idx == o.resample_idx).all()
+    # second round with the on-device Philox uniforms
+    g.phdUpdateSynth(sc["Z"])
+    o.phdUpdateSynth(sc["Z"])
+    ga = g.resampleParticles()
+    oa = o.resampleParticles()
+    assert (ga == oa).all()
+    assert assert_state_equal(g, o, "after philox resample")
+
+
+def test_step_loop_on_bundled_ackerman_data():
+    """config #1 shape: run_synth loop (predict, update, estimate, nEff, resample) on the bundled Ackerman
+    scene; every step's counts, ancestors and estimates must match the oracle"""
+    cfg = P.load_config(os.path.join(GOLDEN, "config_ackerman.cfg"))
+    cfg.set(n_particles=256, max_components=256, seed="7")
+    Z = P.load_measurements(os.path.join(DATA, "measurements_synth_ackerman.txt"))
+    U = P.load_controls(os.path.join(DATA, "controls_synth.txt"))
+    g, o = pair(cfg)
+    n_res = 0
+    for k in range(40):
+        u = U[k - 1] if k > 0 else None
+        ge, gr = g.step(k, u, Z[k])
+        oe, orr = o.step(k, u, Z[k])
+        assert gr == orr, "resampling decision differs at step %d" % k
+        n_res += gr
+        close(ge.pose, oe.pose, "expected pose step %d" % k, atol=1e-6)
+        close(ge.neff, oe.neff, "nEff step %d" % k)
+        assert (g.map_sizes == o.map_sizes).all(), "component counts differ at step %d" % k
+        assert (g.resample_idx == o.resample_idx).all(), "ancestors differ at step %d" % k
+    assert n_res > 0
+    assert_state_equal(g, o, "after 40 steps")
+
+
+def test_step_loop_constant_velocity_data():
+    """config #2 shape (reduced particle count for the CPU oracle): CV motion model on measurements_synth_cv"""
+    cfg = P.load_config(os.path.join(GOLDEN, "config_ackerman.cfg"))
+    cfg.set(motion_type=0, n_particles=128, max_components=256, initial_vx=2.0, initial_vyaw=0.2, acc_x=0.5, acc_y=0.5,
+            acc_yaw=0.087, dt=0.02, max_range=10.0, std_range=1.0, std_bearing=0.0349, seed="3")
+    Z = P.load_measurements(os.path.join(DATA, "measurements_synth_cv.txt"))
+    g, o = pair(cfg)
+    for k in range(20):
+        ge, gr = g.step(k, None, Z[k])
+        oe, orr = o.step(k, None, Z[k])
+        assert gr == orr
+        assert (g.map_sizes == o.map_sizes).all()
+    assert_state_equal(g, o, "after 20 CV steps")
+
+
+def test_edge_cases():
+    # empty measurement set: no-op (main.cpp:1258)
+    cfg = S.scene_config(8, 4, 2, max_components=64)
+    sc = S.make_scene(8, 4, 2, seed=1)
+    g, o = pair(cfg, sc)
+    g.phdUpdateSynth(np.zeros((0, 2), np.float32))
+    assert assert_state_equal(g, o, "empty Z")
+    # empty maps: only births survive (weight = w_b/(w_b+kappa))
+    g2, o2 = pair(cfg)
+    g2.phdUpdateSynth(sc["Z"])
+    o2.phdUpdateSynth(sc["Z"])
+    assert assert_state_equal(g2, o2, "empty map")
+    assert (g2.map_sizes == 2).all()
+    # labelled measurements (fields=3) with labeled_measurements=1: dynamic labels give zero weight
+    cfg3 = S.scene_config(8, 4, 2, max_components=64, labeled_measurements=1, measurement_fields=3)
+    g3, o3 = pair(cfg3, sc)
+    Z3 = np.concatenate([sc["Z"], np.float32([[0], [1]])], 1)
+    g3.phdUpdateSynth(Z3)
+    o3.phdUpdateSynth(Z3)
+    assert assert_state_equal(g3, o3, "labelled")
+    # more than 256 measurements are truncated (src/phdfilter.cu:3390-3394)
+    Zbig = S.make_scene(8, 4, 300, seed=2)["Z"]
+    cfg4 = S.scene_config(8, 4, 256, max_components=512)
+    g4, o4 = pair(cfg4, sc)
+    g4.phdUpdateSynth(Zbig)
+    o4.phdUpdateSynth(Zbig)
+    assert assert_state_equal(g4, o4, "M > 256")
+
+
+def test_capacity_overflow_is_reported():
+    cfg = S.scene_config(4, 30, 40, max_components=32)
+    sc = S.make_scene(4, 30, 40, seed=1)
+    g = P.PhdSlam(cfg)
+    S.load_scene(g, sc)
+    with pytest.raises(P.PhdSlamError) as ei:
+        g.phdUpdateSynth(sc["Z"])      # 30 surviving components + 40 births > 32
+    assert ei.value.code == -3
+
+
+def test_properties_at_scale():
+    """size-independent properties on a scene too large for the oracle: weights normalised, counts bounded,
+    dense-term invariant sum_j w_detect + w_birth = 1 - kappa/norm sampled, resampling ancestors sorted"""
+    Pn, C, M = 4096, 64, 32
+    cfg = S.scene_config(Pn, C, M, max_components=256)
+    sc = S.make_scene(Pn, C, M, seed=2)
+    g = P.PhdSlam(cfg)
+    S.load_scene(g, sc)
+    terms, nin, dlw = g.update_terms(sc["Z"])
+    assert (nin == C).all()
+    T = C * (M + 1) + M
+    t = terms.reshape(Pn, T)[::257]
+    det = t[:, C:C + M * C]["weight"].reshape(-1, M, C).astype(np.float64).sum(2)
+    bw = t[:, C + M * C:]["weight"].astype(np.float64)
+    np.testing.assert_allclose(det + bw, 1 - cfg.clutter_density / (cfg.birth_weight / bw), rtol=1e-4, atol=1e-6)
+    g.phdUpdateSynth(sc["Z"])
+    w = g.log_weights.astype(np.float64)
+    assert abs(np.exp(w).sum() - 1) < 1e-4
+    sizes = g.map_sizes
+    assert sizes.min() >= C and sizes.max() <= C + M
+    anc = g.resampleParticles()
+    assert (np.diff(anc) >= 0).all() and anc.min() >= 0 and anc.max() < Pn
+    assert (g.map_sizes == sizes[anc]).all()
+    np.testing.assert_allclose(g.log_weights, -np.log(Pn), rtol=1e-6)
