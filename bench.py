@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py -- GM-PHD updates/s of the RB-PHD-SLAM filter step on B200 (driver contract).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one full filter step (predict + in-range split + GM-PHD update + prune/merge + weight update and
+normalisation + state estimate + resampling when nEff triggers it) over one synthetic scene of exactly
+P x C x M (particles x in-range components x measurements); one update = one (particle, component,
+measurement) detection term, so a step is exactly P*C*M updates.  The device state is restored to the same
+scene before every step (outside the timed region) so that all K steps do identical work.
+
+  value     whole-job updates/s, device-timed (CUDA events on the filter's stream) with the scene resident in HBM
+  e2e       the same metric through the C-ABI call phdslam_step() with HOST measurement / control buffers,
+            wall clock, including the host<->device copies the call performs
+  roofline  GM-PHD update kernel (update_dense_kernel): algorithmic bytes (28.99 B/update at
+            C=256, M=64) / its CUDA-event duration, against the measured HBM copy bandwidth
+  --impl reference  the CPU oracle (the reference's named CPU path src/scphd_cpu.cpp is an empty stub; its CUDA
+            path cannot be built or run without a GPU toolchain of 2012), all host threads, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "cuda-phdslam_b200"))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: the single-GPU configuration the updates/s metric is quoted on
+    "synthetic_65536x256x64_phd": dict(P=65536, C=256, M=64, max_components=384),
+    # smaller shapes for quick checks
+    "synthetic_8192x256x64_phd": dict(P=8192, C=256, M=64, max_components=384),
+    "synthetic_1024x64x32_phd": dict(P=1024, C=64, M=32, max_components=128),
+}
+DEFAULT_WORKLOAD = "synthetic_65536x256x64_phd"
+
+
+def alg_bytes_per_update(C, M):
+    """B_alg = [28*C + 28*(C*(M+1)+M) + 32] / (C*M)"""
+    return (28.0 * C + 28.0 * (C * (M + 1) + M) + 32.0) / (C * M)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def cpu_oracle_rate(wl, target_seconds=12.0, threads=None):
+    """Times the CPU oracle (all host threads) on a bounded particle sample of the same workload.
+    Returns (updates/s, cores, sample description, ms per sample step)."""
+    import phdslam_b200  # noqa: F401  (config helpers; no GPU use)
+    from phdslam_b200 import scene as S
+    from oracle import oracle as O
+    C, M = wl["C"], wl["M"]
+    threads = threads or os.cpu_count() or 1
+    Ps = max(threads, 8)
+    rate = None
+    for attempt in range(3):
+        cfg = S.scene_config(Ps, C, M, max_components=wl["max_components"])
+        sc = S.make_scene(Ps, C, M, seed=0)
+        o = O.Oracle(cfg, threads=threads)
+        S.load_scene(o, sc)
+        t0 = time.perf_counter()
+        o.step(1, np.float32([1.0, 0.05]), sc["Z"])
+        dt = time.perf_counter() - t0
+        rate = Ps * C * M / dt
+        o.close()
+        if dt >= 0.4 * target_seconds or attempt == 2:
+            break
+        Ps = int(min(max(Ps * target_seconds / max(dt, 1e-3) * 0.8, Ps * 2), 65536))
+    sample = "%d of the workload's particles (C=%d, M=%d), one full filter step, %d OpenMP threads, %.2f s" % (Ps, C, M, threads, dt)
+    return rate, threads, sample, dt * 1e3, Ps
+
+
+def run_reference(args, wl):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    C, M = wl["C"], wl["M"]
+    from phdslam_b200 import scene as S
+    from oracle import oracle as O
+    threads = os.cpu_count() or 1
+    # size the per-step sample so that warmup+steps finish within a few minutes
+    r0, _, _, _, _ = cpu_oracle_rate(wl, target_seconds=3.0, threads=threads)
+    budget = 150.0 / max(args.steps + args.warmup, 1)
+    Ps = int(max(threads, min(wl["P"], r0 * min(budget, 20.0) / (C * M))))
+    cfg = S.scene_config(Ps, C, M, max_components=wl["max_components"])
+    sc = S.make_scene(Ps, C, M, seed=0)
+    times = []
+    for k in range(args.warmup + args.steps):
+        o = O.Oracle(cfg, threads=threads)
+        S.load_scene(o, sc)
+        t0 = time.perf_counter()
+        o.step(1, np.float32([1.0, 0.05]), sc["Z"])
+        dt = time.perf_counter() - t0
+        o.close()
+        if k >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = Ps * C * M / (ms * 1e-3)
+    sample = "%d of %d particles per step (C=%d, M=%d), full filter step, %d threads" % (Ps, wl["P"], C, M, threads)
+    line = {
+        "impl": "reference", "metric": "GM-PHD updates/s (particle x comp x meas)", "value": value, "unit": "updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "particles": wl["P"], "components": C, "measurements": M,
+                   "note": "CPU oracle port of the reference algorithm (its scphd_cpu.cpp is an empty stub); bounded sample"},
+        "cpu_baseline": {"value": value, "unit": "updates/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args, wl):
+    import torch
+    import phdslam_b200 as PS
+    from phdslam_b200 import scene as S
+    rank, world, local = dist_env()
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch N>1 with torch.distributed.run" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the filter has no CPU fallback (use --impl reference for the CPU oracle)")
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    P, C, M = wl["P"], wl["C"], wl["M"]
+    P_total = P * world                      # weak scaling: P particles per GPU
+    cfg = S.scene_config(P_total, C, M, max_components=wl["max_components"], seed="0")
+    filt = PS.PhdSlam(cfg, device=local)
+    if world > 1:
+        filt.dist_init(rank, world)
+    sc = S.make_scene(P, C, M, seed=rank)
+    sc["log_weights"][:] = -np.log(np.float32(P_total))
+    S.load_scene(filt, sc)
+    filt.snapshot()
+    Z = sc["Z"]
+    u = np.float32([1.0, 0.05])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        filt.synchronize()
+
+    stream = torch.cuda.ExternalStream(filt.stream, device=torch.device("cuda", local))
+    for _ in range(args.warmup):
+        filt.restore()
+        filt.step(1, u, Z)
+    barrier()
+    l0 = filt.timings().launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    dev_ms, wall_ms, upd_ms, mrg_ms, other = [], [], [], [], []
+    n_resampled = 0
+    for k in range(args.steps):
+        filt.restore()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        est, res = filt.step(1, u, Z)
+        e1.record(stream)
+        barrier()
+        t1 = time.perf_counter()
+        n_resampled += int(res)
+        dev_ms.append(e0.elapsed_time(e1))
+        wall_ms.append((t1 - t0) * 1e3)
+        t = filt.timings()
+        upd_ms.append(t.update_ms)
+        mrg_ms.append(t.merge_ms)
+        other.append((t.predict_ms, t.weights_ms, t.estimate_ms, t.resample_ms if res else 0.0))
+    clocks = sampler.stop() if rank == 0 else None
+    launches = filt.timings().launches - l0
+    # restore() launches no kernels (cudaMemcpyAsync only), so `launches` counts the timed steps' kernels
+    dev_total, wall_total = float(np.sum(dev_ms)), float(np.sum(wall_ms))
+    if world > 1:
+        tt = torch.tensor([dev_total, wall_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_total, wall_total = float(tt[0]), float(tt[1])
+    if rank != 0:
+        return
+    updates_per_step = float(P_total) * C * M
+    ms_per_step = dev_total / args.steps
+    value = updates_per_step / (ms_per_step * 1e-3)
+    e2e_value = updates_per_step / (wall_total / args.steps * 1e-3)
+    peak, peak_src = measured_peaks()
+    upd = float(np.mean(upd_ms))
+    balg = alg_bytes_per_update(C, M)
+    achieved = (float(P) * C * M * balg) / (upd * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(args.workload, {}).get("update_dense_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    cpu_rate, cores, sample, _, _ = cpu_oracle_rate(wl) if not args.no_cpu_baseline else (None, 0, "skipped", 0, 0)
+    oth = np.mean(np.array(other), axis=0)
+    line = {
+        "metric": "GM-PHD updates/s (particle x comp x meas)", "value": value, "unit": "updates/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "particles_per_gpu": P, "components": C, "measurements": M,
+                   "filter": "PHD", "update_mode": "dense (reference-equivalent update terms materialised in HBM)",
+                   "cache": "inputs larger than L2 (map %.0f MB + dense update terms %.1f GB per step)"
+                            % (P * C * 24 / 1e6, P * (C * (M + 1) + M) * 28 / 1e9),
+                   "steps_that_resampled": n_resampled},
+        "filter_steps_per_s": 1e3 / ms_per_step,
+        "phase_ms": {"update": upd, "merge": float(np.mean(mrg_ms)), "predict": float(oth[0]), "weights": float(oth[1]),
+                     "estimate": float(oth[2]), "resample": float(oth[3])},
+        "roofline": {"bound": "hbm", "kernel": "update_dense_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_update": balg, "kernel_ms": upd},
+        "cpu_baseline": {"value": cpu_rate, "unit": "updates/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": 3 * 256 * 4 + 8, "d2h_bytes_per_step": 3 * 128,
+                "ms_per_step": wall_total / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

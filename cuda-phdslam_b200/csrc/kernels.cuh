@@ -540,32 +540,40 @@ __global__ void __launch_bounds__(UPD_THREADS) update_dense_kernel(UpdArgs a) {
 /* prune + merge: pruneMap + mergeAndCopyMaps + phdUpdateMergeKernel                             */
 /* (reference src/phdfilter.cu:3120-3333, 2707-2898; computeMahalDist device_math.cuh:309-325)    */
 /*                                                                                               */
-/* One CTA (4 warps) per particle.  Survivors of the prune (weight >= minFeatureWeight) are       */
-/* compacted from the dense weight plane into shared memory in term order, followed by the        */
-/* "nearly in range" (class 2) components.  Candidates are ranked once by (weight desc, index      */
-/* asc) with a bitonic sort -- weights of unmerged candidates never change, so the greedy arg-max  */
-/* of every round is the next unmerged entry of that ranking.  Each round: all threads evaluate    */
-/* the distance of their candidates to the seed and publish membership as ballot words; warp 0     */
-/* then accumulates the moment-matched merge over the members in ascending index order (the        */
-/* canonical order of the oracle).                                                                */
+/* One WARP per particle, no block-level barriers.  The reference re-scans every update term of   */
+/* the particle three times per output component; here                                            */
+/*  A. the warp streams the dense weight plane once, compacts the survivors of the prune          */
+/*     (weight >= minFeatureWeight, term order preserved) into 32-byte records in a global        */
+/*     scratch (L1/L2 resident), then appends the "nearly in range" components;                   */
+/*  B. candidates are ranked once by (weight desc, index asc) with a warp bitonic sort --         */
+/*     weights of unmerged candidates never change, so every greedy arg-max is the next           */
+/*     unmerged entry of that ranking;                                                            */
+/*  C. candidates are binned into a uniform grid whose cell size is the canonical gate radius     */
+/*     (see oracle merge_gate_radius2), so a seed only examines its 3x3 cell neighbourhood;        */
+/*  D. each round evaluates the gate + Mahalanobis/Hellinger distance for those few candidates,   */
+/*     then accumulates the moment-matched merge over the members in ascending index order (the   */
+/*     canonical order of the oracle).                                                            */
 /* =========================================================================================== */
 #define MRG_THREADS 128
 #define MRG_WARPS (MRG_THREADS / 32)
+#define MRG_GMAX 16
 
 struct MrgArgs {
   const float* dense; const unsigned long long* toff; unsigned long long tbase;
-  const int* n_in; int M, n, p0;
+  const int* n_in; int M, n, p0, p1;
   const float* map_in; const int* count_in; const uint8_t* cls;
   float* map_out; int* count_out;
+  float4* cand;                        /* scratch: [p1-p0][Smax][2] */
   Reductions* red;
   int Smax;
   DevCfg c;
 };
 
-static inline size_t merge_smem_bytes(int Smax) {
-  /* 7 candidate planes + 64-bit sort keys + membership/alive words */
-  return (size_t)Smax * (7 * 4 + 8) + (size_t)(Smax / 32 + 1) * 2 * 4 + 64;
+__host__ __device__ static inline size_t merge_warp_smem_bytes(int Smax) {
+  /* region A: float w[Smax] during the sort, then cell ids / counters / cell starts; order; items; alive+memb */
+  return (size_t)Smax * 4 + (size_t)Smax * 2 + (size_t)Smax * 2 + (size_t)(Smax / 32) * 8;
 }
+static inline size_t merge_smem_bytes(int Smax) { return merge_warp_smem_bytes(Smax) * MRG_WARPS; }
 
 __device__ __forceinline__ float dev_mahal(float ac0, float ac1, float ac2, float ac3, float am0, float am1,
                                            float bc0, float bc1, float bc2, float bc3, float bm0, float bm1) {
@@ -599,250 +607,353 @@ __device__ __forceinline__ float dev_hellinger(float ac0, float ac1, float ac2, 
   return dist;
 }
 
+/* "a ranks before b": real before pad, heavier first, ties by lower index */
+__device__ __forceinline__ bool rank_before(const float* w, unsigned a, unsigned b) {
+  if (a == 0xffffu) return false;
+  if (b == 0xffffu) return true;
+  float wa = w[a], wb = w[b];
+  return (wa > wb) || (wa == wb && a < b);
+}
+
 __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const DevCfg& c = a.c;
   const int Smax = a.Smax;
-  unsigned long long* s_key = (unsigned long long*)smem_raw;          /* Smax */
-  float* s_c0 = (float*)(s_key + Smax);
-  float* s_c1 = s_c0 + Smax;
-  float* s_c2 = s_c1 + Smax;
-  float* s_c3 = s_c2 + Smax;
-  float* s_m0 = s_c3 + Smax;
-  float* s_m1 = s_m0 + Smax;
-  float* s_wt = s_m1 + Smax;
-  unsigned* s_alive = (unsigned*)(s_wt + Smax);                       /* Smax/32+1 words */
-  unsigned* s_memb = s_alive + (Smax / 32 + 1);
-  __shared__ int s_wcnt[MRG_WARPS];
-  __shared__ int s_n, s_seed, s_pos, s_stop, s_nout;
+  const int lane = lane_id(), warp = warp_id();
+  const int pl = a.p0 + blockIdx.x * MRG_WARPS + warp;
+  if (pl >= a.p1) return;   /* warps are independent: no block barrier below */
 
-  const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
-  const int pl = a.p0 + blockIdx.x;
+  unsigned char* base = smem_raw + (size_t)warp * merge_warp_smem_bytes(Smax);
+  float* s_w = (float*)base;                                   /* region A (sort phase) */
+  unsigned char* s_cell = base;                                /* region A (grid phase): Smax bytes */
+  unsigned* s_cnt = (unsigned*)(base + Smax);                  /*   256 counters (needs Smax >= 512 ... checked on host) */
+  unsigned short* s_start = (unsigned short*)(base + Smax + 1024); /* 257 cell starts */
+  unsigned short* s_order = (unsigned short*)(base + (size_t)Smax * 4);
+  unsigned short* s_items = s_order + Smax;
+  unsigned* s_alive = (unsigned*)(s_items + Smax);
+  unsigned* s_memb = s_alive + Smax / 32;
+
   const int Cmax = c.Cmax;
   const int M = a.M;
   const int C = a.n_in[pl];
-  const unsigned long long T = (unsigned long long)C * (unsigned)(M + 1) + (unsigned)M;
-  const unsigned long long Tpad = (T + 7ull) & ~7ull;
+  const int T = C * (M + 1) + M;
+  const unsigned long long Tpad = ((unsigned long long)T + 7ull) & ~7ull;
   const float* D = a.dense + (a.toff[pl] - a.tbase) * PHD_NPLANES;
   const float* Dw = D + 6 * Tpad;
   const int cnt = a.count_in[pl];
   const float* mp = a.map_in + (size_t)pl * PHD_MAP_PLANES * Cmax;
   const uint8_t* cl = a.cls + (size_t)pl * Cmax;
   float* mo = a.map_out + (size_t)pl * PHD_MAP_PLANES * Cmax;
+  float4* cand = a.cand + (size_t)(pl - a.p0) * Smax * 2;
+  const unsigned lt_mask = (1u << lane) - 1u;
 
-  /* ---- 1. prune: stable compaction of surviving dense terms (flags :2308-2319, pruneMap :3120-3174) ---- */
-  /* pass A: each warp counts the survivors of its contiguous quarter of the term range */
-  const int Ti = (int)T;
-  const int seg = ((Ti + MRG_WARPS * 32 - 1) / (MRG_WARPS * 32)) * 32; /* per-warp segment, multiple of 32 */
-  const int t_lo = warp * seg, t_hi = min(Ti, t_lo + seg);
-  int mycount = 0;
-  for (int t = t_lo + lane; t < t_lo + seg; t += 32) {
-    bool keep = (t < t_hi) && !(Dw[t] < c.min_w);
-    mycount += __popc(__ballot_sync(FULL_MASK, keep));
-  }
-  if (lane == 0) s_wcnt[warp] = mycount;
-  __syncthreads();
-  int woff = 0, nsurv = 0;
+  /* ---- A. prune (flags :2308-2319, pruneMap :3120-3174): stable compaction of the surviving terms ---- */
+  int n = 0;
+  float tmax = 0.0f, xmin = FLT_MAX, xmax = -FLT_MAX, ymin = FLT_MAX, ymax = -FLT_MAX;
+  for (int t0 = 0; t0 < T; t0 += 128) {
+    float wv[4];
 #pragma unroll
-  for (int w = 0; w < MRG_WARPS; ++w) {
-    if (w < warp) woff += s_wcnt[w];
-    nsurv += s_wcnt[w];
-  }
-  /* pass B: place */
-  int run = woff;
-  for (int t = t_lo + lane; t < t_lo + seg; t += 32) {
-    float wv = (t < t_hi) ? Dw[t] : 0.0f;
-    bool keep = (t < t_hi) && !(wv < c.min_w);
-    unsigned bal = __ballot_sync(FULL_MASK, keep);
-    if (keep) {
-      int pos = run + __popc(bal & ((1u << lane) - 1u));
-      if (pos < Smax) {
-        s_c0[pos] = D[t]; s_c1[pos] = D[Tpad + t]; s_c2[pos] = D[2 * Tpad + t]; s_c3[pos] = D[3 * Tpad + t];
-        s_m0[pos] = D[4 * Tpad + t]; s_m1[pos] = D[5 * Tpad + t]; s_wt[pos] = wv;
-      }
+    for (int u = 0; u < 4; ++u) {
+      int t = t0 + u * 32 + lane;
+      wv[u] = (t < T) ? __ldg(Dw + t) : 0.0f;
     }
-    run += __popc(bal);
-  }
-  __syncthreads();
-  /* ---- 2. append the nearly-in-range components in map order (:3243-3252) ---- */
-  if (warp == 0) {
-    int pos0 = nsurv;
-    for (int base = 0; base < cnt; base += 32) {
-      int i = base + lane;
-      bool k2 = (i < cnt) && (cl[i] == 2);
-      unsigned bal = __ballot_sync(FULL_MASK, k2);
-      if (k2) {
-        int pos = pos0 + __popc(bal & ((1u << lane) - 1u));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int t = t0 + u * 32 + lane;
+      bool keep = (t < T) && !(wv[u] < c.min_w);
+      unsigned bal = __ballot_sync(FULL_MASK, keep);
+      if (keep) {
+        int pos = n + __popc(bal & lt_mask);
         if (pos < Smax) {
-          s_wt[pos] = mp[0 * Cmax + i]; s_m0[pos] = mp[1 * Cmax + i]; s_m1[pos] = mp[2 * Cmax + i];
-          s_c0[pos] = mp[3 * Cmax + i]; s_c1[pos] = mp[4 * Cmax + i]; s_c2[pos] = mp[4 * Cmax + i]; s_c3[pos] = mp[5 * Cmax + i];
+          float4 r0 = make_float4(__ldg(D + t), __ldg(D + Tpad + t), __ldg(D + 2 * Tpad + t), __ldg(D + 3 * Tpad + t));
+          float4 r1 = make_float4(__ldg(D + 4 * Tpad + t), __ldg(D + 5 * Tpad + t), wv[u], 0.0f);
+          cand[2 * pos] = r0;
+          cand[2 * pos + 1] = r1;
+          s_w[pos] = wv[u];
+          tmax = fmaxf(tmax, r0.x + r0.w);
+          xmin = fminf(xmin, r1.x); xmax = fmaxf(xmax, r1.x);
+          ymin = fminf(ymin, r1.y); ymax = fmaxf(ymax, r1.y);
         }
       }
-      pos0 += __popc(bal);
+      n += __popc(bal);
     }
-    if (lane == 0) {
-      if (pos0 > Smax) {
-        atomicOr(&a.red->err_flag, 1);
-        pos0 = Smax;
+  }
+  /* nearly-in-range components in map order (:3243-3252) */
+  for (int b0 = 0; b0 < cnt; b0 += 32) {
+    int i = b0 + lane;
+    bool k2 = (i < cnt) && (cl[i] == 2);
+    unsigned bal = __ballot_sync(FULL_MASK, k2);
+    if (k2) {
+      int pos = n + __popc(bal & lt_mask);
+      if (pos < Smax) {
+        float pxy = mp[4 * Cmax + i];
+        float4 r0 = make_float4(mp[3 * Cmax + i], pxy, pxy, mp[5 * Cmax + i]);
+        float4 r1 = make_float4(mp[1 * Cmax + i], mp[2 * Cmax + i], mp[0 * Cmax + i], 0.0f);
+        cand[2 * pos] = r0;
+        cand[2 * pos + 1] = r1;
+        s_w[pos] = r1.z;
+        tmax = fmaxf(tmax, r0.x + r0.w);
+        xmin = fminf(xmin, r1.x); xmax = fmaxf(xmax, r1.x);
+        ymin = fminf(ymin, r1.y); ymax = fmaxf(ymax, r1.y);
       }
-      s_n = pos0;
     }
+    n += __popc(bal);
   }
-  __syncthreads();
-  const int n = s_n;
+  if (n > Smax) {
+    if (lane == 0) atomicOr(&a.red->err_flag, 1);
+    n = Smax;
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    tmax = fmaxf(tmax, __shfl_xor_sync(FULL_MASK, tmax, off));
+    xmin = fminf(xmin, __shfl_xor_sync(FULL_MASK, xmin, off));
+    xmax = fmaxf(xmax, __shfl_xor_sync(FULL_MASK, xmax, off));
+    ymin = fminf(ymin, __shfl_xor_sync(FULL_MASK, ymin, off));
+    ymax = fmaxf(ymax, __shfl_xor_sync(FULL_MASK, ymax, off));
+  }
+  __syncwarp();   /* candidate records written by other lanes are read below */
 
-  /* ---- 3. rank candidates: key = (~ordered(weight) << 32) | index, ascending bitonic sort ---- */
-  int npow = 32;
-  while (npow < n) npow <<= 1;
-  for (int i = tid; i < npow; i += MRG_THREADS) {
-    unsigned long long key = ~0ull;
-    if (i < n) key = ((unsigned long long)(~float_to_ordered_uint(s_wt[i])) << 32) | (unsigned)i;
-    s_key[i] = key;
-  }
-  for (int i = tid; i < (n + 31) / 32 + 1; i += MRG_THREADS) {
-    int lo = i * 32;
-    unsigned w = 0;
-    if (lo < n) w = (n - lo >= 32) ? 0xffffffffu : ((1u << (n - lo)) - 1u);
-    s_alive[i] = w;
-    s_memb[i] = 0;
-  }
-  __syncthreads();
-  for (int k = 2; k <= npow; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < npow; i += MRG_THREADS) {
-        int ixj = i ^ j;
-        if (ixj > i) {
-          unsigned long long ka = s_key[i], kb = s_key[ixj];
-          bool up = ((i & k) == 0);
-          if ((ka > kb) == up) {
-            s_key[i] = kb;
-            s_key[ixj] = ka;
+  int nout = 0;
+  if (n > 0) {
+    /* ---- B. rank by (weight desc, index asc) ---- */
+    int npow = 32;
+    while (npow < n) npow <<= 1;
+    for (int i = lane; i < npow; i += 32) s_order[i] = (i < n) ? (unsigned short)i : (unsigned short)0xffffu;
+    __syncwarp();
+    for (int k = 2; k <= npow; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = lane; i < npow; i += 32) {
+          int ixj = i ^ j;
+          if (ixj > i) {
+            unsigned oa = s_order[i], ob = s_order[ixj];
+            bool up = ((i & k) == 0);
+            bool a_first = rank_before(s_w, oa, ob);
+            /* ascending block: want a before b; descending block: want b before a */
+            if (up ? !a_first && (oa != ob) : a_first) {
+              s_order[i] = (unsigned short)ob;
+              s_order[ixj] = (unsigned short)oa;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+
+    /* ---- C. uniform grid over candidate means; cell size >= gate radius ---- */
+    const float rg2 = (c.distance_metric == 0) ? (2.0f * c.min_sep) * tmax : INFINITY;
+    int G = 1;
+    float cs = 1.0f;
+    {
+      float ext = fmaxf(xmax - xmin, ymax - ymin);
+      float rg = sqrtf(rg2) * 1.0001f;
+      if (rg2 >= 0.0f && rg < ext && ext < FLT_MAX) {      /* false for inf / NaN radius or degenerate extent */
+        int g = (int)(ext / rg) + 1;
+        if (g > MRG_GMAX) g = MRG_GMAX;
+        G = g;
+        cs = fmaxf(rg, (ext / (float)g) * 1.0001f);
+      }
+    }
+    const int ncell = G * G;
+    for (int i = lane; i < 256; i += 32) s_cnt[i] = 0;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+      float4 r1 = cand[2 * i + 1];
+      int cx = 0, cy = 0;
+      if (G > 1) {
+        cx = (int)((r1.x - xmin) / cs);
+        cy = (int)((r1.y - ymin) / cs);
+        cx = min(max(cx, 0), G - 1);
+        cy = min(max(cy, 0), G - 1);
+      }
+      int cid = cy * G + cx;
+      s_cell[i] = (unsigned char)cid;
+      atomicAdd(&s_cnt[cid], 1u);
+    }
+    __syncwarp();
+    {
+      /* exclusive scan of up to 256 cell counts: 8 per lane */
+      unsigned loc[8];
+      unsigned sum = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        int ci = lane * 8 + k;
+        loc[k] = (ci < ncell) ? s_cnt[ci] : 0u;
+        sum += loc[k];
+      }
+      unsigned inc = sum;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        unsigned t = __shfl_up_sync(FULL_MASK, inc, off);
+        if (lane >= off) inc += t;
+      }
+      unsigned ex = inc - sum;
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        int ci = lane * 8 + k;
+        if (ci <= ncell) s_start[ci] = (unsigned short)ex;
+        if (ci < 256) s_cnt[ci] = 0;     /* becomes the running fill count */
+        ex += loc[k];
+      }
+      if (lane == 31 && ncell == 256) s_start[256] = (unsigned short)ex;
+    }
+    __syncwarp();
+    /* stable scatter in index order */
+    for (int b0 = 0; b0 < n; b0 += 32) {
+      int i = b0 + lane;
+      int cid = (i < n) ? (int)s_cell[i] : 0x7fffffff - lane;    /* inactive lanes get unique keys */
+      unsigned same = __match_any_sync(FULL_MASK, cid);
+      unsigned before = 0;
+      if (i < n) before = s_cnt[cid];
+      __syncwarp();
+      if (i < n) {
+        s_items[s_start[cid] + before + __popc(same & lt_mask)] = (unsigned short)i;
+        if ((same & lt_mask) == 0) s_cnt[cid] = before + __popc(same);
+      }
+      __syncwarp();
+    }
+    for (int i = lane; i < Smax / 32; i += 32) {
+      int lo = i * 32;
+      unsigned w = 0;
+      if (lo < n) w = (n - lo >= 32) ? 0xffffffffu : ((1u << (n - lo)) - 1u);
+      s_alive[i] = w;
+      s_memb[i] = 0;
+    }
+    __syncwarp();
+
+    /* ---- D. greedy merge rounds (:2739-2894) ---- */
+    const int nwords = (n + 31) / 32;
+    int pos = 0;
+    bool stop = false;
+    while (!stop) {
+      int seed = -1;
+      while (pos < n) {
+        int i = pos + lane;
+        unsigned ci = (i < n) ? (unsigned)s_order[i] : 0xffffu;
+        bool al = (ci != 0xffffu) && ((s_alive[ci >> 5] >> (ci & 31)) & 1u);
+        unsigned bal = __ballot_sync(FULL_MASK, al);
+        if (bal) {
+          int first = __ffs(bal) - 1;
+          seed = (int)__shfl_sync(FULL_MASK, ci, first);
+          pos += first;
+          break;
+        }
+        pos += 32;
+      }
+      if (seed < 0) break;
+      const float4 A0 = cand[2 * seed], A1 = cand[2 * seed + 1];
+      const int scell = s_cell[seed];
+      const int scy = scell / G, scx = scell - scy * G;
+      const int cx0 = max(scx - 1, 0), cx1 = min(scx + 1, G - 1);
+      int beg[3], len[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        int row = scy + d - 1;
+        if (row >= 0 && row < G) {
+          beg[d] = s_start[row * G + cx0];
+          len[d] = (int)s_start[row * G + cx1 + 1] - beg[d];
+        } else {
+          beg[d] = 0;
+          len[d] = 0;
+        }
+      }
+      const int tot = len[0] + len[1] + len[2];
+      for (int q0 = 0; q0 < tot; q0 += 32) {
+        int q = q0 + lane;
+        if (q < tot) {
+          int src = (q < len[0]) ? beg[0] + q : ((q < len[0] + len[1]) ? beg[1] + (q - len[0]) : beg[2] + (q - len[0] - len[1]));
+          unsigned it = s_items[src];
+          if ((s_alive[it >> 5] >> (it & 31)) & 1u) {
+            float4 B0 = cand[2 * it], B1 = cand[2 * it + 1];
+            float gx = A1.x - B1.x, gy = A1.y - B1.y;
+            if (gx * gx + gy * gy <= rg2) {
+              float dist = (c.distance_metric == 0)
+                               ? dev_mahal(A0.x, A0.y, A0.z, A0.w, A1.x, A1.y, B0.x, B0.y, B0.z, B0.w, B1.x, B1.y)
+                               : dev_hellinger(A0.x, A0.y, A0.z, A0.w, A1.x, A1.y, B0.x, B0.y, B0.z, B0.w, B1.x, B1.y);
+              if (dist < c.min_sep) atomicOr(&s_memb[it >> 5], 1u << (it & 31));
+            }
           }
         }
       }
-      __syncthreads();
-    }
-  }
-  if (tid == 0) {
-    s_pos = 0;
-    s_nout = 0;
-    s_stop = 0;
-    s_seed = (n > 0) ? (int)(s_key[0] & 0xffffffffu) : -1;
-  }
-  __syncthreads();
-
-  /* ---- 4. greedy merge rounds (:2739-2894) ---- */
-  const int nwords = (n + 31) / 32;
-  while (true) {
-    const int seed = s_seed;
-    if (seed < 0 || s_stop) break;
-    const float ac0 = s_c0[seed], ac1 = s_c1[seed], ac2 = s_c2[seed], ac3 = s_c3[seed];
-    const float am0 = s_m0[seed], am1 = s_m1[seed];
-    /* membership: warp w evaluates 32-candidate words w, w+4, ... */
-    for (int wd = warp; wd < nwords; wd += MRG_WARPS) {
-      unsigned alive = s_alive[wd];
-      int i = wd * 32 + lane;
-      bool memb = false;
-      if ((alive >> lane) & 1u) {
-        float dist = (c.distance_metric == 0)
-                         ? dev_mahal(ac0, ac1, ac2, ac3, am0, am1, s_c0[i], s_c1[i], s_c2[i], s_c3[i], s_m0[i], s_m1[i])
-                         : dev_hellinger(ac0, ac1, ac2, ac3, am0, am1, s_c0[i], s_c1[i], s_c2[i], s_c3[i], s_m0[i], s_m1[i]);
-        memb = dist < c.min_sep;
-      }
-      unsigned bal = __ballot_sync(FULL_MASK, memb);
-      if (lane == 0) s_memb[wd] = bal;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      /* moment-matched merge over members in ascending index order; every lane computes the same values */
+      __syncwarp();
+      /* moment-matched merge over the members in ascending index order; all lanes compute the same values */
       float wsum = 0.0f, m0 = 0.0f, m1 = 0.0f;
-      for (int wd = 0; wd < nwords; ++wd) {
-        unsigned mb = s_memb[wd];
-        while (mb) {
-          int i = wd * 32 + (__ffs(mb) - 1);
-          mb &= mb - 1;
-          float wi = s_wt[i];
-          wsum = wsum + wi;
-          m0 = m0 + wi * s_m0[i];
-          m1 = m1 + wi * s_m1[i];
+      for (int wg = 0; wg < nwords; wg += 32) {
+        const unsigned mword = (wg + lane < nwords) ? s_memb[wg + lane] : 0u;
+        for (unsigned hb = __ballot_sync(FULL_MASK, mword != 0u); hb; hb &= hb - 1) {
+          int wd = __ffs(hb) - 1;
+          unsigned mb = __shfl_sync(FULL_MASK, mword, wd);
+          for (; mb; mb &= mb - 1) {
+            int i = (wg + wd) * 32 + (__ffs(mb) - 1);
+            float4 B1 = cand[2 * i + 1];
+            wsum = wsum + B1.z;
+            m0 = m0 + B1.z * B1.x;
+            m1 = m1 + B1.z * B1.y;
+          }
         }
       }
-      if (wsum == 0.0f) {
-        if (lane == 0) s_stop = 1;
+      if (wsum == 0.0f) {      /* :2821-2822: the reference abandons the remaining components */
+        stop = true;
       } else {
-        float mm0 = m0 / wsum, mm1 = m1 / wsum;
+        const float mm0 = m0 / wsum, mm1 = m1 / wsum;
         float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
-        for (int wd = 0; wd < nwords; ++wd) {
-          unsigned mb = s_memb[wd];
-          while (mb) {
-            int i = wd * 32 + (__ffs(mb) - 1);
-            mb &= mb - 1;
-            float wi = s_wt[i];
-            float d0 = mm0 - s_m0[i], d1 = mm1 - s_m1[i];
-            v0 = v0 + wi * (s_c0[i] + d0 * d0);
-            v1 = v1 + wi * (s_c1[i] + d0 * d1);
-            v2 = v2 + wi * (s_c2[i] + d1 * d0);
-            v3 = v3 + wi * (s_c3[i] + d1 * d1);
+        for (int wg = 0; wg < nwords; wg += 32) {
+          const unsigned mword = (wg + lane < nwords) ? s_memb[wg + lane] : 0u;
+          for (unsigned hb = __ballot_sync(FULL_MASK, mword != 0u); hb; hb &= hb - 1) {
+            int wd = __ffs(hb) - 1;
+            unsigned mb = __shfl_sync(FULL_MASK, mword, wd);
+            for (; mb; mb &= mb - 1) {
+              int i = (wg + wd) * 32 + (__ffs(mb) - 1);
+              float4 B0 = cand[2 * i], B1 = cand[2 * i + 1];
+              float d0 = mm0 - B1.x, d1 = mm1 - B1.y;
+              v0 = v0 + B1.z * (B0.x + d0 * d0);
+              v1 = v1 + B1.z * (B0.y + d0 * d1);
+              v2 = v2 + B1.z * (B0.z + d1 * d0);
+              v3 = v3 + B1.z * (B0.w + d1 * d1);
+            }
+          }
+          if (wg + lane < nwords) {     /* retire the members of this word group */
+            s_alive[wg + lane] &= ~mword;
+            s_memb[wg + lane] = 0;
           }
         }
         v0 = v0 / wsum; v1 = v1 / wsum; v2 = v2 / wsum; v3 = v3 / wsum;
         v1 = (v1 + v2) / 2.0f;                       /* force_symmetric_covariance */
-        const int slot = s_nout;
-        if (lane == 0) {
-          if (slot < Cmax) {
-            mo[0 * Cmax + slot] = wsum; mo[1 * Cmax + slot] = mm0; mo[2 * Cmax + slot] = mm1;
-            mo[3 * Cmax + slot] = v0; mo[4 * Cmax + slot] = v1; mo[5 * Cmax + slot] = v3;
-          } else {
-            atomicOr(&a.red->err_flag, 2);
+        if (nout < Cmax) {
+          if (lane == 0) {
+            mo[0 * Cmax + nout] = wsum; mo[1 * Cmax + nout] = mm0; mo[2 * Cmax + nout] = mm1;
+            mo[3 * Cmax + nout] = v0; mo[4 * Cmax + nout] = v1; mo[5 * Cmax + nout] = v3;
           }
+        } else if (lane == 0) {
+          atomicOr(&a.red->err_flag, 2);
         }
-        /* retire members */
-        for (int wd = lane; wd < nwords; wd += 32) s_alive[wd] &= ~s_memb[wd];
-        __syncwarp();
-        /* next seed: first still-alive entry of the ranking */
-        int pos = s_pos;
-        int next = -1;
-        while (pos < n) {
-          int cand = (int)(s_key[pos] & 0xffffffffu);
-          if ((s_alive[cand >> 5] >> (cand & 31)) & 1u) {
-            next = cand;
-            break;
-          }
-          ++pos;
-        }
-        if (lane == 0) {
-          s_pos = pos;
-          s_seed = next;
-          s_nout = slot + 1;
-        }
+        nout++;
       }
+      __syncwarp();
     }
-    __syncthreads();
   }
 
-  /* ---- 5. re-append the far (class 0) components (:3311-3318) and publish the map size ---- */
-  if (warp == 0) {
-    int pos0 = s_nout;
-    for (int base = 0; base < cnt; base += 32) {
-      int i = base + lane;
-      bool k0 = (i < cnt) && (cl[i] == 0);
-      unsigned bal = __ballot_sync(FULL_MASK, k0);
-      if (k0) {
-        int pos = pos0 + __popc(bal & ((1u << lane) - 1u));
-        if (pos < Cmax) {
+  /* ---- E. re-append the far (class 0) components (:3311-3318) and publish the map size ---- */
+  int pos0 = nout;
+  for (int b0 = 0; b0 < cnt; b0 += 32) {
+    int i = b0 + lane;
+    bool k0 = (i < cnt) && (cl[i] == 0);
+    unsigned bal = __ballot_sync(FULL_MASK, k0);
+    if (k0) {
+      int pos = pos0 + __popc(bal & lt_mask);
+      if (pos < Cmax) {
 #pragma unroll
-          for (int f = 0; f < PHD_MAP_PLANES; ++f) mo[f * Cmax + pos] = mp[f * Cmax + i];
-        }
+        for (int f = 0; f < PHD_MAP_PLANES; ++f) mo[f * Cmax + pos] = mp[f * Cmax + i];
       }
-      pos0 += __popc(bal);
     }
-    if (lane == 0) {
-      if (pos0 > Cmax) {
-        atomicOr(&a.red->err_flag, 2);
-        pos0 = Cmax;
-      }
-      a.count_out[pl] = pos0;
+    pos0 += __popc(bal);
+  }
+  if (lane == 0) {
+    if (pos0 > Cmax) {
+      atomicOr(&a.red->err_flag, 2);
+      pos0 = Cmax;
     }
+    a.count_out[pl] = pos0;
   }
 }
 

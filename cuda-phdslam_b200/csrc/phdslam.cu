@@ -113,7 +113,7 @@ static void free_state(phdslam* h) {
   cudaFree(h->snap_pose); cudaFree(h->snap_count); cudaFree(h->snap_map); cudaFree(h->snap_card); cudaFree(h->snap_logw);
   cudaFree(h->cls); cudaFree(h->n_in); cudaFree(h->dlogw); cudaFree(h->tpad); cudaFree(h->toff); cudaFree(h->scan_tmp);
   cudaFree(h->dense); cudaFree(h->z_dev); cudaFree(h->draws_dev); cudaFree(h->q_fx); cudaFree(h->cdf_excl);
-  cudaFree(h->ancestors); cudaFree(h->red);
+  cudaFree(h->ancestors); cudaFree(h->red); cudaFree(h->cand);
   if (h->red_host) cudaFreeHost(h->red_host);
 }
 
@@ -185,8 +185,8 @@ extern "C" int phdslam_create(const phdslam_config_t* cfg, int device, phdslam_t
   h->n_global = cfg->n_particles; h->n_local = cfg->n_particles; h->offset = 0;
   h->Cmax = (cfg->max_components + 31) & ~31;
   h->n_card = (cfg->filter_type == 1) ? cfg->max_cardinality + 1 : 0;
-  int smax = 256;
-  while (smax < 4 * h->Cmax && smax < 4096) smax <<= 1;
+  int smax = 1024; /* merge candidates per particle: survivors of the prune + nearly-in-range components */
+  while (smax < 2 * h->Cmax + PHD_MAX_MEAS && smax < 4096) smax <<= 1;
   h->Smax = smax;
   derive_devcfg(h->cfg, h->Cmax, &h->dc);
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -258,7 +258,7 @@ static int scan_u64(phdslam* h, const unsigned long long* in, int n, unsigned lo
 static int check_err_flag(phdslam* h) {
   /* red_host was filled by a preceding async copy + sync */
   if (h->red_host->err_flag & 1) {
-    phdslam_set_error("merge candidate buffer overflow: raise max_components (candidates after prune exceeded 4*max_components)");
+    phdslam_set_error("merge candidate buffer overflow: raise max_components (candidates after prune exceeded 2*max_components+256)");
     return PHDSLAM_ERR_CAPACITY;
   }
   if (h->red_host->err_flag & 2) {
@@ -321,6 +321,17 @@ static int classify_and_scan(phdslam* h, int M) {
   return 0;
 }
 
+static int ensure_cand(phdslam* h, size_t particles) {
+  size_t need = particles * (size_t)h->Smax * 2;
+  if (h->cand_cap >= need) return 0;
+  cudaFree(h->cand);
+  h->cand = nullptr;
+  h->cand_cap = 0;
+  CK(cudaMalloc(&h->cand, need * sizeof(float4)));
+  h->cand_cap = need;
+  return 0;
+}
+
 static int ensure_dense(phdslam* h, size_t floats) {
   if (h->dense_floats >= floats) return 0;
   cudaFree(h->dense);
@@ -370,8 +381,8 @@ static int launch_merge_batch(phdslam* h, int M, int p0, int p1, unsigned long l
   a.dense = h->dense; a.toff = h->toff; a.tbase = tbase; a.n_in = h->n_in; a.M = M; a.n = h->n_local; a.p0 = p0;
   a.map_in = h->map[h->cur]; a.count_in = h->count[h->cur]; a.cls = h->cls;
   a.map_out = h->map[h->cur ^ 1]; a.count_out = h->count[h->cur ^ 1];
-  a.red = h->red; a.Smax = h->Smax; a.c = h->dc;
-  merge_kernel<<<p1 - p0, MRG_THREADS, merge_smem_bytes(h->Smax), h->stream>>>(a);
+  a.red = h->red; a.Smax = h->Smax; a.c = h->dc; a.p1 = p1; a.cand = h->cand;
+  merge_kernel<<<cdiv(p1 - p0, MRG_WARPS), MRG_THREADS, merge_smem_bytes(h->Smax), h->stream>>>(a);
   LAUNCH_CHECK(h);
   return 0;
 }
@@ -405,6 +416,12 @@ extern "C" int phdslam_update(phdslam_t* h, const float* z, int M, int fields) {
   if (rc) return rc;
   rc = ensure_dense(h, max_terms * PHD_NPLANES);
   if (rc) return rc;
+  {
+    int maxb = 0;
+    for (size_t b = 0; b + 1 < bounds.size(); ++b) maxb = std::max(maxb, bounds[b + 1] - bounds[b]);
+    rc = ensure_cand(h, (size_t)maxb);
+    if (rc) return rc;
+  }
   std::vector<unsigned long long> tb(bounds.size(), 0);
   if (bounds.size() > 2) {
     for (size_t b = 0; b + 1 < bounds.size(); ++b)
