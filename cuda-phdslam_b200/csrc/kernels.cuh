@@ -34,11 +34,15 @@ __device__ __forceinline__ float warp_butterfly_sum(float v) {
   return v;
 }
 
-/* canonical warp_sum over a shared/global array (oracle: warp_sum) -- must be called by a full warp */
+/* canonical warp_sum over a shared/global array (oracle: warp_sum) -- must be called by a full warp:
+ * 64 strided partials (two per lane), pair add, xor butterfly */
 __device__ __forceinline__ float warp_sum_array(const float* v, int n) {
-  float acc = 0.0f;
-  for (int i = lane_id(); i < n; i += 32) acc = acc + v[i];
-  return warp_butterfly_sum(acc);
+  float a0 = 0.0f, a1 = 0.0f;
+  for (int i = 2 * lane_id(); i < n; i += 64) {
+    a0 = a0 + v[i];
+    if (i + 1 < n) a1 = a1 + v[i + 1];
+  }
+  return warp_butterfly_sum(a0 + a1);
 }
 
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
@@ -281,19 +285,23 @@ __global__ void scan_apply_kernel(const unsigned long long* __restrict__ in, int
 }
 
 /* =========================================================================================== */
-/* GM-PHD update, dense output: preUpdateSynthKernel + phdUpdateKernel + host birth loop        */
+/* GM-PHD update: preUpdateSynthKernel + phdUpdateKernel + host birth loop                      */
 /* (reference src/phdfilter.cu:1824-1925, 2083-2321, 3468-3507) fused into one pass.             */
 /*                                                                                               */
 /* One CTA (8 warps) per particle.  The particle's in-range components are compacted into shared */
-/* memory, the per-component EKF constants are computed once, then warp w owns measurements      */
-/* m = w, w+8, ...: lanes stride the components, the per-measurement normaliser is a lane-strided */
-/* partial sum + xor butterfly (the canonical reduction the oracle mirrors), and the normalised   */
-/* terms leave as 128-byte coalesced streaming stores, one plane at a time.                      */
+/* memory and the per-component EKF constants are computed once.  Warp w then owns measurements  */
+/* m = w, w+8, ...; each lane owns two ADJACENT components of every 64-component chunk and does  */
+/* the per-(component, measurement) arithmetic on both at once with Blackwell's packed fp32x2    */
+/* instructions (FADD2/FMUL2/FFMA2 via __fadd2_rn/__fmul2_rn/__ffma2_rn), 64-bit shared loads     */
+/* and 64-bit streaming stores.  The per-measurement normaliser is the canonical reduction       */
+/* (packed lane partials -> pair add -> xor butterfly) mirrored by the oracle's warp_sum.         */
+/* Outputs: (DENSE) the reference's features_update array, plane-SoA, 128-byte coalesced          */
+/* streaming stores; (always) the terms that survive the prune as 32-byte records for the merge.  */
 /* Algorithmic traffic per particle: read 24*C + 32 B, write 28*(C*(M+1)+M) + 4 B.               */
 /* =========================================================================================== */
 #define UPD_THREADS 256
 #define UPD_WARPS (UPD_THREADS / 32)
-#define UPD_FLOATS_PER_COMP 23
+#define UPD_FLOATS_PER_COMP 24
 
 struct UpdArgs {
   const float* map; const int* count; const uint8_t* cls; const float* pose;
@@ -304,6 +312,9 @@ struct UpdArgs {
   float* dense;
   const int* n_in;
   float* dlogw;
+  float4* cand;                        /* [batch][Smax][2] surviving terms, unordered, term index in .w of the 2nd half */
+  int* n_cand;                         /* [n] */
+  int Smax;
   DevCfg c;
 };
 
@@ -311,8 +322,53 @@ static inline size_t update_smem_bytes(int Cmax) {
   return ((size_t)UPD_FLOATS_PER_COMP * Cmax + 6 * PHD_MAX_MEAS) * sizeof(float);
 }
 
-__global__ void __launch_bounds__(UPD_THREADS) update_dense_kernel(UpdArgs a) {
-  extern __shared__ float smem[];
+__device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
+
+/* phd_expf on two values at once; bit-identical per element to the scalar function
+ * (rintf(t) == (t + 1.5*2^23) - 1.5*2^23 for |t| < 2^22, and the low mantissa bits of the biased sum are n). */
+__device__ __forceinline__ float2 phd_expf2(float2 x) {
+  const float2 nm = __ffma2_rn(x, splat2(1.44269504088896341f), splat2(12582912.0f));
+  const float2 n = __fadd2_rn(nm, splat2(-12582912.0f));
+  float2 r = __ffma2_rn(n, splat2(-0.693359375f), x);
+  r = __ffma2_rn(n, splat2(2.12194440e-4f), r);
+  const float2 z = __fmul2_rn(r, r);
+  float2 p = splat2(1.9875691500e-4f);
+  p = __ffma2_rn(p, r, splat2(1.3981999507e-3f));
+  p = __ffma2_rn(p, r, splat2(8.3334519073e-3f));
+  p = __ffma2_rn(p, r, splat2(4.1665795894e-2f));
+  p = __ffma2_rn(p, r, splat2(1.6666665459e-1f));
+  p = __ffma2_rn(p, r, splat2(5.0000001201e-1f));
+  p = __ffma2_rn(p, z, r);
+  p = __fadd2_rn(p, splat2(1.0f));
+  float2 sc;
+  sc.x = __uint_as_float(((__float_as_uint(nm.x) - 0x4B400000u) + 127u) << 23);
+  sc.y = __uint_as_float(((__float_as_uint(nm.y) - 0x4B400000u) + 127u) << 23);
+  float2 v = __fmul2_rn(p, sc);
+  v.x = (x.x >= -87.3f) ? v.x : ((x.x != x.x) ? x.x : 0.0f);
+  v.y = (x.y >= -87.3f) ? v.y : ((x.y != x.y) ? x.y : 0.0f);
+  v.x = (x.x > 88.0f) ? INFINITY : v.x;
+  v.y = (x.y > 88.0f) ? INFINITY : v.y;
+  return v;
+}
+
+/* phd_wrap_angle on two values, fast path |a| < 2*pi (always true for differences of two wrapped bearings
+ * except at exactly +-2*pi, which takes the scalar route) */
+__device__ __forceinline__ float2 phd_wrap_angle2(float2 a) {
+  if (fabsf(a.x) >= PHD_TWO_PI_F || fabsf(a.y) >= PHD_TWO_PI_F)
+    return make_float2(phd_wrap_angle(a.x), phd_wrap_angle(a.y));
+  float2 o1, o2;
+  o1.x = (a.x >= PHD_PI_F) ? -PHD_TWO_PI_F : ((a.x <= -PHD_PI_F) ? PHD_TWO_PI_F : 0.0f);
+  o1.y = (a.y >= PHD_PI_F) ? -PHD_TWO_PI_F : ((a.y <= -PHD_PI_F) ? PHD_TWO_PI_F : 0.0f);
+  o2.x = (a.x >= PHD_PI_F) ? PHD_TWO_PI_ERR : ((a.x <= -PHD_PI_F) ? -PHD_TWO_PI_ERR : 0.0f);
+  o2.y = (a.y >= PHD_PI_F) ? PHD_TWO_PI_ERR : ((a.y <= -PHD_PI_F) ? -PHD_TWO_PI_ERR : 0.0f);
+  return __fadd2_rn(__fadd2_rn(a, o1), o2);
+}
+
+__device__ __forceinline__ float2 lds2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+
+template <bool DENSE>
+__global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
+  extern __shared__ __align__(16) float smem[];
   const DevCfg& c = a.c;
   const int Cmax = c.Cmax;
   float* s_w = smem;
@@ -321,18 +377,18 @@ __global__ void __launch_bounds__(UPD_THREADS) update_dense_kernel(UpdArgs a) {
   float* s_pxx = s_my + Cmax;
   float* s_pxy = s_pxx + Cmax;
   float* s_pyy = s_pxy + Cmax;
-  float* s_r = s_pyy + Cmax;
-  float* s_b = s_r + Cmax;
-  float* s_K0 = s_b + Cmax;
+  float* s_nr = s_pyy + Cmax;           /* -range   (so that innovations are packed adds) */
+  float* s_nb = s_nr + Cmax;            /* -bearing */
+  float* s_K0 = s_nb + Cmax;
   float* s_K1 = s_K0 + Cmax;
   float* s_K2 = s_K1 + Cmax;
   float* s_K3 = s_K2 + Cmax;
   float* s_S0 = s_K3 + Cmax;
   float* s_S12 = s_S0 + Cmax;
   float* s_S3 = s_S12 + Cmax;
-  float* s_base = s_S3 + Cmax;
-  float* s_hl = s_base + Cmax;
-  float* s_cu0 = s_hl + Cmax;
+  float* s_base = s_S3 + Cmax;          /* log pd + log w */
+  float* s_nhl = s_base + Cmax;         /* -0.5 log det */
+  float* s_cu0 = s_nhl + Cmax;
   float* s_cu1 = s_cu0 + Cmax;
   float* s_cu2 = s_cu1 + Cmax;
   float* s_cu3 = s_cu2 + Cmax;
@@ -344,6 +400,7 @@ __global__ void __launch_bounds__(UPD_THREADS) update_dense_kernel(UpdArgs a) {
   float* s_L = s_zl + PHD_MAX_MEAS;
   float* s_ds = s_L + PHD_MAX_MEAS;
   __shared__ int s_wcnt[UPD_WARPS];
+  __shared__ int s_ncand;
 
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
   const int pl = a.p0 + blockIdx.x;     /* local particle index */
@@ -353,7 +410,11 @@ __global__ void __launch_bounds__(UPD_THREADS) update_dense_kernel(UpdArgs a) {
   const float px = a.pose[0 * (size_t)n + pl], py = a.pose[1 * (size_t)n + pl], pth = a.pose[2 * (size_t)n + pl];
   const float* mp = a.map + (size_t)pl * PHD_MAP_PLANES * Cmax;
   const uint8_t* cl = a.cls + (size_t)pl * Cmax;
+  float4* cand = a.cand + (size_t)blockIdx.x * a.Smax * 2;
+  const int Smax = a.Smax;
+  const unsigned lt_mask = (1u << lane) - 1u;
 
+  if (tid == 0) s_ncand = 0;
   for (int m = tid; m < M; m += UPD_THREADS) {
     s_zr[m] = a.z[m];
     s_zb[m] = a.z[PHD_MAX_MEAS + m];
@@ -376,7 +437,7 @@ __global__ void __launch_bounds__(UPD_THREADS) update_dense_kernel(UpdArgs a) {
       tot += cw;
     }
     if (in) {
-      int pos = C + woff + __popc(bal & ((1u << lane) - 1u));
+      int pos = C + woff + __popc(bal & lt_mask);
       s_w[pos] = mp[0 * Cmax + i];
       s_mx[pos] = mp[1 * Cmax + i];
       s_my[pos] = mp[2 * Cmax + i];
@@ -390,59 +451,87 @@ __global__ void __launch_bounds__(UPD_THREADS) update_dense_kernel(UpdArgs a) {
 
   const unsigned long long T = (unsigned long long)C * (unsigned)(M + 1) + (unsigned)M;
   const unsigned long long Tpad = (T + 7ull) & ~7ull;
-  float* D = a.dense + (a.toff[pl] - a.tbase) * PHD_NPLANES;
-  float* D0 = D;
-  float* D1 = D + Tpad;
-  float* D2 = D + 2 * Tpad;
-  float* D3 = D + 3 * Tpad;
-  float* D4 = D + 4 * Tpad;
-  float* D5 = D + 5 * Tpad;
-  float* D6 = D + 6 * Tpad;
+  float* D0 = nullptr; float* D1 = nullptr; float* D2 = nullptr; float* D3 = nullptr;
+  float* D4 = nullptr; float* D5 = nullptr; float* D6 = nullptr;
+  if (DENSE) {
+    D0 = a.dense + (a.toff[pl] - a.tbase) * PHD_NPLANES;
+    D1 = D0 + Tpad; D2 = D0 + 2 * Tpad; D3 = D0 + 3 * Tpad; D4 = D0 + 4 * Tpad; D5 = D0 + 5 * Tpad; D6 = D0 + 6 * Tpad;
+  }
 
   /* ---- phase 1: per-component EKF constants (preUpdateSynthKernel :1835-1894) + non-detection terms ---- */
-  for (int j = tid; j < C; j += UPD_THREADS) {
-    const float w = s_w[j], fx = s_mx[j], fy = s_my[j];
-    const float P0 = s_pxx[j], P1 = s_pxy[j], P2 = s_pxy[j], P3 = s_pyy[j];
-    float dx = fx - px;
-    float dy = fy - py;
-    float r2 = dx * dx + dy * dy;
-    float r = sqrtf(r2);
-    float bearing = phd_wrap_angle(phd_atan2f(dy, dx) - pth);
-    float pd = 0.0f;
-    if (r <= c.max_range && fabsf(bearing) <= c.max_bearing) pd = c.pd;
-    float J0 = dx / r, J2 = dy / r, J1 = -dy / r2, J3 = dx / r2;
-    float sg0 = (P0 * J0 + J2 * P1) * J0 + (J0 * P2 + P3 * J2) * J2 + c.var_r;
-    float sg1 = (P0 * J1 + J3 * P1) * J0 + (J1 * P2 + P3 * J3) * J2;
-    float sg2 = (P0 * J0 + J2 * P1) * J1 + (J0 * P2 + P3 * J2) * J3;
-    float sg3 = (P0 * J1 + J3 * P1) * J1 + (J1 * P2 + P3 * J3) * J3 + c.var_b;
-    sg1 = (sg1 + sg2) / 2.0f;
-    sg2 = sg1;
-    float det = sg0 * sg3 - sg1 * sg2;
-    float S0 = sg3 / det, S1 = -sg1 / det, S2 = -sg2 / det, S3 = sg0 / det;
-    float K0 = S0 * (P0 * J0 + P2 * J2) + S1 * (P0 * J1 + P2 * J3);
-    float K1 = S0 * (P1 * J0 + P3 * J2) + S1 * (P1 * J1 + P3 * J3);
-    float K2 = S2 * (P0 * J0 + P2 * J2) + S3 * (P0 * J1 + P2 * J3);
-    float K3 = S2 * (P1 * J0 + P3 * J2) + S3 * (P1 * J1 + P3 * J3);
-    float qa = 1.0f - K0 * J0 - K2 * J1;
-    float qb = -K0 * J2 - K2 * J3;
-    float qc = -K1 * J0 - K3 * J1;
-    float qd = 1.0f - K1 * J2 - K3 * J3;
-    float cu0 = (qa * P0 + qb * P1) * qa + (qa * P2 + qb * P3) * qb + K0 * K0 * c.var_r + K2 * K2 * c.var_b;
-    float cu2 = (qa * P0 + qb * P1) * qc + (qa * P2 + qb * P3) * qd + K0 * c.var_r * K1 + K2 * c.var_b * K3;
-    float cu1 = (qc * P0 + qd * P1) * qa + (qc * P2 + qd * P3) * qb + K0 * c.var_r * K1 + K2 * c.var_b * K3;
-    float cu3 = (qc * P0 + qd * P1) * qc + (qc * P2 + qd * P3) * qd + K1 * K1 * c.var_r + K3 * K3 * c.var_b;
-    s_r[j] = r; s_b[j] = bearing;
-    s_K0[j] = K0; s_K1[j] = K1; s_K2[j] = K2; s_K3[j] = K3;
-    s_S0[j] = S0; s_S12[j] = S1 + S2; s_S3[j] = S3;
-    s_base[j] = phd_safe_log(pd) + phd_safe_log(w);
-    s_hl[j] = 0.5f * phd_safe_log(det);
-    s_cu0[j] = cu0; s_cu1[j] = cu1; s_cu2[j] = cu2; s_cu3[j] = cu3;
-    s_tmp[j] = pd * w;
-    /* non-detection term (:2137-2141) */
-    float wnd = w * (1.0f - pd);
-    s_nd[j] = wnd;
-    st_stream(D0 + j, P0); st_stream(D1 + j, P1); st_stream(D2 + j, P2); st_stream(D3 + j, P3);
-    st_stream(D4 + j, fx); st_stream(D5 + j, fy); st_stream(D6 + j, wnd);
+  for (int j0 = 0; j0 < C; j0 += UPD_THREADS) {
+    const int j = j0 + tid;
+    bool keep = false;
+    float P0 = 0, P1 = 0, P3 = 0, fx = 0, fy = 0, wnd = 0;
+    if (j < C) {
+      const float w = s_w[j];
+      fx = s_mx[j]; fy = s_my[j];
+      P0 = s_pxx[j]; P1 = s_pxy[j]; P3 = s_pyy[j];
+      const float P2 = P1;
+      float dx = fx - px;
+      float dy = fy - py;
+      float r2 = dx * dx + dy * dy;
+      float r = sqrtf(r2);
+      float bearing = phd_wrap_angle(phd_atan2f(dy, dx) - pth);
+      float pd = 0.0f;
+      if (r <= c.max_range && fabsf(bearing) <= c.max_bearing) pd = c.pd;
+      float J0 = dx / r, J2 = dy / r, J1 = -dy / r2, J3 = dx / r2;
+      float sg0 = (P0 * J0 + J2 * P1) * J0 + (J0 * P2 + P3 * J2) * J2 + c.var_r;
+      float sg1 = (P0 * J1 + J3 * P1) * J0 + (J1 * P2 + P3 * J3) * J2;
+      float sg2 = (P0 * J0 + J2 * P1) * J1 + (J0 * P2 + P3 * J2) * J3;
+      float sg3 = (P0 * J1 + J3 * P1) * J1 + (J1 * P2 + P3 * J3) * J3 + c.var_b;
+      sg1 = (sg1 + sg2) / 2.0f;
+      sg2 = sg1;
+      float det = sg0 * sg3 - sg1 * sg2;
+      float S0 = sg3 / det, S1 = -sg1 / det, S2 = -sg2 / det, S3 = sg0 / det;
+      float K0 = S0 * (P0 * J0 + P2 * J2) + S1 * (P0 * J1 + P2 * J3);
+      float K1 = S0 * (P1 * J0 + P3 * J2) + S1 * (P1 * J1 + P3 * J3);
+      float K2 = S2 * (P0 * J0 + P2 * J2) + S3 * (P0 * J1 + P2 * J3);
+      float K3 = S2 * (P1 * J0 + P3 * J2) + S3 * (P1 * J1 + P3 * J3);
+      float qa = 1.0f - K0 * J0 - K2 * J1;
+      float qb = -K0 * J2 - K2 * J3;
+      float qc = -K1 * J0 - K3 * J1;
+      float qd = 1.0f - K1 * J2 - K3 * J3;
+      float cu0 = (qa * P0 + qb * P1) * qa + (qa * P2 + qb * P3) * qb + K0 * K0 * c.var_r + K2 * K2 * c.var_b;
+      float cu2 = (qa * P0 + qb * P1) * qc + (qa * P2 + qb * P3) * qd + K0 * c.var_r * K1 + K2 * c.var_b * K3;
+      float cu1 = (qc * P0 + qd * P1) * qa + (qc * P2 + qd * P3) * qb + K0 * c.var_r * K1 + K2 * c.var_b * K3;
+      float cu3 = (qc * P0 + qd * P1) * qc + (qc * P2 + qd * P3) * qd + K1 * K1 * c.var_r + K3 * K3 * c.var_b;
+      s_nr[j] = -r; s_nb[j] = -bearing;
+      s_K0[j] = K0; s_K1[j] = K1; s_K2[j] = K2; s_K3[j] = K3;
+      s_S0[j] = S0; s_S12[j] = S1 + S2; s_S3[j] = S3;
+      s_base[j] = phd_safe_log(pd) + phd_safe_log(w);
+      s_nhl[j] = -(0.5f * phd_safe_log(det));
+      s_cu0[j] = cu0; s_cu1[j] = cu1; s_cu2[j] = cu2; s_cu3[j] = cu3;
+      s_tmp[j] = pd * w;
+      /* non-detection term (:2137-2141) */
+      wnd = w * (1.0f - pd);
+      s_nd[j] = wnd;
+      if (DENSE) {
+        st_stream(D0 + j, P0); st_stream(D1 + j, P1); st_stream(D2 + j, P2); st_stream(D3 + j, P3);
+        st_stream(D4 + j, fx); st_stream(D5 + j, fy); st_stream(D6 + j, wnd);
+      }
+      keep = !(wnd < c.min_w);
+    }
+    /* survivors of the prune go to the merge as 32-byte records (warp-aggregated slot allocation) */
+    unsigned bal = __ballot_sync(FULL_MASK, keep);
+    if (bal) {
+      int slot0 = 0;
+      if (lane == 0) slot0 = atomicAdd(&s_ncand, __popc(bal));
+      slot0 = __shfl_sync(FULL_MASK, slot0, 0);
+      if (keep) {
+        int slot = slot0 + __popc(bal & lt_mask);
+        if (slot < Smax) {
+          cand[2 * slot] = make_float4(P0, P1, P1, P3);
+          cand[2 * slot + 1] = make_float4(fx, fy, wnd, __int_as_float(j));
+        }
+      }
+    }
+  }
+  /* pad the pair-wise arrays to an even component count with neutral values */
+  if (tid == 0 && (C & 1)) {
+    s_nr[C] = 0.0f; s_nb[C] = 0.0f; s_K0[C] = 0.0f; s_K1[C] = 0.0f; s_K2[C] = 0.0f; s_K3[C] = 0.0f;
+    s_S0[C] = 0.0f; s_S12[C] = 0.0f; s_S3[C] = 0.0f; s_base[C] = PHD_LOG0; s_nhl[C] = 0.0f;
+    s_cu0[C] = 0.0f; s_cu1[C] = 0.0f; s_cu2[C] = 0.0f; s_cu3[C] = 0.0f; s_mx[C] = 0.0f; s_my[C] = 0.0f;
   }
   for (int m = tid; m < M; m += UPD_THREADS) s_tmp[C + m] = c.birth_weight;
   __syncthreads();
@@ -458,44 +547,98 @@ __global__ void __launch_bounds__(UPD_THREADS) update_dense_kernel(UpdArgs a) {
   }
 
   /* ---- phase 2: detection terms; warp w owns measurements w, w+8, ... (:1898-1923, :2190-2252) ---- */
+  const bool even = ((C & 1) == 0);      /* 64-bit stores need (C + m*C + j) even for every m */
   for (int m = warp; m < M; m += UPD_WARPS) {
     const float zr = s_zr[m], zb = s_zb[m];
     const bool dead = c.labeled && (s_zl[m] != 0.0f);
-    float acc = 0.0f;
-    for (int j = lane; j < C; j += 32) {
-      float i0 = zr - s_r[j];
-      float i1 = phd_wrap_angle(zb - s_b[j]);
-      float dist = i0 * i0 * s_S0[j] + i0 * i1 * s_S12[j] + i1 * i1 * s_S3[j];
-      float g = -0.5f * dist - PHD_LOG_2PI_F - s_hl[j];
-      float lw = dead ? PHD_LOG0 : (s_base[j] + g);
-      acc = acc + phd_expf(lw);
+    const float2 zr2 = splat2(zr), zb2 = splat2(zb);
+    float2 acc = make_float2(0.0f, 0.0f);
+    for (int jb = 0; jb < C; jb += 64) {       /* warp-uniform trip count; lanes past the end are masked */
+      const int jr = jb + 2 * lane;
+      const int j = (jr < C) ? jr : 0;
+      const float2 i0 = __fadd2_rn(zr2, lds2(s_nr + j));
+      const float2 i1 = phd_wrap_angle2(__fadd2_rn(zb2, lds2(s_nb + j)));
+      /* NOTE ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false, so the canonical
+       * arithmetic of this loop spells every multiply-add as an explicit fused multiply-add (oracle: fmaf). */
+      float2 d = __fmul2_rn(__fmul2_rn(i0, i0), lds2(s_S0 + j));
+      d = __ffma2_rn(__fmul2_rn(i0, i1), lds2(s_S12 + j), d);
+      d = __ffma2_rn(__fmul2_rn(i1, i1), lds2(s_S3 + j), d);
+      float2 g = __fadd2_rn(__ffma2_rn(d, splat2(-0.5f), splat2(-PHD_LOG_2PI_F)), lds2(s_nhl + j));
+      float2 lw = __fadd2_rn(lds2(s_base + j), g);
+      if (dead) lw = splat2(PHD_LOG0);
+      float2 e = phd_expf2(lw);
+      if (jr >= C) e.x = 0.0f;
+      if (jr + 1 >= C) e.y = 0.0f;
+      acc = __fadd2_rn(acc, e);
     }
-    float sum = warp_butterfly_sum(acc);
+    float sum = warp_butterfly_sum(acc.x + acc.y);
     sum = sum + c.clutter_density;
     sum = sum + c.birth_weight;
     const float L = phd_safe_log(sum);
-    float* d0 = D0 + C + (size_t)m * C;
-    float* d1 = D1 + C + (size_t)m * C;
-    float* d2 = D2 + C + (size_t)m * C;
-    float* d3 = D3 + C + (size_t)m * C;
-    float* d4 = D4 + C + (size_t)m * C;
-    float* d5 = D5 + C + (size_t)m * C;
-    float* d6 = D6 + C + (size_t)m * C;
-    float wacc = 0.0f;
-    for (int j = lane; j < C; j += 32) {
-      float i0 = zr - s_r[j];
-      float i1 = phd_wrap_angle(zb - s_b[j]);
-      float dist = i0 * i0 * s_S0[j] + i0 * i1 * s_S12[j] + i1 * i1 * s_S3[j];
-      float g = -0.5f * dist - PHD_LOG_2PI_F - s_hl[j];
-      float lw = dead ? PHD_LOG0 : (s_base[j] + g);
-      float wt = phd_expf(lw - L);
-      float m0 = s_mx[j] + s_K0[j] * i0 + s_K2[j] * i1;
-      float m1 = s_my[j] + s_K1[j] * i0 + s_K3[j] * i1;
-      st_stream(d0 + j, s_cu0[j]); st_stream(d1 + j, s_cu1[j]); st_stream(d2 + j, s_cu2[j]); st_stream(d3 + j, s_cu3[j]);
-      st_stream(d4 + j, m0); st_stream(d5 + j, m1); st_stream(d6 + j, wt);
-      wacc = wacc + wt;
+    const float2 nL2 = splat2(-L);
+    const size_t toff_m = (size_t)C + (size_t)m * C;
+    float2 wacc = make_float2(0.0f, 0.0f);
+    for (int jb = 0; jb < C; jb += 64) {
+      const int jr = jb + 2 * lane;
+      const bool v0 = (jr < C), v1 = (jr + 1 < C);
+      const int j = v0 ? jr : 0;
+      const float2 i0 = __fadd2_rn(zr2, lds2(s_nr + j));
+      const float2 i1 = phd_wrap_angle2(__fadd2_rn(zb2, lds2(s_nb + j)));
+      /* NOTE ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false, so the canonical
+       * arithmetic of this loop spells every multiply-add as an explicit fused multiply-add (oracle: fmaf). */
+      float2 d = __fmul2_rn(__fmul2_rn(i0, i0), lds2(s_S0 + j));
+      d = __ffma2_rn(__fmul2_rn(i0, i1), lds2(s_S12 + j), d);
+      d = __ffma2_rn(__fmul2_rn(i1, i1), lds2(s_S3 + j), d);
+      float2 g = __fadd2_rn(__ffma2_rn(d, splat2(-0.5f), splat2(-PHD_LOG_2PI_F)), lds2(s_nhl + j));
+      float2 lw = __fadd2_rn(lds2(s_base + j), g);
+      if (dead) lw = splat2(PHD_LOG0);
+      float2 wt = phd_expf2(__fadd2_rn(lw, nL2));
+      const float2 m0 = __ffma2_rn(lds2(s_K2 + j), i1, __ffma2_rn(lds2(s_K0 + j), i0, lds2(s_mx + j)));
+      const float2 m1 = __ffma2_rn(lds2(s_K3 + j), i1, __ffma2_rn(lds2(s_K1 + j), i0, lds2(s_my + j)));
+      const float2 c0 = lds2(s_cu0 + j), c1 = lds2(s_cu1 + j), c2 = lds2(s_cu2 + j), c3 = lds2(s_cu3 + j);
+      if (!v0) wt.x = 0.0f;
+      if (!v1) wt.y = 0.0f;
+      if (DENSE && v0) {
+        const size_t t = toff_m + j;
+        if (even) {
+          __stcs(reinterpret_cast<float2*>(D0 + t), c0); __stcs(reinterpret_cast<float2*>(D1 + t), c1);
+          __stcs(reinterpret_cast<float2*>(D2 + t), c2); __stcs(reinterpret_cast<float2*>(D3 + t), c3);
+          __stcs(reinterpret_cast<float2*>(D4 + t), m0); __stcs(reinterpret_cast<float2*>(D5 + t), m1);
+          __stcs(reinterpret_cast<float2*>(D6 + t), wt);
+        } else {
+          st_stream(D0 + t, c0.x); st_stream(D1 + t, c1.x); st_stream(D2 + t, c2.x); st_stream(D3 + t, c3.x);
+          st_stream(D4 + t, m0.x); st_stream(D5 + t, m1.x); st_stream(D6 + t, wt.x);
+          if (v1) {
+            st_stream(D0 + t + 1, c0.y); st_stream(D1 + t + 1, c1.y); st_stream(D2 + t + 1, c2.y); st_stream(D3 + t + 1, c3.y);
+            st_stream(D4 + t + 1, m0.y); st_stream(D5 + t + 1, m1.y); st_stream(D6 + t + 1, wt.y);
+          }
+        }
+      }
+      wacc = __fadd2_rn(wacc, wt);
+      /* survivors */
+      const bool k0 = v0 && !(wt.x < c.min_w), k1 = v1 && !(wt.y < c.min_w);
+      const unsigned b0 = __ballot_sync(FULL_MASK, k0), b1 = __ballot_sync(FULL_MASK, k1);
+      if (b0 | b1) {
+        int slot0 = 0;
+        if (lane == 0) slot0 = atomicAdd(&s_ncand, __popc(b0) + __popc(b1));
+        slot0 = __shfl_sync(FULL_MASK, slot0, 0);
+        if (k0) {
+          int slot = slot0 + __popc(b0 & lt_mask);
+          if (slot < Smax) {
+            cand[2 * slot] = make_float4(c0.x, c1.x, c2.x, c3.x);
+            cand[2 * slot + 1] = make_float4(m0.x, m1.x, wt.x, __int_as_float((int)(toff_m + j)));
+          }
+        }
+        if (k1) {
+          int slot = slot0 + __popc(b0) + __popc(b1 & lt_mask);
+          if (slot < Smax) {
+            cand[2 * slot] = make_float4(c0.y, c1.y, c2.y, c3.y);
+            cand[2 * slot + 1] = make_float4(m0.y, m1.y, wt.y, __int_as_float((int)(toff_m + j + 1)));
+          }
+        }
+      }
     }
-    float dsum = warp_butterfly_sum(wacc);
+    float dsum = warp_butterfly_sum(wacc.x + wacc.y);
     /* birth term of measurement m (host loop :3468-3507, normalised at :2232-2242) */
     if (lane == 0) {
       float theta = pth + zb;
@@ -510,8 +653,17 @@ __global__ void __launch_bounds__(UPD_THREADS) update_dense_kernel(UpdArgs a) {
       float lb = dead ? PHD_LOG0 : c.log_birth_weight;
       float wb = phd_expf(lb - L);
       size_t t = (size_t)C + (size_t)M * C + m;
-      st_stream(D0 + t, b0); st_stream(D1 + t, b1); st_stream(D2 + t, b1); st_stream(D3 + t, b3);
-      st_stream(D4 + t, px + bdx); st_stream(D5 + t, py + bdy); st_stream(D6 + t, wb);
+      if (DENSE) {
+        st_stream(D0 + t, b0); st_stream(D1 + t, b1); st_stream(D2 + t, b1); st_stream(D3 + t, b3);
+        st_stream(D4 + t, px + bdx); st_stream(D5 + t, py + bdy); st_stream(D6 + t, wb);
+      }
+      if (!(wb < c.min_w)) {
+        int slot = atomicAdd(&s_ncand, 1);
+        if (slot < Smax) {
+          cand[2 * slot] = make_float4(b0, b1, b1, b3);
+          cand[2 * slot + 1] = make_float4(px + bdx, py + bdy, wb, __int_as_float((int)t));
+        }
+      }
       s_L[m] = L;
       s_ds[m] = dsum + wb;
     }
@@ -533,6 +685,7 @@ __global__ void __launch_bounds__(UPD_THREADS) update_dense_kernel(UpdArgs a) {
       out = 0.0f;
     }
     a.dlogw[pl] = out;
+    a.n_cand[pl] = s_ncand;
   }
 }
 
@@ -542,16 +695,15 @@ __global__ void __launch_bounds__(UPD_THREADS) update_dense_kernel(UpdArgs a) {
 /*                                                                                               */
 /* One WARP per particle, no block-level barriers.  The reference re-scans every update term of   */
 /* the particle three times per output component; here                                            */
-/*  A. the warp streams the dense weight plane once, compacts the survivors of the prune          */
-/*     (weight >= minFeatureWeight, term order preserved) into 32-byte records in a global        */
-/*     scratch (L1/L2 resident), then appends the "nearly in range" components;                   */
-/*  B. candidates are ranked once by (weight desc, index asc) with a warp bitonic sort --         */
-/*     weights of unmerged candidates never change, so every greedy arg-max is the next           */
-/*     unmerged entry of that ranking;                                                            */
+/*  A. the warp takes the records of the terms that survived the prune (emitted unordered by the  */
+/*     update kernel), restores term order with a stable LSD radix sort on the term index,        */
+/*     and appends the "nearly in range" components (:3243-3252);                                 */
+/*  B. candidates are ranked once by (weight desc, index asc) with a radix sort -- weights of     */
+/*     unmerged candidates never change, so every greedy arg-max is the next unmerged entry;      */
 /*  C. candidates are binned into a uniform grid whose cell size is the canonical gate radius     */
-/*     (see oracle merge_gate_radius2), so a seed only examines its 3x3 cell neighbourhood;        */
-/*  D. each round evaluates the gate + Mahalanobis/Hellinger distance for those few candidates,   */
-/*     then accumulates the moment-matched merge over the members in ascending index order (the   */
+/*     (oracle: merge_gate_radius2), so a seed only examines its 3x3 cell neighbourhood;           */
+/*  D. each round evaluates gate + Mahalanobis/Hellinger distance for those few candidates, then  */
+/*     accumulates the moment-matched merge over the members in ascending index order (the        */
 /*     canonical order of the oracle).                                                            */
 /* =========================================================================================== */
 #define MRG_THREADS 128
@@ -559,19 +711,20 @@ __global__ void __launch_bounds__(UPD_THREADS) update_dense_kernel(UpdArgs a) {
 #define MRG_GMAX 16
 
 struct MrgArgs {
-  const float* dense; const unsigned long long* toff; unsigned long long tbase;
-  const int* n_in; int M, n, p0, p1;
+  int M, n, p0, p1;
   const float* map_in; const int* count_in; const uint8_t* cls;
   float* map_out; int* count_out;
-  float4* cand;                        /* scratch: [p1-p0][Smax][2] */
+  const float4* cand_in;               /* [p1-p0][Smax][2] from the update kernel (unordered) */
+  const int* n_cand;                   /* [n] */
+  float4* cand;                        /* [p1-p0][Smax][2] scratch: candidates in canonical (term) order */
   Reductions* red;
   int Smax;
   DevCfg c;
 };
 
 __host__ __device__ static inline size_t merge_warp_smem_bytes(int Smax) {
-  /* region A: float w[Smax] during the sort, then cell ids / counters / cell starts; order; items; alive+memb */
-  return (size_t)Smax * 4 + (size_t)Smax * 2 + (size_t)Smax * 2 + (size_t)(Smax / 32) * 8;
+  /* cell ids (Smax) | 256 counters | 264 cell starts (u16) | order (u16 Smax) | items (u16 Smax) | alive + memb words */
+  return (size_t)Smax + 1024 + 528 + (size_t)Smax * 4 + (size_t)(Smax / 32) * 8;
 }
 static inline size_t merge_smem_bytes(int Smax) { return merge_warp_smem_bytes(Smax) * MRG_WARPS; }
 
@@ -579,7 +732,8 @@ __device__ __forceinline__ float dev_mahal(float ac0, float ac1, float ac2, floa
                                            float bc0, float bc1, float bc2, float bc3, float bm0, float bm1) {
   float s0 = (ac0 + bc0) / 2.0f, s1 = (ac1 + bc1) / 2.0f, s2 = (ac2 + bc2) / 2.0f, s3 = (ac3 + bc3) / 2.0f;
   float det = s0 * s3 - s2 * s1;
-  float v0 = s3 / det, v1 = -s1 / det, v2 = -s2 / det, v3 = s0 / det;
+  float rdet = 1.0f / det;
+  float v0 = s3 * rdet, v1 = -s1 * rdet, v2 = -s2 * rdet, v3 = s0 * rdet;
   float i0 = am0 - bm0;
   float i1 = am1 - bm1;
   return i0 * i0 * v0 + i0 * i1 * (v1 + v2) + i1 * i1 * v3;
@@ -607,12 +761,66 @@ __device__ __forceinline__ float dev_hellinger(float ac0, float ac1, float ac2, 
   return dist;
 }
 
-/* "a ranks before b": real before pad, heavier first, ties by lower index */
-__device__ __forceinline__ bool rank_before(const float* w, unsigned a, unsigned b) {
-  if (a == 0xffffu) return false;
-  if (b == 0xffffu) return true;
-  float wa = w[a], wb = w[b];
-  return (wa > wb) || (wa == wb && a < b);
+/* exclusive scan of 256 u32 counters held 8 per lane; returns the 8 exclusive prefixes in ex[] */
+__device__ __forceinline__ void warp_scan256(const unsigned* cnt, unsigned ex[8], int lane) {
+  unsigned loc[8], sum = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    loc[k] = cnt[lane * 8 + k];
+    sum += loc[k];
+  }
+  unsigned inc = sum;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    unsigned t = __shfl_up_sync(FULL_MASK, inc, off);
+    if (lane >= off) inc += t;
+  }
+  unsigned run = inc - sum;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    ex[k] = run;
+    run += loc[k];
+  }
+}
+
+/* One stable LSD radix pass (8-bit digit) over the index list `in` -> `out`, keyed by
+ * key_of(idx) = bits of recs[2*idx+1].{w|z} (optionally transformed).  Warp-synchronous. */
+template <int MODE> /* 0: key = term index (record .w); 1: key = ~ordered(weight) (record .z) */
+__device__ __forceinline__ unsigned radix_key(const float4* recs, unsigned idx) {
+  float4 r1 = recs[2 * idx + 1];
+  if (MODE == 0) return __float_as_uint(r1.w);
+  return ~float_to_ordered_uint(r1.z);
+}
+template <int MODE>
+__device__ __forceinline__ void radix_pass(const float4* recs, const unsigned short* in, unsigned short* out, int n,
+                                           unsigned* hist, int shift, int lane) {
+  const unsigned lt_mask = (1u << lane) - 1u;
+  for (int i = lane; i < 256; i += 32) hist[i] = 0;
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) atomicAdd(&hist[(radix_key<MODE>(recs, in[i]) >> shift) & 255u], 1u);
+  __syncwarp();
+  unsigned ex[8];
+  warp_scan256(hist, ex, lane);
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) hist[lane * 8 + k] = ex[k];
+  __syncwarp();
+  for (int b0 = 0; b0 < n; b0 += 32) {
+    int i = b0 + lane;
+    unsigned idx = 0, d = 0x80000000u | (unsigned)lane;   /* inactive lanes: unique keys */
+    if (i < n) {
+      idx = in[i];
+      d = (radix_key<MODE>(recs, idx) >> shift) & 255u;
+    }
+    unsigned same = __match_any_sync(FULL_MASK, d);
+    unsigned before = (i < n) ? hist[d] : 0u;
+    __syncwarp();
+    if (i < n) {
+      out[before + __popc(same & lt_mask)] = (unsigned short)idx;
+      if ((same & lt_mask) == 0) hist[d] = before + __popc(same);
+    }
+    __syncwarp();
+  }
 }
 
 __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
@@ -624,60 +832,48 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
   if (pl >= a.p1) return;   /* warps are independent: no block barrier below */
 
   unsigned char* base = smem_raw + (size_t)warp * merge_warp_smem_bytes(Smax);
-  float* s_w = (float*)base;                                   /* region A (sort phase) */
-  unsigned char* s_cell = base;                                /* region A (grid phase): Smax bytes */
-  unsigned* s_cnt = (unsigned*)(base + Smax);                  /*   256 counters (needs Smax >= 512 ... checked on host) */
-  unsigned short* s_start = (unsigned short*)(base + Smax + 1024); /* 257 cell starts */
-  unsigned short* s_order = (unsigned short*)(base + (size_t)Smax * 4);
+  unsigned char* s_cell = base;                                        /* (cy << 4) | cx per candidate */
+  unsigned* s_cnt = (unsigned*)(base + Smax);                          /* 256 counters (radix histogram / cell fill) */
+  unsigned short* s_start = (unsigned short*)(base + Smax + 1024);     /* 257 cell starts */
+  unsigned short* s_order = (unsigned short*)(base + Smax + 1024 + 528);
   unsigned short* s_items = s_order + Smax;
   unsigned* s_alive = (unsigned*)(s_items + Smax);
   unsigned* s_memb = s_alive + Smax / 32;
 
   const int Cmax = c.Cmax;
-  const int M = a.M;
-  const int C = a.n_in[pl];
-  const int T = C * (M + 1) + M;
-  const unsigned long long Tpad = ((unsigned long long)T + 7ull) & ~7ull;
-  const float* D = a.dense + (a.toff[pl] - a.tbase) * PHD_NPLANES;
-  const float* Dw = D + 6 * Tpad;
   const int cnt = a.count_in[pl];
   const float* mp = a.map_in + (size_t)pl * PHD_MAP_PLANES * Cmax;
   const uint8_t* cl = a.cls + (size_t)pl * Cmax;
   float* mo = a.map_out + (size_t)pl * PHD_MAP_PLANES * Cmax;
+  const float4* cin = a.cand_in + (size_t)(pl - a.p0) * Smax * 2;
   float4* cand = a.cand + (size_t)(pl - a.p0) * Smax * 2;
   const unsigned lt_mask = (1u << lane) - 1u;
 
-  /* ---- A. prune (flags :2308-2319, pruneMap :3120-3174): stable compaction of the surviving terms ---- */
-  int n = 0;
-  float tmax = 0.0f, xmin = FLT_MAX, xmax = -FLT_MAX, ymin = FLT_MAX, ymax = -FLT_MAX;
-  for (int t0 = 0; t0 < T; t0 += 128) {
-    float wv[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      int t = t0 + u * 32 + lane;
-      wv[u] = (t < T) ? __ldg(Dw + t) : 0.0f;
+  /* ---- A. survivors of the prune (flags :2308-2319, pruneMap :3120-3174) back into term order ---- */
+  int n = a.n_cand[pl];
+  if (n > Smax) {
+    if (lane == 0) atomicOr(&a.red->err_flag, 1);
+    n = Smax;
+  }
+  {
+    const int T = a.M + (int)cnt * (a.M + 1);              /* upper bound of the term index */
+    int bits = 32 - __clz(max(T, 1));
+    for (int i = lane; i < n; i += 32) s_order[i] = (unsigned short)i;
+    __syncwarp();
+    unsigned short* src = s_order;
+    unsigned short* dst = s_items;
+    for (int shift = 0; shift < bits; shift += 8) {
+      radix_pass<0>(cin, src, dst, n, s_cnt, shift, lane);
+      unsigned short* t = src; src = dst; dst = t;
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      int t = t0 + u * 32 + lane;
-      bool keep = (t < T) && !(wv[u] < c.min_w);
-      unsigned bal = __ballot_sync(FULL_MASK, keep);
-      if (keep) {
-        int pos = n + __popc(bal & lt_mask);
-        if (pos < Smax) {
-          float4 r0 = make_float4(__ldg(D + t), __ldg(D + Tpad + t), __ldg(D + 2 * Tpad + t), __ldg(D + 3 * Tpad + t));
-          float4 r1 = make_float4(__ldg(D + 4 * Tpad + t), __ldg(D + 5 * Tpad + t), wv[u], 0.0f);
-          cand[2 * pos] = r0;
-          cand[2 * pos + 1] = r1;
-          s_w[pos] = wv[u];
-          tmax = fmaxf(tmax, r0.x + r0.w);
-          xmin = fminf(xmin, r1.x); xmax = fmaxf(xmax, r1.x);
-          ymin = fminf(ymin, r1.y); ymax = fmaxf(ymax, r1.y);
-        }
-      }
-      n += __popc(bal);
+    for (int i = lane; i < n; i += 32) {
+      unsigned sidx = src[i];
+      float4 r0 = cin[2 * sidx], r1 = cin[2 * sidx + 1];
+      cand[2 * i] = r0;
+      cand[2 * i + 1] = r1;
     }
   }
+  float tmax = 0.0f, xmin = FLT_MAX, xmax = -FLT_MAX, ymin = FLT_MAX, ymax = -FLT_MAX;
   /* nearly-in-range components in map order (:3243-3252) */
   for (int b0 = 0; b0 < cnt; b0 += 32) {
     int i = b0 + lane;
@@ -687,14 +883,8 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
       int pos = n + __popc(bal & lt_mask);
       if (pos < Smax) {
         float pxy = mp[4 * Cmax + i];
-        float4 r0 = make_float4(mp[3 * Cmax + i], pxy, pxy, mp[5 * Cmax + i]);
-        float4 r1 = make_float4(mp[1 * Cmax + i], mp[2 * Cmax + i], mp[0 * Cmax + i], 0.0f);
-        cand[2 * pos] = r0;
-        cand[2 * pos + 1] = r1;
-        s_w[pos] = r1.z;
-        tmax = fmaxf(tmax, r0.x + r0.w);
-        xmin = fminf(xmin, r1.x); xmax = fmaxf(xmax, r1.x);
-        ymin = fminf(ymin, r1.y); ymax = fmaxf(ymax, r1.y);
+        cand[2 * pos] = make_float4(mp[3 * Cmax + i], pxy, pxy, mp[5 * Cmax + i]);
+        cand[2 * pos + 1] = make_float4(mp[1 * Cmax + i], mp[2 * Cmax + i], mp[0 * Cmax + i], 0.0f);
       }
     }
     n += __popc(bal);
@@ -702,6 +892,13 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
   if (n > Smax) {
     if (lane == 0) atomicOr(&a.red->err_flag, 1);
     n = Smax;
+  }
+  __syncwarp();   /* candidate records written by other lanes are read below */
+  for (int i = lane; i < n; i += 32) {
+    float4 r0 = cand[2 * i], r1 = cand[2 * i + 1];
+    tmax = fmaxf(tmax, r0.x + r0.w);
+    xmin = fminf(xmin, r1.x); xmax = fmaxf(xmax, r1.x);
+    ymin = fminf(ymin, r1.y); ymax = fmaxf(ymax, r1.y);
   }
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
@@ -711,33 +908,16 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
     ymin = fminf(ymin, __shfl_xor_sync(FULL_MASK, ymin, off));
     ymax = fmaxf(ymax, __shfl_xor_sync(FULL_MASK, ymax, off));
   }
-  __syncwarp();   /* candidate records written by other lanes are read below */
 
   int nout = 0;
   if (n > 0) {
-    /* ---- B. rank by (weight desc, index asc) ---- */
-    int npow = 32;
-    while (npow < n) npow <<= 1;
-    for (int i = lane; i < npow; i += 32) s_order[i] = (i < n) ? (unsigned short)i : (unsigned short)0xffffu;
+    /* ---- B. rank by (weight desc, index asc): stable LSD radix on ~ordered(weight) ---- */
+    for (int i = lane; i < n; i += 32) s_order[i] = (unsigned short)i;
     __syncwarp();
-    for (int k = 2; k <= npow; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = lane; i < npow; i += 32) {
-          int ixj = i ^ j;
-          if (ixj > i) {
-            unsigned oa = s_order[i], ob = s_order[ixj];
-            bool up = ((i & k) == 0);
-            bool a_first = rank_before(s_w, oa, ob);
-            /* ascending block: want a before b; descending block: want b before a */
-            if (up ? !a_first && (oa != ob) : a_first) {
-              s_order[i] = (unsigned short)ob;
-              s_order[ixj] = (unsigned short)oa;
-            }
-          }
-        }
-        __syncwarp();
-      }
-    }
+    radix_pass<1>(cand, s_order, s_items, n, s_cnt, 0, lane);
+    radix_pass<1>(cand, s_items, s_order, n, s_cnt, 8, lane);
+    radix_pass<1>(cand, s_order, s_items, n, s_cnt, 16, lane);
+    radix_pass<1>(cand, s_items, s_order, n, s_cnt, 24, lane);
 
     /* ---- C. uniform grid over candidate means; cell size >= gate radius ---- */
     const float rg2 = (c.distance_metric == 0) ? (2.0f * c.min_sep) * tmax : INFINITY;
@@ -753,7 +933,6 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
         cs = fmaxf(rg, (ext / (float)g) * 1.0001f);
       }
     }
-    const int ncell = G * G;
     for (int i = lane; i < 256; i += 32) s_cnt[i] = 0;
     __syncwarp();
     for (int i = lane; i < n; i += 32) {
@@ -765,46 +944,29 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
         cx = min(max(cx, 0), G - 1);
         cy = min(max(cy, 0), G - 1);
       }
-      int cid = cy * G + cx;
+      int cid = (cy << 4) | cx;
       s_cell[i] = (unsigned char)cid;
       atomicAdd(&s_cnt[cid], 1u);
     }
     __syncwarp();
     {
-      /* exclusive scan of up to 256 cell counts: 8 per lane */
-      unsigned loc[8];
-      unsigned sum = 0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        int ci = lane * 8 + k;
-        loc[k] = (ci < ncell) ? s_cnt[ci] : 0u;
-        sum += loc[k];
-      }
-      unsigned inc = sum;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        unsigned t = __shfl_up_sync(FULL_MASK, inc, off);
-        if (lane >= off) inc += t;
-      }
-      unsigned ex = inc - sum;
+      unsigned ex[8];
+      warp_scan256(s_cnt, ex, lane);
       __syncwarp();
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        int ci = lane * 8 + k;
-        if (ci <= ncell) s_start[ci] = (unsigned short)ex;
-        if (ci < 256) s_cnt[ci] = 0;     /* becomes the running fill count */
-        ex += loc[k];
+        s_start[lane * 8 + k] = (unsigned short)ex[k];
+        s_cnt[lane * 8 + k] = 0;       /* becomes the running fill count */
       }
-      if (lane == 31 && ncell == 256) s_start[256] = (unsigned short)ex;
+      if (lane == 31) s_start[256] = (unsigned short)n;
     }
     __syncwarp();
     /* stable scatter in index order */
     for (int b0 = 0; b0 < n; b0 += 32) {
       int i = b0 + lane;
-      int cid = (i < n) ? (int)s_cell[i] : 0x7fffffff - lane;    /* inactive lanes get unique keys */
+      unsigned cid = (i < n) ? (unsigned)s_cell[i] : (0x80000000u | (unsigned)lane);
       unsigned same = __match_any_sync(FULL_MASK, cid);
-      unsigned before = 0;
-      if (i < n) before = s_cnt[cid];
+      unsigned before = (i < n) ? s_cnt[cid] : 0u;
       __syncwarp();
       if (i < n) {
         s_items[s_start[cid] + before + __popc(same & lt_mask)] = (unsigned short)i;
@@ -829,8 +991,8 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
       int seed = -1;
       while (pos < n) {
         int i = pos + lane;
-        unsigned ci = (i < n) ? (unsigned)s_order[i] : 0xffffu;
-        bool al = (ci != 0xffffu) && ((s_alive[ci >> 5] >> (ci & 31)) & 1u);
+        unsigned ci = (i < n) ? (unsigned)s_order[i] : 0u;
+        bool al = (i < n) && ((s_alive[ci >> 5] >> (ci & 31)) & 1u);
         unsigned bal = __ballot_sync(FULL_MASK, al);
         if (bal) {
           int first = __ffs(bal) - 1;
@@ -843,60 +1005,55 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
       if (seed < 0) break;
       const float4 A0 = cand[2 * seed], A1 = cand[2 * seed + 1];
       const int scell = s_cell[seed];
-      const int scy = scell / G, scx = scell - scy * G;
+      const int scy = scell >> 4, scx = scell & 15;
       const int cx0 = max(scx - 1, 0), cx1 = min(scx + 1, G - 1);
       int beg[3], len[3];
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
         int row = scy + d - 1;
         if (row >= 0 && row < G) {
-          beg[d] = s_start[row * G + cx0];
-          len[d] = (int)s_start[row * G + cx1 + 1] - beg[d];
+          beg[d] = s_start[(row << 4) | cx0];
+          len[d] = (int)s_start[((row << 4) | cx1) + 1] - beg[d];
         } else {
           beg[d] = 0;
           len[d] = 0;
         }
       }
       const int tot = len[0] + len[1] + len[2];
+      int nmemb = 0;
       for (int q0 = 0; q0 < tot; q0 += 32) {
         int q = q0 + lane;
+        bool memb = false;
+        unsigned it = 0;
         if (q < tot) {
           int src = (q < len[0]) ? beg[0] + q : ((q < len[0] + len[1]) ? beg[1] + (q - len[0]) : beg[2] + (q - len[0] - len[1]));
-          unsigned it = s_items[src];
+          it = s_items[src];
           if ((s_alive[it >> 5] >> (it & 31)) & 1u) {
-            float4 B0 = cand[2 * it], B1 = cand[2 * it + 1];
+            float4 B1 = cand[2 * it + 1];
             float gx = A1.x - B1.x, gy = A1.y - B1.y;
             if (gx * gx + gy * gy <= rg2) {
+              float4 B0 = cand[2 * it];
               float dist = (c.distance_metric == 0)
                                ? dev_mahal(A0.x, A0.y, A0.z, A0.w, A1.x, A1.y, B0.x, B0.y, B0.z, B0.w, B1.x, B1.y)
                                : dev_hellinger(A0.x, A0.y, A0.z, A0.w, A1.x, A1.y, B0.x, B0.y, B0.z, B0.w, B1.x, B1.y);
-              if (dist < c.min_sep) atomicOr(&s_memb[it >> 5], 1u << (it & 31));
+              memb = dist < c.min_sep;
             }
           }
         }
+        if (memb) atomicOr(&s_memb[it >> 5], 1u << (it & 31));
+        nmemb += __popc(__ballot_sync(FULL_MASK, memb));
       }
       __syncwarp();
-      /* moment-matched merge over the members in ascending index order; all lanes compute the same values */
       float wsum = 0.0f, m0 = 0.0f, m1 = 0.0f;
-      for (int wg = 0; wg < nwords; wg += 32) {
-        const unsigned mword = (wg + lane < nwords) ? s_memb[wg + lane] : 0u;
-        for (unsigned hb = __ballot_sync(FULL_MASK, mword != 0u); hb; hb &= hb - 1) {
-          int wd = __ffs(hb) - 1;
-          unsigned mb = __shfl_sync(FULL_MASK, mword, wd);
-          for (; mb; mb &= mb - 1) {
-            int i = (wg + wd) * 32 + (__ffs(mb) - 1);
-            float4 B1 = cand[2 * i + 1];
-            wsum = wsum + B1.z;
-            m0 = m0 + B1.z * B1.x;
-            m1 = m1 + B1.z * B1.y;
-          }
-        }
-      }
-      if (wsum == 0.0f) {      /* :2821-2822: the reference abandons the remaining components */
-        stop = true;
+      float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f, mm0 = 0.0f, mm1 = 0.0f;
+      const bool single = (nmemb == 1) && ((s_memb[seed >> 5] >> (seed & 31)) & 1u);
+      if (single) {
+        /* the seed alone: same operation sequence as the general path with one member */
+        wsum = wsum + A1.z;
+        m0 = m0 + A1.z * A1.x;
+        m1 = m1 + A1.z * A1.y;
       } else {
-        const float mm0 = m0 / wsum, mm1 = m1 / wsum;
-        float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
+        /* members in ascending index order; every lane computes the same values */
         for (int wg = 0; wg < nwords; wg += 32) {
           const unsigned mword = (wg + lane < nwords) ? s_memb[wg + lane] : 0u;
           for (unsigned hb = __ballot_sync(FULL_MASK, mword != 0u); hb; hb &= hb - 1) {
@@ -904,20 +1061,53 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
             unsigned mb = __shfl_sync(FULL_MASK, mword, wd);
             for (; mb; mb &= mb - 1) {
               int i = (wg + wd) * 32 + (__ffs(mb) - 1);
-              float4 B0 = cand[2 * i], B1 = cand[2 * i + 1];
-              float d0 = mm0 - B1.x, d1 = mm1 - B1.y;
-              v0 = v0 + B1.z * (B0.x + d0 * d0);
-              v1 = v1 + B1.z * (B0.y + d0 * d1);
-              v2 = v2 + B1.z * (B0.z + d1 * d0);
-              v3 = v3 + B1.z * (B0.w + d1 * d1);
+              float4 B1 = cand[2 * i + 1];
+              wsum = wsum + B1.z;
+              m0 = m0 + B1.z * B1.x;
+              m1 = m1 + B1.z * B1.y;
             }
           }
-          if (wg + lane < nwords) {     /* retire the members of this word group */
-            s_alive[wg + lane] &= ~mword;
-            s_memb[wg + lane] = 0;
+        }
+      }
+      if (wsum == 0.0f) {      /* :2821-2822: the reference abandons the remaining components */
+        stop = true;
+      } else {
+        const float rw = 1.0f / wsum;
+        mm0 = m0 * rw;
+        mm1 = m1 * rw;
+        if (single) {
+          float d0 = mm0 - A1.x, d1 = mm1 - A1.y;
+          v0 = v0 + A1.z * (A0.x + d0 * d0);
+          v1 = v1 + A1.z * (A0.y + d0 * d1);
+          v2 = v2 + A1.z * (A0.z + d1 * d0);
+          v3 = v3 + A1.z * (A0.w + d1 * d1);
+          if (lane == 0) {
+            s_alive[seed >> 5] &= ~(1u << (seed & 31));
+            s_memb[seed >> 5] = 0;
+          }
+        } else {
+          for (int wg = 0; wg < nwords; wg += 32) {
+            const unsigned mword = (wg + lane < nwords) ? s_memb[wg + lane] : 0u;
+            for (unsigned hb = __ballot_sync(FULL_MASK, mword != 0u); hb; hb &= hb - 1) {
+              int wd = __ffs(hb) - 1;
+              unsigned mb = __shfl_sync(FULL_MASK, mword, wd);
+              for (; mb; mb &= mb - 1) {
+                int i = (wg + wd) * 32 + (__ffs(mb) - 1);
+                float4 B0 = cand[2 * i], B1 = cand[2 * i + 1];
+                float d0 = mm0 - B1.x, d1 = mm1 - B1.y;
+                v0 = v0 + B1.z * (B0.x + d0 * d0);
+                v1 = v1 + B1.z * (B0.y + d0 * d1);
+                v2 = v2 + B1.z * (B0.z + d1 * d0);
+                v3 = v3 + B1.z * (B0.w + d1 * d1);
+              }
+            }
+            if (wg + lane < nwords) {     /* retire the members of this word group */
+              s_alive[wg + lane] &= ~mword;
+              s_memb[wg + lane] = 0;
+            }
           }
         }
-        v0 = v0 / wsum; v1 = v1 / wsum; v2 = v2 / wsum; v3 = v3 / wsum;
+        v0 = v0 * rw; v1 = v1 * rw; v2 = v2 * rw; v3 = v3 * rw;
         v1 = (v1 + v2) / 2.0f;                       /* force_symmetric_covariance */
         if (nout < Cmax) {
           if (lane == 0) {

@@ -113,7 +113,7 @@ static void free_state(phdslam* h) {
   cudaFree(h->snap_pose); cudaFree(h->snap_count); cudaFree(h->snap_map); cudaFree(h->snap_card); cudaFree(h->snap_logw);
   cudaFree(h->cls); cudaFree(h->n_in); cudaFree(h->dlogw); cudaFree(h->tpad); cudaFree(h->toff); cudaFree(h->scan_tmp);
   cudaFree(h->dense); cudaFree(h->z_dev); cudaFree(h->draws_dev); cudaFree(h->q_fx); cudaFree(h->cdf_excl);
-  cudaFree(h->ancestors); cudaFree(h->red); cudaFree(h->cand);
+  cudaFree(h->ancestors); cudaFree(h->red); cudaFree(h->cand); cudaFree(h->cand_in); cudaFree(h->n_cand);
   if (h->red_host) cudaFreeHost(h->red_host);
 }
 
@@ -131,6 +131,7 @@ static int alloc_state(phdslam* h) {
   CK(cudaMalloc(&h->cls, n * C));
   CK(cudaMalloc(&h->n_in, n * sizeof(int)));
   CK(cudaMalloc(&h->dlogw, n * sizeof(float)));
+  CK(cudaMalloc(&h->n_cand, n * sizeof(int)));
   CK(cudaMalloc(&h->tpad, n * sizeof(unsigned long long)));
   CK(cudaMalloc(&h->toff, (n + 1) * sizeof(unsigned long long)));
   CK(cudaMalloc(&h->scan_tmp, (size_t)(cdiv(n, SCAN_TILE) + 1) * sizeof(unsigned long long)));
@@ -193,7 +194,8 @@ extern "C" int phdslam_create(const phdslam_config_t* cfg, int device, phdslam_t
   for (int i = 0; i < 12; ++i) CK(cudaEventCreate(&h->ev[i]));
   rc = alloc_state(h);
   if (rc) { free_state(h); delete h; return rc; }
-  CK(cudaFuncSetAttribute(update_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(h->Cmax)));
+  CK(cudaFuncSetAttribute(update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(h->Cmax)));
+  CK(cudaFuncSetAttribute(update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(h->Cmax)));
   CK(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem_bytes(h->Smax)));
   rc = init_particles(h);
   if (rc) { free_state(h); delete h; return rc; }
@@ -325,9 +327,11 @@ static int ensure_cand(phdslam* h, size_t particles) {
   size_t need = particles * (size_t)h->Smax * 2;
   if (h->cand_cap >= need) return 0;
   cudaFree(h->cand);
-  h->cand = nullptr;
+  cudaFree(h->cand_in);
+  h->cand = h->cand_in = nullptr;
   h->cand_cap = 0;
   CK(cudaMalloc(&h->cand, need * sizeof(float4)));
+  CK(cudaMalloc(&h->cand_in, need * sizeof(float4)));
   h->cand_cap = need;
   return 0;
 }
@@ -342,43 +346,51 @@ static int ensure_dense(phdslam* h, size_t floats) {
   return 0;
 }
 
-/* Particles stream through the dense buffer in batches [p0, p1) whose padded term total fits the budget. */
-static int plan_batches(phdslam* h, std::vector<int>& bounds, size_t* max_batch_terms) {
+/* Particles stream through the scratch buffers in batches [p0, p1): the dense update-term buffer (dense mode,
+ * bounded by update_buffer_bytes) and the merge candidate records (bounded by PHD_CAND_BUDGET). */
+#define PHD_CAND_BUDGET (8ull << 30)
+static int plan_batches(phdslam* h, bool dense, std::vector<int>& bounds, size_t* max_batch_terms) {
   const int n = h->n_local;
   const unsigned long long total = h->red_host->total_terms;
   const unsigned long long budget_terms = std::max<unsigned long long>(h->cfg.update_buffer_bytes / (PHD_NPLANES * 4), 1);
+  int per = (int)std::min<unsigned long long>((unsigned long long)n, std::max<unsigned long long>(PHD_CAND_BUDGET / ((size_t)h->Smax * 64), 1));
+  *max_batch_terms = 0;
+  if (dense) {
+    const unsigned long long maxT = std::max(h->red_host->max_terms, 1);
+    if (maxT > budget_terms) {
+      phdslam_set_error("update_buffer_bytes is smaller than one particle's update terms");
+      return PHDSLAM_ERR_INVALID;
+    }
+    if (total <= budget_terms && per >= n) {
+      *max_batch_terms = (size_t)total;
+    } else {
+      per = (int)std::min<unsigned long long>((unsigned long long)per, std::max<unsigned long long>(budget_terms / maxT, 1));
+      *max_batch_terms = (size_t)std::min<unsigned long long>((unsigned long long)per * maxT, total);
+    }
+  }
   bounds.clear();
-  bounds.push_back(0);
-  if (total <= budget_terms) {
-    bounds.push_back(n);
-    *max_batch_terms = (size_t)total;
-    return 0;
-  }
-  const unsigned long long maxT = std::max(h->red_host->max_terms, 1);
-  if (maxT > budget_terms) {
-    phdslam_set_error("update_buffer_bytes is smaller than one particle's update terms");
-    return PHDSLAM_ERR_INVALID;
-  }
-  int per = (int)std::max<unsigned long long>(budget_terms / maxT, 1);
-  for (int p = per; p < n; p += per) bounds.push_back(p);
+  for (int p = 0; p < n; p += per) bounds.push_back(p);
   bounds.push_back(n);
-  *max_batch_terms = (size_t)per * maxT;
   return 0;
 }
 
-static int launch_update_batch(phdslam* h, int M, int p0, int p1, unsigned long long tbase) {
+static int launch_update_batch(phdslam* h, int M, int p0, int p1, unsigned long long tbase, bool dense) {
   UpdArgs a;
   a.map = h->map[h->cur]; a.count = h->count[h->cur]; a.cls = h->cls; a.pose = h->pose[h->cur];
   a.z = h->z_dev; a.M = M; a.n = h->n_local; a.p0 = p0;
   a.toff = h->toff; a.tbase = tbase; a.dense = h->dense; a.n_in = h->n_in; a.dlogw = h->dlogw; a.c = h->dc;
-  update_dense_kernel<<<p1 - p0, UPD_THREADS, update_smem_bytes(h->Cmax), h->stream>>>(a);
+  a.cand = h->cand_in; a.n_cand = h->n_cand; a.Smax = h->Smax;
+  if (dense)
+    update_kernel<true><<<p1 - p0, UPD_THREADS, update_smem_bytes(h->Cmax), h->stream>>>(a);
+  else
+    update_kernel<false><<<p1 - p0, UPD_THREADS, update_smem_bytes(h->Cmax), h->stream>>>(a);
   LAUNCH_CHECK(h);
   return 0;
 }
 
-static int launch_merge_batch(phdslam* h, int M, int p0, int p1, unsigned long long tbase) {
+static int launch_merge_batch(phdslam* h, int M, int p0, int p1) {
   MrgArgs a;
-  a.dense = h->dense; a.toff = h->toff; a.tbase = tbase; a.n_in = h->n_in; a.M = M; a.n = h->n_local; a.p0 = p0;
+  a.M = M; a.n = h->n_local; a.p0 = p0; a.cand_in = h->cand_in; a.n_cand = h->n_cand;
   a.map_in = h->map[h->cur]; a.count_in = h->count[h->cur]; a.cls = h->cls;
   a.map_out = h->map[h->cur ^ 1]; a.count_out = h->count[h->cur ^ 1];
   a.red = h->red; a.Smax = h->Smax; a.c = h->dc; a.p1 = p1; a.cand = h->cand;
@@ -412,10 +424,13 @@ extern "C" int phdslam_update(phdslam_t* h, const float* z, int M, int fields) {
   if (rc) return rc;
   std::vector<int> bounds;
   size_t max_terms = 0;
-  rc = plan_batches(h, bounds, &max_terms);
+  const bool dense = (h->cfg.update_mode == 0);
+  rc = plan_batches(h, dense, bounds, &max_terms);
   if (rc) return rc;
-  rc = ensure_dense(h, max_terms * PHD_NPLANES);
-  if (rc) return rc;
+  if (dense) {
+    rc = ensure_dense(h, max_terms * PHD_NPLANES);
+    if (rc) return rc;
+  }
   {
     int maxb = 0;
     for (size_t b = 0; b + 1 < bounds.size(); ++b) maxb = std::max(maxb, bounds[b + 1] - bounds[b]);
@@ -433,10 +448,10 @@ extern "C" int phdslam_update(phdslam_t* h, const float* z, int M, int fields) {
   const bool multi = bounds.size() > 2;
   for (size_t b = 0; b + 1 < bounds.size(); ++b) {
     CK(cudaEventRecord(h->ev[3], h->stream));
-    rc = launch_update_batch(h, M, bounds[b], bounds[b + 1], tb[b]);
+    rc = launch_update_batch(h, M, bounds[b], bounds[b + 1], tb[b], dense);
     if (rc) return rc;
     CK(cudaEventRecord(h->ev[4], h->stream));
-    rc = launch_merge_batch(h, M, bounds[b], bounds[b + 1], tb[b]);
+    rc = launch_merge_batch(h, M, bounds[b], bounds[b + 1]);
     if (rc) return rc;
     CK(cudaEventRecord(h->ev[5], h->stream));
     if (multi) {
@@ -486,7 +501,9 @@ extern "C" int phdslam_update_terms(phdslam_t* h, const float* z, int M, int fie
   rc = ensure_dense(h, total * PHD_NPLANES);
   if (rc) return rc;
   CK(cudaEventRecord(h->ev[3], h->stream));
-  rc = launch_update_batch(h, M, 0, n, 0);
+  rc = ensure_cand(h, (size_t)n);
+  if (rc) return rc;
+  rc = launch_update_batch(h, M, 0, n, 0, true);
   if (rc) return rc;
   CK(cudaEventRecord(h->ev[4], h->stream));
   CK(cudaStreamSynchronize(h->stream));

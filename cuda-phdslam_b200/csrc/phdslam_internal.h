@@ -74,7 +74,8 @@ struct phdslam {
   unsigned long long* toff;          /* [n_local+1] exclusive scan */
   unsigned long long* scan_tmp;      /* block sums */
   float* dense; size_t dense_floats; /* dense update-term buffer */
-  float4* cand; size_t cand_cap;     /* merge candidate records (2 x float4 each) */
+  float4* cand; float4* cand_in; size_t cand_cap; /* merge candidate records (2 x float4 each): ordered scratch / update output */
+  int* n_cand;                       /* [n_local] candidates emitted by the update kernel */
   float* z_dev;                      /* [3][256]: range, bearing, label */
   double* draws_dev; size_t draws_cap;
   unsigned long long* q_fx;          /* [n_local] Q40 weights */

@@ -58,11 +58,14 @@ PHD_HD uint32_t phd_f2u(float f) {
 #endif
 }
 
-/* exp(x); results below FLT_MIN flush to 0, x > 88 returns +inf. */
+/* exp(x); results below FLT_MIN flush to 0, x > 88 returns +inf.
+ * n = round(x*log2(e)) is taken with the 1.5*2^23 magic constant inside one fused multiply-add, so the
+ * scalar function and the packed fp32x2 form used by the update kernel (FFMA2) are the same arithmetic. */
 PHD_HD float phd_expf(float x) {
   if (!(x >= -87.3f)) return (x != x) ? x : 0.0f;
   if (x > 88.0f) return INFINITY;
-  float n = rintf(x * 1.44269504088896341f);
+  float nm = fmaf(x, 1.44269504088896341f, 12582912.0f);
+  float n = nm - 12582912.0f;
   float r = fmaf(n, -0.693359375f, x);
   r = fmaf(n, 2.12194440e-4f, r);
   float z = r * r;
@@ -74,9 +77,8 @@ PHD_HD float phd_expf(float x) {
   p = fmaf(p, r, 5.0000001201e-1f);
   p = fmaf(p, z, r);
   p = p + 1.0f;
-  /* p in [0.7,1.5]; scale by 2^n with n in [-126,127] */
-  int e = (int)n;
-  return p * phd_u2f((uint32_t)(e + 127) << 23);
+  /* p in [0.7,1.5]; scale by 2^n, n in [-126,127] = low mantissa bits of nm */
+  return p * phd_u2f(((phd_f2u(nm) - 0x4B400000u) + 127u) << 23);
 }
 
 /* log(x) for x > 0 (denormals handled); caller handles x <= 0 (phd_safe_log). */

@@ -53,22 +53,26 @@ static float float_ceil(double d) {
   return f;
 }
 
-/* Canonical reduction shape of the kernels: 32 lane-strided sequential partial sums,
- * then an xor-butterfly (offsets 16,8,4,2,1).  Stands in for the reference's 256-wide
+/* Canonical reduction shape of the kernels: each of the 32 lanes owns two adjacent elements of every
+ * 64-element chunk and keeps one sequential partial sum per element slot (a packed fp32x2 accumulator),
+ * i.e. 64 strided partials p[i] = sum_k v[64k+i]; the two slots of a lane are added, then an
+ * xor-butterfly (offsets 16,8,4,2,1) runs over the lanes.  Stands in for the reference's 256-wide
  * shared-memory tree (sumByReduction, src/device_math.cuh:452-472). */
 static float warp_sum(const float* v, int n) {
-  float p[32];
-  for (int l = 0; l < 32; ++l) {
+  float p[64];
+  for (int l = 0; l < 64; ++l) {
     float acc = 0.0f;
-    for (int i = l; i < n; i += 32) acc = acc + v[i];
+    for (int i = l; i < n; i += 64) acc = acc + v[i];
     p[l] = acc;
   }
+  float q[32];
+  for (int l = 0; l < 32; ++l) q[l] = p[2 * l] + p[2 * l + 1];
   for (int off = 16; off >= 1; off >>= 1) {
-    float q[32];
-    for (int l = 0; l < 32; ++l) q[l] = p[l] + p[l ^ off];
-    memcpy(p, q, sizeof(p));
+    float t[32];
+    for (int l = 0; l < 32; ++l) t[l] = q[l] + q[l ^ off];
+    memcpy(q, t, sizeof(q));
   }
-  return p[0];
+  return q[0];
 }
 
 extern "C" float oracle_warp_sum(const float* v, int n) { return warp_sum(v, n); }
@@ -312,7 +316,9 @@ static void update_particle(const phdslam_config_t& c, const Pose& pose, const s
     nd = f;
     nd.weight = f.weight * (1.0f - pd);
   }
-  /* detection terms, measurement-major (:1898-1923, copied by :2144-2151) */
+  /* detection terms, measurement-major (:1898-1923, copied by :2144-2151).  Canonical arithmetic of the
+   * per-(component, measurement) inner loop: every multiply-add is an explicit fused multiply-add (the
+   * reference's own build contracts them too: nvcc defaults to -fmad=true); <= 1 ulp from the unfused text. */
   for (int m = 0; m < M; ++m) {
     float zr = z[m * fields], zb = z[m * fields + 1];
     int label = fields > 2 ? (int)z[m * fields + 2] : 0;
@@ -323,13 +329,15 @@ static void update_particle(const phdslam_config_t& c, const Pose& pose, const s
       float innov0 = zr - rj[i];
       float innov1 = phd_wrap_angle(zb - bj[i]);
       G2& t = out.terms[C + m * C + i];
-      t.mean[0] = f.mean[0] + Ki[0] * innov0 + Ki[2] * innov1;
-      t.mean[1] = f.mean[1] + Ki[1] * innov0 + Ki[3] * innov1;
+      t.mean[0] = fmaf(Ki[2], innov1, fmaf(Ki[0], innov0, f.mean[0]));
+      t.mean[1] = fmaf(Ki[3], innov1, fmaf(Ki[1], innov0, f.mean[1]));
       for (int n = 0; n < 4; ++n) t.cov[n] = covu[4 * i + n];
-      float dist = innov0 * innov0 * Si[0] + innov0 * innov1 * (Si[1] + Si[2]) + innov1 * innov1 * Si[3];
-      float g = -0.5f * dist - PHD_LOG_2PI_F - 0.5f * logdet[i];           /* :1911 */
+      float dist = (innov0 * innov0) * Si[0];
+      dist = fmaf(innov0 * innov1, Si[1] + Si[2], dist);
+      dist = fmaf(innov1 * innov1, Si[3], dist);
+      float g = fmaf(dist, -0.5f, -PHD_LOG_2PI_F) + (-(0.5f * logdet[i]));        /* :1911 */
       if (label == 0 || !c.labeled_measurements)
-        t.weight = phd_safe_log(pdv[i]) + phd_safe_log(f.weight) + g;       /* :1916-1917, log domain */
+        t.weight = (phd_safe_log(pdv[i]) + phd_safe_log(f.weight)) + g;            /* :1916-1917, log domain */
       else
         t.weight = phd_safe_log(0.0f);
     }
@@ -380,12 +388,14 @@ static void update_particle(const phdslam_config_t& c, const Pose& pose, const s
   }
 }
 
-/* computeMahalDist (src/device_math.cuh:309-325) with invert_matrix2 (:61-70) */
+/* computeMahalDist (src/device_math.cuh:309-325) with invert_matrix2 (:61-70).  Canonical deviation: the
+ * four divisions by det are one reciprocal and four products (<= 1 ulp per entry). */
 static float mahal(const G2& a, const G2& b) {
   float sigma[4], inv[4];
   for (int i = 0; i < 4; ++i) sigma[i] = (a.cov[i] + b.cov[i]) / 2.0f;
   float det = sigma[0] * sigma[3] - sigma[2] * sigma[1];
-  inv[0] = sigma[3] / det; inv[1] = -sigma[1] / det; inv[2] = -sigma[2] / det; inv[3] = sigma[0] / det;
+  float rdet = 1.0f / det;
+  inv[0] = sigma[3] * rdet; inv[1] = -sigma[1] * rdet; inv[2] = -sigma[2] * rdet; inv[3] = sigma[0] * rdet;
   float i0 = a.mean[0] - b.mean[0];
   float i1 = a.mean[1] - b.mean[1];
   return i0 * i0 * inv[0] + i0 * i1 * (inv[1] + inv[2]) + i1 * i1 * inv[3];
@@ -462,8 +472,9 @@ static void merge_mixture(const phdslam_config_t& c, const std::vector<G2>& cand
     }
     if (wsum == 0.0f) break;                                            /* :2821-2822 */
     mg.weight = wsum;
-    mg.mean[0] = m0 / wsum;                                             /* :2823-2829 */
-    mg.mean[1] = m1 / wsum;
+    const float rw = 1.0f / wsum;      /* canonical: one reciprocal instead of the reference's six divisions */
+    mg.mean[0] = m0 * rw;                                               /* :2823-2829 */
+    mg.mean[1] = m1 * rw;
     float cv[4] = {0, 0, 0, 0};
     for (int i : members) {                                             /* :2836-2872 */
       float d[2] = {mg.mean[0] - cand[i].mean[0], mg.mean[1] - cand[i].mean[1]};
@@ -471,7 +482,7 @@ static void merge_mixture(const phdslam_config_t& c, const std::vector<G2>& cand
         for (int k = 0; k < 2; ++k) cv[j * 2 + k] = cv[j * 2 + k] + cand[i].weight * (cand[i].cov[j * 2 + k] + d[j] * d[k]);
       merged[i] = 1;
     }
-    for (int j = 0; j < 4; ++j) mg.cov[j] = cv[j] / wsum;               /* :2874-2881 */
+    for (int j = 0; j < 4; ++j) mg.cov[j] = cv[j] * rw;                 /* :2874-2881 */
     mg.cov[1] = (mg.cov[1] + mg.cov[2]) / 2.0f;                         /* force_symmetric_covariance, device_math.cuh:710-725 */
     mg.cov[2] = mg.cov[1];
     out.push_back(mg);

@@ -70,13 +70,14 @@ def test_warp_sum_shape():
     lib = O.load()
     v = np.random.default_rng(3).uniform(0, 1, 1000).astype(np.float32)
     got = lib.oracle_warp_sum(v.ctypes.data, len(v))
-    # same tree in numpy
-    p = np.zeros(32, dtype=np.float32)
-    for l in range(32):
+    # same tree in numpy: 64 strided partials, adjacent pairs added, xor butterfly over 32 lanes
+    p = np.zeros(64, dtype=np.float32)
+    for l in range(64):
         acc = np.float32(0)
-        for x in v[l::32]:
+        for x in v[l::64]:
             acc = np.float32(acc + x)
         p[l] = acc
+    p = (p[0::2] + p[1::2]).astype(np.float32)
     for off in (16, 8, 4, 2, 1):
         p = (p + p[np.arange(32) ^ off]).astype(np.float32)
     assert got == p[0]
