@@ -8,9 +8,10 @@
  *   pose   [6][N]            SoA planes px,py,ptheta,vx,vy,vtheta
  *   map    [N][6][Cmax]      per particle one contiguous block of 6 planes {w,mx,my,pxx,pxy,pyy};
  *                            a CTA reads its particle's block with fully coalesced 128-byte requests
- *   dense  per particle p a block of 7 planes {c0,c1,c2,c3,mx,my,w} of Tpad_p terms each, at float
- *          offset 7*toff[p]; term order inside a plane is the reference's features_update order
- *          [non-detect C | detect m-major M*C | birth M] (src/phdfilter.cu:2123-2124,2137-2166)
+ *   dense  per particle p, at float offset 7*toff[p], its update terms in the reference's features_update order
+ *          [non-detect C | detect m-major M*C | birth M] (src/phdfilter.cu:2123-2124,2137-2166), stored in blocks
+ *          of 64 terms; each block holds the 7 planes {c0,c1,c2,c3,mx,my,w} back to back (7 x 256 B), see
+ *          dense_index()
  */
 #ifndef PHD_KERNELS_CUH
 #define PHD_KERNELS_CUH
@@ -195,7 +196,7 @@ __global__ void classify_kernel(const float* __restrict__ map, const int* __rest
   if (lane == 0) {
     n_in[p] = nin;
     unsigned long long t = (unsigned long long)nin * (unsigned)(M + 1) + (unsigned)M;
-    t = (t + 7ull) & ~7ull; /* planes start on 32-byte sectors */
+    t = (t + 63ull) & ~63ull; /* dense terms are stored in blocks of 64 (see dense_index) */
     tpad[p] = t;
     atomicMax(&red->max_terms, (int)t);
   }
@@ -301,7 +302,12 @@ __global__ void scan_apply_kernel(const unsigned long long* __restrict__ in, int
 /* =========================================================================================== */
 #define UPD_THREADS 256
 #define UPD_WARPS (UPD_THREADS / 32)
-#define UPD_FLOATS_PER_COMP 24
+#define UPD_FLOATS_PER_COMP 25
+#define UPD_NF 17            /* per-component constants kept for the (component, measurement) loop */
+
+/* field order of the shared-memory constant records: one record per PAIR of adjacent components, UPD_NF float2
+ * each (136 bytes; lane-consecutive records are conflict-free for 64-bit shared loads) */
+enum { F_NR = 0, F_NB, F_S0, F_S12, F_S3, F_NHL, F_BASE, F_K0, F_K1, F_K2, F_K3, F_MX, F_MY, F_CU0, F_CU1, F_CU2, F_CU3 };
 
 struct UpdArgs {
   const float* map; const int* count; const uint8_t* cls; const float* pose;
@@ -319,13 +325,16 @@ struct UpdArgs {
 };
 
 static inline size_t update_smem_bytes(int Cmax) {
-  return ((size_t)UPD_FLOATS_PER_COMP * Cmax + 6 * PHD_MAX_MEAS) * sizeof(float);
+  return ((size_t)UPD_FLOATS_PER_COMP * Cmax + 6 * PHD_MAX_MEAS + 64) * sizeof(float);
 }
+
+/* dense layout: terms in blocks of 64; a block stores its 7 planes back to back (7 x 256 bytes), so one
+ * warp iteration of the update kernel writes one contiguous 1792-byte block with immediate plane offsets */
+__host__ __device__ __forceinline__ size_t dense_index(size_t t) { return (t >> 6) * (PHD_NPLANES * 64) + (t & 63); }
 
 __device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
 
-/* phd_expf on two values at once; bit-identical per element to the scalar function
- * (rintf(t) == (t + 1.5*2^23) - 1.5*2^23 for |t| < 2^22, and the low mantissa bits of the biased sum are n). */
+/* phd_expf on two values at once; bit-identical per element to the scalar function */
 __device__ __forceinline__ float2 phd_expf2(float2 x) {
   const float2 nm = __ffma2_rn(x, splat2(1.44269504088896341f), splat2(12582912.0f));
   const float2 n = __fadd2_rn(nm, splat2(-12582912.0f));
@@ -344,61 +353,155 @@ __device__ __forceinline__ float2 phd_expf2(float2 x) {
   sc.x = __uint_as_float(((__float_as_uint(nm.x) - 0x4B400000u) + 127u) << 23);
   sc.y = __uint_as_float(((__float_as_uint(nm.y) - 0x4B400000u) + 127u) << 23);
   float2 v = __fmul2_rn(p, sc);
-  v.x = (x.x >= -87.3f) ? v.x : ((x.x != x.x) ? x.x : 0.0f);
-  v.y = (x.y >= -87.3f) ? v.y : ((x.y != x.y) ? x.y : 0.0f);
+  /* x < -87.3 -> 0, x > 88 -> +inf, NaN propagates through v (same results as the scalar early returns) */
+  v.x = (x.x < -87.3f) ? 0.0f : v.x;
+  v.y = (x.y < -87.3f) ? 0.0f : v.y;
   v.x = (x.x > 88.0f) ? INFINITY : v.x;
   v.y = (x.y > 88.0f) ? INFINITY : v.y;
   return v;
 }
 
-/* phd_wrap_angle on two values, fast path |a| < 2*pi (always true for differences of two wrapped bearings
- * except at exactly +-2*pi, which takes the scalar route) */
-__device__ __forceinline__ float2 phd_wrap_angle2(float2 a) {
-  if (fabsf(a.x) >= PHD_TWO_PI_F || fabsf(a.y) >= PHD_TWO_PI_F)
-    return make_float2(phd_wrap_angle(a.x), phd_wrap_angle(a.y));
+/* phd_wrap_angle for |a| < 2*pi: r = a, or (a -+ 2pi) +- err when |a| >= float(pi) */
+__device__ __forceinline__ float2 wrap_small2(float2 a) {
+  const unsigned sx = __float_as_uint(a.x) & 0x80000000u, sy = __float_as_uint(a.y) & 0x80000000u;
+  const bool px = fabsf(a.x) >= PHD_PI_F, py = fabsf(a.y) >= PHD_PI_F;
   float2 o1, o2;
-  o1.x = (a.x >= PHD_PI_F) ? -PHD_TWO_PI_F : ((a.x <= -PHD_PI_F) ? PHD_TWO_PI_F : 0.0f);
-  o1.y = (a.y >= PHD_PI_F) ? -PHD_TWO_PI_F : ((a.y <= -PHD_PI_F) ? PHD_TWO_PI_F : 0.0f);
-  o2.x = (a.x >= PHD_PI_F) ? PHD_TWO_PI_ERR : ((a.x <= -PHD_PI_F) ? -PHD_TWO_PI_ERR : 0.0f);
-  o2.y = (a.y >= PHD_PI_F) ? PHD_TWO_PI_ERR : ((a.y <= -PHD_PI_F) ? -PHD_TWO_PI_ERR : 0.0f);
+  const unsigned tp = __float_as_uint(PHD_TWO_PI_F), er = __float_as_uint(PHD_TWO_PI_ERR);
+  o1.x = px ? __uint_as_float((sx ^ 0x80000000u) | tp) : 0.0f;   /* -sign(a) * float(2*pi) */
+  o1.y = py ? __uint_as_float((sy ^ 0x80000000u) | tp) : 0.0f;
+  o2.x = px ? __uint_as_float(sx | er) : 0.0f;                   /* sign(a) * (float(2*pi) - 2*pi) */
+  o2.y = py ? __uint_as_float(sy | er) : 0.0f;
   return __fadd2_rn(__fadd2_rn(a, o1), o2);
 }
 
-__device__ __forceinline__ float2 lds2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 lds2(const float2* p) { return *p; }
+
+/* One 64-component chunk of one measurement for one warp: lane owns components jr, jr+1.
+ * PASS 1 accumulates exp(log-weight); PASS 2 normalises, writes the dense terms and emits the prune survivors. */
+template <int PASS, bool TAIL, bool FAST, bool DENSE>
+__device__ __forceinline__ void upd_chunk(const float2* __restrict__ rec, int jr, int C, float2 zr2, float2 zb2, bool dead,
+                                          float2 nL2, float2& acc, float* __restrict__ Dm, bool even, float min_w, int lane,
+                                          int* s_ncand, float4* __restrict__ cand, int Smax, int tbase_m) {
+  bool v0 = true, v1 = true;
+  if (TAIL) {
+    v0 = jr < C;
+    v1 = jr + 1 < C;
+    if (!v0) rec -= (size_t)(jr >> 1) * UPD_NF;        /* masked lanes read record 0 */
+  }
+  const float2 i0 = __fadd2_rn(zr2, lds2(rec + F_NR));
+  float2 a1 = __fadd2_rn(zb2, lds2(rec + F_NB));
+  float2 i1;
+  if (FAST) {
+    i1 = wrap_small2(a1);
+  } else {
+    i1.x = phd_wrap_angle(a1.x);
+    i1.y = phd_wrap_angle(a1.y);
+  }
+  /* NOTE ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false, so the canonical
+   * arithmetic of this loop spells every multiply-add as an explicit fused multiply-add (oracle: fmaf). */
+  float2 d = __fmul2_rn(__fmul2_rn(i0, i0), lds2(rec + F_S0));
+  d = __ffma2_rn(__fmul2_rn(i0, i1), lds2(rec + F_S12), d);
+  d = __ffma2_rn(__fmul2_rn(i1, i1), lds2(rec + F_S3), d);
+  const float2 g = __fadd2_rn(__ffma2_rn(d, splat2(-0.5f), splat2(-PHD_LOG_2PI_F)), lds2(rec + F_NHL));
+  float2 lw = __fadd2_rn(lds2(rec + F_BASE), g);
+  if (dead) lw = splat2(PHD_LOG0);
+  if (PASS == 1) {
+    float2 e = phd_expf2(lw);
+    if (TAIL) {
+      if (!v0) e.x = 0.0f;
+      if (!v1) e.y = 0.0f;
+    }
+    acc = __fadd2_rn(acc, e);
+  } else {
+    float2 wt = phd_expf2(__fadd2_rn(lw, nL2));
+    const float2 m0 = __ffma2_rn(lds2(rec + F_K2), i1, __ffma2_rn(lds2(rec + F_K0), i0, lds2(rec + F_MX)));
+    const float2 m1 = __ffma2_rn(lds2(rec + F_K3), i1, __ffma2_rn(lds2(rec + F_K1), i0, lds2(rec + F_MY)));
+    const float2 c0 = lds2(rec + F_CU0), c1 = lds2(rec + F_CU1), c2 = lds2(rec + F_CU2), c3 = lds2(rec + F_CU3);
+    if (TAIL) {
+      if (!v0) wt.x = 0.0f;
+      if (!v1) wt.y = 0.0f;
+    }
+    const int t = tbase_m + jr;                 /* term index of the first component of the pair */
+    if (DENSE && v0) {
+      if (even) {                               /* t is even: the pair sits in one 64-term block, 8-byte aligned */
+        float2* q = reinterpret_cast<float2*>(Dm + dense_index((size_t)t));
+        __stcs(q, c0); __stcs(q + 32, c1); __stcs(q + 64, c2); __stcs(q + 96, c3);
+        __stcs(q + 128, m0); __stcs(q + 160, m1); __stcs(q + 192, wt);
+      } else {
+        float* q = Dm + dense_index((size_t)t);
+        __stcs(q, c0.x); __stcs(q + 64, c1.x); __stcs(q + 128, c2.x); __stcs(q + 192, c3.x);
+        __stcs(q + 256, m0.x); __stcs(q + 320, m1.x); __stcs(q + 384, wt.x);
+        if (v1) {
+          q = Dm + dense_index((size_t)t + 1);
+          __stcs(q, c0.y); __stcs(q + 64, c1.y); __stcs(q + 128, c2.y); __stcs(q + 192, c3.y);
+          __stcs(q + 256, m0.y); __stcs(q + 320, m1.y); __stcs(q + 384, wt.y);
+        }
+      }
+    }
+    acc = __fadd2_rn(acc, wt);
+    /* survivors of the prune (w >= minFeatureWeight, flags :2308-2319) go to the merge as 32-byte records */
+    const bool k0 = v0 && !(wt.x < min_w), k1 = v1 && !(wt.y < min_w);
+    const unsigned b0 = __ballot_sync(FULL_MASK, k0), b1 = __ballot_sync(FULL_MASK, k1);
+    if (b0 | b1) {
+      const unsigned lt_mask = (1u << lane) - 1u;
+      int slot0 = 0;
+      if (lane == 0) slot0 = atomicAdd(s_ncand, __popc(b0) + __popc(b1));
+      slot0 = __shfl_sync(FULL_MASK, slot0, 0);
+      if (k0) {
+        int slot = slot0 + __popc(b0 & lt_mask);
+        if (slot < Smax) {
+          cand[2 * slot] = make_float4(c0.x, c1.x, c2.x, c3.x);
+          cand[2 * slot + 1] = make_float4(m0.x, m1.x, wt.x, __int_as_float(t));
+        }
+      }
+      if (k1) {
+        int slot = slot0 + __popc(b0) + __popc(b1 & lt_mask);
+        if (slot < Smax) {
+          cand[2 * slot] = make_float4(c0.y, c1.y, c2.y, c3.y);
+          cand[2 * slot + 1] = make_float4(m0.y, m1.y, wt.y, __int_as_float(t + 1));
+        }
+      }
+    }
+  }
+}
+
+template <int PASS, bool FAST, bool DENSE>
+__device__ __forceinline__ float2 upd_measurement(const float2* __restrict__ rec0, int C, float2 zr2, float2 zb2, bool dead,
+                                                  float2 nL2, float* __restrict__ Dm, bool even, float min_w, int lane,
+                                                  int* s_ncand, float4* __restrict__ cand, int Smax, int tbase_m) {
+  float2 acc = make_float2(0.0f, 0.0f);
+  const int nfull = C >> 6;
+  const float2* rec = rec0 + (size_t)lane * UPD_NF;
+  int jr = 2 * lane;
+  for (int k = 0; k < nfull; ++k) {
+    upd_chunk<PASS, false, FAST, DENSE>(rec, jr, C, zr2, zb2, dead, nL2, acc, Dm, even, min_w, lane, s_ncand, cand, Smax, tbase_m);
+    rec += 32 * UPD_NF;
+    jr += 64;
+  }
+  if (C & 63)
+    upd_chunk<PASS, true, FAST, DENSE>(rec, jr, C, zr2, zb2, dead, nL2, acc, Dm, even, min_w, lane, s_ncand, cand, Smax, tbase_m);
+  return acc;
+}
 
 template <bool DENSE>
 __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
   extern __shared__ __align__(16) float smem[];
   const DevCfg& c = a.c;
   const int Cmax = c.Cmax;
-  float* s_w = smem;
+  float2* s_rec = reinterpret_cast<float2*>(smem);          /* (Cmax/2) records of UPD_NF float2 */
+  float* s_w = smem + (size_t)UPD_NF * Cmax;
   float* s_mx = s_w + Cmax;
   float* s_my = s_mx + Cmax;
   float* s_pxx = s_my + Cmax;
   float* s_pxy = s_pxx + Cmax;
   float* s_pyy = s_pxy + Cmax;
-  float* s_nr = s_pyy + Cmax;           /* -range   (so that innovations are packed adds) */
-  float* s_nb = s_nr + Cmax;            /* -bearing */
-  float* s_K0 = s_nb + Cmax;
-  float* s_K1 = s_K0 + Cmax;
-  float* s_K2 = s_K1 + Cmax;
-  float* s_K3 = s_K2 + Cmax;
-  float* s_S0 = s_K3 + Cmax;
-  float* s_S12 = s_S0 + Cmax;
-  float* s_S3 = s_S12 + Cmax;
-  float* s_base = s_S3 + Cmax;          /* log pd + log w */
-  float* s_nhl = s_base + Cmax;         /* -0.5 log det */
-  float* s_cu0 = s_nhl + Cmax;
-  float* s_cu1 = s_cu0 + Cmax;
-  float* s_cu2 = s_cu1 + Cmax;
-  float* s_cu3 = s_cu2 + Cmax;
-  float* s_nd = s_cu3 + Cmax;           /* non-detection weights (scheme-1 particle weighting) */
+  float* s_nd = s_pyy + Cmax;           /* non-detection weights (scheme-1 particle weighting) */
   float* s_tmp = s_nd + Cmax;           /* Cmax + 256 : pd*w, then one birth weight per measurement */
   float* s_zr = s_tmp + Cmax + PHD_MAX_MEAS;
   float* s_zb = s_zr + PHD_MAX_MEAS;
   float* s_zl = s_zb + PHD_MAX_MEAS;
   float* s_L = s_zl + PHD_MAX_MEAS;
-  float* s_ds = s_L + PHD_MAX_MEAS;
+  float* s_ds = s_L + PHD_MAX_MEAS;     /* PHD_MAX_MEAS; the remaining slack covers even padding */
   __shared__ int s_wcnt[UPD_WARPS];
   __shared__ int s_ncand;
 
@@ -449,14 +552,8 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
     __syncthreads();
   }
 
-  const unsigned long long T = (unsigned long long)C * (unsigned)(M + 1) + (unsigned)M;
-  const unsigned long long Tpad = (T + 7ull) & ~7ull;
-  float* D0 = nullptr; float* D1 = nullptr; float* D2 = nullptr; float* D3 = nullptr;
-  float* D4 = nullptr; float* D5 = nullptr; float* D6 = nullptr;
-  if (DENSE) {
-    D0 = a.dense + (a.toff[pl] - a.tbase) * PHD_NPLANES;
-    D1 = D0 + Tpad; D2 = D0 + 2 * Tpad; D3 = D0 + 3 * Tpad; D4 = D0 + 4 * Tpad; D5 = D0 + 5 * Tpad; D6 = D0 + 6 * Tpad;
-  }
+  float* D = nullptr;
+  if (DENSE) D = a.dense + (a.toff[pl] - a.tbase) * PHD_NPLANES;
 
   /* ---- phase 1: per-component EKF constants (preUpdateSynthKernel :1835-1894) + non-detection terms ---- */
   for (int j0 = 0; j0 < C; j0 += UPD_THREADS) {
@@ -496,19 +593,22 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
       float cu2 = (qa * P0 + qb * P1) * qc + (qa * P2 + qb * P3) * qd + K0 * c.var_r * K1 + K2 * c.var_b * K3;
       float cu1 = (qc * P0 + qd * P1) * qa + (qc * P2 + qd * P3) * qb + K0 * c.var_r * K1 + K2 * c.var_b * K3;
       float cu3 = (qc * P0 + qd * P1) * qc + (qc * P2 + qd * P3) * qd + K1 * K1 * c.var_r + K3 * K3 * c.var_b;
-      s_nr[j] = -r; s_nb[j] = -bearing;
-      s_K0[j] = K0; s_K1[j] = K1; s_K2[j] = K2; s_K3[j] = K3;
-      s_S0[j] = S0; s_S12[j] = S1 + S2; s_S3[j] = S3;
-      s_base[j] = phd_safe_log(pd) + phd_safe_log(w);
-      s_nhl[j] = -(0.5f * phd_safe_log(det));
-      s_cu0[j] = cu0; s_cu1[j] = cu1; s_cu2[j] = cu2; s_cu3[j] = cu3;
+      float* rec = reinterpret_cast<float*>(s_rec + (size_t)(j >> 1) * UPD_NF) + (j & 1);
+      rec[2 * F_NR] = -r; rec[2 * F_NB] = -bearing;
+      rec[2 * F_K0] = K0; rec[2 * F_K1] = K1; rec[2 * F_K2] = K2; rec[2 * F_K3] = K3;
+      rec[2 * F_S0] = S0; rec[2 * F_S12] = S1 + S2; rec[2 * F_S3] = S3;
+      rec[2 * F_BASE] = phd_safe_log(pd) + phd_safe_log(w);
+      rec[2 * F_NHL] = -(0.5f * phd_safe_log(det));
+      rec[2 * F_CU0] = cu0; rec[2 * F_CU1] = cu1; rec[2 * F_CU2] = cu2; rec[2 * F_CU3] = cu3;
+      rec[2 * F_MX] = fx; rec[2 * F_MY] = fy;
       s_tmp[j] = pd * w;
       /* non-detection term (:2137-2141) */
       wnd = w * (1.0f - pd);
       s_nd[j] = wnd;
       if (DENSE) {
-        st_stream(D0 + j, P0); st_stream(D1 + j, P1); st_stream(D2 + j, P2); st_stream(D3 + j, P3);
-        st_stream(D4 + j, fx); st_stream(D5 + j, fy); st_stream(D6 + j, wnd);
+        float* q = D + dense_index((size_t)j);
+        st_stream(q, P0); st_stream(q + 64, P1); st_stream(q + 128, P2); st_stream(q + 192, P3);
+        st_stream(q + 256, fx); st_stream(q + 320, fy); st_stream(q + 384, wnd);
       }
       keep = !(wnd < c.min_w);
     }
@@ -527,11 +627,12 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
       }
     }
   }
-  /* pad the pair-wise arrays to an even component count with neutral values */
+  /* an odd component count leaves half a record: fill it with neutral values */
   if (tid == 0 && (C & 1)) {
-    s_nr[C] = 0.0f; s_nb[C] = 0.0f; s_K0[C] = 0.0f; s_K1[C] = 0.0f; s_K2[C] = 0.0f; s_K3[C] = 0.0f;
-    s_S0[C] = 0.0f; s_S12[C] = 0.0f; s_S3[C] = 0.0f; s_base[C] = PHD_LOG0; s_nhl[C] = 0.0f;
-    s_cu0[C] = 0.0f; s_cu1[C] = 0.0f; s_cu2[C] = 0.0f; s_cu3[C] = 0.0f; s_mx[C] = 0.0f; s_my[C] = 0.0f;
+    float* rec = reinterpret_cast<float*>(s_rec + (size_t)(C >> 1) * UPD_NF) + 1;
+#pragma unroll
+    for (int f = 0; f < UPD_NF; ++f) rec[2 * f] = 0.0f;
+    rec[2 * F_BASE] = PHD_LOG0;
   }
   for (int m = tid; m < M; m += UPD_THREADS) s_tmp[C + m] = c.birth_weight;
   __syncthreads();
@@ -552,92 +653,23 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
     const float zr = s_zr[m], zb = s_zb[m];
     const bool dead = c.labeled && (s_zl[m] != 0.0f);
     const float2 zr2 = splat2(zr), zb2 = splat2(zb);
-    float2 acc = make_float2(0.0f, 0.0f);
-    for (int jb = 0; jb < C; jb += 64) {       /* warp-uniform trip count; lanes past the end are masked */
-      const int jr = jb + 2 * lane;
-      const int j = (jr < C) ? jr : 0;
-      const float2 i0 = __fadd2_rn(zr2, lds2(s_nr + j));
-      const float2 i1 = phd_wrap_angle2(__fadd2_rn(zb2, lds2(s_nb + j)));
-      /* NOTE ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false, so the canonical
-       * arithmetic of this loop spells every multiply-add as an explicit fused multiply-add (oracle: fmaf). */
-      float2 d = __fmul2_rn(__fmul2_rn(i0, i0), lds2(s_S0 + j));
-      d = __ffma2_rn(__fmul2_rn(i0, i1), lds2(s_S12 + j), d);
-      d = __ffma2_rn(__fmul2_rn(i1, i1), lds2(s_S3 + j), d);
-      float2 g = __fadd2_rn(__ffma2_rn(d, splat2(-0.5f), splat2(-PHD_LOG_2PI_F)), lds2(s_nhl + j));
-      float2 lw = __fadd2_rn(lds2(s_base + j), g);
-      if (dead) lw = splat2(PHD_LOG0);
-      float2 e = phd_expf2(lw);
-      if (jr >= C) e.x = 0.0f;
-      if (jr + 1 >= C) e.y = 0.0f;
-      acc = __fadd2_rn(acc, e);
-    }
+    /* |zb| < 3.14159 and |bearing| <= float(pi) => |zb - bearing| < float(2*pi): wrap needs no fmod */
+    const bool fast = fabsf(zb) < 3.14159f;
+    const int tbase_m = C + m * C;
+    float2 acc;
+    if (fast)
+      acc = upd_measurement<1, true, DENSE>(s_rec, C, zr2, zb2, dead, splat2(0.0f), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m);
+    else
+      acc = upd_measurement<1, false, DENSE>(s_rec, C, zr2, zb2, dead, splat2(0.0f), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m);
     float sum = warp_butterfly_sum(acc.x + acc.y);
     sum = sum + c.clutter_density;
     sum = sum + c.birth_weight;
     const float L = phd_safe_log(sum);
-    const float2 nL2 = splat2(-L);
-    const size_t toff_m = (size_t)C + (size_t)m * C;
-    float2 wacc = make_float2(0.0f, 0.0f);
-    for (int jb = 0; jb < C; jb += 64) {
-      const int jr = jb + 2 * lane;
-      const bool v0 = (jr < C), v1 = (jr + 1 < C);
-      const int j = v0 ? jr : 0;
-      const float2 i0 = __fadd2_rn(zr2, lds2(s_nr + j));
-      const float2 i1 = phd_wrap_angle2(__fadd2_rn(zb2, lds2(s_nb + j)));
-      /* NOTE ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false, so the canonical
-       * arithmetic of this loop spells every multiply-add as an explicit fused multiply-add (oracle: fmaf). */
-      float2 d = __fmul2_rn(__fmul2_rn(i0, i0), lds2(s_S0 + j));
-      d = __ffma2_rn(__fmul2_rn(i0, i1), lds2(s_S12 + j), d);
-      d = __ffma2_rn(__fmul2_rn(i1, i1), lds2(s_S3 + j), d);
-      float2 g = __fadd2_rn(__ffma2_rn(d, splat2(-0.5f), splat2(-PHD_LOG_2PI_F)), lds2(s_nhl + j));
-      float2 lw = __fadd2_rn(lds2(s_base + j), g);
-      if (dead) lw = splat2(PHD_LOG0);
-      float2 wt = phd_expf2(__fadd2_rn(lw, nL2));
-      const float2 m0 = __ffma2_rn(lds2(s_K2 + j), i1, __ffma2_rn(lds2(s_K0 + j), i0, lds2(s_mx + j)));
-      const float2 m1 = __ffma2_rn(lds2(s_K3 + j), i1, __ffma2_rn(lds2(s_K1 + j), i0, lds2(s_my + j)));
-      const float2 c0 = lds2(s_cu0 + j), c1 = lds2(s_cu1 + j), c2 = lds2(s_cu2 + j), c3 = lds2(s_cu3 + j);
-      if (!v0) wt.x = 0.0f;
-      if (!v1) wt.y = 0.0f;
-      if (DENSE && v0) {
-        const size_t t = toff_m + j;
-        if (even) {
-          __stcs(reinterpret_cast<float2*>(D0 + t), c0); __stcs(reinterpret_cast<float2*>(D1 + t), c1);
-          __stcs(reinterpret_cast<float2*>(D2 + t), c2); __stcs(reinterpret_cast<float2*>(D3 + t), c3);
-          __stcs(reinterpret_cast<float2*>(D4 + t), m0); __stcs(reinterpret_cast<float2*>(D5 + t), m1);
-          __stcs(reinterpret_cast<float2*>(D6 + t), wt);
-        } else {
-          st_stream(D0 + t, c0.x); st_stream(D1 + t, c1.x); st_stream(D2 + t, c2.x); st_stream(D3 + t, c3.x);
-          st_stream(D4 + t, m0.x); st_stream(D5 + t, m1.x); st_stream(D6 + t, wt.x);
-          if (v1) {
-            st_stream(D0 + t + 1, c0.y); st_stream(D1 + t + 1, c1.y); st_stream(D2 + t + 1, c2.y); st_stream(D3 + t + 1, c3.y);
-            st_stream(D4 + t + 1, m0.y); st_stream(D5 + t + 1, m1.y); st_stream(D6 + t + 1, wt.y);
-          }
-        }
-      }
-      wacc = __fadd2_rn(wacc, wt);
-      /* survivors */
-      const bool k0 = v0 && !(wt.x < c.min_w), k1 = v1 && !(wt.y < c.min_w);
-      const unsigned b0 = __ballot_sync(FULL_MASK, k0), b1 = __ballot_sync(FULL_MASK, k1);
-      if (b0 | b1) {
-        int slot0 = 0;
-        if (lane == 0) slot0 = atomicAdd(&s_ncand, __popc(b0) + __popc(b1));
-        slot0 = __shfl_sync(FULL_MASK, slot0, 0);
-        if (k0) {
-          int slot = slot0 + __popc(b0 & lt_mask);
-          if (slot < Smax) {
-            cand[2 * slot] = make_float4(c0.x, c1.x, c2.x, c3.x);
-            cand[2 * slot + 1] = make_float4(m0.x, m1.x, wt.x, __int_as_float((int)(toff_m + j)));
-          }
-        }
-        if (k1) {
-          int slot = slot0 + __popc(b0) + __popc(b1 & lt_mask);
-          if (slot < Smax) {
-            cand[2 * slot] = make_float4(c0.y, c1.y, c2.y, c3.y);
-            cand[2 * slot + 1] = make_float4(m0.y, m1.y, wt.y, __int_as_float((int)(toff_m + j + 1)));
-          }
-        }
-      }
-    }
+    float2 wacc;
+    if (fast)
+      wacc = upd_measurement<2, true, DENSE>(s_rec, C, zr2, zb2, dead, splat2(-L), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m);
+    else
+      wacc = upd_measurement<2, false, DENSE>(s_rec, C, zr2, zb2, dead, splat2(-L), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m);
     float dsum = warp_butterfly_sum(wacc.x + wacc.y);
     /* birth term of measurement m (host loop :3468-3507, normalised at :2232-2242) */
     if (lane == 0) {
@@ -652,16 +684,17 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
       float b3 = J1 * J1 * c.bvar_r + J3 * J3 * c.bvar_b;
       float lb = dead ? PHD_LOG0 : c.log_birth_weight;
       float wb = phd_expf(lb - L);
-      size_t t = (size_t)C + (size_t)M * C + m;
+      const int t = C + M * C + m;
       if (DENSE) {
-        st_stream(D0 + t, b0); st_stream(D1 + t, b1); st_stream(D2 + t, b1); st_stream(D3 + t, b3);
-        st_stream(D4 + t, px + bdx); st_stream(D5 + t, py + bdy); st_stream(D6 + t, wb);
+        float* q = D + dense_index((size_t)t);
+        st_stream(q, b0); st_stream(q + 64, b1); st_stream(q + 128, b1); st_stream(q + 192, b3);
+        st_stream(q + 256, px + bdx); st_stream(q + 320, py + bdy); st_stream(q + 384, wb);
       }
       if (!(wb < c.min_w)) {
         int slot = atomicAdd(&s_ncand, 1);
         if (slot < Smax) {
           cand[2 * slot] = make_float4(b0, b1, b1, b3);
-          cand[2 * slot + 1] = make_float4(px + bdx, py + bdy, wb, __int_as_float((int)t));
+          cand[2 * slot + 1] = make_float4(px + bdx, py + bdy, wb, __int_as_float(t));
         }
       }
       s_L[m] = L;
@@ -1302,20 +1335,20 @@ __global__ void iota_kernel(int* p, int n, int base) {
   if (i < n) p[i] = base + i;
 }
 
-/* dense planes -> reference AoS order (tests / phdslam_update_terms export only) */
+/* blocked dense planes -> reference AoS order (tests / phdslam_update_terms export only) */
 __global__ void dense_export_kernel(const float* __restrict__ dense, const unsigned long long* __restrict__ toff,
                                     unsigned long long tbase, const int* __restrict__ n_in, int M, int p0, int np,
                                     const unsigned long long* __restrict__ out_off, phdslam_gaussian2d_t* __restrict__ out) {
   int pl = p0 + blockIdx.x;
   int C = n_in[pl];
   unsigned long long T = (unsigned long long)C * (unsigned)(M + 1) + (unsigned)M;
-  unsigned long long Tpad = (T + 7ull) & ~7ull;
   const float* D = dense + (toff[pl] - tbase) * PHD_NPLANES;
   phdslam_gaussian2d_t* o = out + out_off[pl];
   for (unsigned long long t = threadIdx.x; t < T; t += blockDim.x) {
+    const float* q = D + dense_index((size_t)t);
     phdslam_gaussian2d_t g;
-    g.cov[0] = D[t]; g.cov[1] = D[Tpad + t]; g.cov[2] = D[2 * Tpad + t]; g.cov[3] = D[3 * Tpad + t];
-    g.mean[0] = D[4 * Tpad + t]; g.mean[1] = D[5 * Tpad + t]; g.weight = D[6 * Tpad + t];
+    g.cov[0] = q[0]; g.cov[1] = q[64]; g.cov[2] = q[128]; g.cov[3] = q[192];
+    g.mean[0] = q[256]; g.mean[1] = q[320]; g.weight = q[384];
     o[t] = g;
   }
   (void)np;
