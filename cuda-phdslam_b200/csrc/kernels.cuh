@@ -741,7 +741,9 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
 /* =========================================================================================== */
 #define MRG_THREADS 128
 #define MRG_WARPS (MRG_THREADS / 32)
-#define MRG_GMAX 16
+#define MRG_GMAX 24          /* grid is at most 24 x 24 cells */
+#define MRG_NCELL (MRG_GMAX * MRG_GMAX)
+#define MRG_STAGE 8          /* members of one merge round staged in shared memory (larger clusters take the general path) */
 
 struct MrgArgs {
   int M, n, p0, p1;
@@ -756,8 +758,8 @@ struct MrgArgs {
 };
 
 __host__ __device__ static inline size_t merge_warp_smem_bytes(int Smax) {
-  /* cell ids (Smax) | 256 counters | 264 cell starts (u16) | order (u16 Smax) | items (u16 Smax) | alive + memb words */
-  return (size_t)Smax + 1024 + 528 + (size_t)Smax * 4 + (size_t)(Smax / 32) * 8;
+  /* staging | cell ids (u16 Smax) | counters (1280 B) | cell starts (u16, 1168 B) | order, items (u16 Smax each) | alive + memb words */
+  return (size_t)MRG_STAGE * 32 + 16 + (size_t)Smax * 2 + 1280 + 1168 + (size_t)Smax * 4 + (size_t)(Smax / 32) * 8;
 }
 static inline size_t merge_smem_bytes(int Smax) { return merge_warp_smem_bytes(Smax) * MRG_WARPS; }
 
@@ -792,6 +794,14 @@ __device__ __forceinline__ float dev_hellinger(float ac0, float ac1, float ac2, 
   dist = dist * sqrtf(detp);
   dist = 1.0f - sqrtf(dist) * phd_expf(eps);
   return dist;
+}
+
+/* largest eigenvalue of a candidate covariance (oracle: merge_lambda_max) */
+__device__ __forceinline__ float dev_lambda_max(float4 cv) {
+  float t = cv.x + cv.w;
+  float det = cv.x * cv.w - cv.y * cv.z;
+  float disc = fmaxf(t * t - 4.0f * det, 0.0f);
+  return 0.5f * (t + sqrtf(disc));
 }
 
 /* exclusive scan of 256 u32 counters held 8 per lane; returns the 8 exclusive prefixes in ex[] */
@@ -864,11 +874,14 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
   const int pl = a.p0 + blockIdx.x * MRG_WARPS + warp;
   if (pl >= a.p1) return;   /* warps are independent: no block barrier below */
 
-  unsigned char* base = smem_raw + (size_t)warp * merge_warp_smem_bytes(Smax);
-  unsigned char* s_cell = base;                                        /* (cy << 4) | cx per candidate */
-  unsigned* s_cnt = (unsigned*)(base + Smax);                          /* 256 counters (radix histogram / cell fill) */
-  unsigned short* s_start = (unsigned short*)(base + Smax + 1024);     /* 257 cell starts */
-  unsigned short* s_order = (unsigned short*)(base + Smax + 1024 + 528);
+  unsigned char* base0 = smem_raw + (size_t)warp * merge_warp_smem_bytes(Smax);
+  float4* s_stage = (float4*)base0;                                    /* MRG_STAGE staged member records */
+  unsigned char* s_perm = base0 + MRG_STAGE * 32;                      /* rank -> staging slot */
+  unsigned char* base = base0 + MRG_STAGE * 32 + 16;
+  unsigned short* s_cell = (unsigned short*)base;                      /* cy * MRG_GMAX + cx per candidate */
+  unsigned* s_cnt = (unsigned*)(base + Smax * 2);                      /* 256 radix counters / 576 packed u16 cell counters */
+  unsigned short* s_start = (unsigned short*)(base + Smax * 2 + 1280); /* MRG_NCELL + 1 cell starts */
+  unsigned short* s_order = (unsigned short*)(base + Smax * 2 + 1280 + 1168);
   unsigned short* s_items = s_order + Smax;
   unsigned* s_alive = (unsigned*)(s_items + Smax);
   unsigned* s_memb = s_alive + Smax / 32;
@@ -902,6 +915,7 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
     for (int i = lane; i < n; i += 32) {
       unsigned sidx = src[i];
       float4 r0 = cin[2 * sidx], r1 = cin[2 * sidx + 1];
+      r1.w = dev_lambda_max(r0);          /* the term index is no longer needed: keep the gate eigenvalue there */
       cand[2 * i] = r0;
       cand[2 * i + 1] = r1;
     }
@@ -916,8 +930,9 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
       int pos = n + __popc(bal & lt_mask);
       if (pos < Smax) {
         float pxy = mp[4 * Cmax + i];
-        cand[2 * pos] = make_float4(mp[3 * Cmax + i], pxy, pxy, mp[5 * Cmax + i]);
-        cand[2 * pos + 1] = make_float4(mp[1 * Cmax + i], mp[2 * Cmax + i], mp[0 * Cmax + i], 0.0f);
+        float4 r0 = make_float4(mp[3 * Cmax + i], pxy, pxy, mp[5 * Cmax + i]);
+        cand[2 * pos] = r0;
+        cand[2 * pos + 1] = make_float4(mp[1 * Cmax + i], mp[2 * Cmax + i], mp[0 * Cmax + i], dev_lambda_max(r0));
       }
     }
     n += __popc(bal);
@@ -928,8 +943,8 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
   }
   __syncwarp();   /* candidate records written by other lanes are read below */
   for (int i = lane; i < n; i += 32) {
-    float4 r0 = cand[2 * i], r1 = cand[2 * i + 1];
-    tmax = fmaxf(tmax, r0.x + r0.w);
+    float4 r1 = cand[2 * i + 1];
+    tmax = fmaxf(tmax, r1.w);
     xmin = fminf(xmin, r1.x); xmax = fmaxf(xmax, r1.x);
     ymin = fminf(ymin, r1.y); ymax = fmaxf(ymax, r1.y);
   }
@@ -952,21 +967,22 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
     radix_pass<1>(cand, s_order, s_items, n, s_cnt, 16, lane);
     radix_pass<1>(cand, s_items, s_order, n, s_cnt, 24, lane);
 
-    /* ---- C. uniform grid over candidate means; cell size >= gate radius ---- */
-    const float rg2 = (c.distance_metric == 0) ? (2.0f * c.min_sep) * tmax : INFINITY;
+    /* ---- C. uniform grid over candidate means; cell size >= the largest gate radius ---- */
+    const bool gated = (c.distance_metric == 0);
+    const float gk = 0.625f * c.min_sep;                 /* pair gate: |d|^2 <= gk * (lam_a + lam_b) */
     int G = 1;
     float cs = 1.0f;
-    {
+    if (gated) {
       float ext = fmaxf(xmax - xmin, ymax - ymin);
-      float rg = sqrtf(rg2) * 1.0001f;
-      if (rg2 >= 0.0f && rg < ext && ext < FLT_MAX) {      /* false for inf / NaN radius or degenerate extent */
+      float rg = sqrtf(gk * (tmax + tmax)) * 1.0001f;    /* tmax = largest eigenvalue among the candidates */
+      if (rg >= 0.0f && rg < ext && ext < FLT_MAX) {     /* false for inf / NaN radius or degenerate extent */
         int g = (int)(ext / rg) + 1;
         if (g > MRG_GMAX) g = MRG_GMAX;
         G = g;
         cs = fmaxf(rg, (ext / (float)g) * 1.0001f);
       }
     }
-    for (int i = lane; i < 256; i += 32) s_cnt[i] = 0;
+    for (int i = lane; i < MRG_NCELL / 2; i += 32) s_cnt[i] = 0;        /* two u16 counters per word */
     __syncwarp();
     for (int i = lane; i < n; i += 32) {
       float4 r1 = cand[2 * i + 1];
@@ -977,33 +993,49 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
         cx = min(max(cx, 0), G - 1);
         cy = min(max(cy, 0), G - 1);
       }
-      int cid = (cy << 4) | cx;
-      s_cell[i] = (unsigned char)cid;
-      atomicAdd(&s_cnt[cid], 1u);
+      int cid = cy * MRG_GMAX + cx;
+      s_cell[i] = (unsigned short)cid;
+      atomicAdd(&s_cnt[cid >> 1], (cid & 1) ? 0x10000u : 1u);
     }
     __syncwarp();
     {
-      unsigned ex[8];
-      warp_scan256(s_cnt, ex, lane);
+      /* exclusive scan of the MRG_NCELL (= 576) counters, 18 per lane */
+      const unsigned short* c16 = (const unsigned short*)s_cnt;
+      unsigned loc[MRG_NCELL / 32], sum = 0;
+#pragma unroll
+      for (int k = 0; k < MRG_NCELL / 32; ++k) {
+        loc[k] = c16[lane * (MRG_NCELL / 32) + k];
+        sum += loc[k];
+      }
+      unsigned inc = sum;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        unsigned t = __shfl_up_sync(FULL_MASK, inc, off);
+        if (lane >= off) inc += t;
+      }
+      unsigned run = inc - sum;
       __syncwarp();
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        s_start[lane * 8 + k] = (unsigned short)ex[k];
-        s_cnt[lane * 8 + k] = 0;       /* becomes the running fill count */
+      for (int k = 0; k < MRG_NCELL / 32; ++k) {
+        s_start[lane * (MRG_NCELL / 32) + k] = (unsigned short)run;
+        run += loc[k];
       }
-      if (lane == 31) s_start[256] = (unsigned short)n;
+      if (lane == 31) s_start[MRG_NCELL] = (unsigned short)n;
     }
+    __syncwarp();
+    for (int i = lane; i < MRG_NCELL / 2; i += 32) s_cnt[i] = 0;        /* becomes the running fill count */
     __syncwarp();
     /* stable scatter in index order */
     for (int b0 = 0; b0 < n; b0 += 32) {
       int i = b0 + lane;
       unsigned cid = (i < n) ? (unsigned)s_cell[i] : (0x80000000u | (unsigned)lane);
       unsigned same = __match_any_sync(FULL_MASK, cid);
-      unsigned before = (i < n) ? s_cnt[cid] : 0u;
+      unsigned short* f16 = (unsigned short*)s_cnt;
+      unsigned before = (i < n) ? f16[cid] : 0u;
       __syncwarp();
       if (i < n) {
         s_items[s_start[cid] + before + __popc(same & lt_mask)] = (unsigned short)i;
-        if ((same & lt_mask) == 0) s_cnt[cid] = before + __popc(same);
+        if ((same & lt_mask) == 0) f16[cid] = (unsigned short)(before + __popc(same));
       }
       __syncwarp();
     }
@@ -1038,34 +1070,38 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
       if (seed < 0) break;
       const float4 A0 = cand[2 * seed], A1 = cand[2 * seed + 1];
       const int scell = s_cell[seed];
-      const int scy = scell >> 4, scx = scell & 15;
+      const int scy = scell / MRG_GMAX, scx = scell - scy * MRG_GMAX;
       const int cx0 = max(scx - 1, 0), cx1 = min(scx + 1, G - 1);
       int beg[3], len[3];
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
         int row = scy + d - 1;
         if (row >= 0 && row < G) {
-          beg[d] = s_start[(row << 4) | cx0];
-          len[d] = (int)s_start[((row << 4) | cx1) + 1] - beg[d];
+          beg[d] = s_start[row * MRG_GMAX + cx0];
+          len[d] = (int)s_start[row * MRG_GMAX + cx1 + 1] - beg[d];
         } else {
           beg[d] = 0;
           len[d] = 0;
         }
       }
       const int tot = len[0] + len[1] + len[2];
-      int nmemb = 0;
+      float wsum = 0.0f, m0 = 0.0f, m1 = 0.0f;
+      float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f, mm0 = 0.0f, mm1 = 0.0f, rw = 0.0f;
+      /* candidates of the 3x3 neighbourhood, 32 per iteration; members stage their record in shared memory */
+      int nm = 0;
       for (int q0 = 0; q0 < tot; q0 += 32) {
         int q = q0 + lane;
         bool memb = false;
         unsigned it = 0;
+        float4 B0 = make_float4(0.f, 0.f, 0.f, 0.f), B1 = B0;
         if (q < tot) {
           int src = (q < len[0]) ? beg[0] + q : ((q < len[0] + len[1]) ? beg[1] + (q - len[0]) : beg[2] + (q - len[0] - len[1]));
           it = s_items[src];
           if ((s_alive[it >> 5] >> (it & 31)) & 1u) {
-            float4 B1 = cand[2 * it + 1];
+            B1 = cand[2 * it + 1];
+            B0 = cand[2 * it];
             float gx = A1.x - B1.x, gy = A1.y - B1.y;
-            if (gx * gx + gy * gy <= rg2) {
-              float4 B0 = cand[2 * it];
+            if (!gated || (gx * gx + gy * gy <= gk * (A1.w + B1.w))) {
               float dist = (c.distance_metric == 0)
                                ? dev_mahal(A0.x, A0.y, A0.z, A0.w, A1.x, A1.y, B0.x, B0.y, B0.z, B0.w, B1.x, B1.y)
                                : dev_hellinger(A0.x, A0.y, A0.z, A0.w, A1.x, A1.y, B0.x, B0.y, B0.z, B0.w, B1.x, B1.y);
@@ -1073,20 +1109,53 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
             }
           }
         }
-        if (memb) atomicOr(&s_memb[it >> 5], 1u << (it & 31));
-        nmemb += __popc(__ballot_sync(FULL_MASK, memb));
+        const unsigned mb = __ballot_sync(FULL_MASK, memb);
+        if (memb) {
+          atomicOr(&s_memb[it >> 5], 1u << (it & 31));
+          int slot = nm + __popc(mb & lt_mask);
+          if (slot < MRG_STAGE) {
+            s_stage[2 * slot] = B0;
+            s_stage[2 * slot + 1] = make_float4(B1.x, B1.y, B1.z, __uint_as_float(it));
+          }
+        }
+        nm += __popc(mb);
       }
       __syncwarp();
-      float wsum = 0.0f, m0 = 0.0f, m1 = 0.0f;
-      float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f, mm0 = 0.0f, mm1 = 0.0f;
-      const bool single = (nmemb == 1) && ((s_memb[seed >> 5] >> (seed & 31)) & 1u);
-      if (single) {
-        /* the seed alone: same operation sequence as the general path with one member */
-        wsum = wsum + A1.z;
-        m0 = m0 + A1.z * A1.x;
-        m1 = m1 + A1.z * A1.y;
+      if (nm <= MRG_STAGE) {
+        /* ---- staged path: rank the (few) members by candidate index, then accumulate from shared memory ---- */
+        if (lane < nm) {
+          unsigned my = __float_as_uint(s_stage[2 * lane + 1].w);
+          int rank = 0;
+          for (int k = 0; k < nm; ++k) rank += (__float_as_uint(s_stage[2 * k + 1].w) < my) ? 1 : 0;
+          s_perm[rank] = (unsigned char)lane;
+          atomicAnd(&s_alive[my >> 5], ~(1u << (my & 31)));     /* retire */
+          s_memb[my >> 5] = 0;
+        }
+        __syncwarp();
+        for (int r = 0; r < nm; ++r) {
+          float4 B1 = s_stage[2 * s_perm[r] + 1];
+          wsum = wsum + B1.z;
+          m0 = m0 + B1.z * B1.x;
+          m1 = m1 + B1.z * B1.y;
+        }
+        if (wsum == 0.0f) {      /* :2821-2822: the reference abandons the remaining components */
+          stop = true;
+        } else {
+          rw = 1.0f / wsum;
+          mm0 = m0 * rw;
+          mm1 = m1 * rw;
+          for (int r = 0; r < nm; ++r) {
+            int sl = s_perm[r];
+            float4 B0 = s_stage[2 * sl], B1 = s_stage[2 * sl + 1];
+            float d0 = mm0 - B1.x, d1 = mm1 - B1.y;
+            v0 = v0 + B1.z * (B0.x + d0 * d0);
+            v1 = v1 + B1.z * (B0.y + d0 * d1);
+            v2 = v2 + B1.z * (B0.z + d1 * d0);
+            v3 = v3 + B1.z * (B0.w + d1 * d1);
+          }
+        }
       } else {
-        /* members in ascending index order; every lane computes the same values */
+        /* ---- general path: members walked in ascending index order through the membership bitmask ---- */
         for (int wg = 0; wg < nwords; wg += 32) {
           const unsigned mword = (wg + lane < nwords) ? s_memb[wg + lane] : 0u;
           for (unsigned hb = __ballot_sync(FULL_MASK, mword != 0u); hb; hb &= hb - 1) {
@@ -1101,24 +1170,12 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
             }
           }
         }
-      }
-      if (wsum == 0.0f) {      /* :2821-2822: the reference abandons the remaining components */
-        stop = true;
-      } else {
-        const float rw = 1.0f / wsum;
-        mm0 = m0 * rw;
-        mm1 = m1 * rw;
-        if (single) {
-          float d0 = mm0 - A1.x, d1 = mm1 - A1.y;
-          v0 = v0 + A1.z * (A0.x + d0 * d0);
-          v1 = v1 + A1.z * (A0.y + d0 * d1);
-          v2 = v2 + A1.z * (A0.z + d1 * d0);
-          v3 = v3 + A1.z * (A0.w + d1 * d1);
-          if (lane == 0) {
-            s_alive[seed >> 5] &= ~(1u << (seed & 31));
-            s_memb[seed >> 5] = 0;
-          }
+        if (wsum == 0.0f) {
+          stop = true;
         } else {
+          rw = 1.0f / wsum;
+          mm0 = m0 * rw;
+          mm1 = m1 * rw;
           for (int wg = 0; wg < nwords; wg += 32) {
             const unsigned mword = (wg + lane < nwords) ? s_memb[wg + lane] : 0u;
             for (unsigned hb = __ballot_sync(FULL_MASK, mword != 0u); hb; hb &= hb - 1) {
@@ -1140,12 +1197,14 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
             }
           }
         }
+      }
+      if (!stop) {
         v0 = v0 * rw; v1 = v1 * rw; v2 = v2 * rw; v3 = v3 * rw;
         v1 = (v1 + v2) / 2.0f;                       /* force_symmetric_covariance */
         if (nout < Cmax) {
-          if (lane == 0) {
-            mo[0 * Cmax + nout] = wsum; mo[1 * Cmax + nout] = mm0; mo[2 * Cmax + nout] = mm1;
-            mo[3 * Cmax + nout] = v0; mo[4 * Cmax + nout] = v1; mo[5 * Cmax + nout] = v3;
+          if (lane < PHD_MAP_PLANES) {       /* lane f stores plane f of the merged component */
+            float val = (lane == 0) ? wsum : (lane == 1) ? mm0 : (lane == 2) ? mm1 : (lane == 3) ? v0 : (lane == 4) ? v1 : v3;
+            mo[lane * Cmax + nout] = val;
           }
         } else if (lane == 0) {
           atomicOr(&a.red->err_flag, 2);

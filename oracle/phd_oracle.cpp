@@ -430,22 +430,27 @@ extern "C" float oracle_hellinger(const G2* a, const G2* b) { return hellinger(*
 /* phdUpdateMergeKernel (src/phdfilter.cu:2707-2898): greedy Gaussian-mixture reduction.
  * Canonical choices where the reference is order-dependent: arg-max ties -> lowest index;
  * cluster sums accumulate sequentially in ascending index order.
- * Canonical gate (Mahalanobis metric only): a candidate can join a cluster only if its squared Euclidean
- * distance to the seed is <= Rg2 = (2*minSeparation)*Tmax, Tmax = largest covariance trace among the
- * candidates.  For positive semi-definite covariances d_M^2 >= |d|^2 / Tmax, so a candidate outside the gate
- * has d_M^2 > 2*minSeparation and the reference would not merge it either; the gate (with its factor-2
- * margin against fp32 rounding) only changes results for numerically degenerate covariances.  It lets the
- * kernel look at a 3x3 neighbourhood of a uniform grid instead of at every candidate. */
-static float merge_gate_radius2(const phdslam_config_t& c, const std::vector<G2>& cand) {
-  if (c.distance_metric != 0) return INFINITY;
-  float tmax = 0.0f;
-  for (const G2& g : cand) tmax = fmaxf(tmax, g.cov[0] + g.cov[3]);
-  return (2.0f * c.min_separation) * tmax;
+ * Canonical gate (Mahalanobis metric only): candidate b can join the cluster of seed a only if
+ *     |mu_a - mu_b|^2 <= (0.625 * minSeparation) * (lam_a + lam_b),
+ * lam = largest eigenvalue of the component's covariance.  For positive semi-definite covariances
+ * d_M^2 >= |d|^2 / lam_max((Pa+Pb)/2) >= |d|^2 / ((lam_a+lam_b)/2), so a candidate outside the gate has
+ * d_M^2 > 1.25*minSeparation and the reference would not merge it either; the gate (with its 25 % margin
+ * against fp32 rounding) only changes results for numerically degenerate covariances.  It lets the kernel
+ * look at a 3x3 neighbourhood of a uniform grid (cell size >= the largest gate radius) instead of at every
+ * candidate. */
+static float merge_lambda_max(const G2& g) {
+  float t = g.cov[0] + g.cov[3];
+  float det = g.cov[0] * g.cov[3] - g.cov[1] * g.cov[2];
+  float disc = fmaxf(t * t - 4.0f * det, 0.0f);
+  return 0.5f * (t + sqrtf(disc));
 }
 
 static void merge_mixture(const phdslam_config_t& c, const std::vector<G2>& cand, std::vector<G2>& out) {
   const int n = (int)cand.size();
-  const float rg2 = merge_gate_radius2(c, cand);
+  const bool gated = (c.distance_metric == 0);
+  const float gk = 0.625f * c.min_separation;
+  std::vector<float> lam(n);
+  for (int i = 0; i < n; ++i) lam[i] = merge_lambda_max(cand[i]);
   std::vector<char> merged(n, 0);
   std::vector<int> members;
   while (true) {
@@ -458,7 +463,7 @@ static void merge_mixture(const phdslam_config_t& c, const std::vector<G2>& cand
     for (int i = 0; i < n; ++i) {
       if (merged[i]) continue;
       float gx = mx.mean[0] - cand[i].mean[0], gy = mx.mean[1] - cand[i].mean[1];
-      if (!(gx * gx + gy * gy <= rg2)) continue;
+      if (gated && !(gx * gx + gy * gy <= gk * (lam[best] + lam[i]))) continue;
       float dist = (c.distance_metric == 0) ? mahal(mx, cand[i]) : hellinger(mx, cand[i]);  /* :2802-2805 */
       if (dist < c.min_separation) members.push_back(i);
     }
