@@ -195,7 +195,9 @@ def run_ours(args, wl):
     filt = PS.PhdSlam(cfg, device=local)
     if world > 1:
         filt.dist_init(rank, world)
-    sc = S.make_scene(P, C, M, seed=rank)
+    assert filt.n_local == P
+    # every rank holds P particles of the same landmark scene (same measurements Z), with its own pose / map jitter
+    sc = S.make_scene(P, C, M, seed=0, particle_seed=rank)
     sc["log_weights"][:] = -np.log(np.float32(P_total))
     S.load_scene(filt, sc)
     filt.snapshot()

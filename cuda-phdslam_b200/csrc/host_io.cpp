@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 
+#include "../../include/phd_detmath.h"
 #include "../../include/phdslam.h"
 
 static thread_local std::string g_last_error;
@@ -316,5 +317,48 @@ extern "C" int phdslam_write_log(const char* path, int layout, const phdslam_pos
   }
   fputc('\n', f);
   fclose(f);
+  return 0;
+}
+
+/* ---- global resampling: which rank holds the ancestor of offspring j ----------------------------------- */
+
+/* Same arithmetic as resample_search_kernel / oracle_resample (canonical integer CDF). */
+extern "C" unsigned long long phdslam_resample_threshold(int j, int n_new, unsigned long long total, const double* uniforms,
+                                                         int resample_mode, unsigned call, unsigned long long seed) {
+  const double interval = 1.0 / (double)n_new;
+  double u;
+  if (uniforms) {
+    u = (resample_mode == 1) ? uniforms[0] : uniforms[1 + (size_t)j];
+  } else {
+    phd_philox4_t r = phd_philox4x32_10((resample_mode == 1) ? 0u : (uint32_t)j, call, PHD_STREAM_RESAMPLE, 0u,
+                                        (uint32_t)seed, (uint32_t)(seed >> 32));
+    u = phd_u01d(r.v[0], r.v[1]);
+  }
+  double rr = (double)j * interval + u * interval;
+  double t = floor(rr * (double)total);
+  unsigned long long R = (t <= 0.0) ? 0ull : (unsigned long long)t;
+  if (R >= total) R = total - 1;
+  return R;
+}
+
+extern "C" int phdslam_plan_migration(int world, const unsigned long long* totals, int n_new, const double* uniforms,
+                                      int resample_mode, unsigned call, unsigned long long seed, int* bounds) {
+  if (world < 1 || n_new < 1) return PHDSLAM_ERR_INVALID;
+  unsigned long long total = 0;
+  for (int r = 0; r < world; ++r) total += totals[r];
+  if (total == 0) return PHDSLAM_ERR_NAN;
+  unsigned long long base = 0;
+  bounds[0] = 0;
+  for (int r = 1; r < world; ++r) {
+    base += totals[r - 1];
+    /* first j with R_j >= base (R_j is non-decreasing in j) */
+    int lo = 0, hi = n_new;
+    while (lo < hi) {
+      int mid = lo + (hi - lo) / 2;
+      if (phdslam_resample_threshold(mid, n_new, total, uniforms, resample_mode, call, seed) >= base) hi = mid; else lo = mid + 1;
+    }
+    bounds[r] = lo;
+  }
+  bounds[world] = n_new;
   return 0;
 }

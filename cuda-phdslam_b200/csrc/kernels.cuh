@@ -1385,6 +1385,35 @@ __global__ void resample_gather_kernel(const int* __restrict__ anc, int n_off, i
     for (int k = lane; k < n_card; k += 32) card_out[(size_t)j * n_card + k] = card_in[(size_t)a * n_card + k];
 }
 
+/* migration: pack the ancestors of `cnt` remote offspring into contiguous staging (one warp per record) */
+__global__ void migrate_pack_kernel(const int* __restrict__ anc, int cnt, int anc_offset, int n_src,
+                                    const float* __restrict__ pose_in, const int* __restrict__ count_in,
+                                    const float* __restrict__ map_in, const float* __restrict__ card_in, int Cmax, int n_card,
+                                    float* __restrict__ pose_out /* [cnt][6] */, int* __restrict__ count_out,
+                                    float* __restrict__ map_out /* [cnt][6*Cmax] */, float* __restrict__ card_out) {
+  int j = blockIdx.x * (blockDim.x >> 5) + warp_id();
+  if (j >= cnt) return;
+  const int lane = lane_id();
+  const int a = anc[j] - anc_offset;
+  if (lane < 6) pose_out[(size_t)j * 6 + lane] = pose_in[(size_t)lane * n_src + a];
+  const int c = count_in[a];
+  if (lane == 0) count_out[j] = c;
+  const float* src = map_in + (size_t)a * PHD_MAP_PLANES * Cmax;
+  float* dst = map_out + (size_t)j * PHD_MAP_PLANES * Cmax;
+  for (int f = 0; f < PHD_MAP_PLANES; ++f)
+    for (int k = lane; k < c; k += 32) dst[f * Cmax + k] = src[f * Cmax + k];
+  if (n_card > 0 && card_in)
+    for (int k = lane; k < n_card; k += 32) card_out[(size_t)j * n_card + k] = card_in[(size_t)a * n_card + k];
+}
+/* migration: received AoS poses -> SoA planes at offspring positions [first, first+cnt) */
+__global__ void migrate_unpack_pose_kernel(const float* __restrict__ pose_in /* [cnt][6] */, int cnt, int first, int n_dst,
+                                           float* __restrict__ pose_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cnt * 6) return;
+  int j = i / 6, k = i - j * 6;
+  pose_out[(size_t)k * n_dst + first + j] = pose_in[i];
+}
+
 __global__ void fill_kernel(float* p, int n, float v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;

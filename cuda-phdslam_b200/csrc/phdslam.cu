@@ -17,6 +17,50 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>
+
+/* NCCL is bound at run time (dlopen), not at link time: a process that also hosts PyTorch must use the one
+ * libnccl.so.2 PyTorch brought along, whichever of the two libraries is loaded first. */
+namespace nccl_rt {
+static void* lib = nullptr;
+static ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+static ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+static ncclResult_t (*CommDestroy)(ncclComm_t);
+static ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+static ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+static ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+static ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+static ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+static ncclResult_t (*GroupStart)();
+static ncclResult_t (*GroupEnd)();
+static const char* (*GetErrorString)(ncclResult_t);
+static bool load() {
+  if (lib) return true;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_LOCAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+  if (!h) return false;
+#define SYM(name) *(void**)(&name) = dlsym(h, "nccl" #name); if (!name) return false;
+  SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(AllReduce) SYM(AllGather) SYM(Broadcast) SYM(Send) SYM(Recv)
+  SYM(GroupStart) SYM(GroupEnd) SYM(GetErrorString)
+#undef SYM
+  lib = h;
+  return true;
+}
+}  // namespace nccl_rt
+#define ncclGetUniqueId nccl_rt::GetUniqueId
+#define ncclCommInitRank nccl_rt::CommInitRank
+#define ncclCommDestroy nccl_rt::CommDestroy
+#define ncclAllReduce nccl_rt::AllReduce
+#define ncclAllGather nccl_rt::AllGather
+#define ncclBroadcast nccl_rt::Broadcast
+#define ncclSend nccl_rt::Send
+#define ncclRecv nccl_rt::Recv
+#define ncclGroupStart nccl_rt::GroupStart
+#define ncclGroupEnd nccl_rt::GroupEnd
+#define ncclGetErrorString nccl_rt::GetErrorString
+
 #include "kernels.cuh"
 #include "phdslam_internal.h"
 
@@ -27,6 +71,16 @@
       phdslam_set_error(std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + \
                         std::to_string(__LINE__) + ")");                                             \
       return PHDSLAM_ERR_CUDA;                                                                       \
+    }                                                                                                \
+  } while (0)
+
+#define CKN(call)                                                                                    \
+  do {                                                                                               \
+    ncclResult_t e__ = (call);                                                                       \
+    if (e__ != ncclSuccess) {                                                                        \
+      phdslam_set_error(std::string(#call) + ": " + ncclGetErrorString(e__) + " (" + __FILE__ + ":" + \
+                        std::to_string(__LINE__) + ")");                                             \
+      return PHDSLAM_ERR_NCCL;                                                                       \
     }                                                                                                \
   } while (0)
 
@@ -114,6 +168,9 @@ static void free_state(phdslam* h) {
   cudaFree(h->cls); cudaFree(h->n_in); cudaFree(h->dlogw); cudaFree(h->tpad); cudaFree(h->toff); cudaFree(h->scan_tmp);
   cudaFree(h->dense); cudaFree(h->z_dev); cudaFree(h->draws_dev); cudaFree(h->q_fx); cudaFree(h->cdf_excl);
   cudaFree(h->ancestors); cudaFree(h->red); cudaFree(h->cand); cudaFree(h->cand_in); cudaFree(h->n_cand);
+  cudaFree(h->mig_map); cudaFree(h->mig_pose); cudaFree(h->mig_count); cudaFree(h->mig_anc); cudaFree(h->mig_card);
+  cudaFree(h->mig_pose_in); cudaFree(h->totals_dev);
+  h->mig_pose_in = nullptr; h->totals_dev = nullptr;
   if (h->red_host) cudaFreeHost(h->red_host);
 }
 
@@ -207,6 +264,7 @@ extern "C" void phdslam_destroy(phdslam_t* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  if (h->nccl_comm) ncclCommDestroy((ncclComm_t)h->nccl_comm);
   free_state(h);
   for (int i = 0; i < 12; ++i) cudaEventDestroy(h->ev[i]);
   cudaStreamDestroy(h->stream);
@@ -232,17 +290,55 @@ extern "C" void* phdslam_stream(phdslam_t* h) { return (void*)h->stream; }
 extern "C" int phdslam_synchronize(phdslam_t* h) { CK(cudaStreamSynchronize(h->stream)); return 0; }
 
 extern "C" int phdslam_dist_unique_id(void* id128) {
-  (void)id128;
-  phdslam_set_error("multi-GPU sharding is not built yet");
-  return PHDSLAM_ERR_NCCL;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  if (!nccl_rt::load()) {
+    phdslam_set_error("libnccl.so.2 not found");
+    return PHDSLAM_ERR_NCCL;
+  }
+  ncclUniqueId id;
+  CKN(ncclGetUniqueId(&id));
+  memcpy(id128, &id, sizeof(id));
+  return 0;
 }
-extern "C" int phdslam_dist_init(phdslam_t* h, int rank, int world, const void* id) {
-  (void)id;
-  if (world == 1 && rank == 0) return 0;
-  (void)h;
-  phdslam_set_error("multi-GPU sharding is not built yet");
-  return PHDSLAM_ERR_NCCL;
+
+/* Shard the particle set: rank r owns global particles [r*N/world, (r+1)*N/world).  Re-allocates the device
+ * state for the local share and joins the NCCL communicator used by the weight statistics (all-reduce) and by
+ * the resampling migration (send/recv).  The reference is single-GPU (src/main.cpp:1445-1453). */
+extern "C" int phdslam_dist_init(phdslam_t* h, int rank, int world, const void* id128) {
+  if (world < 1 || rank < 0 || rank >= world) return PHDSLAM_ERR_INVALID;
+  if (world == 1) return 0;
+  if (h->n_global < world) {
+    phdslam_set_error("fewer particles than ranks");
+    return PHDSLAM_ERR_INVALID;
+  }
+  if (!nccl_rt::load()) {
+    phdslam_set_error("libnccl.so.2 not found");
+    return PHDSLAM_ERR_NCCL;
+  }
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  ncclComm_t comm;
+  CKN(ncclCommInitRank(&comm, world, id, rank));
+  h->nccl_comm = (void*)comm;
+  h->rank = rank;
+  h->world = world;
+  free_state(h);
+  h->dense = nullptr; h->dense_floats = 0; h->cand = h->cand_in = nullptr; h->cand_cap = 0;
+  h->draws_dev = nullptr; h->draws_cap = 0;
+  h->snap_pose = nullptr; h->snap_count = nullptr; h->snap_map = nullptr; h->snap_card = nullptr; h->snap_logw = nullptr;
+  h->mig_map = nullptr; h->mig_cap = 0;
+  const long long N = h->n_global;
+  h->offset = (int)(N * rank / world);
+  h->n_local = (int)(N * (rank + 1) / world) - h->offset;
+  h->cur = 0;
+  int rc = alloc_state(h);
+  if (rc) return rc;
+  return init_particles(h);
 }
+
+static inline int rank_offset(const phdslam* h, int r) { return (int)((long long)h->n_global * r / h->world); }
 
 /* ---- exclusive scan helper ---- */
 static int scan_u64(phdslam* h, const unsigned long long* in, int n, unsigned long long* out /* n+1 */,
@@ -405,8 +501,12 @@ static int update_weights(phdslam* h, bool add) {
   CK(cudaMemsetAsync(h->red, 0, sizeof(Reductions), h->stream));
   weights_add_max_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->logw, add ? h->dlogw : nullptr, n, h->red);
   LAUNCH_CHECK(h);
+  if (h->world > 1) /* global max of the log-weights (ordered-uint keys: max is exact and order independent) */
+    CKN(ncclAllReduce(&h->red->max_key, &h->red->max_key, 1, ncclUint32, ncclMax, (ncclComm_t)h->nccl_comm, h->stream));
   weights_sum_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->logw, n, h->red);
   LAUNCH_CHECK(h);
+  if (h->world > 1) /* integer (Q36) sum: identical on every rank for any GPU count */
+    CKN(ncclAllReduce(&h->red->sum_fx, &h->red->sum_fx, 1, ncclUint64, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
   weights_normalise_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->logw, n, h->red);
   LAUNCH_CHECK(h);
   return 0;
@@ -542,6 +642,11 @@ extern "C" int phdslam_estimate(phdslam_t* h, phdslam_estimate_t* out) {
   CK(cudaMemsetAsync(h->red, 0, sizeof(Reductions), h->stream));
   estimate_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->logw, h->pose[h->cur], n, h->offset, h->red);
   LAUNCH_CHECK(h);
+  if (h->world > 1) {
+    /* neff_fx and pose_fx[6] are adjacent 64-bit integers: one exact integer all-reduce; arg-max key by max */
+    CKN(ncclAllReduce(&h->red->neff_fx, &h->red->neff_fx, 7, ncclUint64, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
+    CKN(ncclAllReduce(&h->red->argmax_key, &h->red->argmax_key, 1, ncclUint64, ncclMax, (ncclComm_t)h->nccl_comm, h->stream));
+  }
   CK(cudaMemcpyAsync(h->red_host, h->red, sizeof(Reductions), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaEventRecord(h->ev[8], h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -559,7 +664,7 @@ extern "C" int phdslam_estimate(phdslam_t* h, phdslam_estimate_t* out) {
   }
   double s2 = (double)r.neff_fx * (1.0 / (double)(1ull << PHD_FX_NEFF_BITS));
   out->neff = (float)(1.0 / s2 / (double)h->n_global);
-  if (h->n_global == 1) { /* main.cpp:381-387 */
+  if (h->n_global == 1 && h->world == 1) { /* main.cpp:381-387 */
     std::vector<float> p(6);
     for (int k = 0; k < 6; ++k) CK(cudaMemcpy(&p[k], h->pose[h->cur] + k, sizeof(float), cudaMemcpyDeviceToHost));
     memcpy(&out->expected_pose, p.data(), 6 * sizeof(float));
@@ -569,6 +674,23 @@ extern "C" int phdslam_estimate(phdslam_t* h, phdslam_estimate_t* out) {
 }
 
 /* ---- resample ---- */
+static int ensure_migration(phdslam* h, size_t records) {
+  if (!h->mig_pose_in) CK(cudaMalloc(&h->mig_pose_in, (size_t)h->n_local * 6 * sizeof(float)));
+  if (!h->totals_dev) CK(cudaMalloc(&h->totals_dev, (size_t)h->world * sizeof(unsigned long long)));
+  if (h->mig_cap >= records) return 0;
+  cudaFree(h->mig_map); cudaFree(h->mig_pose); cudaFree(h->mig_count); cudaFree(h->mig_anc); cudaFree(h->mig_card);
+  h->mig_map = nullptr; h->mig_pose = nullptr; h->mig_count = nullptr; h->mig_anc = nullptr; h->mig_card = nullptr;
+  h->mig_cap = 0;
+  const size_t row = (size_t)PHD_MAP_PLANES * h->Cmax;
+  CK(cudaMalloc(&h->mig_map, records * row * sizeof(float)));
+  CK(cudaMalloc(&h->mig_pose, records * 6 * sizeof(float)));
+  CK(cudaMalloc(&h->mig_count, records * sizeof(int)));
+  CK(cudaMalloc(&h->mig_anc, records * sizeof(int)));
+  if (h->n_card) CK(cudaMalloc(&h->mig_card, records * h->n_card * sizeof(float)));
+  h->mig_cap = records;
+  return 0;
+}
+
 extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms, int* ancestors_out) {
   CK(cudaSetDevice(h->device));
   const int n = h->n_local;
@@ -588,28 +710,104 @@ extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms,
     CK(cudaMemcpyAsync(h->draws_dev, uniforms, need * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     udev = h->draws_dev;
   }
+  const int sysmode = (h->cfg.resample_mode == 1);
   CK(cudaEventRecord(h->ev[9], h->stream));
   resample_weights_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->logw, n, h->q_fx);
   LAUNCH_CHECK(h);
   CK(cudaMemsetAsync(h->red, 0, sizeof(Reductions), h->stream));
   int rc = scan_u64(h, h->q_fx, n, h->cdf_excl, &h->red->cdf_total);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(h->red_host, h->red, sizeof(Reductions), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  const unsigned long long total = h->red_host->cdf_total;
-  if (total == 0) {
-    phdslam_set_error("all particle weights are zero or NaN");
-    return PHDSLAM_ERR_NAN;
-  }
-  resample_search_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->cdf_excl, n, 0ull, total, n_new, h->offset, n, h->offset, udev,
-                                                            h->cfg.resample_mode == 1, h->resample_calls, h->dc.seed_lo,
-                                                            h->dc.seed_hi, h->ancestors);
-  LAUNCH_CHECK(h);
   const int b = h->cur;
+  unsigned long long total = 0, base = 0;
+  std::vector<int> bounds;
+  if (h->world > 1) {
+    /* every rank learns every rank's integer weight total: its CDF offset and the global total follow */
+    rc = ensure_migration(h, 1);
+    if (rc) return rc;
+    CKN(ncclAllGather(&h->red->cdf_total, h->totals_dev, 1, ncclUint64, (ncclComm_t)h->nccl_comm, h->stream));
+    std::vector<unsigned long long> totals(h->world);
+    CK(cudaMemcpyAsync(totals.data(), h->totals_dev, (size_t)h->world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < h->world; ++r) {
+      if (r < h->rank) base += totals[r];
+      total += totals[r];
+    }
+    if (total == 0) {
+      phdslam_set_error("all particle weights are zero or NaN");
+      return PHDSLAM_ERR_NAN;
+    }
+    bounds.resize(h->world + 1);
+    rc = phdslam_plan_migration(h->world, totals.data(), n_new, uniforms, h->cfg.resample_mode, h->resample_calls, h->cfg.seed, bounds.data());
+    if (rc) return rc;
+  } else {
+    CK(cudaMemcpyAsync(h->red_host, h->red, sizeof(Reductions), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    total = h->red_host->cdf_total;
+    if (total == 0) {
+      phdslam_set_error("all particle weights are zero or NaN");
+      return PHDSLAM_ERR_NAN;
+    }
+  }
+  /* offspring of this rank whose ancestor is local (remote ones get -1 and are skipped by the gather) */
+  resample_search_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->cdf_excl, n, base, total, n_new, h->offset, n, h->offset, udev,
+                                                            sysmode, h->resample_calls, h->dc.seed_lo, h->dc.seed_hi, h->ancestors);
+  LAUNCH_CHECK(h);
   resample_gather_kernel<<<cdiv(n, 8), 256, 0, h->stream>>>(h->ancestors, n, h->offset, n, n, h->pose[b], h->pose[b ^ 1],
                                                           h->count[b], h->count[b ^ 1], h->map[b], h->map[b ^ 1],
                                                           h->card[b], h->card[b ^ 1], h->Cmax, h->n_card);
   LAUNCH_CHECK(h);
+  if (h->world > 1) {
+    /* migration: ring of shifts; in shift k this rank serves rank+k and is served by rank-k.  Both ends derive
+     * the same offspring interval from `bounds`, so no counts are exchanged. */
+    ncclComm_t comm = (ncclComm_t)h->nccl_comm;
+    const size_t row = (size_t)PHD_MAP_PLANES * h->Cmax;
+    const int me = h->rank, W = h->world;
+    for (int k = 1; k < W; ++k) {
+      const int d = (me + k) % W, sr = (me - k + W) % W;
+      const int off_d = rank_offset(h, d), end_d = rank_offset(h, d + 1);
+      const int out_lo = std::max(bounds[me], off_d), out_hi = std::min(bounds[me + 1], end_d);
+      const int cnt_out = std::max(out_hi - out_lo, 0);
+      const int in_lo = std::max(bounds[sr], h->offset), in_hi = std::min(bounds[sr + 1], h->offset + n);
+      const int cnt_in = std::max(in_hi - in_lo, 0);
+      if (cnt_out > 0) {
+        rc = ensure_migration(h, (size_t)cnt_out);
+        if (rc) return rc;
+        resample_search_kernel<<<cdiv(cnt_out, 256), 256, 0, h->stream>>>(h->cdf_excl, n, base, total, n_new, out_lo, cnt_out, h->offset,
+                                                                        udev, sysmode, h->resample_calls, h->dc.seed_lo,
+                                                                        h->dc.seed_hi, h->mig_anc);
+        LAUNCH_CHECK(h);
+        migrate_pack_kernel<<<cdiv(cnt_out, 8), 256, 0, h->stream>>>(h->mig_anc, cnt_out, h->offset, n, h->pose[b], h->count[b],
+                                                                    h->map[b], h->card[b], h->Cmax, h->n_card, h->mig_pose,
+                                                                    h->mig_count, h->mig_map, h->mig_card);
+        LAUNCH_CHECK(h);
+      }
+      if (cnt_out > 0 || cnt_in > 0) {
+        CKN(ncclGroupStart());
+        if (cnt_out > 0) {
+          CKN(ncclSend(h->mig_pose, (size_t)cnt_out * 6, ncclFloat, d, comm, h->stream));
+          CKN(ncclSend(h->mig_count, (size_t)cnt_out, ncclInt32, d, comm, h->stream));
+          CKN(ncclSend(h->mig_anc, (size_t)cnt_out, ncclInt32, d, comm, h->stream));
+          CKN(ncclSend(h->mig_map, (size_t)cnt_out * row, ncclFloat, d, comm, h->stream));
+          if (h->n_card) CKN(ncclSend(h->mig_card, (size_t)cnt_out * h->n_card, ncclFloat, d, comm, h->stream));
+        }
+        if (cnt_in > 0) {
+          const size_t first = (size_t)(in_lo - h->offset);
+          CKN(ncclRecv(h->mig_pose_in, (size_t)cnt_in * 6, ncclFloat, sr, comm, h->stream));
+          CKN(ncclRecv(h->count[b ^ 1] + first, (size_t)cnt_in, ncclInt32, sr, comm, h->stream));
+          CKN(ncclRecv(h->ancestors + first, (size_t)cnt_in, ncclInt32, sr, comm, h->stream));
+          CKN(ncclRecv(h->map[b ^ 1] + first * row, (size_t)cnt_in * row, ncclFloat, sr, comm, h->stream));
+          if (h->n_card) CKN(ncclRecv(h->card[b ^ 1] + first * h->n_card, (size_t)cnt_in * h->n_card, ncclFloat, sr, comm, h->stream));
+        }
+        CKN(ncclGroupEnd());
+        if (cnt_in > 0) {
+          migrate_unpack_pose_kernel<<<cdiv((long long)cnt_in * 6, 256), 256, 0, h->stream>>>(h->mig_pose_in, cnt_in, in_lo - h->offset, n,
+                                                                                           h->pose[b ^ 1]);
+          LAUNCH_CHECK(h);
+        }
+      }
+      h->tim.migrated_in += (unsigned long long)cnt_in;
+    }
+  }
   fill_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->logw, n, -phd_logf((float)n_new));
   LAUNCH_CHECK(h);
   CK(cudaMemcpyAsync(h->resample_idx, h->ancestors, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));

@@ -89,6 +89,9 @@ struct phdslam {
   cudaEvent_t ev[12];
   phdslam_timings_t tim;
   void* nccl_comm;
+  /* resampling migration staging (sender side), grown on demand */
+  float* mig_map; float* mig_pose; int* mig_count; int* mig_anc; float* mig_card; float* mig_pose_in; size_t mig_cap;
+  unsigned long long* totals_dev; /* [world] all-gathered local CDF totals */
 };
 
 #endif

@@ -81,14 +81,15 @@ class Estimate(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [("predict_ms", C.c_float), ("update_ms", C.c_float), ("merge_ms", C.c_float), ("weights_ms", C.c_float),
-                ("estimate_ms", C.c_float), ("resample_ms", C.c_float), ("launches", C.c_ulonglong)]
+                ("estimate_ms", C.c_float), ("resample_ms", C.c_float), ("launches", C.c_ulonglong),
+                ("migrated_in", C.c_ulonglong)]
 
 
 # every symbol include/phdslam.h declares (tests/test_abi.py checks the built library exports all of them)
 ABI_SYMBOLS = [
     "phdslam_config_defaults", "phdslam_config_load", "phdslam_config_set", "phdslam_last_error", "phdslam_version",
     "phdslam_create", "phdslam_destroy", "phdslam_set_config", "phdslam_get_config", "phdslam_dist_unique_id",
-    "phdslam_dist_init", "phdslam_predict", "phdslam_update", "phdslam_estimate", "phdslam_map_estimate",
+    "phdslam_dist_init", "phdslam_plan_migration", "phdslam_resample_threshold", "phdslam_predict", "phdslam_update", "phdslam_estimate", "phdslam_map_estimate",
     "phdslam_resample", "phdslam_step", "phdslam_n_local", "phdslam_local_offset", "phdslam_get_poses",
     "phdslam_set_poses", "phdslam_get_log_weights", "phdslam_set_log_weights", "phdslam_get_map_sizes",
     "phdslam_get_maps", "phdslam_set_maps", "phdslam_get_resample_idx", "phdslam_get_cardinalities",
@@ -138,6 +139,9 @@ def load_library(path=None):
     lib.phdslam_update_terms.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     lib.phdslam_dist_unique_id.argtypes = [C.c_void_p]
     lib.phdslam_dist_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.phdslam_plan_migration.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_uint, C.c_ulonglong, C.c_void_p]
+    lib.phdslam_resample_threshold.argtypes = [C.c_int, C.c_int, C.c_ulonglong, C.c_void_p, C.c_int, C.c_uint, C.c_ulonglong]
+    lib.phdslam_resample_threshold.restype = C.c_ulonglong
     lib.phdslam_load_measurements.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_float)),
                                               C.POINTER(C.POINTER(C.c_int)), C.POINTER(C.c_int)]
     lib.phdslam_load_controls.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int)]
@@ -215,6 +219,27 @@ def _ptr(a):
     return None if a is None else a.ctypes.data
 
 
+def dist_unique_id():
+    buf = np.zeros(128, dtype=np.uint8)
+    _check(load_library().phdslam_dist_unique_id(buf.ctypes.data))
+    return buf.tobytes()
+
+
+def plan_migration(totals, n_new, uniforms=None, resample_mode=0, call=0, seed=0):
+    """Host-side planning of the global resampling exchange (phdslam_plan_migration): bounds[r] = first offspring
+    whose ancestor lives on a rank >= r."""
+    t = np.ascontiguousarray(totals, dtype=np.uint64)
+    u = None if uniforms is None else np.ascontiguousarray(uniforms, dtype=np.float64)
+    bounds = np.zeros(len(t) + 1, dtype=np.int32)
+    _check(load_library().phdslam_plan_migration(len(t), t.ctypes.data, n_new, _ptr(u), resample_mode, call, seed, bounds.ctypes.data))
+    return bounds
+
+
+def resample_threshold(j, n_new, total, uniforms=None, resample_mode=0, call=0, seed=0):
+    u = None if uniforms is None else np.ascontiguousarray(uniforms, dtype=np.float64)
+    return int(load_library().phdslam_resample_threshold(j, n_new, total, _ptr(u), resample_mode, call, seed))
+
+
 class PhdSlam(object):
     """One filter instance on one GPU (opaque phdslam_t handle with persistent device state)."""
 
@@ -234,6 +259,28 @@ class PhdSlam(object):
             self.close()
         except Exception:
             pass
+
+    def dist_init(self, rank, world, unique_id=None):
+        """Shard the particles over `world` ranks (one process per GPU).  unique_id: 128-byte ncclUniqueId made by
+        rank 0 with dist_unique_id(); when None it is created on rank 0 and broadcast through torch.distributed."""
+        if world == 1:
+            return
+        if unique_id is None:
+            import torch
+            import torch.distributed as dist
+            buf = np.zeros(128, dtype=np.uint8)
+            if rank == 0:
+                _check(self.lib.phdslam_dist_unique_id(buf.ctypes.data))
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+            t = torch.from_numpy(buf).to(dev)
+            dist.broadcast(t, src=0)
+            unique_id = t.cpu().numpy().tobytes()
+        idb = (C.c_char * 128).from_buffer_copy(unique_id)
+        _check(self.lib.phdslam_dist_init(self._h, rank, world, idb))
+
+    @property
+    def local_offset(self):
+        return self.lib.phdslam_local_offset(self._h)
 
     # ---- reference-named operations -------------------------------------------------------------
     def setDeviceConfig(self, cfg):
@@ -258,6 +305,7 @@ class PhdSlam(object):
         return e
 
     def resampleParticles(self, uniforms=None):
+        """uniforms: n_global+1 injected draws (the same array on every rank), or None for the counter-based RNG."""
         n = self.n_local
         u = None if uniforms is None else np.ascontiguousarray(uniforms, dtype=np.float64)
         anc = np.empty(n, dtype=np.int32)

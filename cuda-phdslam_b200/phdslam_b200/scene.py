@@ -24,17 +24,20 @@ def scene_config(P, C, M, max_components=None, **overrides):
     return default_config(**kw)
 
 
-def make_scene(P, C, M, seed=0, n_far=0, n_near=0, max_range=15.0, std_range=0.25, std_bearing=0.008727):
+def make_scene(P, C, M, seed=0, n_far=0, n_near=0, max_range=15.0, std_range=0.25, std_bearing=0.008727, particle_seed=None):
     """Returns dict(poses, log_weights, sizes, maps, Z).
 
     n_far / n_near add components per particle outside the field of view ("far", class 0) and in the
     "nearly in range" shell (class 2) so that the in-range split is exercised.
     """
     rng = np.random.Generator(np.random.Philox(seed))
+    # per-particle randomness (poses, map jitter) may come from its own stream so that several ranks can share
+    # one landmark scene and one measurement set while holding different particles
+    prng = rng if particle_seed is None else np.random.Generator(np.random.Philox([seed, 1000003 + particle_seed]))
     poses = np.zeros(P, dtype=POSE_DTYPE)
-    poses["px"] = rng.normal(0, 0.1, P)
-    poses["py"] = rng.normal(0, 0.1, P)
-    poses["ptheta"] = rng.normal(0, 0.01, P)
+    poses["px"] = prng.normal(0, 0.1, P)
+    poses["py"] = prng.normal(0, 0.1, P)
+    poses["ptheta"] = prng.normal(0, 0.01, P)
 
     def ring(n, r_lo, r_hi):
         r = np.sqrt(rng.uniform(r_lo * r_lo, r_hi * r_hi, n))
@@ -60,7 +63,7 @@ def make_scene(P, C, M, seed=0, n_far=0, n_near=0, max_range=15.0, std_range=0.2
     w = rng.uniform(0.1, 1.0, n_all)
 
     maps = np.zeros((P, n_all), dtype=GAUSSIAN_DTYPE)
-    jit = rng.normal(0, 0.05, (P, n_all, 2)).astype(np.float32)
+    jit = prng.normal(0, 0.05, (P, n_all, 2)).astype(np.float32)
     maps["mean"] = (allm[None, :, :] + jit).astype(np.float32)
     maps["cov"][:, :, 0] = pxx[None, :]
     maps["cov"][:, :, 1] = pxy[None, :]

@@ -122,6 +122,16 @@ int phdslam_get_config(const phdslam_t* h, phdslam_config_t* cfg);
  * nccl_unique_id is the 128-byte ncclUniqueId created by rank 0 (phdslam_dist_unique_id) and broadcast by the caller. */
 int phdslam_dist_unique_id(void* id128);
 int phdslam_dist_init(phdslam_t* h, int rank, int world, const void* nccl_unique_id128);
+/* Host-only planning of the global resampling exchange (no GPU, no NCCL; also used by the CPU tests).
+ * totals[r] = rank r's sum of Q40 fixed-point weights (phd_detmath.h PHD_FX_CDF_BITS).  On return
+ * bounds[r] (r = 0..world) is the first offspring index j whose ancestor lives on a rank >= r, so offspring
+ * j has its ancestor on rank s iff bounds[s] <= j < bounds[s+1] (thresholds are monotone in j).
+ * uniforms: NULL -> counter-based RNG keyed by (seed, call), else n_new+1 injected draws. */
+int phdslam_plan_migration(int world, const unsigned long long* totals, int n_new, const double* uniforms,
+                           int resample_mode, unsigned call, unsigned long long seed, int* bounds);
+/* Offspring threshold R_j = floor(((j + u_j)/n_new) * total) of the canonical resampler (host evaluation). */
+unsigned long long phdslam_resample_threshold(int j, int n_new, unsigned long long total, const double* uniforms,
+                                              int resample_mode, unsigned call, unsigned long long seed);
 
 /* ---- the filter step ---- */
 /* reference: phdPredict(SynthSLAM&, ...) (src/phdfilter.cu:1080-1257) for ONE sub-step.
@@ -190,6 +200,7 @@ int phdslam_update_terms(phdslam_t* h, const float* z, int M, int fields, phdsla
 typedef struct phdslam_timings {
   float predict_ms, update_ms, merge_ms, weights_ms, estimate_ms, resample_ms;
   unsigned long long launches; /* kernels launched by this handle so far */
+  unsigned long long migrated_in; /* particles received from other ranks by resampling so far */
 } phdslam_timings_t;
 /* CUDA-event timings of the most recent call of each phase (events on the handle's stream). */
 int phdslam_get_timings(phdslam_t* h, phdslam_timings_t* out);
