@@ -1,2 +1,169 @@
-// placeholder replaced below
-int main() { return 0; }
+/*
+ * phdslam -- host driver over the C-ABI of libphdslam.so.
+ *
+ * Stands in for the reference's `./bin/cuda-PHDSLAM <config.cfg> [synth]` (src/main.cpp:1442-1514) and its
+ * run_synth() time-step loop (src/main.cpp:1075-1312): same cfg keys, same input text files, and one
+ * state_estimateNNNNN.log per step in the README's 5-line layout (README:31-39; `log_layout = extended` gives the
+ * 7-line layout of writeLog, main.cpp:848-954).  All filter work happens on the GPU inside phdslam_step().
+ *
+ *   phdslam <config.cfg> [synth] [--measurements FILE] [--controls FILE] [--out DIR] [--steps N]
+ *           [--set key=value ...] [--no-header] [--quiet]
+ *
+ * The reference hard-wires <data_directory>/measurements.txt and controls.txt (main.cpp:1079-1086); the two
+ * overrides exist because the bundled files are named measurements_synth_*.txt.  Not built here:
+ * timestamped asynchronous streams (main.cpp:1187-1230), follow_trajectory, the disparity mode.
+ */
+#include <sys/stat.h>
+#include <sys/time.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/phdslam.h"
+
+static double now_ms() {
+  struct timeval tv;
+  gettimeofday(&tv, nullptr);
+  return tv.tv_sec * 1e3 + tv.tv_usec * 1e-3;
+}
+
+#define CHECK(call)                                                               \
+  do {                                                                            \
+    int rc__ = (call);                                                            \
+    if (rc__ != 0) {                                                              \
+      fprintf(stderr, "phdslam: %s failed (%d): %s\n", #call, rc__, phdslam_last_error()); \
+      return 1;                                                                   \
+    }                                                                             \
+  } while (0)
+
+int main(int argc, char** argv) {
+  if (argc < 2) {
+    fprintf(stderr, "usage: %s <config.cfg> [synth] [--measurements FILE] [--controls FILE] [--out DIR] [--steps N] "
+                    "[--set key=value] [--no-header] [--quiet]\n", argv[0]);
+    return 1;
+  }
+  phdslam_config_t cfg;
+  CHECK(phdslam_config_load(argv[1], &cfg));
+  std::string meas_path, ctrl_path, out_dir = ".";
+  int max_steps = -1, has_header = 1;
+  bool quiet = false;
+  for (int i = 2; i < argc; ++i) {
+    std::string a = argv[i];
+    if (a == "synth") continue;
+    if (a == "disparity") {
+      fprintf(stderr, "phdslam: the disparity / stereo mode is outside the hot path and not built\n");
+      return 1;
+    }
+    if (a == "--measurements" && i + 1 < argc) meas_path = argv[++i];
+    else if (a == "--controls" && i + 1 < argc) ctrl_path = argv[++i];
+    else if (a == "--out" && i + 1 < argc) out_dir = argv[++i];
+    else if (a == "--steps" && i + 1 < argc) max_steps = atoi(argv[++i]);
+    else if (a == "--no-header") has_header = 0;
+    else if (a == "--quiet") quiet = true;
+    else if (a == "--set" && i + 1 < argc) {
+      std::string kv = argv[++i];
+      size_t eq = kv.find('=');
+      if (eq == std::string::npos || phdslam_config_set(&cfg, kv.substr(0, eq).c_str(), kv.substr(eq + 1).c_str()) != 0) {
+        fprintf(stderr, "phdslam: bad --set %s\n", kv.c_str());
+        return 1;
+      }
+    } else {
+      fprintf(stderr, "phdslam: unknown argument %s\n", a.c_str());
+      return 1;
+    }
+  }
+  std::string dd = cfg.data_directory;
+  if (!dd.empty() && dd.back() != '/') dd += '/';
+  if (meas_path.empty()) meas_path = dd + "measurements.txt";   /* main.cpp:1079 */
+  if (ctrl_path.empty()) ctrl_path = dd + "controls.txt";       /* main.cpp:1084 */
+
+  float* zdata = nullptr;
+  int* zoff = nullptr;
+  int n_meas_steps = 0;
+  CHECK(phdslam_load_measurements(meas_path.c_str(), cfg.measurement_fields, has_header, &zdata, &zoff, &n_meas_steps));
+  printf("Loaded %d measurements\n", n_meas_steps);
+  float* udata = nullptr;
+  int n_controls = 0;
+  if (cfg.motion_type == 1) {
+    CHECK(phdslam_load_controls(ctrl_path.c_str(), &udata, &n_controls));
+    printf("Loaded %d control inputs\n", n_controls);
+  }
+  int n_steps = n_meas_steps;                                     /* main.cpp:1097 */
+  if (cfg.n_steps > 0 && n_steps > cfg.n_steps) n_steps = cfg.n_steps;   /* :1118 */
+  if (max_steps > 0 && n_steps > max_steps) n_steps = max_steps;
+  if (cfg.follow_trajectory) {
+    fprintf(stderr, "phdslam: follow_trajectory is not built\n");
+    return 1;
+  }
+  mkdir(out_dir.c_str(), 0755);
+
+  phdslam_t* h = nullptr;
+  CHECK(phdslam_create(&cfg, 0, &h));
+  const int P = phdslam_n_local(h);
+  const int n_card = cfg.max_cardinality + 1;
+  std::vector<phdslam_pose_t> poses(P);
+  std::vector<float> logw(P);
+  std::vector<int> ridx(P);
+  std::vector<float> card((size_t)(cfg.filter_type == 1 ? n_card : 1));
+  std::vector<phdslam_gaussian2d_t> map_est(65536);
+  printf("STARTING SIMULATION\n");
+  FILE* tf = fopen((out_dir + "/loopTime.log").c_str(), "w");     /* main.cpp:1300-1305 */
+  for (int n = 0; n < n_steps; ++n) {
+    double t0 = now_ms();
+    if (!quiet) printf("****** Time Step [%d/%d] ******\n", n, n_steps);
+    const int M = zoff[n + 1] - zoff[n];
+    const float* z = zdata + (size_t)zoff[n] * cfg.measurement_fields;
+    const float zero_u[2] = {0.0f, 0.0f};
+    const float* u = zero_u;
+    if (cfg.motion_type == 1 && n > 0) {
+      int ci = n - 1;                                             /* current_control = all_controls[n-1], main.cpp:1234 */
+      if (ci >= n_controls) ci = n_controls - 1;
+      if (ci >= 0) u = udata + 2 * (size_t)ci;
+    }
+    phdslam_estimate_t est;
+    int resampled = 0;
+    int rc = phdslam_step(h, n, u, z, M, cfg.measurement_fields, &est, &resampled);
+    /* state export: recoverSlamState output + particle set (main.cpp:1274-1279) */
+    CHECK(phdslam_get_poses(h, poses.data()));
+    CHECK(phdslam_get_log_weights(h, logw.data()));
+    CHECK(phdslam_get_resample_idx(h, ridx.data()));
+    int n_map = 0;
+    if (cfg.map_estimate & 3) {
+      int which = (cfg.map_estimate & 2) ? 2 : 1;
+      int mrc = phdslam_map_estimate(h, which, map_est.data(), (int)map_est.size(), &n_map);
+      if (mrc != 0) {
+        fprintf(stderr, "phdslam: map estimate failed: %s\n", phdslam_last_error());
+        n_map = 0;
+      }
+    }
+    char name[64];
+    snprintf(name, sizeof(name), "/state_estimate%05d.log", n);
+    CHECK(phdslam_write_log((out_dir + name).c_str(), cfg.log_layout, &est.expected_pose, map_est.data(), n_map, logw.data(),
+                            poses.data(), P, ridx.data(), cfg.filter_type == 1 ? card.data() : nullptr, n_card, cfg.filter_type));
+    double el = now_ms() - t0;
+    if (tf) fprintf(tf, "%g\n", el);
+    if (!quiet)
+      printf("pose %.4f %.4f %.4f  nEff %.4f%s  %.2f ms\n", est.expected_pose.px, est.expected_pose.py, est.expected_pose.ptheta,
+             est.neff, resampled ? "  [resampled]" : "", el);
+    if (rc == PHDSLAM_ERR_NAN) {
+      printf("nan weights detected! exiting...\n");                /* main.cpp:1307-1311 */
+      break;
+    }
+    if (rc != 0) {
+      fprintf(stderr, "phdslam: step %d failed (%d): %s\n", n, rc, phdslam_last_error());
+      return 1;
+    }
+  }
+  if (tf) fclose(tf);
+  phdslam_timings_t t;
+  phdslam_get_timings(h, &t);
+  printf("done: %d steps, %llu kernel launches\n", n_steps, t.launches);
+  phdslam_destroy(h);
+  phdslam_free(zdata);
+  phdslam_free(zoff);
+  phdslam_free(udata);
+  return 0;
+}

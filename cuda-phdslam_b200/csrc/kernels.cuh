@@ -1423,6 +1423,138 @@ __global__ void iota_kernel(int* p, int n, int base) {
   if (i < n) p[i] = base + i;
 }
 
+/* =========================================================================================== */
+/* EAP map: computeExpectedMap (reference src/main.cpp:290-316) + reduceGaussianMixture            */
+/* (src/gm_reduce.cpp:57-134, host Eigen code in the reference) on the device.                    */
+/* All particles' components, weights scaled by exp(particle log-weight), are concatenated; each   */
+/* round takes the heaviest remaining component (ties: lowest concat index), gathers every         */
+/* remaining component within the Cholesky Mahalanobis distance and moment-matches the cluster.    */
+/* Cluster sums are accumulated in double (order independent to < 1 fp32 ulp).                     */
+/* =========================================================================================== */
+struct EapAcc {                 /* per-round accumulators */
+  unsigned long long key;       /* arg-max key: ordered(weight) << 32 | ~global concat index */
+  double w, wx, wy, s0, s1, s2, s3;
+  float seed[8];                /* seed record: c0..c3, x, y, w, valid */
+  int n_out;
+  int pad;
+};
+
+__global__ void eap_concat_kernel(const float* __restrict__ map, const int* __restrict__ count, const float* __restrict__ logw,
+                                  const unsigned long long* __restrict__ off, int n, int Cmax, float4* __restrict__ rec) {
+  int p = blockIdx.x * (blockDim.x >> 5) + warp_id();
+  if (p >= n) return;
+  const int lane = lane_id();
+  const float ew = phd_expf(logw[p]);                 /* map[i].weight *= exp(weights[n]) (main.cpp:301-302) */
+  const float* mp = map + (size_t)p * PHD_MAP_PLANES * Cmax;
+  const int c = count[p];
+  float4* o = rec + 2 * off[p];
+  for (int i = lane; i < c; i += 32) {
+    float pxy = mp[4 * Cmax + i];
+    o[2 * i] = make_float4(mp[3 * Cmax + i], pxy, pxy, mp[5 * Cmax + i]);
+    o[2 * i + 1] = make_float4(mp[1 * Cmax + i], mp[2 * Cmax + i], mp[0 * Cmax + i] * ew, 1.0f);
+  }
+}
+
+__global__ void eap_argmax_kernel(const float4* __restrict__ rec, unsigned long long n_tot, unsigned long long gbase, EapAcc* acc) {
+  unsigned long long key = 0;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_tot;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    float4 r1 = rec[2 * i + 1];
+    if (r1.w != 0.0f) {
+      unsigned long long k = ((unsigned long long)float_to_ordered_uint(r1.z) << 32) | (unsigned long long)(0xffffffffu - (unsigned)(gbase + i));
+      key = (k > key) ? k : key;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    unsigned long long o = __shfl_xor_sync(FULL_MASK, key, off);
+    key = (o > key) ? o : key;
+  }
+  if (lane_id() == 0 && key) atomicMax(&acc->key, key);
+}
+
+/* the rank that owns the global arg-max publishes the seed record (others contribute zeros to the sum) */
+__global__ void eap_seed_kernel(const float4* __restrict__ rec, unsigned long long n_tot, unsigned long long gbase, EapAcc* acc) {
+  if (threadIdx.x != 0) return;
+  for (int k = 0; k < 8; ++k) acc->seed[k] = 0.0f;
+  acc->w = acc->wx = acc->wy = acc->s0 = acc->s1 = acc->s2 = acc->s3 = 0.0;
+  unsigned long long key = acc->key;
+  if (!key) return;
+  unsigned long long g = (unsigned long long)(0xffffffffu - (unsigned)(key & 0xffffffffull));
+  if (g >= gbase && g < gbase + n_tot) {
+    float4 r0 = rec[2 * (g - gbase)], r1 = rec[2 * (g - gbase) + 1];
+    acc->seed[0] = r0.x; acc->seed[1] = r0.y; acc->seed[2] = r0.z; acc->seed[3] = r0.w;
+    acc->seed[4] = r1.x; acc->seed[5] = r1.y; acc->seed[6] = r1.z; acc->seed[7] = 1.0f;
+  }
+}
+
+/* mahalanobisDistance of gm_reduce.cpp:31-38: L L^T = (Pa+Pb)/2, x = L^-1 d, |x|^2 (oracle: mahal_llt) */
+__device__ __forceinline__ float dev_mahal_llt(const float* a, float4 b0, float4 b1) {
+  float s00 = 0.5f * (a[0] + b0.x);
+  float s10 = 0.5f * (a[1] + b0.y);
+  float s11 = 0.5f * (a[3] + b0.w);
+  float d0 = a[4] - b1.x, d1 = a[5] - b1.y;
+  float l00 = sqrtf(s00);
+  float l10 = s10 / l00;
+  float l11 = sqrtf(s11 - l10 * l10);
+  float x0 = d0 / l00;
+  float x1 = (d1 - l10 * x0) / l11;
+  return x0 * x0 + x1 * x1;
+}
+
+__global__ void eap_cluster_kernel(float4* __restrict__ rec, unsigned long long n_tot, unsigned long long gbase, float min_distance,
+                                   EapAcc* acc) {
+  __shared__ float sd[8];
+  if (threadIdx.x < 8) sd[threadIdx.x] = acc->seed[threadIdx.x];
+  __syncthreads();
+  const unsigned long long key = acc->key;
+  if (!key) return;
+  const unsigned long long gseed = (unsigned long long)(0xffffffffu - (unsigned)(key & 0xffffffffull));
+  double w = 0, wx = 0, wy = 0, s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_tot;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    float4 r1 = rec[2 * i + 1];
+    if (r1.w == 0.0f) continue;
+    float4 r0 = rec[2 * i];
+    bool memb = (gbase + i == gseed) || (dev_mahal_llt(sd, r0, r1) < min_distance);
+    if (memb) {
+      double ww = (double)r1.z, x = (double)r1.x, y = (double)r1.y;
+      w += ww; wx += ww * x; wy += ww * y;
+      s0 += ww * ((double)r0.x + x * x); s1 += ww * ((double)r0.y + y * x);
+      s2 += ww * ((double)r0.z + x * y); s3 += ww * ((double)r0.w + y * y);
+      r1.w = 0.0f;
+      rec[2 * i + 1] = r1;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    w += __shfl_xor_sync(FULL_MASK, w, off); wx += __shfl_xor_sync(FULL_MASK, wx, off); wy += __shfl_xor_sync(FULL_MASK, wy, off);
+    s0 += __shfl_xor_sync(FULL_MASK, s0, off); s1 += __shfl_xor_sync(FULL_MASK, s1, off);
+    s2 += __shfl_xor_sync(FULL_MASK, s2, off); s3 += __shfl_xor_sync(FULL_MASK, s3, off);
+  }
+  if (lane_id() == 0 && w != 0.0) {
+    atomicAdd(&acc->w, w); atomicAdd(&acc->wx, wx); atomicAdd(&acc->wy, wy);
+    atomicAdd(&acc->s0, s0); atomicAdd(&acc->s1, s1); atomicAdd(&acc->s2, s2); atomicAdd(&acc->s3, s3);
+  }
+}
+
+/* moment-matched merge (gm_reduce.cpp:104-130): mean = sum(w mu)/W, cov = sum w (P + (m-mu)(m-mu)^T)/W */
+__global__ void eap_finalize_kernel(EapAcc* acc, phdslam_gaussian2d_t* __restrict__ out, int cap, unsigned long long* key_out) {
+  if (threadIdx.x != 0) return;
+  *key_out = acc->key;
+  if (acc->key && acc->w != 0.0) {
+    double W = acc->w, mx = acc->wx / W, my = acc->wy / W;
+    phdslam_gaussian2d_t g;
+    g.weight = (float)W;
+    g.mean[0] = (float)mx; g.mean[1] = (float)my;
+    g.cov[0] = (float)(acc->s0 / W - mx * mx); g.cov[1] = (float)(acc->s1 / W - my * mx);
+    g.cov[2] = (float)(acc->s2 / W - mx * my); g.cov[3] = (float)(acc->s3 / W - my * my);
+    if (acc->n_out < cap) out[acc->n_out] = g;
+    acc->n_out++;
+  }
+  acc->key = 0;
+}
+
 /* blocked dense planes -> reference AoS order (tests / phdslam_update_terms export only) */
 __global__ void dense_export_kernel(const float* __restrict__ dense, const unsigned long long* __restrict__ toff,
                                     unsigned long long tbase, const int* __restrict__ n_in, int M, int p0, int np,

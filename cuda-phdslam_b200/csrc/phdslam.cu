@@ -976,7 +976,8 @@ extern "C" int phdslam_set_cardinalities(phdslam_t* h, const float* in) {
   return 0;
 }
 
-extern "C" int phdslam_map_estimate(phdslam_t* h, int which, phdslam_gaussian2d_t* out, int cap, int* n_out) {
+extern "C" int phdslam_map_estimate(phdslam_t* h, int which, phdslam_gaussian2d_t* out, int cap, int* n_out_p) {
+  int* n_out = n_out_p;
   CK(cudaSetDevice(h->device));
   if (which == 1) {
     phdslam_estimate_t e;
@@ -998,8 +999,67 @@ extern "C" int phdslam_map_estimate(phdslam_t* h, int which, phdslam_gaussian2d_
     }
     return 0;
   }
-  phdslam_set_error("EAP map estimate (map_estimate & 2) is not built yet");
-  return PHDSLAM_ERR_INVALID;
+  if (which != 2) return PHDSLAM_ERR_INVALID;
+  /* ---- EAP map: computeExpectedMap + reduceGaussianMixture (main.cpp:290-316, gm_reduce.cpp:57-134) ---- */
+  const int n = h->n_local;
+  ncclComm_t comm = (ncclComm_t)h->nccl_comm;
+  /* concat offsets = exclusive scan of the map sizes */
+  std::vector<int> cnt(n);
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(cnt.data(), h->count[h->cur], (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+  std::vector<unsigned long long> off(n + 1, 0);
+  for (int p = 0; p < n; ++p) off[p + 1] = off[p] + (unsigned long long)cnt[p];
+  const unsigned long long n_tot = off[n];
+  unsigned long long gbase = 0;
+  if (h->world > 1) {
+    if (!h->totals_dev) CK(cudaMalloc(&h->totals_dev, (size_t)h->world * sizeof(unsigned long long)));
+    unsigned long long* d_one = nullptr;
+    CK(cudaMalloc(&d_one, sizeof(unsigned long long)));
+    CK(cudaMemcpy(d_one, &n_tot, sizeof(n_tot), cudaMemcpyHostToDevice));
+    CKN(ncclAllGather(d_one, h->totals_dev, 1, ncclUint64, comm, h->stream));
+    std::vector<unsigned long long> all(h->world);
+    CK(cudaMemcpyAsync(all.data(), h->totals_dev, (size_t)h->world * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(d_one);
+    for (int r = 0; r < h->rank; ++r) gbase += all[r];
+  }
+  float4* rec = nullptr;
+  unsigned long long* d_off = nullptr;
+  EapAcc* acc = nullptr;
+  phdslam_gaussian2d_t* d_out = nullptr;
+  unsigned long long* key_host = nullptr;
+  CK(cudaMalloc(&rec, std::max<unsigned long long>(n_tot, 1) * 2 * sizeof(float4)));
+  CK(cudaMalloc(&d_off, (size_t)(n + 1) * sizeof(unsigned long long)));
+  CK(cudaMalloc(&acc, sizeof(EapAcc)));
+  CK(cudaMalloc(&d_out, (size_t)std::max(cap, 1) * sizeof(phdslam_gaussian2d_t)));
+  CK(cudaMallocHost(&key_host, sizeof(unsigned long long)));
+  CK(cudaMemcpyAsync(d_off, off.data(), (size_t)(n + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(acc, 0, sizeof(EapAcc), h->stream));
+  eap_concat_kernel<<<cdiv(n, 8), 256, 0, h->stream>>>(h->map[h->cur], h->count[h->cur], h->logw, d_off, n, h->Cmax, rec);
+  LAUNCH_CHECK(h);
+  const int blocks = (int)std::min<unsigned long long>(std::max<unsigned long long>((n_tot + 255) / 256, 1), 148 * 8);
+  int rc = 0;
+  for (long long round = 0;; ++round) {
+    eap_argmax_kernel<<<blocks, 256, 0, h->stream>>>(rec, n_tot, gbase, acc);
+    LAUNCH_CHECK(h);
+    if (h->world > 1) CKN(ncclAllReduce(&acc->key, &acc->key, 1, ncclUint64, ncclMax, comm, h->stream));
+    eap_seed_kernel<<<1, 32, 0, h->stream>>>(rec, n_tot, gbase, acc);
+    LAUNCH_CHECK(h);
+    if (h->world > 1) CKN(ncclAllReduce(acc->seed, acc->seed, 8, ncclFloat, ncclSum, comm, h->stream));
+    eap_cluster_kernel<<<blocks, 256, 0, h->stream>>>(rec, n_tot, gbase, h->cfg.min_separation, acc);
+    LAUNCH_CHECK(h);
+    if (h->world > 1) CKN(ncclAllReduce(&acc->w, &acc->w, 7, ncclDouble, ncclSum, comm, h->stream));
+    eap_finalize_kernel<<<1, 32, 0, h->stream>>>(acc, d_out, cap, key_host);
+    LAUNCH_CHECK(h);
+    CK(cudaStreamSynchronize(h->stream));
+    if (*key_host == 0) break;
+  }
+  int n_eap = 0;
+  CK(cudaMemcpy(&n_eap, &acc->n_out, sizeof(int), cudaMemcpyDeviceToHost));
+  *n_out_p = n_eap;
+  if (n_eap > 0) CK(cudaMemcpy(out, d_out, (size_t)std::min(n_eap, cap) * sizeof(phdslam_gaussian2d_t), cudaMemcpyDeviceToHost));
+  cudaFree(rec); cudaFree(d_off); cudaFree(acc); cudaFree(d_out); cudaFreeHost(key_host);
+  return rc;
 }
 
 /* ---- timings / snapshot ---- */

@@ -260,3 +260,55 @@ def test_properties_at_scale():
     assert (np.diff(anc) >= 0).all() and anc.min() >= 0 and anc.max() < Pn
     assert (g.map_sizes == sizes[anc]).all()
     np.testing.assert_allclose(g.log_weights, -np.log(Pn), rtol=1e-6)
+
+
+def test_map_estimates_map_and_eap():
+    """row 10: MAP map = map of the heaviest particle; EAP map = computeExpectedMap + reduceGaussianMixture
+    (main.cpp:290-316, gm_reduce.cpp:57-134) on the device: component count bit-exact, values within 1e-4"""
+    Pn, C, M = 24, 30, 12
+    cfg = S.scene_config(Pn, C, M, max_components=128, map_estimate=3)
+    sc = S.make_scene(Pn, C, M, seed=6, n_near=3, n_far=3)
+    g, o = pair(cfg, sc)
+    g.phdUpdateSynth(sc["Z"])
+    o.phdUpdateSynth(sc["Z"])
+    gm, om = g.map_estimate(1), o.map_estimate(1)
+    assert gm.tobytes() == om.tobytes() and len(gm) > 0
+    ge, oe = g.map_estimate(2, cap=8192), o.map_estimate(2)
+    assert len(ge) == len(oe) and len(ge) >= C          # bit-exact component count
+    close(ge["weight"], oe["weight"], "EAP weight", atol=1e-9)
+    close(ge["mean"], oe["mean"], "EAP mean", atol=1e-5)
+    close(ge["cov"], oe["cov"], "EAP cov", atol=2e-6)
+    # the expected map conserves the expected number of features
+    w = np.exp(o.log_weights.astype(np.float64))
+    sizes, maps = o.get_maps()
+    exp_n = float((np.repeat(w, sizes) * maps["weight"]).sum())
+    assert abs(ge["weight"].sum() - exp_n) < 1e-3 * exp_n
+
+
+def test_cli_logs_match_oracle(tmp_path):
+    """rows 13-14 + the process interface: `phdslam <cfg> synth` on the bundled Ackerman data writes
+    state_estimateNNNNN.log files (README 5-line layout) identical to the oracle's, text for text"""
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "cuda-phdslam_b200", "phdslam")
+    assert os.path.exists(exe), "CLI not built"
+    n_steps = 12
+    out = tmp_path / "run"
+    cmd = [exe, os.path.join(GOLDEN, "config_ackerman.cfg"), "synth", "--measurements",
+           os.path.join(DATA, "measurements_synth_ackerman.txt"), "--controls", os.path.join(DATA, "controls_synth.txt"),
+           "--out", str(out), "--steps", str(n_steps), "--set", "n_particles=64", "--set", "map_estimate=1", "--set", "seed=21",
+           "--quiet"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    cfg = P.load_config(os.path.join(GOLDEN, "config_ackerman.cfg"))
+    cfg.set(n_particles=64, map_estimate=1, seed="21")
+    Z = P.load_measurements(os.path.join(DATA, "measurements_synth_ackerman.txt"))
+    U = P.load_controls(os.path.join(DATA, "controls_synth.txt"))
+    o = O.Oracle(cfg)
+    for k in range(n_steps):
+        e, _ = o.step(k, U[k - 1] if k > 0 else np.float32([0, 0]), Z[k])
+        ref = tmp_path / ("ref%05d.log" % k)
+        P.write_log(str(ref), 0, e.pose, o.map_estimate(1), o.log_weights, o.poses, n_card=cfg.max_cardinality + 1)
+        got = open(out / ("state_estimate%05d.log" % k)).read()
+        assert got == open(ref).read(), "log of step %d differs" % k
+        assert len(got.split("\n")) == 6
