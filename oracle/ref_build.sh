@@ -1,0 +1,65 @@
+#!/bin/bash
+# oracle/ref_build.sh -- compile the REFERENCE's own kernels for the CPU (oracle/_ref/libphd_ref.so).
+#
+# TEST INFRASTRUCTURE.  Runs only where /root/reference exists (this container); the built .so travels to the
+# GPU box, /root/reference does not.  No reference source is copied into the repository: the recipe reads the
+# sources where they lie and writes only below oracle/_ref/ (git-ignored).
+#
+# Why not the reference's own build: HEAD does not compile (MotionModel undeclared, thrust headers,
+# cuPrintf needs sm_11 headers, `using namespace thrust` vs CCCL) and needs Boost/Eigen/matio/qmake, none of
+# which is installed.  What IS compilable is the arithmetic: the __global__ kernels and __device__ helpers of
+# the hot path are plain C++ once threadIdx/__syncthreads/__shared__ exist.  oracle/ref_shim/cuda_emul.h
+# provides those (one ucontext fiber per CUDA thread), and this script
+#   1. takes the hot-path functions out of src/phdfilter.cu and src/main.cpp BY LINE RANGE, verbatim, into
+#      oracle/_ref/gen/*.inc (each range is checked against the function name it must start with);
+#   2. makes a copy of src/device_math.cuh in which every step of the three warp-synchronous shared-memory
+#      reductions (sumByReduction / productByReduction / maxByReduction, :452-531) is followed by __syncwarp()
+#      -- the fix every post-Volta port of that code needs; on the hardware the reference was written for the
+#      warp ran in lock-step and the result is the same;
+#   3. compiles oracle/ref_harness.cpp (ours: marshalling + the host glue between kernels) with them.
+# -ffp-contract=off: the CPU build must not fuse a*b+c on its own; -fpermissive -w: 2012-era C++.
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+REF="${PHD_REFERENCE:-/root/reference}"
+OUT="$HERE/_ref"
+GEN="$OUT/gen"
+[ -d "$REF/src" ] || { echo "ref_build: $REF/src not found, nothing to do"; exit 0; }
+mkdir -p "$GEN"
+
+# extract FILE FIRST LAST NAME  -> appends lines FIRST..LAST of FILE; NAME must occur in the first 3 lines
+extract() {
+  local file="$1" first="$2" last="$3" name="$4"
+  sed -n "${first},$((first + 2))p" "$file" | grep -q "$name" || { echo "ref_build: $file:$first is not $name" >&2; exit 1; }
+  [ "$(sed -n "${last}p" "$file")" = "}" ] || { echo "ref_build: $file:$last does not close $name" >&2; exit 1; }
+  echo "/* ---- $(basename "$file"):$first-$last ($name) ---- */"
+  sed -n "${first},${last}p" "$file"
+}
+
+K="$REF/src/phdfilter.cu"
+{
+  extract "$K" 205 242 computeBirth
+  extract "$K" 785 825 phdPredictKernelAckerman
+  extract "$K" 827 859 phdPredictKernel
+  extract "$K" 1279 1358 computeInRangeKernel
+  extract "$K" 1824 1925 preUpdateSynthKernel
+  extract "$K" 2083 2321 phdUpdateKernel
+  extract "$K" 2707 2898 phdUpdateMergeKernel
+} > "$GEN/ref_kernels.inc"
+
+M="$REF/src/main.cpp"
+{
+  extract "$M" 290 316 computeExpectedMap
+  extract "$M" 318 388 recoverSlamState
+  extract "$M" 452 501 resampleParticles
+} > "$GEN/ref_host.inc"
+
+# device_math.cuh with __syncwarp() after every warp-synchronous reduction step
+sed -E 's/^( *sdata\[tid\] = [a-z_A-Z]+ = .*sdata\[tid ?\+ ?(32|16|8|4|2|1)\].*;)\s*$/\1 __syncwarp();/' \
+  "$REF/src/device_math.cuh" > "$GEN/device_math_syncwarp.cuh"
+n=$(grep -c "__syncwarp" "$GEN/device_math_syncwarp.cuh")
+[ "$n" -eq 18 ] || { echo "ref_build: expected 18 warp-synchronous steps in device_math.cuh, patched $n" >&2; exit 1; }
+
+g++ -O1 -std=c++14 -fPIC -shared -fpermissive -w -ffp-contract=off \
+  -I "$HERE/ref_shim" -I "$GEN" -I "$REF/src" -I "$HERE/../include" \
+  -o "$OUT/libphd_ref.so" "$HERE/ref_harness.cpp"
+echo "ref_build: built $OUT/libphd_ref.so from $REF"
