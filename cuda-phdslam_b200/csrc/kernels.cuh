@@ -828,8 +828,9 @@ __device__ __forceinline__ void warp_scan256(const unsigned* cnt, unsigned ex[8]
 
 /* One stable LSD radix pass (8-bit digit) over the index list `in` -> `out`, keyed by
  * key_of(idx) = bits of recs[2*idx+1].{w|z} (optionally transformed).  Warp-synchronous. */
-template <int MODE> /* 0: key = term index (record .w); 1: key = ~ordered(weight) (record .z) */
+template <int MODE> /* 0: key = term index (record .w); 1: key = ~ordered(weight) (record .z); 2: bitrev8(idx mod 256) */
 __device__ __forceinline__ unsigned radix_key(const float4* recs, unsigned idx) {
+  if (MODE == 2) return __brev(idx) >> 24;
   float4 r1 = recs[2 * idx + 1];
   if (MODE == 0) return __float_as_uint(r1.w);
   return ~float_to_ordered_uint(r1.z);
@@ -959,9 +960,13 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
 
   int nout = 0;
   if (n > 0) {
-    /* ---- B. rank by (weight desc, index asc): stable LSD radix on ~ordered(weight) ---- */
-    for (int i = lane; i < n; i += 32) s_order[i] = (unsigned short)i;
+    /* ---- B. rank by (weight desc, reference tie rule): stable LSD radix.  Equal weights are ordered as the
+     * reference's 256-slot arg-max tree orders them: by (bitrev8(i mod 256), i div 256) (oracle merge_tie_key).
+     * With n <= 256 the first pass alone realises that order; otherwise i div 256 is already ascending within
+     * each residue because the pass is stable over the identity order. ---- */
+    for (int i = lane; i < n; i += 32) s_items[i] = (unsigned short)i;
     __syncwarp();
+    radix_pass<2>(cand, s_items, s_order, n, s_cnt, 0, lane);
     radix_pass<1>(cand, s_order, s_items, n, s_cnt, 0, lane);
     radix_pass<1>(cand, s_items, s_order, n, s_cnt, 8, lane);
     radix_pass<1>(cand, s_order, s_items, n, s_cnt, 16, lane);

@@ -428,8 +428,9 @@ extern "C" float oracle_mahalanobis(const G2* a, const G2* b) { return mahal(*a,
 extern "C" float oracle_hellinger(const G2* a, const G2* b) { return hellinger(*a, *b); }
 
 /* phdUpdateMergeKernel (src/phdfilter.cu:2707-2898): greedy Gaussian-mixture reduction.
- * Canonical choices where the reference is order-dependent: arg-max ties -> lowest index;
- * cluster sums accumulate sequentially in ascending index order.
+ * Arg-max ties are broken exactly as the reference's reduction tree breaks them (merge_tie_key).
+ * Canonical choice where the reference's rounding is shape-dependent: cluster sums accumulate sequentially in
+ * ascending index order (the reference: 256 strided partials + shared-memory tree).
  * Canonical gate (Mahalanobis metric only): candidate b can join the cluster of seed a only if
  *     |mu_a - mu_b|^2 <= (0.625 * minSeparation) * (lam_a + lam_b),
  * lam = largest eigenvalue of the component's covariance.  For positive semi-definite covariances
@@ -445,6 +446,17 @@ static float merge_lambda_max(const G2& g) {
   return 0.5f * (t + sqrtf(disc));
 }
 
+/* Arg-max tie rule of the reference's reduction (:2751-2787), which is deterministic: thread `tid` scans the
+ * candidates tid, tid+256, ... and keeps the first maximum (strict <); the 256-slot tree then prefers the
+ * lower slot at every level s = 128, 64, ..., 1, i.e. slots are compared by their bit-reversed number.
+ * Among equal weights the winner is therefore the candidate with the smallest (bitrev8(i mod 256), i div 256).
+ * (Exact ties are common: every clutter-born component has the weight w_b/(kappa + w_b).) */
+static inline unsigned merge_tie_key(int i) {
+  unsigned t = (unsigned)i & 255u, r = 0;
+  for (int b = 0; b < 8; ++b) r |= ((t >> b) & 1u) << (7 - b);
+  return (r << 24) | ((unsigned)i >> 8);
+}
+
 static void merge_mixture(const phdslam_config_t& c, const std::vector<G2>& cand, std::vector<G2>& out) {
   const int n = (int)cand.size();
   const bool gated = (c.distance_metric == 0);
@@ -455,8 +467,12 @@ static void merge_mixture(const phdslam_config_t& c, const std::vector<G2>& cand
   std::vector<int> members;
   while (true) {
     int best = -1;
-    for (int i = 0; i < n; ++i)
-      if (!merged[i] && (best < 0 || cand[best].weight < cand[i].weight)) best = i;   /* :2751-2787 */
+    for (int i = 0; i < n; ++i) {                                                     /* :2751-2787 */
+      if (merged[i]) continue;
+      if (best < 0 || cand[best].weight < cand[i].weight ||
+          (cand[best].weight == cand[i].weight && merge_tie_key(i) < merge_tie_key(best)))
+        best = i;
+    }
     if (best < 0) break;
     const G2& mx = cand[best];
     members.clear();

@@ -9,11 +9,15 @@
  *
  * PARITY PIN: the reference ships no tests, golden vectors or fixtures
  *  and its named CPU path (src/scphd_cpu.cpp) is an empty stub.
- * The pin is therefore (a) oracle/_ref: the reference's own CUDA kernels
- * compiled unmodified for the CPU through a SIMT shim (oracle/ref_build.sh,
- * built only where /root/reference exists) and compared with this oracle in
- * tests/test_oracle_vs_ref.py, with the outputs committed under tests/golden/;
- * (b) closed-form known-answer tests (tests/test_oracle_kat.py).
+ * The pin is therefore (a) oracle/_ref: the reference's own CUDA kernels and
+ * host functions of this path, cut verbatim out of /root/reference/src by
+ * oracle/ref_build.sh and run on the CPU through a CUDA execution-model emulator
+ * (oracle/ref_shim/cuda_emul.h; two documented barrier insertions, see the
+ * recipe), compared with this oracle in tests/test_ref_pin.py, with the outputs
+ * committed as tests/golden/ref_golden.npz (generator:
+ * tests/golden/make_ref_golden.py); (b) closed-form known-answer tests
+ * (tests/test_oracle_kat.py).  CPHD is dead code in the reference
+ * and has no runnable counterpart: that row is pinned by (b) only.
  *
  * Arithmetic: fp32 in the reference's operation order, with the transcendental
  * functions of include/phd_detmath.h so that results are bit-reproducible on the

@@ -1,0 +1,192 @@
+"""ctypes loader for oracle/_ref/libphd_ref.so -- the REFERENCE's own kernels compiled for the CPU.
+
+TEST INFRASTRUCTURE ONLY (see oracle/ref_build.sh, oracle/ref_harness.cpp).  The library exists only where
+oracle/ref_build.sh has run (a container that has /root/reference); `available()` says whether it does.
+Used by tests/test_ref_pin.py and tests/golden/make_ref_golden.py.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .oracle import GAUSSIAN_DTYPE, POSE_DTYPE
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libphd_ref.so")
+_lib = None
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+def load():
+    global _lib
+    if _lib is None:
+        lib = C.CDLL(LIB_PATH)
+        for n in ("ref_wrap_angle", "ref_safe_log"):
+            getattr(lib, n).restype = C.c_float
+            getattr(lib, n).argtypes = [C.c_float]
+        for n in ("ref_mahalanobis", "ref_hellinger"):
+            getattr(lib, n).restype = C.c_float
+            getattr(lib, n).argtypes = [C.c_void_p, C.c_void_p]
+        lib.ref_log_sum_exp.restype = C.c_float
+        lib.ref_log_sum_exp.argtypes = [C.c_void_p, C.c_int]
+        lib.ref_sum_by_reduction.restype = C.c_float
+        lib.ref_sum_by_reduction.argtypes = [C.c_void_p]
+        lib.ref_set_config.argtypes = [C.c_void_p]
+        lib.ref_predict.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.ref_in_range.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.ref_birth_device.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_void_p]
+        lib.ref_update_terms.restype = C.c_size_t
+        lib.ref_update_terms.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]
+        lib.ref_merge.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        lib.ref_update.restype = C.c_size_t
+        lib.ref_update.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_size_t]
+        lib.ref_resample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.ref_recover.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        lib.ref_neff.restype = C.c_float
+        lib.ref_neff.argtypes = [C.c_void_p, C.c_int]
+        _lib = lib
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def set_config(cfg):
+    load().ref_set_config(C.byref(cfg))
+
+
+def wrap_angle(x):
+    lib = load()
+    return np.array([lib.ref_wrap_angle(float(v)) for v in _f32(x)], dtype=np.float32)
+
+
+def safe_log(x):
+    lib = load()
+    return np.array([lib.ref_safe_log(float(v)) for v in _f32(x)], dtype=np.float32)
+
+
+def mahalanobis(a, b):
+    a, b = np.ascontiguousarray(a, GAUSSIAN_DTYPE), np.ascontiguousarray(b, GAUSSIAN_DTYPE)
+    return load().ref_mahalanobis(a.ctypes.data, b.ctypes.data)
+
+
+def hellinger(a, b):
+    a, b = np.ascontiguousarray(a, GAUSSIAN_DTYPE), np.ascontiguousarray(b, GAUSSIAN_DTYPE)
+    return load().ref_hellinger(a.ctypes.data, b.ctypes.data)
+
+
+def log_sum_exp(w):
+    w = _f32(w)
+    return load().ref_log_sum_exp(w.ctypes.data, len(w))
+
+
+def sum_by_reduction(v):
+    x = np.zeros(256, dtype=np.float32)
+    x[:len(v)] = v
+    return load().ref_sum_by_reduction(x.ctypes.data)
+
+
+def predict(poses, control, noise):
+    """control = (v_encoder, alpha); noise [n][2] {n_alpha, n_encoder} (Ackerman) or [n][3] {ax, ay, atheta} (CV)"""
+    p = np.ascontiguousarray(poses, POSE_DTYPE)
+    out = np.zeros_like(p)
+    c, nz = _f32(control), _f32(noise)
+    load().ref_predict(p.ctypes.data, len(p), c.ctypes.data, nz.ctypes.data, out.ctypes.data)
+    return out
+
+
+def in_range(maps, sizes, poses):
+    maps = np.ascontiguousarray(maps, GAUSSIAN_DTYPE)
+    sizes = np.ascontiguousarray(sizes, np.int32)
+    p = np.ascontiguousarray(poses, POSE_DTYPE)
+    cls = np.zeros(max(len(maps), 1), dtype=np.int8)
+    n_in = np.zeros(len(p), np.int32)
+    n_near = np.zeros(len(p), np.int32)
+    load().ref_in_range(maps.ctypes.data, sizes.ctypes.data, len(p), p.ctypes.data, cls.ctypes.data, n_in.ctypes.data,
+                        n_near.ctypes.data)
+    return cls[:len(maps)], n_in, n_near
+
+
+def birth_device(pose, r, b, label=0):
+    p = np.ascontiguousarray(pose, POSE_DTYPE)
+    out = np.zeros(1, GAUSSIAN_DTYPE)
+    load().ref_birth_device(p.ctypes.data, float(r), float(b), int(label), out.ctypes.data)
+    return out[0]
+
+
+def update_terms(poses, features, n_in, Z):
+    """features: concatenated in-range components.  Returns (terms, prune_flags, particle_log_weight_increments)."""
+    p = np.ascontiguousarray(poses, POSE_DTYPE)
+    f = np.ascontiguousarray(features, GAUSSIAN_DTYPE)
+    f = np.concatenate([f, np.zeros(1, GAUSSIAN_DTYPE)])
+    n_in = np.ascontiguousarray(n_in, np.int32)
+    z = _f32(Z).reshape(len(Z), -1)
+    M = z.shape[0]
+    n_upd = int(n_in.sum()) * (M + 1) + len(p) * M
+    terms = np.zeros(n_upd, GAUSSIAN_DTYPE)
+    flags = np.zeros(n_upd, np.int8)
+    pw = np.zeros(len(p), np.float32)
+    n = load().ref_update_terms(p.ctypes.data, len(p), f.ctypes.data, n_in.ctypes.data, z.ctypes.data, M, z.shape[1],
+                                terms.ctypes.data, flags.ctypes.data, pw.ctypes.data)
+    assert n == n_upd
+    return terms, flags, pw
+
+
+def merge(cands):
+    """cands: list of candidate arrays (one per particle).  Returns list of merged arrays."""
+    offs = np.zeros(len(cands) + 1, np.int32)
+    offs[1:] = np.cumsum([len(c) for c in cands])
+    cat = np.concatenate([np.ascontiguousarray(c, GAUSSIAN_DTYPE) for c in cands] + [np.zeros(1, GAUSSIAN_DTYPE)])
+    out = np.zeros(len(cat), GAUSSIAN_DTYPE)
+    sizes = np.zeros(len(cands), np.int32)
+    load().ref_merge(cat.ctypes.data, offs.ctypes.data, len(cands), out.ctypes.data, sizes.ctypes.data)
+    return [out[offs[i]:offs[i] + sizes[i]].copy() for i in range(len(cands))]
+
+
+def update(poses, sizes, maps, log_weights, Z):
+    """whole static-map phdUpdateSynth.  Returns (sizes, maps, log_weights)."""
+    p = np.ascontiguousarray(poses, POSE_DTYPE)
+    sizes = np.ascontiguousarray(sizes, np.int32)
+    maps = np.ascontiguousarray(maps, GAUSSIAN_DTYPE)
+    maps = np.concatenate([maps, np.zeros(1, GAUSSIAN_DTYPE)])
+    lw = _f32(log_weights).copy()
+    z = _f32(Z).reshape(len(Z), -1)
+    M = z.shape[0]
+    cap = int(sizes.sum()) * (M + 1) + len(p) * M + 1
+    out = np.zeros(cap, GAUSSIAN_DTYPE)
+    out_sizes = np.zeros(len(p), np.int32)
+    n = load().ref_update(p.ctypes.data, len(p), sizes.ctypes.data, maps.ctypes.data, lw.ctypes.data, z.ctypes.data, M,
+                          z.shape[1], out_sizes.ctypes.data, out.ctypes.data, cap)
+    return out_sizes, out[:n].copy(), lw
+
+
+def resample(log_weights, uniforms, n_new=-1):
+    """uniforms: every randu01() the reference consumes, in order (n_new + 1 values)."""
+    lw = _f32(log_weights)
+    u = np.ascontiguousarray(uniforms, np.float64)
+    nn = len(lw) if n_new < 0 else n_new
+    assert len(u) >= nn + 1
+    idx = np.zeros(nn, np.int32)
+    nlw = np.zeros(nn, np.float32)
+    load().ref_resample(lw.ctypes.data, len(lw), n_new, u.ctypes.data, idx.ctypes.data, nlw.ctypes.data)
+    return idx, nlw
+
+
+def recover(log_weights, poses):
+    lw = _f32(log_weights)
+    p = np.ascontiguousarray(poses, POSE_DTYPE)
+    e = np.zeros(1, POSE_DTYPE)
+    k = C.c_int()
+    load().ref_recover(lw.ctypes.data, p.ctypes.data, len(lw), e.ctypes.data, C.byref(k))
+    return e[0], k.value
+
+
+def neff(log_weights):
+    lw = _f32(log_weights)
+    return load().ref_neff(lw.ctypes.data, len(lw))

@@ -42,9 +42,19 @@ K="$REF/src/phdfilter.cu"
   extract "$K" 827 859 phdPredictKernel
   extract "$K" 1279 1358 computeInRangeKernel
   extract "$K" 1824 1925 preUpdateSynthKernel
-  extract "$K" 2083 2321 phdUpdateKernel
+  # phdUpdateKernel reads sdata[0] after each per-measurement reduction (`sum += sdata[0]`, :2210) with no
+  # barrier before thread 0 overwrites sdata[0] in the next reduction.  On hardware the other warps read it
+  # immediately and the race is benign; the emulator runs thread 0 far ahead, so the barrier the kernel's own
+  # first loop has (:2184-2185) is added there too.
+  extract "$K" 2083 2321 phdUpdateKernel | sed -E 's/^( *sum \+= sdata\[0\] ;)\s*$/\1 __syncthreads() ;/'
   extract "$K" 2707 2898 phdUpdateMergeKernel
 } > "$GEN/ref_kernels.inc"
+[ "$(grep -c 'sum += sdata\[0\] ; __syncthreads() ;' "$GEN/ref_kernels.inc")" -eq 1 ] || { echo "ref_build: barrier patch failed" >&2; exit 1; }
+
+# the birth-term host loop is inline in phdUpdateSynth (:3468-3510): taken as a block, wrapped by the harness
+sed -n "3468p" "$K" | grep -q "for ( int i = 0 ; i < n_particles ; i++){" || { echo "ref_build: births loop moved" >&2; exit 1; }
+sed -n "3470,3475p" "$K" | grep -q "invert measurement" || { echo "ref_build: births loop moved" >&2; exit 1; }
+sed -n "3468,3510p" "$K" > "$GEN/ref_births.inc"
 
 M="$REF/src/main.cpp"
 {
@@ -54,7 +64,7 @@ M="$REF/src/main.cpp"
 } > "$GEN/ref_host.inc"
 
 # device_math.cuh with __syncwarp() after every warp-synchronous reduction step
-sed -E 's/^( *sdata\[tid\] = [a-z_A-Z]+ = .*sdata\[tid ?\+ ?(32|16|8|4|2|1)\].*;)\s*$/\1 __syncwarp();/' \
+sed -E 's/^( *sdata\[tid\] = [a-z_A-Z]+ = .*sdata\[tid *\+ *(32|16|8|4|2|1)\].*;)\s*$/\1 __syncwarp();/' \
   "$REF/src/device_math.cuh" > "$GEN/device_math_syncwarp.cuh"
 n=$(grep -c "__syncwarp" "$GEN/device_math_syncwarp.cuh")
 [ "$n" -eq 18 ] || { echo "ref_build: expected 18 warp-synchronous steps in device_math.cuh, patched $n" >&2; exit 1; }

@@ -1,0 +1,296 @@
+/*
+ * ref_harness.cpp -- C entry points around the REFERENCE's own kernels, compiled for the CPU.
+ *
+ * TEST INFRASTRUCTURE (part of the oracle; see oracle/ref_build.sh for how and why it is built).  The kernels
+ * and helpers themselves are #included from oracle/_ref/gen/*.inc, which ref_build.sh cuts verbatim out of
+ * /root/reference/src/{phdfilter.cu,main.cpp,device_math.cuh}; this file only
+ *   - supplies the globals those kernels expect (`dev_config`, `config`, constant `Z[256]`, randu01()),
+ *   - marshals flat C arrays into the kernels' argument lists, using the same buffer layouts the reference's
+ *     host wrapper builds (each site cites the wrapper lines it mirrors), and launches them through the
+ *     fiber emulator with the reference's launch shape (256 threads per block),
+ *   - restates the thin host glue BETWEEN kernels of phdUpdateSynth (stable prune, recombination order,
+ *     particle-weight normalisation) so a whole update can be compared.
+ * It is used by tests/test_ref_pin.py to pin oracle/phd_oracle.cpp, and to generate tests/golden/ref_*.npz.
+ */
+#define PHD_CUDA_EMUL_IMPL
+#include "cuda_emul.h"
+
+class MotionModel; /* src/slamtypes.h:335 names it without declaring it */
+
+#include "device_math_syncwarp.cuh" /* = src/device_math.cuh (+ __syncwarp), pulls in src/slamtypes.h */
+
+#include "phdslam.h"
+
+/* globals of src/phdfilter.cu:118-119 and src/main.cpp */
+RangeBearingMeasurement Z[256];
+SlamConfig dev_config;
+SlamConfig config;
+
+#define DEBUG_MSG(x)
+#define DEBUG_VAL(x)
+#define checkCudaErrors(x) (x)
+
+/* src/rng.h:13-25: extern "C" double randu01() -- here: injected draws */
+static const double* g_uniforms = nullptr;
+static size_t g_uniform_pos = 0;
+extern "C" double randu01() { return g_uniforms[g_uniform_pos++]; }
+
+/* src/gm_reduce.h: needs Eigen (absent); only reached when config.mapEstimate & 2 */
+template <class GaussianType>
+vector<GaussianType> reduceGaussianMixture(vector<GaussianType>, REAL) { abort(); }
+
+#include "ref_kernels.inc"
+#include "ref_host.inc"
+
+typedef phdslam_gaussian2d_t G2;
+typedef phdslam_pose_t Pose;
+static_assert(sizeof(G2) == sizeof(Gaussian2D), "layout");
+static_assert(sizeof(Pose) == sizeof(ConstantVelocityState), "layout");
+
+static const int kThreads = 256;
+
+extern "C" void ref_set_config(const phdslam_config_t* c) {
+  SlamConfig s;
+  memset(&s, 0, sizeof(s));
+  s.x0 = c->x0; s.y0 = c->y0; s.yaw0 = c->yaw0; s.vx0 = c->vx0; s.vy0 = c->vy0; s.vyaw0 = c->vyaw0;
+  s.ax = c->ax; s.ay = c->ay; s.ayaw = c->ayaw; s.dt = c->dt;
+  s.minRange = c->min_range; s.maxRange = c->max_range; s.maxBearing = c->max_bearing;
+  s.stdRange = c->std_range; s.stdBearing = c->std_bearing;
+  s.clutterRate = c->clutter_rate; s.clutterDensity = c->clutter_density; s.pd = c->pd;
+  s.n_particles = c->n_particles; s.nPredictParticles = c->n_predict_particles; s.subdividePredict = c->subdivide_predict;
+  s.resampleThresh = c->resample_threshold; s.birthWeight = c->birth_weight; s.birthNoiseFactor = c->birth_noise_factor;
+  s.minSeparation = c->min_separation; s.minFeatureWeight = c->min_feature_weight;
+  s.particleWeighting = c->particle_weighting; s.distanceMetric = c->distance_metric;
+  s.maxCardinality = c->max_cardinality; s.filterType = c->filter_type; s.mapEstimate = c->map_estimate;
+  s.featureModel = c->feature_model; s.motionType = c->motion_type; s.labeledMeasurements = c->labeled_measurements != 0;
+  s.l = c->l; s.h = c->h; s.a = c->a; s.b = c->b; s.stdAlpha = c->std_alpha; s.stdEncoder = c->std_encoder;
+  s.nSamples = 256;
+  dev_config = s;   /* setDeviceConfig, src/phdfilter.cu:3885-3890 */
+  config = s;
+}
+
+static void set_measurements(const float* z, int M, int fields) {
+  for (int m = 0; m < M; ++m) {
+    Z[m].range = z[m * fields];
+    Z[m].bearing = z[m * fields + 1];
+    Z[m].label = fields > 2 ? (int)z[m * fields + 2] : 0;
+  }
+}
+
+/* ---- device_math.cuh helpers ---- */
+extern "C" float ref_wrap_angle(float a) { return wrapAngle(a); }
+extern "C" float ref_safe_log(float x) { return safeLog(x); }
+extern "C" float ref_mahalanobis(const G2* a, const G2* b) {
+  Gaussian2D x, y;
+  memcpy(&x, a, sizeof(x)); memcpy(&y, b, sizeof(y));
+  return computeMahalDist(x, y);
+}
+extern "C" float ref_hellinger(const G2* a, const G2* b) {
+  Gaussian2D x, y;
+  memcpy(&x, a, sizeof(x)); memcpy(&y, b, sizeof(y));
+  return computeHellingerDist(x, y);
+}
+extern "C" float ref_log_sum_exp(const float* w, int n) { return logSumExp(std::vector<float>(w, w + n)); }
+/* sumByReduction through the emulator: the 256-wide shared-memory tree itself */
+extern "C" float ref_sum_by_reduction(const float* v256) {
+  static float sdata[256];
+  emul_launch(1, kThreads, [&] { sumByReduction(sdata, v256[threadIdx.x], threadIdx.x); });
+  return sdata[0];
+}
+
+/* ---- predict: phdPredictKernelAckerman / phdPredictKernel, launched as src/phdfilter.cu:1119-1170 does.
+ * noise = what the host wrapper stores in noiseVector (float), [n][2] {n_alpha, n_encoder} or [n][3]. */
+extern "C" void ref_predict(const Pose* in, int n, const float* control_venc_alpha, const float* noise, Pose* out) {
+  int nb = (n + kThreads - 1) / kThreads;
+  ConstantVelocityState* pin = (ConstantVelocityState*)in;
+  ConstantVelocityState* pout = (ConstantVelocityState*)out;
+  if (config.motionType == ACKERMAN_MOTION) {
+    AckermanControl u;
+    u.v_encoder = control_venc_alpha[0];
+    u.alpha = control_venc_alpha[1];
+    emul_launch(nb, kThreads, [&] { phdPredictKernelAckerman(pin, u, (AckermanNoise*)noise, pout, n); });
+  } else {
+    emul_launch(nb, kThreads, [&] { phdPredictKernel(pin, (ConstantVelocityNoise*)noise, pout, n); });
+  }
+}
+
+/* ---- in-range classification: computeInRangeKernel launched as prepareUpdateInputs does (:2950-2990) ---- */
+extern "C" void ref_in_range(const G2* features, const int* map_sizes, int n_particles, const Pose* poses, char* in_range,
+                             int* n_in, int* n_nearly) {
+  emul_launch(std::min(n_particles, 65535), kThreads, [&] {
+    computeInRangeKernel((Gaussian2D*)features, (int*)map_sizes, n_particles, (ConstantVelocityState*)poses, in_range, n_in,
+                         n_nearly);
+  });
+}
+
+/* births: the host loop of phdUpdateSynth, src/phdfilter.cu:3468-3510, verbatim */
+static void births_host(SynthSLAM& particles, measurementSet& measurements, int n_particles, int n_measure,
+                        vector<Gaussian2D>& births) {
+#include "ref_births.inc"
+}
+/* and its __device__ twin computeBirth (:205-242) */
+extern "C" void ref_birth_device(const Pose* pose, float r, float b, int label, G2* out) {
+  RangeBearingMeasurement z;
+  z.range = r; z.bearing = b; z.label = label;
+  Gaussian2D g;
+  computeBirth(*(const ConstantVelocityState*)pose, z, g);
+  memcpy(out, &g, sizeof(g));
+}
+
+/* ---- preUpdateSynthKernel + phdUpdateKernel on already-split in-range maps (src/phdfilter.cu:3463-3585).
+ * features: concatenated in-range components, n_in[p] per particle.  Outputs use the reference layout
+ * [nondetect C | detect m-major M*C | birth M] per particle at update_offset = off_p*(M+1) + p*M. */
+extern "C" size_t ref_update_terms(const Pose* poses, int n_particles, const G2* features, const int* n_in, const float* z,
+                                   int M, int fields, G2* terms_out, char* prune_flags_out, float* particle_weights_out) {
+  set_measurements(z, M, fields);
+  vector<int> offsets(n_particles + 1, 0), pose_idx;
+  for (int p = 0; p < n_particles; ++p) {
+    offsets[p + 1] = offsets[p] + n_in[p];
+    pose_idx.insert(pose_idx.end(), n_in[p], p);                       /* :3532-3534 */
+  }
+  int n_total = offsets[n_particles];
+  size_t n_update = (size_t)n_total * (M + 1) + (size_t)n_particles * M;
+  SynthSLAM particles(n_particles);
+  for (int p = 0; p < n_particles; ++p) memcpy(&particles.states[p], &poses[p], sizeof(Pose));
+  measurementSet meas(Z, Z + M);
+  vector<Gaussian2D> births((size_t)n_particles * M);
+  births_host(particles, meas, n_particles, M, births);
+  vector<Gaussian2D> preupdate((size_t)std::max(n_total, 1) * M), update(n_update);
+  vector<float> pd(std::max(n_total, 1)), likelihoods((size_t)std::max(n_total, 1) * M), pw(n_particles, 0.0f);
+  vector<char> flags(n_update, 0);
+  pose_idx.push_back(0);
+  if (n_total > 0) {
+    int nb = std::min((int)ceil(n_total / 256.0), 65535);              /* :3555 */
+    emul_launch(nb, kThreads, [&] {
+      preUpdateSynthKernel((ConstantVelocityState*)poses, pose_idx.data(), (Gaussian2D*)features, pd.data(), n_total, M,
+                           likelihoods.data(), preupdate.data());
+    });
+  }
+  emul_launch(std::min(n_particles, 65535), kThreads, [&] {            /* :3573-3578 */
+    phdUpdateKernel<Gaussian2D>((Gaussian2D*)features, pd.data(), preupdate.data(), births.data(), offsets.data(), n_particles,
+                                M, update.data(), (bool*)flags.data(), pw.data());
+  });
+  if (terms_out) memcpy(terms_out, update.data(), n_update * sizeof(G2));
+  if (prune_flags_out) memcpy(prune_flags_out, flags.data(), n_update);
+  if (particle_weights_out) memcpy(particle_weights_out, pw.data(), n_particles * sizeof(float));
+  return n_update;
+}
+
+/* ---- phdUpdateMergeKernel on one or more candidate lists (mergeAndCopyMaps, src/phdfilter.cu:3269-3276) ---- */
+extern "C" void ref_merge(const G2* cand, const int* offsets /* n_particles+1 */, int n_particles, G2* merged_out,
+                          int* merged_sizes) {
+  int n = offsets[n_particles];
+  vector<Gaussian2D> in(std::max(n, 1)), out(std::max(n, 1));
+  memcpy(in.data(), cand, (size_t)n * sizeof(G2));
+  vector<char> flags(std::max(n, 1), 0);
+  emul_launch(n_particles, kThreads, [&] {
+    phdUpdateMergeKernel<Gaussian2D>(in.data(), out.data(), merged_sizes, (bool*)flags.data(), (int*)offsets, n_particles);
+  });
+  memcpy(merged_out, out.data(), (size_t)n * sizeof(G2));   /* particle p's merged map starts at offsets[p] */
+}
+
+/* ---- a whole static-map phdUpdateSynth (src/phdfilter.cu:3336-3761): reference kernels + restated glue ---- */
+extern "C" size_t ref_update(const Pose* poses, int n_particles, const int* map_sizes, const G2* maps, float* log_weights,
+                             const float* z, int M, int fields, int* out_sizes, G2* out_maps, size_t out_cap) {
+  if (M > 256) M = 256;                                                /* :3390-3394 */
+  int n_total = 0;
+  for (int p = 0; p < n_particles; ++p) n_total += map_sizes[p];
+  vector<char> cls(std::max(n_total, 1), 0);
+  vector<int> n_in(n_particles), n_near(n_particles);
+  ref_in_range(maps, map_sizes, n_particles, poses, cls.data(), n_in.data(), n_near.data());
+  /* host 3-way split, order preserved within each class (prepareUpdateInputs :3030-3070) */
+  vector<G2> f_in, f_out1, f_out2;
+  vector<int> n_out1(n_particles, 0), n_out2(n_particles, 0);
+  {
+    size_t k = 0;
+    for (int p = 0; p < n_particles; ++p)
+      for (int i = 0; i < map_sizes[p]; ++i, ++k) {
+        if (cls[k] == 1) f_in.push_back(maps[k]);
+        else if (cls[k] == 2) { f_out2.push_back(maps[k]); n_out2[p]++; }
+        else { f_out1.push_back(maps[k]); n_out1[p]++; }
+      }
+  }
+  size_t n_update = (size_t)f_in.size() * (M + 1) + (size_t)n_particles * M;
+  vector<G2> terms(n_update);
+  vector<char> flags(n_update);
+  vector<float> pw(n_particles);
+  f_in.push_back(G2());
+  ref_update_terms(poses, n_particles, f_in.data(), n_in.data(), z, M, fields, terms.data(), flags.data(), pw.data());
+  /* pruneMap (:3120-3174): stable remove_copy_if + per-particle recount; recombination with the nearly-in-range
+   * features per particle (:3227-3257) */
+  vector<G2> combined;
+  vector<int> offsets(n_particles + 1, 0);
+  {
+    size_t k = 0, k2 = 0;
+    for (int p = 0; p < n_particles; ++p) {
+      size_t np = (size_t)n_in[p] * (M + 1) + M;
+      for (size_t i = 0; i < np; ++i, ++k)
+        if (!flags[k]) combined.push_back(terms[k]);
+      for (int i = 0; i < n_out2[p]; ++i) combined.push_back(f_out2[k2++]);
+      offsets[p + 1] = (int)combined.size();
+    }
+  }
+  vector<G2> merged(std::max<size_t>(combined.size(), 1));
+  vector<int> msizes(n_particles, 0);
+  combined.push_back(G2());
+  ref_merge(combined.data(), offsets.data(), n_particles, merged.data(), msizes.data());
+  /* copy out + re-append the far features (:3296-3318) */
+  size_t w = 0, k1 = 0;
+  for (int p = 0; p < n_particles; ++p) {
+    out_sizes[p] = msizes[p] + n_out1[p];
+    for (int i = 0; i < msizes[p]; ++i, ++w)
+      if (w < out_cap) out_maps[w] = merged[offsets[p] + i];
+    for (int i = 0; i < n_out1[p]; ++i, ++w, ++k1)
+      if (w < out_cap) out_maps[w] = f_out1[k1];
+  }
+  /* particle weights (:3735-3755) */
+  vector<float> lw(log_weights, log_weights + n_particles);
+  if (config.particleWeighting != 2)
+    for (int p = 0; p < n_particles; ++p) lw[p] += pw[p];
+  float s = logSumExp(lw);
+  for (int p = 0; p < n_particles; ++p) log_weights[p] = lw[p] - s;
+  return w;
+}
+
+/* ---- resampleParticles<SynthSLAM> (src/main.cpp:452-501); uniforms = every randu01() it consumes, in order ---- */
+extern "C" void ref_resample(const float* log_weights, int n, int n_new, const double* uniforms, int* idx_out,
+                             float* new_log_weights_out) {
+  SynthSLAM p(n);
+  p.weights.assign(log_weights, log_weights + n);
+  g_uniforms = uniforms;
+  g_uniform_pos = 0;
+  SynthSLAM q = resampleParticles(p, n_new);
+  for (int j = 0; j < q.n_particles; ++j) idx_out[j] = q.resample_idx[j];
+  if (new_log_weights_out)
+    for (int j = 0; j < q.n_particles; ++j) new_log_weights_out[j] = q.weights[j];
+}
+
+/* ---- recoverSlamState (src/main.cpp:318-388) with mapEstimate = 1; the MAP particle is identified by giving
+ * particle i a one-component map whose weight is i ---- */
+extern "C" void ref_recover(const float* log_weights, const Pose* poses, int n, Pose* expected, int* map_particle) {
+  SynthSLAM p(n);
+  p.weights.assign(log_weights, log_weights + n);
+  for (int i = 0; i < n; ++i) {
+    memcpy(&p.states[i], &poses[i], sizeof(Pose));
+    Gaussian2D g;
+    memset(&g, 0, sizeof(g));
+    g.weight = (float)i;
+    p.maps_static[i].assign(1, g);
+  }
+  int saved = config.mapEstimate;
+  config.mapEstimate = 1;
+  ConstantVelocityState e;
+  vector<REAL> cn;
+  recoverSlamState(p, e, cn);
+  config.mapEstimate = saved;
+  memcpy(expected, &e, sizeof(e));
+  *map_particle = (int)p.max_map_static[0].weight;
+}
+
+/* nEff exactly as run_synth spells it (src/main.cpp:1281-1284) -- three lines, restated */
+extern "C" float ref_neff(const float* log_weights, int n) {
+  REAL nEff = 0;
+  for (int i = 0; i < n; i++) nEff += exp(2 * log_weights[i]);
+  nEff = 1.0 / nEff / n;
+  return nEff;
+}

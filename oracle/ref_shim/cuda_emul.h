@@ -57,6 +57,7 @@ struct curandStateMRG32k3a { int unused; };
 typedef curandStateMRG32k3a curandStateMRG32k3a_t;
 static inline float curand_normal(curandStateMRG32k3a*) { abort(); }
 static inline float curand_uniform(curandStateMRG32k3a*) { abort(); }
+static inline float2 curand_normal2(curandStateMRG32k3a*) { abort(); }
 
 /* run body() once per CUDA thread of a grid x block launch (1-D), with the barrier semantics above */
 void emul_launch(unsigned grid, unsigned block, const std::function<void()>& body);

@@ -1,0 +1,78 @@
+"""The sm_100a path (through the C-ABI) against tests/golden/ref_golden.npz -- outputs of the REFERENCE's own
+kernels (compiled for the CPU by oracle/ref_build.sh; generator: tests/golden/make_ref_golden.py).
+Bar: component counts, in-range counts and ancestor indices bit-exact; floats within 1e-4 relative (ref_cases.py
+states the absolute floors used next to the relative bound)."""
+import os
+
+import numpy as np
+import pytest
+
+import phdslam_b200 as P
+from phdslam_b200 import scene as S
+from conftest import GOLDEN
+import ref_cases as RC
+
+pytestmark = pytest.mark.gpu
+
+GOLD = np.load(os.path.join(GOLDEN, "ref_golden.npz"))
+ALL_CASES = list(RC.UPDATE_CASES) + [RC.LABELED_CASE[0]]
+
+
+def gold(name, key):
+    return GOLD["%s/%s" % (name, key)]
+
+
+def filter_for(name):
+    cfg, _ = RC.build_case(name)
+    if name == RC.LABELED_CASE[0]:
+        cfg.set(measurement_fields=3)
+    g = P.PhdSlam(cfg)
+    g.poses = gold(name, "in_poses")
+    g.log_weights = gold(name, "in_logw")
+    g.set_maps(gold(name, "in_sizes"), gold(name, "in_maps"))
+    return cfg, g
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_cuda_update_terms_vs_reference_kernels(name):
+    cfg, g = filter_for(name)
+    terms, n_in, dlw = g.update_terms(gold(name, "Z"))
+    assert (n_in == gold(name, "n_in")).all()
+    RC.assert_gaussians_close(terms, gold(name, "terms"), name + " terms")
+    RC.close(dlw, gold(name, "dlogw"), name + " particle log-weight increment", atol=2e-5)
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_cuda_full_update_vs_reference_kernels(name):
+    cfg, g = filter_for(name)
+    g.phdUpdateSynth(gold(name, "Z"))
+    sizes, maps = g.get_maps()
+    RC.assert_maps_close(sizes, maps, gold(name, "out_sizes"), gold(name, "out_maps"), name)
+    RC.close(g.log_weights, gold(name, "out_logw"), name + " log-weights", atol=2e-5)
+    e = g.recoverSlamState()
+    ge = gold(name, "expected_pose")[0]
+    RC.close(e.pose, np.array([ge[f] for f in ge.dtype.names]), name + " expected pose", atol=1e-6)
+    assert e.map_particle == int(gold(name, "map_particle"))
+    RC.close(e.neff, gold(name, "neff"), name + " nEff")
+
+
+@pytest.mark.parametrize("mt", [1, 0])
+def test_cuda_predict_vs_reference_kernels(mt):
+    cfg = RC.predict_config(mt)
+    g = P.PhdSlam(cfg)
+    g.poses = GOLD["predict%d/poses" % mt]
+    g.phdPredict(GOLD["predict%d/control" % mt], draws=GOLD["predict%d/draws" % mt])
+    got, want = g.poses, GOLD["predict%d/out" % mt]
+    for f in got.dtype.names:
+        RC.close(got[f], want[f], "predict pose." + f, atol=RC.ATOL_POS)
+
+
+@pytest.mark.parametrize("i", range(4))
+def test_cuda_resample_vs_reference(i):
+    lw, u, idx = GOLD["resample%d/logw" % i], GOLD["resample%d/uniforms" % i], GOLD["resample%d/idx" % i]
+    cfg = S.scene_config(len(lw), 1, 1)
+    g = P.PhdSlam(cfg)
+    g.log_weights = lw
+    anc = g.resampleParticles(uniforms=u)
+    assert (anc == idx).all()
+    RC.close(g.log_weights, GOLD["resample%d/new_logw" % i], "weights after resampling")

@@ -1,6 +1,6 @@
 """Known-answer tests that pin the CPU oracle (oracle/phd_oracle.cpp) to closed-form results,
 independent float64 numpy restatements and the invariants of the GM-PHD recursion.
-The reference ships no tests or golden vectors; see also test_oracle_vs_ref.py."""
+The reference ships no tests or golden vectors; see also test_ref_pin.py (the reference's own kernels run on the CPU)."""
 import math
 
 import numpy as np
