@@ -55,6 +55,8 @@ def load():
         lib.oracle_detmath.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.oracle_philox.argtypes = [C.c_uint] * 6 + [C.c_void_p]
         lib.oracle_esf.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        lib.oracle_cphd_factors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = lib
     return _lib
 
@@ -198,6 +200,33 @@ class Oracle(object):
         out = np.zeros(self.n, dtype=np.int32)
         self.lib.oracle_get_resample_idx(self._h, out.ctypes.data)
         return out
+
+    @property
+    def cardinalities(self):
+        out = np.zeros((self.n, self.cfg.max_cardinality + 1), dtype=np.float32)
+        self.lib.oracle_get_cardinalities(self._h, out.ctypes.data)
+        return out
+
+    @cardinalities.setter
+    def cardinalities(self, v):
+        v = np.ascontiguousarray(v, dtype=np.float32)
+        assert v.shape == (self.n, self.cfg.max_cardinality + 1)
+        self.lib.oracle_set_cardinalities(self._h, v.ctypes.data)
+
+
+def cphd_factors(cfg, w, pd, S, prior):
+    """CPHD multi-object terms of one particle: returns (D[M], ND, inc, card_out[N1])"""
+    lib = load()
+    w = np.ascontiguousarray(w, np.float32)
+    pd = np.ascontiguousarray(pd, np.float32)
+    S = np.ascontiguousarray(S, np.float32)
+    prior = np.ascontiguousarray(prior, np.float32)
+    D = np.zeros(len(S), np.float32)
+    card = np.zeros(len(prior), np.float32)
+    nd, inc = C.c_float(), C.c_float()
+    lib.oracle_cphd_factors(C.byref(cfg), w.ctypes.data, pd.ctypes.data, len(w), S.ctypes.data, len(S), prior.ctypes.data,
+                            len(prior), D.ctypes.data, C.byref(nd), C.byref(inc), card.ctypes.data)
+    return D, nd.value, inc.value, card
 
 
 def detmath(fn, x, y=None):

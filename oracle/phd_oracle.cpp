@@ -263,8 +263,11 @@ struct UpdateOut {
 
 /* preUpdateSynthKernel (src/phdfilter.cu:1824-1925) followed by phdUpdateKernel (:2083-2321)
  * for ONE particle.  `in` are the in-range (class 1) components in map order. */
+static void cphd_factors(const phdslam_config_t& c, const float* w, const float* pd, int C, const float* S, int M,
+                         const float* prior, int N1, float* D, float* ND, float* inc, float* card_out);
+
 static void update_particle(const phdslam_config_t& c, const Pose& pose, const std::vector<G2>& in, const float* z,
-                            int M, int fields, UpdateOut& out) {
+                            int M, int fields, UpdateOut& out, std::vector<float>* card = nullptr) {
   const int C = (int)in.size();
   const int T = C * (M + 1) + M;
   out.n_in = C;
@@ -346,6 +349,32 @@ static void update_particle(const phdslam_config_t& c, const Pose& pose, const s
   for (int m = 0; m < M; ++m) {
     int label = fields > 2 ? (int)z[m * fields + 2] : 0;
     out.terms[C + M * C + m] = birth_term(c, pose, z[m * fields], z[m * fields + 1], label);
+  }
+  if (card) {
+    /* CPHD: cphdPreUpdateKernel (:1430-1511) computes the same partial log-weights; the multi-object terms replace
+     * the per-measurement normaliser (cphd_factors), cphdUpdateKernel (:1780-1822) applies them */
+    std::vector<float> ev(std::max(C, 1)), S(M), D(M), wv(std::max(C, 1));
+    for (int m = 0; m < M; ++m) {
+      G2* det = &out.terms[C + m * C];
+      for (int i = 0; i < C; ++i) ev[i] = phd_expf(det[i].weight);
+      S[m] = (C > 0) ? warp_sum(ev.data(), C) : 0.0f;
+    }
+    for (int i = 0; i < C; ++i) wv[i] = in[i].weight;
+    float ND = 0.0f, inc = 0.0f;
+    std::vector<float> card_out(card->size());
+    cphd_factors(c, wv.data(), pdv.data(), C, S.data(), M, card->data(), (int)card->size(), D.data(), &ND, &inc,
+                 card_out.data());
+    for (int m = 0; m < M; ++m) {
+      G2* det = &out.terms[C + m * C];
+      for (int i = 0; i < C; ++i) det[i].weight = phd_expf(det[i].weight + D[m]);
+      G2& bt = out.terms[C + M * C + m];
+      bt.weight = phd_expf(bt.weight + D[m]);
+    }
+    for (int i = 0; i < C; ++i)                                                  /* :1810-1813 */
+      out.terms[i].weight = phd_expf((phd_safe_log(in[i].weight) + ND) + phd_safe_log(1.0f - pdv[i]));
+    out.dlogw = inc;
+    card->swap(card_out);
+    return;
   }
   /* predicted cardinality: sum of pd*w over features then birthWeight per measurement (:2133-2186) */
   std::vector<float> tmp(C + M);
@@ -536,7 +565,9 @@ extern "C" size_t oracle_update_terms(phd_oracle_t* o, const float* z, int M, in
     std::vector<G2> in, out2, out1;
     split_map(o->cfg, o->states[p], o->maps[p], in, out2, out1);
     UpdateOut u;
-    update_particle(o->cfg, o->states[p], in, z, M, fields, u);
+    std::vector<float> card_copy;
+    if (o->cfg.filter_type == 1) card_copy = o->card[p];          /* the dense terms are a query: state is not advanced */
+    update_particle(o->cfg, o->states[p], in, z, M, fields, u, (o->cfg.filter_type == 1) ? &card_copy : nullptr);
     if (n_in_range_out) n_in_range_out[p] = u.n_in;
     if (dlogw_out) dlogw_out[p] = u.dlogw;
     if (terms_out && k + u.terms.size() <= cap) memcpy(terms_out + k, u.terms.data(), u.terms.size() * sizeof(G2));
@@ -556,9 +587,6 @@ static float log_sum_exp_fx(const std::vector<float>& w) {
   return phd_safe_log(sumf) + mx;
 }
 
-static void cphd_update_particle(phd_oracle_t* o, size_t p, const std::vector<G2>& in, const float* z, int M, int fields,
-                                 UpdateOut& u);
-
 /* phdUpdateSynth (src/phdfilter.cu:3336-3761) */
 extern "C" void oracle_update(phd_oracle_t* o, const float* z, int M, int fields) {
   const phdslam_config_t& c = o->cfg;
@@ -571,10 +599,7 @@ extern "C" void oracle_update(phd_oracle_t* o, const float* z, int M, int fields
     std::vector<G2> in, out2, out1;
     split_map(c, o->states[p], o->maps[p], in, out2, out1);
     UpdateOut u;
-    if (c.filter_type == 1)
-      cphd_update_particle(o, p, in, z, M, fields, u);
-    else
-      update_particle(c, o->states[p], in, z, M, fields, u);
+    update_particle(c, o->states[p], in, z, M, fields, u, (c.filter_type == 1) ? &o->card[p] : nullptr);
     dlogw[p] = u.dlogw;
     /* pruneMap (:3120-3174): stable removal of terms with weight < minFeatureWeight (flags :2308-2319) */
     std::vector<G2> cand;
@@ -826,7 +851,7 @@ extern "C" void oracle_step(phd_oracle_t* o, int step_index, const float* contro
 /* ------------------------------------------------------------------------- */
 
 /* Elementary symmetric functions e_0..e_n of `roots` (Vieta recursion of computeEsfKernel,
- * src/phdfilter.cu:1553-1576, evaluated in double so it is safe for M up to 256). */
+ * src/phdfilter.cu:1553-1576, in double). */
 extern "C" void oracle_esf(const double* roots, int n, double* out) {
   out[0] = 1.0;
   for (int i = 1; i <= n; ++i) out[i] = 0.0;
@@ -834,11 +859,137 @@ extern "C" void oracle_esf(const double* roots, int n, double* out) {
     for (int k = m + 1; k >= 1; --k) out[k] = out[k] + roots[m] * out[k - 1];
 }
 
-static void cphd_update_particle(phd_oracle_t* o, size_t p, const std::vector<G2>& in, const float* z, int M, int fields,
-                                 UpdateOut& u) {
-  (void)o; (void)p; (void)in; (void)z; (void)M; (void)fields; (void)u;
-  fprintf(stderr, "oracle: CPHD update not built yet\n");
-  abort();
+/* k * x with the convention 0 * x = 0 even for x = LOG0 (the reference relies on exp() of huge negatives) */
+static inline float mulk(int k, float x) { return k == 0 ? 0.0f : (float)k * x; }
+static inline float lclamp(float t) { return (t < PHD_LOG0) ? PHD_LOG0 : t; }
+/* log of a non-negative double, as float: exact frexp, float log of the mantissa */
+static inline float logd(double v) {
+  if (!(v > 0.0)) return PHD_LOG0;
+  int ex;
+  double mant = frexp(v, &ex);
+  return phd_logf((float)mant) + (float)ex * 0.693147182f;
+}
+/* log-sum-exp of t[0..n): max, then sum of exp(t - max) in ascending order */
+static float lse_seq(const float* t, int n) {
+  if (n <= 0) return PHD_LOG0;
+  float mx = t[0];
+  for (int i = 1; i < n; ++i) mx = (t[i] > mx) ? t[i] : mx;
+  float s = 0.0f;
+  for (int i = 0; i < n; ++i) s = s + phd_expf(t[i] - mx);
+  return phd_safe_log(s) + mx;
+}
+
+/*
+ * CPHD multi-object terms for ONE particle (Vo, Vo & Cantoni 2007), following the reference's kernels:
+ *   cardinalityPredictKernel (src/phdfilter.cu:867-888, live) with the binomial birth cardinality of
+ *   birthsKernel (src/phdfilter.cu.bak:779-791); computeEsfKernel (:1524-1618, commented at HEAD);
+ *   computePsiKernel (:1626-1769); cphdUpdateKernel (:1780-1822).
+ * Canonical evaluation: fp32 log domain as in the reference, except
+ *   - the elementary symmetric functions run in double on roots scaled by the largest one (the reference's fp32
+ *     linear recursion overflows beyond a handful of measurements; its .bak log-domain form needs |.|);
+ *   - the sums over n and j of <Psi1, p>, <Psi1d_m, p> are exchanged (A1[j] below), which turns the reference's
+ *     O(N M^2) into O(N M + M^2); identical in exact arithmetic;
+ *   - factorial[k] + cn_clutter[k] is spelled k*log(clutterRate) - clutterRate (:735-737, :1691-1692).
+ * HEAD creates the birth terms at update time (one per measurement, weight w_b, always detected), so measurement m's
+ * likelihood mass is S_m + w_b (as in the PHD normaliser, :2213-2214), <1,w> includes M*w_b and <q_D,w> does not.
+ *   in : w[C], pd[C] in-range components; S[M] = sum_j pd_j w_j g_j(z_m); prior[N1] log cardinality
+ *   out: D[M] log factor of measurement m's detection and birth terms; *ND log factor of the non-detection terms;
+ *        *inc particle log-weight increment log<Psi0, p>; card_out[N1] updated log cardinality
+ */
+static void cphd_factors(const phdslam_config_t& c, const float* w, const float* pd, int C, const float* S, int M,
+                         const float* prior, int N1, float* D, float* ND, float* inc, float* card_out) {
+  const int N = N1 - 1;
+  const int nlf = std::max(N, M) + 1;
+  std::vector<float> lf(nlf);
+  lf[0] = 0.0f;
+  for (int k = 1; k < nlf; ++k) lf[k] = lf[k - 1] + phd_safe_log((float)k);           /* .bak:2474-2479 */
+  const float lwb = phd_safe_log(c.birth_weight), l1wb = phd_safe_log(1.0f - c.birth_weight);
+  /* birth cardinality Binomial(M, w_b) (.bak:779-791) */
+  std::vector<float> pb(M + 1);
+  for (int k = 0; k <= M; ++k) {
+    float t = lf[M] - lf[k];
+    t = t - lf[M - k];
+    t = t + mulk(k, lwb);
+    t = t + mulk(M - k, l1wb);
+    pb[k] = t;
+  }
+  /* predicted cardinality (:880-887): plain sum of exp, terms with n-j > M are exactly 0 */
+  std::vector<float> pm(N1);
+  for (int n = 0; n <= N; ++n) {
+    float sum = 0.0f;
+    for (int j = std::max(0, n - M); j <= n; ++j) sum = sum + phd_expf(pb[n - j] + prior[j]);
+    pm[n] = (sum != 0.0f) ? phd_safe_log(sum) : PHD_LOG0;
+  }
+  const float lcr = phd_safe_log(c.clutter_rate), lcd = phd_safe_log(c.clutter_density);
+  const float larea = lcr - lcd;
+  /* log lambda_m (:1539-1552) with the birth mass of measurement m */
+  std::vector<float> llam(M);
+  float lmax = PHD_LOG0;
+  for (int m = 0; m < M; ++m) {
+    llam[m] = phd_safe_log(S[m] + c.birth_weight) + larea;
+    lmax = (llam[m] > lmax) ? llam[m] : lmax;
+  }
+  std::vector<double> x(M);
+  for (int m = 0; m < M; ++m) x[m] = (double)phd_expf(llam[m] - lmax);
+  /* full and leave-one-out elementary symmetric functions (:1553-1616) */
+  std::vector<double> e(M + 1);
+  oracle_esf(x.data(), M, e.data());
+  std::vector<float> le(M + 1), led((size_t)M * std::max(M, 1));
+  for (int j = 0; j <= M; ++j) le[j] = logd(e[j]) + mulk(j, lmax);
+  {
+    std::vector<double> xs(M), ed(M + 1);
+    for (int m = 0; m < M; ++m) {
+      int k = 0;
+      for (int n = 0; n < M; ++n)
+        if (n != m) xs[k++] = x[n];
+      oracle_esf(xs.data(), M - 1, ed.data());
+      for (int j = 0; j < M; ++j) led[(size_t)m * M + j] = logd(ed[j]) + mulk(j, lmax);
+    }
+  }
+  /* <q_D, w> and <1, w> (:1649-1683) */
+  std::vector<float> tmp(std::max(C, 1));
+  for (int j = 0; j < C; ++j) tmp[j] = w[j] * (1.0f - pd[j]);
+  const float q = warp_sum(tmp.data(), C);
+  const float Wsum = warp_sum(w, C) + (float)M * c.birth_weight;
+  const float lq = phd_safe_log(q);
+  const float lW = (Wsum > 0.0f) ? phd_logf(Wsum) : 0.0f;
+  std::vector<float> cK(M + 1);
+  for (int k = 0; k <= M; ++k) cK[k] = mulk(k, lcr) - c.clutter_rate;
+  auto logP = [&](int n, int j) -> float { return (j <= n) ? lf[n] - lf[n - j] : PHD_LOG0; };
+  /* Psi0(n) (:1686-1703) and the updated cardinality (:1767-1768) */
+  std::vector<float> psi0(N1), v(N1), t(std::max(M + 1, N1));
+  for (int n = 0; n <= N; ++n) {
+    int stop = std::min(n, M);
+    for (int j = 0; j <= stop; ++j) t[j] = lclamp(((cK[M - j] + logP(n, j)) + mulk(n - j, lq)) + le[j]);
+    psi0[n] = lclamp(lse_seq(t.data(), stop + 1) - mulk(n, lW));
+    v[n] = lclamp(psi0[n] + pm[n]);
+  }
+  float mx = v[0];
+  for (int n = 1; n <= N; ++n) mx = (v[n] > mx) ? v[n] : mx;
+  for (int n = 0; n <= N; ++n) t[n] = phd_expf(v[n] - mx);
+  const float ip0 = phd_safe_log(warp_sum(t.data(), N1)) + mx;                          /* :1717-1722 */
+  for (int n = 0; n <= N; ++n) card_out[n] = lclamp((pm[n] + psi0[n]) - ip0);
+  /* A1[j] = log sum_n p(n) P(n,j+1) <q_D,w>^(n-j-1) / <1,w>^n */
+  std::vector<float> A1(M + 1);
+  for (int j = 0; j <= M; ++j) {
+    int cnt = 0;
+    for (int n = j + 1; n <= N; ++n) t[cnt++] = lclamp(((pm[n] + logP(n, j + 1)) + mulk(n - j - 1, lq)) - mulk(n, lW));
+    A1[j] = lse_seq(t.data(), cnt);
+  }
+  for (int j = 0; j <= M; ++j) t[j] = lclamp((cK[M - j] + le[j]) + A1[j]);
+  const float ip1 = lse_seq(t.data(), M + 1);                                           /* <Psi1, p>, :1706-1735 */
+  *ND = ip1 - ip0;
+  for (int m = 0; m < M; ++m) {                                                         /* <Psi1d_m, p>, :1738-1764 */
+    for (int j = 0; j < M; ++j) t[j] = lclamp((cK[M - 1 - j] + led[(size_t)m * M + j]) + A1[j]);
+    const float ip1d = lse_seq(t.data(), M);
+    D[m] = ((ip1d - ip0) + lcr) - lcd;                                                  /* :1796-1798 */
+  }
+  *inc = ip0;                                                                           /* .bak:2666 */
+}
+
+extern "C" void oracle_cphd_factors(const phdslam_config_t* cfg, const float* w, const float* pd, int C, const float* S,
+                                    int M, const float* prior, int N1, float* D, float* ND, float* inc, float* card_out) {
+  cphd_factors(*cfg, w, pd, C, S, M, prior, N1, D, ND, inc, card_out);
 }
 
 /* ------------------------------------------------------------------------- */
