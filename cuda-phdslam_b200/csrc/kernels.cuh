@@ -321,11 +321,222 @@ struct UpdArgs {
   float4* cand;                        /* [batch][Smax][2] surviving terms, unordered, term index in .w of the 2nd half */
   int* n_cand;                         /* [n] */
   int Smax;
+  /* CPHD (filter_type 1) */
+  const float* lfact;                  /* log-factorial table, PHD_LF_MAX entries */
+  float* card;                         /* [n][n_card] log cardinality, updated in place */
+  int write_card;                      /* 0 for the dense-terms query (state is not advanced) */
   DevCfg c;
 };
 
-static inline size_t update_smem_bytes(int Cmax) {
+__host__ __device__ static inline size_t update_smem_bytes(int Cmax) {
   return ((size_t)UPD_FLOATS_PER_COMP * Cmax + 6 * PHD_MAX_MEAS + 64) * sizeof(float);
+}
+
+/* =========================================================================================== */
+/* CPHD multi-object terms for the particle of this CTA (oracle: cphd_factors).                   */
+/* Reference: cardinalityPredictKernel (src/phdfilter.cu:867-888) + binomial births               */
+/* (src/phdfilter.cu.bak:779-791), computeEsfKernel (:1524-1618), computePsiKernel (:1626-1769),  */
+/* cphdUpdateKernel (:1780-1822) -- all commented out at HEAD.                         */
+/* 256 threads: thread-per-n for the cardinality-indexed terms, warp-per-job for the (M+1)        */
+/* elementary-symmetric-function recursions (scaled, double) and the measurement-indexed          */
+/* log-sum-exps.  Every reduction has the oracle's shape.                                         */
+/* =========================================================================================== */
+#define PHD_LF_MAX 1025            /* log-factorials 0..1024: max_cardinality <= 1023, M <= 256 */
+#define CPHD_E_STRIDE 264          /* doubles per warp ESF array (M + 1 <= 257) */
+#define CPHD_KREG 9                /* ceil(257 / 32) */
+
+static inline size_t cphd_smem_bytes(int n_card) {
+  /* floats: lf | pm | psi (prior, then psi0) | pb, A1, le, cK (257 each) | llam, ip1d (256 each) | 16 scalars
+   * doubles: x[256] | UPD_WARPS ESF arrays */
+  size_t floats = (size_t)PHD_LF_MAX + 2 * (size_t)n_card + 4 * 257 + 2 * 256 + 16;
+  floats = (floats + 1) & ~(size_t)1;
+  return floats * sizeof(float) + (256 + (size_t)(UPD_THREADS / 32) * CPHD_E_STRIDE) * sizeof(double);
+}
+
+__device__ __forceinline__ float cphd_mulk(int k, float x) { return k == 0 ? 0.0f : (float)k * x; }
+__device__ __forceinline__ float cphd_clamp(float t) { return (t < PHD_LOG0) ? PHD_LOG0 : t; }
+__device__ __forceinline__ float cphd_logd(double v) {
+  if (!(v > 0.0)) return PHD_LOG0;
+  int ex;
+  double mant = frexp(v, &ex);
+  return phd_logf((float)mant) + (float)ex * 0.693147182f;
+}
+/* log-sum-exp over i in [0, n) of f(i) with the canonical warp shape (oracle: lse_warp); full warp */
+template <class F>
+__device__ __forceinline__ float cphd_lse_warp(int n, F f) {
+  if (n <= 0) return PHD_LOG0;
+  const int lane = lane_id();
+  float mx = -INFINITY;
+  for (int i = lane; i < n; i += 32) mx = fmaxf(mx, f(i));
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL_MASK, mx, off));
+  float a0 = 0.0f, a1 = 0.0f;
+  for (int i = 2 * lane; i < n; i += 64) {
+    a0 = a0 + phd_expf(f(i) - mx);
+    if (i + 1 < n) a1 = a1 + phd_expf(f(i + 1) - mx);
+  }
+  return phd_safe_log(warp_butterfly_sum(a0 + a1)) + mx;
+}
+
+/* one root x folded into the warp's ESF array E[0..deg+1]: E[k] += x * E[k-1] (old values), lane-strided k */
+__device__ __forceinline__ void cphd_esf_step(double* E, int deg, double x, int lane) {
+  double nk[CPHD_KREG];
+#pragma unroll
+  for (int r = 0; r < CPHD_KREG; ++r) {
+    int k = lane + 1 + 32 * r;
+    nk[r] = (k <= deg + 1) ? __dadd_rn(E[k], __dmul_rn(x, E[k - 1])) : 0.0;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < CPHD_KREG; ++r) {
+    int k = lane + 1 + 32 * r;
+    if (k <= deg + 1) E[k] = nk[r];
+  }
+  __syncwarp();
+}
+
+/* in: s_w[C] weights, s_qd[C] = w*(1-pd), s_S[M] likelihood masses (overwritten by D[m], the log factor of
+ * measurement m's detection and birth terms).  out: scal[0] = ND (log factor of the non-detection terms),
+ * scal[1] = log<Psi0,p> (particle log-weight increment); card updated in place when write_card. */
+__device__ void cphd_block(const DevCfg& c, int C, int M, const float* __restrict__ lfact, float* __restrict__ card,
+                           int write_card, const float* s_w, const float* s_qd, float* s_S, float* scal_out,
+                           unsigned char* smem_cphd) {
+  const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+  const int N1 = c.n_card, N = N1 - 1;
+  float* s_lf = reinterpret_cast<float*>(smem_cphd);
+  float* s_pm = s_lf + PHD_LF_MAX;
+  float* s_psi = s_pm + N1;
+  float* s_pb = s_psi + N1;
+  float* s_A1 = s_pb + 257;
+  float* s_le = s_A1 + 257;
+  float* s_cK = s_le + 257;
+  float* s_llam = s_cK + 257;
+  float* s_ip1d = s_llam + 256;
+  float* s_sc = s_ip1d + 256;            /* 16 scalars: 0 lq, 1 lW, 2 lmax, 3 ip0, 4 ip1 */
+  size_t foff = (size_t)PHD_LF_MAX + 2 * (size_t)N1 + 4 * 257 + 2 * 256 + 16;
+  foff = (foff + 1) & ~(size_t)1;
+  double* s_x = reinterpret_cast<double*>(reinterpret_cast<float*>(smem_cphd) + foff);
+  double* s_e = s_x + 256;
+
+  const int nlf = max(N, M) + 1;
+  const float wb = c.birth_weight;
+  const float lwb = phd_safe_log(wb), l1wb = phd_safe_log(1.0f - wb);
+  const float lcr = phd_safe_log(c.clutter_rate), lcd = phd_safe_log(c.clutter_density);
+  const float larea = lcr - lcd;
+
+  for (int k = tid; k < nlf; k += UPD_THREADS) s_lf[k] = lfact[k];
+  for (int n = tid; n < N1; n += UPD_THREADS) s_psi[n] = card[n];          /* prior */
+  for (int m = tid; m < M; m += UPD_THREADS) s_llam[m] = phd_safe_log(s_S[m] + wb) + larea;   /* :1539-1552 */
+  if (warp == 0) {                                                            /* <q_D,w>, <1,w> (:1649-1683) */
+    float q = warp_sum_array(s_qd, C);
+    float Wsum = warp_sum_array(s_w, C) + (float)M * wb;
+    if (lane == 0) {
+      s_sc[0] = phd_safe_log(q);
+      s_sc[1] = (Wsum > 0.0f) ? phd_logf(Wsum) : 0.0f;
+    }
+  }
+  __syncthreads();
+  /* birth cardinality Binomial(M, w_b) (.bak:779-791), clutter term k*log(cr) - cr (:735-737, :1691-1692) */
+  for (int k = tid; k <= M; k += UPD_THREADS) {
+    float t = s_lf[M] - s_lf[k];
+    t = t - s_lf[M - k];
+    t = t + cphd_mulk(k, lwb);
+    t = t + cphd_mulk(M - k, l1wb);
+    s_pb[k] = t;
+    s_cK[k] = cphd_mulk(k, lcr) - c.clutter_rate;
+  }
+  if (warp == 0) {
+    float mx = PHD_LOG0;
+    for (int m = lane; m < M; m += 32) mx = fmaxf(mx, s_llam[m]);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL_MASK, mx, off));
+    if (lane == 0) s_sc[2] = mx;
+  }
+  __syncthreads();
+  const float lq = s_sc[0], lW = s_sc[1], lmax = s_sc[2];
+  /* predicted cardinality (:880-887): plain sum of exp; the terms with n-j > M are exactly 0 */
+  for (int n = tid; n < N1; n += UPD_THREADS) {
+    float sum = 0.0f;
+    for (int j = max(0, n - M); j <= n; ++j) sum = sum + phd_expf(s_pb[n - j] + s_psi[j]);
+    s_pm[n] = phd_safe_log(sum);
+  }
+  for (int m = tid; m < M; m += UPD_THREADS) s_x[m] = (double)phd_expf(s_llam[m] - lmax);
+  __syncthreads();
+  /* A1[j] = log sum_{n>j} p(n) P(n,j+1) <q_D,w>^(n-j-1) / <1,w>^n : one warp per j */
+  for (int j = warp; j <= M; j += UPD_WARPS) {
+    float v = cphd_lse_warp(N - j, [&](int i) {
+      const int n = j + 1 + i;
+      return cphd_clamp(((s_pm[n] + (s_lf[n] - s_lf[n - j - 1])) + cphd_mulk(n - j - 1, lq)) - cphd_mulk(n, lW));
+    });
+    if (lane == 0) s_A1[j] = v;
+  }
+  __syncthreads();
+  /* elementary symmetric functions of the scaled roots (:1553-1616): job 0 = all roots, job m+1 = leave m out */
+  {
+    double* E = s_e + (size_t)warp * CPHD_E_STRIDE;
+    for (int job = warp; job <= M; job += UPD_WARPS) {
+      for (int k = lane; k <= M; k += 32) E[k] = (k == 0) ? 1.0 : 0.0;
+      __syncwarp();
+      int deg = 0;
+      for (int n = 0; n < M; ++n) {
+        if (n == job - 1) continue;
+        cphd_esf_step(E, deg, s_x[n], lane);
+        ++deg;
+      }
+      if (job == 0) {
+        for (int j = lane; j <= M; j += 32) s_le[j] = cphd_logd(E[j]) + cphd_mulk(j, lmax);
+      } else {
+        /* <Psi1d_m, p> (:1738-1764) */
+        float v = cphd_lse_warp(M, [&](int j) {
+          return cphd_clamp((s_cK[M - 1 - j] + (cphd_logd(E[j]) + cphd_mulk(j, lmax))) + s_A1[j]);
+        });
+        if (lane == 0) s_ip1d[job - 1] = v;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  /* Psi0(n) (:1686-1703), thread per n, sequential log-sum-exp over j (oracle: lse_seq) */
+  for (int n = tid; n < N1; n += UPD_THREADS) {
+    const int stop = min(n, M);
+    float mx = -INFINITY;
+    for (int j = 0; j <= stop; ++j)
+      mx = fmaxf(mx, cphd_clamp(((s_cK[M - j] + (s_lf[n] - s_lf[n - j])) + cphd_mulk(n - j, lq)) + s_le[j]));
+    float sum = 0.0f;
+    for (int j = 0; j <= stop; ++j)
+      sum = sum + phd_expf(cphd_clamp(((s_cK[M - j] + (s_lf[n] - s_lf[n - j])) + cphd_mulk(n - j, lq)) + s_le[j]) - mx);
+    s_psi[n] = cphd_clamp((phd_safe_log(sum) + mx) - cphd_mulk(n, lW));
+  }
+  __syncthreads();
+  if (warp == 0) {        /* <Psi0, p> (:1717-1722) */
+    float v = cphd_lse_warp(N1, [&](int n) { return cphd_clamp(s_psi[n] + s_pm[n]); });
+    if (lane == 0) s_sc[3] = v;
+  } else if (warp == 1) { /* <Psi1, p> (:1706-1735) */
+    float v = cphd_lse_warp(M + 1, [&](int j) { return cphd_clamp((s_cK[M - j] + s_le[j]) + s_A1[j]); });
+    if (lane == 0) s_sc[4] = v;
+  }
+  __syncthreads();
+  const float ip0 = s_sc[3], ip1 = s_sc[4];
+  if (write_card)
+    for (int n = tid; n < N1; n += UPD_THREADS) card[n] = cphd_clamp((s_pm[n] + s_psi[n]) - ip0);    /* :1767-1768 */
+  for (int m = tid; m < M; m += UPD_THREADS) s_S[m] = ((s_ip1d[m] - ip0) + lcr) - lcd;                /* :1796-1798 */
+  if (tid == 0) {
+    scal_out[0] = ip1 - ip0;
+    scal_out[1] = ip0;
+  }
+  __syncthreads();
+}
+
+/* log-factorial table, sequential as the reference builds it (src/phdfilter.cu.bak:2474-2479) */
+__global__ void lfact_kernel(float* lf, int n) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float acc = 0.0f;
+    lf[0] = 0.0f;
+    for (int k = 1; k < n; ++k) {
+      acc = acc + phd_safe_log((float)k);
+      lf[k] = acc;
+    }
+  }
 }
 
 /* dense layout: terms in blocks of 64; a block stores its 7 planes back to back (7 x 256 bytes), so one
@@ -483,7 +694,7 @@ __device__ __forceinline__ float2 upd_measurement(const float2* __restrict__ rec
   return acc;
 }
 
-template <bool DENSE>
+template <bool DENSE, bool CPHD>
 __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
   extern __shared__ __align__(16) float smem[];
   const DevCfg& c = a.c;
@@ -504,6 +715,7 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
   float* s_ds = s_L + PHD_MAX_MEAS;     /* PHD_MAX_MEAS; the remaining slack covers even padding */
   __shared__ int s_wcnt[UPD_WARPS];
   __shared__ int s_ncand;
+  __shared__ float s_cphd_scal[2];
 
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
   const int pl = a.p0 + blockIdx.x;     /* local particle index */
@@ -601,16 +813,18 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
       rec[2 * F_NHL] = -(0.5f * phd_safe_log(det));
       rec[2 * F_CU0] = cu0; rec[2 * F_CU1] = cu1; rec[2 * F_CU2] = cu2; rec[2 * F_CU3] = cu3;
       rec[2 * F_MX] = fx; rec[2 * F_MY] = fy;
-      s_tmp[j] = pd * w;
-      /* non-detection term (:2137-2141) */
+      s_tmp[j] = CPHD ? pd : pd * w;
+      /* non-detection term (:2137-2141); CPHD scales it by <Psi1,p>/<Psi0,p> later (phase 2b) */
       wnd = w * (1.0f - pd);
       s_nd[j] = wnd;
-      if (DENSE) {
-        float* q = D + dense_index((size_t)j);
-        st_stream(q, P0); st_stream(q + 64, P1); st_stream(q + 128, P2); st_stream(q + 192, P3);
-        st_stream(q + 256, fx); st_stream(q + 320, fy); st_stream(q + 384, wnd);
+      if (!CPHD) {
+        if (DENSE) {
+          float* q = D + dense_index((size_t)j);
+          st_stream(q, P0); st_stream(q + 64, P1); st_stream(q + 128, P2); st_stream(q + 192, P3);
+          st_stream(q + 256, fx); st_stream(q + 320, fy); st_stream(q + 384, wnd);
+        }
+        keep = !(wnd < c.min_w);
       }
-      keep = !(wnd < c.min_w);
     }
     /* survivors of the prune go to the merge as 32-byte records (warp-aggregated slot allocation) */
     unsigned bal = __ballot_sync(FULL_MASK, keep);
@@ -647,8 +861,58 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
     }
   }
 
-  /* ---- phase 2: detection terms; warp w owns measurements w, w+8, ... (:1898-1923, :2190-2252) ---- */
   const bool even = ((C & 1) == 0);      /* 64-bit stores need (C + m*C + j) even for every m */
+  if (CPHD) {
+    /* ---- CPHD phase 2a: likelihood mass S_m = sum_j exp(partial log-weight) of every measurement ---- */
+    for (int m = warp; m < M; m += UPD_WARPS) {
+      const float zr = s_zr[m], zb = s_zb[m];
+      const bool dead = c.labeled && (s_zl[m] != 0.0f);
+      const bool fast = fabsf(zb) < 3.14159f;
+      float2 acc;
+      if (fast)
+        acc = upd_measurement<1, true, DENSE>(s_rec, C, splat2(zr), splat2(zb), dead, splat2(0.0f), D, even, c.min_w, lane, &s_ncand, cand, Smax, 0);
+      else
+        acc = upd_measurement<1, false, DENSE>(s_rec, C, splat2(zr), splat2(zb), dead, splat2(0.0f), D, even, c.min_w, lane, &s_ncand, cand, Smax, 0);
+      float sum = warp_butterfly_sum(acc.x + acc.y);
+      if (lane == 0) s_L[m] = sum;
+    }
+    __syncthreads();
+    /* ---- multi-object terms: s_L[m] becomes the log factor D_m of measurement m ---- */
+    cphd_block(c, C, M, a.lfact, a.card + (size_t)pl * c.n_card, a.write_card, s_w, s_nd, s_L, s_cphd_scal,
+               reinterpret_cast<unsigned char*>(smem) + update_smem_bytes(Cmax));
+    const float ND = s_cphd_scal[0];
+    /* ---- CPHD phase 2b: non-detection terms (cphdUpdateKernel :1803-1820) ---- */
+    for (int j0 = 0; j0 < C; j0 += UPD_THREADS) {
+      const int j = j0 + tid;
+      bool keep = false;
+      float P0 = 0, P1 = 0, P3 = 0, fx = 0, fy = 0, wnd = 0;
+      if (j < C) {
+        fx = s_mx[j]; fy = s_my[j];
+        P0 = s_pxx[j]; P1 = s_pxy[j]; P3 = s_pyy[j];
+        wnd = phd_expf((phd_safe_log(s_w[j]) + ND) + phd_safe_log(1.0f - s_tmp[j]));
+        if (DENSE) {
+          float* q = D + dense_index((size_t)j);
+          st_stream(q, P0); st_stream(q + 64, P1); st_stream(q + 128, P1); st_stream(q + 192, P3);
+          st_stream(q + 256, fx); st_stream(q + 320, fy); st_stream(q + 384, wnd);
+        }
+        keep = !(wnd < c.min_w);
+      }
+      unsigned bal = __ballot_sync(FULL_MASK, keep);
+      if (bal) {
+        int slot0 = 0;
+        if (lane == 0) slot0 = atomicAdd(&s_ncand, __popc(bal));
+        slot0 = __shfl_sync(FULL_MASK, slot0, 0);
+        if (keep) {
+          int slot = slot0 + __popc(bal & lt_mask);
+          if (slot < Smax) {
+            cand[2 * slot] = make_float4(P0, P1, P1, P3);
+            cand[2 * slot + 1] = make_float4(fx, fy, wnd, __int_as_float(j));
+          }
+        }
+      }
+    }
+  }
+  /* ---- phase 2: detection terms; warp w owns measurements w, w+8, ... (:1898-1923, :2190-2252) ---- */
   for (int m = warp; m < M; m += UPD_WARPS) {
     const float zr = s_zr[m], zb = s_zb[m];
     const bool dead = c.labeled && (s_zl[m] != 0.0f);
@@ -656,15 +920,20 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
     /* |zb| < 3.14159 and |bearing| <= float(pi) => |zb - bearing| < float(2*pi): wrap needs no fmod */
     const bool fast = fabsf(zb) < 3.14159f;
     const int tbase_m = C + m * C;
-    float2 acc;
-    if (fast)
-      acc = upd_measurement<1, true, DENSE>(s_rec, C, zr2, zb2, dead, splat2(0.0f), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m);
-    else
-      acc = upd_measurement<1, false, DENSE>(s_rec, C, zr2, zb2, dead, splat2(0.0f), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m);
-    float sum = warp_butterfly_sum(acc.x + acc.y);
-    sum = sum + c.clutter_density;
-    sum = sum + c.birth_weight;
-    const float L = phd_safe_log(sum);
+    float L;
+    if (CPHD) {
+      L = -s_L[m];                        /* weights = exp(partial log-weight + D_m) (cphdUpdateKernel :1794-1799) */
+    } else {
+      float2 acc;
+      if (fast)
+        acc = upd_measurement<1, true, DENSE>(s_rec, C, zr2, zb2, dead, splat2(0.0f), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m);
+      else
+        acc = upd_measurement<1, false, DENSE>(s_rec, C, zr2, zb2, dead, splat2(0.0f), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m);
+      float sum = warp_butterfly_sum(acc.x + acc.y);
+      sum = sum + c.clutter_density;
+      sum = sum + c.birth_weight;
+      L = phd_safe_log(sum);
+    }
     float2 wacc;
     if (fast)
       wacc = upd_measurement<2, true, DENSE>(s_rec, C, zr2, zb2, dead, splat2(-L), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m);
@@ -697,7 +966,7 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
           cand[2 * slot + 1] = make_float4(px + bdx, py + bdy, wb, __int_as_float(t));
         }
       }
-      s_L[m] = L;
+      if (!CPHD) s_L[m] = L;
       s_ds[m] = dsum + wb;
     }
   }
@@ -708,7 +977,9 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
     float pw = 0.0f;
     for (int m = 0; m < M; ++m) pw = pw + s_L[m];
     float out;
-    if (c.particle_weighting == 0) {
+    if (CPHD) {
+      out = s_cphd_scal[1];              /* log <Psi0, p> (src/phdfilter.cu.bak:2666) */
+    } else if (c.particle_weighting == 0) {
       out = pw - card_predict;
     } else if (c.particle_weighting == 1) {
       float cn_update = nd_sum;

@@ -151,10 +151,11 @@ static int validate_config(const phdslam_config_t* c) {
     phdslam_set_error("n_predict_particles != 1 is not built yet");
     return PHDSLAM_ERR_INVALID;
   }
-  if (c->filter_type == 1) {
-    phdslam_set_error("filter_type = 1 (CPHD) is not built yet");
+  if (c->filter_type == 1 && (c->max_cardinality < 1 || c->max_cardinality + 1 >= PHD_LF_MAX)) {
+    phdslam_set_error("CPHD: max_cardinality must be in [1, 1023]");
     return PHDSLAM_ERR_INVALID;
   }
+  if (c->filter_type != 0 && c->filter_type != 1) return PHDSLAM_ERR_INVALID;
   if (c->subdivide_predict < 1) return PHDSLAM_ERR_INVALID;
   return 0;
 }
@@ -169,8 +170,8 @@ static void free_state(phdslam* h) {
   cudaFree(h->dense); cudaFree(h->z_dev); cudaFree(h->draws_dev); cudaFree(h->q_fx); cudaFree(h->cdf_excl);
   cudaFree(h->ancestors); cudaFree(h->red); cudaFree(h->cand); cudaFree(h->cand_in); cudaFree(h->n_cand);
   cudaFree(h->mig_map); cudaFree(h->mig_pose); cudaFree(h->mig_count); cudaFree(h->mig_anc); cudaFree(h->mig_card);
-  cudaFree(h->mig_pose_in); cudaFree(h->totals_dev);
-  h->mig_pose_in = nullptr; h->totals_dev = nullptr;
+  cudaFree(h->mig_pose_in); cudaFree(h->totals_dev); cudaFree(h->lfact);
+  h->mig_pose_in = nullptr; h->totals_dev = nullptr; h->lfact = nullptr;
   if (h->red_host) cudaFreeHost(h->red_host);
 }
 
@@ -198,6 +199,7 @@ static int alloc_state(phdslam* h) {
   CK(cudaMalloc(&h->ancestors, n * sizeof(int)));
   CK(cudaMalloc(&h->red, sizeof(Reductions)));
   CK(cudaMallocHost(&h->red_host, sizeof(Reductions)));
+  CK(cudaMalloc(&h->lfact, PHD_LF_MAX * sizeof(float)));
   return 0;
 }
 
@@ -221,6 +223,8 @@ static int init_particles(phdslam* h) {
                                                                             -phd_logf((float)h->n_card));
     LAUNCH_CHECK(h);
   }
+  lfact_kernel<<<1, 32, 0, h->stream>>>(h->lfact, PHD_LF_MAX);
+  LAUNCH_CHECK(h);
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -251,8 +255,18 @@ extern "C" int phdslam_create(const phdslam_config_t* cfg, int device, phdslam_t
   for (int i = 0; i < 12; ++i) CK(cudaEventCreate(&h->ev[i]));
   rc = alloc_state(h);
   if (rc) { free_state(h); delete h; return rc; }
-  CK(cudaFuncSetAttribute(update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(h->Cmax)));
-  CK(cudaFuncSetAttribute(update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(h->Cmax)));
+  CK(cudaFuncSetAttribute(update_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(h->Cmax)));
+  CK(cudaFuncSetAttribute(update_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(h->Cmax)));
+  if (h->n_card) {
+    const size_t sm = update_smem_bytes(h->Cmax) + cphd_smem_bytes(h->n_card);
+    if (sm > 227 * 1024) {
+      phdslam_set_error("CPHD: max_components / max_cardinality need more than 227 KB of shared memory per particle");
+      free_state(h); delete h;
+      return PHDSLAM_ERR_INVALID;
+    }
+    CK(cudaFuncSetAttribute(update_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    CK(cudaFuncSetAttribute(update_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  }
   CK(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem_bytes(h->Smax)));
   rc = init_particles(h);
   if (rc) { free_state(h); delete h; return rc; }
@@ -470,16 +484,24 @@ static int plan_batches(phdslam* h, bool dense, std::vector<int>& bounds, size_t
   return 0;
 }
 
-static int launch_update_batch(phdslam* h, int M, int p0, int p1, unsigned long long tbase, bool dense) {
+static int launch_update_batch(phdslam* h, int M, int p0, int p1, unsigned long long tbase, bool dense, int write_card = 1) {
   UpdArgs a;
+  a.lfact = h->lfact; a.card = h->n_card ? h->card[h->cur] : nullptr; a.write_card = write_card;
   a.map = h->map[h->cur]; a.count = h->count[h->cur]; a.cls = h->cls; a.pose = h->pose[h->cur];
   a.z = h->z_dev; a.M = M; a.n = h->n_local; a.p0 = p0;
   a.toff = h->toff; a.tbase = tbase; a.dense = h->dense; a.n_in = h->n_in; a.dlogw = h->dlogw; a.c = h->dc;
   a.cand = h->cand_in; a.n_cand = h->n_cand; a.Smax = h->Smax;
-  if (dense)
-    update_kernel<true><<<p1 - p0, UPD_THREADS, update_smem_bytes(h->Cmax), h->stream>>>(a);
-  else
-    update_kernel<false><<<p1 - p0, UPD_THREADS, update_smem_bytes(h->Cmax), h->stream>>>(a);
+  if (h->n_card) {
+    const size_t sm = update_smem_bytes(h->Cmax) + cphd_smem_bytes(h->n_card);
+    if (dense)
+      update_kernel<true, true><<<p1 - p0, UPD_THREADS, sm, h->stream>>>(a);
+    else
+      update_kernel<false, true><<<p1 - p0, UPD_THREADS, sm, h->stream>>>(a);
+  } else if (dense) {
+    update_kernel<true, false><<<p1 - p0, UPD_THREADS, update_smem_bytes(h->Cmax), h->stream>>>(a);
+  } else {
+    update_kernel<false, false><<<p1 - p0, UPD_THREADS, update_smem_bytes(h->Cmax), h->stream>>>(a);
+  }
   LAUNCH_CHECK(h);
   return 0;
 }
@@ -603,7 +625,7 @@ extern "C" int phdslam_update_terms(phdslam_t* h, const float* z, int M, int fie
   CK(cudaEventRecord(h->ev[3], h->stream));
   rc = ensure_cand(h, (size_t)n);
   if (rc) return rc;
-  rc = launch_update_batch(h, M, 0, n, 0, true);
+  rc = launch_update_batch(h, M, 0, n, 0, true, /*write_card=*/0);   /* a query: the cardinality is not advanced */
   if (rc) return rc;
   CK(cudaEventRecord(h->ev[4], h->stream));
   CK(cudaStreamSynchronize(h->stream));

@@ -92,6 +92,7 @@ struct phdslam {
   /* resampling migration staging (sender side), grown on demand */
   float* mig_map; float* mig_pose; int* mig_count; int* mig_anc; float* mig_card; float* mig_pose_in; size_t mig_cap;
   unsigned long long* totals_dev; /* [world] all-gathered local CDF totals */
+  float* lfact;                   /* log-factorial table for the CPHD terms (PHD_LF_MAX floats) */
 };
 
 #endif

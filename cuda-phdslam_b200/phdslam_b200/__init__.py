@@ -401,6 +401,19 @@ class PhdSlam(object):
         _check(self.lib.phdslam_get_resample_idx(self._h, out.ctypes.data))
         return out
 
+    @property
+    def cardinalities(self):
+        """CPHD: (n_local, max_cardinality+1) log cardinality distributions (SynthSLAM::cardinalities)"""
+        out = np.zeros((self.n_local, self.cfg.max_cardinality + 1), dtype=np.float32)
+        _check(self.lib.phdslam_get_cardinalities(self._h, out.ctypes.data))
+        return out
+
+    @cardinalities.setter
+    def cardinalities(self, v):
+        v = np.ascontiguousarray(v, dtype=np.float32)
+        assert v.shape == (self.n_local, self.cfg.max_cardinality + 1)
+        _check(self.lib.phdslam_set_cardinalities(self._h, v.ctypes.data))
+
     def timings(self):
         t = Timings()
         _check(self.lib.phdslam_get_timings(self._h, C.byref(t)))

@@ -879,6 +879,15 @@ static float lse_seq(const float* t, int n) {
   return phd_safe_log(s) + mx;
 }
 
+/* log-sum-exp with the kernels' warp reduction shape: max, then warp_sum of exp(t - max) */
+static float lse_warp(float* t, int n) {
+  if (n <= 0) return PHD_LOG0;
+  float mx = t[0];
+  for (int i = 1; i < n; ++i) mx = (t[i] > mx) ? t[i] : mx;
+  for (int i = 0; i < n; ++i) t[i] = phd_expf(t[i] - mx);
+  return phd_safe_log(warp_sum(t, n)) + mx;
+}
+
 /*
  * CPHD multi-object terms for ONE particle (Vo, Vo & Cantoni 2007), following the reference's kernels:
  *   cardinalityPredictKernel (src/phdfilter.cu:867-888, live) with the binomial birth cardinality of
@@ -964,24 +973,22 @@ static void cphd_factors(const phdslam_config_t& c, const float* w, const float*
     psi0[n] = lclamp(lse_seq(t.data(), stop + 1) - mulk(n, lW));
     v[n] = lclamp(psi0[n] + pm[n]);
   }
-  float mx = v[0];
-  for (int n = 1; n <= N; ++n) mx = (v[n] > mx) ? v[n] : mx;
-  for (int n = 0; n <= N; ++n) t[n] = phd_expf(v[n] - mx);
-  const float ip0 = phd_safe_log(warp_sum(t.data(), N1)) + mx;                          /* :1717-1722 */
+  for (int n = 0; n <= N; ++n) t[n] = v[n];
+  const float ip0 = lse_warp(t.data(), N1);                                             /* :1717-1722 */
   for (int n = 0; n <= N; ++n) card_out[n] = lclamp((pm[n] + psi0[n]) - ip0);
   /* A1[j] = log sum_n p(n) P(n,j+1) <q_D,w>^(n-j-1) / <1,w>^n */
   std::vector<float> A1(M + 1);
   for (int j = 0; j <= M; ++j) {
     int cnt = 0;
     for (int n = j + 1; n <= N; ++n) t[cnt++] = lclamp(((pm[n] + logP(n, j + 1)) + mulk(n - j - 1, lq)) - mulk(n, lW));
-    A1[j] = lse_seq(t.data(), cnt);
+    A1[j] = lse_warp(t.data(), cnt);
   }
   for (int j = 0; j <= M; ++j) t[j] = lclamp((cK[M - j] + le[j]) + A1[j]);
-  const float ip1 = lse_seq(t.data(), M + 1);                                           /* <Psi1, p>, :1706-1735 */
+  const float ip1 = lse_warp(t.data(), M + 1);                                          /* <Psi1, p>, :1706-1735 */
   *ND = ip1 - ip0;
   for (int m = 0; m < M; ++m) {                                                         /* <Psi1d_m, p>, :1738-1764 */
     for (int j = 0; j < M; ++j) t[j] = lclamp((cK[M - 1 - j] + led[(size_t)m * M + j]) + A1[j]);
-    const float ip1d = lse_seq(t.data(), M);
+    const float ip1d = lse_warp(t.data(), M);
     D[m] = ((ip1d - ip0) + lcr) - lcd;                                                  /* :1796-1798 */
   }
   *inc = ip0;                                                                           /* .bak:2666 */
