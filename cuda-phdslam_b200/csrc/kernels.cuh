@@ -1025,6 +1025,10 @@ struct MrgArgs {
   float4* cand;                        /* [p1-p0][Smax][2] scratch: candidates in canonical (term) order */
   Reductions* red;
   int Smax;
+  /* fast kernel: shared-memory capacity (candidates per particle); particles above it are queued for merge_kernel */
+  int Scap;
+  int* ovf_list;                       /* [n] local particle indices queued by merge_fast_kernel */
+  int use_list;                        /* merge_kernel: 1 = process red->ovf_n particles of ovf_list instead of [p0, p1) */
   DevCfg c;
 };
 
@@ -1143,7 +1147,12 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
   const DevCfg& c = a.c;
   const int Smax = a.Smax;
   const int lane = lane_id(), warp = warp_id();
-  const int pl = a.p0 + blockIdx.x * MRG_WARPS + warp;
+  int pl = a.p0 + blockIdx.x * MRG_WARPS + warp;
+  if (a.use_list) {         /* the particles merge_fast_kernel could not hold in shared memory */
+    const int k = blockIdx.x * MRG_WARPS + warp;
+    if (k >= a.red->ovf_n) return;
+    pl = a.ovf_list[k];
+  }
   if (pl >= a.p1) return;   /* warps are independent: no block barrier below */
 
   unsigned char* base0 = smem_raw + (size_t)warp * merge_warp_smem_bytes(Smax);
@@ -1512,6 +1521,620 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
       pos0 = Cmax;
     }
     a.count_out[pl] = pos0;
+  }
+}
+
+/* =========================================================================================== */
+/* merge_fast_kernel: the same prune + merge (same candidates, same arithmetic, same output order   */
+/* as merge_kernel and the oracle's merge_mixture), restructured so that nothing is serial in the   */
+/* number of output components.                                                                     */
+/*                                                                                                  */
+/* The greedy reduction "take the heaviest unmerged candidate, absorb every unmerged candidate      */
+/* within the distance threshold, repeat" is a priority maximal-independent-set problem: with the   */
+/* candidates ranked by (weight desc, reference tie rule), candidate r is a SEED iff no seed of      */
+/* lower rank is near it, and otherwise it belongs to the lowest-ranked seed near it (every member   */
+/* of a seed's cluster has a higher rank than the seed, because the seed was the arg-max of what     */
+/* was left).  One CTA of MF_WARPS warps per particle:                                               */
+/*  1. block-wide stable radix sorts put the prune survivors back in term order and rank the          */
+/*     candidates; the gate data {x, y, w, lambda_max} of every candidate sits in shared memory in   */
+/*     RANK order, the full records go to the (L2-resident) scratch buffer in rank order;             */
+/*  2. candidates are binned in the uniform grid of merge_kernel.  Cell by cell (cells dealt to the   */
+/*     warps), the lanes hold the candidates of the cell's 3x3 neighbourhood and the candidates of    */
+/*     the cell are broadcast against them: the cheap Euclidean gate runs on all lanes, pairs that    */
+/*     pass are queued and the Mahalanobis distance is evaluated 32 queued pairs at a time -- no       */
+/*     divergence on the expensive part.  A near pair (lower rank, higher rank) is appended to the    */
+/*     higher-ranked candidate's linked list (nodes from a per-particle pool);                        */
+/*  3. ownership is resolved from the lists in rank order, 32 ranks at a time (ballots);              */
+/*  4. a counting sort by output slot, stable in candidate index, gives every cluster its members    */
+/*     in ascending index order (the canonical accumulation order), and one THREAD per cluster       */
+/*     accumulates the moment-matched merge; stores are coalesced across clusters.                   */
+/* Particles with more candidates than the shared-memory capacity Scap (adapted by the host from     */
+/* the previous step), or with more than MF_POOL * Scap near pairs, are queued for merge_kernel.      */
+/* Mahalanobis metric only.                                                                           */
+/* =========================================================================================== */
+#define MF_WARPS 4
+#define MF_THREADS (MF_WARPS * 32)
+#define MF_POOL 3            /* near-pair pool: MF_POOL list nodes per candidate of capacity (a particle that needs more takes merge_kernel) */
+#define MF_NONE 0xffffu
+#define MF_CELLS 592         /* MRG_NCELL + 1, padded */
+#define MF_QUEUE 256         /* gate survivors queued per warp (ring buffer) */
+#define MF_ACH 8             /* A candidates gated per compaction step (up to MF_ACH * 32 new queue entries; a step that
+                                does not fit the ring sends the particle to merge_kernel) */
+
+__host__ __device__ static inline size_t merge_fast_smem_bytes(int S) {
+  /* gate data 16 B | four u16 arrays | list heads 4 B | near-pair pool | per-warp radix histograms (the grid's cell ends
+   * alias them) | pair queues */
+  return (size_t)S * (16 + 8 + 4 + 4 * MF_POOL) + (size_t)MF_ACH * 16 + (size_t)MF_WARPS * 512 + (size_t)MF_WARPS * MF_QUEUE * 4 + (size_t)S / 8 + 64;
+}
+
+/* arr[idx] += v on a 4-byte aligned u16 array (no carry into the neighbour: counts stay < 65536); returns the old value */
+__device__ __forceinline__ unsigned atomic_add_u16(unsigned short* arr, int idx, unsigned v) {
+  unsigned old = atomicAdd(reinterpret_cast<unsigned*>(arr) + (idx >> 1), (idx & 1) ? (v << 16) : v);
+  return (idx & 1) ? (old >> 16) : (old & 0xffffu);
+}
+
+/* in-place exclusive prefix sum of n u16 entries by one warp (lane-contiguous blocks) */
+__device__ __forceinline__ void warp_exclusive_scan_u16(unsigned short* arr, int n, int lane) {
+  const int per = (n + 31) >> 5;
+  const int lo = min(lane * per, n), hi = min(lo + per, n);
+  unsigned sum = 0;
+  for (int i = lo; i < hi; ++i) sum += arr[i];
+  unsigned inc = sum;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    unsigned t = __shfl_up_sync(FULL_MASK, inc, off);
+    if (lane >= off) inc += t;
+  }
+  unsigned run = inc - sum;
+  __syncwarp();
+  for (int i = lo; i < hi; ++i) {
+    unsigned v = arr[i];
+    arr[i] = (unsigned short)run;
+    run += v;
+  }
+  __syncwarp();
+}
+
+/* Block-wide stable LSD radix pass (8-bit digit) over the index list in -> out, keys in shared memory.
+ * Warp w owns a contiguous slice of the input; per-warp digit histograms make the scatter stable.
+ * TIE: the key is bitrev8(idx mod 256) (oracle: merge_tie_key).  Ends with a block barrier. */
+template <bool TIE>
+__device__ __forceinline__ void block_radix_pass(const unsigned* keys, const unsigned short* in, unsigned short* out, int n,
+                                                 unsigned short* hist /* [MF_WARPS][256] */, int shift) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  unsigned* h32 = reinterpret_cast<unsigned*>(hist);
+  for (int i = tid; i < MF_WARPS * 128; i += MF_THREADS) h32[i] = 0;
+  __syncthreads();
+  const int per = (((n + MF_WARPS - 1) / MF_WARPS) + 31) & ~31;
+  const int lo = min(warp * per, n), hi = min(lo + per, n);
+  unsigned short* hw = hist + warp * 256;
+  for (int i = lo + lane; i < hi; i += 32) {
+    const unsigned idx = in[i];
+    const unsigned d = TIE ? (__brev(idx) >> 24) : ((keys[idx] >> shift) & 255u);
+    atomic_add_u16(hw, (int)d, 1u);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    unsigned tot[8], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      unsigned t = 0;
+#pragma unroll
+      for (int w = 0; w < MF_WARPS; ++w) t += hist[w * 256 + lane * 8 + k];
+      tot[k] = t;
+      sum += t;
+    }
+    unsigned inc = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      unsigned t = __shfl_up_sync(FULL_MASK, inc, off);
+      if (lane >= off) inc += t;
+    }
+    unsigned run = inc - sum;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      unsigned o = run;
+#pragma unroll
+      for (int w = 0; w < MF_WARPS; ++w) {
+        const unsigned cw = hist[w * 256 + lane * 8 + k];
+        hist[w * 256 + lane * 8 + k] = (unsigned short)o;
+        o += cw;
+      }
+      run += tot[k];
+    }
+  }
+  __syncthreads();
+  for (int b0 = lo; b0 < hi; b0 += 32) {
+    const int i = b0 + lane;
+    unsigned idx = 0, d = 0x80000000u | (unsigned)lane;   /* inactive lanes: unique keys */
+    if (i < hi) {
+      idx = in[i];
+      d = TIE ? (__brev(idx) >> 24) : ((keys[idx] >> shift) & 255u);
+    }
+    const unsigned same = __match_any_sync(FULL_MASK, d);
+    const unsigned before = (i < hi) ? hw[d] : 0u;
+    __syncwarp();
+    if (i < hi) {
+      out[before + __popc(same & lt_mask)] = (unsigned short)idx;
+      if ((same & lt_mask) == 0) hw[d] = (unsigned short)(before + __popc(same));
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ float s_red[MF_WARPS][5];
+  __shared__ int s_cnt2[MF_WARPS];
+  __shared__ int s_flag;                 /* a near list overflowed: the particle goes to merge_kernel */
+  __shared__ int s_kzero;                /* first cluster with zero weight (:2821-2822) */
+  __shared__ int s_nseeds, s_klimit, s_n, s_pool_n, s_stopr, s_und;
+  const DevCfg& c = a.c;
+  const int S = a.Scap;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pl = a.p0 + blockIdx.x;
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  float4* Gc = reinterpret_cast<float4*>(smem_raw);                    /* [S] gate records {mx, my, lambda_max, rank} in CELL order */
+  unsigned short* P1 = reinterpret_cast<unsigned short*>(Gc + S + MF_ACH);   /* [S] source slot per candidate; later rank per candidate
+                                                                                (the gate records are padded: the A side is read MF_ACH at a time) */
+  unsigned short* Abuf = P1 + S;
+  unsigned short* Bbuf = Abuf + S;
+  unsigned short* own = Bbuf + S;                                      /* [S] grid cell, then rank of the owning seed, then output slot */
+  unsigned* HD = reinterpret_cast<unsigned*>(own + S);                 /* [S] near list of a candidate (by rank): head node, MF_NONE = empty */
+  unsigned* pool = HD + S;                                             /* [MF_POOL * S] list nodes: lower rank | next node << 16 */
+  unsigned short* hist = reinterpret_cast<unsigned short*>(pool + MF_POOL * S);   /* [MF_WARPS][256]; the grid's cell ends alias it */
+  unsigned* queue = reinterpret_cast<unsigned*>(hist + MF_WARPS * 256);/* [MF_WARPS][MF_QUEUE] */
+  unsigned* selfbits = queue + MF_WARPS * MF_QUEUE;                    /* [S / 32] candidate (by rank) is within its own threshold */
+  unsigned* K = reinterpret_cast<unsigned*>(Gc);                       /* sort keys (before the gate records are built) */
+  unsigned* Wtmp = HD;                                                 /* weight keys by emission slot (before the lists exist) */
+  unsigned short* cend = hist;
+
+  const int Cmax = c.Cmax;
+  const int cnt = a.count_in[pl];
+  const float* mp = a.map_in + (size_t)pl * PHD_MAP_PLANES * Cmax;
+  const uint8_t* cl = a.cls + (size_t)pl * Cmax;
+  float* mo = a.map_out + (size_t)pl * PHD_MAP_PLANES * Cmax;
+  const float4* cin = a.cand_in + (size_t)(pl - a.p0) * a.Smax * 2;
+  float4* crec = a.cand + (size_t)(pl - a.p0) * a.Smax * 2;            /* full records in rank order */
+
+  /* ---- A. does the particle fit? ---- */
+  const int n1 = a.n_cand[pl];
+  {
+    int c2 = 0;
+    for (int b0 = warp * 32; b0 < cnt; b0 += MF_THREADS) {
+      const int i = b0 + lane;
+      c2 += __popc(__ballot_sync(FULL_MASK, (i < cnt) && (cl[i] == 2)));
+    }
+    if (lane == 0) s_cnt2[warp] = c2;
+    if (tid == 0) {
+      s_flag = 0;
+      s_kzero = 0x7fffffff;
+      s_pool_n = 0;
+    }
+  }
+  __syncthreads();
+  int n2 = 0;
+#pragma unroll
+  for (int w = 0; w < MF_WARPS; ++w) n2 += s_cnt2[w];
+  if (tid == 0) atomicMax(&a.red->max_cand, min(n1, a.Smax) + n2);
+  if (n1 > a.Smax || n1 + n2 > S) {
+    if (tid == 0) a.ovf_list[atomicAdd(&a.red->ovf_n, 1)] = pl;
+    return;
+  }
+
+  /* ---- B. survivors of the prune back into term order (pruneMap :3120-3174); weight keys on the way ---- */
+  for (int i = tid; i < n1; i += MF_THREADS) {
+    const float4 r1 = cin[2 * i + 1];
+    K[i] = __float_as_uint(r1.w);
+    Wtmp[i] = ~float_to_ordered_uint(r1.z);
+    Abuf[i] = (unsigned short)i;
+  }
+  __syncthreads();
+  unsigned short* src = Abuf;
+  unsigned short* dst = Bbuf;
+  {
+    const int T = a.M + cnt * (a.M + 1);
+    const int bits = 32 - __clz(max(T, 1));
+    for (int shift = 0; shift < bits; shift += 8) {
+      block_radix_pass<false>(K, src, dst, n1, hist, shift);
+      unsigned short* t = src; src = dst; dst = t;
+    }
+  }
+  for (int i = tid; i < n1; i += MF_THREADS) P1[i] = src[i];
+  __syncthreads();
+  for (int i = tid; i < n1; i += MF_THREADS) K[i] = Wtmp[P1[i]];
+  /* nearly-in-range components in map order (:3243-3252) */
+  if (warp == 0) {
+    int n = n1;
+    for (int b0 = 0; b0 < cnt; b0 += 32) {
+      const int i = b0 + lane;
+      const bool k2 = (i < cnt) && (cl[i] == 2);
+      const unsigned bal = __ballot_sync(FULL_MASK, k2);
+      if (k2) {
+        const int pos = n + __popc(bal & lt_mask);
+        P1[pos] = (unsigned short)i;
+        K[pos] = ~float_to_ordered_uint(mp[i]);
+      }
+      n += __popc(bal);
+    }
+    if (lane == 0) s_n = n;
+  }
+  __syncthreads();
+  const int n = s_n;
+
+  int nout = 0;
+  if (n > 0) {
+    /* ---- C. rank by (weight desc, reference tie rule), see merge_kernel step B ---- */
+    for (int i = tid; i < n; i += MF_THREADS) Abuf[i] = (unsigned short)i;
+    __syncthreads();
+    src = Abuf; dst = Bbuf;
+    block_radix_pass<true>(K, src, dst, n, hist, 0);
+    { unsigned short* t = src; src = dst; dst = t; }
+    for (int shift = 0; shift < 32; shift += 8) {
+      block_radix_pass<false>(K, src, dst, n, hist, shift);
+      unsigned short* t = src; src = dst; dst = t;
+    }
+    unsigned short* ord = src;       /* rank -> candidate index; later the cluster ends */
+    unsigned short* items = dst;     /* output slot of a seed */
+
+    /* ---- D. candidate records in rank order to the scratch buffer (stays in L1/L2) ---- */
+    float tmax = 0.0f, xmin = FLT_MAX, xmax = -FLT_MAX, ymin = FLT_MAX, ymax = -FLT_MAX;
+    for (int r = tid; r < n; r += MF_THREADS) {
+      const int i = ord[r];
+      const int s = P1[i];
+      float4 r0, r1;
+      if (i < n1) {
+        r0 = cin[2 * s];
+        r1 = cin[2 * s + 1];
+      } else {
+        const float pxy = mp[4 * Cmax + s];
+        r0 = make_float4(mp[3 * Cmax + s], pxy, pxy, mp[5 * Cmax + s]);
+        r1 = make_float4(mp[1 * Cmax + s], mp[2 * Cmax + s], mp[s], 0.0f);
+      }
+      r1.w = dev_lambda_max(r0);
+      crec[2 * r] = r0;
+      crec[2 * r + 1] = r1;
+      P1[i] = (unsigned short)r;     /* candidate index -> rank */
+      own[r] = (unsigned short)MF_NONE;
+      HD[r] = MF_NONE;
+      tmax = fmaxf(tmax, r1.w);
+      xmin = fminf(xmin, r1.x); xmax = fmaxf(xmax, r1.x);
+      ymin = fminf(ymin, r1.y); ymax = fmaxf(ymax, r1.y);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      tmax = fmaxf(tmax, __shfl_xor_sync(FULL_MASK, tmax, off));
+      xmin = fminf(xmin, __shfl_xor_sync(FULL_MASK, xmin, off));
+      xmax = fmaxf(xmax, __shfl_xor_sync(FULL_MASK, xmax, off));
+      ymin = fminf(ymin, __shfl_xor_sync(FULL_MASK, ymin, off));
+      ymax = fmaxf(ymax, __shfl_xor_sync(FULL_MASK, ymax, off));
+    }
+    if (lane == 0) {
+      s_red[warp][0] = tmax; s_red[warp][1] = xmin; s_red[warp][2] = xmax; s_red[warp][3] = ymin; s_red[warp][4] = ymax;
+    }
+    for (int i = tid; i < MF_CELLS / 2; i += MF_THREADS) reinterpret_cast<unsigned*>(cend)[i] = 0;
+    for (int i = tid; i < (S >> 5); i += MF_THREADS) selfbits[i] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < MF_WARPS; ++w) {
+      tmax = fmaxf(tmax, s_red[w][0]);
+      xmin = fminf(xmin, s_red[w][1]); xmax = fmaxf(xmax, s_red[w][2]);
+      ymin = fminf(ymin, s_red[w][3]); ymax = fmaxf(ymax, s_red[w][4]);
+    }
+
+    /* ---- E. uniform grid over the candidate means, cell size >= the largest gate radius; gate records in cell order.
+     * Is every candidate within the threshold of itself (it is, unless its covariance is degenerate)? ---- */
+    const float gk = 0.625f * c.min_sep;                   /* pair gate: |d|^2 <= gk * (lam_a + lam_b) */
+    int G = 1;
+    float cs = 1.0f;
+    {
+      const float ext = fmaxf(xmax - xmin, ymax - ymin);
+      const float rg = sqrtf(gk * (tmax + tmax)) * 1.0001f;
+      if (rg >= 0.0f && rg < ext && ext < FLT_MAX) {
+        int g = (int)(ext / rg) + 1;
+        if (g > MRG_GMAX) g = MRG_GMAX;
+        G = g;
+        cs = fmaxf(rg, (ext / (float)g) * 1.0001f);
+      }
+    }
+    unsigned short* cellr = reinterpret_cast<unsigned short*>(pool);   /* cell of every candidate (the pool is free until the pair phase) */
+    for (int r = tid; r < n; r += MF_THREADS) {
+      const float4 A0 = crec[2 * r], g = crec[2 * r + 1];
+      int cx = 0, cy = 0;
+      if (G > 1) {
+        cx = (int)((g.x - xmin) / cs);
+        cy = (int)((g.y - ymin) / cs);
+        cx = min(max(cx, 0), G - 1);
+        cy = min(max(cy, 0), G - 1);
+      }
+      const int cid = cy * MRG_GMAX + cx;
+      cellr[r] = (unsigned short)cid;
+      atomic_add_u16(cend, cid, 1u);
+      if (0.0f <= gk * (g.w + g.w) &&
+          dev_mahal(A0.x, A0.y, A0.z, A0.w, g.x, g.y, A0.x, A0.y, A0.z, A0.w, g.x, g.y) < c.min_sep)
+        atomicOr(&selfbits[r >> 5], 1u << (r & 31));
+    }
+    __syncthreads();
+    if (warp == 0) warp_exclusive_scan_u16(cend, MRG_NCELL, lane);        /* cell starts */
+    __syncthreads();
+    for (int r = tid; r < n; r += MF_THREADS) {
+      const float4 g = crec[2 * r + 1];
+      Gc[atomic_add_u16(cend, (int)cellr[r], 1u)] = make_float4(g.x, g.y, g.w, (float)r);
+    }
+    __syncthreads();                                       /* cend[c] is now the END of cell c */
+
+    /* ---- F. near pairs (:2802-2806).  Row by row (rows dealt to the warps), two cells at a time: every unordered pair
+     * of candidates in neighbouring cells is gated once.  The lanes hold the B side (the two cells, the cell to their
+     * right and the four cells below); the candidates of the two cells (the A side) are broadcast against them,
+     * MF_ACH at a time; B is paired with A only if it comes later in cell order.  Pairs that pass the gate are queued
+     * and the Mahalanobis distance is evaluated 32 queued pairs at a time. ---- */
+    {
+      unsigned* q = queue + warp * MF_QUEUE;   /* ring of pairs of cell-order positions */
+      const int pool_cap = MF_POOL * S;
+      int qh = 0, qn = 0;
+      /* seed = the lower-ranked candidate, the argument order of the reference.  A near pair becomes a node of the
+       * higher-ranked candidate's list. */
+      auto evaluate = [&](int cntq) {
+        bool near = false;
+        unsigned ar = 0, br = 0;
+        if (lane < cntq) {
+          const unsigned e = q[(qh + lane) & (MF_QUEUE - 1)];
+          float4 A1 = Gc[e & 0xffffu], B1 = Gc[e >> 16];
+          if (A1.w < B1.w) {           /* A = the higher rank (the candidate), B = the lower rank (the seed) */
+            const float4 t = A1; A1 = B1; B1 = t;
+          }
+          ar = (unsigned)A1.w;
+          br = (unsigned)B1.w;
+          const float4 A0 = crec[2 * ar], B0 = crec[2 * br];
+          near = dev_mahal(B0.x, B0.y, B0.z, B0.w, B1.x, B1.y, A0.x, A0.y, A0.z, A0.w, A1.x, A1.y) < c.min_sep;
+        }
+        const unsigned nb = __ballot_sync(FULL_MASK, near);
+        if (nb) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&s_pool_n, __popc(nb));
+          base = __shfl_sync(FULL_MASK, base, 0);
+          if (near) {
+            const int k = base + __popc(nb & lt_mask);
+            if (k < pool_cap) pool[k] = br | (atomicExch(&HD[ar], (unsigned)k) << 16);
+            else s_flag = 1;
+          }
+        }
+      };
+      const int Ge = (G + 1) & ~1;                                     /* pairs of cells are dealt to the warps round-robin */
+      int cy = 0, cx = 2 * warp;
+      while (true) {
+        while (cx >= Ge) {
+          cx -= Ge;
+          ++cy;
+        }
+        if (cy >= G) break;
+        const unsigned short* row = cend + cy * MRG_GMAX;
+        const int cxa = min(cx + 1, G - 1);                          /* last A cell */
+        const int a_beg = (cy + cx > 0) ? row[cx - 1] : 0;
+        const int na = (int)row[cxa] - a_beg;
+        if (na > 0) {
+          const int len1 = (int)row[min(cxa + 1, G - 1)] - a_beg;      /* the A cells (first) + the cell to their right */
+          int beg2 = 0, len2 = 0;
+          if (cy + 1 < G) {
+            beg2 = row[MRG_GMAX + max(cx - 1, 0) - 1];
+            len2 = (int)row[MRG_GMAX + min(cxa + 1, G - 1)] - beg2;
+          }
+          const int tot = len1 + len2;
+          for (int q0 = 0; q0 < tot; q0 += 32) {
+            const int qq = q0 + lane;
+            const bool valid = qq < tot;
+            const int posb = (qq < len1) ? a_beg + qq : beg2 + (qq - len1);
+            const float4 B1 = Gc[valid ? posb : a_beg];
+            /* A candidates at cell-order offsets < min(na, qq) can pair with this B */
+            const int alim = valid ? min(na, qq) : 0;
+            for (int a0 = 0; a0 < na; a0 += MF_ACH) {
+              if (!__any_sync(FULL_MASK, a0 < alim)) break;             /* the rest of the A side precedes no B of this chunk */
+              const float4* Ap = Gc + a_beg + a0;
+              const int arem = alim - a0;
+              unsigned mask = 0u;
+#pragma unroll
+              for (int k = 0; k < MF_ACH; ++k) {
+                const float4 A1 = Ap[k];                                /* broadcast (reads past the A side are masked) */
+                const float gx = B1.x - A1.x, gy = B1.y - A1.y;
+                if ((k < arem) && (gx * gx + gy * gy <= gk * (B1.z + A1.z))) mask |= 1u << k;
+              }
+              /* compaction: every lane appends its pairs to the ring */
+              const int cntl = __popc(mask);
+              int inc = cntl;
+#pragma unroll
+              for (int off = 1; off < 32; off <<= 1) {
+                const int t = __shfl_up_sync(FULL_MASK, inc, off);
+                if (lane >= off) inc += t;
+              }
+              const int total = __shfl_sync(FULL_MASK, inc, 31);
+              if (qn + total > MF_QUEUE) {
+                s_flag = 1;
+              } else if (total) {
+                int slot = qh + qn + inc - cntl;
+                const unsigned pb = (unsigned)posb << 16;
+                for (unsigned m = mask; m; m &= m - 1) {
+                  q[slot & (MF_QUEUE - 1)] = (unsigned)(a_beg + a0 + (__ffs(m) - 1)) | pb;
+                  ++slot;
+                }
+                qn += total;
+                __syncwarp();
+                while (qn >= 32) {
+                  evaluate(32);
+                  qh = (qh + 32) & (MF_QUEUE - 1);
+                  qn -= 32;
+                }
+                __syncwarp();
+              }
+            }
+          }
+        }
+        cx += 2 * MF_WARPS;
+      }
+      __syncwarp();
+      evaluate(qn);
+    }
+    if (tid == 0) s_und = 0;
+    __syncthreads();
+
+    /* ---- G. ownership from the near lists: candidate r is owned by the lowest-ranked SEED among its lower-ranked near
+     * neighbours, and is a seed itself if there is none.  A candidate can decide once no undecided neighbour ranks
+     * below its lowest-ranked seed neighbour; block-wide sweeps until every candidate has decided (the lowest-ranked
+     * undecided candidate always can). ---- */
+    if (!s_flag) {
+      for (int sweep = 0;; ++sweep) {
+        bool pending = false;
+        for (int r = tid; r < n; r += MF_THREADS) {
+          if (own[r] != MF_NONE) continue;
+          unsigned minseed = MF_NONE, minund = MF_NONE;
+          for (unsigned node = HD[r]; node != MF_NONE;) {
+            const unsigned nd = pool[node];
+            const unsigned e = nd & 0xffffu;
+            node = nd >> 16;
+            const unsigned st = reinterpret_cast<volatile unsigned short*>(own)[e];
+            if (st == MF_NONE) minund = min(minund, e);
+            else if (st == e) minseed = min(minseed, e);
+          }
+          if (minund == MF_NONE || minseed < minund) own[r] = (unsigned short)((minseed != MF_NONE) ? minseed : (unsigned)r);
+          else pending = true;
+        }
+        if (pending) s_und = sweep + 1;
+        __syncthreads();
+        const bool again = (s_und == sweep + 1);
+        __syncthreads();
+        if (!again) break;
+      }
+      /* output slots of the seeds, in rank order (= descending seed weight) */
+      if (warp == 0) {
+        unsigned stopr = MF_NONE;    /* first seed that is not within the threshold of itself */
+        int nseeds = 0;
+        for (int rb = 0; rb < n; rb += 32) {
+          const int r = rb + lane;
+          const bool isseed = (r < n) && (own[r] == r);
+          const unsigned bal = __ballot_sync(FULL_MASK, isseed);
+          if (isseed) items[r] = (unsigned short)(nseeds + __popc(bal & lt_mask));
+          const unsigned sb = bal & ~selfbits[rb >> 5];
+          if (sb && stopr == MF_NONE) stopr = (unsigned)(rb + __ffs(sb) - 1);
+          nseeds += __popc(bal);
+        }
+        __syncwarp();
+        if (lane == 0) {
+          s_nseeds = nseeds;
+          s_stopr = (int)stopr;
+          /* a seed outside its own threshold ends the reduction after its cluster (the oracle picks it again, finds
+           * nothing and stops, :2821-2822); it is not a member of its own cluster */
+          s_klimit = (stopr != MF_NONE) ? (int)items[stopr] + 1 : nseeds;
+        }
+      }
+    }
+    __syncthreads();
+    if (s_flag) {
+      if (tid == 0) a.ovf_list[atomicAdd(&a.red->ovf_n, 1)] = pl;
+      return;
+    }
+    const int nseeds = s_nseeds, klimit = s_klimit;
+    unsigned short* slotA = items;
+    unsigned short* csz = ord;       /* cluster sizes -> starts -> ends (the rank -> index table is no longer needed) */
+    unsigned short* memb = reinterpret_cast<unsigned short*>(pool);   /* member lists (the near lists are no longer needed) */
+    unsigned short* keyA = reinterpret_cast<unsigned short*>(HD);     /* output slot of every candidate's cluster */
+    const unsigned stopr = (unsigned)s_stopr;
+    for (int k = tid; k < ((nseeds + 2) >> 1); k += MF_THREADS) reinterpret_cast<unsigned*>(csz)[k] = 0;
+    __syncthreads();
+    for (int r = tid; r < n; r += MF_THREADS) {
+      unsigned key = slotA[own[r]];
+      if ((unsigned)r == stopr) key = MF_NONE;
+      keyA[r] = (unsigned short)key;
+      if (key != MF_NONE) atomic_add_u16(csz, (int)key, 1u);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      warp_exclusive_scan_u16(csz, nseeds, lane);
+      /* members of every cluster in ascending candidate index: stable scatter over the candidate order */
+      for (int ib = 0; ib < n; ib += 32) {
+        const int i = ib + lane;
+        unsigned r = 0, key = MF_NONE;
+        if (i < n) {
+          r = P1[i];
+          key = keyA[r];
+        }
+        const unsigned mk = (key != MF_NONE) ? key : (0x80000000u | (unsigned)lane);
+        const unsigned same = __match_any_sync(FULL_MASK, mk);
+        const unsigned before = (key != MF_NONE) ? csz[key] : 0u;
+        __syncwarp();
+        if (key != MF_NONE) {
+          memb[before + __popc(same & lt_mask)] = (unsigned short)r;
+          if ((same & lt_mask) == 0) csz[key] = (unsigned short)(before + __popc(same));
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+
+    /* ---- H. moment-matched merge, one thread per cluster (:2808-2881) ---- */
+    for (int k = tid; k < klimit; k += MF_THREADS) {
+      const int beg = (k > 0) ? csz[k - 1] : 0, end = csz[k];
+      float wsum = 0.0f, m0 = 0.0f, m1 = 0.0f;
+      for (int j = beg; j < end; ++j) {
+        const float4 B1 = crec[2 * memb[j] + 1];
+        wsum = wsum + B1.z;
+        m0 = m0 + B1.z * B1.x;
+        m1 = m1 + B1.z * B1.y;
+      }
+      if (wsum == 0.0f) {                                 /* :2821-2822: the reference stops here */
+        atomicMin(&s_kzero, k);
+      } else if (k < Cmax) {
+        const float rw = 1.0f / wsum;
+        const float mm0 = m0 * rw, mm1 = m1 * rw;
+        float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
+        for (int j = beg; j < end; ++j) {
+          const int rr = memb[j];
+          const float4 B0 = crec[2 * rr], B1 = crec[2 * rr + 1];
+          const float d0 = mm0 - B1.x, d1 = mm1 - B1.y;
+          v0 = v0 + B1.z * (B0.x + d0 * d0);
+          v1 = v1 + B1.z * (B0.y + d0 * d1);
+          v2 = v2 + B1.z * (B0.z + d1 * d0);
+          v3 = v3 + B1.z * (B0.w + d1 * d1);
+        }
+        v0 = v0 * rw; v1 = v1 * rw; v2 = v2 * rw; v3 = v3 * rw;
+        v1 = (v1 + v2) / 2.0f;                             /* force_symmetric_covariance */
+        mo[0 * Cmax + k] = wsum;
+        mo[1 * Cmax + k] = mm0;
+        mo[2 * Cmax + k] = mm1;
+        mo[3 * Cmax + k] = v0;
+        mo[4 * Cmax + k] = v1;
+        mo[5 * Cmax + k] = v3;
+      }
+    }
+    __syncthreads();
+    nout = min(klimit, s_kzero);
+    if (nout > Cmax && tid == 0) atomicOr(&a.red->err_flag, 2);
+  }
+
+  /* ---- I. re-append the far (class 0) components (:3311-3318) and publish the map size ---- */
+  if (warp == 0) {
+    int pos0 = nout;
+    for (int b0 = 0; b0 < cnt; b0 += 32) {
+      const int i = b0 + lane;
+      const bool k0 = (i < cnt) && (cl[i] == 0);
+      const unsigned bal = __ballot_sync(FULL_MASK, k0);
+      if (k0) {
+        const int pos = pos0 + __popc(bal & lt_mask);
+        if (pos < Cmax) {
+#pragma unroll
+          for (int f = 0; f < PHD_MAP_PLANES; ++f) mo[f * Cmax + pos] = mp[f * Cmax + i];
+        }
+      }
+      pos0 += __popc(bal);
+    }
+    if (lane == 0) {
+      if (pos0 > Cmax) {
+        atomicOr(&a.red->err_flag, 2);
+        pos0 = Cmax;
+      }
+      a.count_out[pl] = pos0;
+    }
   }
 }
 

@@ -168,7 +168,7 @@ static void free_state(phdslam* h) {
   cudaFree(h->snap_pose); cudaFree(h->snap_count); cudaFree(h->snap_map); cudaFree(h->snap_card); cudaFree(h->snap_logw);
   cudaFree(h->cls); cudaFree(h->n_in); cudaFree(h->dlogw); cudaFree(h->tpad); cudaFree(h->toff); cudaFree(h->scan_tmp);
   cudaFree(h->dense); cudaFree(h->z_dev); cudaFree(h->draws_dev); cudaFree(h->q_fx); cudaFree(h->cdf_excl);
-  cudaFree(h->ancestors); cudaFree(h->red); cudaFree(h->cand); cudaFree(h->cand_in); cudaFree(h->n_cand);
+  cudaFree(h->ancestors); cudaFree(h->red); cudaFree(h->cand); cudaFree(h->cand_in); cudaFree(h->n_cand); cudaFree(h->ovf_list);
   cudaFree(h->mig_map); cudaFree(h->mig_pose); cudaFree(h->mig_count); cudaFree(h->mig_anc); cudaFree(h->mig_card);
   cudaFree(h->mig_pose_in); cudaFree(h->totals_dev); cudaFree(h->lfact);
   h->mig_pose_in = nullptr; h->totals_dev = nullptr; h->lfact = nullptr;
@@ -190,6 +190,7 @@ static int alloc_state(phdslam* h) {
   CK(cudaMalloc(&h->n_in, n * sizeof(int)));
   CK(cudaMalloc(&h->dlogw, n * sizeof(float)));
   CK(cudaMalloc(&h->n_cand, n * sizeof(int)));
+  CK(cudaMalloc(&h->ovf_list, n * sizeof(int)));
   CK(cudaMalloc(&h->tpad, n * sizeof(unsigned long long)));
   CK(cudaMalloc(&h->toff, (n + 1) * sizeof(unsigned long long)));
   CK(cudaMalloc(&h->scan_tmp, (size_t)(cdiv(n, SCAN_TILE) + 1) * sizeof(unsigned long long)));
@@ -268,6 +269,21 @@ extern "C" int phdslam_create(const phdslam_config_t* cfg, int device, phdslam_t
     CK(cudaFuncSetAttribute(update_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   }
   CK(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem_bytes(h->Smax)));
+  {
+    /* merge_fast_kernel keeps a particle's candidates in shared memory: capacity Scap (multiple of 32), adapted after
+     * every update to the largest candidate count seen (+12.5 %); particles above it take merge_kernel.
+     * PHDSLAM_MERGE_CAP pins the capacity (0 = always merge_kernel): a test / profiling knob. */
+    h->Scap_max = std::min(h->Smax, 4096);
+    while (merge_fast_smem_bytes(h->Scap_max) > 200 * 1024) h->Scap_max -= 32;
+    h->Scap = std::min(h->Scap_max, std::max(256, (h->Cmax + h->Cmax / 4 + 31) & ~31));
+    h->Scap_pinned = 0;
+    if (const char* e = getenv("PHDSLAM_MERGE_CAP")) {
+      int v = atoi(e);
+      h->Scap = (v <= 0) ? 0 : std::min(h->Scap_max, std::max(32, (v + 31) & ~31));
+      h->Scap_pinned = 1;
+    }
+    CK(cudaFuncSetAttribute(merge_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_fast_smem_bytes(h->Scap_max)));
+  }
   rc = init_particles(h);
   if (rc) { free_state(h); delete h; return rc; }
   *out = h;
@@ -512,6 +528,16 @@ static int launch_merge_batch(phdslam* h, int M, int p0, int p1) {
   a.map_in = h->map[h->cur]; a.count_in = h->count[h->cur]; a.cls = h->cls;
   a.map_out = h->map[h->cur ^ 1]; a.count_out = h->count[h->cur ^ 1];
   a.red = h->red; a.Smax = h->Smax; a.c = h->dc; a.p1 = p1; a.cand = h->cand;
+  a.Scap = h->Scap; a.ovf_list = h->ovf_list; a.use_list = 0;
+  if (h->Scap > 0 && h->dc.distance_metric == 0) {
+    merge_fast_kernel<<<p1 - p0, MF_THREADS, merge_fast_smem_bytes(h->Scap), h->stream>>>(a);
+    LAUNCH_CHECK(h);
+    a.use_list = 1;   /* whatever did not fit the shared-memory capacity (normally nothing: the warps exit at once) */
+    merge_kernel<<<cdiv(p1 - p0, MRG_WARPS), MRG_THREADS, merge_smem_bytes(h->Smax), h->stream>>>(a);
+    LAUNCH_CHECK(h);
+    CK(cudaMemsetAsync(&h->red->ovf_n, 0, sizeof(int), h->stream));
+    return 0;
+  }
   merge_kernel<<<cdiv(p1 - p0, MRG_WARPS), MRG_THREADS, merge_smem_bytes(h->Smax), h->stream>>>(a);
   LAUNCH_CHECK(h);
   return 0;
@@ -600,6 +626,10 @@ extern "C" int phdslam_update(phdslam_t* h, const float* z, int M, int fields) {
   h->tim.update_ms = upd_ms;
   h->tim.merge_ms = mrg_ms;
   cudaEventElapsedTime(&h->tim.weights_ms, h->ev[5], h->ev[6]);
+  if (!h->Scap_pinned) {
+    const int mc = h->red_host->max_cand;
+    h->Scap = std::min(h->Scap_max, std::max(64, (mc + mc / 16 + 8 + 31) & ~31));
+  }
   rc = check_err_flag(h);
   if (rc) return rc;
   return 0;

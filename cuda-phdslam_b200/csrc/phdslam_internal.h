@@ -45,6 +45,8 @@ struct Reductions {       /* device-resident cross-particle accumulators (all or
   int err_flag;                   /* capacity / overflow flags raised by kernels */
   int max_terms;                  /* max over particles of padded dense term count */
   unsigned long long total_terms; /* sum over particles of padded dense term count */
+  int max_cand;                   /* max over particles of the merge candidate count (sizes the next step's merge) */
+  int ovf_n;                      /* particles queued for the general merge kernel */
 };
 
 struct phdslam {
@@ -55,6 +57,9 @@ struct phdslam {
   int rank, world;
   int n_global, n_local, offset;
   int Cmax, n_card, Smax;
+  int Scap_max, Scap_pinned;
+  int Scap;              /* shared-memory candidate capacity of merge_fast_kernel, adapted from the last step */
+  int* ovf_list;         /* [n_local] */
   /* persistent state, double buffered (front = cur) */
   int cur;
   float* pose[2];        /* [6][n_local] SoA */

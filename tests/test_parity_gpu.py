@@ -312,3 +312,78 @@ def test_cli_logs_match_oracle(tmp_path):
         got = open(out / ("state_estimate%05d.log" % k)).read()
         assert got == open(ref).read(), "log of step %d differs" % k
         assert len(got.split("\n")) == 6
+
+
+# ---- prune + merge: the shared-memory kernel (merge_fast_kernel), its overflow queue and merge_kernel agree ----
+def _with_cap(monkeypatch, cap):
+    if cap is None:
+        monkeypatch.delenv("PHDSLAM_MERGE_CAP", raising=False)
+    else:
+        monkeypatch.setenv("PHDSLAM_MERGE_CAP", cap)
+
+
+@pytest.mark.parametrize("cap", [None, "0", "96", "160"])
+def test_merge_kernels_match_oracle(monkeypatch, cap):
+    """cap None: adaptive capacity (every particle in merge_fast_kernel); "0": merge_kernel only; "96"/"160": the
+    particles above the capacity go through the overflow queue, the others stay in shared memory"""
+    _with_cap(monkeypatch, cap)
+    Pn, C, M = 40, 60, 20
+    cfg = S.scene_config(Pn, C, M, max_components=256)
+    sc = S.make_scene(Pn, C, M, seed=21, n_near=5, n_far=6)
+    # uneven maps so that a fixed capacity splits the particles between the two kernels
+    sizes = sc["sizes"].copy()
+    maps = sc["maps"].reshape(Pn, -1).copy()
+    for p in range(Pn):
+        sizes[p] = maps.shape[1] - (p % 5) * 9
+    g, o = P.PhdSlam(cfg), O.Oracle(cfg)
+    for f in (g, o):
+        f.poses = sc["poses"]
+        f.log_weights = sc["log_weights"]
+        f.set_maps(sizes, np.concatenate([maps[p, :sizes[p]] for p in range(Pn)]))
+    for k in range(3):
+        Z = S.make_scene(Pn, C, M, seed=21 + k)["Z"]
+        g.phdUpdateSynth(Z)
+        o.phdUpdateSynth(Z)
+        assert assert_state_equal(g, o, "cap=%s update %d" % (cap, k)), "state expected bit-identical"
+
+
+@pytest.mark.parametrize("cap", [None, "0"])
+def test_merge_dense_clusters_and_ties(monkeypatch, cap):
+    """many mutually overlapping components (long gate queues, one grid cell), exact weight ties, zero weights"""
+    _with_cap(monkeypatch, cap)
+    Pn, C, M = 12, 90, 12
+    cfg = S.scene_config(Pn, C, M, max_components=256, min_separation=25.0)
+    sc = S.make_scene(Pn, C, M, seed=5)
+    maps = sc["maps"].reshape(Pn, C).copy()
+    rng = np.random.Generator(np.random.Philox(77))
+    centres = rng.uniform(-8, 8, (6, 2)).astype(np.float32)
+    for p in range(Pn):
+        which = rng.integers(0, 6, C)
+        maps["mean"][p] = centres[which] + rng.normal(0, 0.15, (C, 2)).astype(np.float32)
+        maps["weight"][p, ::3] = 0.25            # exact ties
+        maps["weight"][p, 5] = 0.0
+    sc["maps"] = maps.reshape(-1)
+    g, o = pair(cfg, sc)
+    for k in range(2):
+        Z = S.make_scene(Pn, C, M, seed=40 + k)["Z"]
+        g.phdUpdateSynth(Z)
+        o.phdUpdateSynth(Z)
+        assert assert_state_equal(g, o, "dense clusters, update %d" % k), "state expected bit-identical"
+
+
+def test_merge_kernels_agree_at_scale(monkeypatch):
+    """4096 particles: merge_fast_kernel (adaptive capacity, two steps so that it adapts) vs merge_kernel, bit for bit"""
+    Pn, C, M = 4096, 96, 32
+    cfg = S.scene_config(Pn, C, M, max_components=256)
+    sc = S.make_scene(Pn, C, M, seed=9, n_near=4, n_far=3)
+    res = []
+    for cap in (None, "0"):
+        _with_cap(monkeypatch, cap)
+        g = P.PhdSlam(cfg)
+        S.load_scene(g, sc)
+        for k in range(2):
+            g.phdUpdateSynth(S.make_scene(Pn, C, M, seed=9 + k)["Z"])
+        sizes, maps = g.get_maps()
+        res.append((sizes.copy(), maps.tobytes(), g.log_weights.tobytes()))
+    assert (res[0][0] == res[1][0]).all()
+    assert res[0][1] == res[1][1] and res[0][2] == res[1][2]
