@@ -37,13 +37,17 @@ WORKLOADS = {
     # smaller shapes for quick checks
     "synthetic_8192x256x64_phd": dict(P=8192, C=256, M=64, max_components=384),
     "synthetic_1024x64x32_phd": dict(P=1024, C=64, M=32, max_components=128),
+    # BASELINE.json configs[3], one GPU's shard (1M particles over 8 GPUs): CPHD with the cardinality distribution
+    "synthetic_131072x128x50_cphd": dict(P=131072, C=128, M=50, max_components=256, filter_type=1, max_cardinality=255),
+    # BASELINE.json configs[4] per-GPU shape at a size one GPU's update buffer streams through: global resampling every step
+    "synthetic_262144x128x100_phd": dict(P=262144, C=128, M=100, max_components=256, resample_threshold=1.0),
 }
 DEFAULT_WORKLOAD = "synthetic_65536x256x64_phd"
 
 
-def alg_bytes_per_update(C, M):
-    """B_alg = [28*C + 28*(C*(M+1)+M) + 32] / (C*M)"""
-    return (28.0 * C + 28.0 * (C * (M + 1) + M) + 32.0) / (C * M)
+def alg_bytes_per_update(C, M, n_card=0):
+    """B_alg = [28*C + 28*(C*(M+1)+M) + 32 (+ 2*4*(N+1) cardinality in/out for CPHD)] / (C*M)"""
+    return (28.0 * C + 28.0 * (C * (M + 1) + M) + 32.0 + 8.0 * n_card) / (C * M)
 
 
 def measured_peaks():
@@ -120,7 +124,8 @@ def cpu_oracle_rate(wl, target_seconds=12.0, threads=None):
     Ps = max(threads, 8)
     rate = None
     for attempt in range(3):
-        cfg = S.scene_config(Ps, C, M, max_components=wl["max_components"])
+        extra = {k: v for k, v in wl.items() if k not in ("P", "C", "M", "max_components")}
+        cfg = S.scene_config(Ps, C, M, max_components=wl["max_components"], **extra)
         sc = S.make_scene(Ps, C, M, seed=0)
         o = O.Oracle(cfg, threads=threads)
         S.load_scene(o, sc)
@@ -148,7 +153,8 @@ def run_reference(args, wl):
     r0, _, _, _, _ = cpu_oracle_rate(wl, target_seconds=3.0, threads=threads)
     budget = 150.0 / max(args.steps + args.warmup, 1)
     Ps = int(max(threads, min(wl["P"], r0 * min(budget, 20.0) / (C * M))))
-    cfg = S.scene_config(Ps, C, M, max_components=wl["max_components"])
+    extra = {k: v for k, v in wl.items() if k not in ("P", "C", "M", "max_components")}
+    cfg = S.scene_config(Ps, C, M, max_components=wl["max_components"], **extra)
     sc = S.make_scene(Ps, C, M, seed=0)
     times = []
     for k in range(args.warmup + args.steps):
@@ -191,7 +197,8 @@ def run_ours(args, wl):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     P, C, M = wl["P"], wl["C"], wl["M"]
     P_total = P * world                      # weak scaling: P particles per GPU
-    cfg = S.scene_config(P_total, C, M, max_components=wl["max_components"], seed="0")
+    extra = {k: v for k, v in wl.items() if k not in ("P", "C", "M", "max_components")}
+    cfg = S.scene_config(P_total, C, M, max_components=wl["max_components"], seed="0", **extra)
     filt = PS.PhdSlam(cfg, device=local)
     if world > 1:
         filt.dist_init(rank, world)
@@ -246,6 +253,9 @@ def run_ours(args, wl):
         tt = torch.tensor([dev_total, wall_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dev_total, wall_total = float(tt[0]), float(tt[1])
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     updates_per_step = float(P_total) * C * M
@@ -254,7 +264,7 @@ def run_ours(args, wl):
     e2e_value = updates_per_step / (wall_total / args.steps * 1e-3)
     peak, peak_src = measured_peaks()
     upd = float(np.mean(upd_ms))
-    balg = alg_bytes_per_update(C, M)
+    balg = alg_bytes_per_update(C, M, wl.get("max_cardinality", -1) + 1 if wl.get("filter_type") == 1 else 0)
     achieved = (float(P) * C * M * balg) / (upd * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -270,7 +280,7 @@ def run_ours(args, wl):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "particles_per_gpu": P, "components": C, "measurements": M,
-                   "filter": "PHD", "update_mode": "dense (reference-equivalent update terms materialised in HBM)",
+                   "filter": "CPHD" if wl.get("filter_type") == 1 else "PHD", "update_mode": "dense (reference-equivalent update terms materialised in HBM)",
                    "cache": "inputs larger than L2 (map %.0f MB + dense update terms %.1f GB per step)"
                             % (P * C * 24 / 1e6, P * (C * (M + 1) + M) * 28 / 1e9),
                    "steps_that_resampled": n_resampled},
@@ -287,6 +297,7 @@ def run_ours(args, wl):
         "clocks": clocks,
     }
     print(json.dumps(line))
+    sys.stdout.flush()
 
 
 def main():

@@ -378,19 +378,36 @@ __device__ __forceinline__ float cphd_lse_warp(int n, F f) {
   return phd_safe_log(warp_butterfly_sum(a0 + a1)) + mx;
 }
 
-/* one root x folded into the warp's ESF array E[0..deg+1]: E[k] += x * E[k-1] (old values), lane-strided k */
-__device__ __forceinline__ void cphd_esf_step(double* E, int deg, double x, int lane) {
-  double nk[CPHD_KREG];
+/* Elementary symmetric functions of the roots x[0..M) without root `skip` (-1: none), one warp, coefficients in
+ * REGISTERS: lane L holds E[L + 32 r], r < kr = ceil((M + 1) / 32).  Folding one root is E[k] += x * E[k-1] on the old
+ * values; E[k-1] comes from the lane below by shuffle (from lane 31 of the row below for lane 0).  Same operations in
+ * the same order as the oracle's esf(): every coefficient is an independent chain of __dmul_rn / __dadd_rn, and the
+ * terms beyond the current degree are exact zeros.  Result to the warp's shared array Es[0..M]. */
+__device__ __forceinline__ void cphd_esf_warp(const double* __restrict__ x, int M, int skip, double* __restrict__ Es, int lane) {
+  double E[CPHD_KREG];
 #pragma unroll
-  for (int r = 0; r < CPHD_KREG; ++r) {
-    int k = lane + 1 + 32 * r;
-    nk[r] = (k <= deg + 1) ? __dadd_rn(E[k], __dmul_rn(x, E[k - 1])) : 0.0;
+  for (int r = 0; r < CPHD_KREG; ++r) E[r] = 0.0;
+  if (lane == 0) E[0] = 1.0;
+  const int kr = (M + 32) >> 5;
+  for (int n = 0; n < M; ++n) {
+    if (n == skip) continue;
+    const double xn = x[n];
+    double carry = 0.0;
+#pragma unroll
+    for (int r = 0; r < CPHD_KREG; ++r) {
+      if (r < kr) {
+        const double up = __shfl_up_sync(FULL_MASK, E[r], 1);
+        const double last = __shfl_sync(FULL_MASK, E[r], 31);
+        const double prev = (lane == 0) ? carry : up;
+        carry = last;
+        E[r] = __dadd_rn(E[r], __dmul_rn(xn, prev));
+      }
+    }
   }
-  __syncwarp();
 #pragma unroll
   for (int r = 0; r < CPHD_KREG; ++r) {
-    int k = lane + 1 + 32 * r;
-    if (k <= deg + 1) E[k] = nk[r];
+    const int k = lane + 32 * r;
+    if (k <= M) Es[k] = E[r];
   }
   __syncwarp();
 }
@@ -475,14 +492,7 @@ __device__ void cphd_block(const DevCfg& c, int C, int M, const float* __restric
   {
     double* E = s_e + (size_t)warp * CPHD_E_STRIDE;
     for (int job = warp; job <= M; job += UPD_WARPS) {
-      for (int k = lane; k <= M; k += 32) E[k] = (k == 0) ? 1.0 : 0.0;
-      __syncwarp();
-      int deg = 0;
-      for (int n = 0; n < M; ++n) {
-        if (n == job - 1) continue;
-        cphd_esf_step(E, deg, s_x[n], lane);
-        ++deg;
-      }
+      cphd_esf_warp(s_x, M, job - 1, E, lane);
       if (job == 0) {
         for (int j = lane; j <= M; j += 32) s_le[j] = cphd_logd(E[j]) + cphd_mulk(j, lmax);
       } else {
@@ -1549,22 +1559,22 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
 /*     in ascending index order (the canonical accumulation order), and one THREAD per cluster       */
 /*     accumulates the moment-matched merge; stores are coalesced across clusters.                   */
 /* Particles with more candidates than the shared-memory capacity Scap (adapted by the host from     */
-/* the previous step), or with more than MF_POOL * Scap near pairs, are queued for merge_kernel.      */
+/* the previous step), or with more than 2.5 * Scap near pairs, are queued for merge_kernel.      */
 /* Mahalanobis metric only.                                                                           */
 /* =========================================================================================== */
 #define MF_WARPS 4
 #define MF_THREADS (MF_WARPS * 32)
-#define MF_POOL 3            /* near-pair pool: MF_POOL list nodes per candidate of capacity (a particle that needs more takes merge_kernel) */
+#define MF_POOL2 5           /* near-pair pool: MF_POOL2 / 2 list nodes per candidate of capacity (a particle that needs more takes merge_kernel) */
 #define MF_NONE 0xffffu
 #define MF_CELLS 592         /* MRG_NCELL + 1, padded */
-#define MF_QUEUE 256         /* gate survivors queued per warp (ring buffer) */
+#define MF_QUEUE 128         /* gate survivors queued per warp (ring buffer) */
 #define MF_ACH 8             /* A candidates gated per compaction step (up to MF_ACH * 32 new queue entries; a step that
                                 does not fit the ring sends the particle to merge_kernel) */
 
 __host__ __device__ static inline size_t merge_fast_smem_bytes(int S) {
   /* gate data 16 B | four u16 arrays | list heads 4 B | near-pair pool | per-warp radix histograms (the grid's cell ends
    * alias them) | pair queues */
-  return (size_t)S * (16 + 8 + 4 + 4 * MF_POOL) + (size_t)MF_ACH * 16 + (size_t)MF_WARPS * 512 + (size_t)MF_WARPS * MF_QUEUE * 4 + (size_t)S / 8 + 64;
+  return (size_t)S * (16 + 8 + 4 + 2 * MF_POOL2) + (size_t)MF_ACH * 16 + (size_t)MF_WARPS * 512 + (size_t)MF_WARPS * MF_QUEUE * 4 + (size_t)S / 8 + 64;
 }
 
 /* arr[idx] += v on a 4-byte aligned u16 array (no carry into the neighbour: counts stay < 65536); returns the old value */
@@ -1684,8 +1694,8 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
   unsigned short* Bbuf = Abuf + S;
   unsigned short* own = Bbuf + S;                                      /* [S] grid cell, then rank of the owning seed, then output slot */
   unsigned* HD = reinterpret_cast<unsigned*>(own + S);                 /* [S] near list of a candidate (by rank): head node, MF_NONE = empty */
-  unsigned* pool = HD + S;                                             /* [MF_POOL * S] list nodes: lower rank | next node << 16 */
-  unsigned short* hist = reinterpret_cast<unsigned short*>(pool + MF_POOL * S);   /* [MF_WARPS][256]; the grid's cell ends alias it */
+  unsigned* pool = HD + S;                                             /* [MF_POOL2 * S / 2] list nodes: lower rank | next node << 16 */
+  unsigned short* hist = reinterpret_cast<unsigned short*>(pool + (MF_POOL2 * S) / 2);   /* [MF_WARPS][256]; the grid's cell ends alias it */
   unsigned* queue = reinterpret_cast<unsigned*>(hist + MF_WARPS * 256);/* [MF_WARPS][MF_QUEUE] */
   unsigned* selfbits = queue + MF_WARPS * MF_QUEUE;                    /* [S / 32] candidate (by rank) is within its own threshold */
   unsigned* K = reinterpret_cast<unsigned*>(Gc);                       /* sort keys (before the gate records are built) */
@@ -1873,7 +1883,7 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
      * and the Mahalanobis distance is evaluated 32 queued pairs at a time. ---- */
     {
       unsigned* q = queue + warp * MF_QUEUE;   /* ring of pairs of cell-order positions */
-      const int pool_cap = MF_POOL * S;
+      const int pool_cap = (MF_POOL2 * S) / 2;
       int qh = 0, qn = 0;
       /* seed = the lower-ranked candidate, the argument order of the reference.  A near pair becomes a node of the
        * higher-ranked candidate's list. */
@@ -1941,6 +1951,7 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
                 const float gx = B1.x - A1.x, gy = B1.y - A1.y;
                 if ((k < arem) && (gx * gx + gy * gy <= gk * (B1.z + A1.z))) mask |= 1u << k;
               }
+              if (!__any_sync(FULL_MASK, mask != 0u)) continue;
               /* compaction: every lane appends its pairs to the ring */
               const int cntl = __popc(mask);
               int inc = cntl;
