@@ -38,6 +38,7 @@ WORKLOADS = {
     "synthetic_8192x256x64_phd": dict(P=8192, C=256, M=64, max_components=384),
     "synthetic_1024x64x32_phd": dict(P=1024, C=64, M=32, max_components=128),
     # BASELINE.json configs[3], one GPU's shard (1M particles over 8 GPUs): CPHD with the cardinality distribution
+    "synthetic_16384x128x50_cphd": dict(P=16384, C=128, M=50, max_components=256, filter_type=1, max_cardinality=255),
     "synthetic_131072x128x50_cphd": dict(P=131072, C=128, M=50, max_components=256, filter_type=1, max_cardinality=255),
     # BASELINE.json configs[4] per-GPU shape at a size one GPU's update buffer streams through: global resampling every step
     "synthetic_262144x128x100_phd": dict(P=262144, C=128, M=100, max_components=256, resample_threshold=1.0),

@@ -379,37 +379,45 @@ __device__ __forceinline__ float cphd_lse_warp(int n, F f) {
 }
 
 /* Elementary symmetric functions of the roots x[0..M) without root `skip` (-1: none), one warp, coefficients in
- * REGISTERS: lane L holds E[L + 32 r], r < kr = ceil((M + 1) / 32).  Folding one root is E[k] += x * E[k-1] on the old
- * values; E[k-1] comes from the lane below by shuffle (from lane 31 of the row below for lane 0).  Same operations in
- * the same order as the oracle's esf(): every coefficient is an independent chain of __dmul_rn / __dadd_rn, and the
- * terms beyond the current degree are exact zeros.  Result to the warp's shared array Es[0..M]. */
-__device__ __forceinline__ void cphd_esf_warp(const double* __restrict__ x, int M, int skip, double* __restrict__ Es, int lane) {
-  double E[CPHD_KREG];
+ * REGISTERS: lane L holds the KR consecutive coefficients e[KR L .. KR L + KR - 1], KR = ceil((M + 1) / 32).  Folding
+ * one root is e[k] += x * e[k-1] on the old values: inside a lane from the top coefficient down, and the lane's lowest
+ * coefficient takes e[k-1] from the lane below with one shuffle.  Same operations as the oracle's esf(): every
+ * coefficient is an independent chain of __dmul_rn / __dadd_rn, and the terms beyond the current degree are exact
+ * zeros.  Result to the warp's shared array Es[0..M]. */
+template <int KR>
+__device__ __forceinline__ void cphd_esf_warp_t(const double* __restrict__ x, int M, int skip, double* __restrict__ Es, int lane) {
+  double E[KR];
 #pragma unroll
-  for (int r = 0; r < CPHD_KREG; ++r) E[r] = 0.0;
+  for (int i = 0; i < KR; ++i) E[i] = 0.0;
   if (lane == 0) E[0] = 1.0;
-  const int kr = (M + 32) >> 5;
   for (int n = 0; n < M; ++n) {
     if (n == skip) continue;
     const double xn = x[n];
-    double carry = 0.0;
+    double below = __shfl_up_sync(FULL_MASK, E[KR - 1], 1);
+    if (lane == 0) below = 0.0;
 #pragma unroll
-    for (int r = 0; r < CPHD_KREG; ++r) {
-      if (r < kr) {
-        const double up = __shfl_up_sync(FULL_MASK, E[r], 1);
-        const double last = __shfl_sync(FULL_MASK, E[r], 31);
-        const double prev = (lane == 0) ? carry : up;
-        carry = last;
-        E[r] = __dadd_rn(E[r], __dmul_rn(xn, prev));
-      }
-    }
+    for (int i = KR - 1; i >= 1; --i) E[i] = __dadd_rn(E[i], __dmul_rn(xn, E[i - 1]));
+    E[0] = __dadd_rn(E[0], __dmul_rn(xn, below));
   }
 #pragma unroll
-  for (int r = 0; r < CPHD_KREG; ++r) {
-    const int k = lane + 32 * r;
-    if (k <= M) Es[k] = E[r];
+  for (int i = 0; i < KR; ++i) {
+    const int k = KR * lane + i;
+    if (k <= M) Es[k] = E[i];
   }
   __syncwarp();
+}
+__device__ __forceinline__ void cphd_esf_warp(const double* __restrict__ x, int M, int skip, double* __restrict__ Es, int lane) {
+  switch ((M + 32) >> 5) {
+    case 1: cphd_esf_warp_t<1>(x, M, skip, Es, lane); break;
+    case 2: cphd_esf_warp_t<2>(x, M, skip, Es, lane); break;
+    case 3: cphd_esf_warp_t<3>(x, M, skip, Es, lane); break;
+    case 4: cphd_esf_warp_t<4>(x, M, skip, Es, lane); break;
+    case 5: cphd_esf_warp_t<5>(x, M, skip, Es, lane); break;
+    case 6: cphd_esf_warp_t<6>(x, M, skip, Es, lane); break;
+    case 7: cphd_esf_warp_t<7>(x, M, skip, Es, lane); break;
+    case 8: cphd_esf_warp_t<8>(x, M, skip, Es, lane); break;
+    default: cphd_esf_warp_t<CPHD_KREG>(x, M, skip, Es, lane); break;
+  }
 }
 
 /* in: s_w[C] weights, s_qd[C] = w*(1-pd), s_S[M] likelihood masses (overwritten by D[m], the log factor of
@@ -1951,7 +1959,6 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
                 const float gx = B1.x - A1.x, gy = B1.y - A1.y;
                 if ((k < arem) && (gx * gx + gy * gy <= gk * (B1.z + A1.z))) mask |= 1u << k;
               }
-              if (!__any_sync(FULL_MASK, mask != 0u)) continue;
               /* compaction: every lane appends its pairs to the ring */
               const int cntl = __popc(mask);
               int inc = cntl;
