@@ -607,10 +607,14 @@ __device__ __forceinline__ float2 lds2(const float2* p) { return *p; }
 
 /* One 64-component chunk of one measurement for one warp: lane owns components jr, jr+1.
  * PASS 1 accumulates exp(log-weight); PASS 2 normalises, writes the dense terms and emits the prune survivors. */
-template <int PASS, bool TAIL, bool FAST, bool DENSE>
+/* STASH (PHD): pass 1 leaves exp(log-weight) of the pair in the warp's shared-memory stash and pass 2 normalises it with
+ * one multiplication, w = e * exp(-L_m) (oracle: the same product), instead of evaluating the exponential a second time;
+ * nL2 is then exp(-L_m).  Without STASH (CPHD: all first passes run before any second pass) pass 2 recomputes
+ * w = exp(log-weight + nL2). */
+template <int PASS, bool TAIL, bool FAST, bool DENSE, bool STASH>
 __device__ __forceinline__ void upd_chunk(const float2* __restrict__ rec, int jr, int C, float2 zr2, float2 zb2, bool dead,
                                           float2 nL2, float2& acc, float* __restrict__ Dm, bool even, float min_w, int lane,
-                                          int* s_ncand, float4* __restrict__ cand, int Smax, int tbase_m) {
+                                          int* s_ncand, float4* __restrict__ cand, int Smax, int tbase_m, float2* __restrict__ stash) {
   bool v0 = true, v1 = true;
   if (TAIL) {
     v0 = jr < C;
@@ -628,21 +632,25 @@ __device__ __forceinline__ void upd_chunk(const float2* __restrict__ rec, int jr
   }
   /* NOTE ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false, so the canonical
    * arithmetic of this loop spells every multiply-add as an explicit fused multiply-add (oracle: fmaf). */
-  float2 d = __fmul2_rn(__fmul2_rn(i0, i0), lds2(rec + F_S0));
-  d = __ffma2_rn(__fmul2_rn(i0, i1), lds2(rec + F_S12), d);
-  d = __ffma2_rn(__fmul2_rn(i1, i1), lds2(rec + F_S3), d);
-  const float2 g = __fadd2_rn(__ffma2_rn(d, splat2(-0.5f), splat2(-PHD_LOG_2PI_F)), lds2(rec + F_NHL));
-  float2 lw = __fadd2_rn(lds2(rec + F_BASE), g);
-  if (dead) lw = splat2(PHD_LOG0);
+  float2 lw = splat2(0.0f);
+  if (PASS == 1 || !STASH) {
+    float2 d = __fmul2_rn(__fmul2_rn(i0, i0), lds2(rec + F_S0));
+    d = __ffma2_rn(__fmul2_rn(i0, i1), lds2(rec + F_S12), d);
+    d = __ffma2_rn(__fmul2_rn(i1, i1), lds2(rec + F_S3), d);
+    const float2 g = __fadd2_rn(__ffma2_rn(d, splat2(-0.5f), splat2(-PHD_LOG_2PI_F)), lds2(rec + F_NHL));
+    lw = __fadd2_rn(lds2(rec + F_BASE), g);
+    if (dead) lw = splat2(PHD_LOG0);
+  }
   if (PASS == 1) {
     float2 e = phd_expf2(lw);
     if (TAIL) {
       if (!v0) e.x = 0.0f;
       if (!v1) e.y = 0.0f;
     }
+    if (STASH) stash[jr >> 1] = e;
     acc = __fadd2_rn(acc, e);
   } else {
-    float2 wt = phd_expf2(__fadd2_rn(lw, nL2));
+    float2 wt = STASH ? __fmul2_rn(stash[jr >> 1], nL2) : phd_expf2(__fadd2_rn(lw, nL2));
     const float2 m0 = __ffma2_rn(lds2(rec + F_K2), i1, __ffma2_rn(lds2(rec + F_K0), i0, lds2(rec + F_MX)));
     const float2 m1 = __ffma2_rn(lds2(rec + F_K3), i1, __ffma2_rn(lds2(rec + F_K1), i0, lds2(rec + F_MY)));
     const float2 c0 = lds2(rec + F_CU0), c1 = lds2(rec + F_CU1), c2 = lds2(rec + F_CU2), c3 = lds2(rec + F_CU3);
@@ -694,21 +702,22 @@ __device__ __forceinline__ void upd_chunk(const float2* __restrict__ rec, int jr
   }
 }
 
-template <int PASS, bool FAST, bool DENSE>
+template <int PASS, bool FAST, bool DENSE, bool STASH>
 __device__ __forceinline__ float2 upd_measurement(const float2* __restrict__ rec0, int C, float2 zr2, float2 zb2, bool dead,
                                                   float2 nL2, float* __restrict__ Dm, bool even, float min_w, int lane,
-                                                  int* s_ncand, float4* __restrict__ cand, int Smax, int tbase_m) {
+                                                  int* s_ncand, float4* __restrict__ cand, int Smax, int tbase_m,
+                                                  float2* __restrict__ stash) {
   float2 acc = make_float2(0.0f, 0.0f);
   const int nfull = C >> 6;
   const float2* rec = rec0 + (size_t)lane * UPD_NF;
   int jr = 2 * lane;
   for (int k = 0; k < nfull; ++k) {
-    upd_chunk<PASS, false, FAST, DENSE>(rec, jr, C, zr2, zb2, dead, nL2, acc, Dm, even, min_w, lane, s_ncand, cand, Smax, tbase_m);
+    upd_chunk<PASS, false, FAST, DENSE, STASH>(rec, jr, C, zr2, zb2, dead, nL2, acc, Dm, even, min_w, lane, s_ncand, cand, Smax, tbase_m, stash);
     rec += 32 * UPD_NF;
     jr += 64;
   }
   if (C & 63)
-    upd_chunk<PASS, true, FAST, DENSE>(rec, jr, C, zr2, zb2, dead, nL2, acc, Dm, even, min_w, lane, s_ncand, cand, Smax, tbase_m);
+    upd_chunk<PASS, true, FAST, DENSE, STASH>(rec, jr, C, zr2, zb2, dead, nL2, acc, Dm, even, min_w, lane, s_ncand, cand, Smax, tbase_m, stash);
   return acc;
 }
 
@@ -879,6 +888,10 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
     }
   }
 
+  /* PHD: the per-warp stash of pass 1 (Cmax / 2 float2 per warp) overlays the phase-0/1 staging arrays s_w .. s_tmp,
+   * which are dead once warp 0 has taken the sums above */
+  float2* s_stash = reinterpret_cast<float2*>(s_w) + (size_t)warp * (Cmax >> 1);
+  if (!CPHD) __syncthreads();
   const bool even = ((C & 1) == 0);      /* 64-bit stores need (C + m*C + j) even for every m */
   if (CPHD) {
     /* ---- CPHD phase 2a: likelihood mass S_m = sum_j exp(partial log-weight) of every measurement ---- */
@@ -888,9 +901,9 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
       const bool fast = fabsf(zb) < 3.14159f;
       float2 acc;
       if (fast)
-        acc = upd_measurement<1, true, DENSE>(s_rec, C, splat2(zr), splat2(zb), dead, splat2(0.0f), D, even, c.min_w, lane, &s_ncand, cand, Smax, 0);
+        acc = upd_measurement<1, true, DENSE, false>(s_rec, C, splat2(zr), splat2(zb), dead, splat2(0.0f), D, even, c.min_w, lane, &s_ncand, cand, Smax, 0, nullptr);
       else
-        acc = upd_measurement<1, false, DENSE>(s_rec, C, splat2(zr), splat2(zb), dead, splat2(0.0f), D, even, c.min_w, lane, &s_ncand, cand, Smax, 0);
+        acc = upd_measurement<1, false, DENSE, false>(s_rec, C, splat2(zr), splat2(zb), dead, splat2(0.0f), D, even, c.min_w, lane, &s_ncand, cand, Smax, 0, nullptr);
       float sum = warp_butterfly_sum(acc.x + acc.y);
       if (lane == 0) s_L[m] = sum;
     }
@@ -939,24 +952,30 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
     const bool fast = fabsf(zb) < 3.14159f;
     const int tbase_m = C + m * C;
     float L;
+    float2 wacc;
     if (CPHD) {
       L = -s_L[m];                        /* weights = exp(partial log-weight + D_m) (cphdUpdateKernel :1794-1799) */
+      if (fast)
+        wacc = upd_measurement<2, true, DENSE, false>(s_rec, C, zr2, zb2, dead, splat2(-L), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m, nullptr);
+      else
+        wacc = upd_measurement<2, false, DENSE, false>(s_rec, C, zr2, zb2, dead, splat2(-L), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m, nullptr);
     } else {
       float2 acc;
       if (fast)
-        acc = upd_measurement<1, true, DENSE>(s_rec, C, zr2, zb2, dead, splat2(0.0f), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m);
+        acc = upd_measurement<1, true, DENSE, true>(s_rec, C, zr2, zb2, dead, splat2(0.0f), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m, s_stash);
       else
-        acc = upd_measurement<1, false, DENSE>(s_rec, C, zr2, zb2, dead, splat2(0.0f), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m);
+        acc = upd_measurement<1, false, DENSE, true>(s_rec, C, zr2, zb2, dead, splat2(0.0f), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m, s_stash);
       float sum = warp_butterfly_sum(acc.x + acc.y);
       sum = sum + c.clutter_density;
       sum = sum + c.birth_weight;
       L = phd_safe_log(sum);
+      /* every lane reads back only what it stashed itself: no barrier between the passes */
+      const float2 sc2 = splat2(phd_expf(-L));
+      if (fast)
+        wacc = upd_measurement<2, true, DENSE, true>(s_rec, C, zr2, zb2, dead, sc2, D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m, s_stash);
+      else
+        wacc = upd_measurement<2, false, DENSE, true>(s_rec, C, zr2, zb2, dead, sc2, D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m, s_stash);
     }
-    float2 wacc;
-    if (fast)
-      wacc = upd_measurement<2, true, DENSE>(s_rec, C, zr2, zb2, dead, splat2(-L), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m);
-    else
-      wacc = upd_measurement<2, false, DENSE>(s_rec, C, zr2, zb2, dead, splat2(-L), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m);
     float dsum = warp_butterfly_sum(wacc.x + wacc.y);
     /* birth term of measurement m (host loop :3468-3507, normalised at :2232-2242) */
     if (lane == 0) {

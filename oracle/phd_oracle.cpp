@@ -391,8 +391,11 @@ static void update_particle(const phdslam_config_t& c, const Pose& pose, const s
     sum = sum + c.clutter_density;
     sum = sum + c.birth_weight;
     float log_normalizer = phd_safe_log(sum);
+    /* exp(logw - L) of the reference (:2222-2229), evaluated as exp(logw) * exp(-L): the first factor is the term that
+     * was just summed, so the kernel does not evaluate a second exponential per update term (canonical, <= 2 ulp) */
+    const float scale = phd_expf(-log_normalizer);
     for (int i = 0; i < C; ++i) {
-      det[i].weight = phd_expf(det[i].weight - log_normalizer);
+      det[i].weight = ev[i] * scale;
       ev[i] = det[i].weight;
     }
     G2& bt = out.terms[C + M * C + m];
