@@ -10,8 +10,10 @@
  *           [--set key=value ...] [--no-header] [--quiet]
  *
  * The reference hard-wires <data_directory>/measurements.txt and controls.txt (main.cpp:1079-1086); the two
- * overrides exist because the bundled files are named measurements_synth_*.txt.  Not built here:
- * timestamped asynchronous streams (main.cpp:1187-1230), follow_trajectory, the disparity mode.
+ * overrides exist because the bundled files are named measurements_synth_*.txt.  When
+ * <data_directory>/measurement_times.txt exists (with control_times.txt) the streams are asynchronous and every step is
+ * one event of phdslam_plan_events (main.cpp:1187-1230) with its own dt; follow_trajectory pins the (single) particle to
+ * <data_directory>/traj.txt (main.cpp:1122-1127,1239-1243).  Not built: the disparity mode.
  */
 #include <sys/stat.h>
 #include <sys/time.h>
@@ -41,13 +43,13 @@ static double now_ms() {
 
 int main(int argc, char** argv) {
   if (argc < 2) {
-    fprintf(stderr, "usage: %s <config.cfg> [synth] [--measurements FILE] [--controls FILE] [--out DIR] [--steps N] "
-                    "[--set key=value] [--no-header] [--quiet]\n", argv[0]);
+    fprintf(stderr, "usage: %s <config.cfg> [synth] [--measurements FILE] [--controls FILE] [--measurement-times FILE] "
+                    "[--control-times FILE] [--trajectory FILE] [--out DIR] [--steps N] [--set key=value] [--no-header] [--quiet]\n", argv[0]);
     return 1;
   }
   phdslam_config_t cfg;
   CHECK(phdslam_config_load(argv[1], &cfg));
-  std::string meas_path, ctrl_path, out_dir = ".";
+  std::string meas_path, ctrl_path, mt_path, ct_path, traj_path, out_dir = ".";
   int max_steps = -1, has_header = 1;
   bool quiet = false;
   for (int i = 2; i < argc; ++i) {
@@ -59,6 +61,9 @@ int main(int argc, char** argv) {
     }
     if (a == "--measurements" && i + 1 < argc) meas_path = argv[++i];
     else if (a == "--controls" && i + 1 < argc) ctrl_path = argv[++i];
+    else if (a == "--measurement-times" && i + 1 < argc) mt_path = argv[++i];
+    else if (a == "--control-times" && i + 1 < argc) ct_path = argv[++i];
+    else if (a == "--trajectory" && i + 1 < argc) traj_path = argv[++i];
     else if (a == "--out" && i + 1 < argc) out_dir = argv[++i];
     else if (a == "--steps" && i + 1 < argc) max_steps = atoi(argv[++i]);
     else if (a == "--no-header") has_header = 0;
@@ -79,24 +84,53 @@ int main(int argc, char** argv) {
   if (!dd.empty() && dd.back() != '/') dd += '/';
   if (meas_path.empty()) meas_path = dd + "measurements.txt";   /* main.cpp:1079 */
   if (ctrl_path.empty()) ctrl_path = dd + "controls.txt";       /* main.cpp:1084 */
+  if (mt_path.empty()) mt_path = dd + "measurement_times.txt";  /* main.cpp:1088 */
+  if (ct_path.empty()) ct_path = dd + "control_times.txt";      /* main.cpp:1090 */
+  if (traj_path.empty()) traj_path = dd + "traj.txt";           /* main.cpp:1123 */
 
   float* zdata = nullptr;
   int* zoff = nullptr;
   int n_meas_steps = 0;
   CHECK(phdslam_load_measurements(meas_path.c_str(), cfg.measurement_fields, has_header, &zdata, &zoff, &n_meas_steps));
   printf("Loaded %d measurements\n", n_meas_steps);
+  /* time stamps (main.cpp:1087-1117) */
+  double *ztimes = nullptr, *ctimes = nullptr;
+  int n_zt = 0, n_ct = 0;
+  CHECK(phdslam_load_timestamps(mt_path.c_str(), &ztimes, &n_zt));
+  CHECK(phdslam_load_timestamps(ct_path.c_str(), &ctimes, &n_ct));
+  const bool has_timestamps = n_zt > 0;                            /* :1092 */
+  /* the reference loads controls.txt for every motion model (:1084-1086); the constant-velocity model only needs it for
+   * the control time stamps */
   float* udata = nullptr;
   int n_controls = 0;
-  if (cfg.motion_type == 1) {
+  if (cfg.motion_type == 1 || has_timestamps) {
     CHECK(phdslam_load_controls(ctrl_path.c_str(), &udata, &n_controls));
     printf("Loaded %d control inputs\n", n_controls);
   }
+  std::vector<phdslam_event_t> events;
   int n_steps = n_meas_steps;                                     /* main.cpp:1097 */
+  if (has_timestamps) {
+    if (n_zt != n_meas_steps) {
+      fprintf(stderr, "mismatched measurements and measurement timestamps!\n");      /* :1104-1108 */
+      return 1;
+    }
+    if (n_ct != n_controls) {
+      fprintf(stderr, "mismatched controls and controls timestamps!\n");             /* :1109-1113 */
+      return 1;
+    }
+    events.resize((size_t)n_zt + n_ct + 1);
+    n_steps = phdslam_plan_events(ztimes, n_zt, ctimes, n_ct, events.data(), (int)events.size());
+    printf("Loaded %d + %d time stamps: %d events\n", n_zt, n_ct, n_steps);
+  }
   if (cfg.n_steps > 0 && n_steps > cfg.n_steps) n_steps = cfg.n_steps;   /* :1118 */
   if (max_steps > 0 && n_steps > max_steps) n_steps = max_steps;
-  if (cfg.follow_trajectory) {
-    fprintf(stderr, "phdslam: follow_trajectory is not built\n");
-    return 1;
+  phdslam_pose_t* traj = nullptr;
+  int n_traj = 0;
+  if (cfg.follow_trajectory) {                                    /* main.cpp:1122-1127 */
+    CHECK(phdslam_load_trajectory(traj_path.c_str(), &traj, &n_traj));
+    cfg.n_particles = 1;                                          /* only need 1 particle */
+    if (n_steps > n_traj) n_steps = n_traj;
+    printf("Following the trajectory of %s (%d poses)\n", traj_path.c_str(), n_traj);
   }
   mkdir(out_dir.c_str(), 0755);
 
@@ -109,23 +143,41 @@ int main(int argc, char** argv) {
   std::vector<int> ridx(P);
   std::vector<float> card((size_t)(cfg.filter_type == 1 ? n_card : 1));
   std::vector<phdslam_gaussian2d_t> map_est(65536);
+  float current_u[2] = {0.0f, 0.0f};                              /* main.cpp:1166-1168 */
   printf("STARTING SIMULATION\n");
   FILE* tf = fopen((out_dir + "/loopTime.log").c_str(), "w");     /* main.cpp:1300-1305 */
   for (int n = 0; n < n_steps; ++n) {
     double t0 = now_ms();
     if (!quiet) printf("****** Time Step [%d/%d] ******\n", n, n_steps);
-    const int M = zoff[n + 1] - zoff[n];
-    const float* z = zdata + (size_t)zoff[n] * cfg.measurement_fields;
-    const float zero_u[2] = {0.0f, 0.0f};
-    const float* u = zero_u;
-    if (cfg.motion_type == 1 && n > 0) {
+    int zi = n;
+    if (has_timestamps) {
+      /* one event of the asynchronous streams (main.cpp:1187-1230): its dt goes to the device config */
+      const phdslam_event_t& e = events[n];
+      zi = e.z_idx;
+      if (e.c_idx >= 0) {
+        current_u[0] = udata[2 * (size_t)e.c_idx];
+        current_u[1] = udata[2 * (size_t)e.c_idx + 1];
+      }
+      cfg.dt = e.dt;
+      CHECK(phdslam_set_config(h, &cfg));
+    } else if (cfg.motion_type == 1 && n > 0) {
       int ci = n - 1;                                             /* current_control = all_controls[n-1], main.cpp:1234 */
       if (ci >= n_controls) ci = n_controls - 1;
-      if (ci >= 0) u = udata + 2 * (size_t)ci;
+      if (ci >= 0) {
+        current_u[0] = udata[2 * (size_t)ci];
+        current_u[1] = udata[2 * (size_t)ci + 1];
+      }
+    }
+    const int M = (zi >= 0) ? zoff[zi + 1] - zoff[zi] : 0;
+    const float* z = (zi >= 0) ? zdata + (size_t)zoff[zi] * cfg.measurement_fields : nullptr;
+    int step_index = n;
+    if (cfg.follow_trajectory) {                                  /* main.cpp:1239-1243: the pose comes from the file, no prediction */
+      CHECK(phdslam_set_poses(h, &traj[n]));
+      step_index = 0;
     }
     phdslam_estimate_t est;
     int resampled = 0;
-    int rc = phdslam_step(h, n, u, z, M, cfg.measurement_fields, &est, &resampled);
+    int rc = phdslam_step(h, step_index, current_u, z, M, cfg.measurement_fields, &est, &resampled);
     /* state export: recoverSlamState output + particle set (main.cpp:1274-1279) */
     CHECK(phdslam_get_poses(h, poses.data()));
     CHECK(phdslam_get_log_weights(h, logw.data()));
@@ -165,5 +217,8 @@ int main(int argc, char** argv) {
   phdslam_free(zdata);
   phdslam_free(zoff);
   phdslam_free(udata);
+  phdslam_free(ztimes);
+  phdslam_free(ctimes);
+  phdslam_free(traj);
   return 0;
 }

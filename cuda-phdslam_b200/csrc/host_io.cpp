@@ -271,6 +271,79 @@ extern "C" int phdslam_load_controls(const char* path, float** data, int* n) {
   return 0;
 }
 
+/* loadTimestamps (main.cpp:147-167).  The reference pushes one value per getline() and pops the last (the empty line
+ * after the final newline); blank lines are skipped here instead. */
+extern "C" int phdslam_load_timestamps(const char* path, double** data, int* n) {
+  *n = 0;
+  *data = nullptr;
+  std::ifstream f(path);
+  if (!f) return 0;                       /* no time stamps: run_synth steps once per measurement set (:1091-1098) */
+  std::vector<double> all;
+  std::string line;
+  while (std::getline(f, line)) {
+    std::string t = trim(line);
+    if (t.empty()) continue;
+    all.push_back(strtod(t.c_str(), nullptr));
+  }
+  *n = (int)all.size();
+  *data = (double*)malloc(std::max<size_t>(all.size(), 1) * sizeof(double));
+  memcpy(*data, all.data(), all.size() * sizeof(double));
+  return 0;
+}
+
+/* loadTrajectory (main.cpp:247-264) */
+extern "C" int phdslam_load_trajectory(const char* path, phdslam_pose_t** data, int* n) {
+  std::ifstream f(path);
+  if (!f) {
+    phdslam_set_error(std::string("could not open trajectory file: ") + path);
+    return PHDSLAM_ERR_IO;
+  }
+  std::vector<phdslam_pose_t> all;
+  std::string line;
+  while (std::getline(f, line)) {
+    std::string t = trim(line);
+    if (t.empty() || t[0] == '%') continue;
+    std::vector<float> v;
+    split_floats(t, v);
+    phdslam_pose_t s;
+    float* o = &s.px;
+    for (int k = 0; k < 6; ++k) o[k] = (k < (int)v.size()) ? v[k] : 0.0f;
+    all.push_back(s);
+  }
+  *n = (int)all.size();
+  *data = (phdslam_pose_t*)malloc(std::max<size_t>(all.size(), 1) * sizeof(phdslam_pose_t));
+  memcpy(*data, all.data(), all.size() * sizeof(phdslam_pose_t));
+  return 0;
+}
+
+/* the event schedule of run_synth (main.cpp:1187-1230); REAL is float in the reference (slamtypes.h) */
+extern "C" int phdslam_plan_events(const double* zt, int nz, const double* ct, int nc, phdslam_event_t* ev, int cap) {
+  if (nz < 0 || nc < 0 || (cap > 0 && !ev)) return PHDSLAM_ERR_INVALID;
+  float current_time = 0.0f, last_time = 0.0f;     /* main.cpp:83-84 */
+  int z_idx = 0, c_idx = 0, n = 0;
+  const int n_steps = nz + nc;                      /* :1116 */
+  for (; n < n_steps && n < cap; ++n) {
+    if (z_idx >= nz || c_idx >= nc) break;          /* :1189-1192 */
+    const float tz = (float)zt[z_idx], tc = (float)ct[c_idx];
+    phdslam_event_t e;
+    last_time = current_time;
+    current_time = tc;
+    e.dt = current_time - last_time;
+    if (tz < tc) {
+      e.z_idx = z_idx++;
+      e.c_idx = -1;
+    } else if (tz == tc) {
+      e.c_idx = c_idx++;
+      e.z_idx = z_idx++;
+    } else {
+      e.c_idx = c_idx++;
+      e.z_idx = -1;
+    }
+    ev[n] = e;
+  }
+  return n;
+}
+
 extern "C" void phdslam_free(void* p) { free(p); }
 
 /* ---- log writer ----------------------------------------------------------------------------- */

@@ -95,7 +95,8 @@ ABI_SYMBOLS = [
     "phdslam_get_maps", "phdslam_set_maps", "phdslam_get_resample_idx", "phdslam_get_cardinalities",
     "phdslam_set_cardinalities", "phdslam_update_terms", "phdslam_get_timings", "phdslam_stream",
     "phdslam_synchronize", "phdslam_snapshot", "phdslam_restore", "phdslam_load_measurements",
-    "phdslam_load_controls", "phdslam_free", "phdslam_write_log",
+    "phdslam_load_controls", "phdslam_load_timestamps", "phdslam_load_trajectory", "phdslam_plan_events", "phdslam_free",
+    "phdslam_write_log",
 ]
 
 _lib = None
@@ -145,6 +146,9 @@ def load_library(path=None):
     lib.phdslam_load_measurements.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_float)),
                                               C.POINTER(C.POINTER(C.c_int)), C.POINTER(C.c_int)]
     lib.phdslam_load_controls.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int)]
+    lib.phdslam_load_timestamps.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.c_int)]
+    lib.phdslam_load_trajectory.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+    lib.phdslam_plan_events.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.phdslam_free.argtypes = [C.c_void_p]
     lib.phdslam_free.restype = None
     lib.phdslam_write_log.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
@@ -199,6 +203,41 @@ def load_controls(path):
     d = np.ctypeslib.as_array(data, shape=(max(n.value * 2, 1),)).copy()[: n.value * 2].reshape(n.value, 2)
     lib.phdslam_free(data)
     return d
+
+
+def load_timestamps(path):
+    """loadTimestamps (src/main.cpp:147-167); a missing file gives an empty array (run without time stamps)."""
+    lib = load_library()
+    data, n = C.POINTER(C.c_double)(), C.c_int()
+    _check(lib.phdslam_load_timestamps(os.fsencode(path), C.byref(data), C.byref(n)))
+    d = np.ctypeslib.as_array(data, shape=(max(n.value, 1),)).copy()[: n.value] if n.value else np.zeros(0)
+    lib.phdslam_free(data)
+    return d
+
+
+def load_trajectory(path):
+    """loadTrajectory (src/main.cpp:247-264): POSE_DTYPE array."""
+    lib = load_library()
+    data, n = C.c_void_p(), C.c_int()
+    _check(lib.phdslam_load_trajectory(os.fsencode(path), C.byref(data), C.byref(n)))
+    buf = (C.c_char * (max(n.value, 1) * POSE_DTYPE.itemsize)).from_address(data.value)
+    d = np.frombuffer(buf, dtype=POSE_DTYPE, count=n.value).copy()
+    lib.phdslam_free(data)
+    return d
+
+
+EVENT_DTYPE = np.dtype([("z_idx", "i4"), ("c_idx", "i4"), ("dt", "f4")])
+
+
+def plan_events(measurement_times, control_times):
+    """The per-step input schedule of run_synth for time-stamped streams (src/main.cpp:1187-1230): EVENT_DTYPE array."""
+    zt = np.ascontiguousarray(measurement_times, dtype=np.float64)
+    ct = np.ascontiguousarray(control_times, dtype=np.float64)
+    ev = np.zeros(len(zt) + len(ct) + 1, dtype=EVENT_DTYPE)
+    n = load_library().phdslam_plan_events(zt.ctypes.data, len(zt), ct.ctypes.data, len(ct), ev.ctypes.data, len(ev))
+    if n < 0:
+        _check(n)
+    return ev[:n].copy()
 
 
 def write_log(path, layout, expected_pose, map_est, log_weights, poses, resample_idx=None, cardinality=None, n_card=1,

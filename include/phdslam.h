@@ -217,6 +217,27 @@ int phdslam_restore(phdslam_t* h);
  * index into floats of `fields` per record. */
 int phdslam_load_measurements(const char* path, int fields, int has_header, float** data, int** offsets, int* n_steps);
 int phdslam_load_controls(const char* path, float** data /* n x {v_encoder, alpha} */, int* n);
+/* reference: loadTimestamps (src/main.cpp:147-167): one time per line.  A missing file is not an error: *n = 0
+ * (the reference then runs without time stamps, main.cpp:1091-1093). */
+int phdslam_load_timestamps(const char* path, double** data, int* n);
+/* reference: loadTrajectory (src/main.cpp:247-264): lines starting with '%' skipped, six numbers per pose. */
+int phdslam_load_trajectory(const char* path, phdslam_pose_t** data, int* n);
+
+/* The input schedule of run_synth for time-stamped, asynchronous measurement and control streams
+ * (src/main.cpp:1187-1230), one event per time step:
+ *   measurement earlier than the next control -> update with that measurement set, the control is kept
+ *   equal time stamps                         -> take the control and the measurement set
+ *   otherwise                                 -> take the control, no measurements
+ * Every event predicts with dt = (time stamp of control c_idx) - (time of the previous event) -- the reference reads the
+ * CONTROL time stamp in all three branches -- and the loop ends when either stream is exhausted (:1189-1192). */
+typedef struct phdslam_event {
+  int z_idx;        /* measurement set to update with, -1 = none */
+  int c_idx;        /* control to take, -1 = keep the current one */
+  float dt;         /* config.dt of this step (setDeviceConfig, :1199-1200) */
+} phdslam_event_t;
+/* events[cap]; returns the number of events (<= nz + nc, main.cpp:1116), or a negative status */
+int phdslam_plan_events(const double* measurement_times, int nz, const double* control_times, int nc, phdslam_event_t* events,
+                        int cap);
 void phdslam_free(void* p);
 /* reference: writeLog (main.cpp:848-954) in the README 5-line layout (README:31-39) or the 7-line one. */
 int phdslam_write_log(const char* path, int layout, const phdslam_pose_t* expected, const phdslam_gaussian2d_t* map,
