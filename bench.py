@@ -290,7 +290,8 @@ def run_ours(args, wl):
                      "estimate": float(oth[2]), "resample": float(oth[3])},
         "roofline": {"bound": "hbm", "kernel": "update_dense_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_update": balg, "kernel_ms": upd},
+                     "algorithmic_bytes_per_update": balg, "kernel_ms": upd,
+                     "timing": "CUDA events on the filter's stream around the kernel, averaged over the timed steps"},
         "cpu_baseline": {"value": cpu_rate, "unit": "updates/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": 3 * 256 * 4 + 8, "d2h_bytes_per_step": 3 * 128,
                 "ms_per_step": wall_total / args.steps},

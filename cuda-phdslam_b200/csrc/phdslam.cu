@@ -254,6 +254,20 @@ extern "C" int phdslam_create(const phdslam_config_t* cfg, int device, phdslam_t
   derive_devcfg(h->cfg, h->Cmax, &h->dc);
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 12; ++i) CK(cudaEventCreate(&h->ev[i]));
+  {
+    /* Optional (PHDSLAM_OVERLAP=1 / phdslam_set_overlap): the merge of sub-batch k runs on a higher-priority stream
+     * while the update of sub-batch k+1 streams.  Measured on B200 at 65 536 x 256 x 64: no gain (15.8 ms vs 15.1 ms
+     * serial) -- a merge CTA (32 KB of shared memory, 6 per SM) and an update CTA (45 KB, 4 per SM) do not share an SM
+     * profitably: both kernels need their full occupancy to hide latency, so the SMs time-slice either way.  Off by
+     * default. */
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&h->stream_m, cudaStreamNonBlocking, hi));
+    for (int i = 0; i < PHD_MAX_SUB; ++i) CK(cudaEventCreateWithFlags(&h->ev_sub[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_merge_done, cudaEventDisableTiming));
+    const char* e = getenv("PHDSLAM_OVERLAP");
+    h->overlap = (e && atoi(e) != 0) ? 1 : 0;
+  }
   rc = alloc_state(h);
   if (rc) { free_state(h); delete h; return rc; }
   CK(cudaFuncSetAttribute(update_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(h->Cmax)));
@@ -297,6 +311,10 @@ extern "C" void phdslam_destroy(phdslam_t* h) {
   if (h->nccl_comm) ncclCommDestroy((ncclComm_t)h->nccl_comm);
   free_state(h);
   for (int i = 0; i < 12; ++i) cudaEventDestroy(h->ev[i]);
+  for (int i = 0; i < PHD_MAX_SUB; ++i) cudaEventDestroy(h->ev_sub[i]);
+  cudaEventDestroy(h->ev_merge_done);
+  cudaStreamSynchronize(h->stream_m);
+  cudaStreamDestroy(h->stream_m);
   cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -318,6 +336,7 @@ extern "C" int phdslam_n_local(const phdslam_t* h) { return h->n_local; }
 extern "C" int phdslam_local_offset(const phdslam_t* h) { return h->offset; }
 extern "C" void* phdslam_stream(phdslam_t* h) { return (void*)h->stream; }
 extern "C" int phdslam_synchronize(phdslam_t* h) { CK(cudaStreamSynchronize(h->stream)); return 0; }
+extern "C" int phdslam_set_overlap(phdslam_t* h, int on) { h->overlap = on ? 1 : 0; return 0; }
 
 extern "C" int phdslam_dist_unique_id(void* id128) {
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
@@ -500,13 +519,17 @@ static int plan_batches(phdslam* h, bool dense, std::vector<int>& bounds, size_t
   return 0;
 }
 
-static int launch_update_batch(phdslam* h, int M, int p0, int p1, unsigned long long tbase, bool dense, int write_card = 1) {
+/* cand_p0: local particle whose records sit at the start of the candidate buffers (p0 when the buffers hold one batch,
+ * 0 when they hold every local particle) */
+static int launch_update_batch(phdslam* h, int M, int p0, int p1, unsigned long long tbase, bool dense, int write_card = 1,
+                               int cand_p0 = -1) {
+  if (cand_p0 < 0) cand_p0 = p0;
   UpdArgs a;
   a.lfact = h->lfact; a.card = h->n_card ? h->card[h->cur] : nullptr; a.write_card = write_card;
   a.map = h->map[h->cur]; a.count = h->count[h->cur]; a.cls = h->cls; a.pose = h->pose[h->cur];
   a.z = h->z_dev; a.M = M; a.n = h->n_local; a.p0 = p0;
   a.toff = h->toff; a.tbase = tbase; a.dense = h->dense; a.n_in = h->n_in; a.dlogw = h->dlogw; a.c = h->dc;
-  a.cand = h->cand_in; a.n_cand = h->n_cand; a.Smax = h->Smax;
+  a.cand = h->cand_in + (size_t)(p0 - cand_p0) * h->Smax * 2; a.n_cand = h->n_cand; a.Smax = h->Smax;
   if (h->n_card) {
     const size_t sm = update_smem_bytes(h->Cmax) + cphd_smem_bytes(h->n_card);
     if (dense)
@@ -522,23 +545,27 @@ static int launch_update_batch(phdslam* h, int M, int p0, int p1, unsigned long 
   return 0;
 }
 
-static int launch_merge_batch(phdslam* h, int M, int p0, int p1) {
+static int launch_merge_batch(phdslam* h, int M, int p0, int p1, cudaStream_t st = nullptr, int cand_p0 = -1) {
+  if (!st) st = h->stream;
+  if (cand_p0 < 0) cand_p0 = p0;
   MrgArgs a;
-  a.M = M; a.n = h->n_local; a.p0 = p0; a.cand_in = h->cand_in; a.n_cand = h->n_cand;
+  a.M = M; a.n = h->n_local; a.p0 = p0; a.n_cand = h->n_cand;
+  a.cand_in = h->cand_in + (size_t)(p0 - cand_p0) * h->Smax * 2;
   a.map_in = h->map[h->cur]; a.count_in = h->count[h->cur]; a.cls = h->cls;
   a.map_out = h->map[h->cur ^ 1]; a.count_out = h->count[h->cur ^ 1];
-  a.red = h->red; a.Smax = h->Smax; a.c = h->dc; a.p1 = p1; a.cand = h->cand;
+  a.red = h->red; a.Smax = h->Smax; a.c = h->dc; a.p1 = p1;
+  a.cand = h->cand + (size_t)(p0 - cand_p0) * h->Smax * 2;
   a.Scap = h->Scap; a.ovf_list = h->ovf_list; a.use_list = 0;
   if (h->Scap > 0 && h->dc.distance_metric == 0) {
-    merge_fast_kernel<<<p1 - p0, MF_THREADS, merge_fast_smem_bytes(h->Scap), h->stream>>>(a);
+    merge_fast_kernel<<<p1 - p0, MF_THREADS, merge_fast_smem_bytes(h->Scap), st>>>(a);
     LAUNCH_CHECK(h);
     a.use_list = 1;   /* whatever did not fit the shared-memory capacity (normally nothing: the warps exit at once) */
-    merge_kernel<<<cdiv(p1 - p0, MRG_WARPS), MRG_THREADS, merge_smem_bytes(h->Smax), h->stream>>>(a);
+    merge_kernel<<<cdiv(p1 - p0, MRG_WARPS), MRG_THREADS, merge_smem_bytes(h->Smax), st>>>(a);
     LAUNCH_CHECK(h);
-    CK(cudaMemsetAsync(&h->red->ovf_n, 0, sizeof(int), h->stream));
+    CK(cudaMemsetAsync(&h->red->ovf_n, 0, sizeof(int), st));
     return 0;
   }
-  merge_kernel<<<cdiv(p1 - p0, MRG_WARPS), MRG_THREADS, merge_smem_bytes(h->Smax), h->stream>>>(a);
+  merge_kernel<<<cdiv(p1 - p0, MRG_WARPS), MRG_THREADS, merge_smem_bytes(h->Smax), st>>>(a);
   LAUNCH_CHECK(h);
   return 0;
 }
@@ -579,10 +606,13 @@ extern "C" int phdslam_update(phdslam_t* h, const float* z, int M, int fields) {
     rc = ensure_dense(h, max_terms * PHD_NPLANES);
     if (rc) return rc;
   }
+  /* overlap needs candidate buffers for every local particle (the merge of one sub-batch reads them while the update of
+   * the next one writes) */
+  const bool overlap = h->overlap && ((unsigned long long)h->n_local * h->Smax * 64ull <= PHD_CAND_BUDGET);
   {
     int maxb = 0;
     for (size_t b = 0; b + 1 < bounds.size(); ++b) maxb = std::max(maxb, bounds[b + 1] - bounds[b]);
-    rc = ensure_cand(h, (size_t)maxb);
+    rc = ensure_cand(h, overlap ? (size_t)h->n_local : (size_t)maxb);
     if (rc) return rc;
   }
   std::vector<unsigned long long> tb(bounds.size(), 0);
@@ -593,7 +623,34 @@ extern "C" int phdslam_update(phdslam_t* h, const float* z, int M, int fields) {
   }
   CK(cudaMemsetAsync(h->red, 0, sizeof(Reductions), h->stream));
   float upd_ms = 0, mrg_ms = 0;
-  const bool multi = bounds.size() > 2;
+  bool multi = bounds.size() > 2;
+  if (overlap) {
+    /* sub-batches: the update of sub-batch k+1 (this stream, HBM-bound) runs under the merge of sub-batch k (the
+     * higher-priority stream, issue-bound).  Sub-batches of one dense batch share its dense buffer. */
+    const int n = h->n_local;
+    const int n_dense = (int)bounds.size() - 1;
+    int per_sub = std::max(2048, cdiv(n, PHD_MAX_SUB / 4));
+    while (cdiv(n, per_sub) + n_dense > PHD_MAX_SUB) per_sub *= 2;
+    CK(cudaEventRecord(h->ev[3], h->stream));
+    CK(cudaStreamWaitEvent(h->stream_m, h->ev[3], 0));           /* the merge stream starts behind the classification */
+    int k = 0;
+    for (int b = 0; b < n_dense; ++b) {
+      for (int p0 = bounds[b]; p0 < bounds[b + 1]; p0 += per_sub, ++k) {
+        const int p1 = std::min(p0 + per_sub, bounds[b + 1]);
+        rc = launch_update_batch(h, M, p0, p1, tb[b], dense, 1, 0);
+        if (rc) return rc;
+        CK(cudaEventRecord(h->ev_sub[k], h->stream));
+        CK(cudaStreamWaitEvent(h->stream_m, h->ev_sub[k], 0));
+        rc = launch_merge_batch(h, M, p0, p1, h->stream_m, 0);
+        if (rc) return rc;
+      }
+    }
+    CK(cudaEventRecord(h->ev[4], h->stream));                     /* end of the last update kernel */
+    CK(cudaEventRecord(h->ev_merge_done, h->stream_m));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_merge_done, 0));
+    CK(cudaEventRecord(h->ev[5], h->stream));                     /* end of the last merge kernel */
+    multi = false;                                                /* one pair of spans: update, then the exposed merge tail */
+  } else
   for (size_t b = 0; b + 1 < bounds.size(); ++b) {
     CK(cudaEventRecord(h->ev[3], h->stream));
     rc = launch_update_batch(h, M, bounds[b], bounds[b + 1], tb[b], dense);

@@ -14,6 +14,7 @@ void phdslam_set_error(const std::string& s);
 
 #define PHD_MAX_MEAS 256   /* reference: __constant__ RangeBearingMeasurement Z[256] (src/phdfilter.cu:120) */
 #define PHD_NPLANES 7      /* dense update term = {c0,c1,c2,c3,mx,my,w}, the field order of Gaussian2D */
+#define PHD_MAX_SUB 64     /* sub-batches per update whose merge overlaps the next sub-batch's update */
 #define PHD_MAP_PLANES 6   /* persistent map component = {w,mx,my,pxx,pxy,pyy} (covariance stored once) */
 
 /* Constants derived on the host once per set_config and passed BY VALUE to every kernel
@@ -92,6 +93,10 @@ struct phdslam {
   unsigned predict_calls, resample_calls;
   unsigned long long launches;
   cudaEvent_t ev[12];
+  /* update / merge overlap: merge kernels run on a second, higher-priority stream behind per-sub-batch events */
+  cudaStream_t stream_m;
+  cudaEvent_t ev_sub[PHD_MAX_SUB], ev_merge_done;
+  int overlap;
   phdslam_timings_t tim;
   void* nccl_comm;
   /* resampling migration staging (sender side), grown on demand */

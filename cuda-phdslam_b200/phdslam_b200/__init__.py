@@ -94,7 +94,7 @@ ABI_SYMBOLS = [
     "phdslam_set_poses", "phdslam_get_log_weights", "phdslam_set_log_weights", "phdslam_get_map_sizes",
     "phdslam_get_maps", "phdslam_set_maps", "phdslam_get_resample_idx", "phdslam_get_cardinalities",
     "phdslam_set_cardinalities", "phdslam_update_terms", "phdslam_get_timings", "phdslam_stream",
-    "phdslam_synchronize", "phdslam_snapshot", "phdslam_restore", "phdslam_load_measurements",
+    "phdslam_synchronize", "phdslam_set_overlap", "phdslam_snapshot", "phdslam_restore", "phdslam_load_measurements",
     "phdslam_load_controls", "phdslam_load_timestamps", "phdslam_load_trajectory", "phdslam_plan_events", "phdslam_free",
     "phdslam_write_log",
 ]
@@ -129,12 +129,13 @@ def load_library(path=None):
     lib.phdslam_map_estimate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     lib.phdslam_resample.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.phdslam_step.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
-    for name in ("phdslam_n_local", "phdslam_local_offset", "phdslam_synchronize", "phdslam_snapshot", "phdslam_restore"):
+    for name in ("phdslam_n_local", "phdslam_local_offset", "phdslam_synchronize", "phdslam_set_overlap", "phdslam_snapshot", "phdslam_restore"):
         getattr(lib, name).argtypes = [C.c_void_p]
     for name in ("phdslam_get_poses", "phdslam_set_poses", "phdslam_get_log_weights", "phdslam_set_log_weights",
                  "phdslam_get_map_sizes", "phdslam_get_resample_idx", "phdslam_get_cardinalities",
                  "phdslam_set_cardinalities", "phdslam_get_timings"):
         getattr(lib, name).argtypes = [C.c_void_p, C.c_void_p]
+    lib.phdslam_set_overlap.argtypes = [C.c_void_p, C.c_int]
     lib.phdslam_get_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     lib.phdslam_set_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.phdslam_update_terms.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
@@ -463,6 +464,10 @@ class PhdSlam(object):
 
     def restore(self):
         _check(self.lib.phdslam_restore(self._h))
+
+    def set_overlap(self, on):
+        """update / merge overlap on two streams (default off: no gain on B200); same results either way"""
+        _check(self.lib.phdslam_set_overlap(self._h, int(bool(on))))
 
     def synchronize(self):
         _check(self.lib.phdslam_synchronize(self._h))

@@ -207,6 +207,11 @@ int phdslam_get_timings(phdslam_t* h, phdslam_timings_t* out);
 /* Raw stream handle (cudaStream_t) so a caller can record its own events on the stream kernels run on. */
 void* phdslam_stream(phdslam_t* h);
 int phdslam_synchronize(phdslam_t* h);
+/* on = 1: the prune + merge of one sub-batch of particles runs (on a second, higher-priority stream) under the GM-PHD
+ * update of the next sub-batch; the results are identical.  Off by default: on B200 the two kernels do not share an SM
+ * profitably.  With overlap, phdslam_timings_t.update_ms is the span of the update kernels and
+ * merge_ms the part of the merge that is still running when the last update kernel ends. */
+int phdslam_set_overlap(phdslam_t* h, int on);
 /* Snapshot / restore of the whole device state inside the handle (bench: identical work every step). */
 int phdslam_snapshot(phdslam_t* h);
 int phdslam_restore(phdslam_t* h);

@@ -387,3 +387,20 @@ def test_merge_kernels_agree_at_scale(monkeypatch):
         res.append((sizes.copy(), maps.tobytes(), g.log_weights.tobytes()))
     assert (res[0][0] == res[1][0]).all()
     assert res[0][1] == res[1][1] and res[0][2] == res[1][2]
+
+
+def test_update_merge_overlap_gives_identical_state():
+    """phdslam_set_overlap(1): merge on a second stream under the next sub-batch's update -- same maps, same weights"""
+    Pn, C, M = 6000, 48, 20
+    cfg = S.scene_config(Pn, C, M, max_components=128)
+    sc = S.make_scene(Pn, C, M, seed=12, n_near=2, n_far=2)
+    res = []
+    for on in (0, 1):
+        g = P.PhdSlam(cfg)
+        g.set_overlap(on)
+        S.load_scene(g, sc)
+        for k in range(2):
+            g.phdUpdateSynth(S.make_scene(Pn, C, M, seed=12 + k)["Z"])
+        sizes, maps = g.get_maps()
+        res.append((sizes.copy(), maps.tobytes(), g.log_weights.tobytes()))
+    assert (res[0][0] == res[1][0]).all() and res[0][1] == res[1][1] and res[0][2] == res[1][2]
