@@ -41,6 +41,7 @@ WORKLOADS = {
     "synthetic_16384x128x50_cphd": dict(P=16384, C=128, M=50, max_components=256, filter_type=1, max_cardinality=255),
     "synthetic_131072x128x50_cphd": dict(P=131072, C=128, M=50, max_components=256, filter_type=1, max_cardinality=255),
     # BASELINE.json configs[4] per-GPU shape at a size one GPU's update buffer streams through: global resampling every step
+    "synthetic_32768x128x100_phd": dict(P=32768, C=128, M=100, max_components=256, resample_threshold=1.0),
     "synthetic_262144x128x100_phd": dict(P=262144, C=128, M=100, max_components=256, resample_threshold=1.0),
 }
 DEFAULT_WORKLOAD = "synthetic_65536x256x64_phd"

@@ -1595,13 +1595,12 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
 #define MF_NONE 0xffffu
 #define MF_CELLS 592         /* MRG_NCELL + 1, padded */
 #define MF_QUEUE 128         /* gate survivors queued per warp (ring buffer) */
-#define MF_ACH 8             /* A candidates gated per compaction step (up to MF_ACH * 32 new queue entries; a step that
-                                does not fit the ring sends the particle to merge_kernel) */
+#define MF_ACH 8             /* A candidates gated per compaction step (up to MF_ACH * 32 new queue entries) */
 
 __host__ __device__ static inline size_t merge_fast_smem_bytes(int S) {
-  /* gate data 16 B | four u16 arrays | list heads 4 B | near-pair pool | per-warp radix histograms (the grid's cell ends
-   * alias them) | pair queues */
-  return (size_t)S * (16 + 8 + 4 + 2 * MF_POOL2) + (size_t)MF_ACH * 16 + (size_t)MF_WARPS * 512 + (size_t)MF_WARPS * MF_QUEUE * 4 + (size_t)S / 8 + 64;
+  /* gate records 16 B | four u16 arrays (two of them double as the list heads) | near-pair pool | per-warp radix
+   * histograms (the grid's cell ends alias them) | pair queues | self-threshold bits */
+  return (size_t)S * (16 + 8 + 2 * MF_POOL2) + (size_t)MF_ACH * 16 + (size_t)MF_WARPS * 512 + (size_t)MF_WARPS * MF_QUEUE * 4 + (size_t)S / 8 + 64;
 }
 
 /* arr[idx] += v on a 4-byte aligned u16 array (no carry into the neighbour: counts stay < 65536); returns the old value */
@@ -1720,13 +1719,14 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
   unsigned short* Abuf = P1 + S;
   unsigned short* Bbuf = Abuf + S;
   unsigned short* own = Bbuf + S;                                      /* [S] grid cell, then rank of the owning seed, then output slot */
-  unsigned* HD = reinterpret_cast<unsigned*>(own + S);                 /* [S] near list of a candidate (by rank): head node, MF_NONE = empty */
-  unsigned* pool = HD + S;                                             /* [MF_POOL2 * S / 2] list nodes: lower rank | next node << 16 */
+  unsigned* HD = reinterpret_cast<unsigned*>(Abuf);                    /* [S] near list of a candidate (by rank): head node, MF_NONE = empty
+                                                                          (over the two sort buffers, free between the record load and the output slots) */
+  unsigned* pool = reinterpret_cast<unsigned*>(own + S);               /* [MF_POOL2 * S / 2] list nodes: lower rank | next node << 16 */
   unsigned short* hist = reinterpret_cast<unsigned short*>(pool + (MF_POOL2 * S) / 2);   /* [MF_WARPS][256]; the grid's cell ends alias it */
   unsigned* queue = reinterpret_cast<unsigned*>(hist + MF_WARPS * 256);/* [MF_WARPS][MF_QUEUE] */
   unsigned* selfbits = queue + MF_WARPS * MF_QUEUE;                    /* [S / 32] candidate (by rank) is within its own threshold */
   unsigned* K = reinterpret_cast<unsigned*>(Gc);                       /* sort keys (before the gate records are built) */
-  unsigned* Wtmp = HD;                                                 /* weight keys by emission slot (before the lists exist) */
+  unsigned* Wtmp = pool;                                               /* weight keys by emission slot (before the lists exist) */
   unsigned short* cend = hist;
 
   const int Cmax = c.Cmax;
@@ -1836,7 +1836,6 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
       crec[2 * r + 1] = r1;
       P1[i] = (unsigned short)r;     /* candidate index -> rank */
       own[r] = (unsigned short)MF_NONE;
-      HD[r] = MF_NONE;
       tmax = fmaxf(tmax, r1.w);
       xmin = fminf(xmin, r1.x); xmax = fmaxf(xmax, r1.x);
       ymin = fminf(ymin, r1.y); ymax = fmaxf(ymax, r1.y);
@@ -1900,6 +1899,7 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
     for (int r = tid; r < n; r += MF_THREADS) {
       const float4 g = crec[2 * r + 1];
       Gc[atomic_add_u16(cend, (int)cellr[r], 1u)] = make_float4(g.x, g.y, g.w, (float)r);
+      HD[r] = MF_NONE;
     }
     __syncthreads();                                       /* cend[c] is now the END of cell c */
 
@@ -1987,11 +1987,32 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
                 if (lane >= off) inc += t;
               }
               const int total = __shfl_sync(FULL_MASK, inc, 31);
-              if (qn + total > MF_QUEUE) {
-                s_flag = 1;
+              const unsigned pb = (unsigned)posb << 16;
+              if (qn + total > MF_QUEUE) {        /* the ring cannot take this step: drain it first */
+                __syncwarp();
+                while (qn > 0) {
+                  const int cq = min(qn, 32);
+                  evaluate(cq);
+                  qh = (qh + cq) & (MF_QUEUE - 1);
+                  qn -= cq;
+                }
+                __syncwarp();
+              }
+              if (total > MF_QUEUE) {
+                /* a very dense neighbourhood: one pair per lane and round (the ring is empty here) */
+                while (__any_sync(FULL_MASK, mask != 0u)) {
+                  const bool has = mask != 0u;
+                  const unsigned hb = __ballot_sync(FULL_MASK, has);
+                  if (has) {
+                    q[(qh + __popc(hb & lt_mask)) & (MF_QUEUE - 1)] = (unsigned)(a_beg + a0 + (__ffs(mask) - 1)) | pb;
+                    mask &= mask - 1;
+                  }
+                  __syncwarp();
+                  evaluate(__popc(hb));
+                  __syncwarp();
+                }
               } else if (total) {
                 int slot = qh + qn + inc - cntl;
-                const unsigned pb = (unsigned)posb << 16;
                 for (unsigned m = mask; m; m &= m - 1) {
                   q[slot & (MF_QUEUE - 1)] = (unsigned)(a_beg + a0 + (__ffs(m) - 1)) | pb;
                   ++slot;
@@ -2075,7 +2096,7 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
     unsigned short* slotA = items;
     unsigned short* csz = ord;       /* cluster sizes -> starts -> ends (the rank -> index table is no longer needed) */
     unsigned short* memb = reinterpret_cast<unsigned short*>(pool);   /* member lists (the near lists are no longer needed) */
-    unsigned short* keyA = reinterpret_cast<unsigned short*>(HD);     /* output slot of every candidate's cluster */
+    unsigned short* keyA = memb + S;                                  /* output slot of every candidate's cluster */
     const unsigned stopr = (unsigned)s_stopr;
     for (int k = tid; k < ((nseeds + 2) >> 1); k += MF_THREADS) reinterpret_cast<unsigned*>(csz)[k] = 0;
     __syncthreads();
