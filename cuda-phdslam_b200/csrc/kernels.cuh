@@ -2371,6 +2371,17 @@ __global__ void migrate_unpack_pose_kernel(const float* __restrict__ pose_in /* 
   pose_out[(size_t)k * n_dst + first + j] = pose_in[i];
 }
 
+/* "shotgun" prediction (reference src/phdfilter.cu:796-797, 1185-1238): prediction j descends from particle j / k */
+__global__ void fanout_kernel(int n_out, int k, float logk, const float* __restrict__ logw_in, float* __restrict__ logw_out,
+                              const int* __restrict__ ridx_in, int* __restrict__ ridx_out, int* __restrict__ anc) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_out) return;
+  const int i = j / k;
+  anc[j] = i;
+  logw_out[j] = logw_in[i] - logk;
+  ridx_out[j] = ridx_in[i];
+}
+
 __global__ void fill_kernel(float* p, int n, float v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;

@@ -147,8 +147,8 @@ static int validate_config(const phdslam_config_t* c) {
     phdslam_set_error("feature_model != 0 (dynamic / mixed features) is outside the hot path");
     return PHDSLAM_ERR_INVALID;
   }
-  if (c->n_predict_particles != 1) {
-    phdslam_set_error("n_predict_particles != 1 is not built yet");
+  if (c->n_predict_particles < 1 || c->n_predict_particles > 64) {
+    phdslam_set_error("n_predict_particles must be in [1, 64]");
     return PHDSLAM_ERR_INVALID;
   }
   if (c->filter_type == 1 && (c->max_cardinality < 1 || c->max_cardinality + 1 >= PHD_LF_MAX)) {
@@ -175,8 +175,21 @@ static void free_state(phdslam* h) {
   if (h->red_host) cudaFreeHost(h->red_host);
 }
 
+/* Particle capacity.  With n_predict_particles = k > 1 every prediction multiplies the particle count by k and the loop
+ * resamples back to n_particles once the count exceeds 5 n_particles (src/main.cpp:1286): the count before a prediction
+ * is at most 5 n, so the largest reachable count is g^m n with g = k^subdivide_predict and g^(m-1) <= 5 < g^m. */
+static int particle_capacity(const phdslam_config_t& c, int n) {
+  if (c.n_predict_particles <= 1) return n;
+  long long g = 1;                              /* growth per time step: every sub-step of the prediction fans out */
+  for (int i = 0; i < std::max(c.subdivide_predict, 1); ++i) g *= c.n_predict_particles;
+  long long f = 1;
+  while (f <= 5) f *= g;
+  return (int)std::min<long long>(f * n, 0x7fffffffLL);
+}
+
 static int alloc_state(phdslam* h) {
-  const size_t n = (size_t)h->n_local;
+  h->n_cap = (h->world > 1) ? h->n_local : particle_capacity(h->cfg, h->n_local);
+  const size_t n = (size_t)h->n_cap;
   const size_t C = (size_t)h->Cmax;
   for (int b = 0; b < 2; ++b) {
     CK(cudaMalloc(&h->pose[b], 6 * n * sizeof(float)));
@@ -321,8 +334,9 @@ extern "C" void phdslam_destroy(phdslam_t* h) {
 
 extern "C" int phdslam_set_config(phdslam_t* h, const phdslam_config_t* cfg) {
   if (cfg->n_particles != h->cfg.n_particles || ((cfg->max_components + 31) & ~31) != h->Cmax ||
-      cfg->filter_type != h->cfg.filter_type) {
-    phdslam_set_error("n_particles / max_components / filter_type are fixed at create time");
+      cfg->filter_type != h->cfg.filter_type || cfg->n_predict_particles != h->cfg.n_predict_particles ||
+      (cfg->n_predict_particles > 1 && cfg->subdivide_predict != h->cfg.subdivide_predict)) {
+    phdslam_set_error("n_particles / max_components / filter_type / n_predict_particles are fixed at create time");
     return PHDSLAM_ERR_INVALID;
   }
   int rc = validate_config(cfg);
@@ -371,6 +385,10 @@ extern "C" int phdslam_dist_init(phdslam_t* h, int rank, int world, const void* 
   ncclComm_t comm;
   CKN(ncclCommInitRank(&comm, world, id, rank));
   h->nccl_comm = (void*)comm;
+  if (world > 1 && h->cfg.n_predict_particles > 1) {
+    phdslam_set_error("n_predict_particles > 1 changes the particle count every step and is single-GPU only");
+    return PHDSLAM_ERR_INVALID;
+  }
   h->rank = rank;
   h->world = world;
   free_state(h);
@@ -416,8 +434,36 @@ static int check_err_flag(phdslam* h) {
 }
 
 /* ---- predict ---- */
+/* "shotgun" prediction (src/phdfilter.cu:1091, 796-797, 1185-1238): every particle becomes k particles (same map,
+ * cardinality and resample index, log-weight - log k); the predict kernel then moves each of them with its own noise */
+static int fan_out(phdslam* h) {
+  const int k = h->cfg.n_predict_particles, n = h->n_local;
+  const long long n_out = (long long)n * k;
+  if (n_out > h->n_cap) {
+    phdslam_set_error("n_predict_particles: particle count exceeds the capacity (resample before predicting again)");
+    return PHDSLAM_ERR_CAPACITY;
+  }
+  const int b = h->cur;
+  fanout_kernel<<<cdiv(n_out, 256), 256, 0, h->stream>>>((int)n_out, k, phd_safe_log((float)k), h->logw, h->dlogw, h->resample_idx,
+                                                        h->n_in, h->ancestors);
+  LAUNCH_CHECK(h);
+  resample_gather_kernel<<<cdiv(n_out, 8), 256, 0, h->stream>>>(h->ancestors, (int)n_out, 0, n, (int)n_out, h->pose[b], h->pose[b ^ 1],
+                                                              h->count[b], h->count[b ^ 1], h->map[b], h->map[b ^ 1],
+                                                              h->card[b], h->card[b ^ 1], h->Cmax, h->n_card);
+  LAUNCH_CHECK(h);
+  std::swap(h->logw, h->dlogw);             /* both are n_cap floats; dlogw is per-update scratch */
+  std::swap(h->resample_idx, h->n_in);      /* both are n_cap ints; n_in is per-update scratch */
+  h->cur ^= 1;
+  h->n_local = h->n_global = (int)n_out;
+  return 0;
+}
+
 extern "C" int phdslam_predict(phdslam_t* h, const float* control, const double* draws) {
   CK(cudaSetDevice(h->device));
+  if (h->cfg.n_predict_particles > 1) {
+    int rcf = fan_out(h);
+    if (rcf) return rcf;
+  }
   const int n = h->n_local;
   const int per = (h->cfg.motion_type == 1) ? 2 : 3;
   const double* ddev = nullptr;
@@ -804,8 +850,8 @@ extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms,
   CK(cudaSetDevice(h->device));
   const int n = h->n_local;
   if (n_new < 0) n_new = h->n_global;
-  if (n_new != h->n_global) {
-    phdslam_set_error("resampling to a different particle count is not supported (device state is fixed-size)");
+  if (n_new != h->n_global && (h->world > 1 || n_new > h->n_cap || n_new < 1)) {
+    phdslam_set_error("resampling to a different particle count needs a single GPU and n_new within the particle capacity");
     return PHDSLAM_ERR_INVALID;
   }
   const double* udev = nullptr;
@@ -858,12 +904,15 @@ extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms,
     }
   }
   /* offspring of this rank whose ancestor is local (remote ones get -1 and are skipped by the gather) */
-  resample_search_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->cdf_excl, n, base, total, n_new, h->offset, n, h->offset, udev,
-                                                            sysmode, h->resample_calls, h->dc.seed_lo, h->dc.seed_hi, h->ancestors);
+  /* offspring owned by this rank: n (= its share of n_new), or all n_new on a single GPU (which may differ from n:
+   * the down-sampling after "shotgun" predictions, src/main.cpp:1286-1289) */
+  const int n_off = (h->world > 1) ? n : n_new;
+  resample_search_kernel<<<cdiv(n_off, 256), 256, 0, h->stream>>>(h->cdf_excl, n, base, total, n_new, h->offset, n_off, h->offset, udev,
+                                                                sysmode, h->resample_calls, h->dc.seed_lo, h->dc.seed_hi, h->ancestors);
   LAUNCH_CHECK(h);
-  resample_gather_kernel<<<cdiv(n, 8), 256, 0, h->stream>>>(h->ancestors, n, h->offset, n, n, h->pose[b], h->pose[b ^ 1],
-                                                          h->count[b], h->count[b ^ 1], h->map[b], h->map[b ^ 1],
-                                                          h->card[b], h->card[b ^ 1], h->Cmax, h->n_card);
+  resample_gather_kernel<<<cdiv(n_off, 8), 256, 0, h->stream>>>(h->ancestors, n_off, h->offset, n, n_off, h->pose[b], h->pose[b ^ 1],
+                                                              h->count[b], h->count[b ^ 1], h->map[b], h->map[b ^ 1],
+                                                              h->card[b], h->card[b ^ 1], h->Cmax, h->n_card);
   LAUNCH_CHECK(h);
   if (h->world > 1) {
     /* migration: ring of shifts; in shift k this rank serves rank+k and is served by rank-k.  Both ends derive
@@ -917,15 +966,16 @@ extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms,
       h->tim.migrated_in += (unsigned long long)cnt_in;
     }
   }
-  fill_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->logw, n, -phd_logf((float)n_new));
+  fill_kernel<<<cdiv(n_off, 256), 256, 0, h->stream>>>(h->logw, n_off, -phd_logf((float)n_new));
   LAUNCH_CHECK(h);
-  CK(cudaMemcpyAsync(h->resample_idx, h->ancestors, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->resample_idx, h->ancestors, (size_t)n_off * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaEventRecord(h->ev[10], h->stream));
-  if (ancestors_out) CK(cudaMemcpyAsync(ancestors_out, h->ancestors, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (ancestors_out) CK(cudaMemcpyAsync(ancestors_out, h->ancestors, (size_t)n_off * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   cudaEventElapsedTime(&h->tim.resample_ms, h->ev[9], h->ev[10]);
   h->cur ^= 1;
   h->resample_calls++;
+  if (h->world == 1) h->n_local = h->n_global = n_new;
   return 0;
 }
 
@@ -1187,12 +1237,14 @@ extern "C" int phdslam_snapshot(phdslam_t* h) {
   const size_t n = h->n_local, C = h->Cmax;
   CK(cudaStreamSynchronize(h->stream));
   if (!h->snap_pose) {
-    CK(cudaMalloc(&h->snap_pose, 6 * n * sizeof(float)));
-    CK(cudaMalloc(&h->snap_count, n * sizeof(int)));
-    CK(cudaMalloc(&h->snap_map, n * PHD_MAP_PLANES * C * sizeof(float)));
-    CK(cudaMalloc(&h->snap_logw, n * sizeof(float)));
-    if (h->n_card) CK(cudaMalloc(&h->snap_card, n * h->n_card * sizeof(float)));
+    const size_t nc = h->n_cap;
+    CK(cudaMalloc(&h->snap_pose, 6 * nc * sizeof(float)));
+    CK(cudaMalloc(&h->snap_count, nc * sizeof(int)));
+    CK(cudaMalloc(&h->snap_map, nc * PHD_MAP_PLANES * C * sizeof(float)));
+    CK(cudaMalloc(&h->snap_logw, nc * sizeof(float)));
+    if (h->n_card) CK(cudaMalloc(&h->snap_card, nc * h->n_card * sizeof(float)));
   }
+  h->snap_n = (int)n;
   CK(cudaMemcpy(h->snap_pose, h->pose[h->cur], 6 * n * sizeof(float), cudaMemcpyDeviceToDevice));
   CK(cudaMemcpy(h->snap_count, h->count[h->cur], n * sizeof(int), cudaMemcpyDeviceToDevice));
   CK(cudaMemcpy(h->snap_map, h->map[h->cur], n * PHD_MAP_PLANES * C * sizeof(float), cudaMemcpyDeviceToDevice));
@@ -1205,6 +1257,7 @@ extern "C" int phdslam_snapshot(phdslam_t* h) {
 extern "C" int phdslam_restore(phdslam_t* h) {
   CK(cudaSetDevice(h->device));
   if (!h->snap_pose) return PHDSLAM_ERR_INVALID;
+  if (h->world == 1) h->n_local = h->n_global = h->snap_n;
   const size_t n = h->n_local, C = h->Cmax;
   CK(cudaMemcpyAsync(h->pose[h->cur], h->snap_pose, 6 * n * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemcpyAsync(h->count[h->cur], h->snap_count, n * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));

@@ -57,6 +57,7 @@ struct phdslam {
   cudaStream_t stream;
   int rank, world;
   int n_global, n_local, offset;
+  int n_cap;             /* particle capacity of every per-particle array (> n_particles only for n_predict_particles > 1) */
   int Cmax, n_card, Smax;
   int Scap_max, Scap_pinned;
   int Scap;              /* shared-memory candidate capacity of merge_fast_kernel, adapted from the last step */
@@ -72,6 +73,7 @@ struct phdslam {
   /* snapshot for bench */
   float* snap_pose; int* snap_count; float* snap_map; float* snap_card; float* snap_logw;
   unsigned snap_predict_calls, snap_resample_calls;
+  int snap_n;
   /* per-step scratch */
   uint8_t* cls;                      /* [n_local][Cmax] in-range class */
   int* n_in;                         /* [n_local] */

@@ -344,12 +344,13 @@ class PhdSlam(object):
         _check(self.lib.phdslam_estimate(self._h, C.byref(e)))
         return e
 
-    def resampleParticles(self, uniforms=None):
-        """uniforms: n_global+1 injected draws (the same array on every rank), or None for the counter-based RNG."""
-        n = self.n_local
+    def resampleParticles(self, uniforms=None, n_new=-1):
+        """uniforms: n_new+1 injected draws (the same array on every rank), or None for the counter-based RNG.
+        n_new != current count (single GPU only): the down-sampling of run_synth after "shotgun" predictions."""
+        n = self.n_local if n_new < 0 else n_new
         u = None if uniforms is None else np.ascontiguousarray(uniforms, dtype=np.float64)
         anc = np.empty(n, dtype=np.int32)
-        _check(self.lib.phdslam_resample(self._h, -1, _ptr(u), anc.ctypes.data))
+        _check(self.lib.phdslam_resample(self._h, n_new, _ptr(u), anc.ctypes.data))
         return anc
 
     def step(self, step_index, control, Z):

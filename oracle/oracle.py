@@ -121,10 +121,10 @@ class Oracle(object):
         self.lib.oracle_estimate(self._h, C.byref(e))
         return e
 
-    def resampleParticles(self, uniforms=None, literal=False):
+    def resampleParticles(self, uniforms=None, literal=False, n_new=-1):
         u = None if uniforms is None else np.ascontiguousarray(uniforms, dtype=np.float64)
-        anc = np.empty(self.n, dtype=np.int32)
-        self.lib.oracle_resample(self._h, -1, _ptr(u), int(literal), anc.ctypes.data)
+        anc = np.empty(self.n if n_new < 0 else n_new, dtype=np.int32)
+        self.lib.oracle_resample(self._h, n_new, _ptr(u), int(literal), anc.ctypes.data)
         return anc
 
     def step(self, step_index, control, Z):

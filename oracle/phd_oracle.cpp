@@ -142,9 +142,26 @@ extern "C" void oracle_set_cardinalities(phd_oracle_t* o, const float* in) {
  * Noise draws: injected (reference call order, :1113-1117 / :1148-1152) or Philox4x32-10. */
 extern "C" void oracle_predict(phd_oracle_t* o, const float* control, const double* draws) {
   const phdslam_config_t& c = o->cfg;
-  if (c.n_predict_particles != 1) {
-    fprintf(stderr, "oracle: n_predict_particles != 1 is not on the path yet\n");
-    abort();
+  if (c.n_predict_particles > 1) {
+    /* "shotgun" prediction (:1091, :796-797, :1185-1238): every particle spawns nPredictParticles predictions
+     * (prediction j descends from particle j / k); maps, cardinalities and resample indices are duplicated and the
+     * weights scaled down by k */
+    const int k = c.n_predict_particles, n0 = (int)o->states.size();
+    std::vector<Pose> ns((size_t)n0 * k);
+    std::vector<float> nw((size_t)n0 * k);
+    std::vector<std::vector<G2>> nm((size_t)n0 * k);
+    std::vector<std::vector<float>> nc((size_t)n0 * k);
+    std::vector<int> nr((size_t)n0 * k);
+    const float logk = phd_safe_log((float)k);
+    for (int j = 0; j < n0 * k; ++j) {
+      const int i = j / k;
+      ns[j] = o->states[i];
+      nw[j] = o->weights[i] - logk;              /* :1208 */
+      nm[j] = o->maps[i];
+      nc[j] = o->card[i];
+      nr[j] = o->resample_idx[i];
+    }
+    o->states.swap(ns); o->weights.swap(nw); o->maps.swap(nm); o->card.swap(nc); o->resample_idx.swap(nr);
   }
   int n = (int)o->states.size();
   float dt = c.dt / (float)c.subdivide_predict; /* REAL dt = dev_config.dt/dev_config.subdividePredict */
