@@ -136,12 +136,11 @@ int main(int argc, char** argv) {
 
   phdslam_t* h = nullptr;
   CHECK(phdslam_create(&cfg, 0, &h));
-  const int P = phdslam_n_local(h);
   const int n_card = cfg.max_cardinality + 1;
-  std::vector<phdslam_pose_t> poses(P);
-  std::vector<float> logw(P);
-  std::vector<int> ridx(P);
-  std::vector<float> card((size_t)(cfg.filter_type == 1 ? n_card : 1));
+  std::vector<phdslam_pose_t> poses;
+  std::vector<float> logw;
+  std::vector<int> ridx;
+  std::vector<float> card((size_t)(cfg.filter_type == 1 ? n_card : 1)), all_card;
   std::vector<phdslam_gaussian2d_t> map_est(65536);
   float current_u[2] = {0.0f, 0.0f};                              /* main.cpp:1166-1168 */
   printf("STARTING SIMULATION\n");
@@ -178,10 +177,25 @@ int main(int argc, char** argv) {
     phdslam_estimate_t est;
     int resampled = 0;
     int rc = phdslam_step(h, step_index, current_u, z, M, cfg.measurement_fields, &est, &resampled);
-    /* state export: recoverSlamState output + particle set (main.cpp:1274-1279) */
+    /* state export: recoverSlamState output + particle set (main.cpp:1274-1279); the particle count changes from
+     * step to step when n_predict_particles > 1 */
+    const int P = phdslam_n_local(h);
+    poses.resize(P); logw.resize(P); ridx.resize(P);
     CHECK(phdslam_get_poses(h, poses.data()));
     CHECK(phdslam_get_log_weights(h, logw.data()));
     CHECK(phdslam_get_resample_idx(h, ridx.data()));
+    if (cfg.filter_type == 1 && est.map_particle >= 0) {
+      /* cardinality distribution of the maximum-weight particle (recoverSlamState, main.cpp:357-361); the estimate was
+       * taken before the resampling of this step, so look the particle up among the offspring */
+      int j = -1;
+      for (int i = 0; i < P && j < 0; ++i)
+        if (ridx[i] == est.map_particle) j = i;
+      if (j >= 0) {
+        all_card.resize((size_t)P * n_card);
+        CHECK(phdslam_get_cardinalities(h, all_card.data()));
+        std::copy(all_card.begin() + (size_t)j * n_card, all_card.begin() + (size_t)(j + 1) * n_card, card.begin());
+      }
+    }
     int n_map = 0;
     if (cfg.map_estimate & 3) {
       int which = (cfg.map_estimate & 2) ? 2 : 1;
