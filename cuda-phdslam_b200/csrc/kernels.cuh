@@ -329,7 +329,7 @@ struct UpdArgs {
 };
 
 __host__ __device__ static inline size_t update_smem_bytes(int Cmax) {
-  return ((size_t)UPD_FLOATS_PER_COMP * Cmax + 6 * PHD_MAX_MEAS + 64) * sizeof(float);
+  return ((size_t)UPD_FLOATS_PER_COMP * Cmax + 11 * PHD_MAX_MEAS + 64) * sizeof(float);
 }
 
 /* =========================================================================================== */
@@ -739,7 +739,8 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
   float* s_zb = s_zr + PHD_MAX_MEAS;
   float* s_zl = s_zb + PHD_MAX_MEAS;
   float* s_L = s_zl + PHD_MAX_MEAS;
-  float* s_ds = s_L + PHD_MAX_MEAS;     /* PHD_MAX_MEAS; the remaining slack covers even padding */
+  float* s_ds = s_L + PHD_MAX_MEAS;
+  float* s_bb = s_ds + PHD_MAX_MEAS;    /* 5 x PHD_MAX_MEAS: birth covariance (b0, b1, b3) and mean per measurement; the remaining slack covers even padding */
   __shared__ int s_wcnt[UPD_WARPS];
   __shared__ int s_ncand;
   __shared__ float s_cphd_scal[2];
@@ -875,7 +876,21 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
     for (int f = 0; f < UPD_NF; ++f) rec[2 * f] = 0.0f;
     rec[2 * F_BASE] = PHD_LOG0;
   }
-  for (int m = tid; m < M; m += UPD_THREADS) s_tmp[C + m] = c.birth_weight;
+  for (int m = tid; m < M; m += UPD_THREADS) {
+    s_tmp[C + m] = c.birth_weight;
+    /* birth term of measurement m (host loop :3468-3507): one thread per measurement, not one lane per warp round */
+    const float zr = s_zr[m], zb = s_zb[m];
+    float sn, cs;
+    phd_sincosf(pth + zb, &sn, &cs);
+    const float bdx = zr * cs;
+    const float bdy = zr * sn;
+    const float J0 = bdx / zr, J1 = bdy / zr, J2 = -bdy, J3 = bdx;
+    s_bb[m] = J0 * J0 * c.bvar_r + J2 * J2 * c.bvar_b;
+    s_bb[PHD_MAX_MEAS + m] = J0 * J1 * c.bvar_r + J2 * J3 * c.bvar_b;
+    s_bb[2 * PHD_MAX_MEAS + m] = J1 * J1 * c.bvar_r + J3 * J3 * c.bvar_b;
+    s_bb[3 * PHD_MAX_MEAS + m] = px + bdx;
+    s_bb[4 * PHD_MAX_MEAS + m] = py + bdy;
+  }
   __syncthreads();
 
   /* predicted cardinality (:2133-2186) and, for scheme 1, the prior / non-detect weight sums */
@@ -979,28 +994,21 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
     float dsum = warp_butterfly_sum(wacc.x + wacc.y);
     /* birth term of measurement m (host loop :3468-3507, normalised at :2232-2242) */
     if (lane == 0) {
-      float theta = pth + zb;
-      float sn, cs;
-      phd_sincosf(theta, &sn, &cs);
-      float bdx = zr * cs;
-      float bdy = zr * sn;
-      float J0 = bdx / zr, J1 = bdy / zr, J2 = -bdy, J3 = bdx;
-      float b0 = J0 * J0 * c.bvar_r + J2 * J2 * c.bvar_b;
-      float b1 = J0 * J1 * c.bvar_r + J2 * J3 * c.bvar_b;
-      float b3 = J1 * J1 * c.bvar_r + J3 * J3 * c.bvar_b;
+      const float b0 = s_bb[m], b1 = s_bb[PHD_MAX_MEAS + m], b3 = s_bb[2 * PHD_MAX_MEAS + m];
+      const float bmx = s_bb[3 * PHD_MAX_MEAS + m], bmy = s_bb[4 * PHD_MAX_MEAS + m];
       float lb = dead ? PHD_LOG0 : c.log_birth_weight;
       float wb = phd_expf(lb - L);
       const int t = C + M * C + m;
       if (DENSE) {
         float* q = D + dense_index((size_t)t);
         st_stream(q, b0); st_stream(q + 64, b1); st_stream(q + 128, b1); st_stream(q + 192, b3);
-        st_stream(q + 256, px + bdx); st_stream(q + 320, py + bdy); st_stream(q + 384, wb);
+        st_stream(q + 256, bmx); st_stream(q + 320, bmy); st_stream(q + 384, wb);
       }
       if (!(wb < c.min_w)) {
         int slot = atomicAdd(&s_ncand, 1);
         if (slot < Smax) {
           cand[2 * slot] = make_float4(b0, b1, b1, b3);
-          cand[2 * slot + 1] = make_float4(px + bdx, py + bdy, wb, __int_as_float(t));
+          cand[2 * slot + 1] = make_float4(bmx, bmy, wb, __int_as_float(t));
         }
       }
       if (!CPHD) s_L[m] = L;
