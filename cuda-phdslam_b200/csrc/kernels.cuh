@@ -651,13 +651,19 @@ __device__ __forceinline__ void upd_chunk(const float2* __restrict__ rec, int jr
     acc = __fadd2_rn(acc, e);
   } else {
     float2 wt = STASH ? __fmul2_rn(stash[jr >> 1], nL2) : phd_expf2(__fadd2_rn(lw, nL2));
-    const float2 m0 = __ffma2_rn(lds2(rec + F_K2), i1, __ffma2_rn(lds2(rec + F_K0), i0, lds2(rec + F_MX)));
-    const float2 m1 = __ffma2_rn(lds2(rec + F_K3), i1, __ffma2_rn(lds2(rec + F_K1), i0, lds2(rec + F_MY)));
-    const float2 c0 = lds2(rec + F_CU0), c1 = lds2(rec + F_CU1), c2 = lds2(rec + F_CU2), c3 = lds2(rec + F_CU3);
     if (TAIL) {
       if (!v0) wt.x = 0.0f;
       if (!v1) wt.y = 0.0f;
     }
+    /* survivors of the prune (w >= minFeatureWeight, flags :2308-2319) go to the merge as 32-byte records; their slots
+     * are requested here and used after the dense stores, so that the round trip of the atomic is hidden */
+    const bool k0 = v0 && !(wt.x < min_w), k1 = v1 && !(wt.y < min_w);
+    const unsigned b0 = __ballot_sync(FULL_MASK, k0), b1 = __ballot_sync(FULL_MASK, k1);
+    int slot0 = 0;
+    if ((b0 | b1) && lane == 0) slot0 = atomicAdd(s_ncand, __popc(b0) + __popc(b1));
+    const float2 m0 = __ffma2_rn(lds2(rec + F_K2), i1, __ffma2_rn(lds2(rec + F_K0), i0, lds2(rec + F_MX)));
+    const float2 m1 = __ffma2_rn(lds2(rec + F_K3), i1, __ffma2_rn(lds2(rec + F_K1), i0, lds2(rec + F_MY)));
+    const float2 c0 = lds2(rec + F_CU0), c1 = lds2(rec + F_CU1), c2 = lds2(rec + F_CU2), c3 = lds2(rec + F_CU3);
     const int t = tbase_m + jr;                 /* term index of the first component of the pair */
     if (DENSE && v0) {
       if (even) {                               /* t is even: the pair sits in one 64-term block, 8-byte aligned */
@@ -676,13 +682,8 @@ __device__ __forceinline__ void upd_chunk(const float2* __restrict__ rec, int jr
       }
     }
     acc = __fadd2_rn(acc, wt);
-    /* survivors of the prune (w >= minFeatureWeight, flags :2308-2319) go to the merge as 32-byte records */
-    const bool k0 = v0 && !(wt.x < min_w), k1 = v1 && !(wt.y < min_w);
-    const unsigned b0 = __ballot_sync(FULL_MASK, k0), b1 = __ballot_sync(FULL_MASK, k1);
     if (b0 | b1) {
       const unsigned lt_mask = (1u << lane) - 1u;
-      int slot0 = 0;
-      if (lane == 0) slot0 = atomicAdd(s_ncand, __popc(b0) + __popc(b1));
       slot0 = __shfl_sync(FULL_MASK, slot0, 0);
       if (k0) {
         int slot = slot0 + __popc(b0 & lt_mask);
