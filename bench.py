@@ -225,6 +225,7 @@ def run_ours(args, wl):
         filt.step(1, u, Z)
     barrier()
     l0 = filt.timings().launches
+    mig0 = filt.timings().migrated_in
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -251,10 +252,25 @@ def run_ours(args, wl):
     launches = filt.timings().launches - l0
     # restore() launches no kernels (cudaMemcpyAsync only), so `launches` counts the timed steps' kernels
     dev_total, wall_total = float(np.sum(dev_ms)), float(np.sum(wall_ms))
+    exchange = None
     if world > 1:
         tt = torch.tensor([dev_total, wall_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dev_total, wall_total = float(tt[0]), float(tt[1])
+        # global resampling: particles this rank received over NVLink (pose 24 B + size 4 B + ancestor 4 B + the map block
+        # of 6 planes x Cmax floats [+ cardinality]) against the time of the whole resampling phase (CDF scan, search,
+        # local gather and the send/recv ring), max over ranks
+        cmax = (wl["max_components"] + 31) // 32 * 32
+        rec = 32 + 24 * cmax + (4 * (wl.get("max_cardinality", -1) + 1) if wl.get("filter_type") == 1 else 0)
+        mig = float(filt.timings().migrated_in - mig0) / max(args.steps, 1)
+        rs = float(np.mean([o[3] for o in other]))
+        mm = torch.tensor([mig, rs], device="cuda", dtype=torch.float64)
+        dist.all_reduce(mm, op=dist.ReduceOp.MAX)
+        mig, rs = float(mm[0]), float(mm[1])
+        exchange = {"migrated_particles_per_step_max_rank": mig, "bytes_per_step_max_rank": mig * rec, "resample_phase_ms": rs,
+                    "achieved_GBps_lower_bound": (mig * rec / (rs * 1e-3) / 1e9) if rs > 0 else None,
+                    "nvlink5_peak_GBps_per_direction": 900.0,
+                    "note": "bytes received by the busiest rank / the whole resampling phase (scan + search + gather + ring)"}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -275,6 +291,20 @@ def run_ours(args, wl):
             traffic = json.load(open(tp)).get(args.workload, {}).get("update_dense_kernel_dram_bytes_per_launch")
         except Exception:
             traffic = None
+    # the prune + merge kernel is not HBM-bound (175 MB of DRAM reads per 8192 particles): its bound is the SM issue rate.
+    # warp-instructions per particle come from the committed ncu capture, the duration is measured live.
+    merge_roof = None
+    try:
+        wi = json.load(open(tp)).get(args.workload, {}).get("merge_fast_warp_instructions_per_particle")
+        if wi and clocks and clocks.get("sm_max_mhz"):
+            mrg = float(np.mean(mrg_ms))
+            peak_issue = 148 * 4 * clocks["sm_max_mhz"] * 1e6 / 1e9          # G warp-instructions/s: 148 SMs x 4 schedulers
+            ach = float(P) * wi / (mrg * 1e-3) / 1e9
+            merge_roof = {"bound": "issue", "kernel": "merge_fast_kernel", "achieved": ach, "peak": peak_issue,
+                          "unit": "G warp-instr/s", "frac": ach / peak_issue, "kernel_ms": mrg,
+                          "warp_instructions_per_particle": wi}
+    except Exception:
+        merge_roof = None
     cpu_rate, cores, sample, _, _ = cpu_oracle_rate(wl) if not args.no_cpu_baseline else (None, 0, "skipped", 0, 0)
     oth = np.mean(np.array(other), axis=0)
     line = {
@@ -299,6 +329,10 @@ def run_ours(args, wl):
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if exchange is not None:
+        line["exchange"] = exchange
+    if merge_roof is not None:
+        line["roofline_merge"] = merge_roof
     print(json.dumps(line))
     sys.stdout.flush()
 
