@@ -362,10 +362,39 @@ __device__ __forceinline__ float cphd_logd(double v) {
   return phd_logf((float)mant) + (float)ex * 0.693147182f;
 }
 /* log-sum-exp over i in [0, n) of f(i) with the canonical warp shape (oracle: lse_warp); full warp */
+#define CPHD_LSE_R 5               /* terms of up to 64 * CPHD_LSE_R elements are evaluated once and kept in registers */
 template <class F>
 __device__ __forceinline__ float cphd_lse_warp(int n, F f) {
   if (n <= 0) return PHD_LOG0;
   const int lane = lane_id();
+  if (n <= 64 * CPHD_LSE_R) {
+    /* same maximum, same per-lane summation order (elements 2 lane + 64 r and the one after it) as the loops below */
+    float v0[CPHD_LSE_R], v1[CPHD_LSE_R];
+    float mxc = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < CPHD_LSE_R; ++r) {
+      v0[r] = -INFINITY;
+      v1[r] = -INFINITY;
+      if (64 * r < n) {
+        const int i = 2 * lane + 64 * r;
+        if (i < n) v0[r] = f(i);
+        if (i + 1 < n) v1[r] = f(i + 1);
+        mxc = fmaxf(mxc, fmaxf(v0[r], v1[r]));
+      }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) mxc = fmaxf(mxc, __shfl_xor_sync(FULL_MASK, mxc, off));
+    float c0 = 0.0f, c1 = 0.0f;
+#pragma unroll
+    for (int r = 0; r < CPHD_LSE_R; ++r) {
+      if (64 * r < n) {
+        const int i = 2 * lane + 64 * r;
+        if (i < n) c0 = c0 + phd_expf(v0[r] - mxc);
+        if (i + 1 < n) c1 = c1 + phd_expf(v1[r] - mxc);
+      }
+    }
+    return phd_safe_log(warp_butterfly_sum(c0 + c1)) + mxc;
+  }
   float mx = -INFINITY;
   for (int i = lane; i < n; i += 32) mx = fmaxf(mx, f(i));
 #pragma unroll
@@ -390,15 +419,16 @@ __device__ __forceinline__ void cphd_esf_warp_t(const double* __restrict__ x, in
 #pragma unroll
   for (int i = 0; i < KR; ++i) E[i] = 0.0;
   if (lane == 0) E[0] = 1.0;
-  for (int n = 0; n < M; ++n) {
-    if (n == skip) continue;
-    const double xn = x[n];
+  auto fold = [&](double xn) {
     double below = __shfl_up_sync(FULL_MASK, E[KR - 1], 1);
     if (lane == 0) below = 0.0;
 #pragma unroll
     for (int i = KR - 1; i >= 1; --i) E[i] = __dadd_rn(E[i], __dmul_rn(xn, E[i - 1]));
     E[0] = __dadd_rn(E[0], __dmul_rn(xn, below));
-  }
+  };
+  const int n_skip = (skip < 0) ? 0 : skip;
+  for (int n = 0; n < n_skip; ++n) fold(x[n]);
+  for (int n = skip + 1; n < M; ++n) fold(x[n]);
 #pragma unroll
   for (int i = 0; i < KR; ++i) {
     const int k = KR * lane + i;

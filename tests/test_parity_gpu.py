@@ -404,3 +404,40 @@ def test_update_merge_overlap_gives_identical_state():
         sizes, maps = g.get_maps()
         res.append((sizes.copy(), maps.tobytes(), g.log_weights.tobytes()))
     assert (res[0][0] == res[1][0]).all() and res[0][1] == res[1][1] and res[0][2] == res[1][2]
+
+
+def test_full_size_step_matches_oracle_on_a_particle_subset():
+    """BASELINE configs[2] at full size (65 536 particles x 256 components x 64 measurements): particles are independent
+    through predict / update / prune / merge, so the oracle run on 24 of them (same poses, same maps, the same Philox
+    counters are NOT needed: the control noise is injected) must reproduce the device maps of those particles bit for
+    bit; the cross-particle outputs are checked through their invariants."""
+    Pn, C, M = 65536, 256, 64
+    cfg = S.scene_config(Pn, C, M, max_components=384)
+    sc = S.make_scene(Pn, C, M, seed=0)
+    g = P.PhdSlam(cfg)
+    S.load_scene(g, sc)
+    g.phdUpdateSynth(sc["Z"])
+    sizes, maps = g.get_maps()
+    w = g.log_weights.astype(np.float64)
+    assert abs(np.exp(w).sum() - 1.0) < 1e-4
+    assert sizes.min() > C // 2 and sizes.max() <= C + M      # neighbouring landmarks of this dense scene merge
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    pick = np.r_[0:8, 30000:30008, Pn - 8:Pn]
+    sub_cfg = S.scene_config(len(pick), C, M, max_components=384)
+    o = O.Oracle(sub_cfg, threads=os.cpu_count() or 1)
+    o.poses = sc["poses"][pick]
+    o.log_weights = sc["log_weights"][pick]
+    n_all = len(sc["maps"]) // Pn
+    o.set_maps(sc["sizes"][pick], np.concatenate([sc["maps"][p * n_all:(p + 1) * n_all] for p in pick]))
+    o.phdUpdateSynth(sc["Z"])
+    os_, om = o.get_maps()
+    assert (os_ == sizes[pick]).all()
+    gm = np.concatenate([maps[off[p]:off[p + 1]] for p in pick])
+    assert gm.tobytes() == om.tobytes(), "maps of the sampled particles are expected to be bit-identical"
+    # the particle log-weight increments: un-normalised differences agree with the oracle's
+    ow = o.log_weights.astype(np.float64)
+    gw = w[pick]
+    np.testing.assert_allclose((gw - gw[0]), (ow - ow[0]), rtol=1e-4, atol=2e-4)
+    anc = g.resampleParticles()
+    assert (np.diff(anc) >= 0).all() and anc.min() >= 0 and anc.max() < Pn
+    assert (g.map_sizes == sizes[anc]).all()
