@@ -40,6 +40,9 @@ WORKLOADS = {
     # BASELINE.json configs[3], one GPU's shard (1M particles over 8 GPUs): CPHD with the cardinality distribution
     "synthetic_16384x128x50_cphd": dict(P=16384, C=128, M=50, max_components=256, filter_type=1, max_cardinality=255),
     "synthetic_131072x128x50_cphd": dict(P=131072, C=128, M=50, max_components=256, filter_type=1, max_cardinality=255),
+    # north_star target sentence: "the GM-PHD update at 1M particles on one GPU" (configs[3]'s particle count and C x M
+    # shape on ONE B200; the 184 GB of dense update terms stream through the 32 GB update buffer in batches)
+    "synthetic_1048576x128x50_phd": dict(P=1048576, C=128, M=50, max_components=256),
     # BASELINE.json configs[4] per-GPU shape at a size one GPU's update buffer streams through: global resampling every step
     "synthetic_32768x128x100_phd": dict(P=32768, C=128, M=100, max_components=256, resample_threshold=1.0),
     "synthetic_262144x128x100_phd": dict(P=262144, C=128, M=100, max_components=256, resample_threshold=1.0),
@@ -63,17 +66,49 @@ def measured_peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).
+    A timed step lasts ~15 ms, far below nvidia-smi's 100 ms loop period, so the sampler polls NVML directly
+    (pynvml, every 2 ms, only while `active` is set around a timed step); nvidia-smi is the fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.rows = []          # (sm_mhz, reasons bitmask) per NVML sample
+        self.smi_rows = []
         self.proc = None
+        self.nvml = None
+        self.handle = None
+        self.sm_max = None
+        self.active = False
+        self.stop_flag = False
+        self.t = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v for v in vis.split(",") if v.strip().isdigit()]
+            h = pynvml.nvmlDeviceGetHandleByIndex(int(ids[self.index]) if self.index < len(ids) else self.index)
+        return pynvml, h
 
     def start(self):
+        try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.sm_max = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -83,29 +118,60 @@ class ClockSampler(object):
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            if self.active:
+                try:
+                    sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                    try:
+                        rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                    except Exception:
+                        rs = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                    if self.active:
+                        self.rows.append((sm, rs))
+                except Exception:
+                    pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.smi_rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        self.stop_flag = True
+        if self.nvml is not None:
+            if self.t:
+                self.t.join(timeout=2)
+            n = self.nvml
+            names = [("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown),
+                     ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", n.nvmlClocksThrottleReasonSwThermalSlowdown),
+                     ("sw_power_cap", n.nvmlClocksThrottleReasonSwPowerCap),
+                     ("hw_power_brake_slowdown", n.nvmlClocksThrottleReasonHwPowerBrakeSlowdown)]
+            reasons = sorted(nm for nm, bit in names if any(r[1] & bit for r in self.rows))
+            sm = [r[0] for r in self.rows]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max, "reasons": reasons,
+                    "samples": len(sm), "how": "NVML polled every 2 ms inside the timed steps only"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             pass
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = self.smi_rows
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 9:
                 for k, nm in enumerate(names):
                     if r[5 + k].lower().startswith("active"):
                         reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "how": "nvidia-smi -lms 100 over the timed loop"}
 
 
 def dist_env():
@@ -235,12 +301,14 @@ def run_ours(args, wl):
         filt.restore()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.active = True
         t0 = time.perf_counter()
         e0.record(stream)
         est, res = filt.step(1, u, Z)
         e1.record(stream)
         barrier()
         t1 = time.perf_counter()
+        sampler.active = sampler.proc is not None     # NVML samples only inside timed steps; nvidia-smi runs throughout
         n_resampled += int(res)
         dev_ms.append(e0.elapsed_time(e1))
         wall_ms.append((t1 - t0) * 1e3)

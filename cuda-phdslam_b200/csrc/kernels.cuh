@@ -1874,7 +1874,6 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
       crec[2 * r] = r0;
       crec[2 * r + 1] = r1;
       P1[i] = (unsigned short)r;     /* candidate index -> rank */
-      own[r] = (unsigned short)MF_NONE;
       tmax = fmaxf(tmax, r1.w);
       xmin = fminf(xmin, r1.x); xmax = fmaxf(xmax, r1.x);
       ymin = fminf(ymin, r1.y); ymax = fmaxf(ymax, r1.y);
@@ -1937,7 +1936,10 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
     __syncthreads();
     for (int r = tid; r < n; r += MF_THREADS) {
       const float4 g = crec[2 * r + 1];
-      Gc[atomic_add_u16(cend, (int)cellr[r], 1u)] = make_float4(g.x, g.y, g.w, (float)r);
+      const unsigned cid = cellr[r];
+      const unsigned pos = atomic_add_u16(cend, (int)cid, 1u);
+      Gc[pos] = make_float4(g.x, g.y, g.w, (float)r);
+      own[pos] = (unsigned short)cid;        /* the cell of every cell-order position, for the pair phase */
       HD[r] = MF_NONE;
     }
     __syncthreads();                                       /* cend[c] is now the END of cell c */
@@ -1979,101 +1981,61 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
           }
         }
       };
-      const int Ge = (G + 1) & ~1;                                     /* pairs of cells are dealt to the warps round-robin */
-      int cy = 0, cx = 2 * warp;
-      while (true) {
-        while (cx >= Ge) {
-          cx -= Ge;
-          ++cy;
-        }
-        if (cy >= G) break;
-        const unsigned short* row = cend + cy * MRG_GMAX;
-        const int cxa = min(cx + 1, G - 1);                          /* last A cell */
-        const int a_beg = (cy + cx > 0) ? row[cx - 1] : 0;
-        const int na = (int)row[cxa] - a_beg;
-        if (na > 0) {
-          const int len1 = (int)row[min(cxa + 1, G - 1)] - a_beg;      /* the A cells (first) + the cell to their right */
-          int beg2 = 0, len2 = 0;
-          if (cy + 1 < G) {
-            beg2 = row[MRG_GMAX + max(cx - 1, 0) - 1];
-            len2 = (int)row[MRG_GMAX + min(cxa + 1, G - 1)] - beg2;
+      /* one lane per B candidate (cell order, so the lanes of a warp share most of their neighbourhood); its A side is
+       * two contiguous runs of cell-order positions: the row above, cells cx-1..cx+1, and its own row from cell cx-1 up
+       * to itself.  Every unordered pair of candidates in neighbouring cells is gated exactly once. */
+      for (int b0 = warp * 32; b0 < n; b0 += MF_THREADS) {
+        const int pb = b0 + lane;
+        const bool valid = pb < n;
+        float4 B1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        int beg1 = 0, len1 = 0, beg2 = 0, tot = 0;
+        if (valid) {
+          B1 = Gc[pb];
+          const int cid = own[pb];                                     /* the cell of this position (phase E) */
+          const int cy = cid / MRG_GMAX, cx = cid - cy * MRG_GMAX;
+          const int left = cid - ((cx > 0) ? 1 : 0);
+          beg1 = (left > 0) ? cend[left - 1] : 0;
+          len1 = pb - beg1;
+          int len2 = 0;
+          if (cy > 0) {
+            const int up = left - MRG_GMAX;
+            beg2 = (up > 0) ? cend[up - 1] : 0;
+            len2 = (int)cend[cid - MRG_GMAX + ((cx + 1 < G) ? 1 : 0)] - beg2;
           }
-          const int tot = len1 + len2;
-          for (int q0 = 0; q0 < tot; q0 += 32) {
-            const int qq = q0 + lane;
-            const bool valid = qq < tot;
-            const int posb = (qq < len1) ? a_beg + qq : beg2 + (qq - len1);
-            const float4 B1 = Gc[valid ? posb : a_beg];
-            /* A candidates at cell-order offsets < min(na, qq) can pair with this B */
-            const int alim = valid ? min(na, qq) : 0;
-            for (int a0 = 0; a0 < na; a0 += MF_ACH) {
-              if (!__any_sync(FULL_MASK, a0 < alim)) break;             /* the rest of the A side precedes no B of this chunk */
-              const float4* Ap = Gc + a_beg + a0;
-              const int arem = alim - a0;
-              unsigned mask = 0u;
+          tot = len1 + len2;
+        }
+        const unsigned pbs = (unsigned)pb << 16;
+        int tmaxw = tot;
 #pragma unroll
-              for (int k = 0; k < MF_ACH; ++k) {
-                const float4 A1 = Ap[k];                                /* broadcast (reads past the A side are masked) */
-                const float gx = B1.x - A1.x, gy = B1.y - A1.y;
-                if ((k < arem) && (gx * gx + gy * gy <= gk * (B1.z + A1.z))) mask |= 1u << k;
-              }
-              /* compaction: every lane appends its pairs to the ring */
-              const int cntl = __popc(mask);
-              int inc = cntl;
-#pragma unroll
-              for (int off = 1; off < 32; off <<= 1) {
-                const int t = __shfl_up_sync(FULL_MASK, inc, off);
-                if (lane >= off) inc += t;
-              }
-              const int total = __shfl_sync(FULL_MASK, inc, 31);
-              const unsigned pb = (unsigned)posb << 16;
-              if (qn + total > MF_QUEUE) {        /* the ring cannot take this step: drain it first */
-                __syncwarp();
-                while (qn > 0) {
-                  const int cq = min(qn, 32);
-                  evaluate(cq);
-                  qh = (qh + cq) & (MF_QUEUE - 1);
-                  qn -= cq;
-                }
-                __syncwarp();
-              }
-              if (total > MF_QUEUE) {
-                /* a very dense neighbourhood: one pair per lane and round (the ring is empty here) */
-                while (__any_sync(FULL_MASK, mask != 0u)) {
-                  const bool has = mask != 0u;
-                  const unsigned hb = __ballot_sync(FULL_MASK, has);
-                  if (has) {
-                    q[(qh + __popc(hb & lt_mask)) & (MF_QUEUE - 1)] = (unsigned)(a_beg + a0 + (__ffs(mask) - 1)) | pb;
-                    mask &= mask - 1;
-                  }
-                  __syncwarp();
-                  evaluate(__popc(hb));
-                  __syncwarp();
-                }
-              } else if (total) {
-                int slot = qh + qn + inc - cntl;
-                for (unsigned m = mask; m; m &= m - 1) {
-                  q[slot & (MF_QUEUE - 1)] = (unsigned)(a_beg + a0 + (__ffs(m) - 1)) | pb;
-                  ++slot;
-                }
-                qn += total;
-                __syncwarp();
-                while (qn >= 32) {
-                  evaluate(32);
-                  qh = (qh + 32) & (MF_QUEUE - 1);
-                  qn -= 32;
-                }
-                __syncwarp();
-              }
+        for (int off = 16; off >= 1; off >>= 1) tmaxw = max(tmaxw, __shfl_xor_sync(FULL_MASK, tmaxw, off));
+        for (int t = 0; t < tmaxw; ++t) {
+          const int pa = (t < len1) ? beg1 + t : beg2 + (t - len1);
+          bool pass = false;
+          if (t < tot) {
+            const float4 A1 = Gc[pa];
+            const float gx = B1.x - A1.x, gy = B1.y - A1.y;
+            pass = gx * gx + gy * gy <= gk * (B1.z + A1.z);
+          }
+          const unsigned bal = __ballot_sync(FULL_MASK, pass);
+          if (bal) {
+            if (pass) q[(qh + qn + __popc(bal & lt_mask)) & (MF_QUEUE - 1)] = (unsigned)pa | pbs;
+            qn += __popc(bal);
+            __syncwarp();
+            if (qn >= 32) {
+              evaluate(32);
+              qh = (qh + 32) & (MF_QUEUE - 1);
+              qn -= 32;
+              __syncwarp();
             }
           }
         }
-        cx += 2 * MF_WARPS;
       }
       __syncwarp();
       evaluate(qn);
     }
     if (tid == 0) s_und = 0;
+    __syncthreads();
+    for (int r = tid; r < n; r += MF_THREADS) own[r] = (unsigned short)MF_NONE;   /* held the cells until here */
     __syncthreads();
 
     /* ---- G. ownership from the near lists: candidate r is owned by the lowest-ranked SEED among its lower-ranked near
