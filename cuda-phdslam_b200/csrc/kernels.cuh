@@ -1944,10 +1944,8 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
     }
     __syncthreads();                                       /* cend[c] is now the END of cell c */
 
-    /* ---- F. near pairs (:2802-2806).  Row by row (rows dealt to the warps), two cells at a time: every unordered pair
-     * of candidates in neighbouring cells is gated once.  The lanes hold the B side (the two cells, the cell to their
-     * right and the four cells below); the candidates of the two cells (the A side) are broadcast against them,
-     * MF_ACH at a time; B is paired with A only if it comes later in cell order.  Pairs that pass the gate are queued
+    /* ---- F. near pairs (:2802-2806).  Every unordered pair of candidates in neighbouring cells is gated once by the
+     * Euclidean test, one lane per candidate (see the loop below).  Pairs that pass are compacted into a per-warp ring
      * and the Mahalanobis distance is evaluated 32 queued pairs at a time. ---- */
     {
       unsigned* q = queue + warp * MF_QUEUE;   /* ring of pairs of cell-order positions */
