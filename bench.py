@@ -43,6 +43,7 @@ WORKLOADS = {
     # north_star target sentence: "the GM-PHD update at 1M particles on one GPU" (configs[3]'s particle count and C x M
     # shape on ONE B200; the 184 GB of dense update terms stream through the 32 GB update buffer in batches)
     "synthetic_1048576x128x50_phd": dict(P=1048576, C=128, M=50, max_components=256),
+    "synthetic_16384x128x50_phd": dict(P=16384, C=128, M=50, max_components=256),      # the same shape, ncu-sized
     # BASELINE.json configs[4] per-GPU shape at a size one GPU's update buffer streams through: global resampling every step
     "synthetic_32768x128x100_phd": dict(P=32768, C=128, M=100, max_components=256, resample_threshold=1.0),
     "synthetic_262144x128x100_phd": dict(P=262144, C=128, M=100, max_components=256, resample_threshold=1.0),

@@ -1022,29 +1022,38 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
       else
         wacc = upd_measurement<2, false, DENSE, true>(s_rec, C, zr2, zb2, dead, sc2, D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m, s_stash);
     }
-    float dsum = warp_butterfly_sum(wacc.x + wacc.y);
-    /* birth term of measurement m (host loop :3468-3507, normalised at :2232-2242) */
+    /* the sum of the detection weights is needed by Vo's empty-map particle weighting only (:2264-2279) */
+    float dsum = 0.0f;
+    if (c.particle_weighting == 1) dsum = warp_butterfly_sum(wacc.x + wacc.y);
     if (lane == 0) {
-      const float b0 = s_bb[m], b1 = s_bb[PHD_MAX_MEAS + m], b3 = s_bb[2 * PHD_MAX_MEAS + m];
-      const float bmx = s_bb[3 * PHD_MAX_MEAS + m], bmy = s_bb[4 * PHD_MAX_MEAS + m];
-      float lb = dead ? PHD_LOG0 : c.log_birth_weight;
-      float wb = phd_expf(lb - L);
-      const int t = C + M * C + m;
-      if (DENSE) {
-        float* q = D + dense_index((size_t)t);
-        st_stream(q, b0); st_stream(q + 64, b1); st_stream(q + 128, b1); st_stream(q + 192, b3);
-        st_stream(q + 256, bmx); st_stream(q + 320, bmy); st_stream(q + 384, wb);
-      }
-      if (!(wb < c.min_w)) {
-        int slot = atomicAdd(&s_ncand, 1);
-        if (slot < Smax) {
-          cand[2 * slot] = make_float4(b0, b1, b1, b3);
-          cand[2 * slot + 1] = make_float4(bmx, bmy, wb, __int_as_float(t));
-        }
-      }
       if (!CPHD) s_L[m] = L;
-      s_ds[m] = dsum + wb;
+      s_ds[m] = dsum;
     }
+  }
+  /* birth terms of this warp's measurements (host loop :3468-3507, normalised at :2232-2242): one lane per measurement
+   * after the loop instead of lane 0 inside every round; each lane reads what lane 0 of its own warp wrote */
+  __syncwarp();
+  for (int m = warp + UPD_WARPS * lane; m < M; m += UPD_WARPS * 32) {
+    const bool dead = c.labeled && (s_zl[m] != 0.0f);
+    const float L = CPHD ? -s_L[m] : s_L[m];
+    const float b0 = s_bb[m], b1 = s_bb[PHD_MAX_MEAS + m], b3 = s_bb[2 * PHD_MAX_MEAS + m];
+    const float bmx = s_bb[3 * PHD_MAX_MEAS + m], bmy = s_bb[4 * PHD_MAX_MEAS + m];
+    const float lb = dead ? PHD_LOG0 : c.log_birth_weight;
+    const float wb = phd_expf(lb - L);
+    const int t = C + M * C + m;
+    if (DENSE) {
+      float* q = D + dense_index((size_t)t);
+      st_stream(q, b0); st_stream(q + 64, b1); st_stream(q + 128, b1); st_stream(q + 192, b3);
+      st_stream(q + 256, bmx); st_stream(q + 320, bmy); st_stream(q + 384, wb);
+    }
+    if (!(wb < c.min_w)) {
+      const int slot = atomicAdd(&s_ncand, 1);
+      if (slot < Smax) {
+        cand[2 * slot] = make_float4(b0, b1, b1, b3);
+        cand[2 * slot + 1] = make_float4(bmx, bmy, wb, __int_as_float(t));
+      }
+    }
+    s_ds[m] = s_ds[m] + wb;
   }
   __syncthreads();
 
