@@ -1643,6 +1643,7 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
 #define MF_NONE 0xffffu
 #define MF_CELLS 592         /* MRG_NCELL + 1, padded */
 #define MF_QUEUE 128         /* gate survivors queued per warp (ring buffer) */
+#define MF_SEG 8             /* cell-order positions per gate segment (pair phase) */
 #define MF_ACH 8             /* A candidates gated per compaction step (up to MF_ACH * 32 new queue entries) */
 
 __host__ __device__ static inline size_t merge_fast_smem_bytes(int S) {
@@ -1988,16 +1989,15 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
           }
         }
       };
-      /* one lane per B candidate (cell order, so the lanes of a warp share most of their neighbourhood); its A side is
-       * two contiguous runs of cell-order positions: the row above, cells cx-1..cx+1, and its own row from cell cx-1 up
-       * to itself.  Every unordered pair of candidates in neighbouring cells is gated exactly once. */
+      /* The A side of a B candidate is two contiguous runs of cell-order positions: the row above, cells cx-1..cx+1, and
+       * its own row from cell cx-1 up to itself, so every unordered pair of candidates in neighbouring cells is gated
+       * exactly once.  Neighbourhood sizes differ a lot between the 32 candidates of a warp round (clusters), so the runs
+       * are cut into segments of MF_SEG positions and the SEGMENTS are dealt to the lanes (prefix sum over the round's
+       * candidates, owner found by a shuffle binary search): ~80 % of the gate's lane slots do useful work instead of ~25 %. */
       for (int b0 = warp * 32; b0 < n; b0 += MF_THREADS) {
         const int pb = b0 + lane;
-        const bool valid = pb < n;
-        float4 B1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         int beg1 = 0, len1 = 0, beg2 = 0, tot = 0;
-        if (valid) {
-          B1 = Gc[pb];
+        if (pb < n) {
           const int cid = own[pb];                                     /* the cell of this position (phase E) */
           const int cy = cid / MRG_GMAX, cx = cid - cy * MRG_GMAX;
           const int left = cid - ((cx > 0) ? 1 : 0);
@@ -2011,27 +2011,83 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
           }
           tot = len1 + len2;
         }
-        const unsigned pbs = (unsigned)pb << 16;
-        int tmaxw = tot;
+        const int nseg = (tot + MF_SEG - 1) / MF_SEG;
+        int incl = nseg;
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) tmaxw = max(tmaxw, __shfl_xor_sync(FULL_MASK, tmaxw, off));
-        for (int t = 0; t < tmaxw; ++t) {
-          const int pa = (t < len1) ? beg1 + t : beg2 + (t - len1);
-          bool pass = false;
-          if (t < tot) {
-            const float4 A1 = Gc[pa];
-            const float gx = B1.x - A1.x, gy = B1.y - A1.y;
-            pass = gx * gx + gy * gy <= gk * (B1.z + A1.z);
+        for (int off = 1; off < 32; off <<= 1) {
+          const int t = __shfl_up_sync(FULL_MASK, incl, off);
+          if (lane >= off) incl += t;
+        }
+        const int T = __shfl_sync(FULL_MASK, incl, 31);
+        const int excl = incl - nseg;
+        for (int s0 = 0; s0 < T; s0 += 32) {
+          const int sidx = s0 + lane;
+          int o = 0;                                                   /* owner: the last candidate with excl <= sidx */
+#pragma unroll
+          for (int step = 16; step >= 1; step >>= 1) {
+            const int e = __shfl_sync(FULL_MASK, excl, o + step);
+            if (e <= sidx) o += step;
           }
-          const unsigned bal = __ballot_sync(FULL_MASK, pass);
-          if (bal) {
-            if (pass) q[(qh + qn + __popc(bal & lt_mask)) & (MF_QUEUE - 1)] = (unsigned)pa | pbs;
-            qn += __popc(bal);
+          const int ob1 = __shfl_sync(FULL_MASK, beg1, o), ol1 = __shfl_sync(FULL_MASK, len1, o);
+          const int ob2 = __shfl_sync(FULL_MASK, beg2, o) - ol1;
+          const int t0 = (sidx - __shfl_sync(FULL_MASK, excl, o)) * MF_SEG;
+          const int otot = __shfl_sync(FULL_MASK, tot, o);             /* every lane takes part in the shuffle */
+          const int tend = (sidx < T) ? otot : 0;
+          const int pbo = min(b0 + o, n - 1);
+          const float4 B1 = Gc[pbo];
+          const unsigned pbs = (unsigned)pbo << 16;
+          unsigned mask = 0u;                                         /* bit k: position t0 + k passes the gate */
+#pragma unroll
+          for (int k = 0; k < MF_SEG; ++k) {
+            const int t = t0 + k;
+            if (t < tend) {
+              const float4 A1 = Gc[((t < ol1) ? ob1 : ob2) + t];
+              const float gx = B1.x - A1.x, gy = B1.y - A1.y;
+              if (gx * gx + gy * gy <= gk * (B1.z + A1.z)) mask |= 1u << k;
+            }
+          }
+          /* compaction: every lane appends its pairs to the ring */
+          const int cntl = __popc(mask);
+          int inc = cntl;
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(FULL_MASK, inc, off);
+            if (lane >= off) inc += t;
+          }
+          const int total = __shfl_sync(FULL_MASK, inc, 31);
+          if (total == 0) continue;
+          if (qn + total <= MF_QUEUE) {
+            int slot = qh + qn + inc - cntl;
+            for (unsigned m = mask; m; m &= m - 1) {
+              const int t = t0 + (__ffs(m) - 1);
+              q[slot & (MF_QUEUE - 1)] = (unsigned)(((t < ol1) ? ob1 : ob2) + t) | pbs;
+              ++slot;
+            }
+            qn += total;
             __syncwarp();
-            if (qn >= 32) {
+            while (qn >= 32) {
               evaluate(32);
               qh = (qh + 32) & (MF_QUEUE - 1);
               qn -= 32;
+            }
+            __syncwarp();
+          } else {
+            /* a very dense neighbourhood: one pair per lane and round */
+            while (__any_sync(FULL_MASK, mask != 0u)) {
+              const bool has = mask != 0u;
+              const unsigned hb = __ballot_sync(FULL_MASK, has);
+              if (has) {
+                const int t = t0 + (__ffs(mask) - 1);
+                q[(qh + qn + __popc(hb & lt_mask)) & (MF_QUEUE - 1)] = (unsigned)(((t < ol1) ? ob1 : ob2) + t) | pbs;
+                mask &= mask - 1;
+              }
+              qn += __popc(hb);
+              __syncwarp();
+              if (qn >= 32) {
+                evaluate(32);
+                qh = (qh + 32) & (MF_QUEUE - 1);
+                qn -= 32;
+              }
               __syncwarp();
             }
           }
