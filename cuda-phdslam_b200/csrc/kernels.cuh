@@ -411,7 +411,7 @@ __device__ __forceinline__ float cphd_lse_warp(int n, F f) {
  * REGISTERS: lane L holds the KR consecutive coefficients e[KR L .. KR L + KR - 1], KR = ceil((M + 1) / 32).  Folding
  * one root is e[k] += x * e[k-1] on the old values: inside a lane from the top coefficient down, and the lane's lowest
  * coefficient takes e[k-1] from the lane below with one shuffle.  Same operations as the oracle's esf(): every
- * coefficient is an independent chain of __dmul_rn / __dadd_rn, and the terms beyond the current degree are exact
+ * coefficient is an independent chain of double fused multiply-adds, and the terms beyond the current degree are exact
  * zeros.  Result to the warp's shared array Es[0..M]. */
 template <int KR>
 __device__ __forceinline__ void cphd_esf_warp_t(const double* __restrict__ x, int M, int skip, double* __restrict__ Es, int lane) {
@@ -423,8 +423,8 @@ __device__ __forceinline__ void cphd_esf_warp_t(const double* __restrict__ x, in
     double below = __shfl_up_sync(FULL_MASK, E[KR - 1], 1);
     if (lane == 0) below = 0.0;
 #pragma unroll
-    for (int i = KR - 1; i >= 1; --i) E[i] = __dadd_rn(E[i], __dmul_rn(xn, E[i - 1]));
-    E[0] = __dadd_rn(E[0], __dmul_rn(xn, below));
+    for (int i = KR - 1; i >= 1; --i) E[i] = __fma_rn(xn, E[i - 1], E[i]);
+    E[0] = __fma_rn(xn, below, E[0]);
   };
   const int n_skip = (skip < 0) ? 0 : skip;
   for (int n = 0; n < n_skip; ++n) fold(x[n]);
@@ -480,7 +480,7 @@ __device__ void cphd_block(const DevCfg& c, int C, int M, const float* __restric
   const float larea = lcr - lcd;
 
   for (int k = tid; k < nlf; k += UPD_THREADS) s_lf[k] = lfact[k];
-  for (int n = tid; n < N1; n += UPD_THREADS) s_psi[n] = card[n];          /* prior */
+  for (int n = tid; n < N1; n += UPD_THREADS) s_psi[n] = phd_expf(card[n]); /* prior pmf (linear); becomes Psi0 below */
   for (int m = tid; m < M; m += UPD_THREADS) s_llam[m] = phd_safe_log(s_S[m] + wb) + larea;   /* :1539-1552 */
   if (warp == 0) {                                                            /* <q_D,w>, <1,w> (:1649-1683) */
     float q = warp_sum_array(s_qd, C);
@@ -497,7 +497,7 @@ __device__ void cphd_block(const DevCfg& c, int C, int M, const float* __restric
     t = t - s_lf[M - k];
     t = t + cphd_mulk(k, lwb);
     t = t + cphd_mulk(M - k, l1wb);
-    s_pb[k] = t;
+    s_pb[k] = phd_expf(t);                                                  /* birth pmf (linear) */
     s_cK[k] = cphd_mulk(k, lcr) - c.clutter_rate;
   }
   if (warp == 0) {
@@ -509,10 +509,11 @@ __device__ void cphd_block(const DevCfg& c, int C, int M, const float* __restric
   }
   __syncthreads();
   const float lq = s_sc[0], lW = s_sc[1], lmax = s_sc[2];
-  /* predicted cardinality (:880-887): plain sum of exp; the terms with n-j > M are exactly 0 */
+  /* predicted cardinality (:880-887): the reference's plain sum of exp(birth(n-j) + prior(j)), evaluated as the
+   * convolution of the two pmfs (N1 + M + 1 exponentials instead of N1 (M + 1)); the terms with n-j > M are exactly 0 */
   for (int n = tid; n < N1; n += UPD_THREADS) {
     float sum = 0.0f;
-    for (int j = max(0, n - M); j <= n; ++j) sum = sum + phd_expf(s_pb[n - j] + s_psi[j]);
+    for (int j = max(0, n - M); j <= n; ++j) sum = fmaf(s_pb[n - j], s_psi[j], sum);
     s_pm[n] = phd_safe_log(sum);
   }
   for (int m = tid; m < M; m += UPD_THREADS) s_x[m] = (double)phd_expf(s_llam[m] - lmax);

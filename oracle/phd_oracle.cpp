@@ -876,7 +876,7 @@ extern "C" void oracle_esf(const double* roots, int n, double* out) {
   out[0] = 1.0;
   for (int i = 1; i <= n; ++i) out[i] = 0.0;
   for (int m = 0; m < n; ++m)
-    for (int k = m + 1; k >= 1; --k) out[k] = out[k] + roots[m] * out[k - 1];
+    for (int k = m + 1; k >= 1; --k) out[k] = fma(roots[m], out[k - 1], out[k]);   /* one rounding per fold, as the kernel's DFMA */
 }
 
 /* k * x with the convention 0 * x = 0 even for x = LOG0 (the reference relies on exp() of huge negatives) */
@@ -942,11 +942,14 @@ static void cphd_factors(const phdslam_config_t& c, const float* w, const float*
     t = t + mulk(M - k, l1wb);
     pb[k] = t;
   }
-  /* predicted cardinality (:880-887): plain sum of exp, terms with n-j > M are exactly 0 */
-  std::vector<float> pm(N1);
+  /* predicted cardinality (:880-887): the reference's plain sum of exp(birth(n-j) + prior(j)), canonically evaluated as
+   * the convolution of the two pmfs (N1 + M + 1 exponentials instead of N1 (M + 1)); terms with n-j > M are exactly 0 */
+  std::vector<float> pm(N1), epb(M + 1), epr(N1);
+  for (int k = 0; k <= M; ++k) epb[k] = phd_expf(pb[k]);
+  for (int n = 0; n <= N; ++n) epr[n] = phd_expf(prior[n]);
   for (int n = 0; n <= N; ++n) {
     float sum = 0.0f;
-    for (int j = std::max(0, n - M); j <= n; ++j) sum = sum + phd_expf(pb[n - j] + prior[j]);
+    for (int j = std::max(0, n - M); j <= n; ++j) sum = fmaf(epb[n - j], epr[j], sum);
     pm[n] = (sum != 0.0f) ? phd_safe_log(sum) : PHD_LOG0;
   }
   const float lcr = phd_safe_log(c.clutter_rate), lcd = phd_safe_log(c.clutter_density);
