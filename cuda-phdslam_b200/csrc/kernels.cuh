@@ -1340,7 +1340,7 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
 
     /* ---- C. uniform grid over candidate means; cell size >= the largest gate radius ---- */
     const bool gated = (c.distance_metric == 0);
-    const float gk = 0.625f * c.min_sep;                 /* pair gate: |d|^2 <= gk * (lam_a + lam_b) */
+    const float gk = 0.515625f * c.min_sep;                 /* pair gate: |d|^2 <= gk * (lam_a + lam_b) */
     int G = 1;
     float cs = 1.0f;
     if (gated) {
@@ -1912,7 +1912,7 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
 
     /* ---- E. uniform grid over the candidate means, cell size >= the largest gate radius; gate records in cell order.
      * Is every candidate within the threshold of itself (it is, unless its covariance is degenerate)? ---- */
-    const float gk = 0.625f * c.min_sep;                   /* pair gate: |d|^2 <= gk * (lam_a + lam_b) */
+    const float gk = 0.515625f * c.min_sep;                   /* pair gate: |d|^2 <= gk * (lam_a + lam_b) */
     int G = 1;
     float cs = 1.0f;
     {

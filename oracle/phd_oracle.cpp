@@ -481,10 +481,10 @@ extern "C" float oracle_hellinger(const G2* a, const G2* b) { return hellinger(*
  * Canonical choice where the reference's rounding is shape-dependent: cluster sums accumulate sequentially in
  * ascending index order (the reference: 256 strided partials + shared-memory tree).
  * Canonical gate (Mahalanobis metric only): candidate b can join the cluster of seed a only if
- *     |mu_a - mu_b|^2 <= (0.625 * minSeparation) * (lam_a + lam_b),
+ *     |mu_a - mu_b|^2 <= (0.515625 * minSeparation) * (lam_a + lam_b),
  * lam = largest eigenvalue of the component's covariance.  For positive semi-definite covariances
  * d_M^2 >= |d|^2 / lam_max((Pa+Pb)/2) >= |d|^2 / ((lam_a+lam_b)/2), so a candidate outside the gate has
- * d_M^2 > 1.25*minSeparation and the reference would not merge it either; the gate (with its 25 % margin
+ * d_M^2 > 1.03*minSeparation and the reference would not merge it either; the gate (with its 3 % margin
  * against fp32 rounding) only changes results for numerically degenerate covariances.  It lets the kernel
  * look at a 3x3 neighbourhood of a uniform grid (cell size >= the largest gate radius) instead of at every
  * candidate. */
@@ -509,7 +509,7 @@ static inline unsigned merge_tie_key(int i) {
 static void merge_mixture(const phdslam_config_t& c, const std::vector<G2>& cand, std::vector<G2>& out) {
   const int n = (int)cand.size();
   const bool gated = (c.distance_metric == 0);
-  const float gk = 0.625f * c.min_separation;
+  const float gk = 0.515625f * c.min_separation;
   std::vector<float> lam(n);
   for (int i = 0; i < n; ++i) lam[i] = merge_lambda_max(cand[i]);
   std::vector<char> merged(n, 0);
