@@ -336,7 +336,9 @@ def run_ours(args, wl):
         mm = torch.tensor([mig, rs], device="cuda", dtype=torch.float64)
         dist.all_reduce(mm, op=dist.ReduceOp.MAX)
         mig, rs = float(mm[0]), float(mm[1])
-        exchange = {"migrated_particles_per_step_max_rank": mig, "bytes_per_step_max_rank": mig * rec, "resample_phase_ms": rs,
+        exchange = {"mode": ("nvlink peer-window push: the gather kernel writes offspring into the owner's buffers (CUDA IPC)"
+                             if filt.dist_p2p else "nccl send/recv ring (pack, send, unpack)"),
+                    "migrated_particles_per_step_max_rank": mig, "bytes_per_step_max_rank": mig * rec, "resample_phase_ms": rs,
                     "achieved_GBps_lower_bound": (mig * rec / (rs * 1e-3) / 1e9) if rs > 0 else None,
                     "nvlink5_peak_GBps_per_direction": 900.0,
                     "note": "bytes received by the busiest rank / the whole resampling phase (scan + search + gather + ring)"}

@@ -2385,26 +2385,42 @@ __global__ void resample_search_kernel(const unsigned long long* __restrict__ ex
   anc[jj] = anc_offset + lo;
 }
 
-/* one warp per offspring: copy pose, map block (only `count` live components per plane), cardinality */
+/* one warp per offspring: copy pose, map block (only `count` live components per plane), cardinality.
+ * Local resampling: the destination is this GPU's back buffer (dst_first = 0, anc_out = nullptr).
+ * NVLink exchange (world > 1, peer window mapped): the same kernel PUSHES the offspring a peer owns straight into that
+ * peer's back buffer -- pose_out / count_out / map_out / card_out / anc_out are peer pointers, dst_first the first slot
+ * of the interval, n_dst the peer's particle count -- so the gather and the transfer are one kernel and nothing is
+ * packed, staged or unpacked (coalesced 128-byte stores over NVLink). */
 __global__ void resample_gather_kernel(const int* __restrict__ anc, int n_off, int anc_offset, int n_src, int n_dst,
                                        const float* __restrict__ pose_in, float* __restrict__ pose_out,
                                        const int* __restrict__ count_in, int* __restrict__ count_out,
                                        const float* __restrict__ map_in, float* __restrict__ map_out,
-                                       const float* __restrict__ card_in, float* __restrict__ card_out, int Cmax, int n_card) {
+                                       const float* __restrict__ card_in, float* __restrict__ card_out, int Cmax, int n_card,
+                                       int dst_first, int* __restrict__ anc_out) {
   int j = blockIdx.x * (blockDim.x >> 5) + warp_id();
   if (j >= n_off) return;
   const int lane = lane_id();
   const int a = anc[j] - anc_offset;
   if (a < 0 || a >= n_src) return;
-  if (lane < 6) pose_out[(size_t)lane * n_dst + j] = pose_in[(size_t)lane * n_src + a];
+  const size_t jd = (size_t)dst_first + j;
+  if (lane < 6) pose_out[(size_t)lane * n_dst + jd] = pose_in[(size_t)lane * n_src + a];
   const int cnt = count_in[a];
-  if (lane == 0) count_out[j] = cnt;
+  if (lane == 0) {
+    count_out[jd] = cnt;
+    if (anc_out) anc_out[jd] = anc[j];
+  }
   const float* src = map_in + (size_t)a * PHD_MAP_PLANES * Cmax;
-  float* dst = map_out + (size_t)j * PHD_MAP_PLANES * Cmax;
+  float* dst = map_out + jd * PHD_MAP_PLANES * Cmax;
   for (int f = 0; f < PHD_MAP_PLANES; ++f)
     for (int k = lane; k < cnt; k += 32) dst[f * Cmax + k] = src[f * Cmax + k];
   if (n_card > 0 && card_in)
-    for (int k = lane; k < n_card; k += 32) card_out[(size_t)j * n_card + k] = card_in[(size_t)a * n_card + k];
+    for (int k = lane; k < n_card; k += 32) card_out[jd * n_card + k] = card_in[(size_t)a * n_card + k];
+}
+
+/* after the exchange: offspring whose ancestor lives on a peer (-1 from the local search) take the index the peer pushed */
+__global__ void resample_take_pushed_kernel(int* __restrict__ anc, const int* __restrict__ anc_in, int n) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n && anc[j] < 0) anc[j] = anc_in[j];
 }
 
 /* migration: pack the ancestors of `cnt` remote offspring into contiguous staging (one warp per record) */

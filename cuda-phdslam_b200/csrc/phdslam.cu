@@ -160,7 +160,45 @@ static int validate_config(const phdslam_config_t* c) {
   return 0;
 }
 
+/* layout of the peer window for a rank with n particles: 256-byte header (magic), then the arrays below */
+struct SlabLayout {
+  size_t pose[2], count[2], map[2], card[2], anc_in, bytes;
+};
+static SlabLayout slab_layout(size_t n, size_t Cmax, size_t n_card) {
+  SlabLayout L;
+  size_t o = 256;
+  auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 255) & ~(size_t)255; return at; };
+  for (int b = 0; b < 2; ++b) {
+    L.pose[b] = take(6 * n * sizeof(float));
+    L.count[b] = take(n * sizeof(int));
+    L.map[b] = take(n * PHD_MAP_PLANES * Cmax * sizeof(float));
+    L.card[b] = take(n * n_card * sizeof(float));
+  }
+  L.anc_in = take(n * sizeof(int));
+  L.bytes = std::max(o, (size_t)4 << 20);      /* >= 4 MB: an allocation of its own, never a sub-allocation */
+  return L;
+}
+
+static void close_peers(phdslam* h) {
+  if (h->peer_base) {
+    for (int r = 0; r < h->world; ++r)
+      if (r != h->rank && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
+    delete[] h->peer_base;
+    h->peer_base = nullptr;
+  }
+  h->p2p = 0;
+}
+
 static void free_state(phdslam* h) {
+  close_peers(h);
+  if (h->peer_slab) {
+    cudaFree(h->peer_slab);
+    h->peer_slab = nullptr;
+    h->anc_in = nullptr;
+    for (int b = 0; b < 2; ++b) { h->pose[b] = nullptr; h->count[b] = nullptr; h->map[b] = nullptr; h->card[b] = nullptr; }
+  }
+  cudaFree(h->barrier_dev);
+  h->barrier_dev = nullptr;
   for (int b = 0; b < 2; ++b) {
     cudaFree(h->pose[b]); cudaFree(h->count[b]); cudaFree(h->map[b]); cudaFree(h->card[b]);
   }
@@ -170,8 +208,8 @@ static void free_state(phdslam* h) {
   cudaFree(h->dense); cudaFree(h->z_dev); cudaFree(h->draws_dev); cudaFree(h->q_fx); cudaFree(h->cdf_excl);
   cudaFree(h->ancestors); cudaFree(h->red); cudaFree(h->cand); cudaFree(h->cand_in); cudaFree(h->n_cand); cudaFree(h->ovf_list);
   cudaFree(h->mig_map); cudaFree(h->mig_pose); cudaFree(h->mig_count); cudaFree(h->mig_anc); cudaFree(h->mig_card);
-  cudaFree(h->mig_pose_in); cudaFree(h->totals_dev); cudaFree(h->lfact);
-  h->mig_pose_in = nullptr; h->totals_dev = nullptr; h->lfact = nullptr;
+  cudaFree(h->mig_pose_in); cudaFree(h->totals_dev); cudaFree(h->lfact); cudaFree(h->mig_anc2);
+  h->mig_pose_in = nullptr; h->totals_dev = nullptr; h->lfact = nullptr; h->mig_anc2 = nullptr; h->mig_anc_cap = 0;
   if (h->red_host) cudaFreeHost(h->red_host);
 }
 
@@ -191,6 +229,22 @@ static int alloc_state(phdslam* h) {
   h->n_cap = (h->world > 1) ? h->n_local : particle_capacity(h->cfg, h->n_local);
   const size_t n = (size_t)h->n_cap;
   const size_t C = (size_t)h->Cmax;
+  if (h->world > 1) {
+    /* one peer-mappable allocation (see phdslam_internal.h) */
+    const SlabLayout L = slab_layout(n, C, (size_t)h->n_card);
+    CK(cudaMalloc(&h->peer_slab, L.bytes));
+    h->peer_slab_bytes = L.bytes;
+    for (int b = 0; b < 2; ++b) {
+      h->pose[b] = reinterpret_cast<float*>(h->peer_slab + L.pose[b]);
+      h->count[b] = reinterpret_cast<int*>(h->peer_slab + L.count[b]);
+      h->map[b] = reinterpret_cast<float*>(h->peer_slab + L.map[b]);
+      h->card[b] = h->n_card ? reinterpret_cast<float*>(h->peer_slab + L.card[b]) : nullptr;
+    }
+    h->anc_in = reinterpret_cast<int*>(h->peer_slab + L.anc_in);
+    h->slab_sw = 0;
+    CK(cudaMalloc(&h->barrier_dev, 2 * sizeof(int)));
+    CK(cudaMemset(h->barrier_dev, 0, 2 * sizeof(int)));
+  } else
   for (int b = 0; b < 2; ++b) {
     CK(cudaMalloc(&h->pose[b], 6 * n * sizeof(float)));
     CK(cudaMalloc(&h->count[b], n * sizeof(int)));
@@ -351,6 +405,7 @@ extern "C" int phdslam_local_offset(const phdslam_t* h) { return h->offset; }
 extern "C" void* phdslam_stream(phdslam_t* h) { return (void*)h->stream; }
 extern "C" int phdslam_synchronize(phdslam_t* h) { CK(cudaStreamSynchronize(h->stream)); return 0; }
 extern "C" int phdslam_set_overlap(phdslam_t* h, int on) { h->overlap = on ? 1 : 0; return 0; }
+extern "C" int phdslam_dist_p2p(const phdslam_t* h) { return h->p2p; }
 
 extern "C" int phdslam_dist_unique_id(void* id128) {
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
@@ -361,6 +416,50 @@ extern "C" int phdslam_dist_unique_id(void* id128) {
   ncclUniqueId id;
   CKN(ncclGetUniqueId(&id));
   memcpy(id128, &id, sizeof(id));
+  return 0;
+}
+
+/* Map every peer's window through CUDA IPC (one process per GPU on one node).  Any failure -- IPC unsupported, no peer
+ * access between two devices, PHDSLAM_P2P=0 -- leaves p2p = 0 on EVERY rank (the decision is all-reduced) and the
+ * resampling exchange uses the NCCL send/recv ring instead. */
+static int map_peer_windows(phdslam* h) {
+  const int W = h->world, me = h->rank;
+  ncclComm_t comm = (ncclComm_t)h->nccl_comm;
+  const char* env = getenv("PHDSLAM_P2P");
+  int ok = (env && atoi(env) == 0) ? 0 : 1;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  const unsigned long long magic = 0x5048445f50325000ull + (unsigned)me;
+  if (ok && cudaIpcGetMemHandle(&mine, h->peer_slab) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+  CK(cudaMemcpyAsync(h->peer_slab, &magic, sizeof(magic), cudaMemcpyHostToDevice, h->stream));
+  unsigned char* hbuf = nullptr;                          /* [W] handles, all-gathered */
+  CK(cudaMalloc(&hbuf, (size_t)W * sizeof(mine)));
+  CK(cudaMemcpyAsync(hbuf + (size_t)me * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+  CKN(ncclAllGather(hbuf + (size_t)me * sizeof(mine), hbuf, sizeof(mine), ncclChar, comm, h->stream));
+  std::vector<cudaIpcMemHandle_t> all(W);
+  CK(cudaMemcpyAsync(all.data(), hbuf, (size_t)W * sizeof(mine), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));                   /* every rank's magic is in place: the all-gather completed */
+  h->peer_base = new unsigned char*[W];
+  for (int r = 0; r < W; ++r) h->peer_base[r] = nullptr;
+  h->peer_base[me] = h->peer_slab;
+  for (int r = 0; r < W && ok; ++r) {
+    if (r == me) continue;
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+    h->peer_base[r] = (unsigned char*)p;
+    unsigned long long seen = 0;
+    if (cudaMemcpy(&seen, p, sizeof(seen), cudaMemcpyDeviceToHost) != cudaSuccess ||
+        seen != 0x5048445f50325000ull + (unsigned)r) { cudaGetLastError(); ok = 0; }
+  }
+  /* unanimous decision */
+  int* flag = reinterpret_cast<int*>(hbuf);
+  CK(cudaMemcpyAsync(flag, &ok, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CKN(ncclAllReduce(flag, flag, 1, ncclInt32, ncclMin, comm, h->stream));
+  CK(cudaMemcpyAsync(&ok, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(hbuf);
+  if (!ok) close_peers(h);
+  h->p2p = ok;
   return 0;
 }
 
@@ -402,7 +501,9 @@ extern "C" int phdslam_dist_init(phdslam_t* h, int rank, int world, const void* 
   h->cur = 0;
   int rc = alloc_state(h);
   if (rc) return rc;
-  return init_particles(h);
+  rc = init_particles(h);
+  if (rc) return rc;
+  return map_peer_windows(h);
 }
 
 static inline int rank_offset(const phdslam* h, int r) { return (int)((long long)h->n_global * r / h->world); }
@@ -449,7 +550,7 @@ static int fan_out(phdslam* h) {
   LAUNCH_CHECK(h);
   resample_gather_kernel<<<cdiv(n_out, 8), 256, 0, h->stream>>>(h->ancestors, (int)n_out, 0, n, (int)n_out, h->pose[b], h->pose[b ^ 1],
                                                               h->count[b], h->count[b ^ 1], h->map[b], h->map[b ^ 1],
-                                                              h->card[b], h->card[b ^ 1], h->Cmax, h->n_card);
+                                                              h->card[b], h->card[b ^ 1], h->Cmax, h->n_card, 0, nullptr);
   LAUNCH_CHECK(h);
   std::swap(h->logw, h->dlogw);             /* both are n_cap floats; dlogw is per-update scratch */
   std::swap(h->resample_idx, h->n_in);      /* both are n_cap ints; n_in is per-update scratch */
@@ -722,6 +823,7 @@ extern "C" int phdslam_update(phdslam_t* h, const float* z, int M, int fields) {
   /* pose planes are not touched by the update: keep the front pose buffer consistent with `cur` */
   std::swap(h->pose[0], h->pose[1]);
   std::swap(h->card[0], h->card[1]);
+  h->slab_sw ^= 1;   /* pose[i] / card[i] now live in slot i ^ slab_sw of the peer window (same on every rank) */
   if (!multi) {
     cudaEventElapsedTime(&upd_ms, h->ev[3], h->ev[4]);
     cudaEventElapsedTime(&mrg_ms, h->ev[4], h->ev[5]);
@@ -912,9 +1014,46 @@ extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms,
   LAUNCH_CHECK(h);
   resample_gather_kernel<<<cdiv(n_off, 8), 256, 0, h->stream>>>(h->ancestors, n_off, h->offset, n, n_off, h->pose[b], h->pose[b ^ 1],
                                                               h->count[b], h->count[b ^ 1], h->map[b], h->map[b ^ 1],
-                                                              h->card[b], h->card[b ^ 1], h->Cmax, h->n_card);
+                                                              h->card[b], h->card[b ^ 1], h->Cmax, h->n_card, 0, nullptr);
   LAUNCH_CHECK(h);
-  if (h->world > 1) {
+  if (h->world > 1 && h->p2p) {
+    /* NVLink exchange: for every peer d, the offspring interval d owns whose ancestors live here (both ends derive it
+     * from `bounds`, nothing is negotiated) is searched on the local CDF and pushed by the gather kernel straight into
+     * d's back buffer through the mapped peer window.  d's back buffer is free: the all-gather above completed, so d
+     * has finished its merge.  The all-reduce at the end is the barrier that makes every push visible to its owner. */
+    const int me = h->rank, W = h->world;
+    for (int k = 1; k < W; ++k) {
+      const int d = (me + k) % W, sr = (me - k + W) % W;
+      const int off_d = rank_offset(h, d), end_d = rank_offset(h, d + 1);
+      const int out_lo = std::max(bounds[me], off_d), out_hi = std::min(bounds[me + 1], end_d);
+      const int cnt_out = std::max(out_hi - out_lo, 0);
+      const int in_lo = std::max(bounds[sr], h->offset), in_hi = std::min(bounds[sr + 1], h->offset + n);
+      h->tim.migrated_in += (unsigned long long)std::max(in_hi - in_lo, 0);
+      if (cnt_out <= 0) continue;
+      if (h->mig_anc_cap < (size_t)cnt_out) {
+        cudaFree(h->mig_anc2);
+        h->mig_anc2 = nullptr;
+        CK(cudaMalloc(&h->mig_anc2, (size_t)cnt_out * sizeof(int)));
+        h->mig_anc_cap = (size_t)cnt_out;
+      }
+      resample_search_kernel<<<cdiv(cnt_out, 256), 256, 0, h->stream>>>(h->cdf_excl, n, base, total, n_new, out_lo, cnt_out, h->offset,
+                                                                      udev, sysmode, h->resample_calls, h->dc.seed_lo,
+                                                                      h->dc.seed_hi, h->mig_anc2);
+      LAUNCH_CHECK(h);
+      const size_t nd = (size_t)(end_d - off_d);
+      const SlabLayout L = slab_layout(nd, (size_t)h->Cmax, (size_t)h->n_card);
+      unsigned char* pb = h->peer_base[d];
+      resample_gather_kernel<<<cdiv(cnt_out, 8), 256, 0, h->stream>>>(
+          h->mig_anc2, cnt_out, h->offset, n, (int)nd, h->pose[b], reinterpret_cast<float*>(pb + L.pose[b ^ 1 ^ h->slab_sw]), h->count[b],
+          reinterpret_cast<int*>(pb + L.count[b ^ 1]), h->map[b], reinterpret_cast<float*>(pb + L.map[b ^ 1]), h->card[b],
+          h->n_card ? reinterpret_cast<float*>(pb + L.card[b ^ 1 ^ h->slab_sw]) : nullptr, h->Cmax, h->n_card, out_lo - off_d,
+          reinterpret_cast<int*>(pb + L.anc_in));
+      LAUNCH_CHECK(h);
+    }
+    CKN(ncclAllReduce(h->barrier_dev, h->barrier_dev + 1, 1, ncclInt32, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
+    resample_take_pushed_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->ancestors, h->anc_in, n);
+    LAUNCH_CHECK(h);
+  } else if (h->world > 1) {
     /* migration: ring of shifts; in shift k this rank serves rank+k and is served by rank-k.  Both ends derive
      * the same offspring interval from `bounds`, so no counts are exchanged. */
     ncclComm_t comm = (ncclComm_t)h->nccl_comm;

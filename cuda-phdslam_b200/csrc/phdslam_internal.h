@@ -104,6 +104,16 @@ struct phdslam {
   /* resampling migration staging (sender side), grown on demand */
   float* mig_map; float* mig_pose; int* mig_count; int* mig_anc; float* mig_card; float* mig_pose_in; size_t mig_cap;
   unsigned long long* totals_dev; /* [world] all-gathered local CDF totals */
+  /* NVLink peer window (world > 1): pose/count/map/card of both buffers and the pushed-ancestor array live in ONE
+   * allocation that every peer maps through CUDA IPC, so that the resampling exchange is a gather kernel that writes
+   * the offspring straight into the owner's back buffer (no packing, no send/recv).  p2p = 0: NCCL send/recv path. */
+  unsigned char* peer_slab; size_t peer_slab_bytes;
+  int* anc_in;                    /* [n_local] ancestors pushed by the peers */
+  int p2p;                        /* 1: peers' slabs are mapped */
+  int slab_sw;                    /* pose[i] and card[i] live in window slot i ^ slab_sw (the update swaps the pointers) */
+  unsigned char** peer_base;      /* [world] mapped slab of every rank (own slab at [rank]) */
+  int* barrier_dev;               /* 2 ints: end-of-exchange all-reduce */
+  int* mig_anc2; size_t mig_anc_cap; /* ancestors of the offspring interval being pushed */
   float* lfact;                   /* log-factorial table for the CPHD terms (PHD_LF_MAX floats) */
 };
 

@@ -94,7 +94,7 @@ ABI_SYMBOLS = [
     "phdslam_set_poses", "phdslam_get_log_weights", "phdslam_set_log_weights", "phdslam_get_map_sizes",
     "phdslam_get_maps", "phdslam_set_maps", "phdslam_get_resample_idx", "phdslam_get_cardinalities",
     "phdslam_set_cardinalities", "phdslam_update_terms", "phdslam_get_timings", "phdslam_stream",
-    "phdslam_synchronize", "phdslam_set_overlap", "phdslam_snapshot", "phdslam_restore", "phdslam_load_measurements",
+    "phdslam_synchronize", "phdslam_set_overlap", "phdslam_dist_p2p", "phdslam_snapshot", "phdslam_restore", "phdslam_load_measurements",
     "phdslam_load_controls", "phdslam_load_timestamps", "phdslam_load_trajectory", "phdslam_plan_events", "phdslam_free",
     "phdslam_write_log",
 ]
@@ -469,6 +469,12 @@ class PhdSlam(object):
     def set_overlap(self, on):
         """update / merge overlap on two streams (default off: no gain on B200); same results either way"""
         _check(self.lib.phdslam_set_overlap(self._h, int(bool(on))))
+
+    @property
+    def dist_p2p(self):
+        """True when the resampling exchange pushes particles into the peers' buffers over NVLink (mapped with CUDA IPC)"""
+        self.lib.phdslam_dist_p2p.argtypes = [C.c_void_p]
+        return bool(self.lib.phdslam_dist_p2p(self._h))
 
     def synchronize(self):
         _check(self.lib.phdslam_synchronize(self._h))

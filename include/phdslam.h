@@ -212,6 +212,10 @@ int phdslam_synchronize(phdslam_t* h);
  * profitably.  With overlap, phdslam_timings_t.update_ms is the span of the update kernels and
  * merge_ms the part of the merge that is still running when the last update kernel ends. */
 int phdslam_set_overlap(phdslam_t* h, int on);
+/* 1 when phdslam_dist_init mapped every peer's particle buffers over NVLink (CUDA IPC) and the global resampling
+ * exchange is the fused gather-and-push kernel; 0 when it runs the NCCL send/recv ring (PHDSLAM_P2P=0, or no peer
+ * access between the GPUs).  Both give bit-identical particles. */
+int phdslam_dist_p2p(const phdslam_t* h);
 /* Snapshot / restore of the whole device state inside the handle (bench: identical work every step). */
 int phdslam_snapshot(phdslam_t* h);
 int phdslam_restore(phdslam_t* h);

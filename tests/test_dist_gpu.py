@@ -10,13 +10,18 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, uid, q):
+def _cfg(S, N, C, M, cphd):
+    extra = dict(filter_type=1, max_cardinality=63) if cphd else {}
+    return S.scene_config(N, C, M, max_components=64, seed="11", **extra)
+
+
+def _worker(rank, world, uid, q, cphd=False):
     sys.path.insert(0, os.path.join(ROOT, "cuda-phdslam_b200"))
     sys.path.insert(0, ROOT)
     import phdslam_b200 as P
     from phdslam_b200 import scene as S
     N, C, M = 301, 16, 8
-    cfg = S.scene_config(N, C, M, max_components=64, seed="11")
+    cfg = _cfg(S, N, C, M, cphd)
     sc = S.make_scene(N, C, M, seed=4, n_near=2, n_far=2)
     g = P.PhdSlam(cfg, device=rank)
     g.dist_init(rank, world, unique_id=uid)
@@ -39,14 +44,21 @@ def _worker(rank, world, uid, q):
     out["anc2"] = g.resampleParticles()          # counter-based RNG
     out["sizes2"], out["maps2"] = g.get_maps()
     out["w2"] = g.log_weights
+    if cphd:
+        out["card2"] = g.cardinalities
     out["migrated"] = g.timings().migrated_in
+    out["p2p"] = g.dist_p2p
     q.put((rank, lo, n, out))
 
 
-def test_two_gpu_sharding_matches_oracle():
+@pytest.mark.parametrize("p2p,cphd", [(1, False), (0, False), (1, True), (0, True)])
+def test_two_gpu_sharding_matches_oracle(p2p, cphd, monkeypatch):
+    """p2p = 1: the resampling exchange pushes the offspring into the peer's buffers over NVLink (CUDA IPC window, one
+    fused gather kernel); p2p = 0: the NCCL send/recv ring.  Both must reproduce the single-process oracle bit for bit."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    monkeypatch.setenv("PHDSLAM_P2P", str(p2p))       # inherited by the spawned workers
     import torch.multiprocessing as mp
     sys.path.insert(0, os.path.join(ROOT, "cuda-phdslam_b200"))
     import phdslam_b200 as P
@@ -56,7 +68,7 @@ def test_two_gpu_sharding_matches_oracle():
     uid = P.dist_unique_id()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, uid, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, uid, q, cphd)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
@@ -64,7 +76,7 @@ def test_two_gpu_sharding_matches_oracle():
         p.join(timeout=60)
         assert p.exitcode == 0
     N, C, M = 301, 16, 8
-    cfg = S.scene_config(N, C, M, max_components=64, seed="11")
+    cfg = _cfg(S, N, C, M, cphd)
     sc = S.make_scene(N, C, M, seed=4, n_near=2, n_far=2)
     o = O.Oracle(cfg)
     S.load_scene(o, sc)
@@ -88,4 +100,12 @@ def test_two_gpu_sharding_matches_oracle():
     os2, om2 = o.get_maps()
     assert (cat("sizes2") == os2).all() and cat("maps2").tobytes() == om2.tobytes()
     assert cat("w2").tobytes() == o.log_weights.tobytes()
+    if cphd:                                           # the cardinality distributions travel with the particles
+        assert cat("card2").tobytes() == o.cardinalities.tobytes()
     assert sum(r[3]["migrated"] for r in res) > 0      # some offspring really crossed GPUs
+    modes = {r[3]["p2p"] for r in res}
+    assert len(modes) == 1                             # the ranks agree on the exchange path
+    if p2p == 0:
+        assert modes == {False}
+    else:
+        print("NVLink peer window mapped:", modes)
