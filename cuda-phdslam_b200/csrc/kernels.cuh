@@ -347,14 +347,25 @@ __host__ __device__ static inline size_t update_smem_bytes(int Cmax) {
 
 static inline size_t cphd_smem_bytes(int n_card) {
   /* floats: lf | pm | psi (prior, then psi0) | pb, A1, le, cK (257 each) | llam, ip1d (256 each) | 16 scalars
-   * doubles: x[256] | UPD_WARPS ESF arrays */
+   * doubles: x[256] | UPD_WARPS ESF arrays (also c[n_card], then a[M+1]) | d[n_card] */
   size_t floats = (size_t)PHD_LF_MAX + 2 * (size_t)n_card + 4 * 257 + 2 * 256 + 16;
   floats = (floats + 1) & ~(size_t)1;
-  return floats * sizeof(float) + (256 + (size_t)(UPD_THREADS / 32) * CPHD_E_STRIDE) * sizeof(double);
+  return floats * sizeof(float) + (256 + (size_t)(UPD_THREADS / 32) * CPHD_E_STRIDE + (size_t)n_card) * sizeof(double);
 }
 
 __device__ __forceinline__ float cphd_mulk(int k, float x) { return k == 0 ? 0.0f : (float)k * x; }
 __device__ __forceinline__ float cphd_clamp(float t) { return (t < PHD_LOG0) ? PHD_LOG0 : t; }
+#define CPHD_LOG_NC 4.852030263919617 /* log 128: cardinality scale of the linear-domain sums (oracle: the same) */
+/* exp of a double argument with float accuracy and double range (oracle: expd): t = k ln2 + r, exp(t) = 2^k expf(r) */
+__device__ __forceinline__ double cphd_expd(double t) {
+  if (t != t) return t;
+  if (!(t > -700.0)) return 0.0;
+  if (t > 700.0) t = 700.0;
+  const double kd = rint(t * 1.4426950408889634);
+  const double r = __fma_rn(-kd, 0.6931471805599453, t);
+  const double m = (double)phd_expf((float)r);
+  return m * __longlong_as_double((long long)((int)kd + 1023) << 52);      /* exact: the result is a normal number */
+}
 __device__ __forceinline__ float cphd_logd(double v) {
   if (!(v > 0.0)) return PHD_LOG0;
   int ex;
@@ -472,6 +483,9 @@ __device__ void cphd_block(const DevCfg& c, int C, int M, const float* __restric
   foff = (foff + 1) & ~(size_t)1;
   double* s_x = reinterpret_cast<double*>(reinterpret_cast<float*>(smem_cphd) + foff);
   double* s_e = s_x + 256;
+  double* s_d = s_e + (size_t)UPD_WARPS * CPHD_E_STRIDE;   /* d[k] = (q s)^k / k!, k = 0..N */
+  double* s_c = s_e;                                       /* c[n] = p-(n) n! / (s <1,w>)^n: dead before the ESFs start */
+  double* s_a = s_e;                                       /* a[j] of Psi0: after the ESFs */
 
   const int nlf = max(N, M) + 1;
   const float wb = c.birth_weight;
@@ -518,13 +532,26 @@ __device__ void cphd_block(const DevCfg& c, int C, int M, const float* __restric
   }
   for (int m = tid; m < M; m += UPD_THREADS) s_x[m] = (double)phd_expf(s_llam[m] - lmax);
   __syncthreads();
-  /* A1[j] = log sum_{n>j} p(n) P(n,j+1) <q_D,w>^(n-j-1) / <1,w>^n : one warp per j */
-  for (int j = warp; j <= M; j += UPD_WARPS) {
-    float v = cphd_lse_warp(N - j, [&](int i) {
-      const int n = j + 1 + i;
-      return cphd_clamp(((s_pm[n] + (s_lf[n] - s_lf[n - j - 1])) + cphd_mulk(n - j - 1, lq)) - cphd_mulk(n, lW));
-    });
-    if (lane == 0) s_A1[j] = v;
+  /* The two (N+1) x (M+1) tables of the update -- A1[j] here and Psi0(n) below -- are convolutions with
+   * d[k] = (q s)^k / k!; they are evaluated in the linear domain in double, one fused multiply-add per term (the
+   * reference: one exponential of a log-domain sum per term, :1686-1764).  s = 128 / <1,w> keeps every factor inside
+   * the double range (oracle: cphd_factors). */
+  const double lsd = CPHD_LOG_NC - (double)lW;
+  const double lqs = (double)lq + lsd;
+  for (int n = tid; n < N1; n += UPD_THREADS) {
+    s_c[n] = cphd_expd(((double)s_pm[n] + (double)s_lf[n]) - (double)n * CPHD_LOG_NC);
+    s_d[n] = (n == 0) ? 1.0 : cphd_expd((double)n * lqs - (double)s_lf[n]);
+  }
+  __syncthreads();
+  /* A1[j] = log(s^(j+1) sum_{n>j} c[n] d[n-j-1]): four lanes per j, n = j+1+p step 4, combined (p0+p1)+(p2+p3) */
+  for (int j0 = 0; j0 <= M; j0 += UPD_THREADS / 4) {
+    const int j = j0 + (tid >> 2), p = tid & 3;
+    double part = 0.0;
+    if (j <= M)
+      for (int n = j + 1 + p; n <= N; n += 4) part = __fma_rn(s_c[n], s_d[n - j - 1], part);
+    part = part + __shfl_xor_sync(FULL_MASK, part, 1);
+    part = part + __shfl_xor_sync(FULL_MASK, part, 2);
+    if (j <= M && p == 0) s_A1[j] = cphd_clamp((float)((double)cphd_logd(part) + (double)(j + 1) * lsd));
   }
   __syncthreads();
   /* elementary symmetric functions of the scaled roots (:1553-1616): job 0 = all roots, job m+1 = leave m out */
@@ -545,16 +572,25 @@ __device__ void cphd_block(const DevCfg& c, int C, int M, const float* __restric
     }
   }
   __syncthreads();
-  /* Psi0(n) (:1686-1703), thread per n, sequential log-sum-exp over j (oracle: lse_seq) */
+  /* Psi0(n) (:1686-1703) = n! / (s <1,w>)^n * sum_j a[j] d[n-j], a[j] = exp(cK[M-j] + le[j] + j log s - amax) */
+  if (warp == 0) {
+    float mx = PHD_LOG0;
+    for (int j = lane; j <= M; j += 32)
+      mx = fmaxf(mx, (float)((double)cphd_clamp(s_cK[M - j] + s_le[j]) + (double)j * lsd));
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL_MASK, mx, off));
+    if (lane == 0) s_sc[5] = mx;
+  }
+  __syncthreads();
+  const float amax = s_sc[5];
+  for (int j = tid; j <= M; j += UPD_THREADS)
+    s_a[j] = cphd_expd(((double)cphd_clamp(s_cK[M - j] + s_le[j]) + (double)j * lsd) - (double)amax);
+  __syncthreads();
   for (int n = tid; n < N1; n += UPD_THREADS) {
     const int stop = min(n, M);
-    float mx = -INFINITY;
-    for (int j = 0; j <= stop; ++j)
-      mx = fmaxf(mx, cphd_clamp(((s_cK[M - j] + (s_lf[n] - s_lf[n - j])) + cphd_mulk(n - j, lq)) + s_le[j]));
-    float sum = 0.0f;
-    for (int j = 0; j <= stop; ++j)
-      sum = sum + phd_expf(cphd_clamp(((s_cK[M - j] + (s_lf[n] - s_lf[n - j])) + cphd_mulk(n - j, lq)) + s_le[j]) - mx);
-    s_psi[n] = cphd_clamp((phd_safe_log(sum) + mx) - cphd_mulk(n, lW));
+    double sum = 0.0;
+    for (int j = 0; j <= stop; ++j) sum = __fma_rn(s_a[j], s_d[n - j], sum);
+    s_psi[n] = cphd_clamp((float)((((double)cphd_logd(sum) + (double)amax) + (double)s_lf[n]) - (double)n * CPHD_LOG_NC));
   }
   __syncthreads();
   if (warp == 0) {        /* <Psi0, p> (:1717-1722) */

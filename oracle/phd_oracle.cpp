@@ -889,15 +889,17 @@ static inline float logd(double v) {
   double mant = frexp(v, &ex);
   return phd_logf((float)mant) + (float)ex * 0.693147182f;
 }
-/* log-sum-exp of t[0..n): max, then sum of exp(t - max) in ascending order */
-static float lse_seq(const float* t, int n) {
-  if (n <= 0) return PHD_LOG0;
-  float mx = t[0];
-  for (int i = 1; i < n; ++i) mx = (t[i] > mx) ? t[i] : mx;
-  float s = 0.0f;
-  for (int i = 0; i < n; ++i) s = s + phd_expf(t[i] - mx);
-  return phd_safe_log(s) + mx;
+/* exp of a double argument as a double with float accuracy and double RANGE: t = k ln2 + r, exp(t) = 2^k * expf(r).
+ * Only IEEE double operations, the deterministic float exp and an exact scaling: identical in the kernel. */
+static inline double expd(double t) {
+  if (t != t) return t;
+  if (!(t > -700.0)) return 0.0;
+  if (t > 700.0) t = 700.0;
+  const double kd = rint(t * 1.4426950408889634);
+  const double r = fma(-kd, 0.6931471805599453, t);
+  return ldexp((double)phd_expf((float)r), (int)kd);
 }
+#define CPHD_LOG_NC 4.852030263919617 /* log 128: cardinality scale of the linear-domain sums */
 
 /* log-sum-exp with the kernels' warp reduction shape: max, then warp_sum of exp(t - max) */
 static float lse_warp(float* t, int n) {
@@ -987,24 +989,45 @@ static void cphd_factors(const phdslam_config_t& c, const float* w, const float*
   const float lW = (Wsum > 0.0f) ? phd_logf(Wsum) : 0.0f;
   std::vector<float> cK(M + 1);
   for (int k = 0; k <= M; ++k) cK[k] = mulk(k, lcr) - c.clutter_rate;
-  auto logP = [&](int n, int j) -> float { return (j <= n) ? lf[n] - lf[n - j] : PHD_LOG0; };
+  /* The two (N+1) x (M+1) tables of the update -- Psi0(n) and A1[j] below -- are sums of products n!/(n-j)! q^(n-j) ...,
+   * i.e. CONVOLUTIONS with d[k] = (q s)^k / k!.  The reference evaluates every term as one exponential of a log-domain
+   * sum (:1686-1703, :1706-1764); canonically they are evaluated in the linear domain in double, one fused multiply-add
+   * per term and 3 (N+1) + M + 1 exponentials in all.  s = 128 / <1,w> centres k!/128^k so that every factor stays
+   * inside the double range for any map weight (k <= 1023); a term that still underflows is below e^-700 of the sum. */
+  const double lsd = CPHD_LOG_NC - (double)lW;                                           /* log s */
+  const double lqs = (double)lq + lsd;
+  std::vector<double> cc(N1), dd(N1), aa(M + 1);
+  for (int n = 0; n <= N; ++n) {
+    cc[n] = expd(((double)pm[n] + (double)lf[n]) - (double)n * CPHD_LOG_NC);             /* p-(n) n! / (s <1,w>)^n */
+    dd[n] = (n == 0) ? 1.0 : expd((double)n * lqs - (double)lf[n]);                      /* (q s)^n / n! */
+  }
   /* Psi0(n) (:1686-1703) and the updated cardinality (:1767-1768) */
   std::vector<float> psi0(N1), v(N1), t(std::max(M + 1, N1));
+  float amax = PHD_LOG0;
+  for (int j = 0; j <= M; ++j) {
+    t[j] = lclamp(cK[M - j] + le[j]);
+    const float u = (float)((double)t[j] + (double)j * lsd);
+    amax = (u > amax) ? u : amax;
+  }
+  for (int j = 0; j <= M; ++j) aa[j] = expd(((double)t[j] + (double)j * lsd) - (double)amax);
   for (int n = 0; n <= N; ++n) {
     int stop = std::min(n, M);
-    for (int j = 0; j <= stop; ++j) t[j] = lclamp(((cK[M - j] + logP(n, j)) + mulk(n - j, lq)) + le[j]);
-    psi0[n] = lclamp(lse_seq(t.data(), stop + 1) - mulk(n, lW));
+    double sum = 0.0;
+    for (int j = 0; j <= stop; ++j) sum = fma(aa[j], dd[n - j], sum);
+    psi0[n] = lclamp((float)((((double)logd(sum) + (double)amax) + (double)lf[n]) - (double)n * CPHD_LOG_NC));
     v[n] = lclamp(psi0[n] + pm[n]);
   }
   for (int n = 0; n <= N; ++n) t[n] = v[n];
   const float ip0 = lse_warp(t.data(), N1);                                             /* :1717-1722 */
   for (int n = 0; n <= N; ++n) card_out[n] = lclamp((pm[n] + psi0[n]) - ip0);
-  /* A1[j] = log sum_n p(n) P(n,j+1) <q_D,w>^(n-j-1) / <1,w>^n */
+  /* A1[j] = log sum_{n>j} p(n) P(n,j+1) <q_D,w>^(n-j-1) / <1,w>^n = log(s^(j+1) sum_n c[n] d[n-j-1]):
+   * four strided partial sums (n = j+1+p, step 4), combined (p0+p1)+(p2+p3) */
   std::vector<float> A1(M + 1);
   for (int j = 0; j <= M; ++j) {
-    int cnt = 0;
-    for (int n = j + 1; n <= N; ++n) t[cnt++] = lclamp(((pm[n] + logP(n, j + 1)) + mulk(n - j - 1, lq)) - mulk(n, lW));
-    A1[j] = lse_warp(t.data(), cnt);
+    double part[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int n = j + 1; n <= N; ++n) part[(n - j - 1) & 3] = fma(cc[n], dd[n - j - 1], part[(n - j - 1) & 3]);
+    const double sum = (part[0] + part[1]) + (part[2] + part[3]);
+    A1[j] = lclamp((float)((double)logd(sum) + (double)(j + 1) * lsd));
   }
   for (int j = 0; j <= M; ++j) t[j] = lclamp((cK[M - j] + le[j]) + A1[j]);
   const float ip1 = lse_warp(t.data(), M + 1);                                          /* <Psi1, p>, :1706-1735 */
