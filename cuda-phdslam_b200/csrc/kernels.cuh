@@ -347,10 +347,10 @@ __host__ __device__ static inline size_t update_smem_bytes(int Cmax) {
 
 static inline size_t cphd_smem_bytes(int n_card) {
   /* floats: lf | pm | psi (prior, then psi0) | pb, A1, le, cK (257 each) | llam, ip1d (256 each) | 16 scalars
-   * doubles: x[256] | UPD_WARPS ESF arrays (also c[n_card], then a[M+1]) | d[n_card] */
+   * doubles: x[256] | e (full ESF), a, g (CPHD_E_STRIDE each) | c[n_card] | d[n_card] */
   size_t floats = (size_t)PHD_LF_MAX + 2 * (size_t)n_card + 4 * 257 + 2 * 256 + 16;
   floats = (floats + 1) & ~(size_t)1;
-  return floats * sizeof(float) + (256 + (size_t)(UPD_THREADS / 32) * CPHD_E_STRIDE + (size_t)n_card) * sizeof(double);
+  return floats * sizeof(float) + (256 + 3 * (size_t)CPHD_E_STRIDE + 2 * (size_t)n_card) * sizeof(double);
 }
 
 __device__ __forceinline__ float cphd_mulk(int k, float x) { return k == 0 ? 0.0f : (float)k * x; }
@@ -482,10 +482,11 @@ __device__ void cphd_block(const DevCfg& c, int C, int M, const float* __restric
   size_t foff = (size_t)PHD_LF_MAX + 2 * (size_t)N1 + 4 * 257 + 2 * 256 + 16;
   foff = (foff + 1) & ~(size_t)1;
   double* s_x = reinterpret_cast<double*>(reinterpret_cast<float*>(smem_cphd) + foff);
-  double* s_e = s_x + 256;
-  double* s_d = s_e + (size_t)UPD_WARPS * CPHD_E_STRIDE;   /* d[k] = (q s)^k / k!, k = 0..N */
-  double* s_c = s_e;                                       /* c[n] = p-(n) n! / (s <1,w>)^n: dead before the ESFs start */
-  double* s_a = s_e;                                       /* a[j] of Psi0: after the ESFs */
+  double* s_ef = s_x + 256;                  /* elementary symmetric functions e_0..e_M of all the (scaled) roots */
+  double* s_a = s_ef + CPHD_E_STRIDE;        /* a[j] of Psi0 */
+  double* s_g = s_a + CPHD_E_STRIDE;         /* g[j] of <Psi1d_m, p> */
+  double* s_c = s_g + CPHD_E_STRIDE;         /* c[n] = p-(n) n! / (s <1,w>)^n, n = 0..N */
+  double* s_d = s_c + N1;                    /* d[k] = (q s)^k / k!, k = 0..N */
 
   const int nlf = max(N, M) + 1;
   const float wb = c.birth_weight;
@@ -543,36 +544,24 @@ __device__ void cphd_block(const DevCfg& c, int C, int M, const float* __restric
     s_d[n] = (n == 0) ? 1.0 : cphd_expd((double)n * lqs - (double)s_lf[n]);
   }
   __syncthreads();
-  /* A1[j] = log(s^(j+1) sum_{n>j} c[n] d[n-j-1]): four lanes per j, n = j+1+p step 4, combined (p0+p1)+(p2+p3) */
-  for (int j0 = 0; j0 <= M; j0 += UPD_THREADS / 4) {
-    const int j = j0 + (tid >> 2), p = tid & 3;
-    double part = 0.0;
-    if (j <= M)
-      for (int n = j + 1 + p; n <= N; n += 4) part = __fma_rn(s_c[n], s_d[n - j - 1], part);
-    part = part + __shfl_xor_sync(FULL_MASK, part, 1);
-    part = part + __shfl_xor_sync(FULL_MASK, part, 2);
-    if (j <= M && p == 0) s_A1[j] = cphd_clamp((float)((double)cphd_logd(part) + (double)(j + 1) * lsd));
-  }
-  __syncthreads();
-  /* elementary symmetric functions of the scaled roots (:1553-1616): job 0 = all roots, job m+1 = leave m out */
-  {
-    double* E = s_e + (size_t)warp * CPHD_E_STRIDE;
-    for (int job = warp; job <= M; job += UPD_WARPS) {
-      cphd_esf_warp(s_x, M, job - 1, E, lane);
-      if (job == 0) {
-        for (int j = lane; j <= M; j += 32) s_le[j] = cphd_logd(E[j]) + cphd_mulk(j, lmax);
-      } else {
-        /* <Psi1d_m, p> (:1738-1764) */
-        float v = cphd_lse_warp(M, [&](int j) {
-          return cphd_clamp((s_cK[M - 1 - j] + (cphd_logd(E[j]) + cphd_mulk(j, lmax))) + s_A1[j]);
-        });
-        if (lane == 0) s_ip1d[job - 1] = v;
-      }
-      __syncwarp();
+  if (warp == UPD_WARPS - 1) {
+    /* elementary symmetric functions of the scaled roots (:1553-1576), by the last warp while the others do A1 */
+    cphd_esf_warp(s_x, M, -1, s_ef, lane);
+    for (int j = lane; j <= M; j += 32) s_le[j] = cphd_logd(s_ef[j]) + cphd_mulk(j, lmax);
+  } else {
+    /* A1[j] = log(s^(j+1) sum_{n>j} c[n] d[n-j-1]): four lanes per j, n = j+1+p step 4, combined (p0+p1)+(p2+p3) */
+    for (int j0 = 0; j0 <= M; j0 += (UPD_THREADS - 32) / 4) {
+      const int j = j0 + (tid >> 2), p = tid & 3;
+      double part = 0.0;
+      if (j <= M)
+        for (int n = j + 1 + p; n <= N; n += 4) part = __fma_rn(s_c[n], s_d[n - j - 1], part);
+      part = part + __shfl_xor_sync(FULL_MASK, part, 1);
+      part = part + __shfl_xor_sync(FULL_MASK, part, 2);
+      if (j <= M && p == 0) s_A1[j] = cphd_clamp((float)((double)cphd_logd(part) + (double)(j + 1) * lsd));
     }
   }
   __syncthreads();
-  /* Psi0(n) (:1686-1703) = n! / (s <1,w>)^n * sum_j a[j] d[n-j], a[j] = exp(cK[M-j] + le[j] + j log s - amax) */
+  /* normalisers of the two linear functionals below */
   if (warp == 0) {
     float mx = PHD_LOG0;
     for (int j = lane; j <= M; j += 32)
@@ -580,12 +569,47 @@ __device__ void cphd_block(const DevCfg& c, int C, int M, const float* __restric
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL_MASK, mx, off));
     if (lane == 0) s_sc[5] = mx;
+  } else if (warp == 1) {
+    float mx = PHD_LOG0;
+    for (int j = lane; j < M; j += 32) mx = fmaxf(mx, cphd_clamp((s_cK[M - 1 - j] + s_le[j]) + s_A1[j]));
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL_MASK, mx, off));
+    if (lane == 0) s_sc[6] = mx;
   }
   __syncthreads();
-  const float amax = s_sc[5];
-  for (int j = tid; j <= M; j += UPD_THREADS)
+  const float amax = s_sc[5], gmax = s_sc[6];
+  for (int j = tid; j <= M; j += UPD_THREADS) {
     s_a[j] = cphd_expd(((double)cphd_clamp(s_cK[M - j] + s_le[j]) + (double)j * lsd) - (double)amax);
+    if (j < M)
+      s_g[j] = cphd_expd((((double)s_cK[M - 1 - j] + (double)j * (double)lmax) + (double)s_A1[j]) - (double)gmax);
+  }
   __syncthreads();
+  /* <Psi1d_m, p> (:1738-1764) = sum_j g[j] e_j(roots without m): the leave-one-out coefficients come from the full ones
+   * by composite deflation, e'_k = e_k - x_m e'_(k-1) forward up to the crossover ks (first k with e_(k+1) <= x_m e_k),
+   * backward from the top beyond it, O(M) per measurement instead of the reference's O(M^2) recomputation (:1577-1616);
+   * one thread per measurement, the products with g[j] accumulated on the fly (oracle: cphd_factors, the same operations) */
+  for (int m = tid; m < M; m += UPD_THREADS) {
+    const double xm = s_x[m];
+    int ks = M;
+    if (xm > 0.0)
+      for (int k = 0; k < M; ++k)
+        if (s_ef[k + 1] <= xm * s_ef[k]) { ks = k; break; }
+    double acc = 0.0, f = 1.0;
+    for (int k = 0; k < ks; ++k) {
+      if (k > 0) f = __fma_rn(-xm, f, s_ef[k]);
+      acc = __fma_rn(s_g[k], f, acc);
+    }
+    if (ks < M) {
+      const double r = 1.0 / xm;
+      double b = s_ef[M] * r;
+      for (int k = M - 1; k >= ks; --k) {
+        if (k < M - 1) b = (s_ef[k + 1] - b) * r;
+        acc = __fma_rn(s_g[k], b, acc);
+      }
+    }
+    s_ip1d[m] = cphd_clamp((float)((double)cphd_logd(acc) + (double)gmax));
+  }
+  /* Psi0(n) (:1686-1703) = n! / (s <1,w>)^n * sum_j a[j] d[n-j], a[j] = exp(cK[M-j] + le[j] + j log s - amax) */
   for (int n = tid; n < N1; n += UPD_THREADS) {
     const int stop = min(n, M);
     double sum = 0.0;

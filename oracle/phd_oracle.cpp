@@ -968,18 +968,8 @@ static void cphd_factors(const phdslam_config_t& c, const float* w, const float*
   /* full and leave-one-out elementary symmetric functions (:1553-1616) */
   std::vector<double> e(M + 1);
   oracle_esf(x.data(), M, e.data());
-  std::vector<float> le(M + 1), led((size_t)M * std::max(M, 1));
+  std::vector<float> le(M + 1);
   for (int j = 0; j <= M; ++j) le[j] = logd(e[j]) + mulk(j, lmax);
-  {
-    std::vector<double> xs(M), ed(M + 1);
-    for (int m = 0; m < M; ++m) {
-      int k = 0;
-      for (int n = 0; n < M; ++n)
-        if (n != m) xs[k++] = x[n];
-      oracle_esf(xs.data(), M - 1, ed.data());
-      for (int j = 0; j < M; ++j) led[(size_t)m * M + j] = logd(ed[j]) + mulk(j, lmax);
-    }
-  }
   /* <q_D, w> and <1, w> (:1649-1683) */
   std::vector<float> tmp(std::max(C, 1));
   for (int j = 0; j < C; ++j) tmp[j] = w[j] * (1.0f - pd[j]);
@@ -1032,10 +1022,44 @@ static void cphd_factors(const phdslam_config_t& c, const float* w, const float*
   for (int j = 0; j <= M; ++j) t[j] = lclamp((cK[M - j] + le[j]) + A1[j]);
   const float ip1 = lse_warp(t.data(), M + 1);                                          /* <Psi1, p>, :1706-1735 */
   *ND = ip1 - ip0;
-  for (int m = 0; m < M; ++m) {                                                         /* <Psi1d_m, p>, :1738-1764 */
-    for (int j = 0; j < M; ++j) t[j] = lclamp((cK[M - 1 - j] + led[(size_t)m * M + j]) + A1[j]);
-    const float ip1d = lse_warp(t.data(), M);
-    D[m] = ((ip1d - ip0) + lcr) - lcd;                                                  /* :1796-1798 */
+  /* <Psi1d_m, p> (:1738-1764) = sum_j g[j] e_j(roots without m), g[j] = exp(cK[M-1-j] + j lmax + A1[j]): a linear
+   * functional of the leave-one-out elementary symmetric functions.  The reference recomputes the whole O(M^2) Vieta
+   * recursion for every m (:1577-1616, O(M^3) in all); canonically the leave-one-out coefficients come from the full ones
+   * by deflation, e'_k = e_k - x_m e'_(k-1), in O(M) per m: forward up to the crossover ks = first k with
+   * e_(k+1) <= x_m e_k (the peak of e_k x_m^-k: ESF sequences are log-concave), backward from the top beyond it
+   * (Peters-Wilkinson composite deflation: each direction is used where it damps rounding errors; ~1e-15 relative for
+   * coefficients above 1e-100, tests/test_cphd_kat.py), and the products with g[j] are accumulated on the fly. */
+  {
+    float gmax = PHD_LOG0;
+    for (int j = 0; j < M; ++j) {
+      const float u = lclamp((cK[M - 1 - j] + le[j]) + A1[j]);
+      gmax = (u > gmax) ? u : gmax;
+    }
+    std::vector<double> g(std::max(M, 1));
+    for (int j = 0; j < M; ++j)
+      g[j] = expd((((double)cK[M - 1 - j] + (double)j * (double)lmax) + (double)A1[j]) - (double)gmax);
+    for (int m = 0; m < M; ++m) {
+      const double xm = x[m];
+      int ks = M;
+      if (xm > 0.0)
+        for (int k = 0; k < M; ++k)
+          if (e[k + 1] <= xm * e[k]) { ks = k; break; }
+      double acc = 0.0, f = 1.0;
+      for (int k = 0; k < ks; ++k) {                      /* forward: e'_0 = 1, e'_k = e_k - x_m e'_(k-1) */
+        if (k > 0) f = fma(-xm, f, e[k]);
+        acc = fma(g[k], f, acc);
+      }
+      if (ks < M) {                                       /* backward: e'_(M-1) = e_M / x_m, e'_(k-1) = (e_k - e'_k) / x_m */
+        const double r = 1.0 / xm;
+        double b = e[M] * r;
+        for (int k = M - 1; k >= ks; --k) {
+          if (k < M - 1) b = (e[k + 1] - b) * r;
+          acc = fma(g[k], b, acc);
+        }
+      }
+      const float ip1d = lclamp((float)((double)logd(acc) + (double)gmax));
+      D[m] = ((ip1d - ip0) + lcr) - lcd;                                                  /* :1796-1798 */
+    }
   }
   *inc = ip0;                                                                           /* .bak:2666 */
 }

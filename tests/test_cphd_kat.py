@@ -104,6 +104,31 @@ def test_cphd_factors_vs_literal_float64(C, M, N1, seed):
     assert abs(np.sum(np.exp(card.astype(np.float64))) - 1.0) < 2e-3      # a probability distribution
 
 
+@pytest.mark.parametrize("kind", ["all_equal", "half_equal", "wide_spread", "one_dominant", "two_clusters"])
+def test_cphd_leave_one_out_deflation_adversarial_roots(kind):
+    """The oracle obtains the leave-one-out elementary symmetric functions by composite deflation of the full ones
+    (forward below the crossover, backward above it) instead of recomputing them per measurement.  Root sets that break a
+    one-directional deflation -- repeated roots (clutter-only measurements share one lambda), widely spread magnitudes,
+    one dominant root -- must still match the literal formulas, which rebuild every polynomial with numpy.poly."""
+    C, M, N1 = 40, 48, 128
+    cfg, w, pdv, Sm, prior = scenario(C, M, N1, 21)
+    rng = np.random.default_rng(5)
+    if kind == "all_equal":
+        Sm = np.zeros(M, np.float32)                                   # every lambda = w_b * area
+    elif kind == "half_equal":
+        Sm = np.concatenate([np.zeros(M // 2), rng.uniform(0.5, 60.0, M - M // 2)]).astype(np.float32)
+    elif kind == "wide_spread":
+        Sm = (10.0 ** rng.uniform(-6, 3, M)).astype(np.float32)
+    elif kind == "one_dominant":
+        Sm = np.concatenate([np.full(M - 1, 1e-5), [500.0]]).astype(np.float32)
+    else:
+        Sm = np.concatenate([np.full(M // 2, 3.0), np.full(M - M // 2, 0.02)]).astype(np.float32)
+    D, ND, inc, card = O.cphd_factors(cfg, w, pdv, Sm, prior)
+    D2, ND2, inc2, card2, _ = literal_cphd(cfg, w, pdv, Sm, prior)
+    np.testing.assert_allclose(D, D2, rtol=0, atol=3e-3)
+    assert abs(ND - ND2) < 3e-3 and abs(inc - inc2) < 3e-3 + 1e-5 * abs(inc2)
+
+
 def test_cphd_large_measurement_set_is_finite():
     """256 measurements: the linear fp32 recursion of the reference overflows; scaled double does not"""
     cfg, w, pdv, Sm, prior = scenario(100, 256, 257, 9)
