@@ -345,12 +345,18 @@ __host__ __device__ static inline size_t update_smem_bytes(int Cmax) {
 #define CPHD_E_STRIDE 264          /* doubles per warp ESF array (M + 1 <= 257) */
 #define CPHD_KREG 9                /* ceil(257 / 32) */
 
-static inline size_t cphd_smem_bytes(int n_card) {
-  /* floats: lf | pm | psi (prior, then psi0) | pb, A1, le, cK (257 each) | llam, ip1d (256 each) | 16 scalars
-   * doubles: x[256] | e (full ESF), a, g (CPHD_E_STRIDE each) | c[n_card] | d[n_card] */
-  size_t floats = (size_t)PHD_LF_MAX + 2 * (size_t)n_card + 4 * 257 + 2 * 256 + 16;
-  floats = (floats + 1) & ~(size_t)1;
-  return floats * sizeof(float) + (256 + 3 * (size_t)CPHD_E_STRIDE + 2 * (size_t)n_card) * sizeof(double);
+/* shared-memory layout of cphd_block, sized by the cardinality bins AND the measurement count of the step (the arrays
+ * indexed by measurement / ESF degree take M + 1 entries, not 257): 47 KB instead of 62 KB per particle at N = 255,
+ * M = 50, Cmax = 256, which is the difference between 3 and 4 resident CTAs per SM.
+ * floats: lf[nlf] | pm[N1] | psi[N1] (prior pmf, then Psi0) | pb, A1, le, cK, llam, ip1d (Mp each) | 16 scalars
+ * doubles: x, e (full ESF), a, g (Mp each) | c[N1] | d[N1] */
+__host__ __device__ static inline int cphd_mp(int M) { return (M + 4) & ~3; }
+__host__ __device__ static inline int cphd_nlf(int n_card, int M) { return ((n_card - 1 > M ? n_card - 1 : M) + 4) & ~3; }
+__host__ __device__ static inline size_t cphd_float_count(int n_card, int M) {
+  return (size_t)cphd_nlf(n_card, M) + 2 * (((size_t)n_card + 3) & ~(size_t)3) + 6 * (size_t)cphd_mp(M) + 16;
+}
+__host__ __device__ static inline size_t cphd_smem_bytes(int n_card, int M) {
+  return cphd_float_count(n_card, M) * sizeof(float) + (4 * (size_t)cphd_mp(M) + 2 * (size_t)n_card) * sizeof(double);
 }
 
 __device__ __forceinline__ float cphd_mulk(int k, float x) { return k == 0 ? 0.0f : (float)k * x; }
@@ -469,23 +475,22 @@ __device__ void cphd_block(const DevCfg& c, int C, int M, const float* __restric
                            unsigned char* smem_cphd) {
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
   const int N1 = c.n_card, N = N1 - 1;
+  const int Mp = cphd_mp(M), N1p = (N1 + 3) & ~3;
   float* s_lf = reinterpret_cast<float*>(smem_cphd);
-  float* s_pm = s_lf + PHD_LF_MAX;
-  float* s_psi = s_pm + N1;
-  float* s_pb = s_psi + N1;
-  float* s_A1 = s_pb + 257;
-  float* s_le = s_A1 + 257;
-  float* s_cK = s_le + 257;
-  float* s_llam = s_cK + 257;
-  float* s_ip1d = s_llam + 256;
-  float* s_sc = s_ip1d + 256;            /* 16 scalars: 0 lq, 1 lW, 2 lmax, 3 ip0, 4 ip1 */
-  size_t foff = (size_t)PHD_LF_MAX + 2 * (size_t)N1 + 4 * 257 + 2 * 256 + 16;
-  foff = (foff + 1) & ~(size_t)1;
-  double* s_x = reinterpret_cast<double*>(reinterpret_cast<float*>(smem_cphd) + foff);
-  double* s_ef = s_x + 256;                  /* elementary symmetric functions e_0..e_M of all the (scaled) roots */
-  double* s_a = s_ef + CPHD_E_STRIDE;        /* a[j] of Psi0 */
-  double* s_g = s_a + CPHD_E_STRIDE;         /* g[j] of <Psi1d_m, p> */
-  double* s_c = s_g + CPHD_E_STRIDE;         /* c[n] = p-(n) n! / (s <1,w>)^n, n = 0..N */
+  float* s_pm = s_lf + cphd_nlf(N1, M);
+  float* s_psi = s_pm + N1p;
+  float* s_pb = s_psi + N1p;
+  float* s_A1 = s_pb + Mp;
+  float* s_le = s_A1 + Mp;
+  float* s_cK = s_le + Mp;
+  float* s_llam = s_cK + Mp;
+  float* s_ip1d = s_llam + Mp;
+  float* s_sc = s_ip1d + Mp;             /* 16 scalars: 0 lq, 1 lW, 2 lmax, 3 ip0, 4 ip1, 5 amax, 6 gmax */
+  double* s_x = reinterpret_cast<double*>(reinterpret_cast<float*>(smem_cphd) + cphd_float_count(N1, M));
+  double* s_ef = s_x + Mp;                   /* elementary symmetric functions e_0..e_M of all the (scaled) roots */
+  double* s_a = s_ef + Mp;                   /* a[j] of Psi0 */
+  double* s_g = s_a + Mp;                    /* g[j] of <Psi1d_m, p> */
+  double* s_c = s_g + Mp;                    /* c[n] = p-(n) n! / (s <1,w>)^n, n = 0..N */
   double* s_d = s_c + N1;                    /* d[k] = (q s)^k / k!, k = 0..N */
 
   const int nlf = max(N, M) + 1;

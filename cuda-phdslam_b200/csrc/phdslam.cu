@@ -340,7 +340,7 @@ extern "C" int phdslam_create(const phdslam_config_t* cfg, int device, phdslam_t
   CK(cudaFuncSetAttribute(update_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(h->Cmax)));
   CK(cudaFuncSetAttribute(update_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(h->Cmax)));
   if (h->n_card) {
-    const size_t sm = update_smem_bytes(h->Cmax) + cphd_smem_bytes(h->n_card);
+    const size_t sm = update_smem_bytes(h->Cmax) + cphd_smem_bytes(h->n_card, PHD_MAX_MEAS);
     if (sm > 227 * 1024) {
       phdslam_set_error("CPHD: max_components / max_cardinality need more than 227 KB of shared memory per particle");
       free_state(h); delete h;
@@ -678,7 +678,7 @@ static int launch_update_batch(phdslam* h, int M, int p0, int p1, unsigned long 
   a.toff = h->toff; a.tbase = tbase; a.dense = h->dense; a.n_in = h->n_in; a.dlogw = h->dlogw; a.c = h->dc;
   a.cand = h->cand_in + (size_t)(p0 - cand_p0) * h->Smax * 2; a.n_cand = h->n_cand; a.Smax = h->Smax;
   if (h->n_card) {
-    const size_t sm = update_smem_bytes(h->Cmax) + cphd_smem_bytes(h->n_card);
+    const size_t sm = update_smem_bytes(h->Cmax) + cphd_smem_bytes(h->n_card, M);
     if (dense)
       update_kernel<true, true><<<p1 - p0, UPD_THREADS, sm, h->stream>>>(a);
     else
