@@ -595,23 +595,26 @@ __device__ void cphd_block(const DevCfg& c, int C, int M, const float* __restric
    * one thread per measurement, the products with g[j] accumulated on the fly (oracle: cphd_factors, the same operations) */
   for (int m = tid; m < M; m += UPD_THREADS) {
     const double xm = s_x[m];
-    int ks = M;
+    const double r = (xm > 0.0) ? 1.0 / xm : 0.0;
+    int ks = M;                                   /* first k with e_(k+1) <= x_m e_k; no early exit: the loads pipeline */
     if (xm > 0.0)
-      for (int k = 0; k < M; ++k)
-        if (s_ef[k + 1] <= xm * s_ef[k]) { ks = k; break; }
-    double acc = 0.0, f = 1.0;
-    for (int k = 0; k < ks; ++k) {
-      if (k > 0) f = __fma_rn(-xm, f, s_ef[k]);
-      acc = __fma_rn(s_g[k], f, acc);
-    }
-    if (ks < M) {
-      const double r = 1.0 / xm;
-      double b = s_ef[M] * r;
-      for (int k = M - 1; k >= ks; --k) {
-        if (k < M - 1) b = (s_ef[k + 1] - b) * r;
-        acc = __fma_rn(s_g[k], b, acc);
+      for (int k = M - 1; k >= 0; --k)
+        if (s_ef[k + 1] <= xm * s_ef[k]) ks = k;
+    /* forward (k < ks) and backward (k >= ks) recursions are independent: one loop, two dependency chains */
+    double accf = 0.0, accb = 0.0, f = 1.0, b = s_ef[M] * r;
+    const int nb = M - ks, nmax = max(ks, nb);
+    for (int i = 0; i < nmax; ++i) {
+      if (i < ks) {
+        if (i > 0) f = __fma_rn(-xm, f, s_ef[i]);
+        accf = __fma_rn(s_g[i], f, accf);
+      }
+      if (i < nb) {
+        const int k = M - 1 - i;
+        if (i > 0) b = (s_ef[k + 1] - b) * r;
+        accb = __fma_rn(s_g[k], b, accb);
       }
     }
+    const double acc = accf + accb;
     s_ip1d[m] = cphd_clamp((float)((double)cphd_logd(acc) + (double)gmax));
   }
   /* Psi0(n) (:1686-1703) = n! / (s <1,w>)^n * sum_j a[j] d[n-j], a[j] = exp(cK[M-j] + le[j] + j log s - amax) */

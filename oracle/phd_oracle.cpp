@@ -1044,19 +1044,20 @@ static void cphd_factors(const phdslam_config_t& c, const float* w, const float*
       if (xm > 0.0)
         for (int k = 0; k < M; ++k)
           if (e[k + 1] <= xm * e[k]) { ks = k; break; }
-      double acc = 0.0, f = 1.0;
+      double accf = 0.0, accb = 0.0, f = 1.0;
       for (int k = 0; k < ks; ++k) {                      /* forward: e'_0 = 1, e'_k = e_k - x_m e'_(k-1) */
         if (k > 0) f = fma(-xm, f, e[k]);
-        acc = fma(g[k], f, acc);
+        accf = fma(g[k], f, accf);
       }
       if (ks < M) {                                       /* backward: e'_(M-1) = e_M / x_m, e'_(k-1) = (e_k - e'_k) / x_m */
         const double r = 1.0 / xm;
         double b = e[M] * r;
         for (int k = M - 1; k >= ks; --k) {
           if (k < M - 1) b = (e[k + 1] - b) * r;
-          acc = fma(g[k], b, acc);
+          accb = fma(g[k], b, accb);
         }
       }
+      const double acc = accf + accb;                     /* the two directions are independent chains in the kernel */
       const float ip1d = lclamp((float)((double)logd(acc) + (double)gmax));
       D[m] = ((ip1d - ip0) + lcr) - lcd;                                                  /* :1796-1798 */
     }
