@@ -309,6 +309,26 @@ __global__ void scan_apply_kernel(const unsigned long long* __restrict__ in, int
  * each (136 bytes; lane-consecutive records are conflict-free for 64-bit shared loads) */
 enum { F_NR = 0, F_NB, F_S0, F_S12, F_S3, F_NHL, F_BASE, F_K0, F_K1, F_K2, F_K3, F_MX, F_MY, F_CU0, F_CU1, F_CU2, F_CU3 };
 
+/* The update kernel emits the prune survivors in SEGMENTS of consecutive terms: 32 non-detection terms (one warp
+ * ballot), 64 detection terms (one warp iteration of one measurement), one birth term.  One atomicAdd reserves the slots
+ * of a segment, and inside it the survivors take consecutive candidate slots in term order.  merge_fast_kernel rebuilds
+ * (first slot, count) of every segment from the term indices the records carry and restores the reference's term order
+ * (pruneMap keeps it, :3120-3174) with one prefix sum over the segments instead of a radix sort of the term indices. */
+/* segment of term t of a particle with C in-range components and M measurements */
+__device__ __forceinline__ int upd_segment_of(int t, int C, int M) {
+  if (t < C) return t >> 5;
+  const int u = t - C;
+  const int nd = (C + 31) >> 5, nch = (C + 63) >> 6;
+  if (u < M * C) {
+    const int m = u / C;
+    return nd + m * nch + ((u - m * C) >> 6);
+  }
+  return nd + M * nch + (u - M * C);
+}
+__host__ __device__ static inline int upd_nseg_nd(int C) { return (C + 31) >> 5; }
+__host__ __device__ static inline int upd_nchunk(int C) { return (C + 63) >> 6; }
+__host__ __device__ static inline int upd_nseg(int C, int M) { return upd_nseg_nd(C) + M * upd_nchunk(C) + M; }
+
 struct UpdArgs {
   const float* map; const int* count; const uint8_t* cls; const float* pose;
   const float* z;                      /* [3][PHD_MAX_MEAS] range, bearing, label */
@@ -784,15 +804,17 @@ __device__ __forceinline__ void upd_chunk(const float2* __restrict__ rec, int jr
     if (b0 | b1) {
       const unsigned lt_mask = (1u << lane) - 1u;
       slot0 = __shfl_sync(FULL_MASK, slot0, 0);
+      /* slots in TERM order: components 2 lane, 2 lane + 1 follow those of the lower lanes */
+      const int pos = __popc(b0 & lt_mask) + __popc(b1 & lt_mask);
       if (k0) {
-        int slot = slot0 + __popc(b0 & lt_mask);
+        int slot = slot0 + pos;
         if (slot < Smax) {
           cand[2 * slot] = make_float4(c0.x, c1.x, c2.x, c3.x);
           cand[2 * slot + 1] = make_float4(m0.x, m1.x, wt.x, __int_as_float(t));
         }
       }
       if (k1) {
-        int slot = slot0 + __popc(b0) + __popc(b1 & lt_mask);
+        int slot = slot0 + pos + (k0 ? 1 : 0);
         if (slot < Smax) {
           cand[2 * slot] = make_float4(c0.y, c1.y, c2.y, c3.y);
           cand[2 * slot + 1] = make_float4(m0.y, m1.y, wt.y, __int_as_float(t + 1));
@@ -1176,6 +1198,7 @@ struct MrgArgs {
   float* map_out; int* count_out;
   const float4* cand_in;               /* [p1-p0][Smax][2] from the update kernel (unordered) */
   const int* n_cand;                   /* [n] */
+  const int* n_in;                     /* [n] in-range components per particle */
   float4* cand;                        /* [p1-p0][Smax][2] scratch: candidates in canonical (term) order */
   Reductions* red;
   int Smax;
@@ -1822,6 +1845,7 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float s_red[MF_WARPS][5];
   __shared__ int s_cnt2[MF_WARPS];
+  __shared__ int s_scan[MF_WARPS];
   __shared__ int s_flag;                 /* a near list overflowed: the particle goes to merge_kernel */
   __shared__ int s_kzero;                /* first cluster with zero weight (:2821-2822) */
   __shared__ int s_nseeds, s_klimit, s_n, s_pool_n, s_stopr, s_und;
@@ -1880,27 +1904,62 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
     return;
   }
 
-  /* ---- B. survivors of the prune back into term order (pruneMap :3120-3174); weight keys on the way ---- */
+  /* ---- B. survivors of the prune back into term order (pruneMap :3120-3174); weight keys on the way.  The update kernel
+   * emitted them segment by segment (upd_nseg): the slots of a segment are consecutive and in term order, so the first
+   * and last slot of every segment follow from comparing the segment of each record with its slot neighbours', an
+   * exclusive prefix sum of the segment sizes in term order gives every segment its first position. ---- */
+  const int Cin = a.n_in[pl];
+  const int nseg = upd_nseg(Cin, a.M);
+  unsigned short* seg_first = reinterpret_cast<unsigned short*>(K + S);   /* [nseg] (the rest of the gate-record area) */
+  unsigned short* seg_last = seg_first + nseg;
+  if ((size_t)nseg * 4 > (size_t)S * 12) {          /* no room for the table: the general kernel sorts instead */
+    if (tid == 0) a.ovf_list[atomicAdd(&a.red->ovf_n, 1)] = pl;
+    return;
+  }
   for (int i = tid; i < n1; i += MF_THREADS) {
     const float4 r1 = cin[2 * i + 1];
-    K[i] = __float_as_uint(r1.w);
+    Abuf[i] = (unsigned short)upd_segment_of(__float_as_int(r1.w), Cin, a.M);
     Wtmp[i] = ~float_to_ordered_uint(r1.z);
-    Abuf[i] = (unsigned short)i;
+  }
+  for (int sg = tid; sg < nseg; sg += MF_THREADS) {
+    seg_first[sg] = 1;                               /* empty: last - first + 1 = 0 */
+    seg_last[sg] = 0;
   }
   __syncthreads();
-  unsigned short* src = Abuf;
-  unsigned short* dst = Bbuf;
+  for (int i = tid; i < n1; i += MF_THREADS) {
+    const unsigned sg = Abuf[i];
+    if (i == 0 || Abuf[i - 1] != sg) seg_first[sg] = (unsigned short)i;
+    if (i == n1 - 1 || Abuf[i + 1] != sg) seg_last[sg] = (unsigned short)i;
+  }
+  __syncthreads();
   {
-    const int T = a.M + cnt * (a.M + 1);
-    const int bits = 32 - __clz(max(T, 1));
-    for (int shift = 0; shift < bits; shift += 8) {
-      block_radix_pass<false>(K, src, dst, n1, hist, shift);
-      unsigned short* t = src; src = dst; dst = t;
+    const int per = (nseg + MF_THREADS - 1) / MF_THREADS;
+    const int s_lo = min(tid * per, nseg), s_hi = min(s_lo + per, nseg);
+    int sum = 0;
+    for (int sg = s_lo; sg < s_hi; ++sg) sum += (int)seg_last[sg] - (int)seg_first[sg] + 1;
+    int inc = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int t = __shfl_up_sync(FULL_MASK, inc, off);
+      if (lane >= off) inc += t;
+    }
+    if (lane == 31) s_scan[warp] = inc;
+    __syncthreads();
+    int start = inc - sum;
+#pragma unroll
+    for (int w = 0; w < MF_WARPS; ++w)
+      if (w < warp) start += s_scan[w];
+    for (int sg = s_lo; sg < s_hi; ++sg) {
+      const int base = seg_first[sg], cnt = (int)seg_last[sg] - base + 1;
+      for (int i = 0; i < cnt; ++i) {
+        if (start + i < n1) {
+          P1[start + i] = (unsigned short)(base + i);
+          K[start + i] = Wtmp[base + i];
+        }
+      }
+      start += cnt;
     }
   }
-  for (int i = tid; i < n1; i += MF_THREADS) P1[i] = src[i];
-  __syncthreads();
-  for (int i = tid; i < n1; i += MF_THREADS) K[i] = Wtmp[P1[i]];
   /* nearly-in-range components in map order (:3243-3252) */
   if (warp == 0) {
     int n = n1;
@@ -1925,7 +1984,8 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
     /* ---- C. rank by (weight desc, reference tie rule), see merge_kernel step B ---- */
     for (int i = tid; i < n; i += MF_THREADS) Abuf[i] = (unsigned short)i;
     __syncthreads();
-    src = Abuf; dst = Bbuf;
+    unsigned short* src = Abuf;
+    unsigned short* dst = Bbuf;
     block_radix_pass<true>(K, src, dst, n, hist, 0);
     { unsigned short* t = src; src = dst; dst = t; }
     for (int shift = 0; shift < 32; shift += 8) {

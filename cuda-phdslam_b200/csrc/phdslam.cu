@@ -702,6 +702,7 @@ static int launch_merge_batch(phdslam* h, int M, int p0, int p1, cudaStream_t st
   a.map_out = h->map[h->cur ^ 1]; a.count_out = h->count[h->cur ^ 1];
   a.red = h->red; a.Smax = h->Smax; a.c = h->dc; a.p1 = p1;
   a.cand = h->cand + (size_t)(p0 - cand_p0) * h->Smax * 2;
+  a.n_in = h->n_in;
   a.Scap = h->Scap; a.ovf_list = h->ovf_list; a.use_list = 0;
   if (h->Scap > 0 && h->dc.distance_metric == 0) {
     merge_fast_kernel<<<p1 - p0, MF_THREADS, merge_fast_smem_bytes(h->Scap), st>>>(a);
@@ -761,6 +762,7 @@ extern "C" int phdslam_update(phdslam_t* h, const float* z, int M, int fields) {
     for (size_t b = 0; b + 1 < bounds.size(); ++b) maxb = std::max(maxb, bounds[b + 1] - bounds[b]);
     rc = ensure_cand(h, overlap ? (size_t)h->n_local : (size_t)maxb);
     if (rc) return rc;
+
   }
   std::vector<unsigned long long> tb(bounds.size(), 0);
   if (bounds.size() > 2) {
