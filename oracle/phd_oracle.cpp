@@ -920,6 +920,11 @@ static float lse_warp(float* t, int n) {
  *     linear recursion overflows beyond a handful of measurements; its .bak log-domain form needs |.|);
  *   - the sums over n and j of <Psi1, p>, <Psi1d_m, p> are exchanged (A1[j] below), which turns the reference's
  *     O(N M^2) into O(N M + M^2); identical in exact arithmetic;
+ *   - the (N+1) x (M+1) tables Psi0(n), A1[j] and the predicted cardinality are convolutions and are evaluated in the
+ *     linear domain (double, one fused multiply-add per term; float products for the cardinality prediction) instead of
+ *     one exponential of a log-domain sum per term; identical in exact arithmetic, float accuracy;
+ *   - <Psi1d_m, p> takes the leave-one-out elementary symmetric functions from the full ones by composite deflation
+ *     (O(M) per measurement) instead of recomputing the recursion per measurement (O(M^2));
  *   - factorial[k] + cn_clutter[k] is spelled k*log(clutterRate) - clutterRate (:735-737, :1691-1692).
  * HEAD creates the birth terms at update time (one per measurement, weight w_b, always detected), so measurement m's
  * likelihood mass is S_m + w_b (as in the PHD normaliser, :2213-2214), <1,w> includes M*w_b and <q_D,w> does not.
