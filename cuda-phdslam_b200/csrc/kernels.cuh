@@ -1949,15 +1949,19 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
 #pragma unroll
     for (int w = 0; w < MF_WARPS; ++w)
       if (w < warp) start += s_scan[w];
-    for (int sg = s_lo; sg < s_hi; ++sg) {
-      const int base = seg_first[sg], cnt = (int)seg_last[sg] - base + 1;
-      for (int i = 0; i < cnt; ++i) {
-        if (start + i < n1) {
-          P1[start + i] = (unsigned short)(base + i);
-          K[start + i] = Wtmp[base + i];
-        }
-      }
+    for (int sg = s_lo; sg < s_hi; ++sg) {            /* seg_last becomes the first POSITION of the segment */
+      const int cnt = (int)seg_last[sg] - (int)seg_first[sg] + 1;
+      seg_last[sg] = (unsigned short)start;
       start += cnt;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n1; i += MF_THREADS) {        /* slot i -> its position in term order */
+    const unsigned sg = Abuf[i];
+    const int pos = (int)seg_last[sg] + (i - (int)seg_first[sg]);
+    if (pos < n1) {
+      P1[pos] = (unsigned short)i;
+      K[pos] = Wtmp[i];
     }
   }
   /* nearly-in-range components in map order (:3243-3252) */
