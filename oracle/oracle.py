@@ -229,6 +229,17 @@ def cphd_factors(cfg, w, pd, S, prior):
     return D, nd.value, inc.value, card
 
 
+def cphd_predict_cardinality(cfg, prior, M):
+    """(pb[M+1], pm[N1]): binomial birth cardinality and predicted cardinality of one particle (log domain)"""
+    lib = load()
+    prior = np.ascontiguousarray(prior, np.float32)
+    pb = np.zeros(M + 1, np.float32)
+    pm = np.zeros(len(prior), np.float32)
+    lib.oracle_cphd_predict_cardinality.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.oracle_cphd_predict_cardinality(C.byref(cfg), prior.ctypes.data, len(prior), int(M), pb.ctypes.data, pm.ctypes.data)
+    return pb, pm
+
+
 def detmath(fn, x, y=None):
     lib = load()
     x = np.ascontiguousarray(x, dtype=np.float32)

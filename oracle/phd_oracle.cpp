@@ -910,6 +910,50 @@ static float lse_warp(float* t, int n) {
   return phd_safe_log(warp_sum(t, n)) + mx;
 }
 
+/* Birth cardinality Binomial(M, w_b) (src/phdfilter.cu.bak:779-791) and the predicted cardinality of
+ * cardinalityPredictKernel (src/phdfilter.cu:867-888), p-(n) = log sum_j exp(birth(n-j) + prior(j)): the reference's plain
+ * sum of exponentials, canonically evaluated as the convolution of the two pmfs (N1 + M + 1 exponentials instead of
+ * N1 (M + 1)); terms with n-j > M are exactly 0.  lf: log-factorials 0..max(N, M); out: pb[M+1], pm[N1]. */
+static void cphd_predict_cardinality(const phdslam_config_t& c, const float* prior, int N1, int M, const std::vector<float>& lf,
+                                     std::vector<float>& pb, std::vector<float>& pm) {
+  const int N = N1 - 1;
+  const float lwb = phd_safe_log(c.birth_weight), l1wb = phd_safe_log(1.0f - c.birth_weight);
+  pb.assign(M + 1, 0.0f);
+  for (int k = 0; k <= M; ++k) {
+    float t = lf[M] - lf[k];
+    t = t - lf[M - k];
+    t = t + mulk(k, lwb);
+    t = t + mulk(M - k, l1wb);
+    pb[k] = t;
+  }
+  pm.assign(N1, 0.0f);
+  std::vector<float> epb(M + 1), epr(N1);
+  for (int k = 0; k <= M; ++k) epb[k] = phd_expf(pb[k]);
+  for (int n = 0; n <= N; ++n) epr[n] = phd_expf(prior[n]);
+  for (int n = 0; n <= N; ++n) {
+    float sum = 0.0f;
+    for (int j = std::max(0, n - M); j <= n; ++j) sum = fmaf(epb[n - j], epr[j], sum);
+    pm[n] = (sum != 0.0f) ? phd_safe_log(sum) : PHD_LOG0;
+  }
+}
+
+static std::vector<float> cphd_log_factorials(int nlf) {
+  std::vector<float> lf(nlf);
+  lf[0] = 0.0f;
+  for (int k = 1; k < nlf; ++k) lf[k] = lf[k - 1] + phd_safe_log((float)k);           /* .bak:2474-2479 */
+  return lf;
+}
+
+/* test entry: pb_out[M+1] birth cardinality, pm_out[N1] predicted cardinality (pinned against the reference's
+ * cardinalityPredictKernel in tests/test_ref_pin.py) */
+extern "C" void oracle_cphd_predict_cardinality(const phdslam_config_t* cfg, const float* prior, int N1, int M, float* pb_out,
+                                                float* pm_out) {
+  std::vector<float> lf = cphd_log_factorials(std::max(N1 - 1, M) + 1), pb, pm;
+  cphd_predict_cardinality(*cfg, prior, N1, M, lf, pb, pm);
+  memcpy(pb_out, pb.data(), pb.size() * sizeof(float));
+  memcpy(pm_out, pm.data(), pm.size() * sizeof(float));
+}
+
 /*
  * CPHD multi-object terms for ONE particle (Vo, Vo & Cantoni 2007), following the reference's kernels:
  *   cardinalityPredictKernel (src/phdfilter.cu:867-888, live) with the binomial birth cardinality of
@@ -936,29 +980,9 @@ static void cphd_factors(const phdslam_config_t& c, const float* w, const float*
                          const float* prior, int N1, float* D, float* ND, float* inc, float* card_out) {
   const int N = N1 - 1;
   const int nlf = std::max(N, M) + 1;
-  std::vector<float> lf(nlf);
-  lf[0] = 0.0f;
-  for (int k = 1; k < nlf; ++k) lf[k] = lf[k - 1] + phd_safe_log((float)k);           /* .bak:2474-2479 */
-  const float lwb = phd_safe_log(c.birth_weight), l1wb = phd_safe_log(1.0f - c.birth_weight);
-  /* birth cardinality Binomial(M, w_b) (.bak:779-791) */
-  std::vector<float> pb(M + 1);
-  for (int k = 0; k <= M; ++k) {
-    float t = lf[M] - lf[k];
-    t = t - lf[M - k];
-    t = t + mulk(k, lwb);
-    t = t + mulk(M - k, l1wb);
-    pb[k] = t;
-  }
-  /* predicted cardinality (:880-887): the reference's plain sum of exp(birth(n-j) + prior(j)), canonically evaluated as
-   * the convolution of the two pmfs (N1 + M + 1 exponentials instead of N1 (M + 1)); terms with n-j > M are exactly 0 */
-  std::vector<float> pm(N1), epb(M + 1), epr(N1);
-  for (int k = 0; k <= M; ++k) epb[k] = phd_expf(pb[k]);
-  for (int n = 0; n <= N; ++n) epr[n] = phd_expf(prior[n]);
-  for (int n = 0; n <= N; ++n) {
-    float sum = 0.0f;
-    for (int j = std::max(0, n - M); j <= n; ++j) sum = fmaf(epb[n - j], epr[j], sum);
-    pm[n] = (sum != 0.0f) ? phd_safe_log(sum) : PHD_LOG0;
-  }
+  const std::vector<float> lf = cphd_log_factorials(nlf);
+  std::vector<float> pb, pm;
+  cphd_predict_cardinality(c, prior, N1, M, lf, pb, pm);
   const float lcr = phd_safe_log(c.clutter_rate), lcd = phd_safe_log(c.clutter_density);
   const float larea = lcr - lcd;
   /* log lambda_m (:1539-1552) with the birth mass of measurement m */

@@ -77,6 +77,8 @@ float oracle_warp_sum(const float* v, int n);
 void oracle_detmath(int fn, const float* x, const float* y, float* out, float* out2, int n);
 void oracle_philox(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned* out4);
 void oracle_esf(const double* roots, int n, double* out /* n+1 */);
+/* CPHD birth cardinality pb[M+1] and predicted cardinality pm[N1] (cardinalityPredictKernel, src/phdfilter.cu:867-888) */
+void oracle_cphd_predict_cardinality(const phdslam_config_t* cfg, const float* prior, int N1, int M, float* pb_out, float* pm_out);
 /* CPHD multi-object terms of one particle (see phd_oracle.cpp: cphd_factors) */
 void oracle_cphd_factors(const phdslam_config_t* cfg, const float* w, const float* pd, int C, const float* S, int M,
                          const float* prior, int N1, float* D /* M */, float* ND, float* inc, float* card_out /* N1 */);

@@ -187,6 +187,19 @@ def recover(log_weights, poses):
     return e[0], k.value
 
 
+def cardinality_predict(prior, births):
+    """cardinalityPredictKernel (src/phdfilter.cu:867-888): prior [P][N1], births [N1] log-probabilities -> predicted [P][N1].
+    set_config() must carry max_cardinality = N1 - 1."""
+    lib = load()
+    prior = np.ascontiguousarray(prior, np.float32)
+    births = np.ascontiguousarray(births, np.float32)
+    assert prior.ndim == 2 and births.shape == (prior.shape[1],)
+    out = np.zeros_like(prior)
+    lib.ref_cardinality_predict.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.ref_cardinality_predict(prior.ctypes.data, births.ctypes.data, prior.shape[0], out.ctypes.data)
+    return out
+
+
 def neff(log_weights):
     lw = _f32(log_weights)
     return load().ref_neff(lw.ctypes.data, len(lw))

@@ -40,6 +40,7 @@ K="$REF/src/phdfilter.cu"
   extract "$K" 205 242 computeBirth
   extract "$K" 785 825 phdPredictKernelAckerman
   extract "$K" 827 859 phdPredictKernel
+  extract "$K" 867 888 cardinalityPredictKernel
   extract "$K" 1279 1358 computeInRangeKernel
   extract "$K" 1824 1925 preUpdateSynthKernel
   # phdUpdateKernel reads sdata[0] after each per-measurement reduction (`sum += sdata[0]`, :2210) with no

@@ -39,6 +39,9 @@ extern "C" double randu01() { return g_uniforms[g_uniform_pos++]; }
 template <class GaussianType>
 vector<GaussianType> reduceGaussianMixture(vector<GaussianType>, REAL) { abort(); }
 
+/* src/phdfilter.cu:114 `extern __shared__ REAL shmem[]`: the dynamic shared memory of cardinalityPredictKernel */
+static REAL shmem[4096];
+
 #include "ref_kernels.inc"
 #include "ref_host.inc"
 
@@ -96,6 +99,15 @@ extern "C" float ref_sum_by_reduction(const float* v256) {
   static float sdata[256];
   emul_launch(1, kThreads, [&] { sumByReduction(sdata, v256[threadIdx.x], threadIdx.x); });
   return sdata[0];
+}
+
+/* ---- CPHD cardinality prediction: cardinalityPredictKernel (src/phdfilter.cu:867-888), the one CPHD kernel that is
+ * compiled at HEAD: one block per particle, one thread per cardinality n (its launch is commented out at HEAD together
+ * with the rest of the CPHD update; the .bak pipeline launches it with <<<nParticles, maxCardinality+1>>>, .bak:592).
+ * prior [n_particles][N+1], births [N+1] log-probabilities; out [n_particles][N+1]. */
+extern "C" void ref_cardinality_predict(const float* prior, const float* births, int n_particles, float* out) {
+  const int n1 = dev_config.maxCardinality + 1;
+  emul_launch(n_particles, n1, [&] { cardinalityPredictKernel((REAL*)prior, (REAL*)births, nullptr, out); });
 }
 
 /* ---- predict: phdPredictKernelAckerman / phdPredictKernel, launched as src/phdfilter.cu:1119-1170 does.
