@@ -200,6 +200,21 @@ def cardinality_predict(prior, births):
     return out
 
 
+def expected_map(log_weights, sizes, maps, cap=65536):
+    """EAP map: recoverSlamState with mapEstimate = 2 -> computeExpectedMap (src/main.cpp:290-316) + the reference's own
+    reduceGaussianMixture (src/gm_reduce.cpp:57-134, compiled over the Eigen stand-in of oracle/ref_shim/eigen3)"""
+    lib = load()
+    lw = _f32(log_weights)
+    sizes = np.ascontiguousarray(sizes, np.int32)
+    maps = np.ascontiguousarray(maps)
+    out = np.zeros(cap, dtype=maps.dtype)
+    lib.ref_expected_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.ref_expected_map.restype = C.c_int
+    n = lib.ref_expected_map(lw.ctypes.data, sizes.ctypes.data, maps.ctypes.data, len(lw), out.ctypes.data, cap)
+    assert n <= cap
+    return out[:n].copy()
+
+
 def neff(log_weights):
     lw = _f32(log_weights)
     return load().ref_neff(lw.ctypes.data, len(lw))

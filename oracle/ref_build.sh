@@ -16,7 +16,10 @@
 #      reductions (sumByReduction / productByReduction / maxByReduction, :452-531) is followed by __syncwarp()
 #      -- the fix every post-Volta port of that code needs; on the hardware the reference was written for the
 #      warp ran in lock-step and the result is the same;
-#   3. compiles oracle/ref_harness.cpp (ours: marshalling + the host glue between kernels) with them.
+#   3. takes the EAP map reduction out of src/gm_reduce.cpp (GaussianX, its Mahalanobis distance, the
+#      reduceGaussianMixture template) and compiles it over oracle/ref_shim/eigen3/Eigen/* -- a ~100-line stand-in for
+#      the dozen Eigen operations that file uses (Eigen is not installed);
+#   4. compiles oracle/ref_harness.cpp (ours: marshalling + the host glue between kernels) with them.
 # -ffp-contract=off: the CPU build must not fuse a*b+c on its own; -fpermissive -w: 2012-era C++.
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
@@ -63,6 +66,22 @@ M="$REF/src/main.cpp"
   extract "$M" 318 388 recoverSlamState
   extract "$M" 452 501 resampleParticles
 } > "$GEN/ref_host.inc"
+
+# the EAP map reduction (src/gm_reduce.cpp): GaussianX, mahalanobisDistance(GaussianX, GaussianX), compare_gaussians and
+# the reduceGaussianMixture template, verbatim; the Gaussian4D overload of mahalanobisDistance (:39-53, Eigen::Map on
+# fixed-size types, never called by the template) is left out.  Eigen is absent: oracle/ref_shim/eigen3/Eigen/* stands in.
+G="$REF/src/gm_reduce.cpp"
+sed -n "8p" "$G" | grep -q "using namespace Eigen" || { echo "ref_build: gm_reduce.cpp moved" >&2; exit 1; }
+sed -n "10p" "$G" | grep -q "struct GaussianX" || { echo "ref_build: gm_reduce.cpp moved" >&2; exit 1; }
+sed -n "55p" "$G" | grep -q "compare_gaussians" || { echo "ref_build: gm_reduce.cpp moved" >&2; exit 1; }
+{
+  echo "/* ---- gm_reduce.cpp:8,10-28 (GaussianX) ---- */"
+  sed -n "8p;10,28p" "$G"
+  extract "$G" 30 37 mahalanobisDistance
+  echo "/* ---- gm_reduce.cpp:55 ---- */"
+  sed -n "55p" "$G"
+  extract "$G" 57 134 reduceGaussianMixture
+} > "$GEN/ref_gm_reduce.inc"
 
 # device_math.cuh with __syncwarp() after every warp-synchronous reduction step
 sed -E 's/^( *sdata\[tid\] = [a-z_A-Z]+ = .*sdata\[tid *\+ *(32|16|8|4|2|1)\].*;)\s*$/\1 __syncwarp();/' \

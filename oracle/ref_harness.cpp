@@ -3,7 +3,7 @@
  *
  * TEST INFRASTRUCTURE (part of the oracle; see oracle/ref_build.sh for how and why it is built).  The kernels
  * and helpers themselves are #included from oracle/_ref/gen/*.inc, which ref_build.sh cuts verbatim out of
- * /root/reference/src/{phdfilter.cu,main.cpp,device_math.cuh}; this file only
+ * /root/reference/src/{phdfilter.cu,main.cpp,device_math.cuh,gm_reduce.cpp}; this file only
  *   - supplies the globals those kernels expect (`dev_config`, `config`, constant `Z[256]`, randu01()),
  *   - marshals flat C arrays into the kernels' argument lists, using the same buffer layouts the reference's
  *     host wrapper builds (each site cites the wrapper lines it mirrors), and launches them through the
@@ -35,9 +35,13 @@ static const double* g_uniforms = nullptr;
 static size_t g_uniform_pos = 0;
 extern "C" double randu01() { return g_uniforms[g_uniform_pos++]; }
 
-/* src/gm_reduce.h: needs Eigen (absent); only reached when config.mapEstimate & 2 */
-template <class GaussianType>
-vector<GaussianType> reduceGaussianMixture(vector<GaussianType>, REAL) { abort(); }
+/* src/gm_reduce.cpp:8-134, the reference's own EAP map reduction, over the Eigen stand-in of oracle/ref_shim/eigen3 */
+#include <deque>
+#include <algorithm>
+#include "eigen3/Eigen/Core"
+#include "eigen3/Eigen/Cholesky"
+#include "eigen3/Eigen/LU"
+#include "ref_gm_reduce.inc"
 
 /* src/phdfilter.cu:114 `extern __shared__ REAL shmem[]`: the dynamic shared memory of cardinalityPredictKernel */
 static REAL shmem[4096];
@@ -297,6 +301,28 @@ extern "C" void ref_recover(const float* log_weights, const Pose* poses, int n, 
   config.mapEstimate = saved;
   memcpy(expected, &e, sizeof(e));
   *map_particle = (int)p.max_map_static[0].weight;
+}
+
+/* ---- recoverSlamState with mapEstimate = 2: the EAP map, computeExpectedMap (src/main.cpp:290-316) +
+ * reduceGaussianMixture (src/gm_reduce.cpp:57-134).  maps: concatenated, map_sizes[i] components of particle i. ---- */
+extern "C" int ref_expected_map(const float* log_weights, const int* map_sizes, const G2* maps, int n, G2* out, int cap) {
+  SynthSLAM p(n);
+  p.weights.assign(log_weights, log_weights + n);
+  size_t off = 0;
+  for (int i = 0; i < n; ++i) {
+    memset(&p.states[i], 0, sizeof(ConstantVelocityState));
+    p.maps_static[i].assign((const Gaussian2D*)maps + off, (const Gaussian2D*)maps + off + map_sizes[i]);
+    off += (size_t)map_sizes[i];
+  }
+  int saved = config.mapEstimate;
+  config.mapEstimate = 2;
+  ConstantVelocityState e;
+  vector<REAL> cn;
+  recoverSlamState(p, e, cn);
+  config.mapEstimate = saved;
+  const int m = (int)p.exp_map_static.size();
+  for (int i = 0; i < m && i < cap; ++i) memcpy(&out[i], &p.exp_map_static[i], sizeof(G2));
+  return m;
 }
 
 /* nEff exactly as run_synth spells it (src/main.cpp:1281-1284) -- three lines, restated */
