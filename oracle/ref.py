@@ -215,6 +215,24 @@ def expected_map(log_weights, sizes, maps, cap=65536):
     return out[:n].copy()
 
 
+def write_log(directory, expected_pose, map_est, log_weights, poses, resample_idx, cardinality, t):
+    """writeLog (src/main.cpp:848-954) run inside `directory`: appends to state_estimate%05d.log there.
+    set_config() decides maxCardinality / filterType / nPredictParticles."""
+    lib = load()
+    e = np.ascontiguousarray(expected_pose)
+    m = np.ascontiguousarray(map_est)
+    w = _f32(log_weights)
+    p = np.ascontiguousarray(poses)
+    ri = np.ascontiguousarray(resample_idx, np.int32)
+    cn = _f32(cardinality)
+    lib.ref_write_log.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                  C.c_void_p, C.c_int, C.c_int]
+    rc = lib.ref_write_log(os.fsencode(directory), e.ctypes.data, m.ctypes.data if len(m) else None, len(m), w.ctypes.data,
+                           p.ctypes.data, len(w), ri.ctypes.data, cn.ctypes.data, len(cn), int(t))
+    assert rc == 0
+    return os.path.join(directory, "state_estimate%05d.log" % t)
+
+
 def neff(log_weights):
     lw = _f32(log_weights)
     return load().ref_neff(lw.ctypes.data, len(lw))

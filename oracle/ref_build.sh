@@ -65,6 +65,7 @@ M="$REF/src/main.cpp"
   extract "$M" 290 316 computeExpectedMap
   extract "$M" 318 388 recoverSlamState
   extract "$M" 452 501 resampleParticles
+  extract "$M" 848 954 writeLog
 } > "$GEN/ref_host.inc"
 
 # the EAP map reduction (src/gm_reduce.cpp): GaussianX, mahalanobisDistance(GaussianX, GaussianX), compare_gaussians and

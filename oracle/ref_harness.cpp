@@ -38,6 +38,10 @@ extern "C" double randu01() { return g_uniforms[g_uniform_pos++]; }
 /* src/gm_reduce.cpp:8-134, the reference's own EAP map reduction, over the Eigen stand-in of oracle/ref_shim/eigen3 */
 #include <deque>
 #include <algorithm>
+#include <fstream>
+#include <iomanip>
+#include <sstream>
+#include <unistd.h>
 #include "eigen3/Eigen/Core"
 #include "eigen3/Eigen/Cholesky"
 #include "eigen3/Eigen/LU"
@@ -323,6 +327,24 @@ extern "C" int ref_expected_map(const float* log_weights, const int* map_sizes, 
   const int m = (int)p.exp_map_static.size();
   for (int i = 0; i < m && i < cap; ++i) memcpy(&out[i], &p.exp_map_static[i], sizeof(G2));
   return m;
+}
+
+/* ---- writeLog (src/main.cpp:848-954): writes ./state_estimateNNNNN.log (append mode) -- run inside `dir` ---- */
+extern "C" int ref_write_log(const char* dir, const Pose* expected, const G2* map, int n_map, const float* log_weights,
+                             const Pose* poses, int n, const int* idx_resample, const float* cn, int n_cn, int t) {
+  char cwd[4096];
+  if (!getcwd(cwd, sizeof(cwd)) || chdir(dir) != 0) return -1;
+  SynthSLAM p(n);
+  p.weights.assign(log_weights, log_weights + n);
+  for (int i = 0; i < n; ++i) memcpy(&p.states[i], &poses[i], sizeof(Pose));
+  ConstantVelocityState e;
+  memcpy(&e, expected, sizeof(e));
+  vector<Gaussian2D> ms((const Gaussian2D*)map, (const Gaussian2D*)map + n_map);
+  vector<Gaussian4D> md;
+  vector<int> idx(idx_resample, idx_resample + n);
+  vector<REAL> cnv(cn, cn + n_cn);
+  writeLog(p, e, ms, md, idx, cnv, t);
+  return chdir(cwd);
 }
 
 /* nEff exactly as run_synth spells it (src/main.cpp:1281-1284) -- three lines, restated */
