@@ -233,6 +233,41 @@ def write_log(directory, expected_pose, map_est, log_weights, poses, resample_id
     return os.path.join(directory, "state_estimate%05d.log" % t)
 
 
+def load_timestamps(path, cap=1 << 16):
+    lib = load()
+    out = np.zeros(cap, np.float32)
+    lib.ref_load_timestamps.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
+    n = lib.ref_load_timestamps(os.fsencode(path), out.ctypes.data, cap)
+    return out[:n].copy()
+
+
+def load_controls(path, cap=1 << 16):
+    lib = load()
+    out = np.zeros((cap, 2), np.float32)
+    lib.ref_load_controls.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
+    n = lib.ref_load_controls(os.fsencode(path), out.ctypes.data, cap)
+    return out[:n].copy()
+
+
+def load_measurements(path, cap_vals=1 << 18, cap_sets=1 << 14):
+    """loadMeasurements<measurementSet> (src/main.cpp:221-245) with HEAD's `r b label` parser (:192-208): list of (M_k, 3)"""
+    lib = load()
+    out = np.zeros((cap_vals, 3), np.float32)
+    counts = np.zeros(cap_sets, np.int32)
+    lib.ref_load_measurements.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    n = lib.ref_load_measurements(os.fsencode(path), out.ctypes.data, cap_vals, counts.ctypes.data, cap_sets)
+    o = np.concatenate([[0], np.cumsum(counts[:n])])
+    return [out[o[i]:o[i + 1]].copy() for i in range(n)]
+
+
+def load_trajectory(path, cap=1 << 16):
+    lib = load()
+    out = np.zeros(cap, dtype=np.dtype([(k, "f4") for k in ("px", "py", "ptheta", "vx", "vy", "vtheta")]))
+    lib.ref_load_trajectory.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
+    n = lib.ref_load_trajectory(os.fsencode(path), out.ctypes.data, cap)
+    return out[:n].copy()
+
+
 def neff(log_weights):
     lw = _f32(log_weights)
     return load().ref_neff(lw.ctypes.data, len(lw))

@@ -62,6 +62,11 @@ sed -n "3468,3510p" "$K" > "$GEN/ref_births.inc"
 
 M="$REF/src/main.cpp"
 {
+  extract "$M" 147 167 loadTimestamps
+  extract "$M" 169 190 loadControls
+  extract "$M" 192 208 parseMeasurements
+  extract "$M" 221 245 loadMeasurements
+  extract "$M" 247 264 loadTrajectory
   extract "$M" 290 316 computeExpectedMap
   extract "$M" 318 388 recoverSlamState
   extract "$M" 452 501 resampleParticles

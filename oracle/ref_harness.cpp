@@ -347,6 +347,35 @@ extern "C" int ref_write_log(const char* dir, const Pose* expected, const G2* ma
   return chdir(cwd);
 }
 
+/* ---- text inputs: loadTimestamps / loadControls / loadMeasurements / loadTrajectory (src/main.cpp:147-264) ---- */
+extern "C" int ref_load_timestamps(const char* path, float* out, int cap) {
+  vector<REAL> t = loadTimestamps(path);
+  for (size_t i = 0; i < t.size() && (int)i < cap; ++i) out[i] = t[i];
+  return (int)t.size();
+}
+extern "C" int ref_load_controls(const char* path, float* out /* [cap][2] v_encoder, alpha */, int cap) {
+  vector<AckermanControl> u = loadControls(path);
+  for (size_t i = 0; i < u.size() && (int)i < cap; ++i) { out[2 * i] = u[i].v_encoder; out[2 * i + 1] = u[i].alpha; }
+  return (int)u.size();
+}
+extern "C" int ref_load_measurements(const char* path, float* out /* [cap_vals][3] */, int cap_vals, int* counts, int cap_sets) {
+  vector<measurementSet> all;
+  loadMeasurements(path, all);
+  size_t k = 0;
+  for (size_t s = 0; s < all.size(); ++s) {
+    if ((int)s < cap_sets) counts[s] = (int)all[s].size();
+    for (size_t i = 0; i < all[s].size(); ++i, ++k)
+      if ((int)k < cap_vals) { out[3 * k] = all[s][i].range; out[3 * k + 1] = all[s][i].bearing; out[3 * k + 2] = (float)all[s][i].label; }
+  }
+  return (int)all.size();
+}
+extern "C" int ref_load_trajectory(const char* path, Pose* out, int cap) {
+  vector<ConstantVelocityState> t;
+  loadTrajectory(path, t);
+  for (size_t i = 0; i < t.size() && (int)i < cap; ++i) memcpy(&out[i], &t[i], sizeof(Pose));
+  return (int)t.size();
+}
+
 /* nEff exactly as run_synth spells it (src/main.cpp:1281-1284) -- three lines, restated */
 extern "C" float ref_neff(const float* log_weights, int n) {
   REAL nEff = 0;
