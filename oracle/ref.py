@@ -268,6 +268,17 @@ def load_trajectory(path, cap=1 << 16):
     return out[:n].copy()
 
 
+def plan_events(measurement_times, control_times):
+    """the has_timestamps branch of run_synth's loop (src/main.cpp:1188-1230): (z_idx, c_idx, dt) per event"""
+    lib = load()
+    mt, ct = _f32(measurement_times), _f32(control_times)
+    cap = len(mt) + len(ct) + 1
+    z, c, dt = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.float32)
+    lib.ref_plan_events.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    n = lib.ref_plan_events(mt.ctypes.data, len(mt), ct.ctypes.data, len(ct), z.ctypes.data, c.ctypes.data, dt.ctypes.data, cap)
+    return z[:n].copy(), c[:n].copy(), dt[:n].copy()
+
+
 def neff(log_weights):
     lw = _f32(log_weights)
     return load().ref_neff(lw.ctypes.data, len(lw))

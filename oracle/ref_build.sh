@@ -89,6 +89,11 @@ sed -n "55p" "$G" | grep -q "compare_gaussians" || { echo "ref_build: gm_reduce.
   extract "$G" 57 134 reduceGaussianMixture
 } > "$GEN/ref_gm_reduce.inc"
 
+# the input schedule of time-stamped runs is inline in run_synth's loop (src/main.cpp:1188-1230): taken as a block
+sed -n "1187p" "$M" | grep -q "if ( has_timestamps )" || { echo "ref_build: event schedule moved" >&2; exit 1; }
+sed -n "1231p" "$M" | grep -q "else" || { echo "ref_build: event schedule moved" >&2; exit 1; }
+sed -n "1188,1230p" "$M" > "$GEN/ref_events.inc"
+
 # device_math.cuh with __syncwarp() after every warp-synchronous reduction step
 sed -E 's/^( *sdata\[tid\] = [a-z_A-Z]+ = .*sdata\[tid *\+ *(32|16|8|4|2|1)\].*;)\s*$/\1 __syncwarp();/' \
   "$REF/src/device_math.cuh" > "$GEN/device_math_syncwarp.cuh"

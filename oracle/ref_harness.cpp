@@ -376,6 +376,40 @@ extern "C" int ref_load_trajectory(const char* path, Pose* out, int cap) {
   return (int)t.size();
 }
 
+/* ---- the input schedule of a time-stamped run: the has_timestamps branch of run_synth's loop (src/main.cpp:1188-1230),
+ * verbatim, inside a loop with the variables run_synth declares (:1161-1168, globals :83-84).  Output per event: the
+ * measurement set taken (-1 none), the control taken (-1: the current one is kept), config.dt. ---- */
+static REAL current_time = 0, last_time = 0;
+static void setDeviceConfig(const SlamConfig&) {}
+extern "C" int ref_plan_events(const float* mt, int nz, const float* ct, int nc, int* z_out, int* c_out, float* dt_out, int cap) {
+  vector<REAL> measurement_times(mt, mt + nz), control_times(ct, ct + nc);
+  vector<measurementSet> allMeasurements(nz);
+  vector<AckermanControl> all_controls(nc);
+  measurementSet ZZ;
+  AckermanControl current_control;
+  current_control.alpha = 0; current_control.v_encoder = 0;
+  bool do_predict = false;
+  REAL dt = 0;
+  unsigned int z_idx = 0;
+  int c_idx = 0;
+  current_time = last_time = 0;
+  const int nSteps = nz + nc; /* :1116 */
+  int k = 0;
+  for (int n = 0; n < nSteps; n++) {
+    const unsigned int z0 = z_idx;
+    const int c0 = c_idx;
+#include "ref_events.inc"
+    if (k < cap) {
+      z_out[k] = (z_idx > z0) ? (int)z0 : -1;
+      c_out[k] = (c_idx > c0) ? c0 : -1;
+      dt_out[k] = dt;
+    }
+    ++k;
+  }
+  (void)do_predict;
+  return k;
+}
+
 /* nEff exactly as run_synth spells it (src/main.cpp:1281-1284) -- three lines, restated */
 extern "C" float ref_neff(const float* log_weights, int n) {
   REAL nEff = 0;
