@@ -129,3 +129,50 @@ def test_plan_bounds_properties():
     assert b[0] == 0 and b[-1] == 1000 and (np.diff(b) >= 0).all()
     assert b[1] == 0 and b[2] == b[3]                              # empty ranks get empty intervals
     assert abs(int(b[2]) - 625) <= 2                               # 5/8 of the offspring descend from rank 1
+
+
+@pytest.mark.parametrize("world,n,mode,skew", [(3, 101, 0, 0), (4, 1000, 0, 1), (8, 997, 0, 0), (8, 1024, 1, 2), (5, 64, 0, 2)])
+def test_exchange_plan_for_larger_worlds(world, n, mode, skew):
+    """The exchange the GPUs run at N = 4 / 8 (one interval of offspring per (serving rank, owning rank) pair, derived by
+    both ends from the all-gathered totals alone) simulated in one process with the library's own planning functions:
+    every offspring slot is served exactly once, by the rank that owns its ancestor, and the ancestors equal the
+    single-process oracle's.  skew 1: almost all the weight on one rank; skew 2: some ranks carry no weight at all."""
+    sys.path.insert(0, os.path.join(ROOT, "cuda-phdslam_b200"))
+    sys.path.insert(0, ROOT)
+    import phdslam_b200 as P
+    from phdslam_b200 import scene as S
+    from oracle import oracle as O
+    rng = np.random.default_rng(1000 * world + n + mode)
+    w = rng.normal(0, 2, n)
+    lo = [n * r // world for r in range(world + 1)]
+    if skew == 1:
+        w[lo[1]:lo[2]] += 12.0
+    if skew == 2:
+        for r in range(0, world, 2):
+            w[lo[r]:lo[r + 1]] = -200.0                          # exp underflows to an integer weight of 0
+    w = (w - np.log(np.exp(w).sum())).astype(np.float32)
+    u = rng.uniform(0, 1, n + 1)
+    q40 = np.rint(O.detmath("exp", w).astype(np.float64) * float(1 << 40)).astype(np.uint64)
+    totals = np.array([int(q40[lo[r]:lo[r + 1]].astype(object).sum()) for r in range(world)], dtype=np.uint64)
+    total = int(totals.astype(object).sum())
+    bounds = P.plan_migration(totals, n, uniforms=u, resample_mode=mode)
+    assert bounds[0] == 0 and bounds[-1] == n and (np.diff(bounds) >= 0).all()
+    served = np.zeros(n, dtype=np.int64)
+    anc = np.full(n, -1, dtype=np.int64)
+    for me in range(world):                                      # what rank `me` does (phdslam_resample, world > 1)
+        base = int(totals[:me].astype(object).sum())
+        cdf = base + np.cumsum(q40[lo[me]:lo[me + 1]].astype(object))
+        for k in range(world):                                   # k = 0: its own offspring; k > 0: the ring of shifts
+            d = (me + k) % world
+            a, b = max(bounds[me], lo[d]), min(bounds[me + 1], lo[d + 1])
+            for j in range(a, b):
+                R = P.resample_threshold(j, n, total, uniforms=u, resample_mode=mode)
+                i = int(np.searchsorted(np.array(cdf, dtype=object), R, side="right"))
+                assert 0 <= i < lo[me + 1] - lo[me], "offspring %d planned onto rank %d, which does not own its ancestor" % (j, me)
+                served[j] += 1
+                anc[j] = lo[me] + i
+    assert (served == 1).all()
+    cfg = S.scene_config(n, 1, 1, resample_mode=mode)
+    o = O.Oracle(cfg)
+    o.log_weights = w
+    assert (anc == o.resampleParticles(u)).all()
