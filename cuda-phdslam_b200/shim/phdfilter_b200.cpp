@@ -1,0 +1,162 @@
+/*
+ * phdfilter_b200.cpp -- drop-in for the reference's src/phdfilter.cu.
+ *
+ * A maintainer of cheesinglee/cuda-PHDSLAM switches the static-map PHD / CPHD path to this library by compiling THIS file
+ * instead of src/phdfilter.cu (next to the reference's own main.cpp, slamtypes.h, phdfilter.h) and linking -lphdslam.
+ * It defines the functions of src/phdfilter.h:10-34 that src/phdfilter.cu defines and run_synth calls (initRandomNumberGenerators,
+ * setDeviceConfig, phdPredict, phdUpdateSynth), with the reference's types; the device handle lives
+ * across calls, so the per-step re-upload of every map (src/phdfilter.cu:2901-3103) disappears: host state is pushed when
+ * the host has edited it and pulled when the host wants to look at it.
+ *
+ * tests/test_shim_compiles.py compiles it against the reference's headers and links it against libphdslam.so
+ * (CPU container only: the reference tree is not shipped).
+ */
+class MotionModel; /* src/slamtypes.h:335 names it without declaring it */
+#include "slamtypes.h"
+#include "phdfilter.h"
+#include <phdslam.h> /* include/phdslam.h of this repository */
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+extern SlamConfig config; /* src/main.cpp:80 */
+static phdslam_t* g_h = nullptr;
+static bool g_device_is_current = false; /* the device holds the particles the host last pushed (or their successors) */
+
+static_assert(sizeof(Gaussian2D) == sizeof(phdslam_gaussian2d_t), "Gaussian2D layout (src/slamtypes.h:123-127)");
+static_assert(sizeof(ConstantVelocityState) == sizeof(phdslam_pose_t), "ConstantVelocityState layout (src/slamtypes.h:44-51)");
+
+static void check(int rc, const char* what) {
+  if (rc != 0) { /* the reference's checkCudaErrors prints and exits (helper_cuda.h) */
+    fprintf(stderr, "%s: %s\n", what, phdslam_last_error());
+    exit(1);
+  }
+}
+
+static phdslam_config_t to_cfg(const SlamConfig& c) { /* field for field, src/slamtypes.h:142-250 */
+  phdslam_config_t k;
+  phdslam_config_defaults(&k);
+  k.x0 = c.x0; k.y0 = c.y0; k.yaw0 = c.yaw0; k.vx0 = c.vx0; k.vy0 = c.vy0; k.vyaw0 = c.vyaw0;
+  k.motion_type = c.motionType; k.ax = c.ax; k.ay = c.ay; k.ayaw = c.ayaw; k.dt = c.dt;
+  k.min_range = c.minRange; k.max_range = c.maxRange; k.max_bearing = c.maxBearing;
+  k.std_range = c.stdRange; k.std_bearing = c.stdBearing;
+  k.clutter_rate = c.clutterRate; k.clutter_density = c.clutterDensity; k.pd = c.pd;
+  k.n_particles = c.n_particles; k.n_predict_particles = c.nPredictParticles; k.subdivide_predict = c.subdividePredict;
+  k.resample_threshold = c.resampleThresh; k.birth_weight = c.birthWeight; k.birth_noise_factor = c.birthNoiseFactor;
+  k.min_separation = c.minSeparation; k.min_feature_weight = c.minFeatureWeight; k.particle_weighting = c.particleWeighting;
+  k.distance_metric = c.distanceMetric; k.max_cardinality = c.maxCardinality; k.filter_type = c.filterType;
+  k.map_estimate = c.mapEstimate; k.feature_model = c.featureModel;
+  k.l = c.l; k.h = c.h; k.a = c.a; k.b = c.b; k.std_encoder = c.stdEncoder; k.std_alpha = c.stdAlpha;
+  k.labeled_measurements = c.labeledMeasurements;
+  return k;
+}
+
+void initRandomNumberGenerators() {} /* src/phdfilter.cu:142: the library's Philox generator is counter based, nothing to seed per thread */
+
+void setDeviceConfig(const SlamConfig& c) { /* src/phdfilter.cu:3885-3890 */
+  phdslam_config_t k = to_cfg(c);
+  if (!g_h) check(phdslam_create(&k, 0, &g_h), "phdslam_create");
+  else check(phdslam_set_config(g_h, &k), "phdslam_set_config");
+}
+
+/* host -> device: run_synth initialises the particles on the host (src/main.cpp:1129-1144) */
+static void push(SynthSLAM& p) {
+  std::vector<int> sizes;
+  std::vector<phdslam_gaussian2d_t> flat;
+  for (size_t i = 0; i < p.maps_static.size(); ++i) {
+    sizes.push_back((int)p.maps_static[i].size());
+    for (size_t j = 0; j < p.maps_static[i].size(); ++j) {
+      phdslam_gaussian2d_t g;
+      memcpy(&g, &p.maps_static[i][j], sizeof(g));
+      flat.push_back(g);
+    }
+  }
+  flat.push_back(phdslam_gaussian2d_t());
+  check(phdslam_set_poses(g_h, (const phdslam_pose_t*)&p.states[0]), "phdslam_set_poses");
+  check(phdslam_set_log_weights(g_h, &p.weights[0]), "phdslam_set_log_weights");
+  check(phdslam_set_maps(g_h, sizes.data(), flat.data()), "phdslam_set_maps");
+  g_device_is_current = true;
+}
+
+/* device -> host: what run_synth reads between calls (weights for nEff and the log, poses for the log, maps for
+ * writeParticlesMat) */
+static void pull(SynthSLAM& p) {
+  const int n = phdslam_n_local(g_h);
+  p.states.resize(n); p.weights.resize(n); p.maps_static.resize(n); p.resample_idx.resize(n);
+  p.n_particles = n;
+  check(phdslam_get_poses(g_h, (phdslam_pose_t*)&p.states[0]), "phdslam_get_poses");
+  check(phdslam_get_log_weights(g_h, &p.weights[0]), "phdslam_get_log_weights");
+  check(phdslam_get_resample_idx(g_h, &p.resample_idx[0]), "phdslam_get_resample_idx");
+  std::vector<int> sizes(n);
+  check(phdslam_get_map_sizes(g_h, sizes.data()), "phdslam_get_map_sizes");
+  size_t total = 0;
+  for (int i = 0; i < n; ++i) total += (size_t)sizes[i];
+  std::vector<phdslam_gaussian2d_t> flat(total + 1);
+  check(phdslam_get_maps(g_h, flat.data(), total + 1), "phdslam_get_maps");
+  size_t k = 0;
+  for (int i = 0; i < n; ++i) {
+    p.maps_static[i].resize(sizes[i]);
+    for (int j = 0; j < sizes[i]; ++j, ++k) memcpy(&p.maps_static[i][j], &flat[k], sizeof(Gaussian2D));
+  }
+}
+
+void phdPredict(SynthSLAM& particles, ...) { /* src/phdfilter.cu:1080-1257 */
+  if (!g_device_is_current) push(particles);
+  float u[2] = {0.0f, 0.0f};
+  if (config.motionType == ACKERMAN_MOTION) { /* the reference passes the control through C varargs (:1141-1144) */
+    va_list ap;
+    va_start(ap, particles);
+    AckermanControl c = va_arg(ap, AckermanControl);
+    va_end(ap);
+    u[0] = c.v_encoder;
+    u[1] = c.alpha;
+  }
+  check(phdslam_predict(g_h, u, nullptr), "phdslam_predict");
+  pull(particles);
+}
+
+SynthSLAM phdUpdateSynth(SynthSLAM& particles, measurementSet Z) { /* src/phdfilter.cu:3336-3761 */
+  if (!g_device_is_current) push(particles);
+  SynthSLAM before = particles; /* the reference returns the pre-merge copy (particlesPreMerge, src/main.cpp:1268) */
+  std::vector<float> z;
+  for (size_t i = 0; i < Z.size(); ++i) {
+    z.push_back(Z[i].range);
+    z.push_back(Z[i].bearing);
+    z.push_back((float)Z[i].label);
+  }
+  z.push_back(0.0f);
+  check(phdslam_update(g_h, z.data(), (int)Z.size(), 3), "phdslam_update");
+  pull(particles);
+  return before;
+}
+
+/* recoverSlamState(SynthSLAM&, ...) is declared in src/phdfilter.h but DEFINED in src/main.cpp:318-388, on the host copy of
+ * the particles -- which pull() keeps current, so the reference's own definition keeps working unchanged (including its
+ * host EAP reduction, src/gm_reduce.cpp).  This is the device version (fixed-point expected pose, MAP map copy, EAP map
+ * reduced on the GPU); a maintainer calls it instead at src/main.cpp:1274 to skip the host O(n^2) reduction. */
+void recoverSlamStateDevice(SynthSLAM& particles, ConstantVelocityState& expectedPose, vector<REAL>& cn_estimate) {
+  phdslam_estimate_t e;
+  check(phdslam_estimate(g_h, &e), "phdslam_estimate");
+  memcpy(&expectedPose, &e.expected_pose, sizeof(expectedPose));
+  const int cap = 1 << 16;
+  std::vector<phdslam_gaussian2d_t> m(cap);
+  for (int which = 1; which <= 2; which <<= 1) { /* bit 1: MAP map, bit 2: EAP map */
+    if (!(config.mapEstimate & which)) continue;
+    int n = 0;
+    check(phdslam_map_estimate(g_h, which, m.data(), cap, &n), "phdslam_map_estimate");
+    vector<Gaussian2D>& out = (which == 1) ? particles.max_map_static : particles.exp_map_static;
+    out.resize(n);
+    for (int i = 0; i < n; ++i) memcpy(&out[i], &m[i], sizeof(Gaussian2D));
+  }
+  if (config.filterType == CPHD_TYPE) { /* cardinality distribution of the maximum-weight particle (:356-361) */
+    const int n1 = config.maxCardinality + 1, np = phdslam_n_local(g_h);
+    std::vector<float> all((size_t)np * n1);
+    check(phdslam_get_cardinalities(g_h, all.data()), "phdslam_get_cardinalities");
+    cn_estimate.assign(all.begin() + (size_t)e.map_particle * n1, all.begin() + (size_t)(e.map_particle + 1) * n1);
+  }
+}
+
+/* resampleParticles lives in src/main.cpp:453-501; a maintainer who wants the device resampler replaces its body with
+ *   phdslam_resample(g_h, n_particles, nullptr, &particles.resample_idx[0]); pull(particles);
+ * or the whole loop body (src/main.cpp:1244-1297) with one phdslam_step(). */
