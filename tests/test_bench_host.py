@@ -78,3 +78,14 @@ def test_clock_sampler_survives_queries_slower_than_a_step(bench):
     c = _run_sampler(bench, 0.03, 64)
     assert c["sm_mhz"] == 1900.0 and c["samples"] >= 1
     assert c["reasons"] == ["hw_thermal_slowdown"]
+
+
+def test_text_config_runner_oracle_arm():
+    """profiles/text_configs.py (BASELINE configs[0] / configs[1] in full) runs its CPU arm on the bundled text data"""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "profiles", "text_configs.py"), "--impl", "oracle",
+                                   "--max-steps", "4", "--threads", "2"], text=True, timeout=300)
+    lines = [json.loads(l) for l in out.strip().split("\n")]
+    assert [l["particles"] for l in lines] == [256, 4096] and all(l["steps"] == 4 and l["ms_per_step_mean"] > 0 for l in lines)
