@@ -381,7 +381,6 @@ __host__ __device__ static inline size_t cphd_smem_bytes(int n_card, int M) {
 
 __device__ __forceinline__ float cphd_mulk(int k, float x) { return k == 0 ? 0.0f : (float)k * x; }
 __device__ __forceinline__ float cphd_clamp(float t) { return (t < PHD_LOG0) ? PHD_LOG0 : t; }
-#define CPHD_LOG_NC 4.852030263919617 /* log 128: cardinality scale of the linear-domain sums (oracle: the same) */
 /* exp of a double argument with float accuracy and double range (oracle: expd): t = k ln2 + r, exp(t) = 2^k expf(r) */
 __device__ __forceinline__ double cphd_expd(double t) {
   if (t != t) return t;
@@ -562,10 +561,11 @@ __device__ void cphd_block(const DevCfg& c, int C, int M, const float* __restric
    * d[k] = (q s)^k / k!; they are evaluated in the linear domain in double, one fused multiply-add per term (the
    * reference: one exponential of a log-domain sum per term, :1686-1764).  s = 128 / <1,w> keeps every factor inside
    * the double range (oracle: cphd_factors). */
-  const double lsd = CPHD_LOG_NC - (double)lW;
+  const double lnc = phd_cphd_log_nc(N1);              /* log of the cardinality scale (phd_detmath.h) */
+  const double lsd = lnc - (double)lW;
   const double lqs = (double)lq + lsd;
   for (int n = tid; n < N1; n += UPD_THREADS) {
-    s_c[n] = cphd_expd(((double)s_pm[n] + (double)s_lf[n]) - (double)n * CPHD_LOG_NC);
+    s_c[n] = cphd_expd(((double)s_pm[n] + (double)s_lf[n]) - (double)n * lnc);
     s_d[n] = (n == 0) ? 1.0 : cphd_expd((double)n * lqs - (double)s_lf[n]);
   }
   __syncthreads();
@@ -642,7 +642,7 @@ __device__ void cphd_block(const DevCfg& c, int C, int M, const float* __restric
     const int stop = min(n, M);
     double sum = 0.0;
     for (int j = 0; j <= stop; ++j) sum = __fma_rn(s_a[j], s_d[n - j], sum);
-    s_psi[n] = cphd_clamp((float)((((double)cphd_logd(sum) + (double)amax) + (double)s_lf[n]) - (double)n * CPHD_LOG_NC));
+    s_psi[n] = cphd_clamp((float)((((double)cphd_logd(sum) + (double)amax) + (double)s_lf[n]) - (double)n * lnc));
   }
   __syncthreads();
   if (warp == 0) {        /* <Psi0, p> (:1717-1722) */

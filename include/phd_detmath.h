@@ -301,4 +301,15 @@ PHD_HD int64_t phd_fx_from_prod(float w, float x, int bits) {
   return (int64_t)llrint(d);
 }
 
+/* ---------------------------------------------------------------------------
+ * CPHD: log of the cardinality scale n_c of the linear-domain tables (kernels.cuh cphd_block, oracle cphd_factors:
+ * c[n] = p-(n) n! / n_c^n, d[k] = (q n_c / <1,w>)^k / k!).  n!/n_c^n <= 1 needs n_c >= n/e, d[k] <= e^n_c needs
+ * n_c < 709: 128 up to 345 cardinality bins, 256 up to 690, 512 up to the maximum of 1024 bins.
+ * One function for kernel and oracle: the value is a literal on both sides.
+ * ------------------------------------------------------------------------- */
+PHD_HD double phd_cphd_log_nc(int n_bins) {
+  return (n_bins <= 345) ? 4.852030263919617 /* log 128 */ : (n_bins <= 690) ? 5.545177444479562 /* log 256 */
+                                                                            : 6.238324625039508; /* log 512 */
+}
+
 #endif /* PHD_DETMATH_H */

@@ -899,7 +899,6 @@ static inline double expd(double t) {
   const double r = fma(-kd, 0.6931471805599453, t);
   return ldexp((double)phd_expf((float)r), (int)kd);
 }
-#define CPHD_LOG_NC 4.852030263919617 /* log 128: cardinality scale of the linear-domain sums */
 
 /* log-sum-exp with the kernels' warp reduction shape: max, then warp_sum of exp(t - max) */
 static float lse_warp(float* t, int n) {
@@ -1013,11 +1012,12 @@ static void cphd_factors(const phdslam_config_t& c, const float* w, const float*
    * sum (:1686-1703, :1706-1764); canonically they are evaluated in the linear domain in double, one fused multiply-add
    * per term and 3 (N+1) + M + 1 exponentials in all.  s = 128 / <1,w> centres k!/128^k so that every factor stays
    * inside the double range for any map weight (k <= 1023); a term that still underflows is below e^-700 of the sum. */
-  const double lsd = CPHD_LOG_NC - (double)lW;                                           /* log s */
+  const double lnc = phd_cphd_log_nc(N1);                                                /* log of the cardinality scale */
+  const double lsd = lnc - (double)lW;                                           /* log s */
   const double lqs = (double)lq + lsd;
   std::vector<double> cc(N1), dd(N1), aa(M + 1);
   for (int n = 0; n <= N; ++n) {
-    cc[n] = expd(((double)pm[n] + (double)lf[n]) - (double)n * CPHD_LOG_NC);             /* p-(n) n! / (s <1,w>)^n */
+    cc[n] = expd(((double)pm[n] + (double)lf[n]) - (double)n * lnc);             /* p-(n) n! / (s <1,w>)^n */
     dd[n] = (n == 0) ? 1.0 : expd((double)n * lqs - (double)lf[n]);                      /* (q s)^n / n! */
   }
   /* Psi0(n) (:1686-1703) and the updated cardinality (:1767-1768) */
@@ -1033,7 +1033,7 @@ static void cphd_factors(const phdslam_config_t& c, const float* w, const float*
     int stop = std::min(n, M);
     double sum = 0.0;
     for (int j = 0; j <= stop; ++j) sum = fma(aa[j], dd[n - j], sum);
-    psi0[n] = lclamp((float)((((double)logd(sum) + (double)amax) + (double)lf[n]) - (double)n * CPHD_LOG_NC));
+    psi0[n] = lclamp((float)((((double)logd(sum) + (double)amax) + (double)lf[n]) - (double)n * lnc));
     v[n] = lclamp(psi0[n] + pm[n]);
   }
   for (int n = 0; n <= N; ++n) t[n] = v[n];

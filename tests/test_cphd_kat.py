@@ -140,11 +140,9 @@ def test_cphd_large_measurement_set_is_finite():
 @pytest.mark.parametrize("C,M,N1,wscale,pd", [(2, 5, 345, 0.005, 0.95), (200, 60, 345, 1.0, 0.95), (30, 12, 345, 1.0, 1.0),
                                              (0, 3, 345, 1.0, 0.95), (50, 256, 300, 1.0, 0.5), (120, 40, 1024, 1.0, 0.95)])
 def test_cphd_linear_domain_tables_stay_in_range(C, M, N1, wscale, pd):
-    """Psi0 / A1 are evaluated as double-precision convolutions scaled by s = 128/<1,w>.  n!/128^n <= 1 up to n = 345, so for
-    max_cardinality <= 344 no prior can overflow the tables: nearly empty and heavy maps (<1,w> from 0.01 to ~110),
-    q_D = 0 and 256 measurements must all give finite factors, a normalised posterior cardinality and agreement with the
-    literal float64 formulas where those are representable.  Beyond 345 bins (last case: 1024) the tables are exact as long
-    as the predicted cardinality carries no weight far above 128 e (DESIGN.md section 7 states the limit).
+    """Psi0 / A1 are evaluated as double-precision convolutions scaled by s = n_c/<1,w> (n_c = 128 up to 345 bins):
+    nearly empty and heavy maps (<1,w> from 0.01 to ~110), q_D = 0 and 256 measurements must all give finite factors, a
+    normalised posterior cardinality and agreement with the literal float64 formulas where those are representable.
     (The random likelihood masses of `scenario` pull the posterior towards ~40 objects whatever the map weight is; for
     <1,w> above ~150 the Poisson prior is below e^-87 there and the reference's fp32 `exp(birth + prior)` prediction
     (src/phdfilter.cu:880-887), which the oracle restates, flushes it to zero -- a property of the reference's arithmetic,
@@ -166,6 +164,30 @@ def test_cphd_linear_domain_tables_stay_in_range(C, M, N1, wscale, pd):
     if np.isfinite(ND2):
         assert abs(ND - ND2) < 5e-3
     keep = np.isfinite(card2) & (card2 > -60)
+    np.testing.assert_allclose(card[keep], card2[keep], rtol=0, atol=1e-2)
+
+
+@pytest.mark.parametrize("C,N1,pd", [(700, 1024, 0.08), (400, 690, 0.15), (300, 346, 0.2)])
+def test_cphd_large_cardinalities_use_a_larger_table_scale(C, N1, pd):
+    """Hundreds of objects (a low detection probability makes that consistent with 60 measurements): the scale of the
+    linear-domain tables grows with the bin count (phd_cphd_log_nc: 128 up to 345 bins, 256 up to 690, 512 beyond), so that
+    n!/n_c^n stays below 1 over the whole cardinality range.  With the fixed scale of 128 the posterior of the 700-object
+    case came out as LOG0."""
+    M = 60
+    rng = np.random.default_rng(C + M)
+    cfg = S.scene_config(1, C, M, filter_type=1, max_cardinality=N1 - 1, pd=pd)
+    w = rng.uniform(0.5, 1.5, C).astype(np.float32)
+    pdv = np.full(C, pd, np.float32)
+    Sm = rng.uniform(0.5, 60.0, M).astype(np.float32)
+    n = np.arange(N1)
+    lam = float(C)
+    prior = (n * math.log(lam) - lam - gammaln(n + 1.0)).astype(np.float32)
+    D, ND, inc, card = O.cphd_factors(cfg, w, pdv, Sm, prior)
+    D2, ND2, inc2, card2, _ = literal_cphd(cfg, w, pdv, Sm, prior)
+    np.testing.assert_allclose(D, D2, rtol=0, atol=3e-3)
+    assert abs(ND - ND2) < 3e-3 and abs(inc - inc2) < 3e-3 + 1e-5 * abs(inc2)
+    keep = card2 > -40
+    assert abs(int(card.argmax()) - int(card2.argmax())) <= 1 and abs(int(card2.argmax()) - C) < 0.05 * C
     np.testing.assert_allclose(card[keep], card2[keep], rtol=0, atol=1e-2)
 
 
