@@ -559,7 +559,7 @@ __device__ void cphd_block(const DevCfg& c, int C, int M, const float* __restric
   __syncthreads();
   /* The two (N+1) x (M+1) tables of the update -- A1[j] here and Psi0(n) below -- are convolutions with
    * d[k] = (q s)^k / k!; they are evaluated in the linear domain in double, one fused multiply-add per term (the
-   * reference: one exponential of a log-domain sum per term, :1686-1764).  s = 128 / <1,w> keeps every factor inside
+   * reference: one exponential of a log-domain sum per term, :1686-1764).  s = n_c / <1,w> keeps every factor inside
    * the double range (oracle: cphd_factors). */
   const double lnc = phd_cphd_log_nc(N1);              /* log of the cardinality scale (phd_detmath.h) */
   const double lsd = lnc - (double)lW;

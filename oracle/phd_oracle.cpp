@@ -1010,7 +1010,7 @@ static void cphd_factors(const phdslam_config_t& c, const float* w, const float*
   /* The two (N+1) x (M+1) tables of the update -- Psi0(n) and A1[j] below -- are sums of products n!/(n-j)! q^(n-j) ...,
    * i.e. CONVOLUTIONS with d[k] = (q s)^k / k!.  The reference evaluates every term as one exponential of a log-domain
    * sum (:1686-1703, :1706-1764); canonically they are evaluated in the linear domain in double, one fused multiply-add
-   * per term and 3 (N+1) + M + 1 exponentials in all.  s = 128 / <1,w> centres k!/128^k so that every factor stays
+   * per term and 3 (N+1) + M + 1 exponentials in all.  s = n_c / <1,w> centres k!/n_c^k so that every factor stays
    * inside the double range for any map weight (k <= 1023); a term that still underflows is below e^-700 of the sum. */
   const double lnc = phd_cphd_log_nc(N1);                                                /* log of the cardinality scale */
   const double lsd = lnc - (double)lW;                                           /* log s */
