@@ -122,3 +122,19 @@ def test_no_cpu_fallback_without_gpu(lib):
         assert e.code == -1
     else:
         raise AssertionError("PhdSlam must fail loudly without a CUDA device")
+
+
+def test_header_is_plain_c99_and_links(tmp_path):
+    """The drop-in boundary is a C ABI: include/phdslam.h compiles as C99 (-pedantic, no C++), a C program links against
+    libphdslam.so and calls an entry point that needs no device."""
+    import subprocess
+    src = tmp_path / "cabi.c"
+    src.write_text('#include "phdslam.h"\n'
+                   'int main(void) { phdslam_config_t c; phdslam_config_defaults(&c);\n'
+                   '  return (c.n_particles == 512 && phdslam_version() != 0) ? 0 : 1; }\n')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, "cuda-phdslam_b200")
+    exe = str(tmp_path / "cabi")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), str(src),
+                           "-L", lib_dir, "-lphdslam", "-Wl,-rpath," + lib_dir, "-o", exe])
+    assert subprocess.call([exe]) == 0
