@@ -6,6 +6,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 
 from conftest import DATA, GOLDEN, ROOT
 
@@ -138,3 +139,22 @@ def test_header_is_plain_c99_and_links(tmp_path):
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), str(src),
                            "-L", lib_dir, "-lphdslam", "-Wl,-rpath," + lib_dir, "-o", exe])
     assert subprocess.call([exe]) == 0
+
+
+def test_product_path_fails_loudly_without_a_device(tmp_path):
+    """No CPU fallback: on a machine without a GPU phdslam_create reports PHDSLAM_ERR_CUDA and the CLI exits non-zero
+    (skipped where a device is present)."""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    cfg = P.default_config(n_particles=8)
+    with pytest.raises(P.PhdSlamError) as e:
+        P.PhdSlam(cfg, device=0)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([os.path.join(root, "cuda-phdslam_b200", "phdslam"), os.path.join(GOLDEN, "config_ackerman.cfg"), "synth",
+                        "--measurements", os.path.join(DATA, "measurements_synth_ackerman.txt"),
+                        "--controls", os.path.join(DATA, "controls_synth.txt"), "--out", str(tmp_path)],
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
