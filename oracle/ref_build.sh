@@ -55,6 +55,38 @@ K="$REF/src/phdfilter.cu"
 } > "$GEN/ref_kernels.inc"
 [ "$(grep -c 'sum += sdata\[0\] ; __syncthreads() ;' "$GEN/ref_kernels.inc")" -eq 1 ] || { echo "ref_build: barrier patch failed" >&2; exit 1; }
 
+# ---- CPHD: the reference's multi-object update kernels.  HEAD keeps them COMMENTED OUT (every line prefixed with `//`,
+# src/phdfilter.cu:701-748,1430-1822); the live older forms are in src/phdfilter.cu.bak.  Both are made executable here:
+#   head: the commented ranges with the ONE leading `//` of every line removed (nested `////` comments stay comments) --
+#         the newest CPHD arithmetic the reference holds (linear-domain signed ESF recursion, log|.| at the end);
+#   bak : the live kernels of the .bak, verbatim (log-domain ESF recursion whose leave-one-out variant takes fabs() of a
+#         DIFFERENCE of exponentials at every step, and <Psi1d,p> normalised by the wrong maximum: see tests/test_ref_pin.py).
+# extract_commented FILE FIRST LAST NAME: as extract, for a `//`-commented range
+extract_commented() {
+  local file="$1" first="$2" last="$3" name="$4"
+  sed -n "${first},$((first + 2))p" "$file" | grep -q "^//.*$name" || { echo "ref_build: $file:$first is not commented $name" >&2; exit 1; }
+  [ "$(sed -n "${last}p" "$file")" = "//}" ] || { echo "ref_build: $file:$last does not close $name" >&2; exit 1; }
+  [ "$(sed -n "${first},${last}p" "$file" | grep -vc '^//')" -eq "$(sed -n "${first},${last}p" "$file" | grep -c '^$')" ] || { echo "ref_build: $file:$first-$last has live lines" >&2; exit 1; }
+  echo "/* ---- $(basename "$file"):$first-$last ($name, uncommented) ---- */"
+  sed -n "${first},${last}p" "$file" | sed 's#^//##'
+}
+{
+  extract_commented "$K" 543 607 computePreUpdateComponents
+  extract_commented "$K" 702 748 cphdConstantsKernel
+  extract_commented "$K" 1430 1511 cphdPreUpdateKernel
+  extract_commented "$K" 1524 1618 computeEsfKernel
+  extract_commented "$K" 1626 1769 computePsiKernel
+  extract_commented "$K" 1780 1822 cphdUpdateKernel
+} > "$GEN/ref_cphd_head.inc"
+B="$REF/src/phdfilter.cu.bak"
+{
+  extract "$B" 369 415 cphdConstantsKernel
+  extract "$B" 1058 1181 cphdPreUpdateKernel
+  extract "$B" 1194 1278 computeEsfKernel
+  extract "$B" 1286 1428 computePsiKernel
+  extract "$B" 1436 1478 cphdUpdateKernel
+} > "$GEN/ref_cphd_bak.inc"
+
 # the birth-term host loop is inline in phdUpdateSynth (:3468-3510): taken as a block, wrapped by the harness
 sed -n "3468p" "$K" | grep -q "for ( int i = 0 ; i < n_particles ; i++){" || { echo "ref_build: births loop moved" >&2; exit 1; }
 sed -n "3470,3475p" "$K" | grep -q "invert measurement" || { echo "ref_build: births loop moved" >&2; exit 1; }

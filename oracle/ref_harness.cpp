@@ -272,6 +272,69 @@ extern "C" size_t ref_update(const Pose* poses, int n_particles, const int* map_
   return w;
 }
 
+/* ---- CPHD: the reference's multi-object update, HEAD's commented-out kernels (src/phdfilter.cu:701-748,1430-1822, made
+ * live by ref_build.sh) and the live older kernels of src/phdfilter.cu.bak:369-415,1058-1478, each set in its own
+ * namespace.  The launch sequence and shapes are the .bak wrapper's (phdUpdate, .bak:2503-2544; initCphdConstants,
+ * .bak:418-448): cphdConstantsKernel<<<N+1, N+1>>>, cphdPreUpdateKernel<<<ceil(n_update/128), 128>>>,
+ * computeEsfKernel<<<particles, M>>>, computePsiKernel<<<particles, N+1>>>, cphdUpdateKernel<<<particles, M>>>.
+ * The kernels' 256-wide shared-memory reductions need max_cardinality = 255 (as the reference's default run has).
+ * Layout of the update terms (cphdPreUpdateKernel): per particle at (M+1)*off_p: C*M detection terms, FEATURE-major
+ * (feature j, measurement m at j*M + m), then the C non-detection terms. ---- */
+namespace cphd_head {
+#include "ref_cphd_head.inc"
+}
+namespace cphd_bak {
+#include "ref_cphd_bak.inc"
+}
+
+#define CPHD_PIPELINE(NS)                                                                                              \
+  emul_launch(N1, N1, [&] { NS::cphdConstantsKernel(lfact.data(), Ctab.data(), cn_clutter.data()); });                 \
+  if (n_total > 0)                                                                                                     \
+    emul_launch((n_update + 127) / 128, 128, [&] {                                                                     \
+      NS::cphdPreUpdateKernel((Gaussian2D*)features, offsets.data(), n_particles, M, (ConstantVelocityState*)poses,    \
+                              upd.data(), w_partial.data(), qdw.data());                                               \
+    });                                                                                                                \
+  emul_launch(n_particles, M, [&] { NS::computeEsfKernel(w_partial.data(), offsets.data(), M, esf.data(), esfd.data()); }); \
+  emul_launch(n_particles, N1, [&] {                                                                                   \
+    NS::computePsiKernel((Gaussian2D*)features, (REAL*)cn_predict, esf.data(), esfd.data(), offsets.data(), M, qdw.data(), \
+                         lfact.data(), Ctab.data(), cn_clutter.data(), cn_update_out, ip0_out, ip1_out, ip1d_out);     \
+  });                                                                                                                  \
+  emul_launch(n_particles, M, [&] {                                                                                    \
+    NS::cphdUpdateKernel(offsets.data(), M, ip0_out, ip1_out, ip1d_out, (bool*)flags.data(), upd.data());              \
+  });
+
+/* variant 0 = HEAD (uncommented), 1 = .bak.  features: concatenated in-range components, n_in[p] per particle;
+ * cn_predict [n_particles][N+1] log predicted cardinality.  Outputs: terms_out / flags_out [(M+1) * sum n_in],
+ * cn_update_out [n_particles][N+1], ip0/ip1 [n_particles] = log<Psi0,p>, log<Psi1,p>, ip1d [n_particles][M],
+ * esf_out [n_particles][M+1] (log e_j), esfd_out [n_particles][M][M] (log leave-one-out e_j, M-1 used per row),
+ * lambda is not exported by the kernels.  Returns the number of update terms. */
+extern "C" int ref_cphd_update(int variant, const Pose* poses, int n_particles, const G2* features, const int* n_in,
+                               const float* z, int M, int fields, const float* cn_predict, G2* terms_out, char* flags_out,
+                               float* cn_update_out, float* ip0_out, float* ip1_out, float* ip1d_out, float* esf_out,
+                               float* esfd_out) {
+  const int N1 = dev_config.maxCardinality + 1;
+  if (N1 != 256 || M < 1 || M > 256) return -1;
+  set_measurements(z, M, fields);
+  vector<int> offsets(n_particles + 1, 0);
+  for (int p = 0; p < n_particles; ++p) offsets[p + 1] = offsets[p] + n_in[p];
+  const int n_total = offsets[n_particles];
+  const int n_update = n_total * (M + 1);
+  /* initCphdConstants (.bak:418-448, HEAD :751-782 commented): log-factorials on the host, tables by the kernel */
+  vector<REAL> lfact(N1), Ctab((size_t)N1 * N1), cn_clutter(N1);
+  lfact[0] = 0;
+  for (int n = 1; n < N1; n++) lfact[n] = lfact[n - 1] + safeLog((REAL)n);
+  vector<Gaussian2D> upd(std::max(n_update, 1));
+  vector<REAL> w_partial((size_t)std::max(n_total, 1) * M), qdw(std::max(n_total, 1));
+  vector<REAL> esf((size_t)n_particles * (M + 1)), esfd((size_t)n_particles * M * M, 0.0f);
+  vector<char> flags(std::max(n_update, 1), 0);
+  if (variant == 0) { CPHD_PIPELINE(cphd_head) } else { CPHD_PIPELINE(cphd_bak) }
+  if (terms_out) memcpy(terms_out, upd.data(), (size_t)n_update * sizeof(G2));
+  if (flags_out) memcpy(flags_out, flags.data(), (size_t)n_update);
+  if (esf_out) memcpy(esf_out, esf.data(), esf.size() * sizeof(float));
+  if (esfd_out) memcpy(esfd_out, esfd.data(), esfd.size() * sizeof(float));
+  return n_update;
+}
+
 /* ---- resampleParticles<SynthSLAM> (src/main.cpp:452-501); uniforms = every randu01() it consumes, in order ---- */
 extern "C" void ref_resample(const float* log_weights, int n, int n_new, const double* uniforms, int* idx_out,
                              float* new_log_weights_out) {
