@@ -282,3 +282,48 @@ def plan_events(measurement_times, control_times):
 def neff(log_weights):
     lw = _f32(log_weights)
     return load().ref_neff(lw.ctypes.data, len(lw))
+
+
+def cphd_update(poses, features, n_in, Z, cn_predict, variant="head"):
+    """The reference's CPHD multi-object update through the emulator: cphdConstantsKernel, cphdPreUpdateKernel,
+    computeEsfKernel, computePsiKernel, cphdUpdateKernel with the .bak wrapper's launch sequence (.bak:2503-2544).
+    variant "head": HEAD's commented-out kernels (src/phdfilter.cu:543-607,701-748,1430-1822) made live;
+    variant "bak": the live kernels of src/phdfilter.cu.bak:369-415,1058-1478.
+    features: concatenated in-range components (n_in[p] per particle); cn_predict [P][256] log predicted cardinality
+    (set_config() must carry max_cardinality = 255: the kernels' reductions are 256 wide).
+    Returns a dict: detect [sum C][M] and nondetect [sum C] gaussians (weights final), flags, cn_update [P][256],
+    ip0 / ip1 [P] (log<Psi0,p>, log<Psi1,p>), ip1d [P][M], esf [P][M+1], esfd [P][M][M]."""
+    lib = load()
+    p = np.ascontiguousarray(poses, POSE_DTYPE)
+    f = np.concatenate([np.ascontiguousarray(features, GAUSSIAN_DTYPE), np.zeros(1, GAUSSIAN_DTYPE)])
+    n_in = np.ascontiguousarray(n_in, np.int32)
+    z = _f32(Z).reshape(len(Z), -1)
+    M, P = z.shape[0], len(p)
+    cn = np.ascontiguousarray(cn_predict, np.float32)
+    assert cn.shape == (P, 256)
+    ntot = int(n_in.sum())
+    n_upd = ntot * (M + 1)
+    terms = np.zeros(max(n_upd, 1), GAUSSIAN_DTYPE)
+    flags = np.zeros(max(n_upd, 1), np.int8)
+    cn_up = np.zeros((P, 256), np.float32)
+    ip0, ip1, ip1d = np.zeros(P, np.float32), np.zeros(P, np.float32), np.zeros((P, M), np.float32)
+    esf, esfd = np.zeros((P, M + 1), np.float32), np.zeros((P, M, M), np.float32)
+    lib.ref_cphd_update.restype = C.c_int
+    lib.ref_cphd_update.argtypes = [C.c_int] + [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int] + \
+        [C.c_void_p] * 10
+    wp = np.zeros((max(ntot, 1), M), np.float32)
+    n = lib.ref_cphd_update({"head": 0, "bak": 1}[variant], p.ctypes.data, P, f.ctypes.data, n_in.ctypes.data, z.ctypes.data,
+                            M, z.shape[1], cn.ctypes.data, terms.ctypes.data, flags.ctypes.data, cn_up.ctypes.data,
+                            ip0.ctypes.data, ip1.ctypes.data, ip1d.ctypes.data, esf.ctypes.data, esfd.ctypes.data, wp.ctypes.data)
+    assert n == n_upd, n
+    det, nd, dfl, nfl = [], [], [], []
+    off = 0
+    for c in n_in:                                 # per particle: C*M detection terms (feature-major), then C non-detection
+        blk = terms[off * (M + 1):(off + c) * (M + 1)]
+        fl = flags[off * (M + 1):(off + c) * (M + 1)]
+        det.append(blk[:c * M].reshape(c, M)); dfl.append(fl[:c * M].reshape(c, M))
+        nd.append(blk[c * M:]); nfl.append(fl[c * M:])
+        off += c
+    return dict(detect=np.concatenate(det) if det else np.zeros((0, M), GAUSSIAN_DTYPE), nondetect=np.concatenate(nd),
+                detect_flags=np.concatenate(dfl), nondetect_flags=np.concatenate(nfl), cn_update=cn_up, ip0=ip0, ip1=ip1,
+                ip1d=ip1d, esf=esf, esfd=esfd, w_partial=wp[:ntot])

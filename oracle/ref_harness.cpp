@@ -311,7 +311,7 @@ namespace cphd_bak {
 extern "C" int ref_cphd_update(int variant, const Pose* poses, int n_particles, const G2* features, const int* n_in,
                                const float* z, int M, int fields, const float* cn_predict, G2* terms_out, char* flags_out,
                                float* cn_update_out, float* ip0_out, float* ip1_out, float* ip1d_out, float* esf_out,
-                               float* esfd_out) {
+                               float* esfd_out, float* w_partial_out /* [sum n_in][M] partial log-weights */) {
   const int N1 = dev_config.maxCardinality + 1;
   if (N1 != 256 || M < 1 || M > 256) return -1;
   set_measurements(z, M, fields);
@@ -332,6 +332,7 @@ extern "C" int ref_cphd_update(int variant, const Pose* poses, int n_particles, 
   if (flags_out) memcpy(flags_out, flags.data(), (size_t)n_update);
   if (esf_out) memcpy(esf_out, esf.data(), esf.size() * sizeof(float));
   if (esfd_out) memcpy(esfd_out, esfd.data(), esfd.size() * sizeof(float));
+  if (w_partial_out) memcpy(w_partial_out, w_partial.data(), (size_t)n_total * M * sizeof(float));
   return n_update;
 }
 

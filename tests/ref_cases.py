@@ -119,3 +119,98 @@ def ackerman_noise(cfg, draws):
 
 def predict_config(motion_type, n=64):
     return S.scene_config(n, 1, 1, motion_type=motion_type, acc_x=0.5, acc_y=0.2, acc_yaw=0.1, subdivide_predict=2)
+
+
+# ---- CPHD: the reference's multi-object update (HEAD's commented-out kernels made live / the .bak's live kernels, both
+# through the emulator: oracle/ref_build.sh).  The reference creates births BEFORE the update (addBirths, .bak:794-900)
+# and this implementation, like HEAD's PHD path, inside it; with birth_weight = 0 the two coincide, and the predicted
+# cardinality handed to computePsiKernel is the prior.  max_cardinality = 255: the reference's reductions are 256 wide.
+# name -> (P, C, M, seed, variant, cfg overrides)
+#   variant "head": every output of HEAD's kernels is usable while its fp32 LINEAR-domain ESF recursion stays finite
+#                   (roots lambda_m ~ 1e3 for a detected landmark: about a dozen of them overflow 3e38);
+#   variant "bak" : log-domain kernels, finite at any M, but (1) the leave-one-out ESF recursion takes fabs() of a
+#                   DIFFERENCE of exponentials at every step (.bak:1264-1266: not an elementary symmetric function) and
+#                   (2) <Psi1d_m,p> is normalised with the wrong maximum (.bak:1417 `exp(val-max_val0)`).  Both defects
+#                   sit on the detection side only; the detection factor of measurement m is therefore taken from the
+#                   same kernels run on Z \ {z_m}: Psi1d[w,Z](m) = Psi1[w, Z \ {z_m}] (Vo, Vo & Cantoni 2007, eq. 21-22),
+#                   which only exercises the full-ESF code.  tests/test_ref_pin.py checks that identity on HEAD's kernels.
+CPHD_CASES = {
+    "cphd_m1": (3, 10, 1, 1, "head", dict()),
+    "cphd_m8": (3, 12, 8, 2, "head", dict()),
+    "cphd_m8_lowpd": (4, 5, 8, 5, "head", dict(pd=0.6, clutter_rate=5.0)),
+    "cphd_m30": (2, 20, 30, 3, "bak", dict()),
+    "cphd_m30_sparse": (3, 6, 30, 7, "bak", dict(pd=0.8)),
+}
+CPHD_RTOL_WEIGHT = 1e-4     # component weights against the reference kernels' (fp32 log-domain sums of up to 256 x 31 terms)
+CPHD_ATOL_LOG = 1e-4        # log-domain scalars (log<Psi0,p>, log cardinality rows): |a - b| <= 1e-4 + 1e-6 |b|
+
+
+def build_cphd_case(name):
+    Pn, C, M, seed, variant, over = CPHD_CASES[name]
+    cfg = S.scene_config(Pn, C, M, max_components=512, filter_type=1, max_cardinality=255, birth_weight=0.0, **over)
+    sc = S.make_scene(Pn, C, M, seed=seed, n_near=0, n_far=0)
+    # predicted cardinality: Poisson(sum of the map weights), as the .bak wrapper substitutes (.bak:2473-2499)
+    lf = np.concatenate([[0.0], np.cumsum(np.log(np.arange(1, 256, dtype=np.float64)))])
+    cn = np.zeros((Pn, 256), np.float32)
+    off = 0
+    for p in range(Pn):
+        ws = float(sc["maps"]["weight"][off:off + sc["sizes"][p]].astype(np.float64).sum())
+        off += sc["sizes"][p]
+        cn[p] = (np.arange(256) * np.log(ws) - ws - lf).astype(np.float32)
+    sc["cn_predict"] = cn
+    return cfg, sc, variant
+
+
+def reference_cphd(name):
+    """Runs the reference's CPHD kernels (needs oracle/_ref).  Returns the dict stored in tests/golden/ref_cphd_golden.npz."""
+    from oracle import ref as R
+    cfg, sc, variant = build_cphd_case(name)
+    R.set_config(cfg)
+    cls, n_in, _ = R.in_range(sc["maps"], sc["sizes"], sc["poses"])
+    assert (cls == 1).all()
+    r = R.cphd_update(sc["poses"], sc["maps"], n_in, sc["Z"], sc["cn_predict"], variant)
+    M = len(sc["Z"])
+    ip1d = r["ip1d"].copy()
+    detect = r["detect"].copy()
+    if variant == "bak":
+        for m in range(M):                                   # Psi1d(m) = Psi1 on Z without z_m: full-ESF code only
+            rm = R.cphd_update(sc["poses"], sc["maps"], n_in, np.delete(sc["Z"], m, axis=0), sc["cn_predict"], variant)
+            ip1d[:, m] = rm["ip1"]
+        lcr, lcd = np.log(np.float32(cfg.clutter_rate)), np.log(np.float32(cfg.clutter_density))
+        part = np.repeat(np.arange(len(n_in)), n_in)
+        # cphdUpdateKernel's detection weight (.bak:1449-1452) with the repaired factor, in the kernel's fp32 order
+        t = r["w_partial"] + ip1d[part, :] - r["ip0"][part, None] + lcr - lcd
+        detect["weight"] = np.exp(t.astype(np.float32))
+    return dict(in_poses=sc["poses"], in_sizes=sc["sizes"], in_maps=sc["maps"], Z=sc["Z"], cn_predict=sc["cn_predict"],
+                n_in=n_in, detect=detect, nondetect=r["nondetect"], cn_update=r["cn_update"], ip0=r["ip0"], ip1=r["ip1"],
+                ip1d=ip1d, esf=r["esf"])
+
+
+def split_cphd_terms(terms, n_in, M):
+    """this implementation's dense layout [non-detect C | detect m-major M*C | birth M] per particle ->
+    (nondetect [sum C], detect [sum C][M] feature-major as the reference stores them, births [P][M])"""
+    nd, det, births = [], [], []
+    off = 0
+    for c in n_in:
+        t = terms[off:off + c * (M + 1) + M]
+        off += c * (M + 1) + M
+        nd.append(t[:c])
+        det.append(t[c:c + M * c].reshape(M, c).T)
+        births.append(t[c + M * c:])
+    return np.concatenate(nd), np.concatenate(det), np.stack(births)
+
+
+def assert_cphd_matches_reference(ref, terms, n_in, dlogw, card, what):
+    """terms / n_in / dlogw: update_terms() of the implementation under test on the case's inputs; card: its cardinality
+    rows after the update."""
+    M = len(ref["Z"])
+    assert (np.asarray(n_in) == ref["n_in"]).all(), what
+    nd, det, births = split_cphd_terms(terms, n_in, M)
+    assert (births["weight"] == 0).all(), what + ": birth_weight = 0"
+    close(nd["weight"], ref["nondetect"]["weight"], what + " non-detection weights", rtol=CPHD_RTOL_WEIGHT, atol=1e-12)
+    close(det["weight"], ref["detect"]["weight"], what + " detection weights", rtol=CPHD_RTOL_WEIGHT, atol=1e-30)
+    close(det["mean"], ref["detect"]["mean"], what + " detection means", atol=ATOL_POS)
+    close_cov(det["cov"], ref["detect"]["cov"], what + " detection covariances")
+    close(dlogw, ref["ip0"], what + " particle increment log<Psi0,p>", rtol=1e-6, atol=CPHD_ATOL_LOG)
+    live = ref["cn_update"] > -80.0
+    close(np.asarray(card)[live], ref["cn_update"][live], what + " posterior cardinality", rtol=1e-6, atol=CPHD_ATOL_LOG)

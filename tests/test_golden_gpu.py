@@ -76,3 +76,27 @@ def test_cuda_resample_vs_reference(i):
     anc = g.resampleParticles(uniforms=u)
     assert (anc == idx).all()
     RC.close(g.log_weights, GOLD["resample%d/new_logw" % i], "weights after resampling")
+
+
+# ---- CPHD: the sm_100a path against the reference's own CPHD kernels (tests/golden/ref_cphd_golden.npz; what they are
+# and how they were run: tests/test_cphd_ref_pin.py, tests/ref_cases.py CPHD_CASES) ----
+CPHD_GOLD = np.load(os.path.join(GOLDEN, "ref_cphd_golden.npz"))
+
+
+@pytest.mark.parametrize("name", list(RC.CPHD_CASES))
+def test_cuda_cphd_update_vs_reference_kernels(name):
+    cfg, sc, _ = RC.build_cphd_case(name)
+    pre = name + "/"
+    ref = {k[len(pre):]: CPHD_GOLD[k] for k in CPHD_GOLD.files if k.startswith(pre)}
+    g = P.PhdSlam(cfg)
+    g.poses = ref["in_poses"]
+    g.log_weights = sc["log_weights"]
+    g.set_maps(ref["in_sizes"], ref["in_maps"])
+    g.cardinalities = ref["cn_predict"]
+    terms, n_in, dlw = g.update_terms(ref["Z"])
+    lw0 = g.log_weights.astype(np.float64)
+    g.phdUpdateSynth(ref["Z"])
+    RC.assert_cphd_matches_reference(ref, terms, n_in, dlw, g.cardinalities, name)
+    w = lw0 + ref["ip0"].astype(np.float64)
+    w -= np.log(np.sum(np.exp(w - w.max()))) + w.max()
+    RC.close(g.log_weights, w, name + " particle log-weights", atol=2e-5)
