@@ -174,27 +174,30 @@ int main(int argc, char** argv) {
       CHECK(phdslam_set_poses(h, &traj[n]));
       step_index = 0;
     }
+    /* the filter half of the iteration: predict, update, recoverSlamState (main.cpp:1244-1274) */
     phdslam_estimate_t est;
+    memset(&est, 0, sizeof(est));
+    est.map_particle = -1;
     int resampled = 0;
-    int rc = phdslam_step(h, step_index, current_u, z, M, cfg.measurement_fields, &est, &resampled);
-    /* state export: recoverSlamState output + particle set (main.cpp:1274-1279); the particle count changes from
-     * step to step when n_predict_particles > 1 */
+    int rc = phdslam_step_filter(h, step_index, current_u, z, M, cfg.measurement_fields, &est);
+    if (rc != 0 && rc != PHDSLAM_ERR_NAN) {
+      fprintf(stderr, "phdslam: step %d failed (%d): %s\n", n, rc, phdslam_last_error());
+      return 1;
+    }
+    /* state export where the reference looks at the particle set: after recoverSlamState, BEFORE resampleParticles
+     * (main.cpp:1274-1279) -- the weighted particles, the map of the maximum-weight particle, and the resample indices
+     * of the previous step.  The particle count changes from step to step when n_predict_particles > 1. */
     const int P = phdslam_n_local(h);
     poses.resize(P); logw.resize(P); ridx.resize(P);
     CHECK(phdslam_get_poses(h, poses.data()));
     CHECK(phdslam_get_log_weights(h, logw.data()));
     CHECK(phdslam_get_resample_idx(h, ridx.data()));
-    if (cfg.filter_type == 1 && est.map_particle >= 0) {
-      /* cardinality distribution of the maximum-weight particle (recoverSlamState, main.cpp:357-361); the estimate was
-       * taken before the resampling of this step, so look the particle up among the offspring */
-      int j = -1;
-      for (int i = 0; i < P && j < 0; ++i)
-        if (ridx[i] == est.map_particle) j = i;
-      if (j >= 0) {
-        all_card.resize((size_t)P * n_card);
-        CHECK(phdslam_get_cardinalities(h, all_card.data()));
-        std::copy(all_card.begin() + (size_t)j * n_card, all_card.begin() + (size_t)(j + 1) * n_card, card.begin());
-      }
+    if (cfg.filter_type == 1 && est.map_particle >= 0 && est.map_particle < P) {
+      /* cardinality distribution of the maximum-weight particle (recoverSlamState, main.cpp:357-361) */
+      all_card.resize((size_t)P * n_card);
+      CHECK(phdslam_get_cardinalities(h, all_card.data()));
+      std::copy(all_card.begin() + (size_t)est.map_particle * n_card, all_card.begin() + (size_t)(est.map_particle + 1) * n_card,
+                card.begin());
     }
     int n_map = 0;
     if (cfg.map_estimate & 3) {
@@ -209,6 +212,14 @@ int main(int argc, char** argv) {
     snprintf(name, sizeof(name), "/state_estimate%05d.log", n);
     CHECK(phdslam_write_log((out_dir + name).c_str(), cfg.log_layout, &est.expected_pose, map_est.data(), n_map, logw.data(),
                             poses.data(), P, ridx.data(), cfg.filter_type == 1 ? card.data() : nullptr, n_card, cfg.filter_type));
+    /* the nEff test and resampleParticles (main.cpp:1281-1297) */
+    if (rc == 0) {
+      int rrc = phdslam_step_resample(h, M, &est, &resampled);
+      if (rrc != 0) {
+        fprintf(stderr, "phdslam: resampling of step %d failed (%d): %s\n", n, rrc, phdslam_last_error());
+        return 1;
+      }
+    }
     double el = now_ms() - t0;
     if (tf) fprintf(tf, "%g\n", el);
     if (!quiet)
@@ -217,10 +228,6 @@ int main(int argc, char** argv) {
     if (rc == PHDSLAM_ERR_NAN) {
       printf("nan weights detected! exiting...\n");                /* main.cpp:1307-1311 */
       break;
-    }
-    if (rc != 0) {
-      fprintf(stderr, "phdslam: step %d failed (%d): %s\n", n, rc, phdslam_last_error());
-      return 1;
     }
   }
   if (tf) fclose(tf);

@@ -2417,7 +2417,7 @@ __global__ void weights_add_max_kernel(float* __restrict__ logw, const float* __
   unsigned nanb = __ballot_sync(FULL_MASK, isnan_);
   if (lane_id() == 0) {
     atomicMax(&red->max_key, key);
-    if (nanb) atomicAdd(&red->nan_count, __popc(nanb));
+    if (nanb) atomicAdd(&red->nan_count, (unsigned long long)__popc(nanb));
   }
 }
 __global__ void weights_sum_kernel(const float* __restrict__ logw, int n, Reductions* red) {
@@ -2430,6 +2430,7 @@ __global__ void weights_sum_kernel(const float* __restrict__ logw, int n, Reduct
   }
   v = warp_sum_u64(v);
   if (lane_id() == 0 && v) atomicAdd(&red->sum_fx, v);
+  if (i == 0 && red->err_flag) atomicAdd(&red->err_ranks, 1ull);   /* travels with the sum: every rank learns of the error */
 }
 __global__ void weights_normalise_kernel(float* __restrict__ logw, int n, const Reductions* red) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -155,8 +155,21 @@ static int validate_config(const phdslam_config_t* c) {
     phdslam_set_error("CPHD: max_cardinality must be in [1, 1023]");
     return PHDSLAM_ERR_INVALID;
   }
-  if (c->filter_type != 0 && c->filter_type != 1) return PHDSLAM_ERR_INVALID;
-  if (c->subdivide_predict < 1) return PHDSLAM_ERR_INVALID;
+  if (c->filter_type != 0 && c->filter_type != 1) {
+    phdslam_set_error("filter_type must be 0 (PHD) or 1 (CPHD)");
+    return PHDSLAM_ERR_INVALID;
+  }
+  if (c->particle_weighting < 0 || c->particle_weighting > 1) {
+    /* scheme 2 (single-feature, src/phdfilter.cu:3600-3661) is an unfinished host fallback in the reference itself (mirrored
+     * feature index, evalGaussianMixture with the wrong sign and no weights: DESIGN.md section 2); refusing it is better
+     * than a run whose particle weights are silently never updated */
+    phdslam_set_error("particle_weighting must be 0 (cluster process) or 1 (Vo empty map); scheme 2 is not reproduced");
+    return PHDSLAM_ERR_INVALID;
+  }
+  if (c->subdivide_predict < 1) {
+    phdslam_set_error("subdivide_predict must be >= 1");
+    return PHDSLAM_ERR_INVALID;
+  }
   return 0;
 }
 
@@ -297,6 +310,8 @@ static int init_particles(phdslam* h) {
   return 0;
 }
 
+static int create_impl(phdslam* h, const phdslam_config_t* cfg, int device);
+
 extern "C" int phdslam_create(const phdslam_config_t* cfg, int device, phdslam_t** out) {
   if (!cfg || !out) return PHDSLAM_ERR_INVALID;
   int rc = validate_config(cfg);
@@ -309,6 +324,19 @@ extern "C" int phdslam_create(const phdslam_config_t* cfg, int device, phdslam_t
   CK(cudaSetDevice(device));
   phdslam* h = new phdslam();
   memset(h, 0, sizeof(*h));
+  rc = create_impl(h, cfg, device);
+  if (rc) {                      /* nothing leaks on a failed create: streams, events and whatever was allocated go */
+    const std::string why = phdslam_last_error();
+    phdslam_destroy(h);
+    phdslam_set_error(why);
+    return rc;
+  }
+  *out = h;
+  return 0;
+}
+
+static int create_impl(phdslam* h, const phdslam_config_t* cfg, int device) {
+  int rc;
   h->cfg = *cfg;
   h->device = device;
   h->rank = 0; h->world = 1;
@@ -336,14 +364,13 @@ extern "C" int phdslam_create(const phdslam_config_t* cfg, int device, phdslam_t
     h->overlap = (e && atoi(e) != 0) ? 1 : 0;
   }
   rc = alloc_state(h);
-  if (rc) { free_state(h); delete h; return rc; }
+  if (rc) return rc;
   CK(cudaFuncSetAttribute(update_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(h->Cmax)));
   CK(cudaFuncSetAttribute(update_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(h->Cmax)));
   if (h->n_card) {
     const size_t sm = update_smem_bytes(h->Cmax) + cphd_smem_bytes(h->n_card, PHD_MAX_MEAS);
     if (sm > 227 * 1024) {
       phdslam_set_error("CPHD: max_components / max_cardinality need more than 227 KB of shared memory per particle");
-      free_state(h); delete h;
       return PHDSLAM_ERR_INVALID;
     }
     CK(cudaFuncSetAttribute(update_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -365,24 +392,22 @@ extern "C" int phdslam_create(const phdslam_config_t* cfg, int device, phdslam_t
     }
     CK(cudaFuncSetAttribute(merge_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_fast_smem_bytes(h->Scap_max)));
   }
-  rc = init_particles(h);
-  if (rc) { free_state(h); delete h; return rc; }
-  *out = h;
-  return 0;
+  return init_particles(h);
 }
 
 extern "C" void phdslam_destroy(phdslam_t* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->stream);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->stream_m) cudaStreamSynchronize(h->stream_m);
   if (h->nccl_comm) ncclCommDestroy((ncclComm_t)h->nccl_comm);
   free_state(h);
-  for (int i = 0; i < 12; ++i) cudaEventDestroy(h->ev[i]);
-  for (int i = 0; i < PHD_MAX_SUB; ++i) cudaEventDestroy(h->ev_sub[i]);
-  cudaEventDestroy(h->ev_merge_done);
-  cudaStreamSynchronize(h->stream_m);
-  cudaStreamDestroy(h->stream_m);
-  cudaStreamDestroy(h->stream);
+  for (int i = 0; i < 12; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (int i = 0; i < PHD_MAX_SUB; ++i) if (h->ev_sub[i]) cudaEventDestroy(h->ev_sub[i]);
+  if (h->ev_merge_done) cudaEventDestroy(h->ev_merge_done);
+  if (h->stream_m) cudaStreamDestroy(h->stream_m);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  cudaGetLastError();
   delete h;
 }
 
@@ -477,6 +502,10 @@ extern "C" int phdslam_dist_init(phdslam_t* h, int rank, int world, const void* 
     phdslam_set_error("libnccl.so.2 not found");
     return PHDSLAM_ERR_NCCL;
   }
+  if (h->cfg.n_predict_particles > 1) {
+    phdslam_set_error("n_predict_particles > 1 changes the particle count every step and is single-GPU only");
+    return PHDSLAM_ERR_INVALID;
+  }
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
   ncclUniqueId id;
@@ -484,10 +513,6 @@ extern "C" int phdslam_dist_init(phdslam_t* h, int rank, int world, const void* 
   ncclComm_t comm;
   CKN(ncclCommInitRank(&comm, world, id, rank));
   h->nccl_comm = (void*)comm;
-  if (world > 1 && h->cfg.n_predict_particles > 1) {
-    phdslam_set_error("n_predict_particles > 1 changes the particle count every step and is single-GPU only");
-    return PHDSLAM_ERR_INVALID;
-  }
   h->rank = rank;
   h->world = world;
   free_state(h);
@@ -529,6 +554,10 @@ static int check_err_flag(phdslam* h) {
   }
   if (h->red_host->err_flag & 2) {
     phdslam_set_error("a particle's map exceeded max_components");
+    return PHDSLAM_ERR_CAPACITY;
+  }
+  if (h->red_host->err_ranks) {   /* all-reduced with the weight sum: every rank leaves the step with the same status */
+    phdslam_set_error("another rank's update exceeded its map / candidate capacity");
     return PHDSLAM_ERR_CAPACITY;
   }
   return 0;
@@ -721,15 +750,16 @@ static int launch_merge_batch(phdslam* h, int M, int p0, int p1, cudaStream_t st
 /* w += dw; normalise (src/phdfilter.cu:3735-3755) */
 static int update_weights(phdslam* h, bool add) {
   const int n = h->n_local;
-  CK(cudaMemsetAsync(h->red, 0, sizeof(Reductions), h->stream));
+  /* only the weight accumulators are reset: err_flag / max_cand of the update and merge kernels stay for the host */
+  CK(cudaMemsetAsync(h->red, 0, offsetof(Reductions, err_ranks) + sizeof(unsigned long long), h->stream));
   weights_add_max_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->logw, add ? h->dlogw : nullptr, n, h->red);
   LAUNCH_CHECK(h);
   if (h->world > 1) /* global max of the log-weights (ordered-uint keys: max is exact and order independent) */
     CKN(ncclAllReduce(&h->red->max_key, &h->red->max_key, 1, ncclUint32, ncclMax, (ncclComm_t)h->nccl_comm, h->stream));
   weights_sum_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->logw, n, h->red);
   LAUNCH_CHECK(h);
-  if (h->world > 1) /* integer (Q36) sum: identical on every rank for any GPU count */
-    CKN(ncclAllReduce(&h->red->sum_fx, &h->red->sum_fx, 1, ncclUint64, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
+  if (h->world > 1) /* integer (Q36) sum: identical on every rank for any GPU count; NaN and error counts ride along */
+    CKN(ncclAllReduce(&h->red->sum_fx, &h->red->sum_fx, 3, ncclUint64, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
   weights_normalise_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->logw, n, h->red);
   LAUNCH_CHECK(h);
   return 0;
@@ -816,9 +846,9 @@ extern "C" int phdslam_update(phdslam_t* h, const float* z, int M, int fields) {
       upd_ms += t1; mrg_ms += t2;
     }
   }
-  CK(cudaMemcpyAsync(h->red_host, h->red, sizeof(Reductions), cudaMemcpyDeviceToHost, h->stream));
-  rc = update_weights(h, h->cfg.particle_weighting != 2);
+  rc = update_weights(h, true);
   if (rc) return rc;
+  CK(cudaMemcpyAsync(h->red_host, h->red, sizeof(Reductions), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaEventRecord(h->ev[6], h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->cur ^= 1; /* merged maps become the front buffer; poses and weights are single-buffered in place */
@@ -839,6 +869,11 @@ extern "C" int phdslam_update(phdslam_t* h, const float* z, int M, int fields) {
   }
   rc = check_err_flag(h);
   if (rc) return rc;
+  h->nan_seen = h->red_host->nan_count != 0;
+  if (h->nan_seen) {              /* the reference notices through nEff at the end of the iteration (main.cpp:1307-1311) */
+    phdslam_set_error("nan weights detected");
+    return PHDSLAM_ERR_NAN;
+  }
   return 0;
 }
 
@@ -1120,10 +1155,12 @@ extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms,
   return 0;
 }
 
-/* ---- one loop iteration of run_synth (src/main.cpp:1231-1297) ---- */
-extern "C" int phdslam_step(phdslam_t* h, int step_index, const float* control, const float* z, int M, int fields,
-                            phdslam_estimate_t* est_out, int* resampled_out) {
-  int rc;
+/* ---- one loop iteration of run_synth (src/main.cpp:1231-1297), in the two halves either side of the point where the
+ * reference looks at the state (recoverSlamState's outputs and writeParticlesMat, :1274-1279) ---- */
+extern "C" int phdslam_step_filter(phdslam_t* h, int step_index, const float* control, const float* z, int M, int fields,
+                                   phdslam_estimate_t* est_out) {
+  int rc, nan_rc = 0;
+  if (est_out) memset(est_out, 0, sizeof(*est_out));
   if (step_index > 0) {
     for (int i = 0; i < h->cfg.subdivide_predict; ++i) {
       rc = phdslam_predict(h, control, nullptr);
@@ -1132,28 +1169,60 @@ extern "C" int phdslam_step(phdslam_t* h, int step_index, const float* control, 
   }
   if (M > 0) {
     rc = phdslam_update(h, z, M, fields);
-    if (rc) return rc;
+    if (rc == PHDSLAM_ERR_NAN) nan_rc = rc;   /* the reference finishes the iteration, then breaks (main.cpp:1307-1311) */
+    else if (rc) return rc;
   }
   phdslam_estimate_t e;
   rc = phdslam_estimate(h, &e);
   if (rc) return rc;
-  int res = 0;
-  if ((e.neff <= h->cfg.resample_threshold && M > 0) || h->n_global > 5 * h->cfg.n_particles) {
-    rc = phdslam_resample(h, h->cfg.n_particles, nullptr, nullptr);
-    if (rc) return rc;
-    res = 1;
-  } else {
-    iota_kernel<<<cdiv(h->n_local, 256), 256, 0, h->stream>>>(h->resample_idx, h->n_local, h->offset);
-    LAUNCH_CHECK(h);
-  }
   if (est_out) *est_out = e;
-  if (resampled_out) *resampled_out = res;
-  if (e.neff != e.neff) {
+  if (nan_rc || e.neff != e.neff) {
     phdslam_set_error("nan weights detected");
     return PHDSLAM_ERR_NAN;
   }
   return 0;
 }
+
+extern "C" int phdslam_step_resample(phdslam_t* h, int M, const phdslam_estimate_t* est, int* resampled_out) {
+  int res = 0;
+  if ((est->neff <= h->cfg.resample_threshold && M > 0) || h->n_global > 5 * h->cfg.n_particles) {   /* :1286 */
+    int rc = phdslam_resample(h, h->cfg.n_particles, nullptr, nullptr);
+    if (rc) return rc;
+    res = 1;
+  } else {                                                                                           /* :1293-1296 */
+    CK(cudaSetDevice(h->device));
+    iota_kernel<<<cdiv(h->n_local, 256), 256, 0, h->stream>>>(h->resample_idx, h->n_local, h->offset);
+    LAUNCH_CHECK(h);
+  }
+  if (resampled_out) *resampled_out = res;
+  return 0;
+}
+
+extern "C" int phdslam_step(phdslam_t* h, int step_index, const float* control, const float* z, int M, int fields,
+                            phdslam_estimate_t* est_out, int* resampled_out) {
+  phdslam_estimate_t e;
+  if (resampled_out) *resampled_out = 0;
+  int rc = phdslam_step_filter(h, step_index, control, z, M, fields, &e);
+  if (est_out) *est_out = e;
+  if (rc) return rc;          /* NaN weights included: nothing sensible to resample from */
+  return phdslam_step_resample(h, M, &e, resampled_out);
+}
+
+/* Sets the number of live particles (single GPU, within the capacity fixed at create time): the caller then imports
+ * poses / weights / maps of that many particles.  The reference's host loop changes the count itself (shotgun prediction,
+ * resampling back to n_particles: src/phdfilter.cu:1185-1238, src/main.cpp:1286-1289); the drop-in shim needs this to
+ * push a host particle set whose size differs from the device's. */
+extern "C" int phdslam_set_particle_count(phdslam_t* h, int n) {
+  if (h->world > 1 || n < 1 || n > h->n_cap) {
+    phdslam_set_error("phdslam_set_particle_count: single GPU only, 1 <= n <= particle capacity");
+    return PHDSLAM_ERR_INVALID;
+  }
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  h->n_local = h->n_global = n;
+  return 0;
+}
+extern "C" int phdslam_particle_capacity(const phdslam_t* h) { return h->n_cap; }
 
 /* ---- import / export ---- */
 extern "C" int phdslam_get_poses(phdslam_t* h, phdslam_pose_t* out) {

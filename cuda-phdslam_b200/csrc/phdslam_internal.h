@@ -37,8 +37,11 @@ struct DevCfg {
 
 struct Reductions {       /* device-resident cross-particle accumulators (all order-independent) */
   unsigned max_key;       /* ordered-uint image of max log-weight (0 = none) */
-  int nan_count;
+  int pad0;
+  /* the next three are adjacent 64-bit integers: ONE exact integer all-reduce when the particles are sharded */
   unsigned long long sum_fx;      /* sum exp(w-max) in Q36 */
+  unsigned long long nan_count;   /* particles whose log-weight is NaN (reference: `if isnan(nEff) break`, main.cpp:1307) */
+  unsigned long long err_ranks;   /* ranks whose update / merge raised err_flag: every rank returns the same status */
   unsigned long long neff_fx;     /* sum exp(2w) in Q60 */
   long long pose_fx[6];           /* sum exp(w)*pose in Q40 */
   unsigned long long argmax_key;  /* (ordered weight << 32) | ~global_index */
@@ -91,6 +94,7 @@ struct phdslam {
   int* ancestors;                    /* [n_local] */
   Reductions* red;                   /* device */
   Reductions* red_host;              /* pinned */
+  int nan_seen;                      /* the last update saw NaN particle weights (reported by phdslam_step after the estimate) */
   /* counters */
   unsigned predict_calls, resample_calls;
   unsigned long long launches;

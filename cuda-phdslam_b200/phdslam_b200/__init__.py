@@ -90,7 +90,8 @@ ABI_SYMBOLS = [
     "phdslam_config_defaults", "phdslam_config_load", "phdslam_config_set", "phdslam_last_error", "phdslam_version",
     "phdslam_create", "phdslam_destroy", "phdslam_set_config", "phdslam_get_config", "phdslam_dist_unique_id",
     "phdslam_dist_init", "phdslam_plan_migration", "phdslam_resample_threshold", "phdslam_predict", "phdslam_update", "phdslam_estimate", "phdslam_map_estimate",
-    "phdslam_resample", "phdslam_step", "phdslam_n_local", "phdslam_local_offset", "phdslam_get_poses",
+    "phdslam_resample", "phdslam_step", "phdslam_step_filter", "phdslam_step_resample", "phdslam_set_particle_count",
+    "phdslam_particle_capacity", "phdslam_n_local", "phdslam_local_offset", "phdslam_get_poses",
     "phdslam_set_poses", "phdslam_get_log_weights", "phdslam_set_log_weights", "phdslam_get_map_sizes",
     "phdslam_get_maps", "phdslam_set_maps", "phdslam_get_resample_idx", "phdslam_get_cardinalities",
     "phdslam_set_cardinalities", "phdslam_update_terms", "phdslam_get_timings", "phdslam_stream",
@@ -129,6 +130,10 @@ def load_library(path=None):
     lib.phdslam_map_estimate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     lib.phdslam_resample.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.phdslam_step.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.phdslam_step_filter.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.phdslam_step_resample.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.phdslam_set_particle_count.argtypes = [C.c_void_p, C.c_int]
+    lib.phdslam_particle_capacity.argtypes = [C.c_void_p]
     for name in ("phdslam_n_local", "phdslam_local_offset", "phdslam_synchronize", "phdslam_set_overlap", "phdslam_snapshot", "phdslam_restore"):
         getattr(lib, name).argtypes = [C.c_void_p]
     for name in ("phdslam_get_poses", "phdslam_set_poses", "phdslam_get_log_weights", "phdslam_set_log_weights",
@@ -362,6 +367,21 @@ class PhdSlam(object):
         _check(self.lib.phdslam_step(self._h, step_index, _ptr(c), z.ctypes.data if M else None, M, fields, C.byref(e),
                                      C.byref(res)))
         return e, bool(res.value)
+
+    def step_filter(self, step_index, control, Z):
+        """predict + update + estimate: the state run_synth looks at (and logs) is the one after this half"""
+        c = None if control is None else np.ascontiguousarray(control, dtype=np.float32)
+        z = np.ascontiguousarray(Z, dtype=np.float32)
+        M = 0 if z.size == 0 else len(z)
+        fields = 2 if M == 0 else z.reshape(M, -1).shape[1]
+        e = Estimate()
+        _check(self.lib.phdslam_step_filter(self._h, step_index, _ptr(c), z.ctypes.data if M else None, M, fields, C.byref(e)))
+        return e
+
+    def step_resample(self, M, est):
+        res = C.c_int()
+        _check(self.lib.phdslam_step_resample(self._h, int(M), C.byref(est), C.byref(res)))
+        return bool(res.value)
 
     def map_estimate(self, which=1, cap=4096):
         out = np.zeros(cap, dtype=GAUSSIAN_DTYPE)

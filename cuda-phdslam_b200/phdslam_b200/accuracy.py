@@ -103,8 +103,9 @@ def run_and_score(filt, truth, Z, U=None, n_steps=None, which_map=1):
     rows = []
     for k in range(n):
         u = None if (U is None or k == 0) else U[k - 1]
-        est, _ = filt.step(k, u, Z[k])
-        m = filt.map_estimate(which_map)
+        est = filt.step_filter(k, u, Z[k])
+        m = filt.map_estimate(which_map)          # where recoverSlamState runs: before resampling (src/main.cpp:1274)
+        filt.step_resample(len(Z[k]), est)
         rows.append(score_step(truth, k, est.pose[:2], m["weight"], m["mean"]))
     return rows
 

@@ -71,7 +71,8 @@ typedef struct phdslam_config {
   float birth_noise_factor;
   float min_separation;
   float min_feature_weight;
-  int particle_weighting;                        /* 0 cluster-process, 1 Vo empty-map */
+  int particle_weighting;                        /* 0 cluster-process, 1 Vo empty-map; 2 (single-feature, unfinished in the
+                                                    reference: src/phdfilter.cu:3600-3661) -> PHDSLAM_ERR_INVALID */
   int distance_metric;                           /* 0 Mahalanobis, 1 Hellinger */
   int max_cardinality;
   int filter_type;                               /* 0 PHD, 1 CPHD */
@@ -172,9 +173,23 @@ int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms, int* ances
  * resampled_out: 1 if resampling happened. */
 int phdslam_step(phdslam_t* h, int step_index, const float* control, const float* z, int M, int fields,
                  phdslam_estimate_t* est_out, int* resampled_out);
+/* The same iteration in its two halves, for a caller that looks at the particle set where run_synth does -- after
+ * recoverSlamState and before resampleParticles (src/main.cpp:1274-1279: the map estimate, the particle weights and
+ * poses of the log are those of the weighted, not yet resampled particles; resample_idx still holds the previous
+ * step's ancestors):
+ *   phdslam_step_filter   = predict + update + estimate (main.cpp:1244-1274, 1281-1284).  Returns PHDSLAM_ERR_NAN
+ *                           (with *est_out filled) when particle weights are NaN (main.cpp:1307-1311);
+ *   phdslam_step_resample = the nEff test and resampleParticles, or resample_idx = identity (main.cpp:1286-1297). */
+int phdslam_step_filter(phdslam_t* h, int step_index, const float* control, const float* z, int M, int fields,
+                        phdslam_estimate_t* est_out);
+int phdslam_step_resample(phdslam_t* h, int M, const phdslam_estimate_t* est, int* resampled_out);
 
 /* ---- state import / export (tests, checkpoints, the log writer) ---- */
 int phdslam_n_local(const phdslam_t* h);             /* particles owned by this rank */
+/* Number of live particles (single GPU; 1 <= n <= phdslam_particle_capacity): for a host loop that changes the
+ * particle count itself (src/phdfilter.cu:1185-1238, src/main.cpp:1286-1289) and then imports the new set. */
+int phdslam_set_particle_count(phdslam_t* h, int n);
+int phdslam_particle_capacity(const phdslam_t* h);
 int phdslam_local_offset(const phdslam_t* h);        /* global index of local particle 0 */
 int phdslam_get_poses(phdslam_t* h, phdslam_pose_t* out /* n_local */);
 int phdslam_set_poses(phdslam_t* h, const phdslam_pose_t* in);

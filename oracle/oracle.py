@@ -47,6 +47,8 @@ def load():
         lib.oracle_map_estimate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         lib.oracle_resample.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         lib.oracle_step.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        lib.oracle_step_filter.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        lib.oracle_step_resample.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         lib.oracle_mahalanobis.argtypes = [C.c_void_p, C.c_void_p]
         lib.oracle_hellinger.argtypes = [C.c_void_p, C.c_void_p]
         lib.oracle_merge.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -135,6 +137,20 @@ class Oracle(object):
         e, res = Estimate(), C.c_int()
         self.lib.oracle_step(self._h, step_index, _ptr(c), z.ctypes.data if M else None, M, fields, C.byref(e), C.byref(res))
         return e, bool(res.value)
+
+    def step_filter(self, step_index, control, Z):
+        c = None if control is None else np.ascontiguousarray(control, dtype=np.float32)
+        z = np.ascontiguousarray(Z, dtype=np.float32)
+        M = 0 if z.size == 0 else len(z)
+        fields = 2 if M == 0 else z.reshape(M, -1).shape[1]
+        e = Estimate()
+        self.lib.oracle_step_filter(self._h, step_index, _ptr(c), z.ctypes.data if M else None, M, fields, C.byref(e))
+        return e
+
+    def step_resample(self, M, est):
+        res = C.c_int()
+        self.lib.oracle_step_resample(self._h, int(M), C.byref(est), C.byref(res))
+        return bool(res.value)
 
     def map_estimate(self, which=1, cap=65536):
         out = np.zeros(cap, dtype=GAUSSIAN_DTYPE)

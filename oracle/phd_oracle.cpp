@@ -844,25 +844,34 @@ extern "C" void oracle_resample(phd_oracle_t* o, int n_new, const double* unifor
   if (ancestors_out) memcpy(ancestors_out, idx.data(), n_new * sizeof(int));
 }
 
-/* run_synth loop body (src/main.cpp:1231-1297) */
-extern "C" void oracle_step(phd_oracle_t* o, int step_index, const float* control, const float* z, int M, int fields,
-                            phdslam_estimate_t* est_out, int* resampled_out) {
+/* run_synth loop body (src/main.cpp:1231-1297), in the two halves either side of the point where the reference looks at
+ * the state (recoverSlamState outputs, writeParticlesMat: :1274-1279) */
+extern "C" void oracle_step_filter(phd_oracle_t* o, int step_index, const float* control, const float* z, int M, int fields,
+                                   phdslam_estimate_t* est_out) {
   const phdslam_config_t& c = o->cfg;
   if (step_index > 0)
     for (int i = 0; i < c.subdivide_predict; ++i) oracle_predict(o, control, nullptr);   /* :1244-1255 */
   if (M > 0) oracle_update(o, z, M, fields);                                             /* :1258-1272 */
-  phdslam_estimate_t e;
-  oracle_estimate(o, &e);                                                                /* :1274, :1281-1284 */
+  oracle_estimate(o, est_out);                                                           /* :1274, :1281-1284 */
+}
+extern "C" void oracle_step_resample(phd_oracle_t* o, int M, const phdslam_estimate_t* e, int* resampled_out) {
+  const phdslam_config_t& c = o->cfg;
   int n = (int)o->states.size();
   int res = 0;
-  if ((e.neff <= c.resample_threshold && M > 0) || n > 5 * c.n_particles) {              /* :1286 */
+  if ((e->neff <= c.resample_threshold && M > 0) || n > 5 * c.n_particles) {             /* :1286 */
     oracle_resample(o, c.n_particles, nullptr, 0, nullptr);
     res = 1;
   } else {
     for (int i = 0; i < n; ++i) o->resample_idx[i] = i;                                  /* :1293-1296 */
   }
-  if (est_out) *est_out = e;
   if (resampled_out) *resampled_out = res;
+}
+extern "C" void oracle_step(phd_oracle_t* o, int step_index, const float* control, const float* z, int M, int fields,
+                            phdslam_estimate_t* est_out, int* resampled_out) {
+  phdslam_estimate_t e;
+  oracle_step_filter(o, step_index, control, z, M, fields, &e);
+  oracle_step_resample(o, M, &e, resampled_out);
+  if (est_out) *est_out = e;
 }
 
 /* ------------------------------------------------------------------------- */

@@ -68,6 +68,10 @@ void oracle_resample(phd_oracle_t* o, int n_new, const double* uniforms, int lit
 void oracle_step(phd_oracle_t* o, int step_index, const float* control, const float* z, int M, int fields,
                  phdslam_estimate_t* est_out, int* resampled_out);
 
+void oracle_step_filter(phd_oracle_t* o, int step_index, const float* control, const float* z, int M, int fields,
+                        phdslam_estimate_t* est_out);
+void oracle_step_resample(phd_oracle_t* o, int M, const phdslam_estimate_t* est, int* resampled_out);
+
 /* pieces exposed for known-answer tests */
 float oracle_mahalanobis(const phdslam_gaussian2d_t* a, const phdslam_gaussian2d_t* b);
 float oracle_hellinger(const phdslam_gaussian2d_t* a, const phdslam_gaussian2d_t* b);

@@ -287,7 +287,9 @@ def test_map_estimates_map_and_eap():
 
 def test_cli_logs_match_oracle(tmp_path):
     """rows 13-14 + the process interface: `phdslam <cfg> synth` on the bundled Ackerman data writes
-    state_estimateNNNNN.log files (README 5-line layout) identical to the oracle's, text for text"""
+    state_estimateNNNNN.log files (README 5-line layout) identical to the oracle's, text for text.  The logged state is
+    the one run_synth looks at: after recoverSlamState, before resampleParticles (src/main.cpp:1274-1279) -- the map is the
+    maximum-weight particle's, the weights are the update's."""
     import subprocess
     from conftest import ROOT
     exe = os.path.join(ROOT, "cuda-phdslam_b200", "phdslam")
@@ -305,13 +307,21 @@ def test_cli_logs_match_oracle(tmp_path):
     Z = P.load_measurements(os.path.join(DATA, "measurements_synth_ackerman.txt"))
     U = P.load_controls(os.path.join(DATA, "controls_synth.txt"))
     o = O.Oracle(cfg)
+    resampled_any = False
     for k in range(n_steps):
-        e, _ = o.step(k, U[k - 1] if k > 0 else np.float32([0, 0]), Z[k])
+        e = o.step_filter(k, U[k - 1] if k > 0 else np.float32([0, 0]), Z[k])
         ref = tmp_path / ("ref%05d.log" % k)
-        P.write_log(str(ref), 0, e.pose, o.map_estimate(1), o.log_weights, o.poses, n_card=cfg.max_cardinality + 1)
+        lw = o.log_weights
+        P.write_log(str(ref), 0, e.pose, o.map_estimate(1), lw, o.poses, n_card=cfg.max_cardinality + 1)
+        if k > 0:
+            resampled_any |= o.step_resample(len(Z[k]), e)
+            assert lw.max() > lw.min(), "the logged weights are the weighted (pre-resampling) ones"
+        else:
+            o.step_resample(len(Z[k]), e)
         got = open(out / ("state_estimate%05d.log" % k)).read()
         assert got == open(ref).read(), "log of step %d differs" % k
         assert len(got.split("\n")) == 6
+    assert resampled_any, "the run must cover a resampling step"
 
 
 # ---- prune + merge: the shared-memory kernel (merge_fast_kernel), its overflow queue and merge_kernel agree ----

@@ -103,9 +103,11 @@ def test_cli_timestamped_streams_match_oracle(tmp_path):
             u = Ut[e["c_idx"]]
         cfg.set(dt=float(e["dt"]))
         o.setDeviceConfig(cfg)
-        est, _ = o.step(k, u, Zt[e["z_idx"]] if e["z_idx"] >= 0 else np.zeros((0, 2), np.float32))
-        ref = tmp_path / ("ref%05d.log" % k)
+        zk = Zt[e["z_idx"]] if e["z_idx"] >= 0 else np.zeros((0, 2), np.float32)
+        est = o.step_filter(k, u, zk)
+        ref = tmp_path / ("ref%05d.log" % k)       # the log is the state before resampling (main.cpp:1274-1279)
         P.write_log(str(ref), 0, est.pose, o.map_estimate(1), o.log_weights, o.poses, n_card=cfg.max_cardinality + 1)
+        o.step_resample(len(zk), est)
         assert open(out / ("state_estimate%05d.log" % k)).read() == open(ref).read(), "log of event %d differs" % k
     assert not os.path.exists(out / ("state_estimate%05d.log" % len(ev)))
 
@@ -136,9 +138,10 @@ def test_cli_follow_trajectory_matches_oracle(tmp_path):
     o = O.Oracle(cfg)
     for k in range(len(traj)):
         o.poses = traj[k:k + 1]
-        est, _ = o.step(0, np.float32([0, 0]), Z[k])
+        est = o.step_filter(0, np.float32([0, 0]), Z[k])
         ref = tmp_path / ("ref%05d.log" % k)
         P.write_log(str(ref), 0, est.pose, o.map_estimate(1), o.log_weights, o.poses, n_card=cfg.max_cardinality + 1)
+        o.step_resample(len(Z[k]), est)
         assert open(out / ("state_estimate%05d.log" % k)).read() == open(ref).read(), "log of step %d differs" % k
     assert not os.path.exists(out / ("state_estimate%05d.log" % len(traj)))
     # mapping with the true poses: the landmarks seen so far are in the map
