@@ -5,11 +5,17 @@
  * instead of src/phdfilter.cu (next to the reference's own main.cpp, slamtypes.h, phdfilter.h) and linking -lphdslam.
  * It defines the functions of src/phdfilter.h:10-34 that src/phdfilter.cu defines and run_synth calls (initRandomNumberGenerators,
  * setDeviceConfig, phdPredict, phdUpdateSynth), with the reference's types; the device handle lives
- * across calls, so the per-step re-upload of every map (src/phdfilter.cu:2901-3103) disappears: host state is pushed when
- * the host has edited it and pulled when the host wants to look at it.
+ * across calls.  run_synth owns the particle set on the HOST and edits it between the calls -- resampleParticles replaces it
+ * (src/main.cpp:1286-1289), follow_trajectory overwrites the poses (:1239-1243), the non-resampling branch resets
+ * resample_idx (:1293-1296) -- so every entry point first compares the host particles with a shadow of what the device last
+ * handed back (poses, weights, resample indices, particle count: O(N) words, no maps) and re-uploads the set, maps and
+ * CPHD cardinalities included, when the host has touched it.  With the host resampler of the reference that is one map
+ * upload per resampling step (the reference itself re-uploads every map on every call, src/phdfilter.cu:2901-3103);
+ * resampleParticlesDevice() below avoids it.
  *
- * tests/test_shim_compiles.py compiles it against the reference's headers and links it against libphdslam.so
- * (CPU container only: the reference tree is not shipped).
+ * tests/test_shim_compiles.py compiles it against the reference's headers and links it against libphdslam.so;
+ * oracle/ref_build.sh links it with the reference's OWN run_synth loop, resampleParticles, recoverSlamState and writeLog
+ * (cut verbatim from src/main.cpp) into oracle/_ref/shim_replay, which tests/test_shim_gpu.py runs on the GPU against the CLI.
  */
 class MotionModel; /* src/slamtypes.h:335 names it without declaring it */
 #include "slamtypes.h"
@@ -22,7 +28,6 @@ class MotionModel; /* src/slamtypes.h:335 names it without declaring it (SURVEY 
 
 extern SlamConfig config; /* src/main.cpp:80 */
 static phdslam_t* g_h = nullptr;
-static bool g_device_is_current = false; /* the device holds the particles the host last pushed (or their successors) */
 
 static_assert(sizeof(Gaussian2D) == sizeof(phdslam_gaussian2d_t), "Gaussian2D layout (src/slamtypes.h:123-127)");
 static_assert(sizeof(ConstantVelocityState) == sizeof(phdslam_pose_t), "ConstantVelocityState layout (src/slamtypes.h:44-51)");
@@ -52,19 +57,52 @@ static phdslam_config_t to_cfg(const SlamConfig& c) { /* field for field, src/sl
   return k;
 }
 
+/* extensions of phdslam_config_t that SlamConfig has no field for (Philox seed, map capacity): set before the first
+ * setDeviceConfig by a host that wants other values than the defaults */
+unsigned long long phdslam_shim_seed = 0;
+int phdslam_shim_max_components = 0;
+
 void initRandomNumberGenerators() {} /* src/phdfilter.cu:142: the library's Philox generator is counter based, nothing to seed per thread */
 
 void setDeviceConfig(const SlamConfig& c) { /* src/phdfilter.cu:3885-3890 */
   phdslam_config_t k = to_cfg(c);
+  k.seed = phdslam_shim_seed;
+  if (phdslam_shim_max_components > 0) k.max_components = phdslam_shim_max_components;
   if (!g_h) check(phdslam_create(&k, 0, &g_h), "phdslam_create");
   else check(phdslam_set_config(g_h, &k), "phdslam_set_config");
 }
 
-/* host -> device: run_synth initialises the particles on the host (src/main.cpp:1129-1144) */
+/* ---- what the device last handed to the host: if the host particles still equal it, the device state is current ---- */
+static struct {
+  bool valid;
+  std::vector<ConstantVelocityState> states;
+  std::vector<REAL> weights;
+  std::vector<int> resample_idx;
+} g_shadow;
+
+static bool host_untouched(const SynthSLAM& p) {
+  const size_t n = g_shadow.states.size();
+  return g_shadow.valid && (size_t)p.n_particles == n && p.states.size() == n && p.weights.size() == n &&
+         p.resample_idx.size() == n && p.maps_static.size() == n &&
+         memcmp(&p.states[0], &g_shadow.states[0], n * sizeof(ConstantVelocityState)) == 0 &&
+         memcmp(&p.weights[0], &g_shadow.weights[0], n * sizeof(REAL)) == 0 &&
+         memcmp(&p.resample_idx[0], &g_shadow.resample_idx[0], n * sizeof(int)) == 0;
+}
+static void remember(const SynthSLAM& p) {
+  g_shadow.states = p.states;
+  g_shadow.weights = p.weights;
+  g_shadow.resample_idx = p.resample_idx;
+  g_shadow.valid = true;
+}
+
+/* host -> device: the whole particle set (run_synth initialises it on the host, src/main.cpp:1129-1144, and replaces it
+ * when it resamples) */
 static void push(SynthSLAM& p) {
+  const int n = p.n_particles;
+  if (n != phdslam_n_local(g_h)) check(phdslam_set_particle_count(g_h, n), "phdslam_set_particle_count");
   std::vector<int> sizes;
   std::vector<phdslam_gaussian2d_t> flat;
-  for (size_t i = 0; i < p.maps_static.size(); ++i) {
+  for (int i = 0; i < n; ++i) {
     sizes.push_back((int)p.maps_static[i].size());
     for (size_t j = 0; j < p.maps_static[i].size(); ++j) {
       phdslam_gaussian2d_t g;
@@ -76,14 +114,25 @@ static void push(SynthSLAM& p) {
   check(phdslam_set_poses(g_h, (const phdslam_pose_t*)&p.states[0]), "phdslam_set_poses");
   check(phdslam_set_log_weights(g_h, &p.weights[0]), "phdslam_set_log_weights");
   check(phdslam_set_maps(g_h, sizes.data(), flat.data()), "phdslam_set_maps");
-  g_device_is_current = true;
+  if (config.filterType == CPHD_TYPE) {
+    const size_t n1 = (size_t)config.maxCardinality + 1;
+    std::vector<float> card((size_t)n * n1);
+    for (int i = 0; i < n; ++i)
+      for (size_t k = 0; k < n1 && k < p.cardinalities[i].size(); ++k) card[i * n1 + k] = p.cardinalities[i][k];
+    check(phdslam_set_cardinalities(g_h, card.data()), "phdslam_set_cardinalities");
+  }
+}
+
+static void sync_to_device(SynthSLAM& p) {
+  if (!host_untouched(p)) push(p);
 }
 
 /* device -> host: what run_synth reads between calls (weights for nEff and the log, poses for the log, maps for
- * writeParticlesMat) */
+ * recoverSlamState / writeParticlesMat, cardinalities for the CPHD estimate) */
 static void pull(SynthSLAM& p) {
   const int n = phdslam_n_local(g_h);
   p.states.resize(n); p.weights.resize(n); p.maps_static.resize(n); p.resample_idx.resize(n);
+  p.maps_dynamic.resize(n); p.cardinalities.resize(n); p.variances.resize(n);
   p.n_particles = n;
   check(phdslam_get_poses(g_h, (phdslam_pose_t*)&p.states[0]), "phdslam_get_poses");
   check(phdslam_get_log_weights(g_h, &p.weights[0]), "phdslam_get_log_weights");
@@ -99,10 +148,17 @@ static void pull(SynthSLAM& p) {
     p.maps_static[i].resize(sizes[i]);
     for (int j = 0; j < sizes[i]; ++j, ++k) memcpy(&p.maps_static[i][j], &flat[k], sizeof(Gaussian2D));
   }
+  if (config.filterType == CPHD_TYPE) {
+    const size_t n1 = (size_t)config.maxCardinality + 1;
+    std::vector<float> card((size_t)n * n1);
+    check(phdslam_get_cardinalities(g_h, card.data()), "phdslam_get_cardinalities");
+    for (int i = 0; i < n; ++i) p.cardinalities[i].assign(card.begin() + i * n1, card.begin() + (i + 1) * n1);
+  }
+  remember(p);
 }
 
 void phdPredict(SynthSLAM& particles, ...) { /* src/phdfilter.cu:1080-1257 */
-  if (!g_device_is_current) push(particles);
+  sync_to_device(particles);
   float u[2] = {0.0f, 0.0f};
   if (config.motionType == ACKERMAN_MOTION) { /* the reference passes the control through C varargs (:1141-1144) */
     va_list ap;
@@ -117,7 +173,7 @@ void phdPredict(SynthSLAM& particles, ...) { /* src/phdfilter.cu:1080-1257 */
 }
 
 SynthSLAM phdUpdateSynth(SynthSLAM& particles, measurementSet Z) { /* src/phdfilter.cu:3336-3761 */
-  if (!g_device_is_current) push(particles);
+  sync_to_device(particles);
   SynthSLAM before = particles; /* the reference returns the pre-merge copy (particlesPreMerge, src/main.cpp:1268) */
   std::vector<float> z;
   for (size_t i = 0; i < Z.size(); ++i) {
@@ -126,7 +182,8 @@ SynthSLAM phdUpdateSynth(SynthSLAM& particles, measurementSet Z) { /* src/phdfil
     z.push_back((float)Z[i].label);
   }
   z.push_back(0.0f);
-  check(phdslam_update(g_h, z.data(), (int)Z.size(), 3), "phdslam_update");
+  int rc = phdslam_update(g_h, z.data(), (int)Z.size(), 3);
+  if (rc != PHDSLAM_ERR_NAN) check(rc, "phdslam_update"); /* NaN weights: run_synth notices through nEff and breaks (:1307) */
   pull(particles);
   return before;
 }
@@ -136,6 +193,7 @@ SynthSLAM phdUpdateSynth(SynthSLAM& particles, measurementSet Z) { /* src/phdfil
  * host EAP reduction, src/gm_reduce.cpp).  This is the device version (fixed-point expected pose, MAP map copy, EAP map
  * reduced on the GPU); a maintainer calls it instead at src/main.cpp:1274 to skip the host O(n^2) reduction. */
 void recoverSlamStateDevice(SynthSLAM& particles, ConstantVelocityState& expectedPose, vector<REAL>& cn_estimate) {
+  sync_to_device(particles);
   phdslam_estimate_t e;
   check(phdslam_estimate(g_h, &e), "phdslam_estimate");
   memcpy(&expectedPose, &e.expected_pose, sizeof(expectedPose));
@@ -149,7 +207,7 @@ void recoverSlamStateDevice(SynthSLAM& particles, ConstantVelocityState& expecte
     out.resize(n);
     for (int i = 0; i < n; ++i) memcpy(&out[i], &m[i], sizeof(Gaussian2D));
   }
-  if (config.filterType == CPHD_TYPE) { /* cardinality distribution of the maximum-weight particle (:356-361) */
+  if (config.filterType == CPHD_TYPE && e.map_particle >= 0) { /* cardinality distribution of the maximum-weight particle (:356-361) */
     const int n1 = config.maxCardinality + 1, np = phdslam_n_local(g_h);
     std::vector<float> all((size_t)np * n1);
     check(phdslam_get_cardinalities(g_h, all.data()), "phdslam_get_cardinalities");
@@ -157,6 +215,13 @@ void recoverSlamStateDevice(SynthSLAM& particles, ConstantVelocityState& expecte
   }
 }
 
-/* resampleParticles lives in src/main.cpp:453-501; a maintainer who wants the device resampler replaces its body with
- *   phdslam_resample(g_h, n_particles, nullptr, &particles.resample_idx[0]); pull(particles);
- * or the whole loop body (src/main.cpp:1244-1297) with one phdslam_step(). */
+/* Device twin of resampleParticles (src/main.cpp:453-501): the maps never leave the GPU.  A maintainer replaces
+ *   particles = resampleParticles(particles, config.n_particles) ;         (src/main.cpp:1289)
+ * with
+ *   resampleParticlesDevice(particles, config.n_particles) ;
+ * (same stratified draws, from the library's counter-based generator instead of rng.cpp). */
+void resampleParticlesDevice(SynthSLAM& particles, int n_new) {
+  sync_to_device(particles);
+  check(phdslam_resample(g_h, n_new, nullptr, nullptr), "phdslam_resample");
+  pull(particles);
+}

@@ -136,3 +136,21 @@ g++ -O1 -std=c++14 -fPIC -shared -fpermissive -w -ffp-contract=off \
   -I "$HERE/ref_shim" -I "$GEN" -I "$REF/src" -I "$HERE/../include" \
   -o "$OUT/libphd_ref.so" "$HERE/ref_harness.cpp"
 echo "ref_build: built $OUT/libphd_ref.so from $REF"
+
+# ---- the drop-in, executed: the reference's own run_synth (src/main.cpp:1076-1313, verbatim: input loading, particle
+# initialisation, the time-step loop with its host resampleParticles) + its recoverSlamState / writeLog / loaders, linked
+# with cuda-phdslam_b200/shim/phdfilter_b200.cpp and libphdslam.so (oracle/shim_replay.cpp says what is stubbed).
+sed -n "1075p" "$M" | grep -q "void run_synth(bool profile_run){" || { echo "ref_build: run_synth moved" >&2; exit 1; }
+sed -n "1178p" "$M" | grep -q "for (int n = 0 ; n < nSteps ; n++ )" || { echo "ref_build: run_synth loop moved" >&2; exit 1; }
+sed -n "1314p" "$M" | grep -q "else" || { echo "ref_build: run_synth loop end moved" >&2; exit 1; }
+sed -n "1076,1313p" "$M" > "$GEN/ref_run_synth_body.inc"
+LIBDIR="$HERE/../cuda-phdslam_b200"
+if [ -f "$LIBDIR/libphdslam.so" ]; then
+  g++ -O1 -std=c++14 -fpermissive -w -ffp-contract=off \
+    -I "$HERE/ref_shim" -I "$GEN" -I "$REF/src" -I "$HERE/../include" \
+    -o "$OUT/shim_replay" "$HERE/shim_replay.cpp" "$LIBDIR/shim/phdfilter_b200.cpp" \
+    -L "$LIBDIR" -lphdslam -Wl,-rpath,'$ORIGIN/../../cuda-phdslam_b200'
+  echo "ref_build: built $OUT/shim_replay (the reference's run_synth over the drop-in shim)"
+else
+  echo "ref_build: libphdslam.so not built yet, skipping shim_replay"
+fi
