@@ -192,19 +192,29 @@ def dist_env():
     return rank, world, local
 
 
+def load_oracle():
+    """The CPU oracle for the timed baseline: rebuilt -O3 -march=native on THIS host; the portable
+    -O3 -march=x86-64-v3 build that travelled with the repository is the fallback.  Same source, bit-identical results."""
+    from oracle import oracle as O
+    if O._lib is None:
+        O.load(O.build_native())
+    flags = "-O3 -march=native, built on this host" if (O.LIB_USED or "").endswith("_native.so") else "-O3 -march=x86-64-v3"
+    return O, flags
+
+
 def cpu_oracle_rate(wl, target_seconds=12.0, threads=None):
     """Times the CPU oracle (all host threads) on a bounded particle sample of the same workload.
-    Returns (updates/s, cores, sample description, ms per sample step)."""
-    import phdslam_b200  # noqa: F401  (config helpers; no GPU use)
+    Returns (updates/s, cores, sample description, ms per sample step, particles in the sample).
+    Nothing here touches libphdslam.so: the config is built in Python (scene_config_py), the scene in numpy."""
     from phdslam_b200 import scene as S
-    from oracle import oracle as O
+    O, flags = load_oracle()
     C, M = wl["C"], wl["M"]
     threads = threads or os.cpu_count() or 1
     Ps = max(threads, 8)
     rate = None
     for attempt in range(3):
         extra = {k: v for k, v in wl.items() if k not in ("P", "C", "M", "max_components")}
-        cfg = S.scene_config(Ps, C, M, max_components=wl["max_components"], **extra)
+        cfg = S.scene_config_py(Ps, C, M, max_components=wl["max_components"], **extra)
         sc = S.make_scene(Ps, C, M, seed=0)
         o = O.Oracle(cfg, threads=threads)
         S.load_scene(o, sc)
@@ -216,8 +226,15 @@ def cpu_oracle_rate(wl, target_seconds=12.0, threads=None):
         if dt >= 0.4 * target_seconds or attempt == 2:
             break
         Ps = int(min(max(Ps * target_seconds / max(dt, 1e-3) * 0.8, Ps * 2), 65536))
-    sample = "%d of the workload's particles (C=%d, M=%d), one full filter step, %d OpenMP threads, %.2f s" % (Ps, C, M, threads, dt)
+    sample = "%d of the workload's particles (C=%d, M=%d), one full filter step, %d OpenMP threads, %.2f s; oracle %s" % (
+        Ps, C, M, threads, dt, flags)
     return rate, threads, sample, dt * 1e3, Ps
+
+
+def cpu_oracle_single_thread_rate(wl, seconds=4.0):
+    """the same step on ONE thread (a scalar port's rate; BASELINE.md section 2 asks for both)"""
+    r, _, _, _, _ = cpu_oracle_rate(wl, target_seconds=seconds, threads=1)
+    return r
 
 
 def run_reference(args, wl):
@@ -225,15 +242,16 @@ def run_reference(args, wl):
     if rank != 0:
         return
     C, M = wl["C"], wl["M"]
-    from phdslam_b200 import scene as S
-    from oracle import oracle as O
+    from phdslam_b200 import scene as S      # numpy scene generator + the ctypes image of the config; no libphdslam.so
+    O, flags = load_oracle()
     threads = os.cpu_count() or 1
     # size the per-step sample so that warmup+steps finish within a few minutes
     r0, _, _, _, _ = cpu_oracle_rate(wl, target_seconds=3.0, threads=threads)
-    budget = 150.0 / max(args.steps + args.warmup, 1)
+    r1 = cpu_oracle_single_thread_rate(wl, seconds=3.0)
+    budget = 140.0 / max(args.steps + args.warmup, 1)
     Ps = int(max(threads, min(wl["P"], r0 * min(budget, 20.0) / (C * M))))
     extra = {k: v for k, v in wl.items() if k not in ("P", "C", "M", "max_components")}
-    cfg = S.scene_config(Ps, C, M, max_components=wl["max_components"], **extra)
+    cfg = S.scene_config_py(Ps, C, M, max_components=wl["max_components"], **extra)
     sc = S.make_scene(Ps, C, M, seed=0)
     times = []
     for k in range(args.warmup + args.steps):
@@ -247,18 +265,97 @@ def run_reference(args, wl):
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
     value = Ps * C * M / (ms * 1e-3)
-    sample = "%d of %d particles per step (C=%d, M=%d), full filter step, %d threads" % (Ps, wl["P"], C, M, threads)
+    sample = "%d of %d particles per step (C=%d, M=%d), full filter step, %d threads; oracle %s" % (Ps, wl["P"], C, M, threads, flags)
+    assert not any("libphdslam" in l for l in open("/proc/self/maps")), "the reference arm must not load the product library"
     line = {
         "impl": "reference", "metric": "GM-PHD updates/s (particle x comp x meas)", "value": value, "unit": "updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "particles": wl["P"], "components": C, "measurements": M,
+        "config": {"workload": args.workload, "particles_per_gpu": wl["P"], "components": C, "measurements": M,
+                   "filter": "CPHD" if wl.get("filter_type") == 1 else "PHD",
                    "note": "CPU oracle port of the reference algorithm (its scphd_cpu.cpp is an empty stub); bounded sample"},
-        "cpu_baseline": {"value": value, "unit": "updates/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "updates/s", "cores": threads, "kind": "port", "sample": sample,
+                         "single_thread_value": r1},
         "e2e": {"value": value, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def time_production_mode(filt, cfg, u, Z, args, barrier, stream, torch, dist):
+    """The same workload with update_mode = 1: the fused update emits only the prune survivors (nothing reads the dense
+    update terms of the reference's layout after the prune), so this is the fastest CORRECT path for filter steps/s --
+    same maps, same weights (tests/test_parity_gpu.py::test_update_modes_agree).  Device-timed, max over ranks."""
+    cfg.set(update_mode=1)
+    filt.setDeviceConfig(cfg)
+    ms = []
+    for k in range(2 + args.steps):
+        filt.restore()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        filt.step(1, u, Z)
+        e1.record(stream)
+        barrier()
+        if k >= 2:
+            ms.append(e0.elapsed_time(e1))
+    t = filt.timings()
+    cfg.set(update_mode=0)
+    filt.setDeviceConfig(cfg)
+    tot = float(np.sum(ms))
+    if dist is not None:
+        tt = torch.tensor([tot], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tot = float(tt[0])
+    per = tot / args.steps
+    return {"update_mode": "fused (only prune survivors leave the SM; no dense update terms)", "ms_per_step": per,
+            "filter_steps_per_s": 1e3 / per, "update_ms": t.update_ms, "merge_ms": t.merge_ms}
+
+
+def check_exchange(filt, u, Z, P_total, torch, dist):
+    """One extra, untimed step with injected uniforms that checks the sharded resampling exchange end to end:
+    every rank checksums its particles (pose, map, cardinality: one uint64 each, computed on the device) before and after
+    the global resampling; rank 0 gathers weights, ancestors and checksums, recomputes the ancestors with the CPU oracle's
+    canonical resampler on the gathered weights (bit-exact), and requires checksum(offspring j) == checksum(ancestor of j)
+    for EVERY offspring -- in particular for those whose ancestor lived on another GPU."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    filt.restore()
+    est = filt.step_filter(1, u, Z)
+    lw = filt.log_weights
+    pre = filt.particle_checksums()
+    uni = np.random.Generator(np.random.Philox(12345)).uniform(0.0, 1.0, P_total + 1)
+    anc = filt.resampleParticles(uni)
+    post = filt.particle_checksums()
+
+    def gather(a, dtype):
+        t = torch.from_numpy(np.ascontiguousarray(a).view(dtype)).cuda()
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return np.concatenate([o.cpu().numpy() for o in out])
+
+    lw_all = gather(lw, np.float32)
+    pre_all = gather(pre, np.int64)
+    post_all = gather(post, np.int64)
+    anc_all = gather(anc.astype(np.int32), np.int32)
+    if rank != 0:
+        return None
+    from phdslam_b200 import scene as S
+    from oracle import oracle as O
+    ocfg = S.scene_config_py(P_total, 1, 1, max_components=32)
+    o = O.Oracle(ocfg)
+    o.log_weights = lw_all
+    oanc = o.resampleParticles(uni)
+    o.close()
+    anc_ok = bool((oanc == anc_all).all())
+    per = P_total // world                 # rank r owns [r*N/W, (r+1)*N/W); P_total = P * world
+    own_j = np.arange(P_total) // per
+    own_a = anc_all // per
+    migrated = int((own_j != own_a).sum())
+    copy_ok = bool((post_all == pre_all[anc_all]).all())
+    return {"ancestors": "bit-exact against the CPU oracle's canonical resampler on the gathered weights" if anc_ok else "MISMATCH",
+            "offspring_checked": int(P_total), "migrated_checked": migrated,
+            "copies": "checksum(offspring) == checksum(ancestor) for every offspring" if copy_ok else "MISMATCH",
+            "neff": float(est.neff), "ok": bool(anc_ok and copy_ok)}
 
 
 def run_ours(args, wl):
@@ -301,8 +398,9 @@ def run_ours(args, wl):
         filt.restore()
         filt.step(1, u, Z)
     barrier()
-    l0 = filt.timings().launches
-    mig0 = filt.timings().migrated_in
+    t_before = filt.timings()
+    l0, mig0 = t_before.launches, t_before.migrated_in
+    h2d0, d2h0 = t_before.h2d_bytes, t_before.d2h_bytes
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -327,8 +425,11 @@ def run_ours(args, wl):
         upd_ms.append(t.update_ms)
         mrg_ms.append(t.merge_ms)
         other.append((t.predict_ms, t.weights_ms, t.estimate_ms, t.resample_ms if res else 0.0))
-    l_timed = filt.timings().launches
-    mig_timed = filt.timings().migrated_in
+    t_after = filt.timings()
+    l_timed, mig_timed = t_after.launches, t_after.migrated_in
+    # bytes the timed phdslam_step() calls moved between host and device, counted inside the library at every copy call
+    h2d_per_step = (t_after.h2d_bytes - h2d0) / float(args.steps)
+    d2h_per_step = (t_after.d2h_bytes - d2h0) / float(args.steps)
     # clocks under load are part of the contract: if (almost) no sample landed during the timed loop -- NVML can be slow
     # right after a profiler run -- all ranks run extra UNTIMED steps under the sampler until there are enough
     need_more = torch.tensor([1 if (rank == 0 and sampler.n_samples() < 3) else 0], device="cuda", dtype=torch.int32)
@@ -344,6 +445,8 @@ def run_ours(args, wl):
             if world == 1 and sampler.n_samples() >= 10:
                 break
     clocks = sampler.stop() if rank == 0 else None
+    production = time_production_mode(filt, cfg, u, Z, args, barrier, stream, torch, dist if world > 1 else None)
+    exchange_check = check_exchange(filt, u, Z, P_total, torch, dist) if world > 1 else None
     launches = l_timed - l0
     # restore() launches no kernels (cudaMemcpyAsync only), so `launches` counts the timed steps' kernels
     dev_total, wall_total = float(np.sum(dev_ms)), float(np.sum(wall_ms))
@@ -421,13 +524,17 @@ def run_ours(args, wl):
                      "algorithmic_bytes_per_update": balg, "kernel_ms": upd,
                      "timing": "CUDA events on the filter's stream around the kernel, averaged over the timed steps"},
         "cpu_baseline": {"value": cpu_rate, "unit": "updates/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": 3 * 256 * 4 + 8, "d2h_bytes_per_step": 3 * 128,
-                "ms_per_step": wall_total / args.steps},
+        "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": d2h_per_step,
+                "ms_per_step": wall_total / args.steps,
+                "bytes": "counted inside libphdslam.so at every host<->device copy of the timed calls (measurement upload; "
+                         "term counts, update status, estimate and CDF total coming back)"},
+        "production": production,
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
     if exchange is not None:
         line["exchange"] = exchange
+        line["exchange_check"] = exchange_check
     if merge_roof is not None:
         line["roofline_merge"] = merge_roof
     print(json.dumps(line))

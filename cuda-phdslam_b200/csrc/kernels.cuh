@@ -2596,6 +2596,36 @@ __global__ void fanout_kernel(int n_out, int k, float logk, const float* __restr
   ridx_out[j] = ridx_in[i];
 }
 
+/* One 64-bit checksum per particle over everything a resampled copy must carry (src/slamtypes.h:313-333: state, map,
+ * cardinality): pose (6 words), map size, the size x 6 live map words and the cardinality row.  Every word is mixed with
+ * its position (splitmix64 finaliser) and the mixes are summed, so the warp can hash in parallel and the result still
+ * depends on the order of the words.  Used by bench.py's exchange_check and the multi-GPU tests: an offspring's checksum
+ * must equal its ancestor's, whichever GPU the ancestor lived on. */
+__device__ __forceinline__ unsigned long long checksum_mix(unsigned long long idx, unsigned word) {
+  unsigned long long x = (idx + 1ull) * 0x9E3779B97F4A7C15ull ^ (unsigned long long)word;
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27; x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return x;
+}
+__global__ void particle_checksum_kernel(const float* __restrict__ pose, const int* __restrict__ count, const float* __restrict__ map,
+                                         const float* __restrict__ card, int n, int Cmax, int n_card,
+                                         unsigned long long* __restrict__ out) {
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= n) return;
+  const int lane = lane_id();
+  const int cnt = count[p];
+  unsigned long long acc = 0;
+  if (lane < 6) acc += checksum_mix(lane, __float_as_uint(pose[(size_t)lane * n + p]));
+  if (lane == 6) acc += checksum_mix(6, (unsigned)cnt);
+  const float* m = map + (size_t)p * PHD_MAP_PLANES * Cmax;
+  for (int k = 0; k < PHD_MAP_PLANES; ++k)
+    for (int i = lane; i < cnt; i += 32) acc += checksum_mix(16ull + (unsigned long long)i * PHD_MAP_PLANES + k, __float_as_uint(m[(size_t)k * Cmax + i]));
+  for (int i = lane; i < n_card; i += 32) acc += checksum_mix((1ull << 32) + i, __float_as_uint(card[(size_t)p * n_card + i]));
+  acc = warp_sum_u64(acc);
+  if (lane == 0) out[p] = acc;
+}
+
 __global__ void fill_kernel(float* p, int n, float v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;

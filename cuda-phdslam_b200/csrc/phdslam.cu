@@ -90,6 +90,25 @@ static bool load() {
     CK(cudaGetLastError());        \
   } while (0)
 
+/* every host<->device copy of the library goes through these four: the byte counters of phdslam_timings_t are counted
+ * from the calls, not estimated (bench.py's e2e.h2d_bytes_per_step / d2h_bytes_per_step) */
+static inline cudaError_t copy_h2d_async(phdslam* h, void* dst, const void* src, size_t n, cudaStream_t st) {
+  h->tim.h2d_bytes += n;
+  return cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, st);
+}
+static inline cudaError_t copy_d2h_async(phdslam* h, void* dst, const void* src, size_t n, cudaStream_t st) {
+  h->tim.d2h_bytes += n;
+  return cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, st);
+}
+static inline cudaError_t copy_h2d(phdslam* h, void* dst, const void* src, size_t n) {
+  h->tim.h2d_bytes += n;
+  return cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice);
+}
+static inline cudaError_t copy_d2h(phdslam* h, void* dst, const void* src, size_t n) {
+  h->tim.d2h_bytes += n;
+  return cudaMemcpy(dst, src, n, cudaMemcpyDeviceToHost);
+}
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 static float float_floor_d(double d) {
@@ -456,13 +475,13 @@ static int map_peer_windows(phdslam* h) {
   memset(&mine, 0, sizeof(mine));
   const unsigned long long magic = 0x5048445f50325000ull + (unsigned)me;
   if (ok && cudaIpcGetMemHandle(&mine, h->peer_slab) != cudaSuccess) { cudaGetLastError(); ok = 0; }
-  CK(cudaMemcpyAsync(h->peer_slab, &magic, sizeof(magic), cudaMemcpyHostToDevice, h->stream));
+  CK(copy_h2d_async(h, h->peer_slab, &magic, sizeof(magic), h->stream));
   unsigned char* hbuf = nullptr;                          /* [W] handles, all-gathered */
   CK(cudaMalloc(&hbuf, (size_t)W * sizeof(mine)));
-  CK(cudaMemcpyAsync(hbuf + (size_t)me * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+  CK(copy_h2d_async(h, hbuf + (size_t)me * sizeof(mine), &mine, sizeof(mine), h->stream));
   CKN(ncclAllGather(hbuf + (size_t)me * sizeof(mine), hbuf, sizeof(mine), ncclChar, comm, h->stream));
   std::vector<cudaIpcMemHandle_t> all(W);
-  CK(cudaMemcpyAsync(all.data(), hbuf, (size_t)W * sizeof(mine), cudaMemcpyDeviceToHost, h->stream));
+  CK(copy_d2h_async(h, all.data(), hbuf, (size_t)W * sizeof(mine), h->stream));
   CK(cudaStreamSynchronize(h->stream));                   /* every rank's magic is in place: the all-gather completed */
   h->peer_base = new unsigned char*[W];
   for (int r = 0; r < W; ++r) h->peer_base[r] = nullptr;
@@ -473,14 +492,14 @@ static int map_peer_windows(phdslam* h) {
     if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
     h->peer_base[r] = (unsigned char*)p;
     unsigned long long seen = 0;
-    if (cudaMemcpy(&seen, p, sizeof(seen), cudaMemcpyDeviceToHost) != cudaSuccess ||
+    if (copy_d2h(h, &seen, p, sizeof(seen)) != cudaSuccess ||
         seen != 0x5048445f50325000ull + (unsigned)r) { cudaGetLastError(); ok = 0; }
   }
   /* unanimous decision */
   int* flag = reinterpret_cast<int*>(hbuf);
-  CK(cudaMemcpyAsync(flag, &ok, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CK(copy_h2d_async(h, flag, &ok, sizeof(int), h->stream));
   CKN(ncclAllReduce(flag, flag, 1, ncclInt32, ncclMin, comm, h->stream));
-  CK(cudaMemcpyAsync(&ok, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(copy_d2h_async(h, &ok, flag, sizeof(int), h->stream));
   CK(cudaStreamSynchronize(h->stream));
   cudaFree(hbuf);
   if (!ok) close_peers(h);
@@ -604,7 +623,7 @@ extern "C" int phdslam_predict(phdslam_t* h, const float* control, const double*
       CK(cudaMalloc(&h->draws_dev, need * sizeof(double)));
       h->draws_cap = need;
     }
-    CK(cudaMemcpyAsync(h->draws_dev, draws, need * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(copy_h2d_async(h, h->draws_dev, draws, need * sizeof(double), h->stream));
     ddev = h->draws_dev;
   }
   float v_enc = control ? control[0] : 0.0f, alpha = control ? control[1] : 0.0f;
@@ -625,7 +644,7 @@ static int upload_measurements(phdslam* h, const float* z, int M, int fields) {
     zz[PHD_MAX_MEAS + m] = z[(size_t)m * fields + 1];
     zz[2 * PHD_MAX_MEAS + m] = (fields > 2) ? z[(size_t)m * fields + 2] : 0.0f;
   }
-  CK(cudaMemcpyAsync(h->z_dev, zz.data(), zz.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CK(copy_h2d_async(h, h->z_dev, zz.data(), zz.size() * sizeof(float), h->stream));
   CK(cudaStreamSynchronize(h->stream)); /* zz is a stack-lifetime staging buffer (768 floats) */
   return 0;
 }
@@ -639,7 +658,7 @@ static int classify_and_scan(phdslam* h, int M) {
   LAUNCH_CHECK(h);
   int rc = scan_u64(h, h->tpad, n, h->toff, &h->red->total_terms);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(h->red_host, h->red, sizeof(Reductions), cudaMemcpyDeviceToHost, h->stream));
+  CK(copy_d2h_async(h, h->red_host, h->red, sizeof(Reductions), h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -797,7 +816,7 @@ extern "C" int phdslam_update(phdslam_t* h, const float* z, int M, int fields) {
   std::vector<unsigned long long> tb(bounds.size(), 0);
   if (bounds.size() > 2) {
     for (size_t b = 0; b + 1 < bounds.size(); ++b)
-      CK(cudaMemcpyAsync(&tb[b], h->toff + bounds[b], sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+      CK(copy_d2h_async(h, &tb[b], h->toff + bounds[b], sizeof(unsigned long long), h->stream));
     CK(cudaStreamSynchronize(h->stream));
   }
   CK(cudaMemsetAsync(h->red, 0, sizeof(Reductions), h->stream));
@@ -848,7 +867,7 @@ extern "C" int phdslam_update(phdslam_t* h, const float* z, int M, int fields) {
   }
   rc = update_weights(h, true);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(h->red_host, h->red, sizeof(Reductions), cudaMemcpyDeviceToHost, h->stream));
+  CK(copy_d2h_async(h, h->red_host, h->red, sizeof(Reductions), h->stream));
   CK(cudaEventRecord(h->ev[6], h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->cur ^= 1; /* merged maps become the front buffer; poses and weights are single-buffered in place */
@@ -903,9 +922,9 @@ extern "C" int phdslam_update_terms(phdslam_t* h, const float* z, int M, int fie
   CK(cudaStreamSynchronize(h->stream));
   cudaEventElapsedTime(&h->tim.update_ms, h->ev[3], h->ev[4]);
   std::vector<int> nin(n);
-  CK(cudaMemcpy(nin.data(), h->n_in, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(copy_d2h(h, nin.data(), h->n_in, (size_t)n * sizeof(int)));
   if (n_in_range_out) memcpy(n_in_range_out, nin.data(), (size_t)n * sizeof(int));
-  if (dlogw_out) CK(cudaMemcpy(dlogw_out, h->dlogw, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+  if (dlogw_out) CK(copy_d2h(h, dlogw_out, h->dlogw, (size_t)n * sizeof(float)));
   if (terms_out) {
     std::vector<unsigned long long> ooff(n + 1, 0);
     for (int p = 0; p < n; ++p) ooff[p + 1] = ooff[p] + (unsigned long long)nin[p] * (M + 1) + M;
@@ -917,11 +936,11 @@ extern "C" int phdslam_update_terms(phdslam_t* h, const float* z, int M, int fie
     phdslam_gaussian2d_t* d_out = nullptr;
     CK(cudaMalloc(&d_off, (n + 1) * sizeof(unsigned long long)));
     CK(cudaMalloc(&d_out, std::max<size_t>(ooff[n], 1) * sizeof(phdslam_gaussian2d_t)));
-    CK(cudaMemcpy(d_off, ooff.data(), (n + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    CK(copy_h2d(h, d_off, ooff.data(), (n + 1) * sizeof(unsigned long long)));
     dense_export_kernel<<<n, 256, 0, h->stream>>>(h->dense, h->toff, 0, h->n_in, M, 0, n, d_off, d_out);
     LAUNCH_CHECK(h);
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(terms_out, d_out, ooff[n] * sizeof(phdslam_gaussian2d_t), cudaMemcpyDeviceToHost));
+    CK(copy_d2h(h, terms_out, d_out, ooff[n] * sizeof(phdslam_gaussian2d_t)));
     cudaFree(d_off);
     cudaFree(d_out);
   }
@@ -941,7 +960,7 @@ extern "C" int phdslam_estimate(phdslam_t* h, phdslam_estimate_t* out) {
     CKN(ncclAllReduce(&h->red->neff_fx, &h->red->neff_fx, 7, ncclUint64, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
     CKN(ncclAllReduce(&h->red->argmax_key, &h->red->argmax_key, 1, ncclUint64, ncclMax, (ncclComm_t)h->nccl_comm, h->stream));
   }
-  CK(cudaMemcpyAsync(h->red_host, h->red, sizeof(Reductions), cudaMemcpyDeviceToHost, h->stream));
+  CK(copy_d2h_async(h, h->red_host, h->red, sizeof(Reductions), h->stream));
   CK(cudaEventRecord(h->ev[8], h->stream));
   CK(cudaStreamSynchronize(h->stream));
   cudaEventElapsedTime(&h->tim.estimate_ms, h->ev[7], h->ev[8]);
@@ -960,7 +979,7 @@ extern "C" int phdslam_estimate(phdslam_t* h, phdslam_estimate_t* out) {
   out->neff = (float)(1.0 / s2 / (double)h->n_global);
   if (h->n_global == 1 && h->world == 1) { /* main.cpp:381-387 */
     std::vector<float> p(6);
-    for (int k = 0; k < 6; ++k) CK(cudaMemcpy(&p[k], h->pose[h->cur] + k, sizeof(float), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 6; ++k) CK(copy_d2h(h, &p[k], h->pose[h->cur] + k, sizeof(float)));
     memcpy(&out->expected_pose, p.data(), 6 * sizeof(float));
     out->map_particle = 0;
   }
@@ -1001,7 +1020,7 @@ extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms,
       CK(cudaMalloc(&h->draws_dev, need * sizeof(double)));
       h->draws_cap = need;
     }
-    CK(cudaMemcpyAsync(h->draws_dev, uniforms, need * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(copy_h2d_async(h, h->draws_dev, uniforms, need * sizeof(double), h->stream));
     udev = h->draws_dev;
   }
   const int sysmode = (h->cfg.resample_mode == 1);
@@ -1020,7 +1039,7 @@ extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms,
     if (rc) return rc;
     CKN(ncclAllGather(&h->red->cdf_total, h->totals_dev, 1, ncclUint64, (ncclComm_t)h->nccl_comm, h->stream));
     std::vector<unsigned long long> totals(h->world);
-    CK(cudaMemcpyAsync(totals.data(), h->totals_dev, (size_t)h->world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CK(copy_d2h_async(h, totals.data(), h->totals_dev, (size_t)h->world * sizeof(unsigned long long), h->stream));
     CK(cudaStreamSynchronize(h->stream));
     for (int r = 0; r < h->world; ++r) {
       if (r < h->rank) base += totals[r];
@@ -1034,7 +1053,7 @@ extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms,
     rc = phdslam_plan_migration(h->world, totals.data(), n_new, uniforms, h->cfg.resample_mode, h->resample_calls, h->cfg.seed, bounds.data());
     if (rc) return rc;
   } else {
-    CK(cudaMemcpyAsync(h->red_host, h->red, sizeof(Reductions), cudaMemcpyDeviceToHost, h->stream));
+    CK(copy_d2h_async(h, h->red_host, h->red, sizeof(Reductions), h->stream));
     CK(cudaStreamSynchronize(h->stream));
     total = h->red_host->cdf_total;
     if (total == 0) {
@@ -1146,7 +1165,7 @@ extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms,
   LAUNCH_CHECK(h);
   CK(cudaMemcpyAsync(h->resample_idx, h->ancestors, (size_t)n_off * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaEventRecord(h->ev[10], h->stream));
-  if (ancestors_out) CK(cudaMemcpyAsync(ancestors_out, h->ancestors, (size_t)n_off * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (ancestors_out) CK(copy_d2h_async(h, ancestors_out, h->ancestors, (size_t)n_off * sizeof(int), h->stream));
   CK(cudaStreamSynchronize(h->stream));
   cudaEventElapsedTime(&h->tim.resample_ms, h->ev[9], h->ev[10]);
   h->cur ^= 1;
@@ -1230,7 +1249,7 @@ extern "C" int phdslam_get_poses(phdslam_t* h, phdslam_pose_t* out) {
   const int n = h->n_local;
   std::vector<float> soa((size_t)6 * n);
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaMemcpy(soa.data(), h->pose[h->cur], soa.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  CK(copy_d2h(h, soa.data(), h->pose[h->cur], soa.size() * sizeof(float)));
   for (int i = 0; i < n; ++i) {
     float* o = &out[i].px;
     for (int k = 0; k < 6; ++k) o[k] = soa[(size_t)k * n + i];
@@ -1246,25 +1265,25 @@ extern "C" int phdslam_set_poses(phdslam_t* h, const phdslam_pose_t* in) {
     for (int k = 0; k < 6; ++k) soa[(size_t)k * n + i] = s[k];
   }
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaMemcpy(h->pose[h->cur], soa.data(), soa.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CK(copy_h2d(h, h->pose[h->cur], soa.data(), soa.size() * sizeof(float)));
   return 0;
 }
 extern "C" int phdslam_get_log_weights(phdslam_t* h, float* out) {
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaMemcpy(out, h->logw, (size_t)h->n_local * sizeof(float), cudaMemcpyDeviceToHost));
+  CK(copy_d2h(h, out, h->logw, (size_t)h->n_local * sizeof(float)));
   return 0;
 }
 extern "C" int phdslam_set_log_weights(phdslam_t* h, const float* in) {
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaMemcpy(h->logw, in, (size_t)h->n_local * sizeof(float), cudaMemcpyHostToDevice));
+  CK(copy_h2d(h, h->logw, in, (size_t)h->n_local * sizeof(float)));
   return 0;
 }
 extern "C" int phdslam_get_map_sizes(phdslam_t* h, int* out) {
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaMemcpy(out, h->count[h->cur], (size_t)h->n_local * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(copy_d2h(h, out, h->count[h->cur], (size_t)h->n_local * sizeof(int)));
   return 0;
 }
 extern "C" int phdslam_get_maps(phdslam_t* h, phdslam_gaussian2d_t* out, size_t cap) {
@@ -1273,7 +1292,7 @@ extern "C" int phdslam_get_maps(phdslam_t* h, phdslam_gaussian2d_t* out, size_t 
   const size_t C = h->Cmax;
   std::vector<int> cnt(n);
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaMemcpy(cnt.data(), h->count[h->cur], (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(copy_d2h(h, cnt.data(), h->count[h->cur], (size_t)n * sizeof(int)));
   std::vector<float> blk(PHD_MAP_PLANES * C);
   /* chunked download keeps host memory bounded for large particle counts */
   const size_t chunk = std::max<size_t>(1, (64u << 20) / (PHD_MAP_PLANES * C * 4));
@@ -1281,7 +1300,7 @@ extern "C" int phdslam_get_maps(phdslam_t* h, phdslam_gaussian2d_t* out, size_t 
   size_t k = 0;
   for (size_t p0 = 0; p0 < (size_t)n; p0 += chunk) {
     size_t np = std::min(chunk, (size_t)n - p0);
-    CK(cudaMemcpy(buf.data(), h->map[h->cur] + p0 * PHD_MAP_PLANES * C, np * PHD_MAP_PLANES * C * 4, cudaMemcpyDeviceToHost));
+    CK(copy_d2h(h, buf.data(), h->map[h->cur] + p0 * PHD_MAP_PLANES * C, np * PHD_MAP_PLANES * C * 4));
     for (size_t p = 0; p < np; ++p) {
       const float* b = buf.data() + p * PHD_MAP_PLANES * C;
       for (int i = 0; i < cnt[p0 + p]; ++i) {
@@ -1319,29 +1338,41 @@ extern "C" int phdslam_set_maps(phdslam_t* h, const int* sizes, const phdslam_ga
         b[3 * C + i] = g.cov[0]; b[4 * C + i] = g.cov[1]; b[5 * C + i] = g.cov[3];
       }
     }
-    CK(cudaMemcpy(h->map[h->cur] + p0 * PHD_MAP_PLANES * C, buf.data(), np * PHD_MAP_PLANES * C * 4, cudaMemcpyHostToDevice));
+    CK(copy_h2d(h, h->map[h->cur] + p0 * PHD_MAP_PLANES * C, buf.data(), np * PHD_MAP_PLANES * C * 4));
   }
-  CK(cudaMemcpy(h->count[h->cur], sizes, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+  CK(copy_h2d(h, h->count[h->cur], sizes, (size_t)n * sizeof(int)));
   return 0;
 }
 extern "C" int phdslam_get_resample_idx(phdslam_t* h, int* out) {
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaMemcpy(out, h->resample_idx, (size_t)h->n_local * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(copy_d2h(h, out, h->resample_idx, (size_t)h->n_local * sizeof(int)));
   return 0;
 }
 extern "C" int phdslam_get_cardinalities(phdslam_t* h, float* out) {
   if (!h->n_card) return PHDSLAM_ERR_INVALID;
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaMemcpy(out, h->card[h->cur], (size_t)h->n_local * h->n_card * sizeof(float), cudaMemcpyDeviceToHost));
+  CK(copy_d2h(h, out, h->card[h->cur], (size_t)h->n_local * h->n_card * sizeof(float)));
   return 0;
 }
 extern "C" int phdslam_set_cardinalities(phdslam_t* h, const float* in) {
   if (!h->n_card) return PHDSLAM_ERR_INVALID;
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaMemcpy(h->card[h->cur], in, (size_t)h->n_local * h->n_card * sizeof(float), cudaMemcpyHostToDevice));
+  CK(copy_h2d(h, h->card[h->cur], in, (size_t)h->n_local * h->n_card * sizeof(float)));
+  return 0;
+}
+
+extern "C" int phdslam_particle_checksums(phdslam_t* h, unsigned long long* out) {
+  CK(cudaSetDevice(h->device));
+  const int n = h->n_local;
+  /* q_fx is per-resampling scratch of n_cap 64-bit words */
+  particle_checksum_kernel<<<cdiv(n, 8), 256, 0, h->stream>>>(h->pose[h->cur], h->count[h->cur], h->map[h->cur], h->card[h->cur], n,
+                                                             h->Cmax, h->n_card, h->q_fx);
+  LAUNCH_CHECK(h);
+  CK(copy_d2h_async(h, out, h->q_fx, (size_t)n * sizeof(unsigned long long), h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
 
@@ -1356,9 +1387,9 @@ extern "C" int phdslam_map_estimate(phdslam_t* h, int which, phdslam_gaussian2d_
     if (lp < 0 || lp >= h->n_local) { *n_out = 0; return 0; }
     const size_t C = h->Cmax;
     int cnt = 0;
-    CK(cudaMemcpy(&cnt, h->count[h->cur] + lp, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(copy_d2h(h, &cnt, h->count[h->cur] + lp, sizeof(int)));
     std::vector<float> b(PHD_MAP_PLANES * C);
-    CK(cudaMemcpy(b.data(), h->map[h->cur] + (size_t)lp * PHD_MAP_PLANES * C, b.size() * 4, cudaMemcpyDeviceToHost));
+    CK(copy_d2h(h, b.data(), h->map[h->cur] + (size_t)lp * PHD_MAP_PLANES * C, b.size() * 4));
     *n_out = cnt;
     for (int i = 0; i < cnt && i < cap; ++i) {
       phdslam_gaussian2d_t g;
@@ -1375,7 +1406,7 @@ extern "C" int phdslam_map_estimate(phdslam_t* h, int which, phdslam_gaussian2d_
   /* concat offsets = exclusive scan of the map sizes */
   std::vector<int> cnt(n);
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaMemcpy(cnt.data(), h->count[h->cur], (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(copy_d2h(h, cnt.data(), h->count[h->cur], (size_t)n * sizeof(int)));
   std::vector<unsigned long long> off(n + 1, 0);
   for (int p = 0; p < n; ++p) off[p + 1] = off[p] + (unsigned long long)cnt[p];
   const unsigned long long n_tot = off[n];
@@ -1384,10 +1415,10 @@ extern "C" int phdslam_map_estimate(phdslam_t* h, int which, phdslam_gaussian2d_
     if (!h->totals_dev) CK(cudaMalloc(&h->totals_dev, (size_t)h->world * sizeof(unsigned long long)));
     unsigned long long* d_one = nullptr;
     CK(cudaMalloc(&d_one, sizeof(unsigned long long)));
-    CK(cudaMemcpy(d_one, &n_tot, sizeof(n_tot), cudaMemcpyHostToDevice));
+    CK(copy_h2d(h, d_one, &n_tot, sizeof(n_tot)));
     CKN(ncclAllGather(d_one, h->totals_dev, 1, ncclUint64, comm, h->stream));
     std::vector<unsigned long long> all(h->world);
-    CK(cudaMemcpyAsync(all.data(), h->totals_dev, (size_t)h->world * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(copy_d2h_async(h, all.data(), h->totals_dev, (size_t)h->world * 8, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     cudaFree(d_one);
     for (int r = 0; r < h->rank; ++r) gbase += all[r];
@@ -1402,7 +1433,7 @@ extern "C" int phdslam_map_estimate(phdslam_t* h, int which, phdslam_gaussian2d_
   CK(cudaMalloc(&acc, sizeof(EapAcc)));
   CK(cudaMalloc(&d_out, (size_t)std::max(cap, 1) * sizeof(phdslam_gaussian2d_t)));
   CK(cudaMallocHost(&key_host, sizeof(unsigned long long)));
-  CK(cudaMemcpyAsync(d_off, off.data(), (size_t)(n + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
+  CK(copy_h2d_async(h, d_off, off.data(), (size_t)(n + 1) * sizeof(unsigned long long), h->stream));
   CK(cudaMemsetAsync(acc, 0, sizeof(EapAcc), h->stream));
   eap_concat_kernel<<<cdiv(n, 8), 256, 0, h->stream>>>(h->map[h->cur], h->count[h->cur], h->logw, d_off, n, h->Cmax, rec);
   LAUNCH_CHECK(h);
@@ -1424,9 +1455,9 @@ extern "C" int phdslam_map_estimate(phdslam_t* h, int which, phdslam_gaussian2d_
     if (*key_host == 0) break;
   }
   int n_eap = 0;
-  CK(cudaMemcpy(&n_eap, &acc->n_out, sizeof(int), cudaMemcpyDeviceToHost));
+  CK(copy_d2h(h, &n_eap, &acc->n_out, sizeof(int)));
   *n_out_p = n_eap;
-  if (n_eap > 0) CK(cudaMemcpy(out, d_out, (size_t)std::min(n_eap, cap) * sizeof(phdslam_gaussian2d_t), cudaMemcpyDeviceToHost));
+  if (n_eap > 0) CK(copy_d2h(h, out, d_out, (size_t)std::min(n_eap, cap) * sizeof(phdslam_gaussian2d_t)));
   cudaFree(rec); cudaFree(d_off); cudaFree(acc); cudaFree(d_out); cudaFreeHost(key_host);
   return rc;
 }

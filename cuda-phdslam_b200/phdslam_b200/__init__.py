@@ -82,7 +82,7 @@ class Estimate(C.Structure):
 class Timings(C.Structure):
     _fields_ = [("predict_ms", C.c_float), ("update_ms", C.c_float), ("merge_ms", C.c_float), ("weights_ms", C.c_float),
                 ("estimate_ms", C.c_float), ("resample_ms", C.c_float), ("launches", C.c_ulonglong),
-                ("migrated_in", C.c_ulonglong)]
+                ("migrated_in", C.c_ulonglong), ("h2d_bytes", C.c_ulonglong), ("d2h_bytes", C.c_ulonglong)]
 
 
 # every symbol include/phdslam.h declares (tests/test_abi.py checks the built library exports all of them)
@@ -91,7 +91,7 @@ ABI_SYMBOLS = [
     "phdslam_create", "phdslam_destroy", "phdslam_set_config", "phdslam_get_config", "phdslam_dist_unique_id",
     "phdslam_dist_init", "phdslam_plan_migration", "phdslam_resample_threshold", "phdslam_predict", "phdslam_update", "phdslam_estimate", "phdslam_map_estimate",
     "phdslam_resample", "phdslam_step", "phdslam_step_filter", "phdslam_step_resample", "phdslam_set_particle_count",
-    "phdslam_particle_capacity", "phdslam_n_local", "phdslam_local_offset", "phdslam_get_poses",
+    "phdslam_particle_capacity", "phdslam_particle_checksums", "phdslam_n_local", "phdslam_local_offset", "phdslam_get_poses",
     "phdslam_set_poses", "phdslam_get_log_weights", "phdslam_set_log_weights", "phdslam_get_map_sizes",
     "phdslam_get_maps", "phdslam_set_maps", "phdslam_get_resample_idx", "phdslam_get_cardinalities",
     "phdslam_set_cardinalities", "phdslam_update_terms", "phdslam_get_timings", "phdslam_stream",
@@ -134,6 +134,7 @@ def load_library(path=None):
     lib.phdslam_step_resample.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.phdslam_set_particle_count.argtypes = [C.c_void_p, C.c_int]
     lib.phdslam_particle_capacity.argtypes = [C.c_void_p]
+    lib.phdslam_particle_checksums.argtypes = [C.c_void_p, C.c_void_p]
     for name in ("phdslam_n_local", "phdslam_local_offset", "phdslam_synchronize", "phdslam_set_overlap", "phdslam_snapshot", "phdslam_restore"):
         getattr(lib, name).argtypes = [C.c_void_p]
     for name in ("phdslam_get_poses", "phdslam_set_poses", "phdslam_get_log_weights", "phdslam_set_log_weights",
@@ -367,6 +368,12 @@ class PhdSlam(object):
         _check(self.lib.phdslam_step(self._h, step_index, _ptr(c), z.ctypes.data if M else None, M, fields, C.byref(e),
                                      C.byref(res)))
         return e, bool(res.value)
+
+    def particle_checksums(self):
+        """one uint64 per local particle over pose, map and cardinality: an offspring's equals its ancestor's"""
+        out = np.zeros(self.n_local, dtype=np.uint64)
+        _check(self.lib.phdslam_particle_checksums(self._h, out.ctypes.data))
+        return out
 
     def step_filter(self, step_index, control, Z):
         """predict + update + estimate: the state run_synth looks at (and logs) is the one after this half"""

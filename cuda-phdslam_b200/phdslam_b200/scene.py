@@ -7,7 +7,7 @@ range/bearing noise + uniform clutter) mirrors python/RangeBearingMeasurementMod
 """
 import numpy as np
 
-from . import GAUSSIAN_DTYPE, POSE_DTYPE, default_config
+from . import GAUSSIAN_DTYPE, POSE_DTYPE, Config, default_config
 
 
 def scene_config(P, C, M, max_components=None, **overrides):
@@ -22,6 +22,38 @@ def scene_config(P, C, M, max_components=None, **overrides):
     )
     kw.update(overrides)
     return default_config(**kw)
+
+
+def scene_config_py(P, C, M, max_components=None, **overrides):
+    """scene_config() WITHOUT libphdslam.so: the same phdslam_config_t image built field by field in Python (defaults of
+    phdslam_config_defaults restated; tests/test_bench_host.py checks it is byte-identical to scene_config()).
+    For bench.py's --impl reference arm, whose process must not load the product library."""
+    f32 = np.float32
+    c = Config()
+    d = dict(motion_type=1, ax=0.5, ay=0.0, ayaw=0.0087, dt=0.1, max_bearing=float(f32(np.pi)), min_range=0.0, max_range=20.0,
+             std_bearing=0.0524, std_range=1.0, clutter_rate=15.0, pd=0.98, n_particles=512, n_predict_particles=1,
+             resample_threshold=0.15, subdivide_predict=1, birth_weight=0.05, birth_noise_factor=1.5, min_separation=5.0,
+             min_feature_weight=0.00001, particle_weighting=1, max_cardinality=256, filter_type=1, map_estimate=1,
+             max_steps=10000, n_steps=-1, data_directory=b"data/", measurement_fields=2, max_components=256,
+             update_buffer_bytes=32 << 30)
+    kw = dict(
+        motion_type=1, n_particles=P, filter_type=0, feature_model=0,
+        max_range=15.0, max_bearing=3.141593, min_range=0.0, std_range=0.25, std_bearing=0.008727, pd=0.95,
+        clutter_rate=20.0, birth_weight=1e-4, birth_noise_factor=1.0, min_feature_weight=1e-6, min_separation=10.0,
+        particle_weighting=0, distance_metric=0, resample_threshold=0.5, map_estimate=0,
+        l=1.415, h=0.38, a=1.89, b=0.5, std_encoder=1.0, std_alpha=0.034907, dt=0.1,
+        max_components=max_components if max_components is not None else max(64, 2 * C + M),
+    )
+    kw.update(overrides)
+    d.update(kw)
+    names = {n for n, _ in Config._fields_}
+    for k, v in d.items():
+        if k not in names:
+            raise KeyError("scene_config_py: %r is not a plain field of phdslam_config_t" % k)
+        setattr(c, k, int(v) if k == "seed" else v)
+    # config.clutterDensity = config.clutterRate / (2*config.maxBearing*config.maxRange) (main.cpp:1065), in fp32
+    c.clutter_density = float(f32(c.clutter_rate) / (f32(2.0) * f32(c.max_bearing) * f32(c.max_range)))
+    return c
 
 
 def make_scene(P, C, M, seed=0, n_far=0, n_near=0, max_range=15.0, std_range=0.25, std_bearing=0.008727, particle_seed=None):

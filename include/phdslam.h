@@ -204,6 +204,11 @@ int phdslam_get_resample_idx(phdslam_t* h, int* out);
 int phdslam_get_cardinalities(phdslam_t* h, float* out);
 int phdslam_set_cardinalities(phdslam_t* h, const float* in);
 
+/* One 64-bit checksum per local particle over what a resampled copy carries (src/slamtypes.h:313-333): pose, map size,
+ * map components, CPHD cardinality row.  An offspring's checksum equals its ancestor's, whichever GPU owned the ancestor
+ * (bench.py's exchange_check, tests/test_dist_gpu.py). */
+int phdslam_particle_checksums(phdslam_t* h, unsigned long long* out /* n_local */);
+
 /* Dense GM-PHD update of the current state against z WITHOUT prune/merge or weight update:
  * the features_update array of phdUpdateKernel (src/phdfilter.cu:2083-2321) in the reference's order
  * [non-detect C | detect m-major M*C | birth M] per particle, plus the per-particle log-weight increment
@@ -216,6 +221,8 @@ typedef struct phdslam_timings {
   float predict_ms, update_ms, merge_ms, weights_ms, estimate_ms, resample_ms;
   unsigned long long launches; /* kernels launched by this handle so far */
   unsigned long long migrated_in; /* particles received from other ranks by resampling so far */
+  unsigned long long h2d_bytes;   /* bytes this handle copied host -> device so far (counted at every copy call) */
+  unsigned long long d2h_bytes;   /* bytes this handle copied device -> host so far */
 } phdslam_timings_t;
 /* CUDA-event timings of the most recent call of each phase (events on the handle's stream). */
 int phdslam_get_timings(phdslam_t* h, phdslam_timings_t* out);

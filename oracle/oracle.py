@@ -17,16 +17,34 @@ GAUSSIAN_DTYPE = np.dtype([("cov", "f4", (4,)), ("mean", "f4", (2,)), ("weight",
 _lib = None
 
 
+LIB_USED = None
+
+
 def build():
     subprocess.check_call(["make", "-s", "-C", _HERE])
 
 
-def load():
-    global _lib
+def build_native(timeout=180):
+    """-O3 -march=native build for the host this process runs on (the timed CPU baseline).  Returns its path or None."""
+    path = os.path.join(_HERE, "libphd_oracle_native.so")
+    try:
+        subprocess.check_call(["make", "-s", "-B", "-C", _HERE, "native"], timeout=timeout, stdout=subprocess.DEVNULL,
+                              stderr=subprocess.DEVNULL)
+        C.CDLL(path)          # loads and relocates: a binary this CPU cannot run fails here, not in the timed loop
+        return path
+    except Exception:
+        return None
+
+
+def load(path=None):
+    """path: another build of the same source (build_native()); must be chosen before the first load()."""
+    global _lib, LIB_USED
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = path or os.environ.get("PHD_ORACLE_LIB") or LIB_PATH
+        if path == LIB_PATH and not os.path.exists(LIB_PATH):
             build()
-        lib = C.CDLL(LIB_PATH)
+        LIB_USED = path
+        lib = C.CDLL(path)
         lib.oracle_create.restype = C.c_void_p
         lib.oracle_create.argtypes = [C.c_void_p]
         lib.oracle_mahalanobis.restype = C.c_float

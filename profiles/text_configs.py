@@ -4,6 +4,7 @@
 
     python profiles/text_configs.py --impl oracle [--threads N]      # the CPU oracle
     python profiles/text_configs.py --impl ours                      # the CUDA library (needs a GPU)
+    python profiles/text_configs.py --impl both                      # both arms on the same box, one after the other
 
 configs[0]: measurements_synth_ackerman.txt + controls_synth.txt, cfg/config.cfg sensor / filter values, 256 particles
 configs[1]: measurements_synth_cv.txt, constant-velocity motion, 4096 particles
@@ -44,6 +45,8 @@ def run(name, cfg, Z, U, impl, threads, max_steps):
         f = P.PhdSlam(cfg, device=0)
     else:
         from oracle import oracle as O
+        if O._lib is None:
+            O.load(O.build_native())           # -O3 -march=native on the host that is timed
         f = O.Oracle(cfg, threads=threads)
     n_steps = min(len(Z), max_steps) if U is None else min(len(Z), len(U) + 1, max_steps)
     ms, pairs = [], 0
@@ -68,7 +71,7 @@ def run(name, cfg, Z, U, impl, threads, max_steps):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--impl", default="oracle", choices=["oracle", "ours"])
+    ap.add_argument("--impl", default="oracle", choices=["oracle", "ours", "both"])
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 1)
     ap.add_argument("--max-steps", type=int, default=1 << 30)
     ap.add_argument("--only", type=int, default=-1)
@@ -76,7 +79,10 @@ def main():
     for i, (name, cfg, Z, U) in enumerate(configs()):
         if a.only >= 0 and i != a.only:
             continue
-        run(name, cfg, Z, U, a.impl, a.threads, a.max_steps)
+        for impl in (("ours", "oracle") if a.impl == "both" else (a.impl,)):
+            run(name, cfg, Z, U, impl, a.threads, a.max_steps)
+            if impl == "oracle" and a.impl == "both" and a.threads > 1:
+                run(name, cfg, Z, U, impl, 1, min(a.max_steps, 100))      # single-thread figure on a prefix of the run
 
 
 if __name__ == "__main__":

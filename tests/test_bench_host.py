@@ -89,3 +89,28 @@ def test_text_config_runner_oracle_arm():
                                    "--max-steps", "4", "--threads", "2"], text=True, timeout=300)
     lines = [json.loads(l) for l in out.strip().split("\n")]
     assert [l["particles"] for l in lines] == [256, 4096] and all(l["steps"] == 4 and l["ms_per_step_mean"] > 0 for l in lines)
+
+
+def test_python_scene_config_is_byte_identical_to_the_library_one(bench):
+    """bench.py's --impl reference arm builds its config without libphdslam.so (scene_config_py): same bytes"""
+    from phdslam_b200 import scene as S
+    for name, wl in bench.WORKLOADS.items():
+        extra = {k: v for k, v in wl.items() if k not in ("P", "C", "M", "max_components")}
+        a = S.scene_config(wl["P"], wl["C"], wl["M"], max_components=wl["max_components"], **extra)
+        b = S.scene_config_py(wl["P"], wl["C"], wl["M"], max_components=wl["max_components"], **extra)
+        assert bytes(a) == bytes(b), name
+
+
+def test_reference_arm_does_not_load_the_product_library():
+    """`bench.py --impl reference` times the CPU oracle only: libphdslam.so must not be mapped into that process
+    (the arm asserts it itself on /proc/self/maps; here the whole command is run on a small workload)"""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--workload", "synthetic_1024x64x32_phd"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().split("\n")[-1])
+    assert line["impl"] == "reference" and line["gpu_launches"] == 0 and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["single_thread_value"] > 0
+    assert line["config"]["particles_per_gpu"] == 1024

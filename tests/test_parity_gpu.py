@@ -197,6 +197,30 @@ def test_step_loop_constant_velocity_data():
     assert_state_equal(g, o, "after 20 CV steps")
 
 
+def test_step_loop_configs1_at_full_size():
+    """BASELINE configs[1] at its literal size: constant-velocity text data, 4096 particles, the first 120 steps of
+    run_synth's loop (predict, update, estimate, nEff test, resampling) against the oracle (all host threads): resampling
+    decisions, component counts and ancestor indices bit-exact at EVERY step, floats within 1e-4 at the end"""
+    cfg = P.load_config(os.path.join(GOLDEN, "config_ackerman.cfg"))
+    cfg.set(motion_type=0, n_particles=4096, max_components=256, initial_vx=2.0, initial_vyaw=0.2, acc_x=0.5, acc_y=0.5,
+            acc_yaw=0.087, dt=0.02, max_range=10.0, std_range=1.0, std_bearing=0.0349, seed="3")
+    Z = P.load_measurements(os.path.join(DATA, "measurements_synth_cv.txt"))
+    g = P.PhdSlam(cfg)
+    o = O.Oracle(cfg, threads=os.cpu_count() or 1)
+    n_res = 0
+    for k in range(120):
+        ge, gr = g.step(k, None, Z[k])
+        oe, orr = o.step(k, None, Z[k])
+        assert gr == orr, "resampling decision differs at step %d" % k
+        n_res += gr
+        assert (g.map_sizes == o.map_sizes).all(), "component counts differ at step %d" % k
+        assert (g.resample_idx == o.resample_idx).all(), "ancestors differ at step %d" % k
+        close(ge.pose, oe.pose, "expected pose step %d" % k, atol=1e-6)
+        close(ge.neff, oe.neff, "nEff step %d" % k)
+    assert n_res >= 3
+    assert_state_equal(g, o, "after 120 CV steps at 4096 particles")
+
+
 def test_edge_cases():
     # empty measurement set: no-op (main.cpp:1258)
     cfg = S.scene_config(8, 4, 2, max_components=64)
@@ -451,3 +475,30 @@ def test_full_size_step_matches_oracle_on_a_particle_subset():
     anc = g.resampleParticles()
     assert (np.diff(anc) >= 0).all() and anc.min() >= 0 and anc.max() < Pn
     assert (g.map_sizes == sizes[anc]).all()
+
+
+@pytest.mark.parametrize("cphd", [False, True])
+def test_update_modes_agree(cphd):
+    """update_mode = 1 (the fused update emits only the prune survivors; production mode, bench.py's `production` key) gives
+    the same maps, weights and cardinalities as update_mode = 0 (the reference-equivalent dense update terms are
+    materialised in HBM first) -- bit for bit -- and both match the oracle"""
+    Pn, C, M = 96, 70, 24
+    extra = dict(filter_type=1, max_cardinality=127) if cphd else {}
+    cfg = S.scene_config(Pn, C, M, max_components=256, **extra)
+    sc = S.make_scene(Pn, C, M, seed=31, n_near=3, n_far=2)
+    out = []
+    for mode in (0, 1):
+        cfg.set(update_mode=mode)
+        g = P.PhdSlam(cfg)
+        S.load_scene(g, sc)
+        g.phdPredict(np.float32([1.0, 0.05]))
+        g.phdUpdateSynth(sc["Z"])
+        sizes, maps = g.get_maps()
+        out.append((sizes, maps.tobytes(), g.log_weights.tobytes(), g.cardinalities.tobytes() if cphd else b""))
+    assert (out[0][0] == out[1][0]).all() and out[0][1:] == out[1][1:]
+    cfg.set(update_mode=0)
+    o = O.Oracle(cfg)
+    S.load_scene(o, sc)
+    o.phdPredict(np.float32([1.0, 0.05]))
+    o.phdUpdateSynth(sc["Z"])
+    assert_state_equal(g, o, "update_mode 1")
