@@ -304,6 +304,7 @@ __global__ void scan_apply_kernel(const unsigned long long* __restrict__ in, int
 #define UPD_WARPS (UPD_THREADS / 32)
 #define UPD_FLOATS_PER_COMP 25
 #define UPD_NF 17            /* per-component constants kept for the (component, measurement) loop */
+#define UPD_MAXCH 32         /* 64-component chunks per particle the fused mode's chunk skipping covers (Cmax <= 2048) */
 
 /* field order of the shared-memory constant records: one record per PAIR of adjacent components, UPD_NF float2
  * each (136 bytes; lane-consecutive records are conflict-free for 64-bit shared loads) */
@@ -378,6 +379,8 @@ __host__ __device__ static inline size_t cphd_float_count(int n_card, int M) {
 __host__ __device__ static inline size_t cphd_smem_bytes(int n_card, int M) {
   return cphd_float_count(n_card, M) * sizeof(float) + (4 * (size_t)cphd_mp(M) + 2 * (size_t)n_card) * sizeof(double);
 }
+
+__host__ __device__ static inline size_t cphd_chunkmax_bytes(int M, int Cmax) { return (size_t)M * ((Cmax + 63) >> 6) * sizeof(float); }
 
 __device__ __forceinline__ float cphd_mulk(int k, float x) { return k == 0 ? 0.0f : (float)k * x; }
 __device__ __forceinline__ float cphd_clamp(float t) { return (t < PHD_LOG0) ? PHD_LOG0 : t; }
@@ -730,10 +733,13 @@ __device__ __forceinline__ float2 lds2(const float2* p) { return *p; }
  * one multiplication, w = e * exp(-L_m) (oracle: the same product), instead of evaluating the exponential a second time;
  * nL2 is then exp(-L_m).  Without STASH (CPHD: all first passes run before any second pass) pass 2 recomputes
  * w = exp(log-weight + nL2). */
+/* cmk (fused mode, pass 1 only; nullptr otherwise): receives the chunk's largest exp(log-weight) (STASH) or largest
+ * log-weight, so that pass 2 can leave out chunks that cannot hold a survivor of the prune (upd_measurement). */
 template <int PASS, bool TAIL, bool FAST, bool DENSE, bool STASH>
 __device__ __forceinline__ void upd_chunk(const float2* __restrict__ rec, int jr, int C, float2 zr2, float2 zb2, bool dead,
                                           float2 nL2, float2& acc, float* __restrict__ Dm, bool even, float min_w, int lane,
-                                          int* s_ncand, float4* __restrict__ cand, int Smax, int tbase_m, float2* __restrict__ stash) {
+                                          int* s_ncand, float4* __restrict__ cand, int Smax, int tbase_m, float2* __restrict__ stash,
+                                          float* __restrict__ cmk = nullptr) {
   bool v0 = true, v1 = true;
   if (TAIL) {
     v0 = jr < C;
@@ -768,6 +774,20 @@ __device__ __forceinline__ void upd_chunk(const float2* __restrict__ rec, int jr
     }
     if (STASH) stash[jr >> 1] = e;
     acc = __fadd2_rn(acc, e);
+    if (!DENSE && cmk) {
+      if (STASH) {     /* e >= +0 (or NaN, which is the largest bit pattern): unsigned order = float order */
+        const unsigned mx = __reduce_max_sync(FULL_MASK, max(__float_as_uint(e.x), __float_as_uint(e.y)));
+        if (lane == 0) *cmk = __uint_as_float(mx);
+      } else {
+        unsigned k0 = float_to_ordered_uint(lw.x), k1 = float_to_ordered_uint(lw.y);
+        if (TAIL) {
+          if (!v0) k0 = 0u;
+          if (!v1) k1 = 0u;
+        }
+        const unsigned mx = __reduce_max_sync(FULL_MASK, max(k0, k1));
+        if (lane == 0) *cmk = ordered_uint_to_float(mx);
+      }
+    }
   } else {
     float2 wt = STASH ? __fmul2_rn(stash[jr >> 1], nL2) : phd_expf2(__fadd2_rn(lw, nL2));
     if (TAIL) {
@@ -824,22 +844,39 @@ __device__ __forceinline__ void upd_chunk(const float2* __restrict__ rec, int jr
   }
 }
 
+/* Fused mode (no dense output) only -- cm != nullptr: pass 1 records per 64-component chunk the largest exp(log-weight)
+ * (PHD) or the largest log-weight (CPHD); pass 2 skips a chunk none of whose terms can survive the prune:
+ *   PHD : w = e * sc is monotone in e, so fmul(max e, sc) < min_w is EXACTLY "no survivor in this chunk";
+ *   CPHD: w = exp(lw + D): skipped when max lw + D < skip_thr = log(min_w) - 0.01 (the margin covers the 2 ulp of the
+ *         deterministic exp; a chunk inside the margin is simply processed).
+ * Nothing else reads the detection weights in that mode (the sum of the detection weights is needed by Vo's empty-map
+ * weighting only, for which the caller passes cm = nullptr), so the maps, weights and cardinalities are bit-identical. */
 template <int PASS, bool FAST, bool DENSE, bool STASH>
 __device__ __forceinline__ float2 upd_measurement(const float2* __restrict__ rec0, int C, float2 zr2, float2 zb2, bool dead,
                                                   float2 nL2, float* __restrict__ Dm, bool even, float min_w, int lane,
                                                   int* s_ncand, float4* __restrict__ cand, int Smax, int tbase_m,
-                                                  float2* __restrict__ stash) {
+                                                  float2* __restrict__ stash, float* __restrict__ cm = nullptr,
+                                                  float skip_thr = 0.0f) {
   float2 acc = make_float2(0.0f, 0.0f);
   const int nfull = C >> 6;
   const float2* rec = rec0 + (size_t)lane * UPD_NF;
   int jr = 2 * lane;
   for (int k = 0; k < nfull; ++k) {
-    upd_chunk<PASS, false, FAST, DENSE, STASH>(rec, jr, C, zr2, zb2, dead, nL2, acc, Dm, even, min_w, lane, s_ncand, cand, Smax, tbase_m, stash);
+    bool skip = false;
+    if (!DENSE && PASS == 2 && cm) skip = STASH ? (__fmul_rn(cm[k], nL2.x) < min_w) : (cm[k] + nL2.x < skip_thr);
+    if (!skip)
+      upd_chunk<PASS, false, FAST, DENSE, STASH>(rec, jr, C, zr2, zb2, dead, nL2, acc, Dm, even, min_w, lane, s_ncand, cand, Smax, tbase_m, stash,
+                                                 (!DENSE && PASS == 1 && cm) ? cm + k : nullptr);
     rec += 32 * UPD_NF;
     jr += 64;
   }
-  if (C & 63)
-    upd_chunk<PASS, true, FAST, DENSE, STASH>(rec, jr, C, zr2, zb2, dead, nL2, acc, Dm, even, min_w, lane, s_ncand, cand, Smax, tbase_m, stash);
+  if (C & 63) {
+    bool skip = false;
+    if (!DENSE && PASS == 2 && cm) skip = STASH ? (__fmul_rn(cm[nfull], nL2.x) < min_w) : (cm[nfull] + nL2.x < skip_thr);
+    if (!skip)
+      upd_chunk<PASS, true, FAST, DENSE, STASH>(rec, jr, C, zr2, zb2, dead, nL2, acc, Dm, even, min_w, lane, s_ncand, cand, Smax, tbase_m, stash,
+                                                (!DENSE && PASS == 1 && cm) ? cm + nfull : nullptr);
+  }
   return acc;
 }
 
@@ -866,6 +903,7 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
   __shared__ int s_wcnt[UPD_WARPS];
   __shared__ int s_ncand;
   __shared__ float s_cphd_scal[2];
+  __shared__ float s_cmw[UPD_WARPS][UPD_MAXCH];   /* fused PHD: chunk maxima of the measurement a warp is working on */
 
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
   const int pl = a.p0 + blockIdx.x;     /* local particle index */
@@ -1030,6 +1068,12 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
   float2* s_stash = reinterpret_cast<float2*>(s_w) + (size_t)warp * (Cmax >> 1);
   if (!CPHD) __syncthreads();
   const bool even = ((C & 1) == 0);      /* 64-bit stores need (C + m*C + j) even for every m */
+  /* fused mode: chunk skipping in pass 2 (upd_measurement); not for Vo's weighting, which sums every detection weight */
+  const int nch = (Cmax + 63) >> 6;
+  const bool use_skip = !DENSE && nch <= UPD_MAXCH && (CPHD || c.particle_weighting != 1);
+  float* s_cmm = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(smem) + update_smem_bytes(Cmax) +
+                                          (CPHD ? cphd_smem_bytes(c.n_card, M) : 0));   /* CPHD: [M][nch] */
+  const float skip_thr = (c.min_w > 0.0f) ? phd_logf(c.min_w) - 0.01f : -INFINITY;
   if (CPHD) {
     /* ---- CPHD phase 2a: likelihood mass S_m = sum_j exp(partial log-weight) of every measurement ---- */
     for (int m = warp; m < M; m += UPD_WARPS) {
@@ -1037,10 +1081,11 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
       const bool dead = c.labeled && (s_zl[m] != 0.0f);
       const bool fast = fabsf(zb) < 3.14159f;
       float2 acc;
+      float* cm = use_skip ? s_cmm + (size_t)m * nch : nullptr;
       if (fast)
-        acc = upd_measurement<1, true, DENSE, false>(s_rec, C, splat2(zr), splat2(zb), dead, splat2(0.0f), D, even, c.min_w, lane, &s_ncand, cand, Smax, 0, nullptr);
+        acc = upd_measurement<1, true, DENSE, false>(s_rec, C, splat2(zr), splat2(zb), dead, splat2(0.0f), D, even, c.min_w, lane, &s_ncand, cand, Smax, 0, nullptr, cm);
       else
-        acc = upd_measurement<1, false, DENSE, false>(s_rec, C, splat2(zr), splat2(zb), dead, splat2(0.0f), D, even, c.min_w, lane, &s_ncand, cand, Smax, 0, nullptr);
+        acc = upd_measurement<1, false, DENSE, false>(s_rec, C, splat2(zr), splat2(zb), dead, splat2(0.0f), D, even, c.min_w, lane, &s_ncand, cand, Smax, 0, nullptr, cm);
       float sum = warp_butterfly_sum(acc.x + acc.y);
       if (lane == 0) s_L[m] = sum;
     }
@@ -1092,16 +1137,19 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
     float2 wacc;
     if (CPHD) {
       L = -s_L[m];                        /* weights = exp(partial log-weight + D_m) (cphdUpdateKernel :1794-1799) */
+      float* cm = use_skip ? s_cmm + (size_t)m * nch : nullptr;
       if (fast)
-        wacc = upd_measurement<2, true, DENSE, false>(s_rec, C, zr2, zb2, dead, splat2(-L), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m, nullptr);
+        wacc = upd_measurement<2, true, DENSE, false>(s_rec, C, zr2, zb2, dead, splat2(-L), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m, nullptr, cm, skip_thr);
       else
-        wacc = upd_measurement<2, false, DENSE, false>(s_rec, C, zr2, zb2, dead, splat2(-L), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m, nullptr);
+        wacc = upd_measurement<2, false, DENSE, false>(s_rec, C, zr2, zb2, dead, splat2(-L), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m, nullptr, cm, skip_thr);
     } else {
       float2 acc;
+      float* cm = use_skip ? s_cmw[warp] : nullptr;
       if (fast)
-        acc = upd_measurement<1, true, DENSE, true>(s_rec, C, zr2, zb2, dead, splat2(0.0f), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m, s_stash);
+        acc = upd_measurement<1, true, DENSE, true>(s_rec, C, zr2, zb2, dead, splat2(0.0f), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m, s_stash, cm);
       else
-        acc = upd_measurement<1, false, DENSE, true>(s_rec, C, zr2, zb2, dead, splat2(0.0f), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m, s_stash);
+        acc = upd_measurement<1, false, DENSE, true>(s_rec, C, zr2, zb2, dead, splat2(0.0f), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m, s_stash, cm);
+      __syncwarp();                       /* lane 0's chunk maxima are read by the whole warp in pass 2 */
       float sum = warp_butterfly_sum(acc.x + acc.y);
       sum = sum + c.clutter_density;
       sum = sum + c.birth_weight;
@@ -1109,9 +1157,10 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
       /* every lane reads back only what it stashed itself: no barrier between the passes */
       const float2 sc2 = splat2(phd_expf(-L));
       if (fast)
-        wacc = upd_measurement<2, true, DENSE, true>(s_rec, C, zr2, zb2, dead, sc2, D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m, s_stash);
+        wacc = upd_measurement<2, true, DENSE, true>(s_rec, C, zr2, zb2, dead, sc2, D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m, s_stash, cm);
       else
-        wacc = upd_measurement<2, false, DENSE, true>(s_rec, C, zr2, zb2, dead, sc2, D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m, s_stash);
+        wacc = upd_measurement<2, false, DENSE, true>(s_rec, C, zr2, zb2, dead, sc2, D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m, s_stash, cm);
+      __syncwarp();                       /* before pass 1 of the warp's next measurement overwrites the maxima */
     }
     /* the sum of the detection weights is needed by Vo's empty-map particle weighting only (:2264-2279) */
     float dsum = 0.0f;
@@ -1786,10 +1835,18 @@ __device__ __forceinline__ void block_radix_pass(const unsigned* keys, const uns
   const int per = (((n + MF_WARPS - 1) / MF_WARPS) + 31) & ~31;
   const int lo = min(warp * per, n), hi = min(lo + per, n);
   unsigned short* hw = hist + warp * 256;
-  for (int i = lo + lane; i < hi; i += 32) {
-    const unsigned idx = in[i];
-    const unsigned d = TIE ? (__brev(idx) >> 24) : ((keys[idx] >> shift) & 255u);
-    atomic_add_u16(hw, (int)d, 1u);
+  for (int b0 = lo; b0 < hi; b0 += 32) {
+    /* the high bytes of the weight keys take a handful of values: one add per distinct digit of the round, not 32 adds on
+     * one counter (no atomics needed either: the histogram row belongs to this warp) */
+    const int i = b0 + lane;
+    unsigned d = 0x80000000u | (unsigned)lane;
+    if (i < hi) {
+      const unsigned idx = in[i];
+      d = TIE ? (__brev(idx) >> 24) : ((keys[idx] >> shift) & 255u);
+    }
+    const unsigned same = __match_any_sync(FULL_MASK, d);
+    if (i < hi && (same & lt_mask) == 0) hw[d] = (unsigned short)(hw[d] + __popc(same));
+    __syncwarp();
   }
   __syncthreads();
   if (warp == 0) {
@@ -1848,7 +1905,7 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
   __shared__ int s_scan[MF_WARPS];
   __shared__ int s_flag;                 /* a near list overflowed: the particle goes to merge_kernel */
   __shared__ int s_kzero;                /* first cluster with zero weight (:2821-2822) */
-  __shared__ int s_nseeds, s_klimit, s_n, s_pool_n, s_stopr, s_und;
+  __shared__ int s_nseeds, s_klimit, s_n, s_pool_n, s_stopr;
   const DevCfg& c = a.c;
   const int S = a.Scap;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -2058,21 +2115,26 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
       }
     }
     unsigned short* cellr = reinterpret_cast<unsigned short*>(pool);   /* cell of every candidate (the pool is free until the pair phase) */
-    for (int r = tid; r < n; r += MF_THREADS) {
-      const float4 A0 = crec[2 * r], g = crec[2 * r + 1];
-      int cx = 0, cy = 0;
-      if (G > 1) {
-        cx = (int)((g.x - xmin) / cs);
-        cy = (int)((g.y - ymin) / cs);
-        cx = min(max(cx, 0), G - 1);
-        cy = min(max(cy, 0), G - 1);
+    for (int r0 = warp * 32; r0 < n; r0 += MF_THREADS) {      /* a warp covers 32 consecutive ranks: one selfbits word */
+      const int r = r0 + lane;
+      bool self = false;
+      if (r < n) {
+        const float4 A0 = crec[2 * r], g = crec[2 * r + 1];
+        int cx = 0, cy = 0;
+        if (G > 1) {
+          cx = (int)((g.x - xmin) / cs);
+          cy = (int)((g.y - ymin) / cs);
+          cx = min(max(cx, 0), G - 1);
+          cy = min(max(cy, 0), G - 1);
+        }
+        const int cid = cy * MRG_GMAX + cx;
+        cellr[r] = (unsigned short)cid;
+        atomic_add_u16(cend, cid, 1u);
+        self = 0.0f <= gk * (g.w + g.w) &&
+               dev_mahal(A0.x, A0.y, A0.z, A0.w, g.x, g.y, A0.x, A0.y, A0.z, A0.w, g.x, g.y) < c.min_sep;
       }
-      const int cid = cy * MRG_GMAX + cx;
-      cellr[r] = (unsigned short)cid;
-      atomic_add_u16(cend, cid, 1u);
-      if (0.0f <= gk * (g.w + g.w) &&
-          dev_mahal(A0.x, A0.y, A0.z, A0.w, g.x, g.y, A0.x, A0.y, A0.z, A0.w, g.x, g.y) < c.min_sep)
-        atomicOr(&selfbits[r >> 5], 1u << (r & 31));
+      const unsigned sb = __ballot_sync(FULL_MASK, self);
+      if (lane == 0) selfbits[r0 >> 5] = sb;
     }
     __syncthreads();
     if (warp == 0) warp_exclusive_scan_u16(cend, MRG_NCELL, lane);        /* cell starts */
@@ -2170,8 +2232,12 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
           const float4 B1 = Gc[pbo];
           const unsigned pbs = (unsigned)pbo << 16;
           unsigned mask = 0u;                                         /* bit k: position t0 + k passes the gate */
+          /* consecutive lanes usually hold consecutive segments of one run, MF_SEG records = 128 bytes apart: read in step
+           * they would all hit the same four banks (an 8-way conflict on every quarter-warp of the 128-bit loads, 58 % of
+           * this kernel's shared-memory wavefronts were excess ones); each lane therefore starts at its own offset */
 #pragma unroll
-          for (int k = 0; k < MF_SEG; ++k) {
+          for (int kk = 0; kk < MF_SEG; ++kk) {
+            const int k = (kk + lane) & (MF_SEG - 1);
             const int t = t0 + k;
             if (t < tend) {
               const float4 A1 = Gc[((t < ol1) ? ob1 : ob2) + t];
@@ -2229,7 +2295,6 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
       __syncwarp();
       evaluate(qn);
     }
-    if (tid == 0) s_und = 0;
     __syncthreads();
     for (int r = tid; r < n; r += MF_THREADS) own[r] = (unsigned short)MF_NONE;   /* held the cells until here */
     __syncthreads();
@@ -2239,27 +2304,35 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
      * below its lowest-ranked seed neighbour; block-wide sweeps until every candidate has decided (the lowest-ranked
      * undecided candidate always can). ---- */
     if (!s_flag) {
-      for (int sweep = 0;; ++sweep) {
-        bool pending = false;
-        for (int r = tid; r < n; r += MF_THREADS) {
-          if (own[r] != MF_NONE) continue;
-          unsigned minseed = MF_NONE, minund = MF_NONE;
-          for (unsigned node = HD[r]; node != MF_NONE;) {
-            const unsigned nd = pool[node];
-            const unsigned e = nd & 0xffffu;
-            node = nd >> 16;
-            const unsigned st = reinterpret_cast<volatile unsigned short*>(own)[e];
-            if (st == MF_NONE) minund = min(minund, e);
-            else if (st == e) minseed = min(minseed, e);
+      /* A candidate's list holds LOWER-ranked neighbours only, so the ranks are resolved in blocks of MF_THREADS, in
+       * ascending order: every neighbour in an earlier block has decided, and the few neighbours inside the same block
+       * are waited for by iterating on the block (reads of an iteration, barrier, writes, barrier: no thread reads a
+       * state another thread is writing).  A candidate decides once no undecided neighbour ranks below its lowest-ranked
+       * seed neighbour -- the lowest-ranked undecided candidate of the block always can, so every iteration makes progress. */
+      for (int r0 = 0; r0 < n; r0 += MF_THREADS) {
+        const int r = r0 + tid;
+        bool todo = r < n;
+        for (;;) {
+          unsigned dec = MF_NONE;
+          if (todo) {
+            unsigned minseed = MF_NONE, minund = MF_NONE;
+            for (unsigned node = HD[r]; node != MF_NONE;) {
+              const unsigned nd = pool[node];
+              const unsigned e = nd & 0xffffu;
+              node = nd >> 16;
+              const unsigned st = own[e];
+              if (st == MF_NONE) minund = min(minund, e);
+              else if (st == e) minseed = min(minseed, e);
+            }
+            if (minund == MF_NONE || minseed < minund) dec = (minseed != MF_NONE) ? minseed : (unsigned)r;
           }
-          if (minund == MF_NONE || minseed < minund) own[r] = (unsigned short)((minseed != MF_NONE) ? minseed : (unsigned)r);
-          else pending = true;
+          __syncthreads();
+          if (dec != MF_NONE) {
+            own[r] = (unsigned short)dec;
+            todo = false;
+          }
+          if (!__syncthreads_or(todo ? 1 : 0)) break;
         }
-        if (pending) s_und = sweep + 1;
-        __syncthreads();
-        const bool again = (s_und == sweep + 1);
-        __syncthreads();
-        if (!again) break;
       }
       /* output slots of the seeds, in rank order (= descending seed weight) */
       if (warp == 0) {
@@ -2443,7 +2516,7 @@ __global__ void weights_normalise_kernel(float* __restrict__ logw, int n, const 
 __global__ void estimate_kernel(const float* __restrict__ logw, const float* __restrict__ pose, int n, int offset, Reductions* red) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   long long acc[6] = {0, 0, 0, 0, 0, 0};
-  unsigned long long e2 = 0, key = 0;
+  unsigned long long e2 = 0, key = 0, cdf = 0;
   if (i < n) {
     float w = logw[i];
     if (w == w) {
@@ -2451,6 +2524,7 @@ __global__ void estimate_kernel(const float* __restrict__ logw, const float* __r
 #pragma unroll
       for (int k = 0; k < 6; ++k) acc[k] = phd_fx_from_prod(ew, pose[(size_t)k * n + i], PHD_FX_POSE_BITS);
       e2 = phd_fx_from_unit(phd_expf(2.0f * w), PHD_FX_NEFF_BITS);
+      cdf = phd_fx_from_unit(ew, PHD_FX_CDF_BITS);        /* = resample_weights_kernel: the rank's resampling CDF total */
       if (w > -FLT_MAX)
         key = ((unsigned long long)float_to_ordered_uint(w) << 32) | (unsigned long long)(0xffffffffu - (unsigned)(offset + i));
     }
@@ -2458,6 +2532,7 @@ __global__ void estimate_kernel(const float* __restrict__ logw, const float* __r
 #pragma unroll
   for (int k = 0; k < 6; ++k) acc[k] = warp_sum_i64(acc[k]);
   e2 = warp_sum_u64(e2);
+  cdf = warp_sum_u64(cdf);
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
     unsigned long long o = __shfl_xor_sync(FULL_MASK, key, off);
@@ -2468,6 +2543,7 @@ __global__ void estimate_kernel(const float* __restrict__ logw, const float* __r
     for (int k = 0; k < 6; ++k)
       if (acc[k]) atomicAdd((unsigned long long*)&red->pose_fx[k], (unsigned long long)acc[k]);
     if (e2) atomicAdd(&red->neff_fx, e2);
+    if (cdf) atomicAdd(&red->cdf_total, cdf);
     atomicMax(&red->argmax_key, key);
   }
 }
@@ -2485,13 +2561,10 @@ __global__ void resample_weights_kernel(const float* __restrict__ logw, int n, u
 
 /* ancestor(j) = min{ i : C_i > floor(r_j * total) }, C = inclusive CDF = excl[i+1] (+ cdf_base for this rank).
  * Offspring j (global) are [j0, j0+n_off); ancestors searched in the local CDF [0,n) shifted by cdf_base. */
-__global__ void resample_search_kernel(const unsigned long long* __restrict__ excl, int n, unsigned long long cdf_base,
-                                       unsigned long long total, int n_new, int j0, int n_off, int anc_offset,
-                                       const double* __restrict__ uniforms, int systematic, unsigned call, uint32_t seed_lo,
-                                       uint32_t seed_hi, int* __restrict__ anc) {
-  int jj = blockIdx.x * blockDim.x + threadIdx.x;
-  if (jj >= n_off) return;
-  int j = j0 + jj;
+/* ancestor of offspring j (global index) if it lives on this rank (local index), else -1 */
+__device__ __forceinline__ int resample_ancestor(const unsigned long long* __restrict__ excl, int n, unsigned long long cdf_base,
+                                                 unsigned long long total, int n_new, int j, const double* __restrict__ uniforms,
+                                                 int systematic, unsigned call, uint32_t seed_lo, uint32_t seed_hi) {
   const double interval = 1.0 / (double)n_new;
   double u;
   if (uniforms) {
@@ -2505,17 +2578,23 @@ __global__ void resample_search_kernel(const unsigned long long* __restrict__ ex
   unsigned long long R = (t <= 0.0) ? 0ull : (unsigned long long)t;
   if (R >= total) R = total - 1;
   /* is the ancestor on this rank?  local inclusive CDF range is (cdf_base, cdf_base + excl[n]] */
-  if (R < cdf_base || R >= cdf_base + excl[n]) {
-    anc[jj] = -1;
-    return;
-  }
+  if (R < cdf_base || R >= cdf_base + excl[n]) return -1;
   unsigned long long Rl = R - cdf_base;
   int lo = 0, hi = n - 1; /* smallest i with excl[i+1] > Rl */
   while (lo < hi) {
     int mid = (lo + hi) >> 1;
     if (excl[mid + 1] > Rl) hi = mid; else lo = mid + 1;
   }
-  anc[jj] = anc_offset + lo;
+  return lo;
+}
+__global__ void resample_search_kernel(const unsigned long long* __restrict__ excl, int n, unsigned long long cdf_base,
+                                       unsigned long long total, int n_new, int j0, int n_off, int anc_offset,
+                                       const double* __restrict__ uniforms, int systematic, unsigned call, uint32_t seed_lo,
+                                       uint32_t seed_hi, int* __restrict__ anc) {
+  int jj = blockIdx.x * blockDim.x + threadIdx.x;
+  if (jj >= n_off) return;
+  const int a = resample_ancestor(excl, n, cdf_base, total, n_new, j0 + jj, uniforms, systematic, call, seed_lo, seed_hi);
+  anc[jj] = (a < 0) ? -1 : anc_offset + a;
 }
 
 /* one warp per offspring: copy pose, map block (only `count` live components per plane), cardinality.
@@ -2548,6 +2627,112 @@ __global__ void resample_gather_kernel(const int* __restrict__ anc, int n_off, i
     for (int k = lane; k < cnt; k += 32) dst[f * Cmax + k] = src[f * Cmax + k];
   if (n_card > 0 && card_in)
     for (int k = lane; k < n_card; k += 32) card_out[jd * n_card + k] = card_in[(size_t)a * n_card + k];
+}
+
+/* NVLink exchange in ONE launch: the offspring intervals every peer owns whose ancestors live here (both ends derive them
+ * from the ranks' CDF totals, nothing is negotiated).  One warp per offspring: ancestor search on the local CDF, then the
+ * particle is written straight into the owner's back buffer through the mapped peer window. */
+#define PHD_MAX_PEERS 8
+struct PushDst {
+  float* pose; int* count; float* map; float* card; int* anc_in;   /* the peer's back buffers (mapped) */
+  int n_dst;       /* the peer's particle count */
+  int dst_first;   /* first local slot (at the peer) of the interval */
+  int j0;          /* first global offspring index of the interval */
+  int first;       /* exclusive prefix of the interval sizes */
+};
+struct PushArgs {
+  PushDst d[PHD_MAX_PEERS];
+  int n_dst_entries, total;
+  const unsigned long long* excl; int n; unsigned long long cdf_base, cdf_total; int n_new, anc_offset;
+  const double* uniforms; int systematic; unsigned call; uint32_t seed_lo, seed_hi;
+  const float* pose_in; const int* count_in; const float* map_in; const float* card_in; int Cmax, n_card;
+};
+__global__ void resample_push_kernel(PushArgs a) {
+  const int jj = blockIdx.x * (blockDim.x >> 5) + warp_id();
+  if (jj >= a.total) return;
+  const int lane = lane_id();
+  int e = 0;
+#pragma unroll
+  for (int k = 1; k < PHD_MAX_PEERS; ++k)
+    if (k < a.n_dst_entries && jj >= a.d[k].first) e = k;
+  const PushDst& D = a.d[e];
+  const int off = jj - D.first;
+  const int j = D.j0 + off;
+  const int al = resample_ancestor(a.excl, a.n, a.cdf_base, a.cdf_total, a.n_new, j, a.uniforms, a.systematic, a.call, a.seed_lo,
+                                   a.seed_hi);
+  if (al < 0) return;     /* cannot happen: the interval was planned from the same totals */
+  const size_t jd = (size_t)D.dst_first + off;
+  if (lane < 6) D.pose[(size_t)lane * D.n_dst + jd] = a.pose_in[(size_t)lane * a.n + al];
+  const int cnt = a.count_in[al];
+  if (lane == 0) {
+    D.count[jd] = cnt;
+    D.anc_in[jd] = a.anc_offset + al;
+  }
+  const float* src = a.map_in + (size_t)al * PHD_MAP_PLANES * a.Cmax;
+  float* dst = D.map + jd * PHD_MAP_PLANES * a.Cmax;
+  for (int f = 0; f < PHD_MAP_PLANES; ++f)
+    for (int k = lane; k < cnt; k += 32) dst[f * a.Cmax + k] = src[f * a.Cmax + k];
+  if (a.n_card > 0 && a.card_in)
+    for (int k = lane; k < a.n_card; k += 32) D.card[jd * a.n_card + k] = a.card_in[(size_t)al * a.n_card + k];
+}
+
+/* Mailbox all-gather over the NVLink peer window: every rank writes a record of up to MBOX_PAYLOAD 64-bit words into its
+ * slot of EVERY rank's mailbox (payload, system fence, then the sequence number as the flag), waits until all ranks'
+ * records of this sequence number have arrived in its own mailbox, and combines them in rank order (word by word: sum or
+ * max) -- one small kernel per exchange, a few microseconds, instead of an NCCL collective per statistic.  Sequence
+ * numbers advance in lock step on all ranks (the same call sequence), MBOX_SLOTS records per source are in flight at
+ * most (a rank can be one exchange ahead of the slowest one).  A rank that never arrives (it left the step with an
+ * error) is noticed after MBOX_TIMEOUT_NS: err_flag bit 4 instead of a hang. */
+#define MBOX_SLOTS 4
+#define MBOX_WORDS 16
+#define MBOX_PAYLOAD 15
+#define MBOX_TIMEOUT_NS 8000000000ull
+struct MboxPeers { unsigned long long* box[PHD_MAX_PEERS]; };   /* mailbox region of every rank (own and mapped) */
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__global__ void mbox_exchange_kernel(MboxPeers pp, int me, int W, unsigned long long seq, unsigned long long* __restrict__ words,
+                                     int n_words, unsigned max_mask, unsigned long long* __restrict__ gathered /* [W][MBOX_WORDS] or null */,
+                                     int* err_flag) {
+  __shared__ unsigned long long s_in[PHD_MAX_PEERS][MBOX_WORDS];
+  const int w = warp_id(), lane = lane_id();
+  const size_t rec = ((size_t)(seq & (MBOX_SLOTS - 1)) * PHD_MAX_PEERS);
+  if (w < W) {
+    /* my record into rank w's mailbox */
+    volatile unsigned long long* out = pp.box[w] + (rec + me) * MBOX_WORDS;
+    if (lane < n_words) out[lane] = words[lane];
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_system();
+      out[MBOX_PAYLOAD] = seq;
+    }
+    /* rank w's record in my mailbox */
+    volatile unsigned long long* in = pp.box[me] + (rec + w) * MBOX_WORDS;
+    int ok = 1;
+    if (lane == 0) {
+      const unsigned long long t0 = global_timer_ns();
+      while (in[MBOX_PAYLOAD] != seq) {
+        if (global_timer_ns() - t0 > MBOX_TIMEOUT_NS) { ok = 0; break; }
+      }
+      __threadfence_system();
+      if (!ok) atomicOr(err_flag, 4);
+    }
+    __syncwarp();
+    if (lane < MBOX_WORDS) s_in[w][lane] = (lane < n_words) ? in[lane] : ((lane == MBOX_PAYLOAD) ? seq : 0ull);
+  }
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t < n_words) {
+    unsigned long long acc = s_in[0][t];
+    for (int r = 1; r < W; ++r) {
+      const unsigned long long v = s_in[r][t];
+      acc = ((max_mask >> t) & 1u) ? (v > acc ? v : acc) : acc + v;
+    }
+    words[t] = acc;
+  }
+  if (gathered && t < W * MBOX_WORDS) gathered[t] = s_in[t / MBOX_WORDS][t % MBOX_WORDS];
 }
 
 /* after the exchange: offspring whose ancestor lives on a peer (-1 from the local search) take the index the peer pushed */

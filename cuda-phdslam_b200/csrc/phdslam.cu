@@ -194,7 +194,7 @@ static int validate_config(const phdslam_config_t* c) {
 
 /* layout of the peer window for a rank with n particles: 256-byte header (magic), then the arrays below */
 struct SlabLayout {
-  size_t pose[2], count[2], map[2], card[2], anc_in, bytes;
+  size_t pose[2], count[2], map[2], card[2], anc_in, mbox, bytes;
 };
 static SlabLayout slab_layout(size_t n, size_t Cmax, size_t n_card) {
   SlabLayout L;
@@ -207,9 +207,12 @@ static SlabLayout slab_layout(size_t n, size_t Cmax, size_t n_card) {
     L.card[b] = take(n * n_card * sizeof(float));
   }
   L.anc_in = take(n * sizeof(int));
+  L.mbox = take((size_t)MBOX_SLOTS * PHD_MAX_PEERS * MBOX_WORDS * sizeof(unsigned long long));
   L.bytes = std::max(o, (size_t)4 << 20);      /* >= 4 MB: an allocation of its own, never a sub-allocation */
   return L;
 }
+
+static inline int rank_offset_of(long long n_global, int world, int r) { return (int)(n_global * r / world); }
 
 static void close_peers(phdslam* h) {
   if (h->peer_base) {
@@ -231,6 +234,11 @@ static void free_state(phdslam* h) {
   }
   cudaFree(h->barrier_dev);
   h->barrier_dev = nullptr;
+  cudaFree(h->gath_dev);
+  h->gath_dev = nullptr;
+  if (h->gath_host) cudaFreeHost(h->gath_host);
+  h->gath_host = nullptr;
+  h->mbox = 0; h->mbox_base = nullptr; h->totals_valid = 0;
   for (int b = 0; b < 2; ++b) {
     cudaFree(h->pose[b]); cudaFree(h->count[b]); cudaFree(h->map[b]); cudaFree(h->card[b]);
   }
@@ -273,6 +281,11 @@ static int alloc_state(phdslam* h) {
       h->card[b] = h->n_card ? reinterpret_cast<float*>(h->peer_slab + L.card[b]) : nullptr;
     }
     h->anc_in = reinterpret_cast<int*>(h->peer_slab + L.anc_in);
+    h->mbox_base = reinterpret_cast<unsigned long long*>(h->peer_slab + L.mbox);
+    CK(cudaMemset(h->mbox_base, 0, (size_t)MBOX_SLOTS * PHD_MAX_PEERS * MBOX_WORDS * sizeof(unsigned long long)));
+    h->mbox_seq = 1;
+    CK(cudaMalloc(&h->gath_dev, (size_t)PHD_MAX_PEERS * MBOX_WORDS * sizeof(unsigned long long)));
+    CK(cudaMallocHost(&h->gath_host, (size_t)PHD_MAX_PEERS * MBOX_WORDS * sizeof(unsigned long long)));
     h->slab_sw = 0;
     CK(cudaMalloc(&h->barrier_dev, 2 * sizeof(int)));
     CK(cudaMemset(h->barrier_dev, 0, 2 * sizeof(int)));
@@ -387,7 +400,7 @@ static int create_impl(phdslam* h, const phdslam_config_t* cfg, int device) {
   CK(cudaFuncSetAttribute(update_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(h->Cmax)));
   CK(cudaFuncSetAttribute(update_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(h->Cmax)));
   if (h->n_card) {
-    const size_t sm = update_smem_bytes(h->Cmax) + cphd_smem_bytes(h->n_card, PHD_MAX_MEAS);
+    const size_t sm = update_smem_bytes(h->Cmax) + cphd_smem_bytes(h->n_card, PHD_MAX_MEAS) + cphd_chunkmax_bytes(PHD_MAX_MEAS, h->Cmax);
     if (sm > 227 * 1024) {
       phdslam_set_error("CPHD: max_components / max_cardinality need more than 227 KB of shared memory per particle");
       return PHDSLAM_ERR_INVALID;
@@ -504,6 +517,27 @@ static int map_peer_windows(phdslam* h) {
   cudaFree(hbuf);
   if (!ok) close_peers(h);
   h->p2p = ok;
+  {
+    const char* e = getenv("PHDSLAM_MBOX");       /* 0: keep the NCCL collectives for the statistics (A/B, fallback) */
+    h->mbox = (ok && W <= PHD_MAX_PEERS && !(e && atoi(e) == 0)) ? 1 : 0;
+  }
+  return 0;
+}
+
+/* One mailbox exchange on the handle's stream: words_dev[0..n_words) of every rank combined in place (bit t of max_mask:
+ * word t by max, otherwise by sum); with want_gathered the W raw records land in gath_dev.  See mbox_exchange_kernel. */
+static int mbox_exchange(phdslam* h, unsigned long long* words_dev, int n_words, unsigned max_mask, bool want_gathered) {
+  MboxPeers pp;
+  for (int r = 0; r < PHD_MAX_PEERS; ++r) pp.box[r] = nullptr;
+  for (int r = 0; r < h->world; ++r) {
+    const size_t nr = (size_t)(rank_offset_of(h->n_global, h->world, r + 1) - rank_offset_of(h->n_global, h->world, r));
+    const SlabLayout L = slab_layout(nr, (size_t)h->Cmax, (size_t)h->n_card);
+    pp.box[r] = reinterpret_cast<unsigned long long*>(h->peer_base[r] + L.mbox);
+  }
+  mbox_exchange_kernel<<<1, 32 * h->world, 0, h->stream>>>(pp, h->rank, h->world, h->mbox_seq, words_dev, n_words, max_mask,
+                                                          want_gathered ? h->gath_dev : nullptr, &h->red->err_flag);
+  LAUNCH_CHECK(h);
+  h->mbox_seq++;
   return 0;
 }
 
@@ -567,6 +601,10 @@ static int scan_u64(phdslam* h, const unsigned long long* in, int n, unsigned lo
 
 static int check_err_flag(phdslam* h) {
   /* red_host was filled by a preceding async copy + sync */
+  if (h->red_host->err_flag & 4) {
+    phdslam_set_error("peer exchange timed out: another rank did not reach the same step");
+    return PHDSLAM_ERR_NCCL;
+  }
   if (h->red_host->err_flag & 1) {
     phdslam_set_error("merge candidate buffer overflow: raise max_components (candidates after prune exceeded 2*max_components+256)");
     return PHDSLAM_ERR_CAPACITY;
@@ -726,7 +764,8 @@ static int launch_update_batch(phdslam* h, int M, int p0, int p1, unsigned long 
   a.toff = h->toff; a.tbase = tbase; a.dense = h->dense; a.n_in = h->n_in; a.dlogw = h->dlogw; a.c = h->dc;
   a.cand = h->cand_in + (size_t)(p0 - cand_p0) * h->Smax * 2; a.n_cand = h->n_cand; a.Smax = h->Smax;
   if (h->n_card) {
-    const size_t sm = update_smem_bytes(h->Cmax) + cphd_smem_bytes(h->n_card, M);
+    /* the fused mode keeps one chunk maximum per (measurement, 64-component chunk) behind the multi-object tables */
+    const size_t sm = update_smem_bytes(h->Cmax) + cphd_smem_bytes(h->n_card, M) + (dense ? 0 : cphd_chunkmax_bytes(M, h->Cmax));
     if (dense)
       update_kernel<true, true><<<p1 - p0, UPD_THREADS, sm, h->stream>>>(a);
     else
@@ -773,11 +812,17 @@ static int update_weights(phdslam* h, bool add) {
   CK(cudaMemsetAsync(h->red, 0, offsetof(Reductions, err_ranks) + sizeof(unsigned long long), h->stream));
   weights_add_max_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->logw, add ? h->dlogw : nullptr, n, h->red);
   LAUNCH_CHECK(h);
-  if (h->world > 1) /* global max of the log-weights (ordered-uint keys: max is exact and order independent) */
+  if (h->mbox) { /* {max_key, pad0 = 0} as one 64-bit word, combined by max */
+    int rc = mbox_exchange(h, reinterpret_cast<unsigned long long*>(&h->red->max_key), 1, 1u, false);
+    if (rc) return rc;
+  } else if (h->world > 1) /* global max of the log-weights (ordered-uint keys: max is exact and order independent) */
     CKN(ncclAllReduce(&h->red->max_key, &h->red->max_key, 1, ncclUint32, ncclMax, (ncclComm_t)h->nccl_comm, h->stream));
   weights_sum_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->logw, n, h->red);
   LAUNCH_CHECK(h);
-  if (h->world > 1) /* integer (Q36) sum: identical on every rank for any GPU count; NaN and error counts ride along */
+  if (h->mbox) {
+    int rc = mbox_exchange(h, &h->red->sum_fx, 3, 0u, false);
+    if (rc) return rc;
+  } else if (h->world > 1) /* integer (Q36) sum: identical on every rank for any GPU count; NaN and error counts ride along */
     CKN(ncclAllReduce(&h->red->sum_fx, &h->red->sum_fx, 3, ncclUint64, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
   weights_normalise_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->logw, n, h->red);
   LAUNCH_CHECK(h);
@@ -787,6 +832,7 @@ static int update_weights(phdslam* h, bool add) {
 extern "C" int phdslam_update(phdslam_t* h, const float* z, int M, int fields) {
   CK(cudaSetDevice(h->device));
   if (M <= 0) return 0;                 /* main.cpp:1258 */
+  h->totals_valid = 0;
   if (fields != 2 && fields != 3) return PHDSLAM_ERR_INVALID;
   if (M > PHD_MAX_MEAS) M = PHD_MAX_MEAS; /* :3390-3394 */
   int rc = upload_measurements(h, z, M, fields);
@@ -955,7 +1001,15 @@ extern "C" int phdslam_estimate(phdslam_t* h, phdslam_estimate_t* out) {
   CK(cudaMemsetAsync(h->red, 0, sizeof(Reductions), h->stream));
   estimate_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->logw, h->pose[h->cur], n, h->offset, h->red);
   LAUNCH_CHECK(h);
-  if (h->world > 1) {
+  h->totals_valid = 0;
+  if (h->mbox) {
+    /* neff_fx, pose_fx[6], argmax_key, cdf_total are nine adjacent 64-bit integers: ONE exchange (sums, the arg-max key by
+     * max); the raw records also tell every rank every rank's resampling CDF total, so a resampling that follows needs
+     * no exchange of its own before it can plan the migration */
+    int rc = mbox_exchange(h, &h->red->neff_fx, 9, 1u << 7, true);
+    if (rc) return rc;
+    CK(copy_d2h_async(h, h->gath_host, h->gath_dev, (size_t)h->world * MBOX_WORDS * sizeof(unsigned long long), h->stream));
+  } else if (h->world > 1) {
     /* neff_fx and pose_fx[6] are adjacent 64-bit integers: one exact integer all-reduce; arg-max key by max */
     CKN(ncclAllReduce(&h->red->neff_fx, &h->red->neff_fx, 7, ncclUint64, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
     CKN(ncclAllReduce(&h->red->argmax_key, &h->red->argmax_key, 1, ncclUint64, ncclMax, (ncclComm_t)h->nccl_comm, h->stream));
@@ -964,6 +1018,14 @@ extern "C" int phdslam_estimate(phdslam_t* h, phdslam_estimate_t* out) {
   CK(cudaEventRecord(h->ev[8], h->stream));
   CK(cudaStreamSynchronize(h->stream));
   cudaEventElapsedTime(&h->tim.estimate_ms, h->ev[7], h->ev[8]);
+  if (h->red_host->err_flag & 4) {
+    phdslam_set_error("peer exchange timed out: another rank did not reach the estimate");
+    return PHDSLAM_ERR_NCCL;
+  }
+  if (h->mbox) {
+    for (int r = 0; r < h->world; ++r) h->totals_host[r] = h->gath_host[(size_t)r * MBOX_WORDS + 8];
+    h->totals_valid = 1;
+  }
   const Reductions& r = *h->red_host;
   const double inv = 1.0 / (double)(1ull << PHD_FX_POSE_BITS);
   float* e = &out->expected_pose.px;
@@ -1034,13 +1096,26 @@ extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms,
   unsigned long long total = 0, base = 0;
   std::vector<int> bounds;
   if (h->world > 1) {
-    /* every rank learns every rank's integer weight total: its CDF offset and the global total follow */
+    /* every rank learns every rank's integer weight total: its CDF offset and the global total follow.  After an
+     * estimate on the same weights the totals are already on the host (they rode on the estimate's exchange). */
     rc = ensure_migration(h, 1);
     if (rc) return rc;
-    CKN(ncclAllGather(&h->red->cdf_total, h->totals_dev, 1, ncclUint64, (ncclComm_t)h->nccl_comm, h->stream));
     std::vector<unsigned long long> totals(h->world);
-    CK(copy_d2h_async(h, totals.data(), h->totals_dev, (size_t)h->world * sizeof(unsigned long long), h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    if (h->mbox && h->totals_valid) {
+      for (int r = 0; r < h->world; ++r) totals[r] = h->totals_host[r];
+    } else {
+      if (h->mbox) {
+        rc = mbox_exchange(h, &h->red->cdf_total, 1, 0u, true);
+        if (rc) return rc;
+        CK(copy_d2h_async(h, h->gath_host, h->gath_dev, (size_t)h->world * MBOX_WORDS * sizeof(unsigned long long), h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (int r = 0; r < h->world; ++r) totals[r] = h->gath_host[(size_t)r * MBOX_WORDS];
+      } else {
+        CKN(ncclAllGather(&h->red->cdf_total, h->totals_dev, 1, ncclUint64, (ncclComm_t)h->nccl_comm, h->stream));
+        CK(copy_d2h_async(h, totals.data(), h->totals_dev, (size_t)h->world * sizeof(unsigned long long), h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+      }
+    }
     for (int r = 0; r < h->world; ++r) {
       if (r < h->rank) base += totals[r];
       total += totals[r];
@@ -1078,6 +1153,9 @@ extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms,
      * d's back buffer through the mapped peer window.  d's back buffer is free: the all-gather above completed, so d
      * has finished its merge.  The all-reduce at the end is the barrier that makes every push visible to its owner. */
     const int me = h->rank, W = h->world;
+    PushArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    int n_e = 0, tot = 0;
     for (int k = 1; k < W; ++k) {
       const int d = (me + k) % W, sr = (me - k + W) % W;
       const int off_d = rank_offset(h, d), end_d = rank_offset(h, d + 1);
@@ -1086,27 +1164,32 @@ extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms,
       const int in_lo = std::max(bounds[sr], h->offset), in_hi = std::min(bounds[sr + 1], h->offset + n);
       h->tim.migrated_in += (unsigned long long)std::max(in_hi - in_lo, 0);
       if (cnt_out <= 0) continue;
-      if (h->mig_anc_cap < (size_t)cnt_out) {
-        cudaFree(h->mig_anc2);
-        h->mig_anc2 = nullptr;
-        CK(cudaMalloc(&h->mig_anc2, (size_t)cnt_out * sizeof(int)));
-        h->mig_anc_cap = (size_t)cnt_out;
-      }
-      resample_search_kernel<<<cdiv(cnt_out, 256), 256, 0, h->stream>>>(h->cdf_excl, n, base, total, n_new, out_lo, cnt_out, h->offset,
-                                                                      udev, sysmode, h->resample_calls, h->dc.seed_lo,
-                                                                      h->dc.seed_hi, h->mig_anc2);
-      LAUNCH_CHECK(h);
       const size_t nd = (size_t)(end_d - off_d);
       const SlabLayout L = slab_layout(nd, (size_t)h->Cmax, (size_t)h->n_card);
       unsigned char* pb = h->peer_base[d];
-      resample_gather_kernel<<<cdiv(cnt_out, 8), 256, 0, h->stream>>>(
-          h->mig_anc2, cnt_out, h->offset, n, (int)nd, h->pose[b], reinterpret_cast<float*>(pb + L.pose[b ^ 1 ^ h->slab_sw]), h->count[b],
-          reinterpret_cast<int*>(pb + L.count[b ^ 1]), h->map[b], reinterpret_cast<float*>(pb + L.map[b ^ 1]), h->card[b],
-          h->n_card ? reinterpret_cast<float*>(pb + L.card[b ^ 1 ^ h->slab_sw]) : nullptr, h->Cmax, h->n_card, out_lo - off_d,
-          reinterpret_cast<int*>(pb + L.anc_in));
+      PushDst& D = pa.d[n_e++];
+      D.pose = reinterpret_cast<float*>(pb + L.pose[b ^ 1 ^ h->slab_sw]);
+      D.count = reinterpret_cast<int*>(pb + L.count[b ^ 1]);
+      D.map = reinterpret_cast<float*>(pb + L.map[b ^ 1]);
+      D.card = h->n_card ? reinterpret_cast<float*>(pb + L.card[b ^ 1 ^ h->slab_sw]) : nullptr;
+      D.anc_in = reinterpret_cast<int*>(pb + L.anc_in);
+      D.n_dst = (int)nd; D.dst_first = out_lo - off_d; D.j0 = out_lo; D.first = tot;
+      tot += cnt_out;
+    }
+    if (tot > 0) {          /* every peer's interval in ONE launch: ancestor search + push over NVLink */
+      pa.n_dst_entries = n_e; pa.total = tot;
+      pa.excl = h->cdf_excl; pa.n = n; pa.cdf_base = base; pa.cdf_total = total; pa.n_new = n_new; pa.anc_offset = h->offset;
+      pa.uniforms = udev; pa.systematic = sysmode; pa.call = h->resample_calls; pa.seed_lo = h->dc.seed_lo; pa.seed_hi = h->dc.seed_hi;
+      pa.pose_in = h->pose[b]; pa.count_in = h->count[b]; pa.map_in = h->map[b]; pa.card_in = h->card[b];
+      pa.Cmax = h->Cmax; pa.n_card = h->n_card;
+      resample_push_kernel<<<cdiv(tot, 8), 256, 0, h->stream>>>(pa);
       LAUNCH_CHECK(h);
     }
-    CKN(ncclAllReduce(h->barrier_dev, h->barrier_dev + 1, 1, ncclInt32, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
+    if (h->mbox) {          /* "all pushes have landed": every rank's pushes precede its record (stream order + system fence) */
+      rc = mbox_exchange(h, nullptr, 0, 0u, false);
+      if (rc) return rc;
+    } else
+      CKN(ncclAllReduce(h->barrier_dev, h->barrier_dev + 1, 1, ncclInt32, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
     resample_take_pushed_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->ancestors, h->anc_in, n);
     LAUNCH_CHECK(h);
   } else if (h->world > 1) {
@@ -1166,10 +1249,16 @@ extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms,
   CK(cudaMemcpyAsync(h->resample_idx, h->ancestors, (size_t)n_off * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaEventRecord(h->ev[10], h->stream));
   if (ancestors_out) CK(copy_d2h_async(h, ancestors_out, h->ancestors, (size_t)n_off * sizeof(int), h->stream));
+  if (h->mbox) CK(copy_d2h_async(h, &h->red_host->err_flag, &h->red->err_flag, sizeof(int), h->stream));
   CK(cudaStreamSynchronize(h->stream));
   cudaEventElapsedTime(&h->tim.resample_ms, h->ev[9], h->ev[10]);
   h->cur ^= 1;
   h->resample_calls++;
+  h->totals_valid = 0;
+  if (h->mbox && (h->red_host->err_flag & 4)) {
+    phdslam_set_error("peer exchange timed out: another rank did not reach the resampling");
+    return PHDSLAM_ERR_NCCL;
+  }
   if (h->world == 1) h->n_local = h->n_global = n_new;
   return 0;
 }
@@ -1276,6 +1365,7 @@ extern "C" int phdslam_get_log_weights(phdslam_t* h, float* out) {
 }
 extern "C" int phdslam_set_log_weights(phdslam_t* h, const float* in) {
   CK(cudaSetDevice(h->device));
+  h->totals_valid = 0;
   CK(cudaStreamSynchronize(h->stream));
   CK(copy_h2d(h, h->logw, in, (size_t)h->n_local * sizeof(float)));
   return 0;
@@ -1498,6 +1588,7 @@ extern "C" int phdslam_snapshot(phdslam_t* h) {
 extern "C" int phdslam_restore(phdslam_t* h) {
   CK(cudaSetDevice(h->device));
   if (!h->snap_pose) return PHDSLAM_ERR_INVALID;
+  h->totals_valid = 0;
   if (h->world == 1) h->n_local = h->n_global = h->snap_n;
   const size_t n = h->n_local, C = h->Cmax;
   CK(cudaMemcpyAsync(h->pose[h->cur], h->snap_pose, 6 * n * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));

@@ -117,6 +117,15 @@ struct phdslam {
   int slab_sw;                    /* pose[i] and card[i] live in window slot i ^ slab_sw (the update swaps the pointers) */
   unsigned char** peer_base;      /* [world] mapped slab of every rank (own slab at [rank]) */
   int* barrier_dev;               /* 2 ints: end-of-exchange all-reduce */
+  /* mailbox exchange through the peer window (kernels.cuh: mbox_exchange_kernel): replaces the tiny NCCL collectives of the
+   * weight statistics, the estimate and the resampling barrier when the window is mapped */
+  int mbox;                       /* 1: use it (p2p && PHDSLAM_MBOX != 0) */
+  unsigned long long* mbox_base;  /* this rank's mailbox region inside the slab */
+  unsigned long long mbox_seq;    /* sequence number of the next exchange (same on every rank) */
+  unsigned long long* gath_dev;   /* [world][16] records of the last gathering exchange */
+  unsigned long long* gath_host;  /* pinned copy */
+  int totals_valid;               /* totals_host = every rank's resampling CDF total for the CURRENT weights (set by estimate) */
+  unsigned long long totals_host[8];
   int* mig_anc2; size_t mig_anc_cap; /* ancestors of the offspring interval being pushed */
   float* lfact;                   /* log-factorial table for the CPHD terms (PHD_LF_MAX floats) */
 };

@@ -129,14 +129,18 @@ static void sync_to_device(SynthSLAM& p) {
 
 /* device -> host: what run_synth reads between calls (weights for nEff and the log, poses for the log, maps for
  * recoverSlamState / writeParticlesMat, cardinalities for the CPHD estimate) */
-static void pull(SynthSLAM& p) {
+static void pull(SynthSLAM& p, bool take_resample_idx = false) {
   const int n = phdslam_n_local(g_h);
+  /* resample_idx belongs to the host loop (resampleParticles sets it, the non-resampling branch resets it, src/main.cpp:
+   * 1286-1297; phdPredict and phdUpdateSynth never touch it): the device's copy is taken only after a device resampling
+   * or when the particle count changed (shotgun prediction: every copy inherits its parent's index, :1185-1238) */
+  take_resample_idx = take_resample_idx || (int)p.resample_idx.size() != n;
   p.states.resize(n); p.weights.resize(n); p.maps_static.resize(n); p.resample_idx.resize(n);
   p.maps_dynamic.resize(n); p.cardinalities.resize(n); p.variances.resize(n);
   p.n_particles = n;
   check(phdslam_get_poses(g_h, (phdslam_pose_t*)&p.states[0]), "phdslam_get_poses");
   check(phdslam_get_log_weights(g_h, &p.weights[0]), "phdslam_get_log_weights");
-  check(phdslam_get_resample_idx(g_h, &p.resample_idx[0]), "phdslam_get_resample_idx");
+  if (take_resample_idx) check(phdslam_get_resample_idx(g_h, &p.resample_idx[0]), "phdslam_get_resample_idx");
   std::vector<int> sizes(n);
   check(phdslam_get_map_sizes(g_h, sizes.data()), "phdslam_get_map_sizes");
   size_t total = 0;
@@ -223,5 +227,5 @@ void recoverSlamStateDevice(SynthSLAM& particles, ConstantVelocityState& expecte
 void resampleParticlesDevice(SynthSLAM& particles, int n_new) {
   sync_to_device(particles);
   check(phdslam_resample(g_h, n_new, nullptr, nullptr), "phdslam_resample");
-  pull(particles);
+  pull(particles, true);
 }

@@ -323,11 +323,11 @@ def test_cli_logs_match_oracle(tmp_path):
     cmd = [exe, os.path.join(GOLDEN, "config_ackerman.cfg"), "synth", "--measurements",
            os.path.join(DATA, "measurements_synth_ackerman.txt"), "--controls", os.path.join(DATA, "controls_synth.txt"),
            "--out", str(out), "--steps", str(n_steps), "--set", "n_particles=64", "--set", "map_estimate=1", "--set", "seed=21",
-           "--quiet"]
+           "--set", "resample_threshold=0.85", "--quiet"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     cfg = P.load_config(os.path.join(GOLDEN, "config_ackerman.cfg"))
-    cfg.set(n_particles=64, map_estimate=1, seed="21")
+    cfg.set(n_particles=64, map_estimate=1, seed="21", resample_threshold=0.85)
     Z = P.load_measurements(os.path.join(DATA, "measurements_synth_ackerman.txt"))
     U = P.load_controls(os.path.join(DATA, "controls_synth.txt"))
     o = O.Oracle(cfg)
