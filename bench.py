@@ -47,7 +47,16 @@ WORKLOADS = {
     # BASELINE.json configs[4] per-GPU shape at a size one GPU's update buffer streams through: global resampling every step
     "synthetic_32768x128x100_phd": dict(P=32768, C=128, M=100, max_components=256, resample_threshold=1.0),
     "synthetic_262144x128x100_phd": dict(P=262144, C=128, M=100, max_components=256, resample_threshold=1.0),
+    # BASELINE.json configs[4] at its literal size: 16 777 216 particles IN TOTAL, split over the GPUs (strong scaling), global
+    # resampling every step.  A rank generates 262 144 distinct particles and tiles them on the device (import_tiled).
+    # Memory per GPU at max_components = 160: maps 2 x 3.84 KB + snapshot 3.84 KB per particle, 32 GB dense buffer, 16 GB
+    # candidate buffers: 146 GB at N = 2 (8.4 M particles per GPU); N = 1 would need 244 GB and does not fit 180 GB.
+    "synthetic_16777216x128x100_phd": dict(P=16777216, C=128, M=100, max_components=160, resample_threshold=1.0, strong=1,
+                                           scene_particles=262144),
+    "synthetic_2097152x128x100_phd": dict(P=2097152, C=128, M=100, max_components=160, resample_threshold=1.0, strong=1,
+                                          scene_particles=65536),     # the same path at a size for quick checks
 }
+NON_CFG_KEYS = ("P", "C", "M", "max_components", "strong", "scene_particles")
 DEFAULT_WORKLOAD = "synthetic_65536x256x64_phd"
 
 
@@ -213,7 +222,7 @@ def cpu_oracle_rate(wl, target_seconds=12.0, threads=None):
     Ps = max(threads, 8)
     rate = None
     for attempt in range(3):
-        extra = {k: v for k, v in wl.items() if k not in ("P", "C", "M", "max_components")}
+        extra = {k: v for k, v in wl.items() if k not in NON_CFG_KEYS}
         cfg = S.scene_config_py(Ps, C, M, max_components=wl["max_components"], **extra)
         sc = S.make_scene(Ps, C, M, seed=0)
         o = O.Oracle(cfg, threads=threads)
@@ -250,7 +259,7 @@ def run_reference(args, wl):
     r1 = cpu_oracle_single_thread_rate(wl, seconds=3.0)
     budget = 140.0 / max(args.steps + args.warmup, 1)
     Ps = int(max(threads, min(wl["P"], r0 * min(budget, 20.0) / (C * M))))
-    extra = {k: v for k, v in wl.items() if k not in ("P", "C", "M", "max_components")}
+    extra = {k: v for k, v in wl.items() if k not in NON_CFG_KEYS}
     cfg = S.scene_config_py(Ps, C, M, max_components=wl["max_components"], **extra)
     sc = S.make_scene(Ps, C, M, seed=0)
     times = []
@@ -372,17 +381,27 @@ def run_ours(args, wl):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     P, C, M = wl["P"], wl["C"], wl["M"]
-    P_total = P * world                      # weak scaling: P particles per GPU
-    extra = {k: v for k, v in wl.items() if k not in ("P", "C", "M", "max_components")}
+    strong = bool(wl.get("strong"))
+    if strong:                               # strong scaling: wl["P"] particles in total
+        if wl["P"] % world:
+            raise SystemExit("the particle count of a strong-scaling workload must be a multiple of --gpus")
+        P_total, P = wl["P"], wl["P"] // world
+    else:
+        P_total = P * world                  # weak scaling: P particles per GPU
+    extra = {k: v for k, v in wl.items() if k not in NON_CFG_KEYS}
     cfg = S.scene_config(P_total, C, M, max_components=wl["max_components"], seed="0", **extra)
     filt = PS.PhdSlam(cfg, device=local)
     if world > 1:
         filt.dist_init(rank, world)
     assert filt.n_local == P
     # every rank holds P particles of the same landmark scene (same measurements Z), with its own pose / map jitter
-    sc = S.make_scene(P, C, M, seed=0, particle_seed=rank)
+    n_scene = min(P, int(wl.get("scene_particles", P)))
+    sc = S.make_scene(n_scene, C, M, seed=0, particle_seed=rank)
     sc["log_weights"][:] = -np.log(np.float32(P_total))
-    S.load_scene(filt, sc)
+    if n_scene < P:
+        filt.import_tiled(sc)                # n_scene distinct particles, repeated on the device
+    else:
+        S.load_scene(filt, sc)
     filt.snapshot()
     Z = sc["Z"]
     u = np.float32([1.0, 0.05])
@@ -509,9 +528,11 @@ def run_ours(args, wl):
     oth = np.mean(np.array(other), axis=0)
     line = {
         "metric": "GM-PHD updates/s (particle x comp x meas)", "value": value, "unit": "updates/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "particles_per_gpu": P, "components": C, "measurements": M,
+        "config": {"workload": args.workload, "particles_per_gpu": P, "particles_total": P_total,
+                   "distinct_particles_per_gpu": n_scene, "components": C, "measurements": M,
                    "filter": "CPHD" if wl.get("filter_type") == 1 else "PHD", "update_mode": "dense (reference-equivalent update terms materialised in HBM)",
                    "cache": "inputs larger than L2 (map %.0f MB + dense update terms %.1f GB per step)"
                             % (P * C * 24 / 1e6, P * (C * (M + 1) + M) * 28 / 1e9),

@@ -1835,18 +1835,11 @@ __device__ __forceinline__ void block_radix_pass(const unsigned* keys, const uns
   const int per = (((n + MF_WARPS - 1) / MF_WARPS) + 31) & ~31;
   const int lo = min(warp * per, n), hi = min(lo + per, n);
   unsigned short* hw = hist + warp * 256;
-  for (int b0 = lo; b0 < hi; b0 += 32) {
-    /* the high bytes of the weight keys take a handful of values: one add per distinct digit of the round, not 32 adds on
-     * one counter (no atomics needed either: the histogram row belongs to this warp) */
-    const int i = b0 + lane;
-    unsigned d = 0x80000000u | (unsigned)lane;
-    if (i < hi) {
-      const unsigned idx = in[i];
-      d = TIE ? (__brev(idx) >> 24) : ((keys[idx] >> shift) & 255u);
-    }
-    const unsigned same = __match_any_sync(FULL_MASK, d);
-    if (i < hi && (same & lt_mask) == 0) hw[d] = (unsigned short)(hw[d] + __popc(same));
-    __syncwarp();
+  for (int i = lo + lane; i < hi; i += 32) {
+    const unsigned idx = in[i];
+    const unsigned d = TIE ? (__brev(idx) >> 24) : ((keys[idx] >> shift) & 255u);
+    atomic_add_u16(hw, (int)d, 1u);        /* result unused: a fire-and-forget shared-memory reduction (measured: aggregating
+                                              equal digits with match_any first is slower -- a dependent load/store chain) */
   }
   __syncthreads();
   if (warp == 0) {
@@ -2404,8 +2397,13 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
     for (int k = tid; k < klimit; k += MF_THREADS) {
       const int beg = (k > 0) ? csz[k - 1] : 0, end = csz[k];
       float wsum = 0.0f, m0 = 0.0f, m1 = 0.0f;
+      /* most clusters have one or two members: their records are requested together (one L2 round trip instead of one per
+       * member); the accumulation order is unchanged */
+      const int ra = (beg < end) ? memb[beg] : 0, rb = (beg + 1 < end) ? memb[beg + 1] : ra;
+      const float4 Pa1 = crec[2 * ra + 1], Pb1 = crec[2 * rb + 1];
+      const float4 Pa0 = crec[2 * ra], Pb0 = crec[2 * rb];
       for (int j = beg; j < end; ++j) {
-        const float4 B1 = crec[2 * memb[j] + 1];
+        const float4 B1 = (j == beg) ? Pa1 : (j == beg + 1) ? Pb1 : crec[2 * memb[j] + 1];
         wsum = wsum + B1.z;
         m0 = m0 + B1.z * B1.x;
         m1 = m1 + B1.z * B1.y;
@@ -2418,7 +2416,8 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
         float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
         for (int j = beg; j < end; ++j) {
           const int rr = memb[j];
-          const float4 B0 = crec[2 * rr], B1 = crec[2 * rr + 1];
+          const float4 B0 = (j == beg) ? Pa0 : (j == beg + 1) ? Pb0 : crec[2 * rr];
+          const float4 B1 = (j == beg) ? Pa1 : (j == beg + 1) ? Pb1 : crec[2 * rr + 1];
           const float d0 = mm0 - B1.x, d1 = mm1 - B1.y;
           v0 = v0 + B1.z * (B0.x + d0 * d0);
           v1 = v1 + B1.z * (B0.y + d0 * d1);
@@ -2811,6 +2810,13 @@ __global__ void particle_checksum_kernel(const float* __restrict__ pose, const i
   if (lane == 0) out[p] = acc;
 }
 
+/* ancestors[j] = j mod n_src; log-weights follow their source */
+__global__ void tile_index_kernel(int* __restrict__ anc, int n, int n_src, float* logw) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  anc[j] = j % n_src;
+  if (j >= n_src) logw[j] = logw[j % n_src];
+}
 __global__ void fill_kernel(float* p, int n, float v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;

@@ -1404,9 +1404,13 @@ extern "C" int phdslam_get_maps(phdslam_t* h, phdslam_gaussian2d_t* out, size_t 
   }
   return 0;
 }
+static int set_maps_prefix(phdslam_t* h, int n, const int* sizes, const phdslam_gaussian2d_t* in);
 extern "C" int phdslam_set_maps(phdslam_t* h, const int* sizes, const phdslam_gaussian2d_t* in) {
+  return set_maps_prefix(h, h->n_local, sizes, in);
+}
+/* maps of the first n local particles */
+static int set_maps_prefix(phdslam_t* h, int n, const int* sizes, const phdslam_gaussian2d_t* in) {
   CK(cudaSetDevice(h->device));
-  const int n = h->n_local;
   const size_t C = h->Cmax;
   for (int p = 0; p < n; ++p)
     if (sizes[p] > h->Cmax || sizes[p] < 0) {
@@ -1451,6 +1455,37 @@ extern "C" int phdslam_set_cardinalities(phdslam_t* h, const float* in) {
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
   CK(copy_h2d(h, h->card[h->cur], in, (size_t)h->n_local * h->n_card * sizeof(float)));
+  return 0;
+}
+
+/* Imports n_src particles and fills the local particles [n_src, n_local) with copies of them (cyclically), on the device:
+ * lets a benchmark build a 16 M-particle scene from one it can afford to generate and upload. */
+extern "C" int phdslam_import_tiled(phdslam_t* h, int n_src, const phdslam_pose_t* poses, const float* logw, const int* sizes,
+                                    const phdslam_gaussian2d_t* maps) {
+  CK(cudaSetDevice(h->device));
+  const int n = h->n_local;
+  if (n_src < 1 || n_src > n) return PHDSLAM_ERR_INVALID;
+  CK(cudaStreamSynchronize(h->stream));
+  const int b = h->cur;
+  std::vector<float> plane(n_src);
+  for (int k = 0; k < 6; ++k) {
+    for (int i = 0; i < n_src; ++i) plane[i] = (&poses[i].px)[k];
+    CK(copy_h2d(h, h->pose[b] + (size_t)k * n, plane.data(), (size_t)n_src * sizeof(float)));
+  }
+  CK(copy_h2d(h, h->logw, logw, (size_t)n_src * sizeof(float)));
+  int rc = set_maps_prefix(h, n_src, sizes, maps);
+  if (rc) return rc;
+  h->totals_valid = 0;
+  if (n_src == n) return 0;
+  /* exactly what a resampling with ancestors j mod n_src does: gather into the back buffers, then flip */
+  tile_index_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->ancestors, n, n_src, h->logw);
+  LAUNCH_CHECK(h);
+  resample_gather_kernel<<<cdiv(n, 8), 256, 0, h->stream>>>(h->ancestors, n, 0, n, n, h->pose[b], h->pose[b ^ 1], h->count[b],
+                                                          h->count[b ^ 1], h->map[b], h->map[b ^ 1], h->card[b], h->card[b ^ 1],
+                                                          h->Cmax, h->n_card, 0, nullptr);
+  LAUNCH_CHECK(h);
+  CK(cudaStreamSynchronize(h->stream));
+  h->cur ^= 1;
   return 0;
 }
 

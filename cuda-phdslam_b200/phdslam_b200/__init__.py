@@ -91,7 +91,7 @@ ABI_SYMBOLS = [
     "phdslam_create", "phdslam_destroy", "phdslam_set_config", "phdslam_get_config", "phdslam_dist_unique_id",
     "phdslam_dist_init", "phdslam_plan_migration", "phdslam_resample_threshold", "phdslam_predict", "phdslam_update", "phdslam_estimate", "phdslam_map_estimate",
     "phdslam_resample", "phdslam_step", "phdslam_step_filter", "phdslam_step_resample", "phdslam_set_particle_count",
-    "phdslam_particle_capacity", "phdslam_particle_checksums", "phdslam_n_local", "phdslam_local_offset", "phdslam_get_poses",
+    "phdslam_particle_capacity", "phdslam_particle_checksums", "phdslam_import_tiled", "phdslam_n_local", "phdslam_local_offset", "phdslam_get_poses",
     "phdslam_set_poses", "phdslam_get_log_weights", "phdslam_set_log_weights", "phdslam_get_map_sizes",
     "phdslam_get_maps", "phdslam_set_maps", "phdslam_get_resample_idx", "phdslam_get_cardinalities",
     "phdslam_set_cardinalities", "phdslam_update_terms", "phdslam_get_timings", "phdslam_stream",
@@ -135,6 +135,7 @@ def load_library(path=None):
     lib.phdslam_set_particle_count.argtypes = [C.c_void_p, C.c_int]
     lib.phdslam_particle_capacity.argtypes = [C.c_void_p]
     lib.phdslam_particle_checksums.argtypes = [C.c_void_p, C.c_void_p]
+    lib.phdslam_import_tiled.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     for name in ("phdslam_n_local", "phdslam_local_offset", "phdslam_synchronize", "phdslam_set_overlap", "phdslam_snapshot", "phdslam_restore"):
         getattr(lib, name).argtypes = [C.c_void_p]
     for name in ("phdslam_get_poses", "phdslam_set_poses", "phdslam_get_log_weights", "phdslam_set_log_weights",
@@ -374,6 +375,15 @@ class PhdSlam(object):
         out = np.zeros(self.n_local, dtype=np.uint64)
         _check(self.lib.phdslam_particle_checksums(self._h, out.ctypes.data))
         return out
+
+    def import_tiled(self, sc):
+        """loads the particles of scene `sc` and fills the rest of the local particles with copies of them (on the device)"""
+        p = np.ascontiguousarray(sc["poses"], dtype=POSE_DTYPE)
+        w = np.ascontiguousarray(sc["log_weights"], dtype=np.float32)
+        sizes = np.ascontiguousarray(sc["sizes"], dtype=np.int32)
+        maps = np.ascontiguousarray(sc["maps"], dtype=GAUSSIAN_DTYPE)
+        assert len(p) == len(w) == len(sizes) <= self.n_local and int(sizes.sum()) == len(maps)
+        _check(self.lib.phdslam_import_tiled(self._h, len(p), p.ctypes.data, w.ctypes.data, sizes.ctypes.data, maps.ctypes.data))
 
     def step_filter(self, step_index, control, Z):
         """predict + update + estimate: the state run_synth looks at (and logs) is the one after this half"""

@@ -238,6 +238,10 @@ int phdslam_set_overlap(phdslam_t* h, int on);
  * exchange is the fused gather-and-push kernel; 0 when it runs the NCCL send/recv ring (PHDSLAM_P2P=0, or no peer
  * access between the GPUs).  Both give bit-identical particles. */
 int phdslam_dist_p2p(const phdslam_t* h);
+/* Imports n_src particles (poses, log-weights, maps) as the first local particles and fills [n_src, n_local) with copies
+ * of them (cyclically) on the device: a benchmark builds a 16 M-particle scene from one it can afford to generate. */
+int phdslam_import_tiled(phdslam_t* h, int n_src, const phdslam_pose_t* poses, const float* log_weights, const int* sizes,
+                         const phdslam_gaussian2d_t* maps);
 /* Snapshot / restore of the whole device state inside the handle (bench: identical work every step). */
 int phdslam_snapshot(phdslam_t* h);
 int phdslam_restore(phdslam_t* h);

@@ -95,7 +95,7 @@ def test_python_scene_config_is_byte_identical_to_the_library_one(bench):
     """bench.py's --impl reference arm builds its config without libphdslam.so (scene_config_py): same bytes"""
     from phdslam_b200 import scene as S
     for name, wl in bench.WORKLOADS.items():
-        extra = {k: v for k, v in wl.items() if k not in ("P", "C", "M", "max_components")}
+        extra = {k: v for k, v in wl.items() if k not in bench.NON_CFG_KEYS}
         a = S.scene_config(wl["P"], wl["C"], wl["M"], max_components=wl["max_components"], **extra)
         b = S.scene_config_py(wl["P"], wl["C"], wl["M"], max_components=wl["max_components"], **extra)
         assert bytes(a) == bytes(b), name

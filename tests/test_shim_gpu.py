@@ -67,9 +67,14 @@ def test_reference_run_synth_over_the_shim_matches_the_cli(tmp_path, filter_type
     for k in range(n_steps):
         a, b = _parse(out_s / ("state_estimate%05d.log" % k)), _parse(out_c / ("state_estimate%05d.log" % k))
         assert len(a) == len(b) == 7
-        # line 6: resample indices (bit-exact); a step whose indices are not the identity follows a resampling
-        assert a[5].shape == b[5].shape and (a[5] == b[5]).all(), "step %d: resample indices differ" % k
-        resampled += int((a[5] != np.arange(len(a[5]))).any())
+        # line 6: resample indices (bit-exact); a step whose indices are not the identity follows a resampling.  At step 0
+        # there is no previous resampling: the reference's vector is still value-initialised (all zeros,
+        # src/slamtypes.h:282-283), the CLI writes the identity.
+        if k == 0:
+            assert (a[5] == 0).all() and (b[5] == np.arange(len(b[5]))).all()
+        else:
+            assert a[5].shape == b[5].shape and (a[5] == b[5]).all(), "step %d: resample indices differ" % k
+            resampled += int((a[5] != np.arange(len(a[5]))).any())
         for i, what in ((0, "expected pose"), (1, "map estimate"), (3, "log-weights"), (4, "particle poses"), (6, "cardinality")):
             assert a[i].shape == b[i].shape, "step %d: %s has another size" % (k, what)
             np.testing.assert_allclose(a[i], b[i], rtol=1e-4, atol=2e-5, err_msg="step %d: %s" % (k, what))
