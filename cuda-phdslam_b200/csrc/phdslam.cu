@@ -1458,6 +1458,22 @@ extern "C" int phdslam_set_cardinalities(phdslam_t* h, const float* in) {
   return 0;
 }
 
+/* local particles [n_src, n_local) become copies of the first n_src (cyclically): exactly what a resampling with ancestors
+ * j mod n_src does -- gather into the back buffers, then flip */
+static int tile_from_prefix(phdslam* h, int n_src) {
+  const int n = h->n_local, b = h->cur;
+  if (n_src >= n) return 0;
+  tile_index_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->ancestors, n, n_src, h->logw);
+  LAUNCH_CHECK(h);
+  resample_gather_kernel<<<cdiv(n, 8), 256, 0, h->stream>>>(h->ancestors, n, 0, n, n, h->pose[b], h->pose[b ^ 1], h->count[b],
+                                                          h->count[b ^ 1], h->map[b], h->map[b ^ 1], h->card[b], h->card[b ^ 1],
+                                                          h->Cmax, h->n_card, 0, nullptr);
+  LAUNCH_CHECK(h);
+  CK(cudaStreamSynchronize(h->stream));
+  h->cur ^= 1;
+  return 0;
+}
+
 /* Imports n_src particles and fills the local particles [n_src, n_local) with copies of them (cyclically), on the device:
  * lets a benchmark build a 16 M-particle scene from one it can afford to generate and upload. */
 extern "C" int phdslam_import_tiled(phdslam_t* h, int n_src, const phdslam_pose_t* poses, const float* logw, const int* sizes,
@@ -1476,17 +1492,8 @@ extern "C" int phdslam_import_tiled(phdslam_t* h, int n_src, const phdslam_pose_
   int rc = set_maps_prefix(h, n_src, sizes, maps);
   if (rc) return rc;
   h->totals_valid = 0;
-  if (n_src == n) return 0;
-  /* exactly what a resampling with ancestors j mod n_src does: gather into the back buffers, then flip */
-  tile_index_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->ancestors, n, n_src, h->logw);
-  LAUNCH_CHECK(h);
-  resample_gather_kernel<<<cdiv(n, 8), 256, 0, h->stream>>>(h->ancestors, n, 0, n, n, h->pose[b], h->pose[b ^ 1], h->count[b],
-                                                          h->count[b ^ 1], h->map[b], h->map[b ^ 1], h->card[b], h->card[b ^ 1],
-                                                          h->Cmax, h->n_card, 0, nullptr);
-  LAUNCH_CHECK(h);
-  CK(cudaStreamSynchronize(h->stream));
-  h->cur ^= 1;
-  return 0;
+  h->tile_n = (n_src < n) ? n_src : 0;
+  return tile_from_prefix(h, n_src);
 }
 
 extern "C" int phdslam_particle_checksums(phdslam_t* h, unsigned long long* out) {
@@ -1600,18 +1607,21 @@ extern "C" int phdslam_get_timings(phdslam_t* h, phdslam_timings_t* out) {
 
 extern "C" int phdslam_snapshot(phdslam_t* h) {
   CK(cudaSetDevice(h->device));
-  const size_t n = h->n_local, C = h->Cmax;
+  /* a tiled particle set (phdslam_import_tiled) is snapshot as its tile_n distinct particles only */
+  const size_t n = h->tile_n ? (size_t)h->tile_n : (size_t)h->n_local, C = h->Cmax;
+  const size_t np = h->n_local;                 /* stride of the pose planes */
   CK(cudaStreamSynchronize(h->stream));
   if (!h->snap_pose) {
-    const size_t nc = h->n_cap;
+    const size_t nc = h->tile_n ? (size_t)h->tile_n : (size_t)h->n_cap;
     CK(cudaMalloc(&h->snap_pose, 6 * nc * sizeof(float)));
     CK(cudaMalloc(&h->snap_count, nc * sizeof(int)));
     CK(cudaMalloc(&h->snap_map, nc * PHD_MAP_PLANES * C * sizeof(float)));
     CK(cudaMalloc(&h->snap_logw, nc * sizeof(float)));
     if (h->n_card) CK(cudaMalloc(&h->snap_card, nc * h->n_card * sizeof(float)));
   }
-  h->snap_n = (int)n;
-  CK(cudaMemcpy(h->snap_pose, h->pose[h->cur], 6 * n * sizeof(float), cudaMemcpyDeviceToDevice));
+  h->snap_n = (int)np;
+  for (int k = 0; k < 6; ++k)
+    CK(cudaMemcpy(h->snap_pose + (size_t)k * n, h->pose[h->cur] + (size_t)k * np, n * sizeof(float), cudaMemcpyDeviceToDevice));
   CK(cudaMemcpy(h->snap_count, h->count[h->cur], n * sizeof(int), cudaMemcpyDeviceToDevice));
   CK(cudaMemcpy(h->snap_map, h->map[h->cur], n * PHD_MAP_PLANES * C * sizeof(float), cudaMemcpyDeviceToDevice));
   CK(cudaMemcpy(h->snap_logw, h->logw, n * sizeof(float), cudaMemcpyDeviceToDevice));
@@ -1625,8 +1635,10 @@ extern "C" int phdslam_restore(phdslam_t* h) {
   if (!h->snap_pose) return PHDSLAM_ERR_INVALID;
   h->totals_valid = 0;
   if (h->world == 1) h->n_local = h->n_global = h->snap_n;
-  const size_t n = h->n_local, C = h->Cmax;
-  CK(cudaMemcpyAsync(h->pose[h->cur], h->snap_pose, 6 * n * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  const size_t n = h->tile_n ? (size_t)h->tile_n : (size_t)h->n_local, C = h->Cmax;
+  const size_t np = h->n_local;
+  for (int k = 0; k < 6; ++k)
+    CK(cudaMemcpyAsync(h->pose[h->cur] + (size_t)k * np, h->snap_pose + (size_t)k * n, n * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemcpyAsync(h->count[h->cur], h->snap_count, n * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemcpyAsync(h->map[h->cur], h->snap_map, n * PHD_MAP_PLANES * C * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemcpyAsync(h->logw, h->snap_logw, n * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
@@ -1634,5 +1646,6 @@ extern "C" int phdslam_restore(phdslam_t* h) {
     CK(cudaMemcpyAsync(h->card[h->cur], h->snap_card, n * h->n_card * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
   h->predict_calls = h->snap_predict_calls;
   h->resample_calls = h->snap_resample_calls;
+  if (h->tile_n) return tile_from_prefix(h, h->tile_n);     /* two kernels, outside any timed region of the caller */
   return 0;
 }

@@ -77,6 +77,8 @@ struct phdslam {
   float* snap_pose; int* snap_count; float* snap_map; float* snap_card; float* snap_logw;
   unsigned snap_predict_calls, snap_resample_calls;
   int snap_n;
+  int tile_n;            /* > 0: the local particles are tile_n distinct ones repeated (phdslam_import_tiled); snapshot / restore
+                            then keep only those and re-tile on the device */
   /* per-step scratch */
   uint8_t* cls;                      /* [n_local][Cmax] in-range class */
   int* n_in;                         /* [n_local] */

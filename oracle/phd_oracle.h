@@ -16,8 +16,13 @@
  * recipe), compared with this oracle in tests/test_ref_pin.py, with the outputs
  * committed as tests/golden/ref_golden.npz (generator:
  * tests/golden/make_ref_golden.py); (b) closed-form known-answer tests
- * (tests/test_oracle_kat.py).  CPHD is dead code in the reference
- * and has no runnable counterpart: that row is pinned by (b) only.
+ * (tests/test_oracle_kat.py).  CPHD is dead code at the reference's HEAD
+ * (commented out line by line) and live, in an older form, in
+ * src/phdfilter.cu.bak; ref_build.sh makes both executable (HEAD: the leading
+ * "//" of every line removed; .bak: verbatim) and tests/test_cphd_ref_pin.py
+ * compares this oracle with their outputs (golden: tests/golden/
+ * ref_cphd_golden.npz): detection / non-detection weights, means, covariances,
+ * log<Psi0,p> and the posterior cardinality within 1e-4.
  *
  * Arithmetic: fp32 in the reference's operation order, with the transcendental
  * functions of include/phd_detmath.h so that results are bit-reproducible on the
