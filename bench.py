@@ -49,13 +49,13 @@ WORKLOADS = {
     "synthetic_262144x128x100_phd": dict(P=262144, C=128, M=100, max_components=256, resample_threshold=1.0),
     # BASELINE.json configs[4] at its literal size: 16 777 216 particles IN TOTAL, split over the GPUs (strong scaling), global
     # resampling every step.  A rank generates 262 144 distinct particles and tiles them on the device (import_tiled).
-    # Maps reach 208 - 221 components after one step at this shape, hence max_components = 224.  Memory per GPU: the two map
-    # buffers 2 x 5.25 KB per particle, 16 GB dense buffer, 16 GB candidate buffers, 1.5 GB snapshot of the distinct
-    # particles: 126 GB at N = 2 (8.4 M particles per GPU).  N = 1 would need 180 GB for the map buffers alone: it does
+    # Maps reach 208 - 230 components after one step at this shape (max_components = 256).  Memory per GPU: the two map
+    # buffers 2 x 6 KB per particle, 16 GB dense buffer, 16 GB candidate buffers, 1.6 GB snapshot of the distinct
+    # particles: 139 GB at N = 2 (8.4 M particles per GPU).  N = 1 would need 206 GB for the map buffers alone: it does
     # not fit one B200 (180 GB), so the sweep starts at N = 2.
-    "synthetic_16777216x128x100_phd": dict(P=16777216, C=128, M=100, max_components=224, resample_threshold=1.0, strong=1,
+    "synthetic_16777216x128x100_phd": dict(P=16777216, C=128, M=100, max_components=256, resample_threshold=1.0, strong=1,
                                            scene_particles=262144, update_buffer_bytes=16 << 30),
-    "synthetic_2097152x128x100_phd": dict(P=2097152, C=128, M=100, max_components=224, resample_threshold=1.0, strong=1,
+    "synthetic_2097152x128x100_phd": dict(P=2097152, C=128, M=100, max_components=256, resample_threshold=1.0, strong=1,
                                           scene_particles=65536, update_buffer_bytes=16 << 30),   # the same path, quick-check size
 }
 NON_CFG_KEYS = ("P", "C", "M", "max_components", "strong", "scene_particles")

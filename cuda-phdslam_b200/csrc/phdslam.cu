@@ -84,6 +84,19 @@ static bool load() {
     }                                                                                                \
   } while (0)
 
+/* Every entry point that touches particle state: select the device and allocate the state on first use.  The allocation
+ * is deferred from phdslam_create so that phdslam_dist_init can allocate this rank's SHARE only (16.7 M particles x 12 KB of
+ * map buffers do not fit one GPU; a rank's share of them does). */
+static int ensure_state(phdslam* h);
+#define ENTER(h)                                  \
+  do {                                            \
+    CK(cudaSetDevice((h)->device));               \
+    if (!(h)->state_ready) {                      \
+      int rc__ = ensure_state(h);                 \
+      if (rc__) return rc__;                      \
+    }                                             \
+  } while (0)
+
 #define LAUNCH_CHECK(h)            \
   do {                             \
     (h)->launches++;               \
@@ -395,8 +408,6 @@ static int create_impl(phdslam* h, const phdslam_config_t* cfg, int device) {
     const char* e = getenv("PHDSLAM_OVERLAP");
     h->overlap = (e && atoi(e) != 0) ? 1 : 0;
   }
-  rc = alloc_state(h);
-  if (rc) return rc;
   CK(cudaFuncSetAttribute(update_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(h->Cmax)));
   CK(cudaFuncSetAttribute(update_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(h->Cmax)));
   if (h->n_card) {
@@ -424,7 +435,17 @@ static int create_impl(phdslam* h, const phdslam_config_t* cfg, int device) {
     }
     CK(cudaFuncSetAttribute(merge_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_fast_smem_bytes(h->Scap_max)));
   }
-  return init_particles(h);
+  (void)rc;
+  return 0;       /* particle state: allocated and initialised on first use (ensure_state) or by phdslam_dist_init */
+}
+
+static int ensure_state(phdslam* h) {
+  int rc = alloc_state(h);
+  if (rc) return rc;
+  rc = init_particles(h);
+  if (rc) return rc;
+  h->state_ready = 1;
+  return 0;
 }
 
 extern "C" void phdslam_destroy(phdslam_t* h) {
@@ -568,7 +589,8 @@ extern "C" int phdslam_dist_init(phdslam_t* h, int rank, int world, const void* 
   h->nccl_comm = (void*)comm;
   h->rank = rank;
   h->world = world;
-  free_state(h);
+  if (h->state_ready) free_state(h);
+  h->state_ready = 0;
   h->dense = nullptr; h->dense_floats = 0; h->cand = h->cand_in = nullptr; h->cand_cap = 0;
   h->draws_dev = nullptr; h->draws_cap = 0;
   h->snap_pose = nullptr; h->snap_count = nullptr; h->snap_map = nullptr; h->snap_card = nullptr; h->snap_logw = nullptr;
@@ -581,6 +603,7 @@ extern "C" int phdslam_dist_init(phdslam_t* h, int rank, int world, const void* 
   if (rc) return rc;
   rc = init_particles(h);
   if (rc) return rc;
+  h->state_ready = 1;
   return map_peer_windows(h);
 }
 
@@ -646,7 +669,7 @@ static int fan_out(phdslam* h) {
 }
 
 extern "C" int phdslam_predict(phdslam_t* h, const float* control, const double* draws) {
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   if (h->cfg.n_predict_particles > 1) {
     int rcf = fan_out(h);
     if (rcf) return rcf;
@@ -830,7 +853,7 @@ static int update_weights(phdslam* h, bool add) {
 }
 
 extern "C" int phdslam_update(phdslam_t* h, const float* z, int M, int fields) {
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   if (M <= 0) return 0;                 /* main.cpp:1258 */
   h->totals_valid = 0;
   if (fields != 2 && fields != 3) return PHDSLAM_ERR_INVALID;
@@ -944,7 +967,7 @@ extern "C" int phdslam_update(phdslam_t* h, const float* z, int M, int fields) {
 
 extern "C" int phdslam_update_terms(phdslam_t* h, const float* z, int M, int fields, phdslam_gaussian2d_t* terms_out,
                                     size_t cap, int* n_in_range_out, float* dlogw_out) {
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   if (M <= 0 || (fields != 2 && fields != 3)) return PHDSLAM_ERR_INVALID;
   if (M > PHD_MAX_MEAS) M = PHD_MAX_MEAS;
   int rc = upload_measurements(h, z, M, fields);
@@ -995,7 +1018,7 @@ extern "C" int phdslam_update_terms(phdslam_t* h, const float* z, int M, int fie
 
 /* ---- estimate ---- */
 extern "C" int phdslam_estimate(phdslam_t* h, phdslam_estimate_t* out) {
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   const int n = h->n_local;
   CK(cudaEventRecord(h->ev[7], h->stream));
   CK(cudaMemsetAsync(h->red, 0, sizeof(Reductions), h->stream));
@@ -1067,7 +1090,7 @@ static int ensure_migration(phdslam* h, size_t records) {
 }
 
 extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms, int* ancestors_out) {
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   const int n = h->n_local;
   if (n_new < 0) n_new = h->n_global;
   if (n_new != h->n_global && (h->world > 1 || n_new > h->n_cap || n_new < 1)) {
@@ -1298,7 +1321,7 @@ extern "C" int phdslam_step_resample(phdslam_t* h, int M, const phdslam_estimate
     if (rc) return rc;
     res = 1;
   } else {                                                                                           /* :1293-1296 */
-    CK(cudaSetDevice(h->device));
+    ENTER(h);
     iota_kernel<<<cdiv(h->n_local, 256), 256, 0, h->stream>>>(h->resample_idx, h->n_local, h->offset);
     LAUNCH_CHECK(h);
   }
@@ -1325,16 +1348,19 @@ extern "C" int phdslam_set_particle_count(phdslam_t* h, int n) {
     phdslam_set_error("phdslam_set_particle_count: single GPU only, 1 <= n <= particle capacity");
     return PHDSLAM_ERR_INVALID;
   }
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   CK(cudaStreamSynchronize(h->stream));
   h->n_local = h->n_global = n;
   return 0;
 }
-extern "C" int phdslam_particle_capacity(const phdslam_t* h) { return h->n_cap; }
+extern "C" int phdslam_particle_capacity(const phdslam_t* h) {
+  if (h->state_ready) return h->n_cap;
+  return (h->world > 1) ? h->n_local : particle_capacity(h->cfg, h->n_local);
+}
 
 /* ---- import / export ---- */
 extern "C" int phdslam_get_poses(phdslam_t* h, phdslam_pose_t* out) {
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   const int n = h->n_local;
   std::vector<float> soa((size_t)6 * n);
   CK(cudaStreamSynchronize(h->stream));
@@ -1346,7 +1372,7 @@ extern "C" int phdslam_get_poses(phdslam_t* h, phdslam_pose_t* out) {
   return 0;
 }
 extern "C" int phdslam_set_poses(phdslam_t* h, const phdslam_pose_t* in) {
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   const int n = h->n_local;
   std::vector<float> soa((size_t)6 * n);
   for (int i = 0; i < n; ++i) {
@@ -1358,26 +1384,26 @@ extern "C" int phdslam_set_poses(phdslam_t* h, const phdslam_pose_t* in) {
   return 0;
 }
 extern "C" int phdslam_get_log_weights(phdslam_t* h, float* out) {
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   CK(cudaStreamSynchronize(h->stream));
   CK(copy_d2h(h, out, h->logw, (size_t)h->n_local * sizeof(float)));
   return 0;
 }
 extern "C" int phdslam_set_log_weights(phdslam_t* h, const float* in) {
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   h->totals_valid = 0;
   CK(cudaStreamSynchronize(h->stream));
   CK(copy_h2d(h, h->logw, in, (size_t)h->n_local * sizeof(float)));
   return 0;
 }
 extern "C" int phdslam_get_map_sizes(phdslam_t* h, int* out) {
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   CK(cudaStreamSynchronize(h->stream));
   CK(copy_d2h(h, out, h->count[h->cur], (size_t)h->n_local * sizeof(int)));
   return 0;
 }
 extern "C" int phdslam_get_maps(phdslam_t* h, phdslam_gaussian2d_t* out, size_t cap) {
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   const int n = h->n_local;
   const size_t C = h->Cmax;
   std::vector<int> cnt(n);
@@ -1410,7 +1436,7 @@ extern "C" int phdslam_set_maps(phdslam_t* h, const int* sizes, const phdslam_ga
 }
 /* maps of the first n local particles */
 static int set_maps_prefix(phdslam_t* h, int n, const int* sizes, const phdslam_gaussian2d_t* in) {
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   const size_t C = h->Cmax;
   for (int p = 0; p < n; ++p)
     if (sizes[p] > h->Cmax || sizes[p] < 0) {
@@ -1438,21 +1464,21 @@ static int set_maps_prefix(phdslam_t* h, int n, const int* sizes, const phdslam_
   return 0;
 }
 extern "C" int phdslam_get_resample_idx(phdslam_t* h, int* out) {
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   CK(cudaStreamSynchronize(h->stream));
   CK(copy_d2h(h, out, h->resample_idx, (size_t)h->n_local * sizeof(int)));
   return 0;
 }
 extern "C" int phdslam_get_cardinalities(phdslam_t* h, float* out) {
   if (!h->n_card) return PHDSLAM_ERR_INVALID;
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   CK(cudaStreamSynchronize(h->stream));
   CK(copy_d2h(h, out, h->card[h->cur], (size_t)h->n_local * h->n_card * sizeof(float)));
   return 0;
 }
 extern "C" int phdslam_set_cardinalities(phdslam_t* h, const float* in) {
   if (!h->n_card) return PHDSLAM_ERR_INVALID;
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   CK(cudaStreamSynchronize(h->stream));
   CK(copy_h2d(h, h->card[h->cur], in, (size_t)h->n_local * h->n_card * sizeof(float)));
   return 0;
@@ -1478,7 +1504,7 @@ static int tile_from_prefix(phdslam* h, int n_src) {
  * lets a benchmark build a 16 M-particle scene from one it can afford to generate and upload. */
 extern "C" int phdslam_import_tiled(phdslam_t* h, int n_src, const phdslam_pose_t* poses, const float* logw, const int* sizes,
                                     const phdslam_gaussian2d_t* maps) {
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   const int n = h->n_local;
   if (n_src < 1 || n_src > n) return PHDSLAM_ERR_INVALID;
   CK(cudaStreamSynchronize(h->stream));
@@ -1497,7 +1523,7 @@ extern "C" int phdslam_import_tiled(phdslam_t* h, int n_src, const phdslam_pose_
 }
 
 extern "C" int phdslam_particle_checksums(phdslam_t* h, unsigned long long* out) {
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   const int n = h->n_local;
   /* q_fx is per-resampling scratch of n_cap 64-bit words */
   particle_checksum_kernel<<<cdiv(n, 8), 256, 0, h->stream>>>(h->pose[h->cur], h->count[h->cur], h->map[h->cur], h->card[h->cur], n,
@@ -1510,7 +1536,7 @@ extern "C" int phdslam_particle_checksums(phdslam_t* h, unsigned long long* out)
 
 extern "C" int phdslam_map_estimate(phdslam_t* h, int which, phdslam_gaussian2d_t* out, int cap, int* n_out_p) {
   int* n_out = n_out_p;
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   if (which == 1) {
     phdslam_estimate_t e;
     int rc = phdslam_estimate(h, &e);
@@ -1596,7 +1622,7 @@ extern "C" int phdslam_map_estimate(phdslam_t* h, int which, phdslam_gaussian2d_
 
 /* ---- timings / snapshot ---- */
 extern "C" int phdslam_get_timings(phdslam_t* h, phdslam_timings_t* out) {
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   CK(cudaStreamSynchronize(h->stream));
   float ms = 0;
   if (h->predict_calls && cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->tim.predict_ms = ms;
@@ -1606,7 +1632,7 @@ extern "C" int phdslam_get_timings(phdslam_t* h, phdslam_timings_t* out) {
 }
 
 extern "C" int phdslam_snapshot(phdslam_t* h) {
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   /* a tiled particle set (phdslam_import_tiled) is snapshot as its tile_n distinct particles only */
   const size_t n = h->tile_n ? (size_t)h->tile_n : (size_t)h->n_local, C = h->Cmax;
   const size_t np = h->n_local;                 /* stride of the pose planes */
@@ -1631,7 +1657,7 @@ extern "C" int phdslam_snapshot(phdslam_t* h) {
   return 0;
 }
 extern "C" int phdslam_restore(phdslam_t* h) {
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   if (!h->snap_pose) return PHDSLAM_ERR_INVALID;
   h->totals_valid = 0;
   if (h->world == 1) h->n_local = h->n_global = h->snap_n;

@@ -60,6 +60,7 @@ struct phdslam {
   cudaStream_t stream;
   int rank, world;
   int n_global, n_local, offset;
+  int state_ready;       /* particle state allocated and initialised (deferred from phdslam_create to the first use) */
   int n_cap;             /* particle capacity of every per-particle array (> n_particles only for n_predict_particles > 1) */
   int Cmax, n_card, Smax;
   int Scap_max, Scap_pinned;

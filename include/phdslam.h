@@ -108,8 +108,9 @@ const char* phdslam_last_error(void);
 const char* phdslam_version(void);
 
 /* ---- lifetime ---- */
-/* Allocates persistent device state for cfg->n_particles particles on CUDA device `device`
- * and initialises them as run_synth does (src/main.cpp:1129-1144): every pose = (x0..vyaw0),
+/* Creates the handle for cfg->n_particles particles on CUDA device `device`; the persistent device state is allocated on
+ * the first call that touches it (or by phdslam_dist_init, for this rank's share only: a particle set that does not fit
+ * one GPU can still be created and then sharded) and initialised as run_synth does (src/main.cpp:1129-1144): every pose = (x0..vyaw0),
  * log-weight = -log(N), empty maps, uniform CPHD cardinality.  Also stands in for
  * initRandomNumberGenerators() + setDeviceConfig() (src/phdfilter.cu:142,3885). */
 int phdslam_create(const phdslam_config_t* cfg, int device, phdslam_t** out);

@@ -18,7 +18,7 @@ PY
 run bench_n2_strong2m PHDSLAM_MBOX=1 "--workload synthetic_2097152x128x100_phd --steps 3 --warmup 2" 29514
 nvidia-smi --query-gpu=memory.used --format=csv > $OUT/${TAG}_mem0.txt
 run bench_n2_strong16m PHDSLAM_MBOX=1 "--workload synthetic_16777216x128x100_phd --steps 3 --warmup 2" 29515
-for cap in 672 736; do
+for cap in; do
   PHDSLAM_MERGE_CAP=$cap timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench_cap$cap.json 2> $OUT/${TAG}_bench_cap$cap.err
   grep -o '"phase_ms": {"update": [0-9.]*, "merge": [0-9.]*' $OUT/${TAG}_bench_cap$cap.json
 done
