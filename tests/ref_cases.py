@@ -20,6 +20,9 @@ UPDATE_CASES = {
     "narrow_fov": (5, 30, 10, 0, 0, 23, dict(max_bearing=1.2, min_range=2.0, max_range=12.0)),
     "single": (1, 1, 1, 0, 0, 29, dict()),
     "low_pd_tight": (4, 36, 16, 2, 2, 31, dict(pd=0.6, min_separation=4.0, min_feature_weight=1e-4, birth_weight=0.05)),
+    # BASELINE shapes per particle (the reference's kernels through the emulator take a few seconds per particle here)
+    "headline_shape": (2, 256, 64, 0, 0, 41, dict()),                 # configs[2]: 256 components x 64 measurements
+    "configs4_shape": (2, 128, 100, 3, 2, 43, dict()),                # configs[4]: 128 components x 100 measurements
 }
 LABELED_CASE = ("labeled", (4, 16, 8, 1, 1, 37, dict(labeled_measurements=1)))
 
