@@ -264,6 +264,8 @@ static void free_state(phdslam* h) {
   cudaFree(h->mig_pose_in); cudaFree(h->totals_dev); cudaFree(h->lfact); cudaFree(h->mig_anc2);
   h->mig_pose_in = nullptr; h->totals_dev = nullptr; h->lfact = nullptr; h->mig_anc2 = nullptr; h->mig_anc_cap = 0;
   if (h->red_host) cudaFreeHost(h->red_host);
+  if (h->z_host) cudaFreeHost(h->z_host);
+  h->red_host = nullptr; h->z_host = nullptr;
 }
 
 /* Particle capacity.  With n_predict_particles = k > 1 every prediction multiplies the particle count by k and the loop
@@ -325,6 +327,7 @@ static int alloc_state(phdslam* h) {
   CK(cudaMalloc(&h->ancestors, n * sizeof(int)));
   CK(cudaMalloc(&h->red, sizeof(Reductions)));
   CK(cudaMallocHost(&h->red_host, sizeof(Reductions)));
+  CK(cudaMallocHost(&h->z_host, 3 * PHD_MAX_MEAS * sizeof(float)));
   CK(cudaMalloc(&h->lfact, PHD_LF_MAX * sizeof(float)));
   return 0;
 }
@@ -665,6 +668,7 @@ static int fan_out(phdslam* h) {
   std::swap(h->resample_idx, h->n_in);      /* both are n_cap ints; n_in is per-update scratch */
   h->cur ^= 1;
   h->n_local = h->n_global = (int)n_out;
+  h->totals_valid = 0;
   return 0;
 }
 
@@ -699,19 +703,24 @@ extern "C" int phdslam_predict(phdslam_t* h, const float* control, const double*
 
 /* ---- update ---- */
 static int upload_measurements(phdslam* h, const float* z, int M, int fields) {
-  std::vector<float> zz(3 * PHD_MAX_MEAS, 0.0f);
+  /* pinned staging buffer owned by the handle: no synchronisation needed -- the previous update (the only other user) has
+   * completed before this call (phdslam_update ends with a stream synchronisation) */
+  float* zz = h->z_host;
+  memset(zz, 0, 3 * PHD_MAX_MEAS * sizeof(float));
   for (int m = 0; m < M; ++m) {
     zz[m] = z[(size_t)m * fields];
     zz[PHD_MAX_MEAS + m] = z[(size_t)m * fields + 1];
     zz[2 * PHD_MAX_MEAS + m] = (fields > 2) ? z[(size_t)m * fields + 2] : 0.0f;
   }
-  CK(copy_h2d_async(h, h->z_dev, zz.data(), zz.size() * sizeof(float), h->stream));
-  CK(cudaStreamSynchronize(h->stream)); /* zz is a stack-lifetime staging buffer (768 floats) */
+  CK(copy_h2d_async(h, h->z_dev, zz, 3 * PHD_MAX_MEAS * sizeof(float), h->stream));
   return 0;
 }
 
 /* classification + dense-offset scan; leaves total/max padded term counts in red_host */
-static int classify_and_scan(phdslam* h, int M) {
+#define PHD_CAND_BUDGET (8ull << 30)
+/* worst_case_ok: the caller can plan from an upper bound of the term counts (every particle with max_components in-range
+ * components), so the counts need not come back to the host: red_host then holds that bound, not the measured values */
+static int classify_and_scan(phdslam* h, int M, bool worst_case_ok = false) {
   const int n = h->n_local;
   CK(cudaMemsetAsync(h->red, 0, sizeof(Reductions), h->stream));
   classify_kernel<<<cdiv(n, 8), 256, 0, h->stream>>>(h->map[h->cur], h->count[h->cur], h->pose[h->cur], n, M, h->cls,
@@ -719,6 +728,18 @@ static int classify_and_scan(phdslam* h, int M) {
   LAUNCH_CHECK(h);
   int rc = scan_u64(h, h->tpad, n, h->toff, &h->red->total_terms);
   if (rc) return rc;
+  if (worst_case_ok) {
+    const unsigned long long tmax = (((unsigned long long)h->Cmax * (unsigned)(M + 1) + (unsigned)M) + 63ull) & ~63ull;
+    const unsigned long long bound = tmax * (unsigned long long)n;
+    const unsigned long long budget_terms = h->cfg.update_buffer_bytes / (PHD_NPLANES * 4);
+    if (bound <= (1ull << 28) && bound <= budget_terms &&
+        (unsigned long long)n * h->Smax * 64ull <= PHD_CAND_BUDGET) {   /* <= 7.5 GB of dense terms, one batch */
+      memset(h->red_host, 0, sizeof(Reductions));
+      h->red_host->total_terms = bound;
+      h->red_host->max_terms = (int)tmax;
+      return 0;
+    }
+  }
   CK(copy_d2h_async(h, h->red_host, h->red, sizeof(Reductions), h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return 0;
@@ -749,7 +770,6 @@ static int ensure_dense(phdslam* h, size_t floats) {
 
 /* Particles stream through the scratch buffers in batches [p0, p1): the dense update-term buffer (dense mode,
  * bounded by update_buffer_bytes) and the merge candidate records (bounded by PHD_CAND_BUDGET). */
-#define PHD_CAND_BUDGET (8ull << 30)
 static int plan_batches(phdslam* h, bool dense, std::vector<int>& bounds, size_t* max_batch_terms) {
   const int n = h->n_local;
   const unsigned long long total = h->red_host->total_terms;
@@ -861,7 +881,7 @@ extern "C" int phdslam_update(phdslam_t* h, const float* z, int M, int fields) {
   int rc = upload_measurements(h, z, M, fields);
   if (rc) return rc;
   CK(cudaEventRecord(h->ev[2], h->stream));
-  rc = classify_and_scan(h, M);
+  rc = classify_and_scan(h, M, /*worst_case_ok=*/true);   /* small particle sets: no host round trip for the term counts */
   if (rc) return rc;
   std::vector<int> bounds;
   size_t max_terms = 0;
@@ -1048,6 +1068,9 @@ extern "C" int phdslam_estimate(phdslam_t* h, phdslam_estimate_t* out) {
   if (h->mbox) {
     for (int r = 0; r < h->world; ++r) h->totals_host[r] = h->gath_host[(size_t)r * MBOX_WORDS + 8];
     h->totals_valid = 1;
+  } else if (h->world == 1) {
+    h->totals_host[0] = h->red_host->cdf_total;      /* the resampling CDF total of the current weights (estimate_kernel) */
+    h->totals_valid = 1;
   }
   const Reductions& r = *h->red_host;
   const double inv = 1.0 / (double)(1ull << PHD_FX_POSE_BITS);
@@ -1151,9 +1174,13 @@ extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms,
     rc = phdslam_plan_migration(h->world, totals.data(), n_new, uniforms, h->cfg.resample_mode, h->resample_calls, h->cfg.seed, bounds.data());
     if (rc) return rc;
   } else {
-    CK(copy_d2h_async(h, h->red_host, h->red, sizeof(Reductions), h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    total = h->red_host->cdf_total;
+    if (h->totals_valid) {
+      total = h->totals_host[0];            /* known since the estimate: no host round trip */
+    } else {
+      CK(copy_d2h_async(h, h->red_host, h->red, sizeof(Reductions), h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      total = h->red_host->cdf_total;
+    }
     if (total == 0) {
       phdslam_set_error("all particle weights are zero or NaN");
       return PHDSLAM_ERR_NAN;
@@ -1273,8 +1300,14 @@ extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms,
   CK(cudaEventRecord(h->ev[10], h->stream));
   if (ancestors_out) CK(copy_d2h_async(h, ancestors_out, h->ancestors, (size_t)n_off * sizeof(int), h->stream));
   if (h->mbox) CK(copy_d2h_async(h, &h->red_host->err_flag, &h->red->err_flag, sizeof(int), h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  cudaEventElapsedTime(&h->tim.resample_ms, h->ev[9], h->ev[10]);
+  h->resample_timed = 1;
+  if (h->world > 1 || ancestors_out || uniforms) {
+    /* the caller's buffers / the peers need the result now; on a single GPU with the counter-based draws nothing does:
+     * the next call on the stream is ordered behind the gather, and phdslam_get_timings reads the events later */
+    CK(cudaStreamSynchronize(h->stream));
+    cudaEventElapsedTime(&h->tim.resample_ms, h->ev[9], h->ev[10]);
+    h->resample_timed = 0;
+  }
   h->cur ^= 1;
   h->resample_calls++;
   h->totals_valid = 0;
@@ -1351,6 +1384,7 @@ extern "C" int phdslam_set_particle_count(phdslam_t* h, int n) {
   ENTER(h);
   CK(cudaStreamSynchronize(h->stream));
   h->n_local = h->n_global = n;
+  h->totals_valid = 0;
   return 0;
 }
 extern "C" int phdslam_particle_capacity(const phdslam_t* h) {
@@ -1626,6 +1660,8 @@ extern "C" int phdslam_get_timings(phdslam_t* h, phdslam_timings_t* out) {
   CK(cudaStreamSynchronize(h->stream));
   float ms = 0;
   if (h->predict_calls && cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->tim.predict_ms = ms;
+  if (h->resample_timed && cudaEventElapsedTime(&ms, h->ev[9], h->ev[10]) == cudaSuccess) h->tim.resample_ms = ms;
+  h->resample_timed = 0;
   h->tim.launches = h->launches;
   *out = h->tim;
   return 0;

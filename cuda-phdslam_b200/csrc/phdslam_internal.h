@@ -97,6 +97,8 @@ struct phdslam {
   int* ancestors;                    /* [n_local] */
   Reductions* red;                   /* device */
   Reductions* red_host;              /* pinned */
+  float* z_host;                     /* pinned staging of the measurements, [3][256] */
+  int resample_timed;                /* ev[9..10] of the last resampling have not been read yet */
   int nan_seen;                      /* the last update saw NaN particle weights (reported by phdslam_step after the estimate) */
   /* counters */
   unsigned predict_calls, resample_calls;
