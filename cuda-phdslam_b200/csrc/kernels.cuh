@@ -1784,7 +1784,7 @@ __global__ void __launch_bounds__(MRG_THREADS) merge_kernel(MrgArgs a) {
 #define MF_NONE 0xffffu
 #define MF_CELLS 592         /* MRG_NCELL + 1, padded */
 #define MF_QUEUE 128         /* gate survivors queued per warp (ring buffer) */
-#define MF_SEG 8             /* cell-order positions per gate segment (pair phase) */
+#define MF_SEG 8             /* cell-order positions per gate segment (pair phase); 16 measured slower (7.47 vs 7.00 ms) */
 #define MF_ACH 8             /* A candidates gated per compaction step (up to MF_ACH * 32 new queue entries) */
 
 __host__ __device__ static inline size_t merge_fast_smem_bytes(int S) {
@@ -2393,45 +2393,60 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
     }
     __syncthreads();
 
-    /* ---- H. moment-matched merge, one thread per cluster (:2808-2881) ---- */
-    for (int k = tid; k < klimit; k += MF_THREADS) {
-      const int beg = (k > 0) ? csz[k - 1] : 0, end = csz[k];
-      float wsum = 0.0f, m0 = 0.0f, m1 = 0.0f;
-      /* most clusters have one or two members: their records are requested together (one L2 round trip instead of one per
-       * member); the accumulation order is unchanged */
-      const int ra = (beg < end) ? memb[beg] : 0, rb = (beg + 1 < end) ? memb[beg + 1] : ra;
-      const float4 Pa1 = crec[2 * ra + 1], Pb1 = crec[2 * rb + 1];
-      const float4 Pa0 = crec[2 * ra], Pb0 = crec[2 * rb];
-      for (int j = beg; j < end; ++j) {
-        const float4 B1 = (j == beg) ? Pa1 : (j == beg + 1) ? Pb1 : crec[2 * memb[j] + 1];
-        wsum = wsum + B1.z;
-        m0 = m0 + B1.z * B1.x;
-        m1 = m1 + B1.z * B1.y;
+    /* ---- H. moment-matched merge, one thread per cluster (:2808-2881).  The members' records are first staged in shared
+     * memory in MEMBER order -- all threads, independent L2 loads in flight -- over arrays that are dead by now (gate
+     * records, candidate -> rank table, seed slots: 20 bytes per candidate in one piece; the tail of the near-pair pool: 8
+     * more), so that the per-cluster loops, which are serial in the members, read shared memory instead of waiting for
+     * one L2 round trip per member. ---- */
+    {
+      const int mtot = (nseeds > 0) ? (int)csz[nseeds - 1] : 0;
+      float* st_mx = reinterpret_cast<float*>(Gc);            /* five planes of S floats: Gc | P1 | items  (20 S + 128 bytes) */
+      float* st_my = st_mx + S;
+      float* st_w = st_my + S;
+      float* st_c0 = st_w + S;
+      float* st_c3 = st_c0 + S;
+      float2* st_c12 = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(pool) + 2 * (size_t)S);   /* behind memb */
+      for (int j = tid; j < mtot; j += MF_THREADS) {
+        const int rr = memb[j];
+        const float4 B0 = crec[2 * rr], B1 = crec[2 * rr + 1];
+        st_mx[j] = B1.x; st_my[j] = B1.y; st_w[j] = B1.z;
+        st_c0[j] = B0.x; st_c3[j] = B0.w;
+        st_c12[j] = make_float2(B0.y, B0.z);
       }
-      if (wsum == 0.0f) {                                 /* :2821-2822: the reference stops here */
-        atomicMin(&s_kzero, k);
-      } else if (k < Cmax) {
-        const float rw = 1.0f / wsum;
-        const float mm0 = m0 * rw, mm1 = m1 * rw;
-        float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
+      __syncthreads();
+      for (int k = tid; k < klimit; k += MF_THREADS) {
+        const int beg = (k > 0) ? csz[k - 1] : 0, end = csz[k];
+        float wsum = 0.0f, m0 = 0.0f, m1 = 0.0f;
         for (int j = beg; j < end; ++j) {
-          const int rr = memb[j];
-          const float4 B0 = (j == beg) ? Pa0 : (j == beg + 1) ? Pb0 : crec[2 * rr];
-          const float4 B1 = (j == beg) ? Pa1 : (j == beg + 1) ? Pb1 : crec[2 * rr + 1];
-          const float d0 = mm0 - B1.x, d1 = mm1 - B1.y;
-          v0 = v0 + B1.z * (B0.x + d0 * d0);
-          v1 = v1 + B1.z * (B0.y + d0 * d1);
-          v2 = v2 + B1.z * (B0.z + d1 * d0);
-          v3 = v3 + B1.z * (B0.w + d1 * d1);
+          const float w = st_w[j];
+          wsum = wsum + w;
+          m0 = m0 + w * st_mx[j];
+          m1 = m1 + w * st_my[j];
         }
-        v0 = v0 * rw; v1 = v1 * rw; v2 = v2 * rw; v3 = v3 * rw;
-        v1 = (v1 + v2) / 2.0f;                             /* force_symmetric_covariance */
-        mo[0 * Cmax + k] = wsum;
-        mo[1 * Cmax + k] = mm0;
-        mo[2 * Cmax + k] = mm1;
-        mo[3 * Cmax + k] = v0;
-        mo[4 * Cmax + k] = v1;
-        mo[5 * Cmax + k] = v3;
+        if (wsum == 0.0f) {                                 /* :2821-2822: the reference stops here */
+          atomicMin(&s_kzero, k);
+        } else if (k < Cmax) {
+          const float rw = 1.0f / wsum;
+          const float mm0 = m0 * rw, mm1 = m1 * rw;
+          float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
+          for (int j = beg; j < end; ++j) {
+            const float w = st_w[j];
+            const float2 c12 = st_c12[j];
+            const float d0 = mm0 - st_mx[j], d1 = mm1 - st_my[j];
+            v0 = v0 + w * (st_c0[j] + d0 * d0);
+            v1 = v1 + w * (c12.x + d0 * d1);
+            v2 = v2 + w * (c12.y + d1 * d0);
+            v3 = v3 + w * (st_c3[j] + d1 * d1);
+          }
+          v0 = v0 * rw; v1 = v1 * rw; v2 = v2 * rw; v3 = v3 * rw;
+          v1 = (v1 + v2) / 2.0f;                             /* force_symmetric_covariance */
+          mo[0 * Cmax + k] = wsum;
+          mo[1 * Cmax + k] = mm0;
+          mo[2 * Cmax + k] = mm1;
+          mo[3 * Cmax + k] = v0;
+          mo[4 * Cmax + k] = v1;
+          mo[5 * Cmax + k] = v3;
+        }
       }
     }
     __syncthreads();
@@ -2685,7 +2700,7 @@ __global__ void resample_push_kernel(PushArgs a) {
 #define MBOX_SLOTS 4
 #define MBOX_WORDS 16
 #define MBOX_PAYLOAD 15
-#define MBOX_TIMEOUT_NS 8000000000ull
+#define MBOX_TIMEOUT_NS 120000000000ull   /* 120 s: ranks may reach their first exchange seconds apart (scene loading) */
 struct MboxPeers { unsigned long long* box[PHD_MAX_PEERS]; };   /* mailbox region of every rank (own and mapped) */
 __device__ __forceinline__ unsigned long long global_timer_ns() {
   unsigned long long t;
