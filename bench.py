@@ -67,6 +67,18 @@ def alg_bytes_per_update(C, M, n_card=0):
     return (28.0 * C + 28.0 * (C * (M + 1) + M) + 32.0 + 8.0 * n_card) / (C * M)
 
 
+def workload_config(name, wl, n_gpus):
+    """the `config` object of a bench line: the same on both arms (what the workload is, not how a run went)"""
+    strong = bool(wl.get("strong"))
+    per = wl["P"] // n_gpus if strong else wl["P"]
+    return {"workload": name, "particles_per_gpu": per, "particles_total": wl["P"] if strong else wl["P"] * n_gpus,
+            "components": wl["C"], "measurements": wl["M"], "filter": "CPHD" if wl.get("filter_type") == 1 else "PHD",
+            "scaling": "strong" if strong else "weak",
+            # timing rule: no L2 flush between the timed steps because every step's inputs and outputs exceed the 126 MB L2
+            "cache": "inputs larger than L2 (map %.0f MB + dense update terms %.1f GB per step per GPU)"
+                     % (per * wl["C"] * 24 / 1e6, per * (wl["C"] * (wl["M"] + 1) + wl["M"]) * 28 / 1e9)}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -282,9 +294,8 @@ def run_reference(args, wl):
         "impl": "reference", "metric": "GM-PHD updates/s (particle x comp x meas)", "value": value, "unit": "updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "particles_per_gpu": wl["P"], "components": C, "measurements": M,
-                   "filter": "CPHD" if wl.get("filter_type") == 1 else "PHD",
-                   "note": "CPU oracle port of the reference algorithm (its scphd_cpu.cpp is an empty stub); bounded sample"},
+        "config": workload_config(args.workload, wl, args.gpus),
+        "run": {"note": "CPU oracle port of the reference algorithm (its scphd_cpu.cpp is an empty stub); bounded sample"},
         "cpu_baseline": {"value": value, "unit": "updates/s", "cores": threads, "kind": "port", "sample": sample,
                          "single_thread_value": r1},
         "e2e": {"value": value, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -466,7 +477,10 @@ def run_ours(args, wl):
             if world == 1 and sampler.n_samples() >= 10:
                 break
     clocks = sampler.stop() if rank == 0 else None
-    production = time_production_mode(filt, cfg, u, Z, args, barrier, stream, torch, dist if world > 1 else None)
+    try:
+        production = time_production_mode(filt, cfg, u, Z, args, barrier, stream, torch, dist if world > 1 else None)
+    except Exception as e:       # the extra key must never cost the headline line (every rank takes the same path)
+        production = {"error": str(e)[:200]}
     exchange_check = check_exchange(filt, u, Z, P_total, torch, dist) if world > 1 else None
     launches = l_timed - l0
     # restore() launches no kernels (cudaMemcpyAsync only), so `launches` counts the timed steps' kernels
@@ -533,12 +547,9 @@ def run_ours(args, wl):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "particles_per_gpu": P, "particles_total": P_total,
-                   "distinct_particles_per_gpu": n_scene, "components": C, "measurements": M,
-                   "filter": "CPHD" if wl.get("filter_type") == 1 else "PHD", "update_mode": "dense (reference-equivalent update terms materialised in HBM)",
-                   "cache": "inputs larger than L2 (map %.0f MB + dense update terms %.1f GB per step)"
-                            % (P * C * 24 / 1e6, P * (C * (M + 1) + M) * 28 / 1e9),
-                   "steps_that_resampled": n_resampled},
+        "config": workload_config(args.workload, wl, world),
+        "run": {"update_mode": "dense (reference-equivalent update terms materialised in HBM)",
+                "distinct_particles_per_gpu": n_scene, "steps_that_resampled": n_resampled},
         "filter_steps_per_s": 1e3 / ms_per_step,
         "phase_ms": {"update": upd, "merge": float(np.mean(mrg_ms)), "predict": float(oth[0]), "weights": float(oth[1]),
                      "estimate": float(oth[2]), "resample": float(oth[3])},

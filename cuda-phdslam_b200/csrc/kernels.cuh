@@ -521,6 +521,8 @@ __device__ void cphd_block(const DevCfg& c, int C, int M, const float* __restric
   const float lcr = phd_safe_log(c.clutter_rate), lcd = phd_safe_log(c.clutter_density);
   const float larea = lcr - lcd;
 
+  __shared__ int s_kmax;                 /* last birth cardinality whose probability is not exactly zero */
+  if (tid == 0) s_kmax = 0;
   for (int k = tid; k < nlf; k += UPD_THREADS) s_lf[k] = lfact[k];
   for (int n = tid; n < N1; n += UPD_THREADS) s_psi[n] = phd_expf(card[n]); /* prior pmf (linear); becomes Psi0 below */
   for (int m = tid; m < M; m += UPD_THREADS) s_llam[m] = phd_safe_log(s_S[m] + wb) + larea;   /* :1539-1552 */
@@ -539,7 +541,9 @@ __device__ void cphd_block(const DevCfg& c, int C, int M, const float* __restric
     t = t - s_lf[M - k];
     t = t + cphd_mulk(k, lwb);
     t = t + cphd_mulk(M - k, l1wb);
-    s_pb[k] = phd_expf(t);                                                  /* birth pmf (linear) */
+    const float pbk = phd_expf(t);
+    s_pb[k] = pbk;                                                          /* birth pmf (linear) */
+    if (pbk != 0.0f) atomicMax(&s_kmax, k);
     s_cK[k] = cphd_mulk(k, lcr) - c.clutter_rate;
   }
   if (warp == 0) {
@@ -553,9 +557,12 @@ __device__ void cphd_block(const DevCfg& c, int C, int M, const float* __restric
   const float lq = s_sc[0], lW = s_sc[1], lmax = s_sc[2];
   /* predicted cardinality (:880-887): the reference's plain sum of exp(birth(n-j) + prior(j)), evaluated as the
    * convolution of the two pmfs (N1 + M + 1 exponentials instead of N1 (M + 1)); the terms with n-j > M are exactly 0 */
+  /* Binomial(M, w_b) underflows to an exact zero a few births beyond its mode (k > 12 at w_b = 1e-4, M = 50): those terms
+   * add fma(0, p, sum) = sum, so leaving them out changes no bit of the sum (the oracle runs the full loop) */
+  const int kmax = s_kmax;
   for (int n = tid; n < N1; n += UPD_THREADS) {
     float sum = 0.0f;
-    for (int j = max(0, n - M); j <= n; ++j) sum = fmaf(s_pb[n - j], s_psi[j], sum);
+    for (int j = max(0, n - kmax); j <= n; ++j) sum = fmaf(s_pb[n - j], s_psi[j], sum);
     s_pm[n] = phd_safe_log(sum);
   }
   for (int m = tid; m < M; m += UPD_THREADS) s_x[m] = (double)phd_expf(s_llam[m] - lmax);
@@ -616,44 +623,50 @@ __device__ void cphd_block(const DevCfg& c, int C, int M, const float* __restric
    * by composite deflation, e'_k = e_k - x_m e'_(k-1) forward up to the crossover ks (first k with e_(k+1) <= x_m e_k),
    * backward from the top beyond it, O(M) per measurement instead of the reference's O(M^2) recomputation (:1577-1616);
    * one thread per measurement, the products with g[j] accumulated on the fly (oracle: cphd_factors, the same operations) */
-  for (int m = tid; m < M; m += UPD_THREADS) {
-    const double xm = s_x[m];
-    const double r = (xm > 0.0) ? 1.0 / xm : 0.0;
-    int ks = M;                                   /* first k with e_(k+1) <= x_m e_k; no early exit: the loads pipeline */
-    if (xm > 0.0)
-      for (int k = M - 1; k >= 0; --k)
-        if (s_ef[k + 1] <= xm * s_ef[k]) ks = k;
-    /* forward (k < ks) and backward (k >= ks) recursions are independent: one loop, two dependency chains */
-    double accf = 0.0, accb = 0.0, f = 1.0, b = s_ef[M] * r;
-    const int nb = M - ks, nmax = max(ks, nb);
-    for (int i = 0; i < nmax; ++i) {
-      if (i < ks) {
-        if (i > 0) f = __fma_rn(-xm, f, s_ef[i]);
-        accf = __fma_rn(s_g[i], f, accf);
+  /* The deflation is one serial recursion per measurement and keeps two warps busy for ~M dependent double FMAs; everything
+   * else that is left -- Psi0(n), <Psi0,p>, <Psi1,p> -- runs UNDER it on the other six warps (their own named barrier between
+   * the Psi0 table and the log-sum-exp that reads it) instead of behind it. */
+  if (warp < 2) {
+    for (int m = tid; m < M; m += 64) {
+      const double xm = s_x[m];
+      const double r = (xm > 0.0) ? 1.0 / xm : 0.0;
+      int ks = M;                                   /* first k with e_(k+1) <= x_m e_k; no early exit: the loads pipeline */
+      if (xm > 0.0)
+        for (int k = M - 1; k >= 0; --k)
+          if (s_ef[k + 1] <= xm * s_ef[k]) ks = k;
+      /* forward (k < ks) and backward (k >= ks) recursions are independent: one loop, two dependency chains */
+      double accf = 0.0, accb = 0.0, f = 1.0, b = s_ef[M] * r;
+      const int nb = M - ks, nmax = max(ks, nb);
+      for (int i = 0; i < nmax; ++i) {
+        if (i < ks) {
+          if (i > 0) f = __fma_rn(-xm, f, s_ef[i]);
+          accf = __fma_rn(s_g[i], f, accf);
+        }
+        if (i < nb) {
+          const int k = M - 1 - i;
+          if (i > 0) b = (s_ef[k + 1] - b) * r;
+          accb = __fma_rn(s_g[k], b, accb);
+        }
       }
-      if (i < nb) {
-        const int k = M - 1 - i;
-        if (i > 0) b = (s_ef[k + 1] - b) * r;
-        accb = __fma_rn(s_g[k], b, accb);
-      }
+      const double acc = accf + accb;
+      s_ip1d[m] = cphd_clamp((float)((double)cphd_logd(acc) + (double)gmax));
     }
-    const double acc = accf + accb;
-    s_ip1d[m] = cphd_clamp((float)((double)cphd_logd(acc) + (double)gmax));
-  }
-  /* Psi0(n) (:1686-1703) = n! / (s <1,w>)^n * sum_j a[j] d[n-j], a[j] = exp(cK[M-j] + le[j] + j log s - amax) */
-  for (int n = tid; n < N1; n += UPD_THREADS) {
-    const int stop = min(n, M);
-    double sum = 0.0;
-    for (int j = 0; j <= stop; ++j) sum = __fma_rn(s_a[j], s_d[n - j], sum);
-    s_psi[n] = cphd_clamp((float)((((double)cphd_logd(sum) + (double)amax) + (double)s_lf[n]) - (double)n * lnc));
-  }
-  __syncthreads();
-  if (warp == 0) {        /* <Psi0, p> (:1717-1722) */
-    float v = cphd_lse_warp(N1, [&](int n) { return cphd_clamp(s_psi[n] + s_pm[n]); });
-    if (lane == 0) s_sc[3] = v;
-  } else if (warp == 1) { /* <Psi1, p> (:1706-1735) */
-    float v = cphd_lse_warp(M + 1, [&](int j) { return cphd_clamp((s_cK[M - j] + s_le[j]) + s_A1[j]); });
-    if (lane == 0) s_sc[4] = v;
+  } else {
+    /* Psi0(n) (:1686-1703) = n! / (s <1,w>)^n * sum_j a[j] d[n-j], a[j] = exp(cK[M-j] + le[j] + j log s - amax) */
+    for (int n = tid - 64; n < N1; n += UPD_THREADS - 64) {
+      const int stop = min(n, M);
+      double sum = 0.0;
+      for (int j = 0; j <= stop; ++j) sum = __fma_rn(s_a[j], s_d[n - j], sum);
+      s_psi[n] = cphd_clamp((float)((((double)cphd_logd(sum) + (double)amax) + (double)s_lf[n]) - (double)n * lnc));
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(UPD_THREADS - 64) : "memory");   /* the six Psi0 warps only */
+    if (warp == 2) {        /* <Psi0, p> (:1717-1722) */
+      float v = cphd_lse_warp(N1, [&](int n) { return cphd_clamp(s_psi[n] + s_pm[n]); });
+      if (lane == 0) s_sc[3] = v;
+    } else if (warp == 3) { /* <Psi1, p> (:1706-1735) */
+      float v = cphd_lse_warp(M + 1, [&](int j) { return cphd_clamp((s_cK[M - j] + s_le[j]) + s_A1[j]); });
+      if (lane == 0) s_sc[4] = v;
+    }
   }
   __syncthreads();
   const float ip0 = s_sc[3], ip1 = s_sc[4];
@@ -1824,6 +1837,7 @@ __device__ __forceinline__ void warp_exclusive_scan_u16(unsigned short* arr, int
 /* Block-wide stable LSD radix pass (8-bit digit) over the index list in -> out, keys in shared memory.
  * Warp w owns a contiguous slice of the input; per-warp digit histograms make the scatter stable.
  * TIE: the key is bitrev8(idx mod 256) (oracle: merge_tie_key).  Ends with a block barrier. */
+#define MF_RADIX_R 6         /* a warp's slice of up to 32 * MF_RADIX_R elements is held in registers across a pass */
 template <bool TIE>
 __device__ __forceinline__ void block_radix_pass(const unsigned* keys, const unsigned short* in, unsigned short* out, int n,
                                                  unsigned short* hist /* [MF_WARPS][256] */, int shift) {
@@ -1831,15 +1845,34 @@ __device__ __forceinline__ void block_radix_pass(const unsigned* keys, const uns
   const unsigned lt_mask = (1u << lane) - 1u;
   unsigned* h32 = reinterpret_cast<unsigned*>(hist);
   for (int i = tid; i < MF_WARPS * 128; i += MF_THREADS) h32[i] = 0;
-  __syncthreads();
   const int per = (((n + MF_WARPS - 1) / MF_WARPS) + 31) & ~31;
   const int lo = min(warp * per, n), hi = min(lo + per, n);
   unsigned short* hw = hist + warp * 256;
-  for (int i = lo + lane; i < hi; i += 32) {
-    const unsigned idx = in[i];
-    const unsigned d = TIE ? (__brev(idx) >> 24) : ((keys[idx] >> shift) & 255u);
-    atomic_add_u16(hw, (int)d, 1u);        /* result unused: a fire-and-forget shared-memory reduction (measured: aggregating
+  /* (index, digit) of the slice's elements: loaded once, back to back, and used by the count AND the scatter */
+  const bool inreg = per <= 32 * MF_RADIX_R;
+  unsigned pk[MF_RADIX_R];
+  if (inreg) {
+#pragma unroll
+    for (int r = 0; r < MF_RADIX_R; ++r) {
+      const int i = lo + lane + 32 * r;
+      pk[r] = (i < hi) ? (unsigned)in[i] : 0xffffffffu;
+    }
+#pragma unroll
+    for (int r = 0; r < MF_RADIX_R; ++r)
+      if (pk[r] != 0xffffffffu) pk[r] |= (TIE ? (__brev(pk[r]) >> 24) : ((keys[pk[r]] >> shift) & 255u)) << 16;
+  }
+  __syncthreads();
+  if (inreg) {
+#pragma unroll
+    for (int r = 0; r < MF_RADIX_R; ++r)
+      if (pk[r] != 0xffffffffu) atomic_add_u16(hw, (int)(pk[r] >> 16), 1u);
+  } else {
+    for (int i = lo + lane; i < hi; i += 32) {
+      const unsigned idx = in[i];
+      const unsigned d = TIE ? (__brev(idx) >> 24) : ((keys[idx] >> shift) & 255u);
+      atomic_add_u16(hw, (int)d, 1u);      /* result unused: a fire-and-forget shared-memory reduction (measured: aggregating
                                               equal digits with match_any first is slower -- a dependent load/store chain) */
+    }
   }
   __syncthreads();
   if (warp == 0) {
@@ -1872,21 +1905,39 @@ __device__ __forceinline__ void block_radix_pass(const unsigned* keys, const uns
     }
   }
   __syncthreads();
-  for (int b0 = lo; b0 < hi; b0 += 32) {
-    const int i = b0 + lane;
-    unsigned idx = 0, d = 0x80000000u | (unsigned)lane;   /* inactive lanes: unique keys */
-    if (i < hi) {
-      idx = in[i];
-      d = TIE ? (__brev(idx) >> 24) : ((keys[idx] >> shift) & 255u);
+  if (inreg) {
+#pragma unroll
+    for (int r = 0; r < MF_RADIX_R; ++r) {
+      if (lo + 32 * r >= hi) break;                       /* warp-uniform */
+      const bool valid = pk[r] != 0xffffffffu;
+      const unsigned idx = pk[r] & 0xffffu;
+      const unsigned d = valid ? (pk[r] >> 16) : (0x80000000u | (unsigned)lane);   /* inactive lanes: unique keys */
+      const unsigned same = __match_any_sync(FULL_MASK, d);
+      const unsigned before = valid ? hw[d] : 0u;
+      __syncwarp();
+      if (valid) {
+        out[before + __popc(same & lt_mask)] = (unsigned short)idx;
+        if ((same & lt_mask) == 0) hw[d] = (unsigned short)(before + __popc(same));
+      }
+      __syncwarp();
     }
-    const unsigned same = __match_any_sync(FULL_MASK, d);
-    const unsigned before = (i < hi) ? hw[d] : 0u;
-    __syncwarp();
-    if (i < hi) {
-      out[before + __popc(same & lt_mask)] = (unsigned short)idx;
-      if ((same & lt_mask) == 0) hw[d] = (unsigned short)(before + __popc(same));
+  } else {
+    for (int b0 = lo; b0 < hi; b0 += 32) {
+      const int i = b0 + lane;
+      unsigned idx = 0, d = 0x80000000u | (unsigned)lane;   /* inactive lanes: unique keys */
+      if (i < hi) {
+        idx = in[i];
+        d = TIE ? (__brev(idx) >> 24) : ((keys[idx] >> shift) & 255u);
+      }
+      const unsigned same = __match_any_sync(FULL_MASK, d);
+      const unsigned before = (i < hi) ? hw[d] : 0u;
+      __syncwarp();
+      if (i < hi) {
+        out[before + __popc(same & lt_mask)] = (unsigned short)idx;
+        if ((same & lt_mask) == 0) hw[d] = (unsigned short)(before + __popc(same));
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
   __syncthreads();
 }

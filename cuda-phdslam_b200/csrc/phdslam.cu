@@ -729,7 +729,10 @@ static int classify_and_scan(phdslam* h, int M, bool worst_case_ok = false) {
   int rc = scan_u64(h, h->tpad, n, h->toff, &h->red->total_terms);
   if (rc) return rc;
   if (worst_case_ok) {
-    const unsigned long long tmax = (((unsigned long long)h->Cmax * (unsigned)(M + 1) + (unsigned)M) + 63ull) & ~63ull;
+    /* sized for the measurement count rounded up to a multiple of 64, so that a run whose sets grow from step to step
+     * does not re-allocate the dense buffer every time */
+    const unsigned Ma = (unsigned)std::min((M + 63) & ~63, PHD_MAX_MEAS);
+    const unsigned long long tmax = (((unsigned long long)h->Cmax * (Ma + 1) + Ma) + 63ull) & ~63ull;
     const unsigned long long bound = tmax * (unsigned long long)n;
     const unsigned long long budget_terms = h->cfg.update_buffer_bytes / (PHD_NPLANES * 4);
     if (bound <= (1ull << 28) && bound <= budget_terms &&

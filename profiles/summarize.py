@@ -20,7 +20,7 @@ for f in sorted(glob.glob(os.path.join(here, pre + "bench*.json"))):
     c, ph = l["config"], l["phase_ms"]
     ec = l.get("exchange_check")
     print("| %s | %s | %d | %s | %.2f | %.1f G | %.2f (%.3f) | %.2f | %.3f / %.3f / %.3f | %s | %s |" % (
-        os.path.basename(f), c["workload"], l["n_gpus"], "{:,}".format(c.get("particles_total", c["particles_per_gpu"] * l["n_gpus"])),
+        os.path.basename(f), c["workload"], l["n_gpus"], "{:,}".format(c.get("particles_total", c["particles_per_gpu"] * l.get("n_gpus", 1))),
         l["ms_per_step"], l["value"] / 1e9, ph["update"], l["roofline"]["frac"], ph["merge"], ph["weights"], ph["estimate"], ph["resample"],
         ("%.2f" % l["production"]["ms_per_step"]) if l.get("production") else "",
         ("ok, %d migrated" % ec["migrated_checked"]) if ec and ec.get("ok") else ("" if ec is None else "FAILED")))

@@ -64,7 +64,9 @@ def run(name, cfg, Z, U, impl, threads, max_steps):
             "particles": int(cfg.n_particles), "ms_per_step_mean": float(np.mean(ms)), "ms_per_step_median": float(np.median(ms)),
             "steps_per_s": float(1e3 / np.mean(ms)),
             "component_measurement_pairs_per_s": float(pairs / (np.sum(ms) * 1e-3)), "final_mean_map_size": float(np.mean(f.map_sizes)),
-            "measurements_per_step_mean": float(np.mean([len(z) for z in Z[:n_steps]])), "host_cores": os.cpu_count()}
+            "measurements_per_step_mean": float(np.mean([len(z) for z in Z[:n_steps]])), "host_cores": os.cpu_count(),
+            "slowest_steps": [(int(k), round(float(ms[k]), 3), len(Z[k])) for k in np.argsort(ms)[::-1][:8]],
+            "ms_per_step_mean_without_step0": float(np.mean(ms[1:])) if len(ms) > 1 else None}
     print(json.dumps(line))
     sys.stdout.flush()
 

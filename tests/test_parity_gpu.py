@@ -182,6 +182,28 @@ def test_step_loop_on_bundled_ackerman_data():
     assert_state_equal(g, o, "after 40 steps")
 
 
+def test_step_loop_configs0_complete_run():
+    """BASELINE configs[0] in full: all 331 steps of the bundled Ackerman scene at 256 particles -- every resampling decision,
+    every component count and every ancestor index of the run equal the oracle's"""
+    cfg = P.load_config(os.path.join(GOLDEN, "config_ackerman.cfg"))
+    cfg.set(n_particles=256, max_components=256, seed="7")
+    Z = P.load_measurements(os.path.join(DATA, "measurements_synth_ackerman.txt"))
+    U = P.load_controls(os.path.join(DATA, "controls_synth.txt"))
+    g = P.PhdSlam(cfg)
+    o = O.Oracle(cfg, threads=os.cpu_count() or 1)
+    n_res = 0
+    for k in range(len(Z)):
+        u = U[k - 1] if k > 0 else None
+        ge, gr = g.step(k, u, Z[k])
+        oe, orr = o.step(k, u, Z[k])
+        assert gr == orr, "resampling decision differs at step %d" % k
+        n_res += gr
+        assert (g.map_sizes == o.map_sizes).all(), "component counts differ at step %d" % k
+        assert (g.resample_idx == o.resample_idx).all(), "ancestors differ at step %d" % k
+    assert len(Z) == 331 and n_res > 20
+    assert_state_equal(g, o, "after the complete run")
+
+
 def test_step_loop_constant_velocity_data():
     """config #2 shape (reduced particle count for the CPU oracle): CV motion model on measurements_synth_cv"""
     cfg = P.load_config(os.path.join(GOLDEN, "config_ackerman.cfg"))
