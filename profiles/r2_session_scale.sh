@@ -1,0 +1,25 @@
+#!/bin/bash
+# round 2, weak-scaling lines of the headline shape with the FINAL kernels: N = 1, 2, 4, 8 on one 8-GPU box, plus configs[3] at N = 8
+TAG=${1:-r2m}
+OUT=gpurun_out
+mkdir -p $OUT
+run() { # N, name, args, port
+  if [ "$1" = "1" ]; then
+    timeout 600 python bench.py --gpus 1 $3 --no-cpu-baseline > $OUT/${TAG}_$2.json 2> $OUT/${TAG}_$2.err
+  else
+    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port $4 bench.py --gpus $1 $3 --no-cpu-baseline > $OUT/${TAG}_$2.json 2> $OUT/${TAG}_$2.err
+  fi
+  python - <<PY
+import json
+try:
+    l=json.loads(open("$OUT/${TAG}_$2.json").read().strip().split("\n")[-1])
+    print("$2", round(l["value"]/1e9,2), "G upd/s", round(l["ms_per_step"],3), "ms", {k:round(v,3) for k,v in l["phase_ms"].items()}, (l.get("exchange_check") or {}).get("ok"), round(l["production"]["ms_per_step"],3))
+except Exception as e:
+    print("$2 FAILED", e); print(open("$OUT/${TAG}_$2.err").read()[-1200:])
+PY
+}
+run 1 bench_n1 "--steps 10 --warmup 3" 29540
+run 2 bench_n2 "--steps 10 --warmup 3" 29541
+run 4 bench_n4 "--steps 10 --warmup 3" 29542
+run 8 bench_n8 "--steps 10 --warmup 3" 29543
+run 8 bench_n8_cphd "--workload synthetic_131072x128x50_cphd --steps 5 --warmup 3" 29544
