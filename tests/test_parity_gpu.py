@@ -499,6 +499,40 @@ def test_full_size_step_matches_oracle_on_a_particle_subset():
     assert (g.map_sizes == sizes[anc]).all()
 
 
+@pytest.mark.parametrize("Pn,C,M,cphd", [(131072, 128, 50, True), (65536, 128, 100, False)])
+def test_full_size_shapes_of_configs3_and_configs4_on_a_particle_subset(Pn, C, M, cphd):
+    """BASELINE configs[3]'s per-GPU shard (131 072 x 128 x 50, CPHD with the cardinality distribution) and configs[4]'s
+    C x M shape (128 x 100, a quarter of its per-GPU particles at N = 8) at device scale: the oracle on 24 sampled
+    particles must reproduce their device maps (and cardinality rows) bit for bit, as in the configs[2] test above."""
+    extra = dict(filter_type=1, max_cardinality=255) if cphd else {}
+    cfg = S.scene_config(Pn, C, M, max_components=256, **extra)
+    sc = S.make_scene(Pn, C, M, seed=0)
+    g = P.PhdSlam(cfg)
+    S.load_scene(g, sc)
+    g.phdUpdateSynth(sc["Z"])
+    sizes, maps = g.get_maps()
+    w = g.log_weights.astype(np.float64)
+    assert abs(np.exp(w).sum() - 1.0) < 1e-4
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    pick = np.r_[0:8, Pn // 2:Pn // 2 + 8, Pn - 8:Pn]
+    sub_cfg = S.scene_config(len(pick), C, M, max_components=256, **extra)
+    o = O.Oracle(sub_cfg, threads=os.cpu_count() or 1)
+    o.poses = sc["poses"][pick]
+    o.log_weights = sc["log_weights"][pick]
+    n_all = len(sc["maps"]) // Pn
+    o.set_maps(sc["sizes"][pick], np.concatenate([sc["maps"][p * n_all:(p + 1) * n_all] for p in pick]))
+    o.phdUpdateSynth(sc["Z"])
+    os_, om = o.get_maps()
+    assert (os_ == sizes[pick]).all()
+    gm = np.concatenate([maps[off[p]:off[p + 1]] for p in pick])
+    assert gm.tobytes() == om.tobytes(), "maps of the sampled particles are expected to be bit-identical"
+    if cphd:
+        assert g.cardinalities[pick].tobytes() == o.cardinalities.tobytes()
+    ow = o.log_weights.astype(np.float64)
+    gw = w[pick]
+    np.testing.assert_allclose((gw - gw[0]), (ow - ow[0]), rtol=1e-4, atol=2e-4)
+
+
 @pytest.mark.parametrize("cphd", [False, True])
 def test_update_modes_agree(cphd):
     """update_mode = 1 (the fused update emits only the prune survivors; production mode, bench.py's `production` key) gives
