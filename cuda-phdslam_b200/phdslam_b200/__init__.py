@@ -370,6 +370,28 @@ class PhdSlam(object):
                                      C.byref(res)))
         return e, bool(res.value)
 
+    def save_particles(self, directory, t, map_estimates=True):
+        """The reference's per-step particle dump (writeParticlesMat, src/main.cpp:594-713: `particles%05d.mat` with the
+        struct fields states, weights, resample_idx, maps_static {weights, means, covs}, max_map_static, exp_map_static)
+        as `particles%05d.npz`.  Maps are concatenated particle after particle; `map_offsets[i]:map_offsets[i+1]` is
+        particle i's map.  (The reference never writes the covariances -- its `ptr_covs` stays NULL, :553 -- this does;
+        the dynamic-map fields of the mixed feature model are absent: that model is not built.)"""
+        sizes, maps = self.get_maps()
+        p = self.poses
+        out = {"states": np.stack([p[f] for f in POSE_DTYPE.names], 1), "weights": self.log_weights,
+               "resample_idx": self.resample_idx, "map_offsets": np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64),
+               "maps_static.weights": maps["weight"], "maps_static.means": maps["mean"], "maps_static.covs": maps["cov"]}
+        if map_estimates:
+            for which, name in ((1, "max_map_static"), (2, "exp_map_static")):
+                if self.cfg.map_estimate & which:
+                    m = self.map_estimate(which, cap=1 << 16)
+                    out[name + ".weights"], out[name + ".means"], out[name + ".covs"] = m["weight"], m["mean"], m["cov"]
+        if self.cfg.filter_type == 1:
+            out["cardinalities"] = self.cardinalities
+        path = os.path.join(directory, "particles%05d.npz" % int(t))
+        np.savez_compressed(path, **out)
+        return path
+
     def particle_checksums(self):
         """one uint64 per local particle over pose, map and cardinality: an offspring's equals its ancestor's"""
         out = np.zeros(self.n_local, dtype=np.uint64)

@@ -558,3 +558,24 @@ def test_update_modes_agree(cphd):
     o.phdPredict(np.float32([1.0, 0.05]))
     o.phdUpdateSynth(sc["Z"])
     assert_state_equal(g, o, "update_mode 1")
+
+
+def test_particle_dump_npz(tmp_path):
+    """the reference's per-step particle dump (writeParticlesMat, src/main.cpp:594-713) as NPZ: every field round-trips"""
+    Pn, C, M = 12, 20, 8
+    cfg = S.scene_config(Pn, C, M, max_components=128, map_estimate=3)
+    sc = S.make_scene(Pn, C, M, seed=2, n_near=1, n_far=1)
+    g = P.PhdSlam(cfg)
+    S.load_scene(g, sc)
+    g.phdUpdateSynth(sc["Z"])
+    path = g.save_particles(str(tmp_path), 7)
+    assert os.path.basename(path) == "particles00007.npz"
+    d = np.load(path)
+    sizes, maps = g.get_maps()
+    assert (np.diff(d["map_offsets"]) == sizes).all()
+    assert d["maps_static.weights"].tobytes() == maps["weight"].tobytes() and d["maps_static.covs"].shape == (len(maps), 4)
+    assert d["maps_static.means"].tobytes() == maps["mean"].tobytes()
+    assert d["weights"].tobytes() == g.log_weights.tobytes() and d["states"].shape == (Pn, 6)
+    assert (d["resample_idx"] == np.arange(Pn)).all()
+    assert d["max_map_static.weights"].tobytes() == g.map_estimate(1)["weight"].tobytes()
+    assert len(d["exp_map_static.weights"]) == len(g.map_estimate(2, cap=8192))
