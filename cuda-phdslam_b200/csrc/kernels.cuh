@@ -2100,27 +2100,40 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
     unsigned short* ord = src;       /* rank -> candidate index; later the cluster ends */
     unsigned short* items = dst;     /* output slot of a seed */
 
-    /* ---- D. candidate records in rank order to the scratch buffer (stays in L1/L2) ---- */
+    /* ---- D. candidate records in rank order to the scratch buffer (stays in L1/L2).  While a record is in registers: is
+     * the candidate within the threshold of itself (it is, unless its covariance is degenerate)?  Its mean is staged in
+     * shared memory (the tail of the near-pair pool, free until the pair phase) for the grid of phase E. ---- */
+    const float gk = 0.515625f * c.min_sep;                   /* pair gate: |d|^2 <= gk * (lam_a + lam_b) */
+    float2* st_xy = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(pool) + 2 * (size_t)S);   /* [S], behind cellr */
     float tmax = 0.0f, xmin = FLT_MAX, xmax = -FLT_MAX, ymin = FLT_MAX, ymax = -FLT_MAX;
-    for (int r = tid; r < n; r += MF_THREADS) {
-      const int i = ord[r];
-      const int s = P1[i];
-      float4 r0, r1;
-      if (i < n1) {
-        r0 = cin[2 * s];
-        r1 = cin[2 * s + 1];
-      } else {
-        const float pxy = mp[4 * Cmax + s];
-        r0 = make_float4(mp[3 * Cmax + s], pxy, pxy, mp[5 * Cmax + s]);
-        r1 = make_float4(mp[1 * Cmax + s], mp[2 * Cmax + s], mp[s], 0.0f);
+    for (int rb = warp * 32; rb < n; rb += MF_THREADS) {      /* a warp covers 32 consecutive ranks: one selfbits word */
+      const int r = rb + lane;
+      bool self = false;
+      if (r < n) {
+        const int i = ord[r];
+        const int s = P1[i];
+        float4 r0, r1;
+        if (i < n1) {
+          r0 = cin[2 * s];
+          r1 = cin[2 * s + 1];
+        } else {
+          const float pxy = mp[4 * Cmax + s];
+          r0 = make_float4(mp[3 * Cmax + s], pxy, pxy, mp[5 * Cmax + s]);
+          r1 = make_float4(mp[1 * Cmax + s], mp[2 * Cmax + s], mp[s], 0.0f);
+        }
+        r1.w = dev_lambda_max(r0);
+        crec[2 * r] = r0;
+        crec[2 * r + 1] = r1;
+        P1[i] = (unsigned short)r;     /* candidate index -> rank */
+        st_xy[r] = make_float2(r1.x, r1.y);
+        tmax = fmaxf(tmax, r1.w);
+        xmin = fminf(xmin, r1.x); xmax = fmaxf(xmax, r1.x);
+        ymin = fminf(ymin, r1.y); ymax = fmaxf(ymax, r1.y);
+        self = 0.0f <= gk * (r1.w + r1.w) &&
+               dev_mahal(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y) < c.min_sep;
       }
-      r1.w = dev_lambda_max(r0);
-      crec[2 * r] = r0;
-      crec[2 * r + 1] = r1;
-      P1[i] = (unsigned short)r;     /* candidate index -> rank */
-      tmax = fmaxf(tmax, r1.w);
-      xmin = fminf(xmin, r1.x); xmax = fmaxf(xmax, r1.x);
-      ymin = fminf(ymin, r1.y); ymax = fmaxf(ymax, r1.y);
+      const unsigned sb = __ballot_sync(FULL_MASK, self);
+      if (lane == 0) selfbits[rb >> 5] = sb;
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
@@ -2134,7 +2147,7 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
       s_red[warp][0] = tmax; s_red[warp][1] = xmin; s_red[warp][2] = xmax; s_red[warp][3] = ymin; s_red[warp][4] = ymax;
     }
     for (int i = tid; i < MF_CELLS / 2; i += MF_THREADS) reinterpret_cast<unsigned*>(cend)[i] = 0;
-    for (int i = tid; i < (S >> 5); i += MF_THREADS) selfbits[i] = 0;
+    for (int i = ((n + 31) >> 5) + tid; i < (S >> 5); i += MF_THREADS) selfbits[i] = 0;  /* words beyond the last rank */
     __syncthreads();
 #pragma unroll
     for (int w = 0; w < MF_WARPS; ++w) {
@@ -2143,9 +2156,7 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
       ymin = fminf(ymin, s_red[w][3]); ymax = fmaxf(ymax, s_red[w][4]);
     }
 
-    /* ---- E. uniform grid over the candidate means, cell size >= the largest gate radius; gate records in cell order.
-     * Is every candidate within the threshold of itself (it is, unless its covariance is degenerate)? ---- */
-    const float gk = 0.515625f * c.min_sep;                   /* pair gate: |d|^2 <= gk * (lam_a + lam_b) */
+    /* ---- E. uniform grid over the candidate means, cell size >= the largest gate radius; gate records in cell order ---- */
     int G = 1;
     float cs = 1.0f;
     {
@@ -2159,39 +2170,57 @@ __global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
       }
     }
     unsigned short* cellr = reinterpret_cast<unsigned short*>(pool);   /* cell of every candidate (the pool is free until the pair phase) */
-    for (int r0 = warp * 32; r0 < n; r0 += MF_THREADS) {      /* a warp covers 32 consecutive ranks: one selfbits word */
-      const int r = r0 + lane;
-      bool self = false;
-      if (r < n) {
-        const float4 A0 = crec[2 * r], g = crec[2 * r + 1];
-        int cx = 0, cy = 0;
-        if (G > 1) {
-          cx = (int)((g.x - xmin) / cs);
-          cy = (int)((g.y - ymin) / cs);
-          cx = min(max(cx, 0), G - 1);
-          cy = min(max(cy, 0), G - 1);
-        }
-        const int cid = cy * MRG_GMAX + cx;
-        cellr[r] = (unsigned short)cid;
-        atomic_add_u16(cend, cid, 1u);
-        self = 0.0f <= gk * (g.w + g.w) &&
-               dev_mahal(A0.x, A0.y, A0.z, A0.w, g.x, g.y, A0.x, A0.y, A0.z, A0.w, g.x, g.y) < c.min_sep;
+    /* lambda_max of this thread's candidates for the second loop, requested now: the loads are in flight under the first
+     * loop, the cell scan and two barriers (up to MF_RADIX_R rounds; larger capacities load inside the loop) */
+    const bool lam_inreg = n <= MF_THREADS * MF_RADIX_R;
+    float lam[MF_RADIX_R];
+    if (lam_inreg) {
+#pragma unroll
+      for (int q = 0; q < MF_RADIX_R; ++q) {
+        const int r = tid + q * MF_THREADS;
+        lam[q] = (r < n) ? crec[2 * r + 1].w : 0.0f;
       }
-      const unsigned sb = __ballot_sync(FULL_MASK, self);
-      if (lane == 0) selfbits[r0 >> 5] = sb;
+    }
+    for (int r = tid; r < n; r += MF_THREADS) {
+      const float2 xy = st_xy[r];
+      int cx = 0, cy = 0;
+      if (G > 1) {
+        cx = (int)((xy.x - xmin) / cs);
+        cy = (int)((xy.y - ymin) / cs);
+        cx = min(max(cx, 0), G - 1);
+        cy = min(max(cy, 0), G - 1);
+      }
+      const int cid = cy * MRG_GMAX + cx;
+      cellr[r] = (unsigned short)cid;
+      atomic_add_u16(cend, cid, 1u);
     }
     __syncthreads();
     if (warp == 0) warp_exclusive_scan_u16(cend, MRG_NCELL, lane);        /* cell starts */
     __syncthreads();
-    for (int r = tid; r < n; r += MF_THREADS) {
-      const float4 g = crec[2 * r + 1];
-      const unsigned cid = cellr[r];
-      const unsigned pos = atomic_add_u16(cend, (int)cid, 1u);
-      Gc[pos] = make_float4(g.x, g.y, g.w, (float)r);
-      own[pos] = (unsigned short)cid;        /* the cell of every cell-order position, for the pair phase */
-      HD[r] = MF_NONE;
+    if (lam_inreg) {
+#pragma unroll
+      for (int q = 0; q < MF_RADIX_R; ++q) {
+        const int r = tid + q * MF_THREADS;
+        if (r < n) {
+          const float2 xy = st_xy[r];
+          const unsigned cid = cellr[r];
+          const unsigned pos = atomic_add_u16(cend, (int)cid, 1u);
+          Gc[pos] = make_float4(xy.x, xy.y, lam[q], (float)r);
+          own[pos] = (unsigned short)cid;      /* the cell of every cell-order position, for the pair phase */
+          HD[r] = MF_NONE;
+        }
+      }
+    } else {
+      for (int r = tid; r < n; r += MF_THREADS) {
+        const float2 xy = st_xy[r];
+        const unsigned cid = cellr[r];
+        const unsigned pos = atomic_add_u16(cend, (int)cid, 1u);
+        Gc[pos] = make_float4(xy.x, xy.y, crec[2 * r + 1].w, (float)r);
+        own[pos] = (unsigned short)cid;
+        HD[r] = MF_NONE;
+      }
     }
-    __syncthreads();                                       /* cend[c] is now the END of cell c */
+    __syncthreads();                                       /* cend[c] is now the END of cell c; st_xy is dead: the pool is free */
 
     /* ---- F. near pairs (:2802-2806).  Every unordered pair of candidates in neighbouring cells is gated once by the
      * Euclidean test, one lane per candidate (see the loop below).  Pairs that pass are compacted into a per-warp ring

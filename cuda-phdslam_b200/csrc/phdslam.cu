@@ -1144,6 +1144,7 @@ extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms,
   const int b = h->cur;
   unsigned long long total = 0, base = 0;
   std::vector<int> bounds;
+  std::vector<unsigned long long> totals_plan;
   if (h->world > 1) {
     /* every rank learns every rank's integer weight total: its CDF offset and the global total follow.  After an
      * estimate on the same weights the totals are already on the host (they rode on the estimate's exchange). */
@@ -1173,9 +1174,7 @@ extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms,
       phdslam_set_error("all particle weights are zero or NaN");
       return PHDSLAM_ERR_NAN;
     }
-    bounds.resize(h->world + 1);
-    rc = phdslam_plan_migration(h->world, totals.data(), n_new, uniforms, h->cfg.resample_mode, h->resample_calls, h->cfg.seed, bounds.data());
-    if (rc) return rc;
+    totals_plan = totals;        /* the migration is planned below, on the host, while the local gather runs */
   } else {
     if (h->totals_valid) {
       total = h->totals_host[0];            /* known since the estimate: no host round trip */
@@ -1200,6 +1199,12 @@ extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms,
                                                               h->count[b], h->count[b ^ 1], h->map[b], h->map[b ^ 1],
                                                               h->card[b], h->card[b ^ 1], h->Cmax, h->n_card, 0, nullptr);
   LAUNCH_CHECK(h);
+  if (h->world > 1) {
+    bounds.resize(h->world + 1);
+    rc = phdslam_plan_migration(h->world, totals_plan.data(), n_new, uniforms, h->cfg.resample_mode, h->resample_calls, h->cfg.seed,
+                                bounds.data());
+    if (rc) return rc;
+  }
   if (h->world > 1 && h->p2p) {
     /* NVLink exchange: for every peer d, the offspring interval d owns whose ancestors live here (both ends derive it
      * from `bounds`, nothing is negotiated) is searched on the local CDF and pushed by the gather kernel straight into
