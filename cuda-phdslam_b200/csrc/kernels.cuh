@@ -1942,7 +1942,7 @@ __device__ __forceinline__ void block_radix_pass(const unsigned* keys, const uns
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(MF_THREADS, 7) merge_fast_kernel(MrgArgs a) {
+__global__ void __launch_bounds__(MF_THREADS, 8) merge_fast_kernel(MrgArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float s_red[MF_WARPS][5];
   __shared__ int s_cnt2[MF_WARPS];
