@@ -142,6 +142,7 @@ int main(int argc, char** argv) {
   std::vector<int> ridx;
   std::vector<float> card((size_t)(cfg.filter_type == 1 ? n_card : 1)), all_card;
   std::vector<phdslam_gaussian2d_t> map_est(65536);
+  std::vector<phdslam_gaussian4d_t> dyn_est(1);
   float current_u[2] = {0.0f, 0.0f};                              /* main.cpp:1166-1168 */
   printf("STARTING SIMULATION\n");
   FILE* tf = fopen((out_dir + "/loopTime.log").c_str(), "w");     /* main.cpp:1300-1305 */
@@ -208,10 +209,21 @@ int main(int argc, char** argv) {
         n_map = 0;
       }
     }
+    /* mixed feature model: the dynamic map of the maximum-weight particle goes on line 3 of the 7-line layout
+     * (writeLog, main.cpp:885-900; run_synth passes particles.max_map_dynamic) */
+    int n_dyn = 0;
+    if (cfg.feature_model == 2 && (cfg.map_estimate & 1)) {
+      dyn_est.resize((size_t)cfg.max_components_dynamic + 8);
+      if (phdslam_map_estimate_dynamic(h, dyn_est.data(), (int)dyn_est.size(), &n_dyn) != 0) {
+        fprintf(stderr, "phdslam: dynamic map estimate failed: %s\n", phdslam_last_error());
+        n_dyn = 0;
+      }
+    }
     char name[64];
     snprintf(name, sizeof(name), "/state_estimate%05d.log", n);
-    CHECK(phdslam_write_log((out_dir + name).c_str(), cfg.log_layout, &est.expected_pose, map_est.data(), n_map, logw.data(),
-                            poses.data(), P, ridx.data(), cfg.filter_type == 1 ? card.data() : nullptr, n_card, cfg.filter_type));
+    CHECK(phdslam_write_log_mixed((out_dir + name).c_str(), cfg.log_layout, &est.expected_pose, map_est.data(), n_map,
+                                  dyn_est.data(), n_dyn, logw.data(), poses.data(), P, ridx.data(),
+                                  cfg.filter_type == 1 ? card.data() : nullptr, n_card, cfg.filter_type));
     /* the nEff test and resampleParticles (main.cpp:1281-1297) */
     if (rc == 0) {
       int rrc = phdslam_step_resample(h, M, &est, &resampled);

@@ -64,6 +64,11 @@ extern "C" void phdslam_config_defaults(phdslam_config_t* c) {
   c->seed = 0;
   c->update_mode = 0;
   c->update_buffer_bytes = 32ull << 30;
+  /* mixed feature model (main.cpp:990,1022-1025,1037-1038) */
+  c->ps = 0.98f;
+  c->tau = 0.0f;
+  c->beta = 1.0f;
+  c->max_components_dynamic = 64;
   c->clutter_density = c->clutter_rate / (2 * c->max_bearing * c->max_range);
 }
 
@@ -83,11 +88,10 @@ static bool parse_bool(const char* v, int* out) {
 /* Keys the reference parses that are not on this path (disparity camera, dynamic features, dead options).
  * Accepted and ignored so that the reference's cfg files load unchanged. */
 static const char* kIgnoredKeys[] = {
-    "debug", "initial_z", "initial_roll", "initial_pitch", "acc_z", "acc_roll", "acc_pitch", "ps", "gate_births",
+    "debug", "initial_z", "initial_roll", "initial_pitch", "acc_z", "acc_roll", "acc_pitch", "gate_births",
     "gate_measurements", "gate_threshold", "min_expected_feature_weight", "max_features", "daughter_mixture_type",
-    "n_samples", "cphd_disttype", "nu", "std_vx_features", "std_vy_features", "std_ax_features", "std_ay_features",
-    "cov_vx_birth", "cov_vy_birth", "std_u", "std_v", "disparity_birth", "image_width", "image_height", "std_d_birth",
-    "fx", "fy", "u0", "v0", "particles_per_feature", "tau", "beta", "save_all_maps", "save_prediction", nullptr};
+    "n_samples", "cphd_disttype", "nu", "std_vx_features", "std_vy_features", "std_u", "std_v", "disparity_birth", "image_width", "image_height", "std_d_birth",
+    "fx", "fy", "u0", "v0", "particles_per_feature", "save_all_maps", "save_prediction", nullptr};
 
 extern "C" int phdslam_config_set(phdslam_config_t* c, const char* key, const char* value) {
   std::string k(key);
@@ -129,6 +133,9 @@ extern "C" int phdslam_config_set(phdslam_config_t* c, const char* key, const ch
   /* extensions */
   I("measurement_fields", measurement_fields) I("max_components", max_components) I("resample_mode", resample_mode)
   I("update_mode", update_mode)
+  /* mixed feature model */
+  F("ps", ps) F("tau", tau) F("beta", beta) F("std_ax_features", std_ax_features) F("std_ay_features", std_ay_features)
+  F("cov_vx_birth", cov_vx_birth) F("cov_vy_birth", cov_vy_birth) I("max_components_dynamic", max_components_dynamic)
   if (k == "log_layout") {
     c->log_layout = (std::string(v) == "extended" || std::string(v) == "1") ? 1 : 0;
     return 0;
@@ -354,6 +361,14 @@ static void put(FILE* f, float v) { fprintf(f, "%g ", (double)v); }
 extern "C" int phdslam_write_log(const char* path, int layout, const phdslam_pose_t* e, const phdslam_gaussian2d_t* map,
                                  int n_map, const float* log_weights, const phdslam_pose_t* poses, int n_particles,
                                  const int* resample_idx, const float* cardinality, int n_card, int filter_type) {
+  return phdslam_write_log_mixed(path, layout, e, map, n_map, nullptr, 0, log_weights, poses, n_particles, resample_idx,
+                                 cardinality, n_card, filter_type);
+}
+
+extern "C" int phdslam_write_log_mixed(const char* path, int layout, const phdslam_pose_t* e, const phdslam_gaussian2d_t* map,
+                                       int n_map, const phdslam_gaussian4d_t* map_dynamic, int n_map_dynamic,
+                                       const float* log_weights, const phdslam_pose_t* poses, int n_particles,
+                                       const int* resample_idx, const float* cardinality, int n_card, int filter_type) {
   FILE* f = fopen(path, "w");
   if (!f) {
     phdslam_set_error(std::string("cannot write ") + path);
@@ -369,7 +384,14 @@ extern "C" int phdslam_write_log(const char* path, int layout, const phdslam_pos
     for (int i = 0; i < 4; ++i) put(f, map[n].cov[i]);
   }
   fputc('\n', f);
-  if (layout == 1) fputc('\n', f); /* dynamic map line of the 7-line layout (main.cpp:885-900): always empty here */
+  if (layout == 1) { /* dynamic map line of the 7-line layout, 21 numbers per Gaussian: weight mean[4] cov[16] (main.cpp:885-900) */
+    for (int n = 0; n < n_map_dynamic; ++n) {
+      put(f, map_dynamic[n].weight);
+      for (int i = 0; i < 4; ++i) put(f, map_dynamic[n].mean[i]);
+      for (int i = 0; i < 16; ++i) put(f, map_dynamic[n].cov[i]);
+    }
+    fputc('\n', f);
+  }
   /* particle log-weights (main.cpp:913-920) */
   for (int n = 0; n < n_particles; ++n) put(f, log_weights[n]);
   fputc('\n', f);

@@ -346,6 +346,11 @@ struct UpdArgs {
   const float* lfact;                  /* log-factorial table, PHD_LF_MAX entries */
   float* card;                         /* [n][n_card] log cardinality, updated in place */
   int write_card;                      /* 0 for the dense-terms query (state is not advanced) */
+  /* mixed feature model (update_mixed_kernel): what the dynamic features of the particle add to the per-measurement
+   * normaliser and to the predicted cardinality (dyn_pre_kernel), and the log normalisers handed back to them */
+  const float* mix_dsum;               /* [n][PHD_MAX_MEAS] */
+  const float* mix_nhat;               /* [n] */
+  float* mix_L;                        /* [n][PHD_MAX_MEAS] */
   DevCfg c;
 };
 
@@ -893,8 +898,8 @@ __device__ __forceinline__ float2 upd_measurement(const float2* __restrict__ rec
   return acc;
 }
 
-template <bool DENSE, bool CPHD>
-__global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
+template <bool DENSE, bool CPHD, bool MIXED>
+__device__ __forceinline__ void update_body(const UpdArgs& a) {
   extern __shared__ __align__(16) float smem[];
   const DevCfg& c = a.c;
   const int Cmax = c.Cmax;
@@ -1069,7 +1074,8 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
   /* predicted cardinality (:2133-2186) and, for scheme 1, the prior / non-detect weight sums */
   float card_predict = 0.0f, cn_predict = 0.0f, nd_sum = 0.0f;
   if (warp == 0) {
-    card_predict = warp_sum_array(s_tmp, C + M);
+    /* mixed model (phdUpdateKernelMixed, src/phdfilter.cu:2398-2446): the births do not count, the dynamic features do */
+    card_predict = MIXED ? (warp_sum_array(s_tmp, C) + a.mix_nhat[pl]) : warp_sum_array(s_tmp, C + M);
     if (c.particle_weighting == 1) {
       cn_predict = warp_sum_array(s_w, C);
       nd_sum = warp_sum_array(s_nd, C);
@@ -1164,9 +1170,12 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
         acc = upd_measurement<1, false, DENSE, true>(s_rec, C, zr2, zb2, dead, splat2(0.0f), D, even, c.min_w, lane, &s_ncand, cand, Smax, tbase_m, s_stash, cm);
       __syncwarp();                       /* lane 0's chunk maxima are read by the whole warp in pass 2 */
       float sum = warp_butterfly_sum(acc.x + acc.y);
+      if (MIXED) sum = sum + a.mix_dsum[(size_t)pl * PHD_MAX_MEAS + m];   /* :2461-2473 */
       sum = sum + c.clutter_density;
       sum = sum + c.birth_weight;
+      if (MIXED && !c.labeled) sum = sum + c.birth_weight;                /* two birth terms per unlabelled measurement, :2478-2480 */
       L = phd_safe_log(sum);
+      if (MIXED && lane == 0) a.mix_L[(size_t)pl * PHD_MAX_MEAS + m] = L;
       /* every lane reads back only what it stashed itself: no barrier between the passes */
       const float2 sc2 = splat2(phd_expf(-L));
       if (fast)
@@ -1229,6 +1238,16 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
     a.dlogw[pl] = out;
     a.n_cand[pl] = s_ncand;
   }
+}
+
+template <bool DENSE, bool CPHD>
+__global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
+  update_body<DENSE, CPHD, false>(a);
+}
+/* the static map of the mixed feature model (feature_model = 2; PHD only) */
+template <bool DENSE>
+__global__ void __launch_bounds__(UPD_THREADS) update_mixed_kernel(UpdArgs a) {
+  update_body<DENSE, false, true>(a);
 }
 
 /* =========================================================================================== */

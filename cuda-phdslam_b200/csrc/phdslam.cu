@@ -62,6 +62,7 @@ static bool load() {
 #define ncclGetErrorString nccl_rt::GetErrorString
 
 #include "kernels.cuh"
+#include "mixed.cuh"
 #include "phdslam_internal.h"
 
 #define CK(call)                                                                                     \
@@ -175,8 +176,15 @@ static int validate_config(const phdslam_config_t* c) {
     phdslam_set_error("n_particles and max_components must be >= 1");
     return PHDSLAM_ERR_INVALID;
   }
-  if (c->feature_model != 0) {
-    phdslam_set_error("feature_model != 0 (dynamic / mixed features) is outside the hot path");
+  if (c->feature_model != 0 && c->feature_model != 2) {
+    /* DYNAMIC_MODEL: the reference's update launch for it is commented out (src/phdfilter.cu:3663-3670) */
+    phdslam_set_error("feature_model must be 0 (static) or 2 (mixed: static + constant-velocity features)");
+    return PHDSLAM_ERR_INVALID;
+  }
+  if (c->feature_model == 2 && (c->filter_type != 0 || c->n_predict_particles != 1 || c->max_components_dynamic < 1 ||
+                                c->max_components_dynamic > 1024)) {
+    phdslam_set_error("feature_model = 2 needs filter_type = 0 (phdUpdateKernelMixed is a PHD update), n_predict_particles = 1 "
+                      "and 1 <= max_components_dynamic <= 1024");
     return PHDSLAM_ERR_INVALID;
   }
   if (c->n_predict_particles < 1 || c->n_predict_particles > 64) {
@@ -262,6 +270,9 @@ static void free_state(phdslam* h) {
   cudaFree(h->ancestors); cudaFree(h->red); cudaFree(h->cand); cudaFree(h->cand_in); cudaFree(h->n_cand); cudaFree(h->ovf_list);
   cudaFree(h->mig_map); cudaFree(h->mig_pose); cudaFree(h->mig_count); cudaFree(h->mig_anc); cudaFree(h->mig_card);
   cudaFree(h->mig_pose_in); cudaFree(h->totals_dev); cudaFree(h->lfact); cudaFree(h->mig_anc2);
+  for (int b = 0; b < 2; ++b) { cudaFree(h->dmap[b]); cudaFree(h->dcount[b]); h->dmap[b] = nullptr; h->dcount[b] = nullptr; }
+  cudaFree(h->mix_dsum); cudaFree(h->mix_nhat); cudaFree(h->mix_L); cudaFree(h->dcand); cudaFree(h->snap_dmap); cudaFree(h->snap_dcount);
+  h->mix_dsum = h->mix_nhat = h->mix_L = nullptr; h->dcand = nullptr; h->snap_dmap = nullptr; h->snap_dcount = nullptr;
   h->mig_pose_in = nullptr; h->totals_dev = nullptr; h->lfact = nullptr; h->mig_anc2 = nullptr; h->mig_anc_cap = 0;
   if (h->red_host) cudaFreeHost(h->red_host);
   if (h->z_host) cudaFreeHost(h->z_host);
@@ -329,6 +340,16 @@ static int alloc_state(phdslam* h) {
   CK(cudaMallocHost(&h->red_host, sizeof(Reductions)));
   CK(cudaMallocHost(&h->z_host, 3 * PHD_MAX_MEAS * sizeof(float)));
   CK(cudaMalloc(&h->lfact, PHD_LF_MAX * sizeof(float)));
+  if (h->Dmax) {
+    for (int b = 0; b < 2; ++b) {
+      CK(cudaMalloc(&h->dmap[b], n * DYN_PLANES * (size_t)h->Dmax * sizeof(float)));
+      CK(cudaMalloc(&h->dcount[b], n * sizeof(int)));
+    }
+    CK(cudaMalloc(&h->mix_dsum, n * PHD_MAX_MEAS * sizeof(float)));
+    CK(cudaMalloc(&h->mix_L, n * PHD_MAX_MEAS * sizeof(float)));
+    CK(cudaMalloc(&h->mix_nhat, n * sizeof(float)));
+    CK(cudaMalloc(&h->dcand, n * (size_t)h->Sd * sizeof(phdslam_gaussian4d_t)));
+  }
   return 0;
 }
 
@@ -351,6 +372,10 @@ static int init_particles(phdslam* h) {
     fill_kernel<<<cdiv((long long)n * h->n_card, 256), 256, 0, h->stream>>>(h->card[h->cur], n * h->n_card,
                                                                             -phd_logf((float)h->n_card));
     LAUNCH_CHECK(h);
+  }
+  if (h->Dmax) {
+    CK(cudaMemsetAsync(h->dcount[0], 0, (size_t)n * sizeof(int), h->stream));
+    CK(cudaMemsetAsync(h->dcount[1], 0, (size_t)n * sizeof(int), h->stream));
   }
   lfact_kernel<<<1, 32, 0, h->stream>>>(h->lfact, PHD_LF_MAX);
   LAUNCH_CHECK(h);
@@ -394,6 +419,10 @@ static int create_impl(phdslam* h, const phdslam_config_t* cfg, int device) {
   int smax = 1024; /* merge candidates per particle: survivors of the prune + nearly-in-range components */
   while (smax < 2 * h->Cmax + PHD_MAX_MEAS && smax < 4096) smax <<= 1;
   h->Smax = smax;
+  if (cfg->feature_model == 2) {
+    h->Dmax = (cfg->max_components_dynamic + 7) & ~7;
+    h->Sd = 4 * h->Dmax + PHD_MAX_MEAS;   /* prune survivors of one particle's dynamic update (more -> PHDSLAM_ERR_CAPACITY) */
+  }
   derive_devcfg(h->cfg, h->Cmax, &h->dc);
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 12; ++i) CK(cudaEventCreate(&h->ev[i]));
@@ -421,6 +450,12 @@ static int create_impl(phdslam* h, const phdslam_config_t* cfg, int device) {
     }
     CK(cudaFuncSetAttribute(update_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     CK(cudaFuncSetAttribute(update_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  }
+  if (h->Dmax) {
+    CK(cudaFuncSetAttribute(update_mixed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(h->Cmax)));
+    CK(cudaFuncSetAttribute(update_mixed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(h->Cmax)));
+    CK(cudaFuncSetAttribute(dyn_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem_bytes(h->Dmax)));
+    CK(cudaFuncSetAttribute(dyn_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem_bytes(h->Dmax)));
   }
   CK(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem_bytes(h->Smax)));
   {
@@ -470,8 +505,10 @@ extern "C" void phdslam_destroy(phdslam_t* h) {
 extern "C" int phdslam_set_config(phdslam_t* h, const phdslam_config_t* cfg) {
   if (cfg->n_particles != h->cfg.n_particles || ((cfg->max_components + 31) & ~31) != h->Cmax ||
       cfg->filter_type != h->cfg.filter_type || cfg->n_predict_particles != h->cfg.n_predict_particles ||
+      cfg->feature_model != h->cfg.feature_model ||
+      (cfg->feature_model == 2 && ((cfg->max_components_dynamic + 7) & ~7) != h->Dmax) ||
       (cfg->n_predict_particles > 1 && cfg->subdivide_predict != h->cfg.subdivide_predict)) {
-    phdslam_set_error("n_particles / max_components / filter_type / n_predict_particles are fixed at create time");
+    phdslam_set_error("n_particles / max_components / filter_type / n_predict_particles / feature_model are fixed at create time");
     return PHDSLAM_ERR_INVALID;
   }
   int rc = validate_config(cfg);
@@ -579,6 +616,10 @@ extern "C" int phdslam_dist_init(phdslam_t* h, int rank, int world, const void* 
     phdslam_set_error("libnccl.so.2 not found");
     return PHDSLAM_ERR_NCCL;
   }
+  if (h->cfg.feature_model == 2) {
+    phdslam_set_error("feature_model = 2 (mixed) is single-GPU: the dynamic maps are not part of the resampling exchange");
+    return PHDSLAM_ERR_INVALID;
+  }
   if (h->cfg.n_predict_particles > 1) {
     phdslam_set_error("n_predict_particles > 1 changes the particle count every step and is single-GPU only");
     return PHDSLAM_ERR_INVALID;
@@ -639,6 +680,10 @@ static int check_err_flag(phdslam* h) {
     phdslam_set_error("a particle's map exceeded max_components");
     return PHDSLAM_ERR_CAPACITY;
   }
+  if (h->red_host->err_flag & 8) {
+    phdslam_set_error("a particle's dynamic map (or its prune survivors) exceeded max_components_dynamic");
+    return PHDSLAM_ERR_CAPACITY;
+  }
   if (h->red_host->err_ranks) {   /* all-reduced with the weight sum: every rank leaves the step with the same status */
     phdslam_set_error("another rank's update exceeded its map / candidate capacity");
     return PHDSLAM_ERR_CAPACITY;
@@ -695,6 +740,14 @@ extern "C" int phdslam_predict(phdslam_t* h, const float* control, const double*
   CK(cudaEventRecord(h->ev[0], h->stream));
   predict_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->pose[h->cur], n, h->offset, v_enc, alpha, ddev, h->predict_calls, h->dc);
   LAUNCH_CHECK(h);
+  if (h->Dmax) {
+    /* predictMapMixed (src/phdfilter.cu:1240-1242, 965-1035): by the whole config.dt on every call, as the reference does */
+    const phdslam_config_t& c = h->cfg;
+    dyn_predict_kernel<<<cdiv((long long)n * h->Dmax, 256), 256, 0, h->stream>>>(
+        h->dmap[h->dcur], h->dcount[h->dcur], n, h->Dmax, c.dt, c.std_ax_features * c.std_ax_features,
+        c.std_ay_features * c.std_ay_features, c.ps, c.beta, c.tau);
+    LAUNCH_CHECK(h);
+  }
   CK(cudaEventRecord(h->ev[1], h->stream));
   h->predict_calls++;
   if (draws) CK(cudaStreamSynchronize(h->stream)); /* the caller may free `draws` on return */
@@ -809,7 +862,13 @@ static int launch_update_batch(phdslam* h, int M, int p0, int p1, unsigned long 
   a.z = h->z_dev; a.M = M; a.n = h->n_local; a.p0 = p0;
   a.toff = h->toff; a.tbase = tbase; a.dense = h->dense; a.n_in = h->n_in; a.dlogw = h->dlogw; a.c = h->dc;
   a.cand = h->cand_in + (size_t)(p0 - cand_p0) * h->Smax * 2; a.n_cand = h->n_cand; a.Smax = h->Smax;
-  if (h->n_card) {
+  a.mix_dsum = h->mix_dsum; a.mix_nhat = h->mix_nhat; a.mix_L = h->mix_L;
+  if (h->Dmax) {
+    if (dense)
+      update_mixed_kernel<true><<<p1 - p0, UPD_THREADS, update_smem_bytes(h->Cmax), h->stream>>>(a);
+    else
+      update_mixed_kernel<false><<<p1 - p0, UPD_THREADS, update_smem_bytes(h->Cmax), h->stream>>>(a);
+  } else if (h->n_card) {
     /* the fused mode keeps one chunk maximum per (measurement, 64-component chunk) behind the multi-object tables */
     const size_t sm = update_smem_bytes(h->Cmax) + cphd_smem_bytes(h->n_card, M) + (dense ? 0 : cphd_chunkmax_bytes(M, h->Cmax));
     if (dense)
@@ -849,6 +908,20 @@ static int launch_merge_batch(phdslam* h, int M, int p0, int p1, cudaStream_t st
   merge_kernel<<<cdiv(p1 - p0, MRG_WARPS), MRG_THREADS, merge_smem_bytes(h->Smax), st>>>(a);
   LAUNCH_CHECK(h);
   return 0;
+}
+
+/* mixed feature model: arguments of the dynamic-map kernels (csrc/mixed.cuh) */
+static DynArgs dyn_args(phdslam* h, int M) {
+  const phdslam_config_t& c = h->cfg;
+  DynArgs a;
+  a.dmap_in = h->dmap[h->dcur]; a.dcount_in = h->dcount[h->dcur];
+  a.dmap_out = h->dmap[h->dcur ^ 1]; a.dcount_out = h->dcount[h->dcur ^ 1];
+  a.pose = h->pose[h->cur]; a.z = h->z_dev; a.M = M; a.n = h->n_local; a.Dmax = h->Dmax; a.Sd = h->Sd;
+  a.dsum = h->mix_dsum; a.nhat = h->mix_nhat; a.L = h->mix_L; a.dlogw = h->dlogw; a.cand = h->dcand; a.red = h->red;
+  a.dt = c.dt; a.var_x = c.std_ax_features * c.std_ax_features; a.var_y = c.std_ay_features * c.std_ay_features;
+  a.ps = c.ps; a.beta = c.beta; a.tau = c.tau; a.cov_vx = c.cov_vx_birth; a.cov_vy = c.cov_vy_birth;
+  a.c = h->dc;
+  return a;
 }
 
 /* w += dw; normalise (src/phdfilter.cu:3735-3755) */
@@ -912,6 +985,10 @@ extern "C" int phdslam_update(phdslam_t* h, const float* z, int M, int fields) {
     CK(cudaStreamSynchronize(h->stream));
   }
   CK(cudaMemsetAsync(h->red, 0, sizeof(Reductions), h->stream));
+  if (h->Dmax) {   /* what the dynamic features add to the normalisers and the predicted cardinality of the static update */
+    dyn_pre_kernel<<<h->n_local, DYN_THREADS, dyn_smem_bytes(h->Dmax), h->stream>>>(dyn_args(h, M));
+    LAUNCH_CHECK(h);
+  }
   float upd_ms = 0, mrg_ms = 0;
   bool multi = bounds.size() > 2;
   if (overlap) {
@@ -957,11 +1034,16 @@ extern "C" int phdslam_update(phdslam_t* h, const float* z, int M, int fields) {
       upd_ms += t1; mrg_ms += t2;
     }
   }
+  if (h->Dmax) {   /* the dynamic map: update terms, prune, merge (after the static update wrote the normalisers) */
+    dyn_update_kernel<<<h->n_local, DYN_THREADS, dyn_smem_bytes(h->Dmax), h->stream>>>(dyn_args(h, M));
+    LAUNCH_CHECK(h);
+  }
   rc = update_weights(h, true);
   if (rc) return rc;
   CK(copy_d2h_async(h, h->red_host, h->red, sizeof(Reductions), h->stream));
   CK(cudaEventRecord(h->ev[6], h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  if (h->Dmax) h->dcur ^= 1;
   h->cur ^= 1; /* merged maps become the front buffer; poses and weights are single-buffered in place */
   /* pose planes are not touched by the update: keep the front pose buffer consistent with `cur` */
   std::swap(h->pose[0], h->pose[1]);
@@ -991,6 +1073,10 @@ extern "C" int phdslam_update(phdslam_t* h, const float* z, int M, int fields) {
 extern "C" int phdslam_update_terms(phdslam_t* h, const float* z, int M, int fields, phdslam_gaussian2d_t* terms_out,
                                     size_t cap, int* n_in_range_out, float* dlogw_out) {
   ENTER(h);
+  if (h->Dmax) {
+    phdslam_set_error("phdslam_update_terms: the dense-terms query covers the static feature model only");
+    return PHDSLAM_ERR_INVALID;
+  }
   if (M <= 0 || (fields != 2 && fields != 3)) return PHDSLAM_ERR_INVALID;
   if (M > PHD_MAX_MEAS) M = PHD_MAX_MEAS;
   int rc = upload_measurements(h, z, M, fields);
@@ -1199,6 +1285,11 @@ extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms,
                                                               h->count[b], h->count[b ^ 1], h->map[b], h->map[b ^ 1],
                                                               h->card[b], h->card[b ^ 1], h->Cmax, h->n_card, 0, nullptr);
   LAUNCH_CHECK(h);
+  if (h->Dmax) {   /* copy_particles carries maps_dynamic too (src/slamtypes.h:324) */
+    dyn_gather_kernel<<<n_off, 64, 0, h->stream>>>(h->ancestors, n_off, n, h->dmap[h->dcur], h->dcount[h->dcur],
+                                                   h->dmap[h->dcur ^ 1], h->dcount[h->dcur ^ 1], h->Dmax);
+    LAUNCH_CHECK(h);
+  }
   if (h->world > 1) {
     bounds.resize(h->world + 1);
     rc = phdslam_plan_migration(h->world, totals_plan.data(), n_new, uniforms, h->cfg.resample_mode, h->resample_calls, h->cfg.seed,
@@ -1317,6 +1408,7 @@ extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms,
     h->resample_timed = 0;
   }
   h->cur ^= 1;
+  if (h->Dmax) h->dcur ^= 1;
   h->resample_calls++;
   h->totals_valid = 0;
   if (h->mbox && (h->red_host->err_flag & 4)) {
@@ -1385,7 +1477,7 @@ extern "C" int phdslam_step(phdslam_t* h, int step_index, const float* control, 
  * resampling back to n_particles: src/phdfilter.cu:1185-1238, src/main.cpp:1286-1289); the drop-in shim needs this to
  * push a host particle set whose size differs from the device's. */
 extern "C" int phdslam_set_particle_count(phdslam_t* h, int n) {
-  if (h->world > 1 || n < 1 || n > h->n_cap) {
+  if (h->world > 1 || n < 1 || n > phdslam_particle_capacity(h)) {
     phdslam_set_error("phdslam_set_particle_count: single GPU only, 1 <= n <= particle capacity");
     return PHDSLAM_ERR_INVALID;
   }
@@ -1472,6 +1564,97 @@ extern "C" int phdslam_get_maps(phdslam_t* h, phdslam_gaussian2d_t* out, size_t 
   }
   return 0;
 }
+/* ---- mixed feature model: the dynamic maps (SynthSLAM::maps_dynamic), host-side transposition like the static ones ---- */
+static int need_mixed(const phdslam* h) {
+  if (h->Dmax) return 0;
+  phdslam_set_error("dynamic maps exist only with feature_model = 2");
+  return PHDSLAM_ERR_INVALID;
+}
+extern "C" int phdslam_get_map_sizes_dynamic(phdslam_t* h, int* out) {
+  ENTER(h);
+  if (need_mixed(h)) return PHDSLAM_ERR_INVALID;
+  CK(cudaStreamSynchronize(h->stream));
+  CK(copy_d2h(h, out, h->dcount[h->dcur], (size_t)h->n_local * sizeof(int)));
+  return 0;
+}
+extern "C" int phdslam_get_maps_dynamic(phdslam_t* h, phdslam_gaussian4d_t* out, size_t cap) {
+  ENTER(h);
+  if (need_mixed(h)) return PHDSLAM_ERR_INVALID;
+  const int n = h->n_local;
+  const size_t D = h->Dmax, per = (size_t)DYN_PLANES * D;
+  std::vector<int> cnt(n);
+  CK(cudaStreamSynchronize(h->stream));
+  CK(copy_d2h(h, cnt.data(), h->dcount[h->dcur], (size_t)n * sizeof(int)));
+  const size_t chunk = std::max<size_t>(1, (64u << 20) / (per * 4));
+  std::vector<float> buf(chunk * per);
+  size_t k = 0;
+  for (size_t p0 = 0; p0 < (size_t)n; p0 += chunk) {
+    const size_t np = std::min(chunk, (size_t)n - p0);
+    CK(copy_d2h(h, buf.data(), h->dmap[h->dcur] + p0 * per, np * per * 4));
+    for (size_t p = 0; p < np; ++p) {
+      const float* b = buf.data() + p * per;
+      for (int i = 0; i < cnt[p0 + p]; ++i) {
+        if (k >= cap) { phdslam_set_error("phdslam_get_maps_dynamic: output too small"); return PHDSLAM_ERR_INVALID; }
+        float* g = reinterpret_cast<float*>(&out[k++]);
+        for (int q = 0; q < DYN_PLANES; ++q) g[q] = b[(size_t)q * D + i];
+      }
+    }
+  }
+  return 0;
+}
+extern "C" int phdslam_set_maps_dynamic(phdslam_t* h, const int* sizes, const phdslam_gaussian4d_t* in) {
+  ENTER(h);
+  if (need_mixed(h)) return PHDSLAM_ERR_INVALID;
+  const int n = h->n_local;
+  const size_t D = h->Dmax, per = (size_t)DYN_PLANES * D;
+  for (int p = 0; p < n; ++p)
+    if (sizes[p] < 0 || (size_t)sizes[p] > D) {
+      phdslam_set_error("phdslam_set_maps_dynamic: a map exceeds max_components_dynamic");
+      return PHDSLAM_ERR_CAPACITY;
+    }
+  CK(cudaStreamSynchronize(h->stream));
+  const size_t chunk = std::max<size_t>(1, (64u << 20) / (per * 4));
+  std::vector<float> buf(chunk * per);
+  size_t k = 0;
+  for (size_t p0 = 0; p0 < (size_t)n; p0 += chunk) {
+    const size_t np = std::min(chunk, (size_t)n - p0);
+    std::fill(buf.begin(), buf.begin() + np * per, 0.0f);
+    for (size_t p = 0; p < np; ++p) {
+      float* b = buf.data() + p * per;
+      for (int i = 0; i < sizes[p0 + p]; ++i) {
+        const float* g = reinterpret_cast<const float*>(&in[k++]);
+        for (int q = 0; q < DYN_PLANES; ++q) b[(size_t)q * D + i] = g[q];
+      }
+    }
+    CK(copy_h2d(h, h->dmap[h->dcur] + p0 * per, buf.data(), np * per * 4));
+  }
+  CK(copy_h2d(h, h->dcount[h->dcur], sizes, (size_t)n * sizeof(int)));
+  return 0;
+}
+/* recoverSlamState: particles.max_map_dynamic = particles.maps_dynamic[max_idx] (src/main.cpp:359); the arg-max particle is
+ * the one the last phdslam_estimate found */
+extern "C" int phdslam_map_estimate_dynamic(phdslam_t* h, phdslam_gaussian4d_t* out, int cap, int* n_out_p) {
+  ENTER(h);
+  if (need_mixed(h)) return PHDSLAM_ERR_INVALID;
+  phdslam_estimate_t e;
+  int rc = phdslam_estimate(h, &e);
+  if (rc) return rc;
+  const int p = e.map_particle;
+  *n_out_p = 0;
+  if (p < 0 || p >= h->n_local) return 0;
+  const size_t D = h->Dmax, per = (size_t)DYN_PLANES * D;
+  int cnt = 0;
+  CK(copy_d2h(h, &cnt, h->dcount[h->dcur] + p, sizeof(int)));
+  std::vector<float> b(per);
+  CK(copy_d2h(h, b.data(), h->dmap[h->dcur] + (size_t)p * per, per * 4));
+  for (int i = 0; i < cnt && i < cap; ++i) {
+    float* g = reinterpret_cast<float*>(&out[i]);
+    for (int q = 0; q < DYN_PLANES; ++q) g[q] = b[(size_t)q * D + i];
+  }
+  *n_out_p = std::min(cnt, cap);
+  return 0;
+}
+
 static int set_maps_prefix(phdslam_t* h, int n, const int* sizes, const phdslam_gaussian2d_t* in);
 extern "C" int phdslam_set_maps(phdslam_t* h, const int* sizes, const phdslam_gaussian2d_t* in) {
   return set_maps_prefix(h, h->n_local, sizes, in);
@@ -1549,6 +1732,10 @@ extern "C" int phdslam_import_tiled(phdslam_t* h, int n_src, const phdslam_pose_
   ENTER(h);
   const int n = h->n_local;
   if (n_src < 1 || n_src > n) return PHDSLAM_ERR_INVALID;
+  if (h->Dmax) {
+    phdslam_set_error("phdslam_import_tiled: static feature model only");
+    return PHDSLAM_ERR_INVALID;
+  }
   CK(cudaStreamSynchronize(h->stream));
   const int b = h->cur;
   std::vector<float> plane(n_src);
@@ -1696,6 +1883,14 @@ extern "C" int phdslam_snapshot(phdslam_t* h) {
   CK(cudaMemcpy(h->snap_map, h->map[h->cur], n * PHD_MAP_PLANES * C * sizeof(float), cudaMemcpyDeviceToDevice));
   CK(cudaMemcpy(h->snap_logw, h->logw, n * sizeof(float), cudaMemcpyDeviceToDevice));
   if (h->n_card) CK(cudaMemcpy(h->snap_card, h->card[h->cur], n * h->n_card * sizeof(float), cudaMemcpyDeviceToDevice));
+  if (h->Dmax) {
+    if (!h->snap_dmap) {
+      CK(cudaMalloc(&h->snap_dmap, (size_t)h->n_cap * DYN_PLANES * h->Dmax * sizeof(float)));
+      CK(cudaMalloc(&h->snap_dcount, (size_t)h->n_cap * sizeof(int)));
+    }
+    CK(cudaMemcpy(h->snap_dmap, h->dmap[h->dcur], n * DYN_PLANES * (size_t)h->Dmax * sizeof(float), cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(h->snap_dcount, h->dcount[h->dcur], n * sizeof(int), cudaMemcpyDeviceToDevice));
+  }
   h->snap_predict_calls = h->predict_calls;
   h->snap_resample_calls = h->resample_calls;
   return 0;
@@ -1714,6 +1909,10 @@ extern "C" int phdslam_restore(phdslam_t* h) {
   CK(cudaMemcpyAsync(h->logw, h->snap_logw, n * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
   if (h->n_card)
     CK(cudaMemcpyAsync(h->card[h->cur], h->snap_card, n * h->n_card * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  if (h->Dmax && h->snap_dmap) {
+    CK(cudaMemcpyAsync(h->dmap[h->dcur], h->snap_dmap, n * DYN_PLANES * (size_t)h->Dmax * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->dcount[h->dcur], h->snap_dcount, n * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+  }
   h->predict_calls = h->snap_predict_calls;
   h->resample_calls = h->snap_resample_calls;
   if (h->tile_n) return tile_from_prefix(h, h->tile_n);     /* two kernels, outside any timed region of the caller */

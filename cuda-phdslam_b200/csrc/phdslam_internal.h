@@ -133,6 +133,14 @@ struct phdslam {
   unsigned long long totals_host[8];
   int* mig_anc2; size_t mig_anc_cap; /* ancestors of the offspring interval being pushed */
   float* lfact;                   /* log-factorial table for the CPHD terms (PHD_LF_MAX floats) */
+  /* mixed feature model (feature_model = 2; csrc/mixed.cuh): the dynamic maps, double buffered like the static ones */
+  int Dmax, Sd;                   /* per-particle capacity of the dynamic map / of its prune survivors */
+  int dcur;
+  float* dmap[2];                 /* [n_cap][21][Dmax] plane-SoA Gaussian4D components */
+  int* dcount[2];                 /* [n_cap] */
+  float* mix_dsum; float* mix_nhat; float* mix_L;   /* [n][256], [n], [n][256]: coupling of the two maps' updates */
+  phdslam_gaussian4d_t* dcand;    /* [n][Sd] */
+  float* snap_dmap; int* snap_dcount;
 };
 
 #endif

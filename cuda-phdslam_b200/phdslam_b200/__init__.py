@@ -22,6 +22,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "libphdslam.so")
 
 POSE_DTYPE = np.dtype([("px", "f4"), ("py", "f4"), ("ptheta", "f4"), ("vx", "f4"), ("vy", "f4"), ("vtheta", "f4")])
 GAUSSIAN_DTYPE = np.dtype([("cov", "f4", (4,)), ("mean", "f4", (2,)), ("weight", "f4")])
+GAUSSIAN4_DTYPE = np.dtype([("cov", "f4", (16,)), ("mean", "f4", (4,)), ("weight", "f4")])   # Gaussian4D (src/slamtypes.h:135-139)
 assert POSE_DTYPE.itemsize == 24 and GAUSSIAN_DTYPE.itemsize == 28
 
 
@@ -52,6 +53,10 @@ class Config(C.Structure):
         ("seed", C.c_ulonglong),
         ("update_mode", C.c_int),
         ("update_buffer_bytes", C.c_ulonglong),
+        ("ps", C.c_float), ("tau", C.c_float), ("beta", C.c_float),
+        ("std_ax_features", C.c_float), ("std_ay_features", C.c_float),
+        ("cov_vx_birth", C.c_float), ("cov_vy_birth", C.c_float),
+        ("max_components_dynamic", C.c_int),
     ]
 
     def set(self, **kw):
@@ -97,7 +102,8 @@ ABI_SYMBOLS = [
     "phdslam_set_cardinalities", "phdslam_update_terms", "phdslam_get_timings", "phdslam_stream",
     "phdslam_synchronize", "phdslam_set_overlap", "phdslam_dist_p2p", "phdslam_snapshot", "phdslam_restore", "phdslam_load_measurements",
     "phdslam_load_controls", "phdslam_load_timestamps", "phdslam_load_trajectory", "phdslam_plan_events", "phdslam_free",
-    "phdslam_write_log",
+    "phdslam_write_log", "phdslam_write_log_mixed",
+    "phdslam_get_map_sizes_dynamic", "phdslam_get_maps_dynamic", "phdslam_set_maps_dynamic", "phdslam_map_estimate_dynamic",
 ]
 
 _lib = None
@@ -145,6 +151,10 @@ def load_library(path=None):
     lib.phdslam_set_overlap.argtypes = [C.c_void_p, C.c_int]
     lib.phdslam_get_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     lib.phdslam_set_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.phdslam_get_map_sizes_dynamic.argtypes = [C.c_void_p, C.c_void_p]
+    lib.phdslam_get_maps_dynamic.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.phdslam_set_maps_dynamic.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.phdslam_map_estimate_dynamic.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.phdslam_update_terms.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     lib.phdslam_dist_unique_id.argtypes = [C.c_void_p]
     lib.phdslam_dist_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -375,7 +385,8 @@ class PhdSlam(object):
         struct fields states, weights, resample_idx, maps_static {weights, means, covs}, max_map_static, exp_map_static)
         as `particles%05d.npz`.  Maps are concatenated particle after particle; `map_offsets[i]:map_offsets[i+1]` is
         particle i's map.  (The reference never writes the covariances -- its `ptr_covs` stays NULL, :553 -- this does;
-        the dynamic-map fields of the mixed feature model are absent: that model is not built.)"""
+        with feature_model = 2 the dynamic maps follow as maps_dynamic.* / max_map_dynamic.* with `map_offsets_dynamic`;
+        exp_map_dynamic is not computed.)"""
         sizes, maps = self.get_maps()
         p = self.poses
         out = {"states": np.stack([p[f] for f in POSE_DTYPE.names], 1), "weights": self.log_weights,
@@ -388,6 +399,14 @@ class PhdSlam(object):
                     out[name + ".weights"], out[name + ".means"], out[name + ".covs"] = m["weight"], m["mean"], m["cov"]
         if self.cfg.filter_type == 1:
             out["cardinalities"] = self.cardinalities
+        if self.cfg.feature_model == 2:
+            dsz, dm = self.get_maps_dynamic()
+            out["map_offsets_dynamic"] = np.concatenate([[0], np.cumsum(dsz)]).astype(np.int64)
+            out["maps_dynamic.weights"], out["maps_dynamic.means"], out["maps_dynamic.covs"] = dm["weight"], dm["mean"], dm["cov"]
+            if map_estimates and (self.cfg.map_estimate & 1):
+                m = self.map_estimate_dynamic()
+                out["max_map_dynamic.weights"], out["max_map_dynamic.means"], out["max_map_dynamic.covs"] = (
+                    m["weight"], m["mean"], m["cov"])
         path = os.path.join(directory, "particles%05d.npz" % int(t))
         np.savez_compressed(path, **out)
         return path
@@ -494,6 +513,32 @@ class PhdSlam(object):
         maps = np.ascontiguousarray(maps, dtype=GAUSSIAN_DTYPE)
         assert len(sizes) == self.n_local and int(sizes.sum()) == len(maps)
         _check(self.lib.phdslam_set_maps(self._h, sizes.ctypes.data, maps.ctypes.data))
+
+    # ---- mixed feature model (feature_model = 2): SynthSLAM::maps_dynamic ----
+    @property
+    def map_sizes_dynamic(self):
+        out = np.zeros(self.n_local, dtype=np.int32)
+        _check(self.lib.phdslam_get_map_sizes_dynamic(self._h, out.ctypes.data))
+        return out
+
+    def get_maps_dynamic(self):
+        sizes = self.map_sizes_dynamic
+        out = np.zeros(int(sizes.sum()), dtype=GAUSSIAN4_DTYPE)
+        _check(self.lib.phdslam_get_maps_dynamic(self._h, out.ctypes.data, len(out)))
+        return sizes, out
+
+    def set_maps_dynamic(self, sizes, maps):
+        sizes = np.ascontiguousarray(sizes, dtype=np.int32)
+        maps = np.ascontiguousarray(maps, dtype=GAUSSIAN4_DTYPE)
+        assert len(sizes) == self.n_local and int(sizes.sum()) == len(maps)
+        _check(self.lib.phdslam_set_maps_dynamic(self._h, sizes.ctypes.data, maps.ctypes.data))
+
+    def map_estimate_dynamic(self, cap=4096):
+        """MAP estimate of the dynamic map (recoverSlamState: max_map_dynamic)."""
+        out = np.zeros(cap, dtype=GAUSSIAN4_DTYPE)
+        n = C.c_int()
+        _check(self.lib.phdslam_map_estimate_dynamic(self._h, out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value].copy()
 
     @property
     def resample_idx(self):

@@ -35,7 +35,7 @@ def scene_config_py(P, C, M, max_components=None, **overrides):
              resample_threshold=0.15, subdivide_predict=1, birth_weight=0.05, birth_noise_factor=1.5, min_separation=5.0,
              min_feature_weight=0.00001, particle_weighting=1, max_cardinality=256, filter_type=1, map_estimate=1,
              max_steps=10000, n_steps=-1, data_directory=b"data/", measurement_fields=2, max_components=256,
-             update_buffer_bytes=32 << 30)
+             update_buffer_bytes=32 << 30, ps=0.98, tau=0.0, beta=1.0, max_components_dynamic=64)
     kw = dict(
         motion_type=1, n_particles=P, filter_type=0, feature_model=0,
         max_range=15.0, max_bearing=3.141593, min_range=0.0, std_range=0.25, std_bearing=0.008727, pd=0.95,

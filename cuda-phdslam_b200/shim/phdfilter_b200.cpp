@@ -54,6 +54,9 @@ static phdslam_config_t to_cfg(const SlamConfig& c) { /* field for field, src/sl
   k.map_estimate = c.mapEstimate; k.feature_model = c.featureModel;
   k.l = c.l; k.h = c.h; k.a = c.a; k.b = c.b; k.std_encoder = c.stdEncoder; k.std_alpha = c.stdAlpha;
   k.labeled_measurements = c.labeledMeasurements;
+  /* mixed feature model (featureModel = MIXED_MODEL) */
+  k.ps = c.ps; k.tau = c.tau; k.beta = c.beta; k.std_ax_features = c.stdAxMap; k.std_ay_features = c.stdAyMap;
+  k.cov_vx_birth = c.covVxBirth; k.cov_vy_birth = c.covVyBirth;
   return k;
 }
 
@@ -114,6 +117,21 @@ static void push(SynthSLAM& p) {
   check(phdslam_set_poses(g_h, (const phdslam_pose_t*)&p.states[0]), "phdslam_set_poses");
   check(phdslam_set_log_weights(g_h, &p.weights[0]), "phdslam_set_log_weights");
   check(phdslam_set_maps(g_h, sizes.data(), flat.data()), "phdslam_set_maps");
+  if (config.featureModel == MIXED_MODEL) {   /* maps_dynamic travel like maps_static */
+    static_assert(sizeof(phdslam_gaussian4d_t) == sizeof(Gaussian4D), "Gaussian4D layout");
+    std::vector<int> dsizes;
+    std::vector<phdslam_gaussian4d_t> dflat;
+    for (int i = 0; i < n; ++i) {
+      dsizes.push_back((int)p.maps_dynamic[i].size());
+      for (size_t j = 0; j < p.maps_dynamic[i].size(); ++j) {
+        phdslam_gaussian4d_t g;
+        memcpy(&g, &p.maps_dynamic[i][j], sizeof(g));
+        dflat.push_back(g);
+      }
+    }
+    dflat.push_back(phdslam_gaussian4d_t());
+    check(phdslam_set_maps_dynamic(g_h, dsizes.data(), dflat.data()), "phdslam_set_maps_dynamic");
+  }
   if (config.filterType == CPHD_TYPE) {
     const size_t n1 = (size_t)config.maxCardinality + 1;
     std::vector<float> card((size_t)n * n1);
@@ -151,6 +169,19 @@ static void pull(SynthSLAM& p, bool take_resample_idx = false) {
   for (int i = 0; i < n; ++i) {
     p.maps_static[i].resize(sizes[i]);
     for (int j = 0; j < sizes[i]; ++j, ++k) memcpy(&p.maps_static[i][j], &flat[k], sizeof(Gaussian2D));
+  }
+  if (config.featureModel == MIXED_MODEL) {
+    std::vector<int> dsizes(n);
+    check(phdslam_get_map_sizes_dynamic(g_h, dsizes.data()), "phdslam_get_map_sizes_dynamic");
+    size_t dtotal = 0;
+    for (int i = 0; i < n; ++i) dtotal += (size_t)dsizes[i];
+    std::vector<phdslam_gaussian4d_t> dflat(dtotal + 1);
+    check(phdslam_get_maps_dynamic(g_h, dflat.data(), dtotal + 1), "phdslam_get_maps_dynamic");
+    size_t q = 0;
+    for (int i = 0; i < n; ++i) {
+      p.maps_dynamic[i].resize(dsizes[i]);
+      for (int j = 0; j < dsizes[i]; ++j, ++q) memcpy(&p.maps_dynamic[i][j], &dflat[q], sizeof(Gaussian4D));
+    }
   }
   if (config.filterType == CPHD_TYPE) {
     const size_t n1 = (size_t)config.maxCardinality + 1;

@@ -46,6 +46,14 @@ typedef struct phdslam_gaussian2d {
   float weight;
 } phdslam_gaussian2d_t;
 
+/* reference: Gaussian4D, src/slamtypes.h:135-139 (84 B; state x, y, vx, vy; cov column-major) -- a component of the
+ * dynamic map of the mixed feature model (feature_model = 2) */
+typedef struct phdslam_gaussian4d {
+  float cov[16];
+  float mean[4];
+  float weight;
+} phdslam_gaussian4d_t;
+
 /*
  * POD mirror of the live fields of the reference's SlamConfig
  * (src/slamtypes.h:142-250) with the defaults of loadConfig
@@ -77,7 +85,9 @@ typedef struct phdslam_config {
   int max_cardinality;
   int filter_type;                               /* 0 PHD, 1 CPHD */
   int map_estimate;                              /* bitmask: 1 = MAP map, 2 = EAP map (main.cpp:344,363) */
-  int feature_model;                             /* only 0 (static) is on the path */
+  int feature_model;                             /* 0 static; 2 mixed = static + constant-velocity features (the `--- mixed
+                                                    feature model ---` fields below); 1 (dynamic only: the reference's update
+                                                    launch for it is commented out, src/phdfilter.cu:3663-3670) -> INVALID */
   float l, h, a, b, std_encoder, std_alpha;      /* Ackerman vehicle */
   int labeled_measurements;
   int follow_trajectory;
@@ -92,6 +102,13 @@ typedef struct phdslam_config {
   unsigned long long seed;                       /* Philox key; the reference seeds mt19937 with time(0) */
   int update_mode;                               /* 0 = dense (reference-equivalent materialised update terms), 1 = fused */
   unsigned long long update_buffer_bytes;        /* cap on the dense update-term buffer; particles stream through it */
+  /* --- mixed feature model (feature_model = 2): reference keys ps, tau, beta, std_ax_features, std_ay_features,
+   * cov_vx_birth, cov_vy_birth (src/main.cpp:990,1022-1025,1037-1038); appended here so that the offsets above stay --- */
+  float ps;                                      /* survival probability of a dynamic feature */
+  float tau, beta;                               /* jump-Markov sigmoid: p = 1/(1 + exp(beta (tau - |v|))) */
+  float std_ax_features, std_ay_features;        /* white-acceleration noise of the constant-velocity feature model */
+  float cov_vx_birth, cov_vy_birth;              /* velocity variances of a dynamic birth term */
+  int max_components_dynamic;                    /* extension: per-particle capacity of the dynamic map */
 } phdslam_config_t;
 
 typedef struct phdslam phdslam_t;
@@ -205,6 +222,14 @@ int phdslam_get_resample_idx(phdslam_t* h, int* out);
 int phdslam_get_cardinalities(phdslam_t* h, float* out);
 int phdslam_set_cardinalities(phdslam_t* h, const float* in);
 
+/* Mixed feature model: the dynamic maps (reference: SynthSLAM::maps_dynamic, src/slamtypes.h:291), concatenated particle
+ * after particle like the static ones.  PHDSLAM_ERR_INVALID unless feature_model = 2. */
+int phdslam_get_map_sizes_dynamic(phdslam_t* h, int* out);
+int phdslam_get_maps_dynamic(phdslam_t* h, phdslam_gaussian4d_t* out, size_t cap);
+int phdslam_set_maps_dynamic(phdslam_t* h, const int* sizes, const phdslam_gaussian4d_t* in);
+/* MAP estimate of the dynamic map: the max-weight particle's (recoverSlamState, src/main.cpp:359) */
+int phdslam_map_estimate_dynamic(phdslam_t* h, phdslam_gaussian4d_t* out, int cap, int* n);
+
 /* One 64-bit checksum per local particle over what a resampled copy carries (src/slamtypes.h:313-333): pose, map size,
  * map components, CPHD cardinality row.  An offspring's checksum equals its ancestor's, whichever GPU owned the ancestor
  * (bench.py's exchange_check, tests/test_dist_gpu.py). */
@@ -279,6 +304,11 @@ void phdslam_free(void* p);
 int phdslam_write_log(const char* path, int layout, const phdslam_pose_t* expected, const phdslam_gaussian2d_t* map,
                       int n_map, const float* log_weights, const phdslam_pose_t* poses, int n_particles,
                       const int* resample_idx, const float* cardinality, int n_card, int filter_type);
+/* the same with the dynamic map estimate on line 3 of the 7-line layout (main.cpp:885-900; the 5-line layout has no such line) */
+int phdslam_write_log_mixed(const char* path, int layout, const phdslam_pose_t* expected, const phdslam_gaussian2d_t* map,
+                            int n_map, const phdslam_gaussian4d_t* map_dynamic, int n_map_dynamic, const float* log_weights,
+                            const phdslam_pose_t* poses, int n_particles, const int* resample_idx, const float* cardinality,
+                            int n_card, int filter_type);
 
 #ifdef __cplusplus
 }

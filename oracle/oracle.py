@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libphd_oracle.so")
 
 POSE_DTYPE = np.dtype([("px", "f4"), ("py", "f4"), ("ptheta", "f4"), ("vx", "f4"), ("vy", "f4"), ("vtheta", "f4")])
 GAUSSIAN_DTYPE = np.dtype([("cov", "f4", (4,)), ("mean", "f4", (2,)), ("weight", "f4")])
+GAUSSIAN4_DTYPE = np.dtype([("cov", "f4", (16,)), ("mean", "f4", (4,)), ("weight", "f4")])   # Gaussian4D, 84 B
 
 _lib = None
 
@@ -59,6 +60,16 @@ def load(path=None):
                   "oracle_set_cardinalities", "oracle_estimate"):
             getattr(lib, n).argtypes = [C.c_void_p, C.c_void_p]
         lib.oracle_set_threads.argtypes = [C.c_void_p, C.c_int]
+        for n in ("oracle_get_map_sizes_dynamic", "oracle_get_maps_dynamic"):
+            getattr(lib, n).argtypes = [C.c_void_p, C.c_void_p]
+        lib.oracle_set_maps_dynamic.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.oracle_mahalanobis4.restype = C.c_float
+        lib.oracle_mahalanobis4.argtypes = [C.c_void_p, C.c_void_p]
+        lib.oracle_merge4.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        lib.oracle_predict_feature4.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.oracle_mixed_terms.restype = C.c_float
+        lib.oracle_mixed_terms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                           C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.oracle_set_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.oracle_predict.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.oracle_update.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
@@ -230,6 +241,24 @@ class Oracle(object):
         self.lib.oracle_set_maps(self._h, sizes.ctypes.data, maps.ctypes.data)
 
     @property
+    def map_sizes_dynamic(self):
+        out = np.zeros(self.n, dtype=np.int32)
+        self.lib.oracle_get_map_sizes_dynamic(self._h, out.ctypes.data)
+        return out
+
+    def get_maps_dynamic(self):
+        sizes = self.map_sizes_dynamic
+        out = np.zeros(int(sizes.sum()), dtype=GAUSSIAN4_DTYPE)
+        self.lib.oracle_get_maps_dynamic(self._h, out.ctypes.data)
+        return sizes, out
+
+    def set_maps_dynamic(self, sizes, maps):
+        sizes = np.ascontiguousarray(sizes, dtype=np.int32)
+        maps = np.ascontiguousarray(maps, dtype=GAUSSIAN4_DTYPE)
+        assert len(sizes) == self.n and int(sizes.sum()) == len(maps)
+        self.lib.oracle_set_maps_dynamic(self._h, sizes.ctypes.data, maps.ctypes.data)
+
+    @property
     def resample_idx(self):
         out = np.zeros(self.n, dtype=np.int32)
         self.lib.oracle_get_resample_idx(self._h, out.ctypes.data)
@@ -246,6 +275,42 @@ class Oracle(object):
         v = np.ascontiguousarray(v, dtype=np.float32)
         assert v.shape == (self.n, self.cfg.max_cardinality + 1)
         self.lib.oracle_set_cardinalities(self._h, v.ctypes.data)
+
+
+def mahalanobis4(a, b):
+    a = np.ascontiguousarray(a, GAUSSIAN4_DTYPE)
+    b = np.ascontiguousarray(b, GAUSSIAN4_DTYPE)
+    return float(load().oracle_mahalanobis4(a.ctypes.data, b.ctypes.data))
+
+
+def merge4(cfg, cand):
+    cand = np.ascontiguousarray(cand, GAUSSIAN4_DTYPE)
+    out = np.zeros(max(len(cand), 1), GAUSSIAN4_DTYPE)
+    n = load().oracle_merge4(C.byref(cfg), cand.ctypes.data, len(cand), out.ctypes.data)
+    return out[:n].copy()
+
+
+def predict_features4(cfg, feats):
+    feats = np.ascontiguousarray(feats, GAUSSIAN4_DTYPE)
+    out = np.zeros(len(feats), GAUSSIAN4_DTYPE)
+    for i in range(len(feats)):
+        load().oracle_predict_feature4(C.byref(cfg), feats[i:i + 1].ctypes.data, out[i:i + 1].ctypes.data)
+    return out
+
+
+def mixed_terms(cfg, pose, smap, dmap, Z):
+    """Dense update terms of ONE particle of the mixed feature model: (static terms, dynamic terms, log-weight increment)."""
+    pose = np.ascontiguousarray(pose, POSE_DTYPE).reshape(1)
+    smap = np.ascontiguousarray(smap, GAUSSIAN_DTYPE)
+    dmap = np.ascontiguousarray(dmap, GAUSSIAN4_DTYPE)
+    z = np.ascontiguousarray(Z, np.float32).reshape(len(Z), -1)
+    M = z.shape[0]
+    st = np.zeros(len(smap) * (M + 1) + M, GAUSSIAN_DTYPE)
+    dt = np.zeros(len(dmap) * (M + 1) + M, GAUSSIAN4_DTYPE)
+    ns, nd = C.c_int(), C.c_int()
+    dl = load().oracle_mixed_terms(C.byref(cfg), pose.ctypes.data, smap.ctypes.data, len(smap), dmap.ctypes.data, len(dmap),
+                                   z.ctypes.data, M, z.shape[1], st.ctypes.data, C.byref(ns), dt.ctypes.data, C.byref(nd))
+    return st[:ns.value].copy(), dt[:nd.value].copy(), float(dl)
 
 
 def cphd_factors(cfg, w, pd, S, prior):

@@ -16,12 +16,14 @@
 #include <vector>
 
 #include "../include/phd_detmath.h"
+#include "../include/phd_mixed_math.h"
 
 #ifdef _OPENMP
 #include <omp.h>
 #endif
 
 typedef phdslam_gaussian2d_t G2;
+typedef phdslam_gaussian4d_t G4;
 typedef phdslam_pose_t Pose;
 
 struct phd_oracle {
@@ -29,6 +31,7 @@ struct phd_oracle {
   std::vector<Pose> states;                 /* ParticleSLAM::states   (src/slamtypes.h:279) */
   std::vector<float> weights;               /* ParticleSLAM::weights  (log domain) */
   std::vector<std::vector<G2>> maps;        /* SynthSLAM::maps_static (src/slamtypes.h:290) */
+  std::vector<std::vector<G4>> maps_dyn;    /* SynthSLAM::maps_dynamic (:291), mixed feature model only */
   std::vector<int> resample_idx;
   std::vector<std::vector<float>> card;     /* SynthSLAM::cardinalities (log domain) */
   unsigned predict_calls = 0;               /* Philox counter words */
@@ -90,6 +93,7 @@ extern "C" phd_oracle_t* oracle_create(const phdslam_config_t* cfg) {
   o->states.assign(n, p0);
   o->weights.assign(n, -phd_logf((float)n)); /* -log(float(n_particles)), main.cpp:1144 */
   o->maps.assign(n, std::vector<G2>());
+  o->maps_dyn.assign(n, std::vector<G4>());
   o->resample_idx.resize(n);
   for (int i = 0; i < n; ++i) o->resample_idx[i] = i;
   o->card.assign(n, std::vector<float>());
@@ -122,6 +126,21 @@ extern "C" void oracle_set_maps(phd_oracle_t* o, const int* sizes, const G2* in)
     k += sizes[i];
   }
 }
+extern "C" void oracle_get_map_sizes_dynamic(const phd_oracle_t* o, int* out) {
+  for (size_t i = 0; i < o->maps_dyn.size(); ++i) out[i] = (int)o->maps_dyn[i].size();
+}
+extern "C" void oracle_get_maps_dynamic(const phd_oracle_t* o, G4* out) {
+  size_t k = 0;
+  for (const auto& m : o->maps_dyn)
+    for (const G4& g : m) out[k++] = g;
+}
+extern "C" void oracle_set_maps_dynamic(phd_oracle_t* o, const int* sizes, const G4* in) {
+  size_t k = 0;
+  for (size_t i = 0; i < o->maps_dyn.size(); ++i) {
+    o->maps_dyn[i].assign(in + k, in + k + sizes[i]);
+    k += sizes[i];
+  }
+}
 extern "C" void oracle_get_resample_idx(const phd_oracle_t* o, int* out) { memcpy(out, o->resample_idx.data(), o->resample_idx.size() * 4); }
 extern "C" void oracle_get_cardinalities(const phd_oracle_t* o, float* out) {
   int nc = o->cfg.max_cardinality + 1;
@@ -150,6 +169,7 @@ extern "C" void oracle_predict(phd_oracle_t* o, const float* control, const doub
     std::vector<Pose> ns((size_t)n0 * k);
     std::vector<float> nw((size_t)n0 * k);
     std::vector<std::vector<G2>> nm((size_t)n0 * k);
+    std::vector<std::vector<G4>> nd((size_t)n0 * k);
     std::vector<std::vector<float>> nc((size_t)n0 * k);
     std::vector<int> nr((size_t)n0 * k);
     const float logk = phd_safe_log((float)k);
@@ -158,9 +178,11 @@ extern "C" void oracle_predict(phd_oracle_t* o, const float* control, const doub
       ns[j] = o->states[i];
       nw[j] = o->weights[i] - logk;              /* :1208 */
       nm[j] = o->maps[i];
+      nd[j] = o->maps_dyn[i];
       nc[j] = o->card[i];
       nr[j] = o->resample_idx[i];
     }
+    o->maps_dyn.swap(nd);
     o->states.swap(ns); o->weights.swap(nw); o->maps.swap(nm); o->card.swap(nc); o->resample_idx.swap(nr);
   }
   int n = (int)o->states.size();
@@ -223,6 +245,19 @@ extern "C" void oracle_predict(phd_oracle_t* o, const float* control, const doub
     }
     o->states[i] = ns;
   }
+  /* map prediction of the dynamic features (:1240-1242 -> predictMapMixed :965-1035 -> predictMapKernelMixed :910-963).
+   * Reference quirks kept: the kernel steps by the WHOLE dev_config.dt on every phdPredict call (so subdividePredict = k
+   * predicts the map k times by dt); the "jump" features (a dynamic feature turning static) are computed and thrown away
+   * (the insertion into maps_static is commented out, :1015-1021), so the static maps are untouched. */
+  if (c.feature_model == 2) {
+    const float var_x = c.std_ax_features * c.std_ax_features, var_y = c.std_ay_features * c.std_ay_features;
+    for (int i = 0; i < n; ++i)
+      for (G4& g : o->maps_dyn[i]) {
+        G4 q;
+        phd_g4_predict(&g, c.dt, var_x, var_y, c.ps, c.beta, c.tau, &q);
+        g = q;
+      }
+  }
 }
 
 /* ------------------------------------------------------------------------- */
@@ -283,8 +318,17 @@ struct UpdateOut {
 static void cphd_factors(const phdslam_config_t& c, const float* w, const float* pd, int C, const float* S, int M,
                          const float* prior, int N1, float* D, float* ND, float* inc, float* card_out);
 
+/* Mixed feature model (phdUpdateKernelMixed, src/phdfilter.cu:2323-2608): the static and the dynamic features of a
+ * particle share the per-measurement normaliser and the predicted cardinality; the dynamic side hands these in. */
+struct MixHook {
+  const float* dsum;   /* [M] sum over the in-range dynamic features of exp(partial log-weight) (:2470-2471) */
+  float nhat_dyn;      /* sum of pd * w over the in-range dynamic features (:2424-2446) */
+  float* L_out;        /* [M] the log normalisers, for the dynamic terms */
+};
+
 static void update_particle(const phdslam_config_t& c, const Pose& pose, const std::vector<G2>& in, const float* z,
-                            int M, int fields, UpdateOut& out, std::vector<float>* card = nullptr) {
+                            int M, int fields, UpdateOut& out, std::vector<float>* card = nullptr,
+                            const MixHook* mix = nullptr) {
   const int C = (int)in.size();
   const int T = C * (M + 1) + M;
   out.n_in = C;
@@ -397,7 +441,8 @@ static void update_particle(const phdslam_config_t& c, const Pose& pose, const s
   std::vector<float> tmp(C + M);
   for (int i = 0; i < C; ++i) tmp[i] = pdv[i] * in[i].weight;
   for (int m = 0; m < M; ++m) tmp[C + m] = c.birth_weight;
-  float cardinality_predict = warp_sum(tmp.data(), C + M);
+  /* mixed model: the birth terms do not enter (val stays 0 for them, :2398-2405,2427-2436), the dynamic features do */
+  float cardinality_predict = mix ? (warp_sum(tmp.data(), C) + mix->nhat_dyn) : warp_sum(tmp.data(), C + M);
   /* per-measurement normaliser and final weights (:2190-2252) */
   float particle_weight = 0.0f;
   std::vector<float> ev(C), dsum(M);
@@ -405,9 +450,12 @@ static void update_particle(const phdslam_config_t& c, const Pose& pose, const s
     G2* det = &out.terms[C + m * C];
     for (int i = 0; i < C; ++i) ev[i] = phd_expf(det[i].weight);
     float sum = (C > 0) ? warp_sum(ev.data(), C) : 0.0f;
+    if (mix) sum = sum + mix->dsum[m];
     sum = sum + c.clutter_density;
     sum = sum + c.birth_weight;
+    if (mix && !c.labeled_measurements) sum = sum + c.birth_weight;   /* "we get 2 birth terms when measurements are unlabeled", :2478-2480 */
     float log_normalizer = phd_safe_log(sum);
+    if (mix) mix->L_out[m] = log_normalizer;
     /* exp(logw - L) of the reference (:2222-2229), evaluated as exp(logw) * exp(-L): the first factor is the term that
      * was just summed, so the kernel does not evaluate a second exponential per update term (canonical, <= 2 ulp) */
     const float scale = phd_expf(-log_normalizer);
@@ -596,6 +644,175 @@ extern "C" size_t oracle_update_terms(phd_oracle_t* o, const float* z, int M, in
   return k;
 }
 
+/* ------------------------------------------------------------------------- */
+/* mixed feature model: the dynamic (constant-velocity) features of a particle  */
+/* ------------------------------------------------------------------------- */
+
+/* First half (before the static update): pre-update constants of the in-range dynamic features, the sum of their
+ * likelihood terms per measurement and their share of the predicted cardinality. */
+static void dyn_pre(const phdslam_config_t& c, const Pose& pose, const std::vector<G4>& in, const float* z, int M, int fields,
+                    std::vector<phd_g4_pre_t>& pre, std::vector<float>& dsum, float* nhat) {
+  const int C = (int)in.size();
+  const float var_r = c.std_range * c.std_range, var_b = c.std_bearing * c.std_bearing;
+  pre.resize(C);
+  std::vector<float> tmp(std::max(C, 1));
+  for (int i = 0; i < C; ++i) {
+    phd_g4_preupdate(pose.px, pose.py, pose.ptheta, &in[i], c.max_range, c.max_bearing, c.pd, var_r, var_b, &pre[i]);
+    tmp[i] = pre[i].pd * in[i].weight;
+  }
+  *nhat = (C > 0) ? warp_sum(tmp.data(), C) : 0.0f;
+  dsum.assign(M, 0.0f);
+  for (int m = 0; m < M; ++m) {
+    const int label = fields > 2 ? (int)z[m * fields + 2] : 0;
+    const int dead = c.labeled_measurements && label != 1;          /* DYNAMIC_MEASUREMENT, :504 */
+    for (int i = 0; i < C; ++i)
+      tmp[i] = phd_expf(phd_g4_detect(&pre[i], &in[i], z[m * fields], z[m * fields + 1], dead, nullptr));
+    dsum[m] = (C > 0) ? warp_sum(tmp.data(), C) : 0.0f;
+  }
+}
+
+/* Second half (after the static update fixed the normalisers L): the dense dynamic update terms in the reference's order
+ * [non-detect C | detect m-major M*C | birth M] (:2414-2446, :2490-2528).  upd_sum / prior_sum: the sums Vo's empty-map
+ * weighting takes over them (:2546-2563). */
+static void dyn_terms(const phdslam_config_t& c, const Pose& pose, const std::vector<G4>& in,
+                      const std::vector<phd_g4_pre_t>& pre, const float* z, int M, int fields, const float* L,
+                      std::vector<G4>& terms, float* upd_sum, float* prior_sum) {
+  const int C = (int)in.size();
+  terms.assign((size_t)C * (M + 1) + M, G4());
+  std::vector<float> tmp(std::max(C, 1));
+  for (int i = 0; i < C; ++i) {
+    terms[i] = in[i];
+    terms[i].weight = in[i].weight * (1.0f - pre[i].pd);
+    tmp[i] = terms[i].weight;
+  }
+  float upd = (C > 0) ? warp_sum(tmp.data(), C) : 0.0f;
+  const float sr = c.std_range * c.birth_noise_factor, sb = c.std_bearing * c.birth_noise_factor;
+  for (int m = 0; m < M; ++m) {
+    const int label = fields > 2 ? (int)z[m * fields + 2] : 0;
+    const int dead = c.labeled_measurements && label != 1;
+    for (int i = 0; i < C; ++i) {
+      G4& t = terms[C + (size_t)m * C + i];
+      const float lw = phd_g4_detect(&pre[i], &in[i], z[m * fields], z[m * fields + 1], dead, t.mean);
+      memcpy(t.cov, pre[i].cov, sizeof(t.cov));
+      t.weight = phd_expf(lw - L[m]);
+      tmp[i] = t.weight;
+    }
+    G4& b = terms[C + (size_t)M * C + m];
+    phd_g4_birth(pose.px, pose.py, pose.ptheta, z[m * fields], z[m * fields + 1], sr * sr, sb * sb, c.cov_vx_birth,
+                 c.cov_vy_birth, &b);
+    b.weight = phd_expf((dead ? PHD_LOG0 : phd_safe_log(c.birth_weight)) - L[m]);
+    upd = upd + (((C > 0) ? warp_sum(tmp.data(), C) : 0.0f) + b.weight);
+  }
+  for (int i = 0; i < C; ++i) tmp[i] = in[i].weight;
+  *prior_sum = (C > 0) ? warp_sum(tmp.data(), C) : 0.0f;
+  *upd_sum = upd;
+}
+
+/* phdUpdateMergeKernel<Gaussian4D> (src/phdfilter.cu:2707-2898): as merge_mixture, without the spatial gate.  The
+ * Hellinger metric has no 4-D form in the reference (the template returns 0, src/device_math.cuh:366-371), so with
+ * distance_metric = 1 every candidate joins the first cluster. */
+static void merge_mixture4(const phdslam_config_t& c, const std::vector<G4>& cand, std::vector<G4>& out) {
+  const int n = (int)cand.size();
+  std::vector<char> merged(n, 0);
+  std::vector<int> members;
+  while (true) {
+    int best = -1;
+    for (int i = 0; i < n; ++i) {
+      if (merged[i]) continue;
+      if (best < 0 || cand[best].weight < cand[i].weight ||
+          (cand[best].weight == cand[i].weight && merge_tie_key(i) < merge_tie_key(best)))
+        best = i;
+    }
+    if (best < 0) break;
+    members.clear();
+    for (int i = 0; i < n; ++i) {
+      if (merged[i]) continue;
+      const float dist = (c.distance_metric == 0) ? phd_g4_mahal(&cand[best], &cand[i]) : 0.0f;
+      if (dist < c.min_separation) members.push_back(i);
+    }
+    G4 mg;
+    if (!phd_g4_moment_match(cand.data(), members.data(), (int)members.size(), &mg)) break;
+    for (int i : members) merged[i] = 1;
+    out.push_back(mg);
+  }
+}
+
+extern "C" int oracle_merge4(const phdslam_config_t* cfg, const G4* in, int n, G4* out) {
+  std::vector<G4> cand(in, in + n), res;
+  merge_mixture4(*cfg, cand, res);
+  memcpy(out, res.data(), res.size() * sizeof(G4));
+  return (int)res.size();
+}
+extern "C" float oracle_mahalanobis4(const G4* a, const G4* b) { return phd_g4_mahal(a, b); }
+extern "C" void oracle_predict_feature4(const phdslam_config_t* c, const G4* in, G4* out) {
+  phd_g4_predict(in, c->dt, c->std_ax_features * c->std_ax_features, c->std_ay_features * c->std_ay_features, c->ps, c->beta,
+                 c->tau, out);
+}
+
+static void split_map4(const phdslam_config_t& c, const Pose& pose, const std::vector<G4>& map, std::vector<G4>& in) {
+  for (const G4& f : map) {
+    G2 q;
+    memset(&q, 0, sizeof(q));
+    q.mean[0] = f.mean[0];
+    q.mean[1] = f.mean[1];
+    if (classify(c, pose, q) == 1) in.push_back(f);   /* everything else is dropped, :3713-3719 */
+  }
+}
+
+/* One particle of phdUpdateSynth with featureModel = MIXED_MODEL (:3449-3462, :3703-3726).  The dense terms of both maps
+ * come back when asked for (the pin against the reference's kernel). */
+static float update_particle_mixed(const phdslam_config_t& c, const Pose& pose, std::vector<G2>& smap, std::vector<G4>& dmap,
+                                   const float* z, int M, int fields, std::vector<G2>* s_terms = nullptr,
+                                   std::vector<G4>* d_terms = nullptr, bool advance = true) {
+  std::vector<G2> in, out2, out1;
+  split_map(c, pose, smap, in, out2, out1);
+  std::vector<G4> din;
+  split_map4(c, pose, dmap, din);
+  std::vector<phd_g4_pre_t> pre;
+  std::vector<float> dsum, L(M);
+  float nhat = 0.0f;
+  dyn_pre(c, pose, din, z, M, fields, pre, dsum, &nhat);
+  MixHook hook{dsum.data(), nhat, L.data()};
+  UpdateOut u;
+  update_particle(c, pose, in, z, M, fields, u, nullptr, &hook);
+  std::vector<G4> dt;
+  float upd = 0.0f, prior = 0.0f;
+  dyn_terms(c, pose, din, pre, z, M, fields, L.data(), dt, &upd, &prior);
+  float dlogw = u.dlogw;
+  if (c.particle_weighting == 1) dlogw = dlogw + ((upd - prior) - (float)M * c.birth_weight);   /* :2546-2566 */
+  if (s_terms) *s_terms = u.terms;
+  if (d_terms) *d_terms = dt;
+  if (!advance) return dlogw;
+  std::vector<G2> cand;
+  for (const G2& t : u.terms)
+    if (!(t.weight < c.min_feature_weight)) cand.push_back(t);
+  cand.insert(cand.end(), out2.begin(), out2.end());
+  std::vector<G2> mergedv;
+  merge_mixture(c, cand, mergedv);
+  mergedv.insert(mergedv.end(), out1.begin(), out1.end());
+  smap.swap(mergedv);
+  std::vector<G4> dcand, dmerged;
+  for (const G4& t : dt)
+    if (!(t.weight < c.min_feature_weight)) dcand.push_back(t);
+  merge_mixture4(c, dcand, dmerged);
+  dmap.swap(dmerged);
+  return dlogw;
+}
+
+/* dense update terms of ONE particle (maps given as they are, classified inside); returns the log-weight increment */
+extern "C" float oracle_mixed_terms(const phdslam_config_t* cfg, const Pose* pose, const G2* smap, int ns, const G4* dmap,
+                                    int nd, const float* z, int M, int fields, G2* s_terms_out, int* n_s_terms, G4* d_terms_out,
+                                    int* n_d_terms) {
+  std::vector<G2> sm(smap, smap + ns), st;
+  std::vector<G4> dm(dmap, dmap + nd), dt;
+  const float dl = update_particle_mixed(*cfg, *pose, sm, dm, z, M, fields, &st, &dt, false);
+  if (s_terms_out) memcpy(s_terms_out, st.data(), st.size() * sizeof(G2));
+  if (d_terms_out) memcpy(d_terms_out, dt.data(), dt.size() * sizeof(G4));
+  *n_s_terms = (int)st.size();
+  *n_d_terms = (int)dt.size();
+  return dl;
+}
+
 /* Canonical order-independent log-sum-exp: fixed-point accumulation of exp(w - max).
  * Stands in for the host logSumExp (src/device_math.cuh:549-558), a sequential fp32 sum. */
 static float log_sum_exp_fx(const std::vector<float>& w) {
@@ -616,6 +833,10 @@ extern "C" void oracle_update(phd_oracle_t* o, const float* z, int M, int fields
   std::vector<float> dlogw(n, 0.0f);
 #pragma omp parallel for schedule(dynamic, 8) num_threads(o->threads)
   for (int p = 0; p < n; ++p) {
+    if (c.feature_model == 2) {
+      dlogw[p] = update_particle_mixed(c, o->states[p], o->maps[p], o->maps_dyn[p], z, M, fields);
+      continue;
+    }
     std::vector<G2> in, out2, out1;
     split_map(c, o->states[p], o->maps[p], in, out2, out1);
     UpdateOut u;
@@ -831,11 +1052,14 @@ extern "C" void oracle_resample(phd_oracle_t* o, int n_new, const double* unifor
   std::vector<Pose> ns(n_new);
   std::vector<std::vector<G2>> nm(n_new);
   std::vector<std::vector<float>> nc(n_new);
+  std::vector<std::vector<G4>> nd(n_new);
   for (int j = 0; j < n_new; ++j) {
     ns[j] = o->states[idx[j]];
     nm[j] = o->maps[idx[j]];
+    nd[j] = o->maps_dyn[idx[j]];
     nc[j] = o->card[idx[j]];
   }
+  o->maps_dyn.swap(nd);
   o->states.swap(ns);
   o->maps.swap(nm);
   o->card.swap(nc);

@@ -53,6 +53,10 @@ void oracle_set_log_weights(phd_oracle_t* o, const float* in);
 void oracle_get_map_sizes(const phd_oracle_t* o, int* out);
 void oracle_get_maps(const phd_oracle_t* o, phdslam_gaussian2d_t* out);
 void oracle_set_maps(phd_oracle_t* o, const int* sizes, const phdslam_gaussian2d_t* in);
+/* mixed feature model (feature_model = 2): SynthSLAM::maps_dynamic */
+void oracle_get_map_sizes_dynamic(const phd_oracle_t* o, int* out);
+void oracle_get_maps_dynamic(const phd_oracle_t* o, phdslam_gaussian4d_t* out);
+void oracle_set_maps_dynamic(phd_oracle_t* o, const int* sizes, const phdslam_gaussian4d_t* in);
 void oracle_get_resample_idx(const phd_oracle_t* o, int* out);
 void oracle_get_cardinalities(const phd_oracle_t* o, float* out);
 void oracle_set_cardinalities(phd_oracle_t* o, const float* in);
@@ -82,6 +86,14 @@ float oracle_mahalanobis(const phdslam_gaussian2d_t* a, const phdslam_gaussian2d
 float oracle_hellinger(const phdslam_gaussian2d_t* a, const phdslam_gaussian2d_t* b);
 int oracle_merge(const phdslam_config_t* cfg, const phdslam_gaussian2d_t* in, int n, phdslam_gaussian2d_t* out);
 int oracle_reduce_mixture(const phdslam_gaussian2d_t* in, int n, float min_distance, phdslam_gaussian2d_t* out);
+/* mixed feature model: computeMahalDist(Gaussian4D,..), phdUpdateMergeKernel<Gaussian4D>, predictMapKernelMixed for one
+ * feature, and the dense update terms of both maps of one particle (phdUpdateKernelMixed) */
+float oracle_mahalanobis4(const phdslam_gaussian4d_t* a, const phdslam_gaussian4d_t* b);
+int oracle_merge4(const phdslam_config_t* cfg, const phdslam_gaussian4d_t* in, int n, phdslam_gaussian4d_t* out);
+void oracle_predict_feature4(const phdslam_config_t* cfg, const phdslam_gaussian4d_t* in, phdslam_gaussian4d_t* out);
+float oracle_mixed_terms(const phdslam_config_t* cfg, const phdslam_pose_t* pose, const phdslam_gaussian2d_t* smap, int ns,
+                         const phdslam_gaussian4d_t* dmap, int nd, const float* z, int M, int fields,
+                         phdslam_gaussian2d_t* s_terms_out, int* n_s_terms, phdslam_gaussian4d_t* d_terms_out, int* n_d_terms);
 float oracle_warp_sum(const float* v, int n);
 void oracle_detmath(int fn, const float* x, const float* y, float* out, float* out2, int n);
 void oracle_philox(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned* out4);

@@ -12,7 +12,7 @@ import numpy as np
 from .oracle import GAUSSIAN_DTYPE, POSE_DTYPE
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_ref", "libphd_ref.so")
+LIB_PATH = os.environ.get("PHD_REF_LIB") or os.path.join(_HERE, "_ref", "libphd_ref.so")
 _lib = None
 
 
@@ -49,6 +49,13 @@ def load():
         lib.ref_recover.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         lib.ref_neff.restype = C.c_float
         lib.ref_neff.argtypes = [C.c_void_p, C.c_int]
+        lib.ref_mahalanobis4.restype = C.c_float
+        lib.ref_mahalanobis4.argtypes = [C.c_void_p, C.c_void_p]
+        lib.ref_predict_features4.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        lib.ref_mixed_update_terms.restype = C.c_float
+        lib.ref_mixed_update_terms.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.ref_merge4.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _lib = lib
     return _lib
 
@@ -327,3 +334,48 @@ def cphd_update(poses, features, n_in, Z, cn_predict, variant="head"):
     return dict(detect=np.concatenate(det) if det else np.zeros((0, M), GAUSSIAN_DTYPE), nondetect=np.concatenate(nd),
                 detect_flags=np.concatenate(dfl), nondetect_flags=np.concatenate(nfl), cn_update=cn_up, ip0=ip0, ip1=ip1,
                 ip1d=ip1d, esf=esf, esfd=esfd, w_partial=wp[:ntot])
+
+
+# ---- mixed feature model (featureModel = MIXED_MODEL): the reference's own device code through the emulator ----
+GAUSSIAN4_DTYPE = np.dtype([("cov", "f4", (16,)), ("mean", "f4", (4,)), ("weight", "f4")])
+
+
+def mahalanobis4(a, b):
+    a = np.ascontiguousarray(a, GAUSSIAN4_DTYPE)
+    b = np.ascontiguousarray(b, GAUSSIAN4_DTYPE)
+    return float(load().ref_mahalanobis4(a.ctypes.data, b.ctypes.data))
+
+
+def predict_features4(feats):
+    """predictMapKernelMixed: (predicted dynamic features, the jump features the host wrapper discards)"""
+    f = np.ascontiguousarray(feats, GAUSSIAN4_DTYPE)
+    out = np.zeros(max(len(f), 1), GAUSSIAN4_DTYPE)
+    jump = np.zeros(max(len(f), 1), GAUSSIAN_DTYPE)
+    load().ref_predict_features4(f.ctypes.data, len(f), out.ctypes.data, jump.ctypes.data)
+    return out[:len(f)].copy(), jump[:len(f)].copy()
+
+
+def mixed_update_terms(pose, s_in, d_in, Z):
+    """phdUpdateKernelMixed on one particle: (static terms, dynamic terms, static prune flags, dynamic prune flags, dlogw)"""
+    p = np.ascontiguousarray(pose, POSE_DTYPE).reshape(1)
+    s_in = np.ascontiguousarray(s_in, GAUSSIAN_DTYPE)
+    d_in = np.ascontiguousarray(d_in, GAUSSIAN4_DTYPE)
+    z = _f32(Z).reshape(len(Z), -1)
+    M = z.shape[0]
+    st = np.zeros(len(s_in) * (M + 1) + M, GAUSSIAN_DTYPE)
+    dt = np.zeros(len(d_in) * (M + 1) + M, GAUSSIAN4_DTYPE)
+    fs = np.zeros(len(st), np.int8)
+    fd = np.zeros(len(dt), np.int8)
+    sp = np.concatenate([s_in, np.zeros(1, GAUSSIAN_DTYPE)])
+    dp = np.concatenate([d_in, np.zeros(1, GAUSSIAN4_DTYPE)])
+    pw = load().ref_mixed_update_terms(p.ctypes.data, sp.ctypes.data, len(s_in), dp.ctypes.data, len(d_in), z.ctypes.data, M,
+                                       z.shape[1], st.ctypes.data, dt.ctypes.data, fs.ctypes.data, fd.ctypes.data)
+    return st, dt, fs, fd, float(pw)
+
+
+def merge4(cand):
+    c = np.ascontiguousarray(cand, GAUSSIAN4_DTYPE)
+    out = np.zeros(max(len(c), 1), GAUSSIAN4_DTYPE)
+    padded = np.concatenate([c, np.zeros(1, GAUSSIAN4_DTYPE)])
+    n = load().ref_merge4(padded.ctypes.data, len(c), out.ctypes.data)
+    return out[:n].copy()

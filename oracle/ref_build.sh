@@ -55,6 +55,19 @@ K="$REF/src/phdfilter.cu"
 } > "$GEN/ref_kernels.inc"
 [ "$(grep -c 'sum += sdata\[0\] ; __syncthreads() ;' "$GEN/ref_kernels.inc")" -eq 1 ] || { echo "ref_build: barrier patch failed" >&2; exit 1; }
 
+# ---- mixed feature model (static + constant-velocity features): the 4-D birth and pre-update device functions, the map
+# prediction kernel and phdUpdateKernelMixed.  Like phdUpdateKernel above, the mixed kernel reads sdata[0] after the
+# per-measurement reduction (`normalizer += sdata[0]`, :2472) with no barrier before thread 0 starts the next reduction:
+# the same barrier is added for the emulator.
+{
+  extract "$K" 244 299 computeBirth
+  extract "$K" 301 395 computePreUpdate
+  extract "$K" 397 521 computePreUpdate
+  extract "$K" 910 963 predictMapKernelMixed
+  extract "$K" 2323 2635 phdUpdateKernelMixed | sed -E 's/^( *normalizer \+= sdata\[0\] ;)\s*$/\1 __syncthreads() ;/'
+} > "$GEN/ref_mixed.inc"
+[ "$(grep -c 'normalizer += sdata\[0\] ; __syncthreads() ;' "$GEN/ref_mixed.inc")" -eq 1 ] || { echo "ref_build: mixed barrier patch failed" >&2; exit 1; }
+
 # ---- CPHD: the reference's multi-object update kernels.  HEAD keeps them COMMENTED OUT (every line prefixed with `//`,
 # src/phdfilter.cu:701-748,1430-1822); the live older forms are in src/phdfilter.cu.bak.  Both are made executable here:
 #   head: the commented ranges with the ONE leading `//` of every line removed (nested `////` comments stay comments) --

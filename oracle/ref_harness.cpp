@@ -75,6 +75,8 @@ extern "C" void ref_set_config(const phdslam_config_t* c) {
   s.maxCardinality = c->max_cardinality; s.filterType = c->filter_type; s.mapEstimate = c->map_estimate;
   s.featureModel = c->feature_model; s.motionType = c->motion_type; s.labeledMeasurements = c->labeled_measurements != 0;
   s.l = c->l; s.h = c->h; s.a = c->a; s.b = c->b; s.stdAlpha = c->std_alpha; s.stdEncoder = c->std_encoder;
+  s.ps = c->ps; s.tau = c->tau; s.beta = c->beta; s.stdAxMap = c->std_ax_features; s.stdAyMap = c->std_ay_features;
+  s.covVxBirth = c->cov_vx_birth; s.covVyBirth = c->cov_vy_birth;
   s.nSamples = 256;
   dev_config = s;   /* setDeviceConfig, src/phdfilter.cu:3885-3890 */
   config = s;
@@ -207,6 +209,70 @@ extern "C" void ref_merge(const G2* cand, const int* offsets /* n_particles+1 */
     phdUpdateMergeKernel<Gaussian2D>(in.data(), out.data(), merged_sizes, (bool*)flags.data(), (int*)offsets, n_particles);
   });
   memcpy(merged_out, out.data(), (size_t)n * sizeof(G2));   /* particle p's merged map starts at offsets[p] */
+}
+
+/* ---- mixed feature model (featureModel = MIXED_MODEL): the reference's own device code, src/phdfilter.cu:244-521,
+ * 910-963, 2323-2635, plus computeMahalDist(Gaussian4D) / ConstantVelocityMotionModel of src/device_math.cuh and the
+ * Gaussian4D instance of phdUpdateMergeKernel ---- */
+#include "ref_mixed.inc"
+typedef phdslam_gaussian4d_t G4;
+static_assert(sizeof(G4) == sizeof(Gaussian4D), "layout");
+
+extern "C" float ref_mahalanobis4(const G4* a, const G4* b) {
+  Gaussian4D x, y;
+  memcpy(&x, a, sizeof(x)); memcpy(&y, b, sizeof(y));
+  return computeMahalDist(x, y);
+}
+/* predictMapMixed (src/phdfilter.cu:965-1035): launch shape and motion-model set-up of the host wrapper; the jump
+ * features come back too (the wrapper discards them) */
+extern "C" void ref_predict_features4(const G4* in, int n, G4* out, G2* jump_out) {
+  vector<Gaussian4D> prior(std::max(n, 1)), pred(std::max(n, 1));
+  vector<Gaussian2D> jump(std::max(n, 1));
+  memcpy(prior.data(), in, (size_t)n * sizeof(G4));
+  ConstantVelocityMotionModel motion_model;
+  motion_model.std_accx = config.stdAxMap;
+  motion_model.std_accy = config.stdAyMap;
+  int n_blocks = (n + 255) / 256;
+  emul_launch(n_blocks, kThreads, [&] { predictMapKernelMixed(prior.data(), motion_model, n, pred.data(), jump.data()); });
+  memcpy(out, pred.data(), (size_t)n * sizeof(G4));
+  if (jump_out) memcpy(jump_out, jump.data(), (size_t)n * sizeof(G2));
+}
+/* phdUpdateKernelMixed on ONE particle (the kernel reads the predicted weights without the particle's offset, :2411,2437,
+ * so only particle 0 of a launch is computed as intended): the in-range static and dynamic features in, the dense update
+ * terms of both maps ([non-detect | detect m-major | birth], :2344-2356) and the particle's log-weight increment out. */
+extern "C" float ref_mixed_update_terms(const Pose* pose, const G2* s_in, int ns, const G4* d_in, int nd, const float* z, int M,
+                                        int fields, G2* s_terms, G4* d_terms, char* s_flags, char* d_flags) {
+  set_measurements(z, M, fields);
+  vector<Gaussian2D> sp(std::max(ns, 1)), su((size_t)ns * (M + 1) + M + 1);
+  vector<Gaussian4D> dp(std::max(nd, 1)), du((size_t)nd * (M + 1) + M + 1);
+  memcpy(sp.data(), s_in, (size_t)ns * sizeof(G2));
+  memcpy(dp.data(), d_in, (size_t)nd * sizeof(G4));
+  int off_s[2] = {0, ns}, off_d[2] = {0, nd};
+  vector<char> fs(su.size(), 0), fd(du.size(), 0);
+  ConstantVelocityState ps;
+  memcpy(&ps, pose, sizeof(ps));
+  REAL pw = 0;
+  emul_launch(1, kThreads, [&] {
+    phdUpdateKernelMixed(&ps, sp.data(), dp.data(), off_s, off_d, 1, M, su.data(), du.data(), (bool*)fs.data(), (bool*)fd.data(),
+                         &pw);
+  });
+  const size_t nst = (size_t)ns * (M + 1) + M, ndt = (size_t)nd * (M + 1) + M;
+  memcpy(s_terms, su.data(), nst * sizeof(G2));
+  memcpy(d_terms, du.data(), ndt * sizeof(G4));
+  if (s_flags) memcpy(s_flags, fs.data(), nst);
+  if (d_flags) memcpy(d_flags, fd.data(), ndt);
+  return pw;
+}
+extern "C" int ref_merge4(const G4* cand, int n, G4* merged_out) {
+  vector<Gaussian4D> in(std::max(n, 1)), out(std::max(n, 1));
+  memcpy(in.data(), cand, (size_t)n * sizeof(G4));
+  vector<char> flags(std::max(n, 1), 0);
+  int offsets[2] = {0, n}, size = 0;
+  emul_launch(1, kThreads, [&] {
+    phdUpdateMergeKernel<Gaussian4D>(in.data(), out.data(), &size, (bool*)flags.data(), offsets, 1);
+  });
+  memcpy(merged_out, out.data(), (size_t)size * sizeof(G4));
+  return size;
 }
 
 /* ---- a whole static-map phdUpdateSynth (src/phdfilter.cu:3336-3761): reference kernels + restated glue ---- */

@@ -1,0 +1,174 @@
+"""The MIXED feature model (feature_model = 2: static + constant-velocity features) on the GPU, through
+the C-ABI: bit-identical to the CPU oracle (the arithmetic of both is include/phd_mixed_math.h + phd_detmath.h), and within
+1e-4 of the REFERENCE's own kernels on the golden cases (tests/golden/ref_mixed_golden.npz, tests/test_mixed_ref_pin.py)."""
+import os
+
+import numpy as np
+import pytest
+
+import phdslam_b200 as P
+from oracle import oracle as O
+from conftest import GOLDEN
+import mixed_cases as MC
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(GOLDEN, "ref_mixed_golden.npz"))
+
+
+def gold(name):
+    pre = name + "/"
+    return {k[len(pre):]: GOLD[k] for k in GOLD.files if k.startswith(pre)}
+
+
+def scene(n, ns, nd, M, labelled, seed, n_far_dynamic=2, n_far_static=3):
+    """n particles around one truth pose; every particle its own jittered copy of a static and a dynamic map (different
+    sizes per particle), some components out of range."""
+    rng = np.random.default_rng(seed)
+    poses = np.zeros(n, MC.POSE)
+    poses["px"], poses["py"], poses["ptheta"] = rng.normal(0, 0.1, n), rng.normal(0, 0.1, n), rng.normal(0, 0.02, n)
+    base_s = np.concatenate([MC.static_features(rng, ns), MC.static_features(rng, n_far_static, r_hi=13.0)])
+    base_s["mean"][ns:] *= 3.0                                           # beyond max_range: class 0 / 2
+    base_d = np.concatenate([MC.dynamic_features(rng, nd), MC.dynamic_features(rng, n_far_dynamic)])
+    base_d["mean"][nd:, :2] *= 3.0
+    ssz, dsz, sm, dm = [], [], [], []
+    for p in range(n):
+        ks = rng.permutation(len(base_s))[:rng.integers(max(len(base_s) - 3, 0), len(base_s) + 1)]
+        kd = rng.permutation(len(base_d))[:rng.integers(max(len(base_d) - 2, 0), len(base_d) + 1)]
+        s = base_s[np.sort(ks)].copy()
+        d = base_d[np.sort(kd)].copy()
+        s["mean"] += rng.normal(0, 0.05, s["mean"].shape).astype(np.float32)
+        d["mean"] += rng.normal(0, 0.05, d["mean"].shape).astype(np.float32)
+        ssz.append(len(s)); dsz.append(len(d)); sm.append(s); dm.append(d)
+    targets = np.concatenate([base_s["mean"][:ns], base_d["mean"][:nd, :2]])
+    Z = MC.measurements(rng, np.zeros(1, MC.POSE)[0], targets, M, labelled, n_static=ns)
+    return dict(poses=poses, ssz=np.array(ssz, np.int32), smaps=np.concatenate(sm), dsz=np.array(dsz, np.int32),
+                dmaps=np.concatenate(dm), Z=Z, targets=targets, ns=ns)
+
+
+def load(f, sc):
+    f.poses = sc["poses"]
+    f.set_maps(sc["ssz"], sc["smaps"])
+    f.set_maps_dynamic(sc["dsz"], sc["dmaps"])
+
+
+def assert_same_state(g, o, what):
+    gs, gm = g.get_maps()
+    os_, om = o.get_maps()
+    gd, gdm = g.get_maps_dynamic()
+    od, odm = o.get_maps_dynamic()
+    assert (gs == os_).all(), what + ": static component counts"
+    assert (gd == od).all(), what + ": dynamic component counts"
+    assert gm.tobytes() == om.tobytes(), what + ": static maps"
+    assert gdm.tobytes() == odm.tobytes(), what + ": dynamic maps"
+    assert g.log_weights.tobytes() == o.log_weights.tobytes(), what + ": log-weights"
+    assert g.poses.tobytes() == o.poses.tobytes(), what + ": poses"
+
+
+@pytest.mark.parametrize("name", list(MC.MIXED_CASES))
+def test_golden_cases_against_the_reference_kernels(name):
+    cfg, pose, sm, dm, Z = MC.build_case(name)
+    gd = gold(name)
+    g = P.PhdSlam(cfg)
+    g.poses = pose
+    g.set_maps([len(sm)], sm)
+    g.set_maps_dynamic([len(dm)], dm)
+    g.phdUpdateSynth(Z)
+    _, smap = g.get_maps()
+    _, dmap = g.get_maps_dynamic()
+    assert len(dmap) == len(gd["d_merged"]) and len(smap) == len(gd["s_merged"])          # bit-exact counts
+    MC.assert_gaussians_close(dmap, gd["d_merged"], name + " dynamic map")
+    MC.assert_gaussians_close(smap, gd["s_merged"], name + " static map")
+    # and the map prediction
+    g2 = P.PhdSlam(cfg)
+    g2.poses = pose
+    g2.set_maps_dynamic([len(dm)], dm)
+    g2.phdPredict(np.float32([0.0, 0.0]))
+    _, pred = g2.get_maps_dynamic()
+    MC.assert_gaussians_close(pred, gd["predicted"], name + " predicted", wfloor=1e-9)
+
+
+@pytest.mark.parametrize("labelled,weighting,metric", [(False, 0, 0), (True, 0, 0), (False, 1, 0), (True, 1, 0), (False, 0, 1)])
+def test_filter_steps_are_bit_identical_to_the_oracle(labelled, weighting, metric):
+    """predict (poses + dynamic map), mixed update, estimate, resampling with injected and counter-based draws, over several
+    steps and 96 particles with different map sizes."""
+    n, M = 96, 14
+    cfg = MC.mixed_config(n, M, labelled, weighting, distance_metric=metric, resample_threshold=1.1, seed="5")
+    sc = scene(n, 18, 6, M, labelled, seed=21 + weighting)
+    g, o = P.PhdSlam(cfg), O.Oracle(cfg)
+    load(g, sc)
+    load(o, sc)
+    rng = np.random.default_rng(3)
+    for k in range(5):
+        u = np.float32([1.0, 0.02 * k])
+        if k:
+            g.phdPredict(u)
+            o.phdPredict(u)
+            assert_same_state(g, o, "step %d predict" % k)
+        Z = MC.measurements(rng, np.zeros(1, MC.POSE)[0], sc["targets"], M - k, labelled, n_static=sc["ns"])
+        g.phdUpdateSynth(Z)
+        o.phdUpdateSynth(Z)
+        assert_same_state(g, o, "step %d update" % k)
+        eg, eo = g.recoverSlamState(), o.recoverSlamState()
+        assert eg.map_particle == eo.map_particle and eg.pose.tobytes() == eo.pose.tobytes()
+        mg = g.map_estimate_dynamic()
+        _, odm = o.get_maps_dynamic()
+        od = o.map_sizes_dynamic
+        lo = int(od[:eo.map_particle].sum())
+        assert mg.tobytes() == odm[lo:lo + od[eo.map_particle]].tobytes()
+        uu = rng.uniform(0, 1, n + 1) if k % 2 == 0 else None
+        ag, ao = g.resampleParticles(uu), o.resampleParticles(uu)
+        assert (ag == ao).all()
+        assert_same_state(g, o, "step %d resample" % k)
+    sizes = g.map_sizes_dynamic
+    assert sizes.max() > 0 and len(np.unique(sizes)) >= 1
+
+
+def test_step_loop_and_snapshot_restore():
+    n, M = 64, 10
+    cfg = MC.mixed_config(n, M, seed="9", resample_threshold=0.6)
+    sc = scene(n, 12, 5, M, False, seed=40)
+    g, o = P.PhdSlam(cfg), O.Oracle(cfg)
+    load(g, sc)
+    load(o, sc)
+    g.snapshot()
+    rng = np.random.default_rng(8)
+    zs = [MC.measurements(rng, np.zeros(1, MC.POSE)[0], sc["targets"], M, False) for _ in range(4)]
+    for k, Z in enumerate(zs):
+        eg, rg = g.step(k, np.float32([1.0, 0.01]), Z)
+        eo, ro = o.step(k, np.float32([1.0, 0.01]), Z)
+        assert rg == ro and eg.neff == eo.neff
+        assert_same_state(g, o, "step %d" % k)
+    first = g.get_maps_dynamic()[1].tobytes()
+    g.restore()
+    o2 = O.Oracle(cfg)
+    load(o2, sc)
+    assert_same_state(g, o2, "restored")
+    for k, Z in enumerate(zs):
+        g.step(k, np.float32([1.0, 0.01]), Z)
+    assert g.get_maps_dynamic()[1].tobytes() == first
+
+
+def test_unsupported_combinations_fail_loudly():
+    for kw in (dict(feature_model=1), dict(filter_type=1, max_cardinality=63), dict(n_predict_particles=2)):
+        ov = dict(MC.MIXED_OVERRIDES)
+        ov.update(kw)
+        cfg = MC.S.scene_config_py(8, 8, 4, **ov)
+        with pytest.raises(Exception):
+            P.PhdSlam(cfg)
+    cfg = MC.mixed_config(4, 4)
+    g = P.PhdSlam(cfg)
+    with pytest.raises(Exception):
+        g.dist_init(0, 2, unique_id=P.dist_unique_id())
+    # static feature model: no dynamic maps
+    with pytest.raises(Exception):
+        P.PhdSlam(MC.S.scene_config_py(4, 8, 4)).get_maps_dynamic()
+
+
+def test_dynamic_map_capacity_is_reported():
+    cfg = MC.mixed_config(2, 40, max_components_dynamic=8, min_separation=1e-6)
+    rng = np.random.default_rng(2)
+    g = P.PhdSlam(cfg)
+    Z = MC.measurements(rng, np.zeros(1, MC.POSE)[0], np.zeros((0, 2)), 40, False)     # 40 births, nothing merges
+    with pytest.raises(Exception) as e:
+        g.phdUpdateSynth(Z)
+    assert "dynamic" in str(e.value)
