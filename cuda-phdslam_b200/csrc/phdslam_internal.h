@@ -141,6 +141,7 @@ struct phdslam {
   float* mix_dsum; float* mix_nhat; float* mix_L;   /* [n][256], [n], [n][256]: coupling of the two maps' updates */
   phdslam_gaussian4d_t* dcand;    /* [n][Sd] */
   float* snap_dmap; int* snap_dcount;
+  cudaEvent_t ev_dyn[4];          /* around dyn_pre_kernel and dyn_update_kernel */
 };
 
 #endif

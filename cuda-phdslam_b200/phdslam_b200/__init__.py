@@ -87,7 +87,8 @@ class Estimate(C.Structure):
 class Timings(C.Structure):
     _fields_ = [("predict_ms", C.c_float), ("update_ms", C.c_float), ("merge_ms", C.c_float), ("weights_ms", C.c_float),
                 ("estimate_ms", C.c_float), ("resample_ms", C.c_float), ("launches", C.c_ulonglong),
-                ("migrated_in", C.c_ulonglong), ("h2d_bytes", C.c_ulonglong), ("d2h_bytes", C.c_ulonglong)]
+                ("migrated_in", C.c_ulonglong), ("h2d_bytes", C.c_ulonglong), ("d2h_bytes", C.c_ulonglong),
+                ("dynamic_ms", C.c_float)]
 
 
 # every symbol include/phdslam.h declares (tests/test_abi.py checks the built library exports all of them)
@@ -259,17 +260,23 @@ def plan_events(measurement_times, control_times):
 
 
 def write_log(path, layout, expected_pose, map_est, log_weights, poses, resample_idx=None, cardinality=None, n_card=1,
-              filter_type=0):
-    """writeLog (src/main.cpp:848-954) / README 5-line layout."""
+              filter_type=0, map_dynamic=None):
+    """writeLog (src/main.cpp:848-954) / README 5-line layout.  map_dynamic: the dynamic map estimate of the mixed feature
+    model (line 3 of the 7-line layout)."""
     e = np.ascontiguousarray(expected_pose, dtype=np.float32)
     m = np.ascontiguousarray(map_est, dtype=GAUSSIAN_DTYPE)
+    d = np.zeros(0, GAUSSIAN4_DTYPE) if map_dynamic is None else np.ascontiguousarray(map_dynamic, dtype=GAUSSIAN4_DTYPE)
     w = np.ascontiguousarray(log_weights, dtype=np.float32)
     p = np.ascontiguousarray(poses, dtype=POSE_DTYPE)
     ri = None if resample_idx is None else np.ascontiguousarray(resample_idx, dtype=np.int32)
     cd = None if cardinality is None else np.ascontiguousarray(cardinality, dtype=np.float32)
-    _check(load_library().phdslam_write_log(
-        os.fsencode(path), layout, e.ctypes.data, m.ctypes.data if len(m) else None, len(m), w.ctypes.data, p.ctypes.data,
-        len(w), None if ri is None else ri.ctypes.data, None if cd is None else cd.ctypes.data, n_card, filter_type))
+    lib = load_library()
+    lib.phdslam_write_log_mixed.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                            C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    _check(lib.phdslam_write_log_mixed(
+        os.fsencode(path), layout, e.ctypes.data, m.ctypes.data if len(m) else None, len(m), d.ctypes.data if len(d) else None,
+        len(d), w.ctypes.data, p.ctypes.data, len(w), None if ri is None else ri.ctypes.data,
+        None if cd is None else cd.ctypes.data, n_card, filter_type))
 
 
 def _ptr(a):

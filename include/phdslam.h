@@ -249,6 +249,7 @@ typedef struct phdslam_timings {
   unsigned long long migrated_in; /* particles received from other ranks by resampling so far */
   unsigned long long h2d_bytes;   /* bytes this handle copied host -> device so far (counted at every copy call) */
   unsigned long long d2h_bytes;   /* bytes this handle copied device -> host so far */
+  float dynamic_ms;               /* mixed feature model: the dynamic-map kernels of the last update (not part of update_ms / merge_ms) */
 } phdslam_timings_t;
 /* CUDA-event timings of the most recent call of each phase (events on the handle's stream). */
 int phdslam_get_timings(phdslam_t* h, phdslam_timings_t* out);

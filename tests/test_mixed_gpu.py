@@ -172,3 +172,58 @@ def test_dynamic_map_capacity_is_reported():
     with pytest.raises(Exception) as e:
         g.phdUpdateSynth(Z)
     assert "dynamic" in str(e.value)
+
+
+def test_cli_writes_the_dynamic_map_line(tmp_path):
+    """The process interface with feature_model = 2 and the 7-line log layout of writeLog (src/main.cpp:848-954): line 3 is
+    the dynamic map of the maximum-weight particle, 21 numbers per component; the whole file equals the oracle's, text for
+    text, over steps that include resampling."""
+    import subprocess
+    from conftest import ROOT
+    import test_mixed_tracking as T
+    exe = os.path.join(ROOT, "cuda-phdslam_b200", "phdslam")
+    assert os.path.exists(exe), "CLI not built"
+    cfg = T.config(16)
+    zs = T.measurement_sets(cfg.dt)[:12]
+    data = tmp_path / "data"
+    data.mkdir()
+    with open(data / "measurements.txt", "w") as f:
+        f.write("header\n")
+        for Z in zs:
+            f.write(" ".join("%.9g" % v for v in Z.reshape(-1)) + "\n")
+    with open(data / "controls.txt", "w") as f:
+        f.write("header\n")
+        for _ in zs:
+            f.write("0 0\n")
+    cfgfile = tmp_path / "mixed.cfg"
+    keys = dict(feature_model=2, n_particles=16, motion_type=0, acc_x=0.2, acc_y=0.2, acc_yaw=0.01, dt=cfg.dt, max_range=cfg.max_range,
+                max_bearing=cfg.max_bearing, min_range=0, std_range=cfg.std_range, std_bearing=cfg.std_bearing, pd=cfg.pd,
+                clutter_rate=cfg.clutter_rate, birth_weight=cfg.birth_weight, birth_noise_factor=cfg.birth_noise_factor,
+                min_feature_weight=cfg.min_feature_weight, min_separation=cfg.min_separation, particle_weighting=0,
+                filter_type=0, map_estimate=1, resample_threshold=0.9, std_ax_features=0.3, std_ay_features=0.3,
+                cov_vx_birth=1.0, cov_vy_birth=1.0, tau=0.25, beta=8.0, ps=0.99, max_components=cfg.max_components,
+                max_components_dynamic=128, log_layout="extended", seed=4, data_directory=str(data) + "/")
+    with open(cfgfile, "w") as f:
+        for k, v in keys.items():
+            f.write("%s = %s\n" % (k, v))
+    out = tmp_path / "run"
+    r = subprocess.run([exe, str(cfgfile), "synth", "--out", str(out), "--steps", str(len(zs)), "--quiet"], capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ocfg = P.load_config(str(cfgfile))
+    o = O.Oracle(ocfg)
+    resampled_any = False
+    U = np.zeros((len(zs), 2), np.float32)
+    for k, Z in enumerate(zs):
+        e = o.step_filter(k, U[k - 1] if k else np.float32([0, 0]), Z)
+        ds, dm = o.get_maps_dynamic()
+        lo = int(ds[:e.map_particle].sum())
+        ref = tmp_path / ("ref%05d.log" % k)
+        P.write_log(str(ref), 1, e.pose, o.map_estimate(1), o.log_weights, o.poses, resample_idx=o.resample_idx,
+                    n_card=ocfg.max_cardinality + 1, map_dynamic=dm[lo:lo + ds[e.map_particle]])
+        resampled_any |= o.step_resample(len(Z), e)
+        got = open(out / ("state_estimate%05d.log" % k)).read()
+        assert got == open(ref).read(), "log of step %d differs" % k
+        lines = got.split("\n")
+        assert len(lines) == 8 and len(lines[2].split()) == 21 * int(ds[e.map_particle])
+    assert resampled_any
