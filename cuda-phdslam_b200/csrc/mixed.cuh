@@ -22,7 +22,7 @@
 #include "../../include/phd_mixed_math.h"
 
 #define DYN_PLANES 21          /* Gaussian4D: cov[16], mean[4], weight */
-#define DYN_THREADS 128
+#define DYN_THREADS 64
 #define DYN_WARPS (DYN_THREADS / 32)
 
 struct DynArgs {
@@ -151,10 +151,7 @@ __global__ void __launch_bounds__(DYN_THREADS) dyn_update_kernel(DynArgs a) {
   float* s_wb = s_L + PHD_MAX_MEAS;                                   /* birth weights */
   float* s_dm = s_wb + PHD_MAX_MEAS;                                  /* Vo: detection + birth weight sum per measurement */
   __shared__ int s_wcnt[DYN_WARPS];
-  __shared__ int s_ncand, s_nout, s_best, s_done;
-  __shared__ float s_bw[DYN_WARPS];
-  __shared__ unsigned s_bk[DYN_WARPS];
-  __shared__ int s_bi[DYN_WARPS];
+  __shared__ int s_ncand;
   const DevCfg& c = a.c;
   const int p = blockIdx.x, tid = threadIdx.x, lane = lane_id(), warp = warp_id();
   const int M = a.M, Dmax = a.Dmax, Sd = a.Sd;
@@ -168,7 +165,7 @@ __global__ void __launch_bounds__(DYN_THREADS) dyn_update_kernel(DynArgs a) {
     s_L[m] = L;
     s_wb[m] = phd_expf((dead ? PHD_LOG0 : c.log_birth_weight) - L);   /* :2266-2271, :2503-2528 */
   }
-  if (tid == 0) { s_ncand = 0; s_nout = 0; }
+  if (tid == 0) s_ncand = 0;
   __syncthreads();
 
   /* Vo's empty-map weighting sums every dynamic update weight (:2546-2563); canonical order as in the oracle's dyn_terms */
@@ -262,69 +259,135 @@ __global__ void __launch_bounds__(DYN_THREADS) dyn_update_kernel(DynArgs a) {
   __threadfence_block();
   __syncthreads();
 
-  /* ---- greedy merge (phdUpdateMergeKernel<Gaussian4D>); the stage buffers are dead: s_ev becomes the merged flags,
-   * s_idx / s_pre the member list of the current cluster ---- */
-  unsigned char* s_merged = reinterpret_cast<unsigned char*>(s_pre);     /* Sd bytes: fits (Sd <= Dmax * 128) */
-  int* s_members = reinterpret_cast<int*>(s_merged + ((Sd + 15) & ~15)); /* Sd ints */
-  for (int i = tid; i < n; i += DYN_THREADS) s_merged[i] = 0;
-  __syncthreads();
-  float* mo = a.dmap_out + (size_t)p * DYN_PLANES * Dmax;
-  for (;;) {
-    /* arg-max of the unmerged weights, ties as the reference's reduction tree breaks them */
-    float bw = -1.0f;
-    unsigned bk = 0xffffffffu;
-    int bi = -1;
-    for (int i = tid; i < n; i += DYN_THREADS) {
-      if (s_merged[i]) continue;
-      const float w = cand[i].weight;
-      const unsigned k = dyn_tie_key(i);
-      if (bi < 0 || bw < w || (bw == w && k < bk)) { bw = w; bk = k; bi = i; }
-    }
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-      const float ow = __shfl_xor_sync(FULL_MASK, bw, off);
-      const unsigned ok = __shfl_xor_sync(FULL_MASK, bk, off);
-      const int oi = __shfl_xor_sync(FULL_MASK, bi, off);
-      if (oi >= 0 && (bi < 0 || bw < ow || (bw == ow && ok < bk))) { bw = ow; bk = ok; bi = oi; }
-    }
-    if (lane == 0) { s_bw[warp] = bw; s_bk[warp] = bk; s_bi[warp] = bi; }
-    __syncthreads();
-    if (tid == 0) {
-      for (int q = 1; q < DYN_WARPS; ++q)
-        if (s_bi[q] >= 0 && (bi < 0 || bw < s_bw[q] || (bw == s_bw[q] && s_bk[q] < bk))) { bw = s_bw[q]; bk = s_bk[q]; bi = s_bi[q]; }
-      s_best = bi;
-      s_done = 0;
-    }
-    __syncthreads();
-    const int best = s_best;
-    if (best < 0) break;
-    const phdslam_gaussian4d_t seed = cand[best];
-    /* members: unmerged candidates closer than minSeparation (:2797-2812); 2 = member */
-    for (int i = tid; i < n; i += DYN_THREADS) {
-      if (s_merged[i]) continue;
-      const phdslam_gaussian4d_t g = cand[i];
-      const float dist = (c.distance_metric == 0) ? phd_g4_mahal(&seed, &g) : 0.0f;
-      if (dist < c.min_sep) s_merged[i] = 2;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      int nm = 0;
-      for (int i = 0; i < n; ++i)
-        if (s_merged[i] == 2) s_members[nm++] = i;
-      phdslam_gaussian4d_t mg;
-      if (!phd_g4_moment_match(cand, s_members, nm, &mg)) {
-        s_done = 1;                                   /* :2821-2822 */
-      } else {
-        for (int q = 0; q < nm; ++q) s_merged[s_members[q]] = 1;
-        if (s_nout < Dmax) dyn_store(mo, Dmax, s_nout, &mg);
-        else atomicOr(&a.red->err_flag, 8);
-        s_nout++;
-      }
-    }
-    __syncthreads();
-    if (s_done) break;
+  /* ---- greedy merge (phdUpdateMergeKernel<Gaussian4D>).  The stage buffers are dead: their shared memory now holds the
+   * merged flags, the candidate weights and the member list of the current cluster.  Every sum runs over the members in
+   * ascending candidate order, as phd_g4_moment_match (the oracle) does; the 21 sums of a cluster are independent, so 5
+   * threads take the weight and the mean sums and 16 threads the covariance sums. ---- */
+  unsigned char* s_merged = reinterpret_cast<unsigned char*>(dyn_smem);                 /* Sd bytes */
+  int* s_members = reinterpret_cast<int*>(dyn_smem + ((Sd + 15) & ~15));                /* Sd ints */
+  float* s_cw = reinterpret_cast<float*>(s_members + Sd);                               /* Sd floats */
+  /* the first n_sh candidates are staged in what is left of the block's shared memory (an L2 round trip per access
+   * otherwise: the rounds below are latency bound); the others stay where the update wrote them */
+  float* s_trp = s_cw + Sd;                                                             /* Sd floats: trace of the position block */
+  float* s_trv = s_trp + Sd;                                                            /* Sd floats: trace of the velocity block */
+  phdslam_gaussian4d_t* s_cand = reinterpret_cast<phdslam_gaussian4d_t*>(s_trv + Sd);
+  const int n_sh = min(n, (int)((dyn_smem_bytes(Dmax) - (size_t)(reinterpret_cast<unsigned char*>(s_cand) - dyn_smem)) /
+                                sizeof(phdslam_gaussian4d_t)));
+  __shared__ phdslam_gaussian4d_t s_seed, s_mg;
+  for (int i = tid; i < n; i += DYN_THREADS) {
+    s_merged[i] = 0;
+    s_cw[i] = cand[i].weight;
+    s_trp[i] = cand[i].cov[0] + cand[i].cov[5];
+    s_trv[i] = cand[i].cov[10] + cand[i].cov[15];
   }
-  if (tid == 0) a.dcount_out[p] = min(s_nout, Dmax);
+  for (int i = tid; i < n_sh * DYN_PLANES; i += DYN_THREADS)
+    reinterpret_cast<float*>(s_cand)[i] = reinterpret_cast<const float*>(cand)[i];
+  __syncthreads();
+#define DYN_CAND(i) (((i) < n_sh) ? (s_cand + (i)) : (cand + (i)))
+  float* mo = a.dmap_out + (size_t)p * DYN_PLANES * Dmax;
+  const float gk = 0.515625f * c.min_sep;
+  /* The rounds are short and strictly sequential: ONE warp runs them (warp barriers only, no block barrier per round; the
+   * other three warps wait at the end and leave their issue slots to the other blocks of the SM). */
+  if (warp == 0) {
+    int nout = 0;
+    for (;;) {
+      /* arg-max of the unmerged weights, ties as the reference's reduction tree breaks them */
+      float bw = -1.0f;
+      unsigned bk = 0xffffffffu;
+      int bi = -1;
+      for (int i = lane; i < n; i += 32) {
+        if (s_merged[i]) continue;
+        const float w = s_cw[i];
+        const unsigned k = dyn_tie_key(i);
+        if (bi < 0 || bw < w || (bw == w && k < bk)) { bw = w; bk = k; bi = i; }
+      }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        const float ow = __shfl_xor_sync(FULL_MASK, bw, off);
+        const unsigned ok = __shfl_xor_sync(FULL_MASK, bk, off);
+        const int oi = __shfl_xor_sync(FULL_MASK, bi, off);
+        if (oi >= 0 && (bi < 0 || bw < ow || (bw == ow && ok < bk))) { bw = ow; bk = ok; bi = oi; }
+      }
+      const int best = bi;
+      if (best < 0) break;
+      if (lane < DYN_PLANES) reinterpret_cast<float*>(&s_seed)[lane] = reinterpret_cast<const float*>(DYN_CAND(best))[lane];
+      __syncwarp();
+      /* members: unmerged candidates closer than minSeparation (:2797-2812), listed in ascending order */
+      int nm = 0;
+      for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        bool mem = false, need = false;
+        if (i < n && !s_merged[i]) {
+          if (i == best) {
+            mem = true;                       /* the seed opens its own cluster (distance 0) */
+          } else if (c.distance_metric == 0) {
+            /* canonical gate (oracle: merge_mixture4): outside it the Mahalanobis distance exceeds 1.03 minSeparation */
+            const phdslam_gaussian4d_t* gp = DYN_CAND(i);
+            const float g0 = s_seed.mean[0] - gp->mean[0], g1 = s_seed.mean[1] - gp->mean[1];
+            const float g2 = s_seed.mean[2] - gp->mean[2], g3 = s_seed.mean[3] - gp->mean[3];
+            need = (g0 * g0 + g1 * g1 <= gk * (s_trp[best] + s_trp[i])) && (g2 * g2 + g3 * g3 <= gk * (s_trv[best] + s_trv[i]));
+          } else {
+            mem = (0.0f < c.min_sep);         /* no 4-D Hellinger distance in the reference: 0 */
+          }
+        }
+        if (__any_sync(FULL_MASK, need)) {    /* most clusters are singletons: no lane needs the 4 x 4 factorisation */
+          if (need) {
+            const phdslam_gaussian4d_t g = *DYN_CAND(i);
+            mem = (phd_g4_mahal(&s_seed, &g) < c.min_sep);
+          }
+        }
+        const unsigned bal = __ballot_sync(FULL_MASK, mem);
+        if (mem) s_members[nm + __popc(bal & ((1u << lane) - 1u))] = i;
+        nm += __popc(bal);
+      }
+      __syncwarp();
+      if (lane < 5) {     /* weight sum and the four weighted mean sums (:2808-2829) */
+        float acc = 0.0f;
+        for (int q = 0; q < nm; ++q) {
+          const phdslam_gaussian4d_t* g = DYN_CAND(s_members[q]);
+          acc = (lane == 0) ? acc + g->weight : acc + g->weight * g->mean[lane - 1];
+        }
+        if (lane == 0) s_mg.weight = acc;
+        else s_mg.mean[lane - 1] = acc;
+      }
+      __syncwarp();
+      const float wsum = s_mg.weight;
+      if (wsum == 0.0f) break;                                         /* :2821-2822 */
+      const float rw = 1.0f / wsum;
+      if (lane < 16) {    /* covariance sums (:2836-2881), element j * 4 + k */
+        const int j4 = lane >> 2, k4 = lane & 3;
+        const float mj = s_mg.mean[j4] * rw, mk = s_mg.mean[k4] * rw;
+        float acc = 0.0f;
+        for (int q = 0; q < nm; ++q) {
+          const phdslam_gaussian4d_t* g = DYN_CAND(s_members[q]);
+          const float dj = mj - g->mean[j4], dk = mk - g->mean[k4];
+          acc = acc + g->weight * (g->cov[lane] + dj * dk);
+        }
+        s_mg.cov[lane] = acc * rw;
+      }
+      __syncwarp();
+      if (lane < DYN_PLANES) {
+        float v;
+        if (lane < 16) {                     /* force_symmetric_covariance: off-diagonal pairs averaged */
+          const int r4 = lane & 3, c4 = lane >> 2;
+          v = (r4 == c4) ? s_mg.cov[lane] : (s_mg.cov[lane] + s_mg.cov[c4 + 4 * r4]) / 2.0f;
+        } else if (lane < 20) {
+          v = s_mg.mean[lane - 16] * rw;
+        } else {
+          v = wsum;
+        }
+        if (nout < Dmax) mo[(size_t)lane * Dmax + nout] = v;
+      }
+      for (int q = lane; q < nm; q += 32) s_merged[s_members[q]] = 1;
+      __syncwarp();
+      nout++;
+    }
+    if (lane == 0) {
+      if (nout > Dmax) atomicOr(&a.red->err_flag, 8);
+      a.dcount_out[p] = min(nout, Dmax);
+    }
+  }
+#undef DYN_CAND
 }
 
 /* resampling: offspring j of this rank takes the dynamic map of its (local) ancestor */

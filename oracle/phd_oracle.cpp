@@ -708,11 +708,23 @@ static void dyn_terms(const phdslam_config_t& c, const Pose& pose, const std::ve
   *upd_sum = upd;
 }
 
-/* phdUpdateMergeKernel<Gaussian4D> (src/phdfilter.cu:2707-2898): as merge_mixture, without the spatial gate.  The
- * Hellinger metric has no 4-D form in the reference (the template returns 0, src/device_math.cuh:366-371), so with
- * distance_metric = 1 every candidate joins the first cluster. */
+/* phdUpdateMergeKernel<Gaussian4D> (src/phdfilter.cu:2707-2898): as merge_mixture.  The Hellinger metric has no 4-D form
+ * in the reference (the template returns 0, src/device_math.cuh:366-371), so with distance_metric = 1 every candidate
+ * joins the first cluster.  Canonical gate (Mahalanobis metric), the 4-D form of merge_mixture's: candidate b can join
+ * the cluster of seed a only if, for the position pair AND for the velocity pair of the state,
+ *     |d|^2 <= (0.515625 * minSeparation) * (tr P_a + tr P_b)      (d, P: that pair's difference and 2 x 2 block).
+ * The Mahalanobis distance of a sub-vector under its marginal never exceeds that of the whole vector, and the trace
+ * bounds the largest eigenvalue of a positive semi-definite block, so a candidate outside either gate has d_M^2 > 1.03 *
+ * minSeparation and the reference would not merge it either.  It spares the kernel a 4 x 4 factorisation for most pairs. */
 static void merge_mixture4(const phdslam_config_t& c, const std::vector<G4>& cand, std::vector<G4>& out) {
   const int n = (int)cand.size();
+  const bool gated = (c.distance_metric == 0);
+  const float gk = 0.515625f * c.min_separation;
+  std::vector<float> trp(n), trv(n);
+  for (int i = 0; i < n; ++i) {
+    trp[i] = cand[i].cov[0] + cand[i].cov[5];
+    trv[i] = cand[i].cov[10] + cand[i].cov[15];
+  }
   std::vector<char> merged(n, 0);
   std::vector<int> members;
   while (true) {
@@ -727,6 +739,16 @@ static void merge_mixture4(const phdslam_config_t& c, const std::vector<G4>& can
     members.clear();
     for (int i = 0; i < n; ++i) {
       if (merged[i]) continue;
+      if (i == best) {                       /* the seed opens its own cluster (distance 0) */
+        members.push_back(i);
+        continue;
+      }
+      if (gated) {
+        const float g0 = cand[best].mean[0] - cand[i].mean[0], g1 = cand[best].mean[1] - cand[i].mean[1];
+        const float g2 = cand[best].mean[2] - cand[i].mean[2], g3 = cand[best].mean[3] - cand[i].mean[3];
+        if (!(g0 * g0 + g1 * g1 <= gk * (trp[best] + trp[i]))) continue;
+        if (!(g2 * g2 + g3 * g3 <= gk * (trv[best] + trv[i]))) continue;
+      }
       const float dist = (c.distance_metric == 0) ? phd_g4_mahal(&cand[best], &cand[i]) : 0.0f;
       if (dist < c.min_separation) members.push_back(i);
     }

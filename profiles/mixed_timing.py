@@ -44,7 +44,7 @@ def main():
     a = ap.parse_args()
     n, Cs, Cd, M = a.particles, a.static, a.dynamic, a.meas
     kw = dict(MC.MIXED_OVERRIDES)
-    kw.update(max_components_dynamic=max(64, 4 * Cd), seed="3")
+    kw.update(max_components_dynamic=max(64, (Cd + M + 37) & ~7), seed="3")   # the map grows by the births of a step
     cfg = S.scene_config(n, Cs, M, max_components=2 * Cs, **kw)
     sc = S.make_scene(n, Cs, M, seed=0)
     dsz, dm, base = dynamic_maps(n, Cd, 1)
