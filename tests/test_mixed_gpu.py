@@ -87,14 +87,19 @@ def test_golden_cases_against_the_reference_kernels(name):
     MC.assert_gaussians_close(pred, gd["predicted"], name + " predicted", wfloor=1e-9)
 
 
-@pytest.mark.parametrize("labelled,weighting,metric", [(False, 0, 0), (True, 0, 0), (False, 1, 0), (True, 1, 0), (False, 0, 1)])
-def test_filter_steps_are_bit_identical_to_the_oracle(labelled, weighting, metric):
+@pytest.mark.parametrize("labelled,weighting,metric,mode", [(False, 0, 0, 0), (True, 0, 0, 0), (False, 1, 0, 0), (True, 1, 0, 0),
+                                                            (False, 0, 1, 0), (False, 0, 0, 1), (True, 1, 0, 1), (False, 0, 0, 2)])
+def test_filter_steps_are_bit_identical_to_the_oracle(labelled, weighting, metric, mode):
     """predict (poses + dynamic map), mixed update, estimate, resampling with injected and counter-based draws, over several
-    steps and 96 particles with different map sizes."""
+    steps and 96 particles with different map sizes.  mode 1: the fused update (update_mode = 1, no dense terms);
+    mode 2: the merge of one sub-batch overlapping the update of the next (phdslam_set_overlap)."""
     n, M = 96, 14
-    cfg = MC.mixed_config(n, M, labelled, weighting, distance_metric=metric, resample_threshold=1.1, seed="5")
+    cfg = MC.mixed_config(n, M, labelled, weighting, distance_metric=metric, resample_threshold=1.1, seed="5",
+                          update_mode=1 if mode == 1 else 0)
     sc = scene(n, 18, 6, M, labelled, seed=21 + weighting)
     g, o = P.PhdSlam(cfg), O.Oracle(cfg)
+    if mode == 2:
+        g.set_overlap(True)
     load(g, sc)
     load(o, sc)
     rng = np.random.default_rng(3)
