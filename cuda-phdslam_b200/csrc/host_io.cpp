@@ -85,7 +85,7 @@ static bool parse_bool(const char* v, int* out) {
   return false;
 }
 
-/* Keys the reference parses that are not on this path (disparity camera, dynamic features, dead options).
+/* Keys the reference parses that are not on this path (disparity camera, constant-position feature noise, dead options).
  * Accepted and ignored so that the reference's cfg files load unchanged. */
 static const char* kIgnoredKeys[] = {
     "debug", "initial_z", "initial_roll", "initial_pitch", "acc_z", "acc_roll", "acc_pitch", "gate_births",

@@ -22,7 +22,12 @@
  * "//" of every line removed; .bak: verbatim) and tests/test_cphd_ref_pin.py
  * compares this oracle with their outputs (golden: tests/golden/
  * ref_cphd_golden.npz): detection / non-detection weights, means, covariances,
- * log<Psi0,p> and the posterior cardinality within 1e-4.
+ * log<Psi0,p> and the posterior cardinality within 1e-4.  The mixed feature
+ * model (static + constant-velocity features, feature_model = 2) is pinned the
+ * same way: the reference's computeBirth / computePreUpdate on Gaussian4D,
+ * predictMapKernelMixed, phdUpdateKernelMixed and the Gaussian4D instance of
+ * phdUpdateMergeKernel run through the emulator (tests/test_mixed_ref_pin.py,
+ * tests/golden/ref_mixed_golden.npz, generator make_ref_mixed_golden.py).
  *
  * Arithmetic: fp32 in the reference's operation order, with the transcendental
  * functions of include/phd_detmath.h so that results are bit-reproducible on the
