@@ -407,4 +407,29 @@ __global__ void dyn_gather_kernel(const int* __restrict__ anc, int n_off, int n_
   }
 }
 
+/* Sharded particles: every rank's dynamic maps are all-gathered ([W][n_max] particles, rank blocks padded to the largest
+ * share) and an offspring takes the map of its GLOBAL ancestor, whichever rank owned it. */
+struct DynOwners {
+  int off[PHD_MAX_PEERS + 1];   /* first global particle of every rank */
+  int W, n_max;
+};
+__global__ void dyn_gather_global_kernel(const int* __restrict__ anc, int n_off, DynOwners ow, const float* __restrict__ all_map,
+                                         const int* __restrict__ all_count, float* __restrict__ dmap_out,
+                                         int* __restrict__ dcount_out, int Dmax) {
+  const int j = blockIdx.x;
+  if (j >= n_off) return;
+  const int g = anc[j];
+  int r = 0;
+  while (r + 1 < ow.W && g >= ow.off[r + 1]) ++r;
+  const size_t src_p = (size_t)r * ow.n_max + (size_t)(g - ow.off[r]);
+  const int cnt = all_count[src_p];
+  if (threadIdx.x == 0) dcount_out[j] = cnt;
+  const float* src = all_map + src_p * DYN_PLANES * Dmax;
+  float* dst = dmap_out + (size_t)j * DYN_PLANES * Dmax;
+  for (int i = threadIdx.x; i < DYN_PLANES * cnt; i += blockDim.x) {
+    const int k = i / cnt, q = i - k * cnt;
+    dst[(size_t)k * Dmax + q] = src[(size_t)k * Dmax + q];
+  }
+}
+
 #endif

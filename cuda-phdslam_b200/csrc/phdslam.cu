@@ -272,6 +272,8 @@ static void free_state(phdslam* h) {
   cudaFree(h->mig_pose_in); cudaFree(h->totals_dev); cudaFree(h->lfact); cudaFree(h->mig_anc2);
   for (int b = 0; b < 2; ++b) { cudaFree(h->dmap[b]); cudaFree(h->dcount[b]); h->dmap[b] = nullptr; h->dcount[b] = nullptr; }
   cudaFree(h->mix_dsum); cudaFree(h->mix_nhat); cudaFree(h->mix_L); cudaFree(h->dcand); cudaFree(h->snap_dmap); cudaFree(h->snap_dcount);
+  cudaFree(h->dyn_all_map); cudaFree(h->dyn_all_count);
+  h->dyn_all_map = nullptr; h->dyn_all_count = nullptr; h->dyn_all_cap = 0;
   h->mix_dsum = h->mix_nhat = h->mix_L = nullptr; h->dcand = nullptr; h->snap_dmap = nullptr; h->snap_dcount = nullptr;
   h->mig_pose_in = nullptr; h->totals_dev = nullptr; h->lfact = nullptr; h->mig_anc2 = nullptr; h->mig_anc_cap = 0;
   if (h->red_host) cudaFreeHost(h->red_host);
@@ -342,8 +344,10 @@ static int alloc_state(phdslam* h) {
   CK(cudaMalloc(&h->lfact, PHD_LF_MAX * sizeof(float)));
   if (h->Dmax) {
     for (int b = 0; b < 2; ++b) {
-      CK(cudaMalloc(&h->dmap[b], n * DYN_PLANES * (size_t)h->Dmax * sizeof(float)));
-      CK(cudaMalloc(&h->dcount[b], n * sizeof(int)));
+      /* one particle of slack: the all-gather of a sharded run sends every rank's block padded to the largest share */
+      CK(cudaMalloc(&h->dmap[b], (n + 1) * DYN_PLANES * (size_t)h->Dmax * sizeof(float)));
+      CK(cudaMalloc(&h->dcount[b], (n + 1) * sizeof(int)));
+      CK(cudaMemset(h->dcount[b], 0, (n + 1) * sizeof(int)));
     }
     CK(cudaMalloc(&h->mix_dsum, n * PHD_MAX_MEAS * sizeof(float)));
     CK(cudaMalloc(&h->mix_L, n * PHD_MAX_MEAS * sizeof(float)));
@@ -618,8 +622,8 @@ extern "C" int phdslam_dist_init(phdslam_t* h, int rank, int world, const void* 
     phdslam_set_error("libnccl.so.2 not found");
     return PHDSLAM_ERR_NCCL;
   }
-  if (h->cfg.feature_model == 2) {
-    phdslam_set_error("feature_model = 2 (mixed) is single-GPU: the dynamic maps are not part of the resampling exchange");
+  if (h->cfg.feature_model == 2 && world > PHD_MAX_PEERS) {
+    phdslam_set_error("feature_model = 2 (mixed): at most 8 ranks");
     return PHDSLAM_ERR_INVALID;
   }
   if (h->cfg.n_predict_particles > 1) {
@@ -1297,7 +1301,7 @@ extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms,
                                                               h->count[b], h->count[b ^ 1], h->map[b], h->map[b ^ 1],
                                                               h->card[b], h->card[b ^ 1], h->Cmax, h->n_card, 0, nullptr);
   LAUNCH_CHECK(h);
-  if (h->Dmax) {   /* copy_particles carries maps_dynamic too (src/slamtypes.h:324) */
+  if (h->Dmax && h->world == 1) {   /* copy_particles carries maps_dynamic too (src/slamtypes.h:324) */
     dyn_gather_kernel<<<n_off, 64, 0, h->stream>>>(h->ancestors, n_off, n, h->dmap[h->dcur], h->dcount[h->dcur],
                                                    h->dmap[h->dcur ^ 1], h->dcount[h->dcur ^ 1], h->Dmax);
     LAUNCH_CHECK(h);
@@ -1404,6 +1408,38 @@ extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms,
       }
       h->tim.migrated_in += (unsigned long long)cnt_in;
     }
+  }
+  if (h->Dmax && h->world > 1) {
+    /* Mixed feature model, sharded: h->ancestors now holds the GLOBAL ancestor of every local offspring (both exchange
+     * paths).  The dynamic maps are small, so they take the simple route: every rank's front buffer is all-gathered (rank
+     * blocks padded to the largest share) and each offspring copies its ancestor's map out of the gathered image. */
+    const int W = h->world;
+    DynOwners ow;
+    memset(&ow, 0, sizeof(ow));
+    ow.W = W;
+    int n_max = 0;
+    for (int r = 0; r <= W; ++r) ow.off[r] = rank_offset(h, r);
+    for (int r = 0; r < W; ++r) n_max = std::max(n_max, ow.off[r + 1] - ow.off[r]);
+    ow.n_max = n_max;
+    const size_t per = (size_t)DYN_PLANES * h->Dmax;
+    const size_t need = (size_t)W * n_max;
+    if (need * per * sizeof(float) > (16ull << 30)) {
+      phdslam_set_error("feature_model = 2, sharded: the all-gathered dynamic maps would exceed 16 GB (lower max_components_dynamic)");
+      return PHDSLAM_ERR_INVALID;
+    }
+    if (h->dyn_all_cap < need) {
+      cudaFree(h->dyn_all_map); cudaFree(h->dyn_all_count);
+      h->dyn_all_map = nullptr; h->dyn_all_count = nullptr; h->dyn_all_cap = 0;
+      CK(cudaMalloc(&h->dyn_all_map, need * per * sizeof(float)));
+      CK(cudaMalloc(&h->dyn_all_count, need * sizeof(int)));
+      h->dyn_all_cap = need;
+    }
+    ncclComm_t comm = (ncclComm_t)h->nccl_comm;
+    CKN(ncclAllGather(h->dcount[h->dcur], h->dyn_all_count, (size_t)n_max, ncclInt32, comm, h->stream));
+    CKN(ncclAllGather(h->dmap[h->dcur], h->dyn_all_map, (size_t)n_max * per, ncclFloat, comm, h->stream));
+    dyn_gather_global_kernel<<<n_off, 64, 0, h->stream>>>(h->ancestors, n_off, ow, h->dyn_all_map, h->dyn_all_count,
+                                                         h->dmap[h->dcur ^ 1], h->dcount[h->dcur ^ 1], h->Dmax);
+    LAUNCH_CHECK(h);
   }
   fill_kernel<<<cdiv(n_off, 256), 256, 0, h->stream>>>(h->logw, n_off, -phd_logf((float)n_new));
   LAUNCH_CHECK(h);
@@ -1651,7 +1687,7 @@ extern "C" int phdslam_map_estimate_dynamic(phdslam_t* h, phdslam_gaussian4d_t* 
   phdslam_estimate_t e;
   int rc = phdslam_estimate(h, &e);
   if (rc) return rc;
-  const int p = e.map_particle;
+  const int p = e.map_particle - h->offset;        /* sharded: only the rank that owns the particle returns its map */
   *n_out_p = 0;
   if (p < 0 || p >= h->n_local) return 0;
   const size_t D = h->Dmax, per = (size_t)DYN_PLANES * D;

@@ -142,6 +142,7 @@ struct phdslam {
   phdslam_gaussian4d_t* dcand;    /* [n][Sd] */
   float* snap_dmap; int* snap_dcount;
   cudaEvent_t ev_dyn[4];          /* around dyn_pre_kernel and dyn_update_kernel */
+  float* dyn_all_map; int* dyn_all_count; size_t dyn_all_cap;   /* sharded runs: all-gathered dynamic maps ([world][n_max] particles) */
 };
 
 #endif

@@ -160,10 +160,6 @@ def test_unsupported_combinations_fail_loudly():
         cfg = MC.S.scene_config_py(8, 8, 4, **ov)
         with pytest.raises(Exception):
             P.PhdSlam(cfg)
-    cfg = MC.mixed_config(4, 4)
-    g = P.PhdSlam(cfg)
-    with pytest.raises(Exception):
-        g.dist_init(0, 2, unique_id=P.dist_unique_id())
     # static feature model: no dynamic maps
     with pytest.raises(Exception):
         P.PhdSlam(MC.S.scene_config_py(4, 8, 4)).get_maps_dynamic()
@@ -232,3 +228,95 @@ def test_cli_writes_the_dynamic_map_line(tmp_path):
         lines = got.split("\n")
         assert len(lines) == 8 and len(lines[2].split()) == 21 * int(ds[e.map_particle])
     assert resampled_any
+
+
+# ---- particle sharding: one process per GPU; the dynamic maps travel with their particles at resampling ----
+def _sharded_worker(rank, world, uid, q, labelled, n):
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "cuda-phdslam_b200"))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import phdslam_b200 as P2
+    M = 12
+    cfg = MC.mixed_config(n, M, labelled, 0, resample_threshold=1.1, seed="6")
+    sc = scene(n, 14, 5, M, labelled, seed=33)
+    g = P2.PhdSlam(cfg, device=rank)
+    g.dist_init(rank, world, unique_id=uid)
+    lo, k = g.local_offset, g.n_local
+    so, do = np.concatenate([[0], np.cumsum(sc["ssz"])]), np.concatenate([[0], np.cumsum(sc["dsz"])])
+    g.poses = sc["poses"][lo:lo + k]
+    g.log_weights = np.full(k, -np.log(n), np.float32) + np.float32(np.linspace(-3, 0, n)[lo:lo + k])   # skewed: offspring cross GPUs
+    g.set_maps(sc["ssz"][lo:lo + k], sc["smaps"][so[lo]:so[lo + k]])
+    g.set_maps_dynamic(sc["dsz"][lo:lo + k], sc["dmaps"][do[lo]:do[lo + k]])
+    out = {}
+    rng = np.random.default_rng(12)
+    for step in range(3):
+        if step:
+            g.phdPredict(np.float32([1.0, 0.03]))
+        Z = MC.measurements(rng, np.zeros(1, MC.POSE)[0], sc["targets"], M, labelled, n_static=sc["ns"])
+        g.phdUpdateSynth(Z)
+        e = g.recoverSlamState()
+        out["est%d" % step] = (e.pose.copy(), e.map_particle, g.map_estimate_dynamic())
+        out["anc%d" % step] = g.resampleParticles(np.random.default_rng(50 + step).uniform(0, 1, n + 1) if step < 2 else None)
+        out["dyn%d" % step] = g.get_maps_dynamic()
+        out["sta%d" % step] = g.get_maps()
+        out["w%d" % step] = g.log_weights
+    out["migrated"] = g.timings().migrated_in
+    q.put((rank, lo, k, out))
+
+
+@pytest.mark.parametrize("p2p,labelled", [(1, False), (0, True)])
+def test_two_gpu_sharding_of_the_mixed_model_matches_oracle(p2p, labelled, monkeypatch):
+    import torch
+    world, n = 2, 75
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs (run with gpurun --gpus %d)" % (world, world))
+    monkeypatch.setenv("PHDSLAM_P2P", str(p2p))
+    import torch.multiprocessing as mp
+    uid = P.dist_unique_id()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, uid, q, labelled, n)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    M = 12
+    cfg = MC.mixed_config(n, M, labelled, 0, resample_threshold=1.1, seed="6")
+    sc = scene(n, 14, 5, M, labelled, seed=33)
+    o = O.Oracle(cfg)
+    load(o, sc)
+    o.log_weights = np.full(n, -np.log(n), np.float32) + np.float32(np.linspace(-3, 0, n))
+    rng = np.random.default_rng(12)
+    crossed = 0
+    for step in range(3):
+        if step:
+            o.phdPredict(np.float32([1.0, 0.03]))
+        Z = MC.measurements(rng, np.zeros(1, MC.POSE)[0], sc["targets"], M, labelled, n_static=sc["ns"])
+        o.phdUpdateSynth(Z)
+        e = o.recoverSlamState()
+        ds, dm = o.get_maps_dynamic()
+        lo = int(ds[:e.map_particle].sum())
+        owner = [r for r in res if r[1] <= e.map_particle < r[1] + r[2]][0]
+        for r in res:
+            pose, mp_, dyn = r[3]["est%d" % step]
+            assert pose.tobytes() == e.pose.tobytes() and mp_ == e.map_particle
+            if r is owner:
+                assert dyn.tobytes() == dm[lo:lo + ds[e.map_particle]].tobytes()
+            else:
+                assert len(dyn) == 0
+        anc = o.resampleParticles(np.random.default_rng(50 + step).uniform(0, 1, n + 1) if step < 2 else None)
+        assert (np.concatenate([r[3]["anc%d" % step] for r in res]) == anc).all()
+        own = lambda i: np.searchsorted([r[1] for r in res], i, side="right") - 1
+        crossed += int((own(np.arange(n)) != own(anc)).sum())
+        ods, odm = o.get_maps_dynamic()
+        oss, osm = o.get_maps()
+        assert (np.concatenate([r[3]["dyn%d" % step][0] for r in res]) == ods).all()
+        assert np.concatenate([r[3]["dyn%d" % step][1] for r in res]).tobytes() == odm.tobytes()
+        assert (np.concatenate([r[3]["sta%d" % step][0] for r in res]) == oss).all()
+        assert np.concatenate([r[3]["sta%d" % step][1] for r in res]).tobytes() == osm.tobytes()
+        assert np.concatenate([r[3]["w%d" % step] for r in res]).tobytes() == o.log_weights.tobytes()
+    assert crossed > 0 and sum(r[3]["migrated"] for r in res) > 0       # offspring (and their dynamic maps) crossed GPUs
