@@ -407,6 +407,23 @@ __global__ void dyn_gather_kernel(const int* __restrict__ anc, int n_off, int n_
   }
 }
 
+/* phdslam_particle_checksums: the dynamic map's share of a particle's checksum (size and live words, position-mixed like
+ * the static words of particle_checksum_kernel), added to what that kernel wrote */
+__global__ void dyn_checksum_add_kernel(const int* __restrict__ dcount, const float* __restrict__ dmap, int n, int Dmax,
+                                        unsigned long long* __restrict__ out) {
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= n) return;
+  const int lane = lane_id();
+  const int cnt = dcount[p];
+  unsigned long long acc = (lane == 0) ? checksum_mix((2ull << 32), (unsigned)cnt) : 0ull;
+  const float* m = dmap + (size_t)p * DYN_PLANES * Dmax;
+  for (int k = 0; k < DYN_PLANES; ++k)
+    for (int i = lane; i < cnt; i += 32)
+      acc += checksum_mix((2ull << 32) + 16ull + (unsigned long long)i * DYN_PLANES + k, __float_as_uint(m[(size_t)k * Dmax + i]));
+  acc = warp_sum_u64(acc);
+  if (lane == 0) out[p] += acc;
+}
+
 /* Sharded particles: every rank's dynamic maps are all-gathered ([W][n_max] particles, rank blocks padded to the largest
  * share) and an offspring takes the map of its GLOBAL ancestor, whichever rank owned it. */
 struct DynOwners {

@@ -1806,6 +1806,10 @@ extern "C" int phdslam_particle_checksums(phdslam_t* h, unsigned long long* out)
   particle_checksum_kernel<<<cdiv(n, 8), 256, 0, h->stream>>>(h->pose[h->cur], h->count[h->cur], h->map[h->cur], h->card[h->cur], n,
                                                              h->Cmax, h->n_card, h->q_fx);
   LAUNCH_CHECK(h);
+  if (h->Dmax) {
+    dyn_checksum_add_kernel<<<cdiv(n, 8), 256, 0, h->stream>>>(h->dcount[h->dcur], h->dmap[h->dcur], n, h->Dmax, h->q_fx);
+    LAUNCH_CHECK(h);
+  }
   CK(copy_d2h_async(h, out, h->q_fx, (size_t)n * sizeof(unsigned long long), h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return 0;

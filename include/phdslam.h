@@ -231,7 +231,7 @@ int phdslam_set_maps_dynamic(phdslam_t* h, const int* sizes, const phdslam_gauss
 int phdslam_map_estimate_dynamic(phdslam_t* h, phdslam_gaussian4d_t* out, int cap, int* n);
 
 /* One 64-bit checksum per local particle over what a resampled copy carries (src/slamtypes.h:313-333): pose, map size,
- * map components, CPHD cardinality row.  An offspring's checksum equals its ancestor's, whichever GPU owned the ancestor
+ * map components, CPHD cardinality row, and the dynamic map of the mixed feature model.  An offspring's checksum equals its ancestor's, whichever GPU owned the ancestor
  * (bench.py's exchange_check, tests/test_dist_gpu.py). */
 int phdslam_particle_checksums(phdslam_t* h, unsigned long long* out /* n_local */);
 

@@ -121,8 +121,10 @@ def test_filter_steps_are_bit_identical_to_the_oracle(labelled, weighting, metri
         lo = int(od[:eo.map_particle].sum())
         assert mg.tobytes() == odm[lo:lo + od[eo.map_particle]].tobytes()
         uu = rng.uniform(0, 1, n + 1) if k % 2 == 0 else None
+        pre = g.particle_checksums()
         ag, ao = g.resampleParticles(uu), o.resampleParticles(uu)
         assert (ag == ao).all()
+        assert (g.particle_checksums() == pre[ag]).all()       # every offspring carries its ancestor's maps, both of them
         assert_same_state(g, o, "step %d resample" % k)
     sizes = g.map_sizes_dynamic
     assert sizes.max() > 0 and len(np.unique(sizes)) >= 1
@@ -258,7 +260,9 @@ def _sharded_worker(rank, world, uid, q, labelled, n):
         g.phdUpdateSynth(Z)
         e = g.recoverSlamState()
         out["est%d" % step] = (e.pose.copy(), e.map_particle, g.map_estimate_dynamic())
+        out["pre%d" % step] = g.particle_checksums()
         out["anc%d" % step] = g.resampleParticles(np.random.default_rng(50 + step).uniform(0, 1, n + 1) if step < 2 else None)
+        out["post%d" % step] = g.particle_checksums()
         out["dyn%d" % step] = g.get_maps_dynamic()
         out["sta%d" % step] = g.get_maps()
         out["w%d" % step] = g.log_weights
@@ -310,6 +314,7 @@ def test_two_gpu_sharding_of_the_mixed_model_matches_oracle(p2p, labelled, monke
                 assert len(dyn) == 0
         anc = o.resampleParticles(np.random.default_rng(50 + step).uniform(0, 1, n + 1) if step < 2 else None)
         assert (np.concatenate([r[3]["anc%d" % step] for r in res]) == anc).all()
+        assert (np.concatenate([r[3]["post%d" % step] for r in res]) == np.concatenate([r[3]["pre%d" % step] for r in res])[anc]).all()
         own = lambda i: np.searchsorted([r[1] for r in res], i, side="right") - 1
         crossed += int((own(np.arange(n)) != own(anc)).sum())
         ods, odm = o.get_maps_dynamic()
