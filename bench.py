@@ -55,10 +55,18 @@ WORKLOADS = {
     # not fit one B200 (180 GB), so the sweep starts at N = 2.
     "synthetic_16777216x128x100_phd": dict(P=16777216, C=128, M=100, max_components=256, resample_threshold=1.0, strong=1,
                                            scene_particles=262144, update_buffer_bytes=16 << 30),
+    # SURVEY 8(f) rank 4, the mixed feature model: Cd constant-velocity features per particle next to the static map, a third
+    # of the measurements observing them (no BASELINE config).  updates = particles x (C + Cd) x M.
+    "synthetic_65536x128+16x50_mixed": dict(P=65536, C=128, M=50, max_components=256, Cd=16, max_components_dynamic=104,
+                                            feature_model=2, std_ax_features=0.5, std_ay_features=0.4, cov_vx_birth=0.25,
+                                            cov_vy_birth=0.36, tau=0.3, beta=4.0, ps=0.97),
+    "synthetic_4096x64+24x32_mixed": dict(P=4096, C=64, M=32, max_components=128, Cd=24, max_components_dynamic=96,
+                                          feature_model=2, std_ax_features=0.5, std_ay_features=0.4, cov_vx_birth=0.25,
+                                          cov_vy_birth=0.36, tau=0.3, beta=4.0, ps=0.97),
     "synthetic_2097152x128x100_phd": dict(P=2097152, C=128, M=100, max_components=256, resample_threshold=1.0, strong=1,
                                           scene_particles=65536, update_buffer_bytes=16 << 30),   # the same path, quick-check size
 }
-NON_CFG_KEYS = ("P", "C", "M", "max_components", "strong", "scene_particles")
+NON_CFG_KEYS = ("P", "C", "M", "max_components", "strong", "scene_particles", "Cd")
 DEFAULT_WORKLOAD = "synthetic_65536x256x64_phd"
 
 
@@ -67,16 +75,35 @@ def alg_bytes_per_update(C, M, n_card=0):
     return (28.0 * C + 28.0 * (C * (M + 1) + M) + 32.0 + 8.0 * n_card) / (C * M)
 
 
+def load_mixed(filt, S, wl, n, sc, particle_seed=None):
+    """Mixed feature model workloads: gives `filt` (PhdSlam or Oracle, n particles loaded from `sc`) its dynamic maps and
+    returns the measurement set with every third measurement observing a dynamic feature.  Other workloads: sc["Z"]."""
+    if not wl.get("Cd"):
+        return sc["Z"]
+    dsz, dm, base = S.make_dynamic_maps(n, wl["Cd"], seed=1, particle_seed=particle_seed)
+    filt.set_maps_dynamic(dsz, dm)
+    return S.mix_dynamic_measurements(sc["Z"], base)
+
+
+def pairs_per_particle(wl):
+    """(component, measurement) detection terms per particle and step: C x M, plus Cd x M in the mixed feature model"""
+    return (wl["C"] + wl.get("Cd", 0)) * wl["M"]
+
+
 def workload_config(name, wl, n_gpus):
     """the `config` object of a bench line: the same on both arms (what the workload is, not how a run went)"""
     strong = bool(wl.get("strong"))
     per = wl["P"] // n_gpus if strong else wl["P"]
-    return {"workload": name, "particles_per_gpu": per, "particles_total": wl["P"] if strong else wl["P"] * n_gpus,
-            "components": wl["C"], "measurements": wl["M"], "filter": "CPHD" if wl.get("filter_type") == 1 else "PHD",
-            "scaling": "strong" if strong else "weak",
-            # timing rule: no L2 flush between the timed steps because every step's inputs and outputs exceed the 126 MB L2
-            "cache": "inputs larger than L2 (map %.0f MB + dense update terms %.1f GB per step per GPU)"
-                     % (per * wl["C"] * 24 / 1e6, per * (wl["C"] * (wl["M"] + 1) + wl["M"]) * 28 / 1e9)}
+    cfg = {"workload": name, "particles_per_gpu": per, "particles_total": wl["P"] if strong else wl["P"] * n_gpus,
+           "components": wl["C"], "measurements": wl["M"], "filter": "CPHD" if wl.get("filter_type") == 1 else "PHD",
+           "scaling": "strong" if strong else "weak",
+           # timing rule: no L2 flush between the timed steps because every step's inputs and outputs exceed the 126 MB L2
+           "cache": "inputs larger than L2 (map %.0f MB + dense update terms %.1f GB per step per GPU)"
+                    % (per * wl["C"] * 24 / 1e6, per * (wl["C"] * (wl["M"] + 1) + wl["M"]) * 28 / 1e9)}
+    if wl.get("Cd"):
+        cfg["feature_model"] = "mixed (static + constant-velocity features)"
+        cfg["dynamic_components"] = wl["Cd"]
+    return cfg
 
 
 def measured_peaks():
@@ -241,10 +268,11 @@ def cpu_oracle_rate(wl, target_seconds=12.0, threads=None):
         sc = S.make_scene(Ps, C, M, seed=0)
         o = O.Oracle(cfg, threads=threads)
         S.load_scene(o, sc)
+        Zs = load_mixed(o, S, wl, Ps, sc)
         t0 = time.perf_counter()
-        o.step(1, np.float32([1.0, 0.05]), sc["Z"])
+        o.step(1, np.float32([1.0, 0.05]), Zs)
         dt = time.perf_counter() - t0
-        rate = Ps * C * M / dt
+        rate = Ps * pairs_per_particle(wl) / dt
         o.close()
         if dt >= 0.4 * target_seconds or attempt == 2:
             break
@@ -272,7 +300,7 @@ def run_reference(args, wl):
     r0, _, _, _, _ = cpu_oracle_rate(wl, target_seconds=3.0, threads=threads)
     r1 = cpu_oracle_single_thread_rate(wl, seconds=3.0)
     budget = 140.0 / max(args.steps + args.warmup, 1)
-    Ps = int(max(threads, min(wl["P"], r0 * min(budget, 20.0) / (C * M))))
+    Ps = int(max(threads, min(wl["P"], r0 * min(budget, 20.0) / pairs_per_particle(wl))))
     extra = {k: v for k, v in wl.items() if k not in NON_CFG_KEYS}
     cfg = S.scene_config_py(Ps, C, M, max_components=wl["max_components"], **extra)
     sc = S.make_scene(Ps, C, M, seed=0)
@@ -280,14 +308,15 @@ def run_reference(args, wl):
     for k in range(args.warmup + args.steps):
         o = O.Oracle(cfg, threads=threads)
         S.load_scene(o, sc)
+        Zs = load_mixed(o, S, wl, Ps, sc)
         t0 = time.perf_counter()
-        o.step(1, np.float32([1.0, 0.05]), sc["Z"])
+        o.step(1, np.float32([1.0, 0.05]), Zs)
         dt = time.perf_counter() - t0
         o.close()
         if k >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
-    value = Ps * C * M / (ms * 1e-3)
+    value = Ps * pairs_per_particle(wl) / (ms * 1e-3)
     sample = "%d of %d particles per step (C=%d, M=%d), full filter step, %d threads; oracle %s" % (Ps, wl["P"], C, M, threads, flags)
     assert not any("libphdslam" in l for l in open("/proc/self/maps")), "the reference arm must not load the product library"
     line = {
@@ -301,6 +330,8 @@ def run_reference(args, wl):
         "e2e": {"value": value, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if wl.get("Cd"):
+        line["metric"] = "GM-PHD updates/s (particle x (static + dynamic comp) x meas)"
     print(json.dumps(line))
 
 
@@ -415,8 +446,8 @@ def run_ours(args, wl):
         filt.import_tiled(sc)                # n_scene distinct particles, repeated on the device
     else:
         S.load_scene(filt, sc)
+    Z = load_mixed(filt, S, wl, n_scene, sc, particle_seed=rank)
     filt.snapshot()
-    Z = sc["Z"]
     u = np.float32([1.0, 0.05])
 
     def barrier():
@@ -436,7 +467,7 @@ def run_ours(args, wl):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    dev_ms, wall_ms, upd_ms, mrg_ms, other = [], [], [], [], []
+    dev_ms, wall_ms, upd_ms, mrg_ms, other, dyn_ms = [], [], [], [], [], []
     n_resampled = 0
     for k in range(args.steps):
         filt.restore()
@@ -457,6 +488,7 @@ def run_ours(args, wl):
         upd_ms.append(t.update_ms)
         mrg_ms.append(t.merge_ms)
         other.append((t.predict_ms, t.weights_ms, t.estimate_ms, t.resample_ms if res else 0.0))
+        dyn_ms.append(t.dynamic_ms)
     t_after = filt.timings()
     l_timed, mig_timed = t_after.launches, t_after.migrated_in
     # bytes the timed phdslam_step() calls moved between host and device, counted inside the library at every copy call
@@ -511,7 +543,7 @@ def run_ours(args, wl):
         dist.destroy_process_group()
     if rank != 0:
         return
-    updates_per_step = float(P_total) * C * M
+    updates_per_step = float(P_total) * pairs_per_particle(wl)
     ms_per_step = dev_total / args.steps
     value = updates_per_step / (ms_per_step * 1e-3)
     e2e_value = updates_per_step / (wall_total / args.steps * 1e-3)
@@ -566,6 +598,9 @@ def run_ours(args, wl):
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if wl.get("Cd"):
+        line["phase_ms"]["dynamic"] = float(np.mean(dyn_ms))      # dyn_pre_kernel + dyn_update_kernel (not in update / merge)
+        line["metric"] = "GM-PHD updates/s (particle x (static + dynamic comp) x meas)"
     if exchange is not None:
         line["exchange"] = exchange
         line["exchange_check"] = exchange_check

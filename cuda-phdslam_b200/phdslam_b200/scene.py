@@ -124,3 +124,40 @@ def load_scene(filt, sc):
     filt.poses = sc["poses"]
     filt.log_weights = sc["log_weights"]
     filt.set_maps(sc["sizes"], sc["maps"])
+
+
+# ---- mixed feature model (feature_model = 2): a dynamic map per particle next to the static scene ----
+MIXED_KEYS = dict(feature_model=2, std_ax_features=0.5, std_ay_features=0.4, cov_vx_birth=0.25, cov_vy_birth=0.36, tau=0.3, beta=4.0,
+                  ps=0.97)
+
+
+def make_dynamic_maps(n, Cd, seed=1, particle_seed=None, max_range=15.0):
+    """Cd constant-velocity features (Gaussian4D) in the field of view, the same for every particle up to a per-particle
+    jitter of the means (as make_scene jitters the static maps).  Returns (sizes[n], maps[n * Cd], the Cd base features)."""
+    from . import GAUSSIAN4_DTYPE
+    rng = np.random.Generator(np.random.Philox(seed))
+    prng = rng if particle_seed is None else np.random.Generator(np.random.Philox([seed, 2000003 + particle_seed]))
+    base = np.zeros(Cd, GAUSSIAN4_DTYPE)
+    r = np.sqrt(rng.uniform(1.0, (0.9 * max_range) ** 2, Cd))
+    a = rng.uniform(-3.0, 3.0, Cd)
+    for i in range(Cd):
+        q = rng.normal(0, 1, (4, 4))
+        q = q @ q.T / 4 + np.eye(4) * 0.5
+        sc = np.array([0.05, 0.05, 0.3, 0.3])
+        base["cov"][i] = (q * sc[:, None] * sc[None, :]).T.reshape(-1)
+        base["mean"][i] = (r[i] * np.cos(a[i]), r[i] * np.sin(a[i]), rng.normal(0, 0.5), rng.normal(0, 0.5))
+        base["weight"][i] = rng.uniform(0.2, 1.0)
+    maps = np.tile(base, n)
+    maps["mean"] += prng.normal(0, 0.05, maps["mean"].shape).astype(np.float32)
+    return np.full(n, Cd, np.int32), maps, base
+
+
+def mix_dynamic_measurements(Z, base, seed=2, every=3):
+    """every `every`-th measurement of the static scene is replaced by a noisy observation of a dynamic feature"""
+    Z = np.array(Z, np.float32).reshape(len(Z), -1).copy()
+    rng = np.random.Generator(np.random.Philox(seed))
+    for m in range(0, len(Z), every):
+        q = base["mean"][int(rng.integers(len(base))), :2]
+        Z[m, 0] = np.hypot(q[0], q[1]) + rng.normal(0, 0.25)
+        Z[m, 1] = np.arctan2(q[1], q[0]) + rng.normal(0, 0.0087)
+    return Z
