@@ -51,9 +51,14 @@ __device__ __forceinline__ void dyn_store(float* mp, int Dmax, int j, const phds
   for (int k = 0; k < DYN_PLANES; ++k) mp[(size_t)k * Dmax + j] = f[k];
 }
 
-__host__ __device__ static inline size_t dyn_smem_bytes(int Dmax) {
-  return (size_t)Dmax * (sizeof(phd_g4_pre_t) + sizeof(int) + DYN_WARPS * sizeof(float)) + 3 * PHD_MAX_MEAS * sizeof(float) +
-         PHD_MAX_MEAS * sizeof(float);
+/* Dynamic shared memory of dyn_pre_kernel / dyn_update_kernel: the stage buffers (pre-update constants, index list and one
+ * exponential array per warp for Dmax components, three per-measurement arrays), or -- they are dead by then -- the merge
+ * arrays of dyn_update_kernel (17 bytes per candidate) with at least the candidate capacity Sd. */
+__host__ __device__ static inline size_t dyn_smem_bytes(int Dmax, int M, int Sd) {
+  const size_t stage = (size_t)Dmax * (sizeof(phd_g4_pre_t) + sizeof(int) + DYN_WARPS * sizeof(float)) +
+                       3 * (size_t)((M + 3) & ~3) * sizeof(float);
+  const size_t merge = 17 * (size_t)Sd + 64;
+  return ((stage > merge ? stage : merge) + 15) & ~(size_t)15;
 }
 
 /* predictMapKernelMixed: every component of every particle, in place */
@@ -142,14 +147,117 @@ __global__ void __launch_bounds__(DYN_THREADS) dyn_pre_kernel(DynArgs a) {
 /* tie rule of the reference's arg-max reduction (oracle: merge_tie_key) */
 __device__ __forceinline__ unsigned dyn_tie_key(int i) { return (__brev((unsigned)i & 255u) >> 24 << 24) | ((unsigned)i >> 8); }
 
-__global__ void __launch_bounds__(DYN_THREADS) dyn_update_kernel(DynArgs a) {
+/* The greedy rounds of the dynamic map's merge, run by ONE warp.  Every sum runs over the members in ascending candidate
+ * order, as phd_g4_moment_match (the oracle) does; the 21 sums of a cluster are independent, so 5 lanes take the weight and
+ * the mean sums and 16 lanes the covariance sums.  ALL_SH: every candidate is staged in shared memory (the usual case).
+ * Returns the number of clusters. */
+template <bool ALL_SH>
+__device__ __forceinline__ int dyn_merge_rounds(const DevCfg& c, int n, int n_sh, const phdslam_gaussian4d_t* s_cand,
+                                                const phdslam_gaussian4d_t* cand, unsigned char* s_merged, int* s_members,
+                                                const float* s_cw, const float* s_trp, const float* s_trv, float* mo, int Dmax) {
+  __shared__ phdslam_gaussian4d_t s_mg;
+  const int lane = lane_id();
+  const float gk = 0.515625f * c.min_sep;
+  auto at = [&](int i) -> const phdslam_gaussian4d_t* { return (ALL_SH || i < n_sh) ? (s_cand + i) : (cand + i); };
+  int nout = 0;
+  for (;;) {
+    /* arg-max of the unmerged weights, ties as the reference's reduction tree breaks them: weights are non-negative, so
+     * their bit patterns order like the values, and the complement of the tie key makes "smallest key" a maximum too */
+    unsigned hi = 0, lo = 0;
+    for (int i = lane; i < n; i += 32) {
+      if (s_merged[i]) continue;
+      const unsigned h = __float_as_uint(s_cw[i]), l = ~dyn_tie_key(i);
+      if (h > hi || (h == hi && l > lo)) { hi = h; lo = l; }
+    }
+    const unsigned mh = __reduce_max_sync(FULL_MASK, hi);
+    const unsigned ml = __reduce_max_sync(FULL_MASK, (hi == mh) ? lo : 0u);
+    if (ml == 0u) break;                                  /* nothing left (a live candidate has a non-zero complement) */
+    const unsigned tk = ~ml;
+    const int best = (int)(((tk & 0xffffffu) << 8) | (__brev(tk >> 24) >> 24));
+    const phdslam_gaussian4d_t* sp = at(best);
+    const float s0 = sp->mean[0], s1 = sp->mean[1], s2 = sp->mean[2], s3 = sp->mean[3];
+    const float tp = s_trp[best], tv = s_trv[best];
+    /* members: unmerged candidates closer than minSeparation (:2797-2812), listed in ascending order */
+    int nm = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int i = i0 + lane;
+      bool mem = false, need = false;
+      if (i < n && !s_merged[i]) {
+        if (i == best) {
+          mem = true;                       /* the seed opens its own cluster (distance 0) */
+        } else if (c.distance_metric == 0) {
+          /* canonical gates (oracle: merge_mixture4): outside them the Mahalanobis distance exceeds 1.03 minSeparation */
+          const phdslam_gaussian4d_t* gp = at(i);
+          const float g0 = s0 - gp->mean[0], g1 = s1 - gp->mean[1], g2 = s2 - gp->mean[2], g3 = s3 - gp->mean[3];
+          need = (g0 * g0 + g1 * g1 <= gk * (tp + s_trp[i])) && (g2 * g2 + g3 * g3 <= gk * (tv + s_trv[i]));
+        } else {
+          mem = (0.0f < c.min_sep);         /* no 4-D Hellinger distance in the reference: 0 */
+        }
+      }
+      if (__any_sync(FULL_MASK, need)) {    /* most clusters are singletons: no lane needs the 4 x 4 factorisation */
+        if (need) {
+          const phdslam_gaussian4d_t sd = *sp, g = *at(i);
+          mem = (phd_g4_mahal(&sd, &g) < c.min_sep);
+        }
+      }
+      const unsigned bal = __ballot_sync(FULL_MASK, mem);
+      if (mem) s_members[nm + __popc(bal & ((1u << lane) - 1u))] = i;
+      nm += __popc(bal);
+    }
+    __syncwarp();
+    if (lane < 5) {     /* weight sum and the four weighted mean sums (:2808-2829) */
+      float acc = 0.0f;
+      for (int q = 0; q < nm; ++q) {
+        const phdslam_gaussian4d_t* g = at(s_members[q]);
+        acc = (lane == 0) ? acc + g->weight : acc + g->weight * g->mean[lane - 1];
+      }
+      if (lane == 0) s_mg.weight = acc;
+      else s_mg.mean[lane - 1] = acc;
+    }
+    __syncwarp();
+    const float wsum = s_mg.weight;
+    if (wsum == 0.0f) break;                                         /* :2821-2822 */
+    const float rw = 1.0f / wsum;
+    if (lane < 16) {    /* covariance sums (:2836-2881), element j * 4 + k */
+      const int j4 = lane >> 2, k4 = lane & 3;
+      const float mj = s_mg.mean[j4] * rw, mk = s_mg.mean[k4] * rw;
+      float acc = 0.0f;
+      for (int q = 0; q < nm; ++q) {
+        const phdslam_gaussian4d_t* g = at(s_members[q]);
+        const float dj = mj - g->mean[j4], dk = mk - g->mean[k4];
+        acc = acc + g->weight * (g->cov[lane] + dj * dk);
+      }
+      s_mg.cov[lane] = acc * rw;
+    }
+    __syncwarp();
+    if (lane < DYN_PLANES) {
+      float v;
+      if (lane < 16) {                     /* force_symmetric_covariance: off-diagonal pairs averaged */
+        const int r4 = lane & 3, c4 = lane >> 2;
+        v = (r4 == c4) ? s_mg.cov[lane] : (s_mg.cov[lane] + s_mg.cov[c4 + 4 * r4]) / 2.0f;
+      } else if (lane < 20) {
+        v = s_mg.mean[lane - 16] * rw;
+      } else {
+        v = wsum;
+      }
+      if (nout < Dmax) mo[(size_t)lane * Dmax + nout] = v;
+    }
+    for (int q = lane; q < nm; q += 32) s_merged[s_members[q]] = 1;
+    __syncwarp();
+    nout++;
+  }
+  return nout;
+}
+
+__global__ void __launch_bounds__(DYN_THREADS, 16) dyn_update_kernel(DynArgs a) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   phd_g4_pre_t* s_pre = reinterpret_cast<phd_g4_pre_t*>(dyn_smem);
   int* s_idx = reinterpret_cast<int*>(s_pre + a.Dmax);
   float* s_ev = reinterpret_cast<float*>(s_idx + a.Dmax);            /* [DYN_WARPS][Dmax] */
-  float* s_L = s_ev + (size_t)DYN_WARPS * a.Dmax;                     /* [PHD_MAX_MEAS] */
-  float* s_wb = s_L + PHD_MAX_MEAS;                                   /* birth weights */
-  float* s_dm = s_wb + PHD_MAX_MEAS;                                  /* Vo: detection + birth weight sum per measurement */
+  const int Mpad = (a.M + 3) & ~3;
+  float* s_L = s_ev + (size_t)DYN_WARPS * a.Dmax;                     /* [Mpad] log normalisers */
+  float* s_wb = s_L + Mpad;                                           /* birth weights */
+  float* s_dm = s_wb + Mpad;                                          /* Vo: detection + birth weight sum per measurement */
   __shared__ int s_wcnt[DYN_WARPS];
   __shared__ int s_ncand;
   const DevCfg& c = a.c;
@@ -259,21 +367,18 @@ __global__ void __launch_bounds__(DYN_THREADS) dyn_update_kernel(DynArgs a) {
   __threadfence_block();
   __syncthreads();
 
-  /* ---- greedy merge (phdUpdateMergeKernel<Gaussian4D>).  The stage buffers are dead: their shared memory now holds the
-   * merged flags, the candidate weights and the member list of the current cluster.  Every sum runs over the members in
-   * ascending candidate order, as phd_g4_moment_match (the oracle) does; the 21 sums of a cluster are independent, so 5
-   * threads take the weight and the mean sums and 16 threads the covariance sums. ---- */
-  unsigned char* s_merged = reinterpret_cast<unsigned char*>(dyn_smem);                 /* Sd bytes */
-  int* s_members = reinterpret_cast<int*>(dyn_smem + ((Sd + 15) & ~15));                /* Sd ints */
-  float* s_cw = reinterpret_cast<float*>(s_members + Sd);                               /* Sd floats */
-  /* the first n_sh candidates are staged in what is left of the block's shared memory (an L2 round trip per access
-   * otherwise: the rounds below are latency bound); the others stay where the update wrote them */
-  float* s_trp = s_cw + Sd;                                                             /* Sd floats: trace of the position block */
-  float* s_trv = s_trp + Sd;                                                            /* Sd floats: trace of the velocity block */
-  phdslam_gaussian4d_t* s_cand = reinterpret_cast<phdslam_gaussian4d_t*>(s_trv + Sd);
-  const int n_sh = min(n, (int)((dyn_smem_bytes(Dmax) - (size_t)(reinterpret_cast<unsigned char*>(s_cand) - dyn_smem)) /
+  /* ---- greedy merge (phdUpdateMergeKernel<Gaussian4D>).  The stage buffers are dead: their shared memory now holds, sized
+   * by the candidate count, the merged flags, the member list of the current cluster, the candidate weights and traces,
+   * and as many candidates as fit behind them (an L2 round trip per access otherwise: the rounds are latency bound);
+   * the others stay where the update wrote them. ---- */
+  unsigned char* s_merged = reinterpret_cast<unsigned char*>(dyn_smem);                 /* n bytes */
+  int* s_members = reinterpret_cast<int*>(dyn_smem + ((n + 15) & ~15));                 /* n ints */
+  float* s_cw = reinterpret_cast<float*>(s_members + n);                                /* n floats */
+  float* s_trp = s_cw + n;                                                              /* trace of the position block */
+  float* s_trv = s_trp + n;                                                             /* trace of the velocity block */
+  phdslam_gaussian4d_t* s_cand = reinterpret_cast<phdslam_gaussian4d_t*>(s_trv + n);
+  const int n_sh = min(n, (int)((dyn_smem_bytes(Dmax, M, Sd) - (size_t)(reinterpret_cast<unsigned char*>(s_cand) - dyn_smem)) /
                                 sizeof(phdslam_gaussian4d_t)));
-  __shared__ phdslam_gaussian4d_t s_seed, s_mg;
   for (int i = tid; i < n; i += DYN_THREADS) {
     s_merged[i] = 0;
     s_cw[i] = cand[i].weight;
@@ -283,111 +388,20 @@ __global__ void __launch_bounds__(DYN_THREADS) dyn_update_kernel(DynArgs a) {
   for (int i = tid; i < n_sh * DYN_PLANES; i += DYN_THREADS)
     reinterpret_cast<float*>(s_cand)[i] = reinterpret_cast<const float*>(cand)[i];
   __syncthreads();
-#define DYN_CAND(i) (((i) < n_sh) ? (s_cand + (i)) : (cand + (i)))
-  float* mo = a.dmap_out + (size_t)p * DYN_PLANES * Dmax;
-  const float gk = 0.515625f * c.min_sep;
   /* The rounds are short and strictly sequential: ONE warp runs them (warp barriers only, no block barrier per round; the
-   * other three warps wait at the end and leave their issue slots to the other blocks of the SM). */
+   * other warp leaves its issue slots to the other blocks of the SM). */
   if (warp == 0) {
-    int nout = 0;
-    for (;;) {
-      /* arg-max of the unmerged weights, ties as the reference's reduction tree breaks them */
-      float bw = -1.0f;
-      unsigned bk = 0xffffffffu;
-      int bi = -1;
-      for (int i = lane; i < n; i += 32) {
-        if (s_merged[i]) continue;
-        const float w = s_cw[i];
-        const unsigned k = dyn_tie_key(i);
-        if (bi < 0 || bw < w || (bw == w && k < bk)) { bw = w; bk = k; bi = i; }
-      }
-#pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) {
-        const float ow = __shfl_xor_sync(FULL_MASK, bw, off);
-        const unsigned ok = __shfl_xor_sync(FULL_MASK, bk, off);
-        const int oi = __shfl_xor_sync(FULL_MASK, bi, off);
-        if (oi >= 0 && (bi < 0 || bw < ow || (bw == ow && ok < bk))) { bw = ow; bk = ok; bi = oi; }
-      }
-      const int best = bi;
-      if (best < 0) break;
-      if (lane < DYN_PLANES) reinterpret_cast<float*>(&s_seed)[lane] = reinterpret_cast<const float*>(DYN_CAND(best))[lane];
-      __syncwarp();
-      /* members: unmerged candidates closer than minSeparation (:2797-2812), listed in ascending order */
-      int nm = 0;
-      for (int i0 = 0; i0 < n; i0 += 32) {
-        const int i = i0 + lane;
-        bool mem = false, need = false;
-        if (i < n && !s_merged[i]) {
-          if (i == best) {
-            mem = true;                       /* the seed opens its own cluster (distance 0) */
-          } else if (c.distance_metric == 0) {
-            /* canonical gate (oracle: merge_mixture4): outside it the Mahalanobis distance exceeds 1.03 minSeparation */
-            const phdslam_gaussian4d_t* gp = DYN_CAND(i);
-            const float g0 = s_seed.mean[0] - gp->mean[0], g1 = s_seed.mean[1] - gp->mean[1];
-            const float g2 = s_seed.mean[2] - gp->mean[2], g3 = s_seed.mean[3] - gp->mean[3];
-            need = (g0 * g0 + g1 * g1 <= gk * (s_trp[best] + s_trp[i])) && (g2 * g2 + g3 * g3 <= gk * (s_trv[best] + s_trv[i]));
-          } else {
-            mem = (0.0f < c.min_sep);         /* no 4-D Hellinger distance in the reference: 0 */
-          }
-        }
-        if (__any_sync(FULL_MASK, need)) {    /* most clusters are singletons: no lane needs the 4 x 4 factorisation */
-          if (need) {
-            const phdslam_gaussian4d_t g = *DYN_CAND(i);
-            mem = (phd_g4_mahal(&s_seed, &g) < c.min_sep);
-          }
-        }
-        const unsigned bal = __ballot_sync(FULL_MASK, mem);
-        if (mem) s_members[nm + __popc(bal & ((1u << lane) - 1u))] = i;
-        nm += __popc(bal);
-      }
-      __syncwarp();
-      if (lane < 5) {     /* weight sum and the four weighted mean sums (:2808-2829) */
-        float acc = 0.0f;
-        for (int q = 0; q < nm; ++q) {
-          const phdslam_gaussian4d_t* g = DYN_CAND(s_members[q]);
-          acc = (lane == 0) ? acc + g->weight : acc + g->weight * g->mean[lane - 1];
-        }
-        if (lane == 0) s_mg.weight = acc;
-        else s_mg.mean[lane - 1] = acc;
-      }
-      __syncwarp();
-      const float wsum = s_mg.weight;
-      if (wsum == 0.0f) break;                                         /* :2821-2822 */
-      const float rw = 1.0f / wsum;
-      if (lane < 16) {    /* covariance sums (:2836-2881), element j * 4 + k */
-        const int j4 = lane >> 2, k4 = lane & 3;
-        const float mj = s_mg.mean[j4] * rw, mk = s_mg.mean[k4] * rw;
-        float acc = 0.0f;
-        for (int q = 0; q < nm; ++q) {
-          const phdslam_gaussian4d_t* g = DYN_CAND(s_members[q]);
-          const float dj = mj - g->mean[j4], dk = mk - g->mean[k4];
-          acc = acc + g->weight * (g->cov[lane] + dj * dk);
-        }
-        s_mg.cov[lane] = acc * rw;
-      }
-      __syncwarp();
-      if (lane < DYN_PLANES) {
-        float v;
-        if (lane < 16) {                     /* force_symmetric_covariance: off-diagonal pairs averaged */
-          const int r4 = lane & 3, c4 = lane >> 2;
-          v = (r4 == c4) ? s_mg.cov[lane] : (s_mg.cov[lane] + s_mg.cov[c4 + 4 * r4]) / 2.0f;
-        } else if (lane < 20) {
-          v = s_mg.mean[lane - 16] * rw;
-        } else {
-          v = wsum;
-        }
-        if (nout < Dmax) mo[(size_t)lane * Dmax + nout] = v;
-      }
-      for (int q = lane; q < nm; q += 32) s_merged[s_members[q]] = 1;
-      __syncwarp();
-      nout++;
-    }
+    float* mo = a.dmap_out + (size_t)p * DYN_PLANES * Dmax;
+    int nout;
+    if (n_sh == n)
+      nout = dyn_merge_rounds<true>(c, n, n_sh, s_cand, cand, s_merged, s_members, s_cw, s_trp, s_trv, mo, Dmax);
+    else
+      nout = dyn_merge_rounds<false>(c, n, n_sh, s_cand, cand, s_merged, s_members, s_cw, s_trp, s_trv, mo, Dmax);
     if (lane == 0) {
       if (nout > Dmax) atomicOr(&a.red->err_flag, 8);
       a.dcount_out[p] = min(nout, Dmax);
     }
   }
-#undef DYN_CAND
 }
 
 /* resampling: offspring j of this rank takes the dynamic map of its (local) ancestor */

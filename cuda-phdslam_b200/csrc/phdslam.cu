@@ -459,8 +459,8 @@ static int create_impl(phdslam* h, const phdslam_config_t* cfg, int device) {
   if (h->Dmax) {
     CK(cudaFuncSetAttribute(update_mixed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(h->Cmax)));
     CK(cudaFuncSetAttribute(update_mixed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(h->Cmax)));
-    CK(cudaFuncSetAttribute(dyn_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem_bytes(h->Dmax)));
-    CK(cudaFuncSetAttribute(dyn_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem_bytes(h->Dmax)));
+    CK(cudaFuncSetAttribute(dyn_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem_bytes(h->Dmax, PHD_MAX_MEAS, h->Sd)));
+    CK(cudaFuncSetAttribute(dyn_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem_bytes(h->Dmax, PHD_MAX_MEAS, h->Sd)));
   }
   CK(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem_bytes(h->Smax)));
   {
@@ -993,7 +993,7 @@ extern "C" int phdslam_update(phdslam_t* h, const float* z, int M, int fields) {
   CK(cudaMemsetAsync(h->red, 0, sizeof(Reductions), h->stream));
   if (h->Dmax) {   /* what the dynamic features add to the normalisers and the predicted cardinality of the static update */
     CK(cudaEventRecord(h->ev_dyn[0], h->stream));
-    dyn_pre_kernel<<<h->n_local, DYN_THREADS, dyn_smem_bytes(h->Dmax), h->stream>>>(dyn_args(h, M));
+    dyn_pre_kernel<<<h->n_local, DYN_THREADS, dyn_smem_bytes(h->Dmax, M, h->Sd), h->stream>>>(dyn_args(h, M));
     LAUNCH_CHECK(h);
     CK(cudaEventRecord(h->ev_dyn[1], h->stream));
   }
@@ -1044,7 +1044,7 @@ extern "C" int phdslam_update(phdslam_t* h, const float* z, int M, int fields) {
   }
   if (h->Dmax) {   /* the dynamic map: update terms, prune, merge (after the static update wrote the normalisers) */
     CK(cudaEventRecord(h->ev_dyn[2], h->stream));
-    dyn_update_kernel<<<h->n_local, DYN_THREADS, dyn_smem_bytes(h->Dmax), h->stream>>>(dyn_args(h, M));
+    dyn_update_kernel<<<h->n_local, DYN_THREADS, dyn_smem_bytes(h->Dmax, M, h->Sd), h->stream>>>(dyn_args(h, M));
     LAUNCH_CHECK(h);
     CK(cudaEventRecord(h->ev_dyn[3], h->stream));
   }
