@@ -404,13 +404,16 @@ __global__ void __launch_bounds__(DYN_THREADS, 16) dyn_update_kernel(DynArgs a) 
   }
 }
 
-/* resampling: offspring j of this rank takes the dynamic map of its (local) ancestor */
-__global__ void dyn_gather_kernel(const int* __restrict__ anc, int n_off, int n_src, const float* __restrict__ dmap_in,
-                                  const int* __restrict__ dcount_in, float* __restrict__ dmap_out, int* __restrict__ dcount_out,
-                                  int Dmax) {
+/* Resampling: offspring j takes the dynamic map of ancestor anc[j] - anc_offset of THIS rank; offspring whose ancestor
+ * lives elsewhere (index outside [0, n_src)) are left alone -- the exchange below fills them.  The same kernel packs the
+ * maps an outgoing interval of offspring needs into the staging buffer that is sent to their owner. */
+__global__ void dyn_gather_kernel(const int* __restrict__ anc, int n_off, int anc_offset, int n_src,
+                                  const float* __restrict__ dmap_in, const int* __restrict__ dcount_in,
+                                  float* __restrict__ dmap_out, int* __restrict__ dcount_out, int Dmax) {
   const int j = blockIdx.x;
   if (j >= n_off) return;
-  const int a = anc[j];
+  const int a = anc[j] - anc_offset;
+  if (a < 0 || a >= n_src) return;
   const int cnt = dcount_in[a];
   if (threadIdx.x == 0) dcount_out[j] = cnt;
   const float* src = dmap_in + (size_t)a * DYN_PLANES * Dmax;
@@ -436,31 +439,6 @@ __global__ void dyn_checksum_add_kernel(const int* __restrict__ dcount, const fl
       acc += checksum_mix((2ull << 32) + 16ull + (unsigned long long)i * DYN_PLANES + k, __float_as_uint(m[(size_t)k * Dmax + i]));
   acc = warp_sum_u64(acc);
   if (lane == 0) out[p] += acc;
-}
-
-/* Sharded particles: every rank's dynamic maps are all-gathered ([W][n_max] particles, rank blocks padded to the largest
- * share) and an offspring takes the map of its GLOBAL ancestor, whichever rank owned it. */
-struct DynOwners {
-  int off[PHD_MAX_PEERS + 1];   /* first global particle of every rank */
-  int W, n_max;
-};
-__global__ void dyn_gather_global_kernel(const int* __restrict__ anc, int n_off, DynOwners ow, const float* __restrict__ all_map,
-                                         const int* __restrict__ all_count, float* __restrict__ dmap_out,
-                                         int* __restrict__ dcount_out, int Dmax) {
-  const int j = blockIdx.x;
-  if (j >= n_off) return;
-  const int g = anc[j];
-  int r = 0;
-  while (r + 1 < ow.W && g >= ow.off[r + 1]) ++r;
-  const size_t src_p = (size_t)r * ow.n_max + (size_t)(g - ow.off[r]);
-  const int cnt = all_count[src_p];
-  if (threadIdx.x == 0) dcount_out[j] = cnt;
-  const float* src = all_map + src_p * DYN_PLANES * Dmax;
-  float* dst = dmap_out + (size_t)j * DYN_PLANES * Dmax;
-  for (int i = threadIdx.x; i < DYN_PLANES * cnt; i += blockDim.x) {
-    const int k = i / cnt, q = i - k * cnt;
-    dst[(size_t)k * Dmax + q] = src[(size_t)k * Dmax + q];
-  }
 }
 
 #endif

@@ -272,8 +272,8 @@ static void free_state(phdslam* h) {
   cudaFree(h->mig_pose_in); cudaFree(h->totals_dev); cudaFree(h->lfact); cudaFree(h->mig_anc2);
   for (int b = 0; b < 2; ++b) { cudaFree(h->dmap[b]); cudaFree(h->dcount[b]); h->dmap[b] = nullptr; h->dcount[b] = nullptr; }
   cudaFree(h->mix_dsum); cudaFree(h->mix_nhat); cudaFree(h->mix_L); cudaFree(h->dcand); cudaFree(h->snap_dmap); cudaFree(h->snap_dcount);
-  cudaFree(h->dyn_all_map); cudaFree(h->dyn_all_count);
-  h->dyn_all_map = nullptr; h->dyn_all_count = nullptr; h->dyn_all_cap = 0;
+  cudaFree(h->dyn_mig_map); cudaFree(h->dyn_mig_count); cudaFree(h->dyn_mig_anc);
+  h->dyn_mig_map = nullptr; h->dyn_mig_count = nullptr; h->dyn_mig_anc = nullptr; h->dyn_mig_cap = 0;
   h->mix_dsum = h->mix_nhat = h->mix_L = nullptr; h->dcand = nullptr; h->snap_dmap = nullptr; h->snap_dcount = nullptr;
   h->mig_pose_in = nullptr; h->totals_dev = nullptr; h->lfact = nullptr; h->mig_anc2 = nullptr; h->mig_anc_cap = 0;
   if (h->red_host) cudaFreeHost(h->red_host);
@@ -1302,7 +1302,7 @@ extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms,
                                                               h->card[b], h->card[b ^ 1], h->Cmax, h->n_card, 0, nullptr);
   LAUNCH_CHECK(h);
   if (h->Dmax && h->world == 1) {   /* copy_particles carries maps_dynamic too (src/slamtypes.h:324) */
-    dyn_gather_kernel<<<n_off, 64, 0, h->stream>>>(h->ancestors, n_off, n, h->dmap[h->dcur], h->dcount[h->dcur],
+    dyn_gather_kernel<<<n_off, 64, 0, h->stream>>>(h->ancestors, n_off, 0, n, h->dmap[h->dcur], h->dcount[h->dcur],
                                                    h->dmap[h->dcur ^ 1], h->dcount[h->dcur ^ 1], h->Dmax);
     LAUNCH_CHECK(h);
   }
@@ -1410,36 +1410,58 @@ extern "C" int phdslam_resample(phdslam_t* h, int n_new, const double* uniforms,
     }
   }
   if (h->Dmax && h->world > 1) {
-    /* Mixed feature model, sharded: h->ancestors now holds the GLOBAL ancestor of every local offspring (both exchange
-     * paths).  The dynamic maps are small, so they take the simple route: every rank's front buffer is all-gathered (rank
-     * blocks padded to the largest share) and each offspring copies its ancestor's map out of the gathered image. */
-    const int W = h->world;
-    DynOwners ow;
-    memset(&ow, 0, sizeof(ow));
-    ow.W = W;
-    int n_max = 0;
-    for (int r = 0; r <= W; ++r) ow.off[r] = rank_offset(h, r);
-    for (int r = 0; r < W; ++r) n_max = std::max(n_max, ow.off[r + 1] - ow.off[r]);
-    ow.n_max = n_max;
-    const size_t per = (size_t)DYN_PLANES * h->Dmax;
-    const size_t need = (size_t)W * n_max;
-    if (need * per * sizeof(float) > (16ull << 30)) {
-      phdslam_set_error("feature_model = 2, sharded: the all-gathered dynamic maps would exceed 16 GB (lower max_components_dynamic)");
-      return PHDSLAM_ERR_INVALID;
-    }
-    if (h->dyn_all_cap < need) {
-      cudaFree(h->dyn_all_map); cudaFree(h->dyn_all_count);
-      h->dyn_all_map = nullptr; h->dyn_all_count = nullptr; h->dyn_all_cap = 0;
-      CK(cudaMalloc(&h->dyn_all_map, need * per * sizeof(float)));
-      CK(cudaMalloc(&h->dyn_all_count, need * sizeof(int)));
-      h->dyn_all_cap = need;
-    }
+    /* Mixed feature model, sharded: the dynamic maps follow their offspring.  h->ancestors now holds the GLOBAL ancestor
+     * of every local offspring (both exchange paths): offspring with a local ancestor copy its dynamic map here; for the
+     * others the ring below repeats the shape of the static ring -- in shift k this rank serves rank+k and is served by
+     * rank-k, both ends derive the offspring interval from `bounds`, the serving side searches the interval's ancestors
+     * again, packs their dynamic maps and sends them; they land directly in the owner's back buffer.  (The dynamic maps are
+     * not in the NVLink peer window: NCCL moves them in both exchange modes.) */
     ncclComm_t comm = (ncclComm_t)h->nccl_comm;
-    CKN(ncclAllGather(h->dcount[h->dcur], h->dyn_all_count, (size_t)n_max, ncclInt32, comm, h->stream));
-    CKN(ncclAllGather(h->dmap[h->dcur], h->dyn_all_map, (size_t)n_max * per, ncclFloat, comm, h->stream));
-    dyn_gather_global_kernel<<<n_off, 64, 0, h->stream>>>(h->ancestors, n_off, ow, h->dyn_all_map, h->dyn_all_count,
-                                                         h->dmap[h->dcur ^ 1], h->dcount[h->dcur ^ 1], h->Dmax);
+    const size_t per = (size_t)DYN_PLANES * h->Dmax;
+    const int me = h->rank, W = h->world;
+    const int db = h->dcur;
+    dyn_gather_kernel<<<n_off, 64, 0, h->stream>>>(h->ancestors, n_off, h->offset, n, h->dmap[db], h->dcount[db], h->dmap[db ^ 1],
+                                                   h->dcount[db ^ 1], h->Dmax);
     LAUNCH_CHECK(h);
+    for (int k = 1; k < W; ++k) {
+      const int d = (me + k) % W, sr = (me - k + W) % W;
+      const int off_d = rank_offset(h, d), end_d = rank_offset(h, d + 1);
+      const int out_lo = std::max(bounds[me], off_d), out_hi = std::min(bounds[me + 1], end_d);
+      const int cnt_out = std::max(out_hi - out_lo, 0);
+      const int in_lo = std::max(bounds[sr], h->offset), in_hi = std::min(bounds[sr + 1], h->offset + n);
+      const int cnt_in = std::max(in_hi - in_lo, 0);
+      if (cnt_out > 0) {
+        if (h->dyn_mig_cap < (size_t)cnt_out) {
+          cudaFree(h->dyn_mig_map); cudaFree(h->dyn_mig_count); cudaFree(h->dyn_mig_anc);
+          h->dyn_mig_map = nullptr; h->dyn_mig_count = nullptr; h->dyn_mig_anc = nullptr; h->dyn_mig_cap = 0;
+          const size_t cap = (size_t)cnt_out + (size_t)cnt_out / 4 + 64;
+          CK(cudaMalloc(&h->dyn_mig_map, cap * per * sizeof(float)));
+          CK(cudaMalloc(&h->dyn_mig_count, cap * sizeof(int)));
+          CK(cudaMalloc(&h->dyn_mig_anc, cap * sizeof(int)));
+          h->dyn_mig_cap = cap;
+        }
+        resample_search_kernel<<<cdiv(cnt_out, 256), 256, 0, h->stream>>>(h->cdf_excl, n, base, total, n_new, out_lo, cnt_out, h->offset,
+                                                                        udev, sysmode, h->resample_calls, h->dc.seed_lo,
+                                                                        h->dc.seed_hi, h->dyn_mig_anc);
+        LAUNCH_CHECK(h);
+        dyn_gather_kernel<<<cnt_out, 64, 0, h->stream>>>(h->dyn_mig_anc, cnt_out, h->offset, n, h->dmap[db], h->dcount[db],
+                                                         h->dyn_mig_map, h->dyn_mig_count, h->Dmax);
+        LAUNCH_CHECK(h);
+      }
+      if (cnt_out > 0 || cnt_in > 0) {
+        CKN(ncclGroupStart());
+        if (cnt_out > 0) {
+          CKN(ncclSend(h->dyn_mig_count, (size_t)cnt_out, ncclInt32, d, comm, h->stream));
+          CKN(ncclSend(h->dyn_mig_map, (size_t)cnt_out * per, ncclFloat, d, comm, h->stream));
+        }
+        if (cnt_in > 0) {
+          const size_t first = (size_t)(in_lo - h->offset);
+          CKN(ncclRecv(h->dcount[db ^ 1] + first, (size_t)cnt_in, ncclInt32, sr, comm, h->stream));
+          CKN(ncclRecv(h->dmap[db ^ 1] + first * per, (size_t)cnt_in * per, ncclFloat, sr, comm, h->stream));
+        }
+        CKN(ncclGroupEnd());
+      }
+    }
   }
   fill_kernel<<<cdiv(n_off, 256), 256, 0, h->stream>>>(h->logw, n_off, -phd_logf((float)n_new));
   LAUNCH_CHECK(h);

@@ -142,7 +142,7 @@ struct phdslam {
   phdslam_gaussian4d_t* dcand;    /* [n][Sd] */
   float* snap_dmap; int* snap_dcount;
   cudaEvent_t ev_dyn[4];          /* around dyn_pre_kernel and dyn_update_kernel */
-  float* dyn_all_map; int* dyn_all_count; size_t dyn_all_cap;   /* sharded runs: all-gathered dynamic maps ([world][n_max] particles) */
+  float* dyn_mig_map; int* dyn_mig_count; int* dyn_mig_anc; size_t dyn_mig_cap;   /* sharded runs: staging of the dynamic maps sent to another rank */
 };
 
 #endif
