@@ -622,10 +622,6 @@ extern "C" int phdslam_dist_init(phdslam_t* h, int rank, int world, const void* 
     phdslam_set_error("libnccl.so.2 not found");
     return PHDSLAM_ERR_NCCL;
   }
-  if (h->cfg.feature_model == 2 && world > PHD_MAX_PEERS) {
-    phdslam_set_error("feature_model = 2 (mixed): at most 8 ranks");
-    return PHDSLAM_ERR_INVALID;
-  }
   if (h->cfg.n_predict_particles > 1) {
     phdslam_set_error("n_predict_particles > 1 changes the particle count every step and is single-GPU only");
     return PHDSLAM_ERR_INVALID;
