@@ -270,10 +270,12 @@ def _sharded_worker(rank, world, uid, q, labelled, n):
     q.put((rank, lo, k, out))
 
 
-@pytest.mark.parametrize("p2p,labelled", [(1, False), (0, True)])
-def test_two_gpu_sharding_of_the_mixed_model_matches_oracle(p2p, labelled, monkeypatch):
+@pytest.mark.parametrize("world,p2p,labelled", [(2, 1, False), (2, 0, True), (4, 1, False), (3, 0, False)])
+def test_sharding_of_the_mixed_model_matches_oracle(world, p2p, labelled, monkeypatch):
+    """2 GPUs: one shift of the dynamic-map ring; 3 and 4 GPUs (a particle count the world size does not divide): the general
+    ring.  Both exchange modes of the static maps."""
     import torch
-    world, n = 2, 75
+    n = 75
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs (run with gpurun --gpus %d)" % (world, world))
     monkeypatch.setenv("PHDSLAM_P2P", str(p2p))
