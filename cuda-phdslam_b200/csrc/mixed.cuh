@@ -13,8 +13,10 @@
  *                       measurement, and sum of pd * w  -> mix_dsum, mix_nhat;
  *   dyn_update_kernel   AFTER it (it needs the normalisers the static kernel wrote to mix_L): the update terms in the
  *                       reference's order, prune, greedy 4-D Mahalanobis merge, the new dynamic map.
- * Dynamic maps are small (moving objects in the field of view: tens of components), so these kernels are one 128-thread
- * block per particle and not tuned further; the layout is plane-SoA like the static map: [particle][21][Dmax].
+ * Dynamic maps are small (moving objects in the field of view: tens of components), so these kernels are one 64-thread
+ * block per particle; the merge rounds of dyn_update_kernel run on one warp (DESIGN.md section 11 has the measurements).
+ * The layout is plane-SoA like the static map: [particle][21][Dmax].  Resampling: dyn_gather_kernel (local copies and the
+ * packing of what migrates to another rank).
  */
 #ifndef PHD_MIXED_CUH
 #define PHD_MIXED_CUH
